@@ -1,0 +1,267 @@
+"""ctypes front end of the CPU ORACLE (oracle/src/*.cpp -> oracle/liboccxc_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs. Nothing under occ_b200/ imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import glob
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liboccxc_oracle.so")
+REF_LIB_PATH = os.path.join(HERE, "_ref", "libocc_ref.so")
+
+FUNC_IDS = {"lda_x": 1, "lda_c_vwn": 7, "lda_c_vwn_rpa": 8, "lda_c_vwn_3": 30, "gga_x_pbe": 101, "gga_x_b88": 106,
+            "gga_c_pbe": 130, "gga_c_lyp": 131, "hyb_gga_xc_b3lyp": 402, "mgga_x_r2scan": 497, "mgga_c_r2scan": 498}
+
+# src/dft/dft_method.cpp:14-37 (same entries in share/methods/dft_methods.json)
+METHODS = {
+    "b3lyp": ["hyb_gga_xc_b3lyp"],
+    "pbe": ["gga_x_pbe", "gga_c_pbe"],
+    "blyp": ["gga_x_b88", "gga_c_lyp"],
+    "lda": ["lda_x", "lda_c_vwn_3"],
+    "svwn": ["lda_x", "lda_c_vwn_3"],
+    "svwn5": ["lda_x", "lda_c_vwn"],
+    "r2scan": ["mgga_x_r2scan", "mgga_c_r2scan"],
+}
+
+
+class BasisT(C.Structure):
+    _fields_ = [("nsh", C.c_int), ("pure", C.c_int), ("l", C.c_void_p), ("origin", C.c_void_p), ("nprim", C.c_void_p),
+                ("prim_off", C.c_void_p), ("exps", C.c_void_p), ("coefs", C.c_void_p), ("shell_atom", C.c_void_p)]
+
+
+class GridSettingsT(C.Structure):
+    _fields_ = [("max_angular_points", C.c_int), ("min_angular_points", C.c_int), ("radial_precision", C.c_double),
+                ("reduced_first_row_element_grid", C.c_int), ("treutler_alrichs_adjustment", C.c_int)]
+
+
+class LeafT(C.Structure):
+    _fields_ = [("offset", C.c_size_t), ("count", C.c_size_t), ("center", C.c_double * 3), ("radius", C.c_double)]
+
+
+class StatsT(C.Structure):
+    _fields_ = [("sum_n_nb2", C.c_double), ("sum_nb2", C.c_double), ("nleaves", C.c_size_t), ("nskipped", C.c_size_t),
+                ("nb_min", C.c_int), ("nb_max", C.c_int), ("t_colloc", C.c_double), ("t_density", C.c_double),
+                ("t_func", C.c_double), ("t_vxc", C.c_double), ("t_total", C.c_double)]
+
+
+LEAF_DTYPE = np.dtype([("offset", np.uint64), ("count", np.uint64), ("center", np.float64, 3), ("radius", np.float64)])
+
+_lib = None
+
+
+def build(force: bool = False):
+    """Compile the oracle (and oracle/_ref when the reference tree is present). Building the checker is not using it."""
+    if force or not os.path.exists(LIB_PATH) or any(
+            os.path.getmtime(p) > os.path.getmtime(LIB_PATH) for p in glob.glob(os.path.join(HERE, "src", "*"))):
+        subprocess.check_call(["make", "-C", HERE, "-s"])
+    if os.path.isdir("/root/reference/src/3rdparty/gau2grid") and not os.path.exists(REF_LIB_PATH):
+        subprocess.check_call(["make", "-C", HERE, "-s", "-j8", "ref"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        L.orc_common_fac.restype = C.c_double
+        L.orc_xc_exx.restype = C.c_double
+        L.orc_molecular_grid_create.restype = C.c_void_p
+        L.orc_grid_npts.restype = C.c_size_t
+        L.orc_grid_atom_npts.restype = C.c_size_t
+        L.orc_hierarchy.restype = C.c_size_t
+        L.orc_grid_npts.argtypes = [C.c_void_p]
+        L.orc_grid_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_grid_atom_npts.argtypes = [C.c_void_p, C.c_int]
+        L.orc_grid_atom_nradial.argtypes = [C.c_void_p, C.c_int]
+        L.orc_grid_destroy.argtypes = [C.c_void_p]
+        _lib = L
+        tables = np.load(os.path.join(os.path.dirname(HERE), "tests", "golden", "lebedev_tables.npz"))
+        for k in tables.files:
+            a = np.ascontiguousarray(tables[k])
+            L.orc_register_lebedev(C.c_int(a.shape[0]), a.ctypes.data_as(C.c_void_p))
+        try:
+            import scipy
+            cands = glob.glob(os.path.join(os.path.dirname(scipy.__file__), "..", "scipy.libs", "libscipy_openblas*.so"))
+            if cands:
+                L.orc_set_blas(cands[0].encode())
+        except Exception:
+            pass
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Basis:
+    """Keeps the numpy arrays alive behind an orc_basis_t."""
+
+    def __init__(self, arrays: dict):
+        self.a = {k: (np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v) for k, v in arrays.items()}
+        a = self.a
+        self.t = BasisT(a["nsh"], a["pure"], _p(a["l"]).value, _p(a["origin"]).value, _p(a["nprim"]).value,
+                        _p(a["prim_off"]).value, _p(a["exps"]).value, _p(a["coefs"]).value, _p(a["shell_atom"]).value)
+        self.nsh = a["nsh"]
+        self.pure = a["pure"]
+        self.nbf = int(sum(lib().orc_nbf_shell(int(l), int(a["pure"])) for l in a["l"]))
+
+    @property
+    def ref(self):
+        return C.byref(self.t)
+
+
+def incorporate_shell_norm(l, exps, coefs):
+    e = np.ascontiguousarray(exps, dtype=np.float64)
+    c = np.array(coefs, dtype=np.float64)
+    lib().orc_incorporate_shell_norm(C.c_int(l), C.c_int(len(e)), _p(e), _p(c))
+    return c
+
+
+def collocate_shell(l, pure, pts, coefs, exps, center, deriv):
+    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+    n = pts.shape[0]
+    nout = lib().orc_nbf_shell(C.c_int(l), C.c_int(pure))
+    out = [np.zeros((nout, n)) for _ in range(4 if deriv else 1)]
+    coefs = np.ascontiguousarray(coefs, dtype=np.float64)
+    exps = np.ascontiguousarray(exps, dtype=np.float64)
+    center = np.ascontiguousarray(center, dtype=np.float64)
+    lib().orc_collocate_shell(C.c_int(l), C.c_int(pure), C.c_size_t(n), _p(pts), C.c_int(len(exps)), _p(coefs), _p(exps),
+                              _p(center), C.c_int(deriv), _p(out[0]), _p(out[1]) if deriv else None,
+                              _p(out[2]) if deriv else None, _p(out[3]) if deriv else None)
+    return out
+
+
+def decay_cutoff(basis: Basis, threshold=1e-10):
+    ext = np.zeros(basis.nsh)
+    lib().orc_decay_cutoff(basis.ref, C.c_double(threshold), _p(ext))
+    return ext
+
+
+def default_grid_settings(**kw):
+    s = GridSettingsT(302, 110, 1e-12, 1, 1)
+    for k, v in kw.items():
+        setattr(s, k, v)
+    return s
+
+
+def molecular_grid(atomic_numbers, positions, basis: Basis, settings=None, nthreads=None):
+    Z = np.ascontiguousarray(atomic_numbers, dtype=np.int32)
+    pos = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
+    s = settings or default_grid_settings()
+    nthreads = nthreads or os.cpu_count() or 1
+    g = lib().orc_molecular_grid_create(C.c_int(len(Z)), _p(Z), _p(pos), basis.ref, C.byref(s), C.c_int(nthreads))
+    try:
+        n = lib().orc_grid_npts(g)
+        pts = np.zeros((n, 3))
+        w = np.zeros(n)
+        lib().orc_grid_copy(g, _p(pts), _p(w))
+        info = {"atom_npts": [lib().orc_grid_atom_npts(g, a) for a in range(len(Z))],
+                "atom_nradial": [lib().orc_grid_atom_nradial(g, a) for a in range(len(Z))]}
+    finally:
+        lib().orc_grid_destroy(g)
+    return pts, w, info
+
+
+def hierarchy(pts, w):
+    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    n = len(w)
+    spts = np.zeros_like(pts)
+    sw = np.zeros_like(w)
+    perm = np.zeros(n, dtype=np.uint64)
+    cap = n // 128 + 2
+    leaves = np.zeros(cap, dtype=LEAF_DTYPE)
+    nl = lib().orc_hierarchy(C.c_size_t(n), _p(pts), _p(w), _p(spts), _p(sw), _p(perm), _p(leaves), C.c_size_t(cap))
+    return spts, sw, perm, leaves[:nl].copy()
+
+
+def xc_eval(func, polarized, rho, sigma=None, tau=None):
+    fid = FUNC_IDS[func] if isinstance(func, str) else int(func)
+    fam = lib().orc_xc_family(C.c_int(fid))
+    s = 2 if polarized else 1
+    rho = np.ascontiguousarray(rho, dtype=np.float64)
+    n = rho.size // s
+    sigma = np.ascontiguousarray(sigma if sigma is not None else np.zeros(n * (3 if polarized else 1)), dtype=np.float64)
+    tau = np.ascontiguousarray(tau if tau is not None else np.zeros(n * s), dtype=np.float64)
+    exc = np.zeros(n)
+    vrho = np.zeros(n * s)
+    vsigma = np.zeros(n * (3 if polarized else 1))
+    vtau = np.zeros(n * s)
+    rc = lib().orc_xc_eval(C.c_int(fid), C.c_int(int(polarized)), C.c_size_t(n), _p(rho), _p(sigma), _p(tau), _p(exc),
+                           _p(vrho), _p(vsigma), _p(vtau))
+    if rc:
+        raise RuntimeError(f"functional with id = {fid} not found")
+    return {"exc": exc, "vrho": vrho.reshape(n, s), "vsigma": vsigma.reshape(n, -1), "vtau": vtau.reshape(n, s),
+            "family": fam}
+
+
+def method_deriv(func_names):
+    return max(lib().orc_xc_family(C.c_int(FUNC_IDS[f])) for f in func_names)
+
+
+def xc_build(basis: Basis, spts, sw, leaves, func_names, nspin, D2, density_threshold=1e-10,
+             screening_threshold=1e-10, nthreads=None, deriv=None):
+    """compute_K_dft restatement. D2: (nspin*nbf, nbf) column-major, already doubled. Returns dict."""
+    ids = np.array([FUNC_IDS[f] for f in func_names], dtype=np.int32)
+    if deriv is None:
+        deriv = method_deriv(func_names)
+    nbf = basis.nbf
+    D2 = np.asfortranarray(D2, dtype=np.float64)
+    assert D2.shape == (nspin * nbf, nbf), (D2.shape, nspin, nbf)
+    K = np.zeros((nspin * nbf, nbf), order="F")
+    exc, na, nb = C.c_double(0), C.c_double(0), C.c_double(0)
+    st = StatsT()
+    spts = np.ascontiguousarray(spts, dtype=np.float64)
+    sw = np.ascontiguousarray(sw, dtype=np.float64)
+    leaves = np.ascontiguousarray(leaves)
+    nthreads = nthreads or os.cpu_count() or 1
+    rc = lib().orc_xc_build(basis.ref, C.c_size_t(len(sw)), _p(spts), _p(sw), C.c_size_t(len(leaves)), _p(leaves),
+                            C.c_int(len(ids)), _p(ids), C.c_int(nspin), C.c_int(deriv), C.c_double(density_threshold),
+                            C.c_double(screening_threshold), _p(D2), _p(K), C.byref(exc), C.byref(na), C.byref(nb),
+                            C.c_int(nthreads), C.byref(st))
+    if rc:
+        raise RuntimeError("orc_xc_build failed")
+    stats = {f: getattr(st, f) for f, _ in StatsT._fields_}
+    return {"K": K, "exc": exc.value, "n_alpha": na.value, "n_beta": nb.value, "stats": stats}
+
+
+# ---- the real reference (gau2grid) for cross-checks ----
+_ref = None
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        if not os.path.exists(REF_LIB_PATH):
+            build()
+        if not os.path.exists(REF_LIB_PATH):
+            return None
+        _ref = C.CDLL(REF_LIB_PATH)
+    return _ref
+
+
+def ref_collocate_shell(l, pure, pts, coefs, exps, center, deriv):
+    """gg_collocation / gg_collocation_deriv1 from the compiled reference gau2grid."""
+    R = ref_lib()
+    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+    n = pts.shape[0]
+    nout = (2 * l + 1) if pure else (l + 1) * (l + 2) // 2
+    order = 300 if pure else 400  # GG_SPHERICAL_CCA / GG_CARTESIAN_CCA
+    out = [np.zeros((nout, n)) for _ in range(4 if deriv else 1)]
+    coefs = np.ascontiguousarray(coefs, dtype=np.float64)
+    exps = np.ascontiguousarray(exps, dtype=np.float64)
+    center = np.ascontiguousarray(center, dtype=np.float64)
+    args = [C.c_int(l), C.c_ulong(n), _p(pts), C.c_ulong(3), C.c_int(len(exps)), _p(coefs), _p(exps), _p(center),
+            C.c_int(order)]
+    if deriv:
+        R.gg_collocation_deriv1(*args, _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]))
+    else:
+        R.gg_collocation(*args, _p(out[0]))
+    return out

@@ -1,0 +1,419 @@
+// oracle/src/functionals.cpp — CPU ORACLE (test infrastructure): the exchange-correlation functionals
+// the reference obtains from libxc 6.2.2 (an un-vendored dependency, 3rdparty/CMakeLists.txt:215-234;
+// call sites src/dft/functional.cpp:29-63).  libxc's source is not available offline, so each
+// functional is restated from its publication in libxc's conventions:
+//   eps = energy per particle;  vrho = d(rho*eps)/d rho_s;  vsigma = d(rho*eps)/d sigma (sigma = |grad rho|^2,
+//   polarized order aa, ab, bb);  vtau = d(rho*eps)/d tau_s with tau = 1/2 sum |grad psi|^2.
+// Every functional is ONE templated energy density F(ra, rb, saa, sab, sbb, ta, tb); potentials come
+// from forward-mode AD (dual.h).  The unpolarized entry evaluates F(rho/2, rho/2, sigma/4, ...).
+//
+// Pinned by the reference's own tests: gga_x_pbe eps (tests/dft_tests.cpp:71-111); Slater+VWN3(=VWN5-P
+// at zeta=0), PBE x+c, B88+LYP, r2SCAN x+c energies through tests/isolated_xc_tests.cpp:71-294.
+// NOT pinned by any reference test ("parity unpinned"): VWN-RPA, the zeta != 0 interpolations of the
+// three VWN variants, every polarized branch, and all potentials (those are checked by finite
+// differences of F and by the polarized(zeta=0) == unpolarized identity in tests/test_oracle_functionals.py).
+#include "dual.h"
+#include "oracle.h"
+#include "oracle_internal.h"
+#include <cmath>
+
+namespace orc {
+namespace {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kDensThreshold = 1e-15; // below this total density every output is zero (libxc dens_threshold)
+constexpr double kSpinFloor = 1e-15;     // per-spin density floor in polarized mode (libxc floors at dens_threshold)
+constexpr double kSigmaFloor = 1e-40;    // keeps sqrt(sigma) differentiable at sigma = 0
+constexpr double kTauFloor = 1e-20;      // libxc tau_threshold
+
+template <class T> inline T sq(const T &x) { return x * x; }
+
+template <class T> struct Vars {
+  T ra, rb, saa, sab, sbb, ta, tb;
+};
+
+// ------------------------------------------------------------------------------------------------
+// LDA exchange (Dirac/Slater): e = -(3/4)(6/pi)^(1/3) sum_s rho_s^(4/3)
+template <class T> T F_lda_x(const Vars<T> &v) {
+  const double c = -0.75 * std::cbrt(6.0 / kPi);
+  return c * (v.ra * cbrt(v.ra) + v.rb * cbrt(v.rb));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Vosko, Wilk, Nusair, Can. J. Phys. 58, 1200 (1980). Index 0: paramagnetic, 1: ferromagnetic, 2: spin stiffness
+const double vwn_A[3] = {0.0310907, 0.01554535, -1.0 / (6.0 * kPi * kPi)};
+const double vwn5_b[3] = {3.72744, 7.06042, 1.13107};
+const double vwn5_c[3] = {12.9352, 18.0578, 13.0045};
+const double vwn5_x0[3] = {-0.10498, -0.32500, -0.0047584};
+const double rpa_b[3] = {13.0720, 20.1231, 1.06835};
+const double rpa_c[3] = {42.7198, 101.578, 11.4813};
+const double rpa_x0[3] = {-0.409286, -0.743294, -0.228344};
+
+template <class T> T vwn_aux(double A, double b, double c, double x0, const T &rs) {
+  const T x = sqrt(rs);
+  const double Q = std::sqrt(4.0 * c - b * b);
+  const T X = rs + b * x + c;
+  const double X0 = x0 * x0 + b * x0 + c;
+  const T at = atan(Q / (2.0 * x + b));
+  return A * (log(rs / X) + (2.0 * b / Q) * at -
+              (b * x0 / X0) * (log(sq(x - x0) / X) + (2.0 * (b + 2.0 * x0) / Q) * at));
+}
+
+template <class T> T f_zeta(const T &z) { // spin-polarisation function f(zeta)
+  const T p = 1.0 + z, m = 1.0 - z;
+  return (p * cbrt(p) + m * cbrt(m) - 2.0) / (std::pow(2.0, 4.0 / 3.0) - 2.0);
+}
+const double kFpp0 = 4.0 / (9.0 * (std::cbrt(2.0) - 1.0)); // f''(0) = 1.7099209341613657
+
+template <class T> void rs_zeta(const Vars<T> &v, T &rho, T &rs, T &zeta) {
+  rho = v.ra + v.rb;
+  rs = cbrt(3.0 / (4.0 * kPi * rho));
+  zeta = (v.ra - v.rb) / rho;
+}
+
+// variant: 0 = VWN5 (lda_c_vwn), 1 = VWN-RPA (lda_c_vwn_rpa), 2 = VWN3 (lda_c_vwn_3)
+template <class T> T eps_vwn(int variant, const T &rs, const T &z) {
+  const T fz = f_zeta(z);
+  const T z4 = sq(sq(z));
+  if (variant == 1) {
+    const T eP = vwn_aux(vwn_A[0], rpa_b[0], rpa_c[0], rpa_x0[0], rs);
+    const T eF = vwn_aux(vwn_A[1], rpa_b[1], rpa_c[1], rpa_x0[1], rs);
+    return eP * (1.0 - fz) + eF * fz;
+  }
+  const T eP = vwn_aux(vwn_A[0], vwn5_b[0], vwn5_c[0], vwn5_x0[0], rs);
+  const T eF = vwn_aux(vwn_A[1], vwn5_b[1], vwn5_c[1], vwn5_x0[1], rs);
+  const T dmc = eF - eP;
+  if (variant == 0) {
+    const T ac = vwn_aux(vwn_A[2], vwn5_b[2], vwn5_c[2], vwn5_x0[2], rs);
+    return eP + ac * fz * (1.0 - z4) / kFpp0 + dmc * fz * z4;
+  }
+  // VWN3: RPA spin stiffness scaled by the Monte-Carlo/RPA ratio of the para->ferro difference
+  const T ePr = vwn_aux(vwn_A[0], rpa_b[0], rpa_c[0], rpa_x0[0], rs);
+  const T eFr = vwn_aux(vwn_A[1], rpa_b[1], rpa_c[1], rpa_x0[1], rs);
+  const T acr = vwn_aux(vwn_A[2], rpa_b[2], rpa_c[2], rpa_x0[2], rs);
+  const T drpa = eFr - ePr;
+  return eP + (dmc / drpa) * acr * fz * (1.0 - z4) / kFpp0 + dmc * fz * z4;
+}
+template <class T, int VARIANT> T F_vwn(const Vars<T> &v) {
+  T rho, rs, z;
+  rs_zeta(v, rho, rs, z);
+  return rho * eps_vwn(VARIANT, rs, z);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Becke, Phys. Rev. A 38, 3098 (1988): beta = 0.0042, gamma = 6
+template <class T> T b88_spin(const T &r, const T &s) {
+  const double Cx = 0.375 * std::cbrt(3.0 / kPi) * std::pow(4.0, 2.0 / 3.0); // 0.9305257363491
+  const double beta = 0.0042, gamma = 6.0;
+  const T r43 = r * cbrt(r);
+  const T x = sqrt(s) / r43;
+  return -r43 * (Cx + beta * sq(x) / (1.0 + gamma * beta * x * asinh(x)));
+}
+template <class T> T F_b88(const Vars<T> &v) { return b88_spin(v.ra, v.saa) + b88_spin(v.rb, v.sbb); }
+
+// ------------------------------------------------------------------------------------------------
+// Lee, Yang, Parr, Phys. Rev. B 37, 785 (1988) in the gradient-only form of Miehlich, Savin, Stoll,
+// Preuss, Chem. Phys. Lett. 157, 200 (1989).
+template <class T> T F_lyp(const Vars<T> &v) {
+  const double a = 0.04918, b = 0.132, c = 0.2533, d = 0.349;
+  const double CF = 0.3 * std::pow(3.0 * kPi * kPi, 2.0 / 3.0);
+  const T rho = v.ra + v.rb;
+  const T rm13 = 1.0 / cbrt(rho);
+  const T den = 1.0 + d * rm13;
+  const T omega = exp(-c * rm13) / den * pow(rho, -11.0 / 3.0);
+  const T delta = c * rm13 + d * rm13 / den;
+  const T stot = v.saa + 2.0 * v.sab + v.sbb;
+  const T ra83 = sq(v.ra) * cbrt(sq(v.ra)), rb83 = sq(v.rb) * cbrt(sq(v.rb));
+  const T t1 = -4.0 * a / den * v.ra * v.rb / rho;
+  const T brack = std::pow(2.0, 11.0 / 3.0) * CF * (ra83 + rb83) + (47.0 / 18.0 - 7.0 * delta / 18.0) * stot -
+                  (2.5 - delta / 18.0) * (v.saa + v.sbb) -
+                  (delta - 11.0) / 9.0 * (v.ra / rho * v.saa + v.rb / rho * v.sbb);
+  const T t2 = -a * b * omega *
+               (v.ra * v.rb * brack - (2.0 / 3.0) * sq(rho) * stot + ((2.0 / 3.0) * sq(rho) - sq(v.ra)) * v.sbb +
+                ((2.0 / 3.0) * sq(rho) - sq(v.rb)) * v.saa);
+  return t1 + t2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Perdew, Burke, Ernzerhof, Phys. Rev. Lett. 77, 3865 (1996)
+template <class T> T ex_unif(const T &n) { return -0.75 * std::cbrt(3.0 / kPi) * n * cbrt(n); }
+template <class T> T s2_of(const T &n, const T &sigma) { // reduced gradient squared
+  const double c = 4.0 * std::pow(3.0 * kPi * kPi, 2.0 / 3.0);
+  return sigma / (c * sq(n) * cbrt(sq(n)));
+}
+template <class T> T pbe_x_n(const T &n, const T &sigma) {
+  const double kappa = 0.804, mu = 0.2195149727645171;
+  const T s2 = s2_of(n, sigma);
+  return ex_unif(n) * (1.0 + kappa - kappa / (1.0 + mu * s2 / kappa));
+}
+template <class T> T F_pbe_x(const Vars<T> &v) { // spin scaling E[ra,rb] = (E[2ra] + E[2rb])/2
+  return 0.5 * (pbe_x_n(2.0 * v.ra, 4.0 * v.saa) + pbe_x_n(2.0 * v.rb, 4.0 * v.sbb));
+}
+
+// Perdew & Wang, Phys. Rev. B 45, 13244 (1992), "modified" constants (more digits) as used by PBE/SCAN codes
+struct PwSet {
+  double A, a1, b1, b2, b3, b4;
+};
+const PwSet pw_mod[3] = {{0.0310907, 0.21370, 7.5957, 3.5876, 1.6382, 0.49294},
+                         {0.01554535, 0.20548, 14.1189, 6.1977, 3.3662, 0.62517},
+                         {0.0168869, 0.11125, 10.357, 3.6231, 0.88026, 0.49671}};
+template <class T> T pw_G(const PwSet &p, const T &rs) {
+  const T srs = sqrt(rs);
+  const T q1 = 2.0 * p.A * (p.b1 * srs + p.b2 * rs + p.b3 * rs * srs + p.b4 * sq(rs));
+  return -2.0 * p.A * (1.0 + p.a1 * rs) * log(1.0 + 1.0 / q1);
+}
+template <class T> T pw_dG(const PwSet &p, const T &rs) { // d pw_G / d rs
+  const T srs = sqrt(rs);
+  const T q1 = 2.0 * p.A * (p.b1 * srs + p.b2 * rs + p.b3 * rs * srs + p.b4 * sq(rs));
+  const T dq1 = p.A * (p.b1 / srs + 2.0 * p.b2 + 3.0 * p.b3 * srs + 4.0 * p.b4 * rs);
+  return -2.0 * p.A * p.a1 * log(1.0 + 1.0 / q1) + 2.0 * p.A * (1.0 + p.a1 * rs) * dq1 / (sq(q1) + q1);
+}
+template <class T> T eps_pw(const T &rs, const T &z) {
+  const T e0 = pw_G(pw_mod[0], rs), e1 = pw_G(pw_mod[1], rs), mac = pw_G(pw_mod[2], rs); // mac = -alpha_c
+  const T fz = f_zeta(z), z4 = sq(sq(z));
+  return e0 - mac * fz * (1.0 - z4) / kFpp0 + (e1 - e0) * fz * z4;
+}
+template <class T> T deps_pw_drs(const T &rs, const T &z) {
+  const T e0 = pw_dG(pw_mod[0], rs), e1 = pw_dG(pw_mod[1], rs), mac = pw_dG(pw_mod[2], rs);
+  const T fz = f_zeta(z), z4 = sq(sq(z));
+  return e0 - mac * fz * (1.0 - z4) / kFpp0 + (e1 - e0) * fz * z4;
+}
+template <class T> T phi_zeta(const T &z) { return 0.5 * (cbrt(sq(1.0 + z)) + cbrt(sq(1.0 - z))); }
+
+template <class T> T F_pbe_c(const Vars<T> &v) {
+  const double beta = 0.06672455060314922, gamma = (1.0 - std::log(2.0)) / (kPi * kPi);
+  T rho, rs, z;
+  rs_zeta(v, rho, rs, z);
+  const T ec = eps_pw(rs, z);
+  const T phi = phi_zeta(z);
+  const T phi3 = phi * sq(phi);
+  const T stot = v.saa + 2.0 * v.sab + v.sbb;
+  // t^2 = sigma / (4 phi^2 ks^2 rho^2), ks^2 = 4 kF / pi, kF = (3 pi^2 rho)^(1/3)
+  const T kF = cbrt(3.0 * kPi * kPi * rho);
+  const T t2 = stot * kPi / (16.0 * sq(phi) * kF * sq(rho));
+  const T A = (beta / gamma) / expm1(-ec / (gamma * phi3));
+  const T At2 = A * t2;
+  const T H = gamma * phi3 * log(1.0 + (beta / gamma) * t2 * (1.0 + At2) / (1.0 + At2 + sq(At2)));
+  return rho * (ec + H);
+}
+
+// ------------------------------------------------------------------------------------------------
+// r2SCAN: Furness, Kaplan, Ning, Perdew, Sun, J. Phys. Chem. Lett. 11, 8208 (2020) (+ erratum)
+const double r2_eta = 0.001, r2_dp2 = 0.361;
+const double r2_cx[8] = {1.0,           -0.667,         -0.4445555,     -0.663086601049,
+                         1.451297044490, -0.887998041597, 0.234528941479, -0.023185843322};
+const double r2_cc[8] = {1.0,           -0.64,          -0.4352,        -1.535685604549,
+                         3.061560252175, -1.915710236206, 0.516884468372, -0.051848879792};
+
+template <class T> T r2_switch(const T &alpha, const double *poly, double c1, double c2, double dd) {
+  if (alpha < 0.0) return exp(-c1 * alpha / (1.0 - alpha));
+  if (alpha <= 2.5) {
+    T r = poly[7];
+    for (int i = 6; i >= 0; --i) r = r * alpha + poly[i];
+    return r;
+  }
+  return -dd * exp(c2 / (1.0 - alpha));
+}
+
+template <class T> T r2scan_x_n(const T &n, const T &sigma_in, const T &tau) {
+  const double k0 = 0.174, k1 = 0.065, mu = 10.0 / 81.0, a1 = 4.9479;
+  const double c1x = 0.667, c2x = 0.8, dx = 1.24;
+  double sum_icx = 0.0;
+  for (int i = 1; i < 8; ++i) sum_icx += i * r2_cx[i];
+  const double C2 = sum_icx * k0; // = -sum i c_xi (1 - h0x) = -0.162742
+  const double Ceta = 20.0 / 27.0 + r2_eta * 5.0 / 3.0;
+  // Fermi-hole-curvature bound sigma <= 8 n tau (libxc XC_FLAGS_ENFORCE_FHC)
+  T sigma = sigma_in;
+  if (value(sigma) > 8.0 * value(n) * value(tau)) sigma = 8.0 * n * tau;
+  const T p = s2_of(n, sigma);
+  const T tauW = sigma / (8.0 * n);
+  const T tauU = 0.3 * std::pow(3.0 * kPi * kPi, 2.0 / 3.0) * n * cbrt(sq(n));
+  const T alpha = (tau - tauW) / (tauU + r2_eta * tauW);
+  const T x = (Ceta * C2 * exp(-sq(p) / std::pow(r2_dp2, 4)) + mu) * p;
+  const T h1 = 1.0 + k1 - k1 / (1.0 + x / k1);
+  const double h0 = 1.0 + k0;
+  const T fx = r2_switch(alpha, r2_cx, c1x, c2x, dx);
+  const T gx = 1.0 - exp(-a1 / sqrt(sqrt(p)));
+  return ex_unif(n) * (h1 + fx * (h0 - h1)) * gx;
+}
+template <class T> T F_r2scan_x(const Vars<T> &v) {
+  return 0.5 * (r2scan_x_n(2.0 * v.ra, 4.0 * v.saa, 2.0 * v.ta) + r2scan_x_n(2.0 * v.rb, 4.0 * v.sbb, 2.0 * v.tb));
+}
+
+template <class T> T F_r2scan_c(const Vars<T> &v) {
+  const double b1c = 0.0285764, b2c = 0.0889, b3c = 0.125541, chi_inf = 0.128026;
+  const double gamma = (1.0 - std::log(2.0)) / (kPi * kPi);
+  const double c1c = 0.64, c2c = 1.5, dc = 0.7;
+  double dfc2 = 0.0;
+  for (int i = 1; i < 8; ++i) dfc2 += i * r2_cc[i];
+  T rho, rs, z;
+  rs_zeta(v, rho, rs, z);
+  T stot = v.saa + 2.0 * v.sab + v.sbb;
+  const T tau = v.ta + v.tb;
+  if (value(stot) > 8.0 * value(rho) * value(tau)) stot = 8.0 * rho * tau;
+  const T p = s2_of(rho, stot);
+  const T zp = 1.0 + z, zm = 1.0 - z;
+  const T ds = 0.5 * (zp * cbrt(sq(zp)) + zm * cbrt(sq(zm)));   // ((1+z)^(5/3) + (1-z)^(5/3))/2
+  const T dxz = 0.5 * (zp * cbrt(zp) + zm * cbrt(zm));           // ((1+z)^(4/3) + (1-z)^(4/3))/2
+  const T phi = phi_zeta(z);
+  const T phi3 = phi * sq(phi);
+  // iso-orbital indicator of the total density
+  const T tauW = stot / (8.0 * rho);
+  const T tauU = 0.3 * std::pow(3.0 * kPi * kPi, 2.0 / 3.0) * rho * cbrt(sq(rho)) * ds;
+  const T alpha = (tau - tauW) / (tauU + r2_eta * tauW);
+  const T fc = r2_switch(alpha, r2_cc, c1c, c2c, dc);
+
+  // alpha = 0 limit
+  const T srs = sqrt(rs);
+  const T den0 = 1.0 + b2c * srs + b3c * rs;
+  const T e_lda0 = -b1c / den0;
+  const T de_lda0 = b1c * (0.5 * b2c / srs + b3c) / sq(den0);
+  const T z2 = sq(z);
+  const T z12 = sq(sq(z2)) * sq(z2);
+  const T gc = (1.0 - 2.3631 * (dxz - 1.0)) * (1.0 - z12);
+  const T w0 = expm1(-e_lda0 / b1c);
+  const T ginf = 1.0 / sqrt(sqrt(1.0 + 4.0 * chi_inf * p));
+  const T H0 = b1c * log(1.0 + w0 * (1.0 - ginf));
+  const T eps0 = (e_lda0 + H0) * gc;
+
+  // alpha = 1 limit
+  const T e_lsda1 = eps_pw(rs, z);
+  const T de_lsda1 = deps_pw_drs(rs, z);
+  const T beta = 0.066725 * (1.0 + 0.1 * rs) / (1.0 + 0.1778 * rs);
+  const T t2 = std::pow(3.0 * kPi * kPi / 16.0, 2.0 / 3.0) * p / (sq(phi) * rs);
+  const T w1 = expm1(-e_lsda1 / (gamma * phi3));
+  const T y = beta * t2 / (gamma * w1);
+  const T e_lsda0 = e_lda0 * gc;
+  const T de_lsda0 = de_lda0 * gc;
+  const T dy = dfc2 / (27.0 * gamma * ds * phi3 * w1) *
+               (20.0 * rs * (de_lsda0 - de_lsda1) - 45.0 * r2_eta * (e_lsda0 - e_lsda1)) * p *
+               exp(-sq(p) / std::pow(r2_dp2, 4));
+  const T g1 = 1.0 / sqrt(sqrt(1.0 + 4.0 * (y - dy)));
+  const T H1 = gamma * phi3 * log(1.0 + w1 * (1.0 - g1));
+  const T eps1 = e_lsda1 + H1;
+
+  return rho * (eps1 + fc * (eps0 - eps1));
+}
+
+// ------------------------------------------------------------------------------------------------
+template <class T> T F_b3lyp(const Vars<T> &v) { // libxc hyb_gga_xc_b3lyp: a0 = 0.20, ax = 0.72, ac = 0.81
+  return 0.08 * F_lda_x(v) + 0.72 * F_b88(v) + 0.19 * F_vwn<T, 1>(v) + 0.81 * F_lyp(v);
+}
+
+template <class T> bool F_dispatch(int id, const Vars<T> &v, T &out) {
+  switch (id) {
+  case ORC_LDA_X: out = F_lda_x(v); return true;
+  case ORC_LDA_C_VWN: out = F_vwn<T, 0>(v); return true;
+  case ORC_LDA_C_VWN_RPA: out = F_vwn<T, 1>(v); return true;
+  case ORC_LDA_C_VWN_3: out = F_vwn<T, 2>(v); return true;
+  case ORC_GGA_X_B88: out = F_b88(v); return true;
+  case ORC_GGA_C_LYP: out = F_lyp(v); return true;
+  case ORC_GGA_X_PBE: out = F_pbe_x(v); return true;
+  case ORC_GGA_C_PBE: out = F_pbe_c(v); return true;
+  case ORC_HYB_GGA_XC_B3LYP: out = F_b3lyp(v); return true;
+  case ORC_MGGA_X_R2SCAN: out = F_r2scan_x(v); return true;
+  case ORC_MGGA_C_R2SCAN: out = F_r2scan_c(v); return true;
+  default: return false;
+  }
+}
+
+} // namespace
+
+int xc_eval_add(int id, int polarized, size_t n, const double *rho, const double *sigma, const double *tau,
+                double *exc, double *vrho, double *vsigma, double *vtau) {
+  const int fam = orc_xc_family(id);
+  if (fam < 0) return 1;
+  for (size_t i = 0; i < n; ++i) {
+    if (!polarized) {
+      const double r = rho[i];
+      if (!(r > kDensThreshold)) continue;
+      using D = Dual<3>;
+      const D R = D::var(r, 0);
+      const D S = D::var(fam >= 1 ? std::max(sigma[i], kSigmaFloor) : kSigmaFloor, 1);
+      const D Tt = D::var(fam >= 2 ? std::max(tau[i], kTauFloor) : kTauFloor, 2);
+      Vars<D> v{0.5 * R, 0.5 * R, 0.25 * S, 0.25 * S, 0.25 * S, 0.5 * Tt, 0.5 * Tt};
+      D F;
+      F_dispatch(id, v, F);
+      exc[i] += F.v / r;
+      vrho[i] += F.d[0];
+      if (fam >= 1) vsigma[i] += F.d[1];
+      if (fam >= 2) vtau[i] += F.d[2];
+    } else {
+      const double ra0 = rho[2 * i], rb0 = rho[2 * i + 1];
+      if (!(ra0 + rb0 > kDensThreshold)) continue;
+      using D = Dual<7>;
+      const double ra = std::max(ra0, kSpinFloor), rb = std::max(rb0, kSpinFloor);
+      double saa = kSigmaFloor, sab = 0.0, sbb = kSigmaFloor, ta = kTauFloor, tb = kTauFloor;
+      if (fam >= 1) {
+        saa = std::max(sigma[3 * i], kSigmaFloor);
+        sbb = std::max(sigma[3 * i + 2], kSigmaFloor);
+        sab = sigma[3 * i + 1];
+        const double lim = 0.5 * (saa + sbb); // libxc: |sigma_ab| <= (sigma_aa + sigma_bb)/2
+        sab = std::min(std::max(sab, -lim), lim);
+      }
+      if (fam >= 2) {
+        ta = std::max(tau[2 * i], kTauFloor);
+        tb = std::max(tau[2 * i + 1], kTauFloor);
+      }
+      Vars<D> v{D::var(ra, 0), D::var(rb, 1), D::var(saa, 2), D::var(sab, 3), D::var(sbb, 4), D::var(ta, 5), D::var(tb, 6)};
+      D F;
+      F_dispatch(id, v, F);
+      exc[i] += F.v / (ra + rb);
+      vrho[2 * i] += F.d[0];
+      vrho[2 * i + 1] += F.d[1];
+      if (fam >= 1) {
+        vsigma[3 * i] += F.d[2];
+        vsigma[3 * i + 1] += F.d[3];
+        vsigma[3 * i + 2] += F.d[4];
+      }
+      if (fam >= 2) {
+        vtau[2 * i] += F.d[5];
+        vtau[2 * i + 1] += F.d[6];
+      }
+    }
+  }
+  return 0;
+}
+
+} // namespace orc
+
+extern "C" {
+
+int orc_xc_family(int id) {
+  switch (id) {
+  case ORC_LDA_X:
+  case ORC_LDA_C_VWN:
+  case ORC_LDA_C_VWN_RPA:
+  case ORC_LDA_C_VWN_3:
+    return 0;
+  case ORC_GGA_X_B88:
+  case ORC_GGA_C_LYP:
+  case ORC_GGA_X_PBE:
+  case ORC_GGA_C_PBE:
+  case ORC_HYB_GGA_XC_B3LYP:
+    return 1;
+  case ORC_MGGA_X_R2SCAN:
+  case ORC_MGGA_C_R2SCAN:
+    return 2;
+  default:
+    return -1;
+  }
+}
+
+double orc_xc_exx(int id) { return id == ORC_HYB_GGA_XC_B3LYP ? 0.20 : 0.0; }
+
+int orc_xc_eval(int id, int polarized, size_t n, const double *rho, const double *sigma, const double *tau,
+                double *exc, double *vrho, double *vsigma, double *vtau) {
+  const int fam = orc_xc_family(id);
+  if (fam < 0) return 1;
+  const int s = polarized ? 2 : 1;
+  for (size_t i = 0; i < n; ++i) exc[i] = 0.0;
+  for (size_t i = 0; i < n * s; ++i) vrho[i] = 0.0;
+  if (fam >= 1 && vsigma)
+    for (size_t i = 0; i < n * (polarized ? 3 : 1); ++i) vsigma[i] = 0.0;
+  if (fam >= 2 && vtau)
+    for (size_t i = 0; i < n * s; ++i) vtau[i] = 0.0;
+  return orc::xc_eval_add(id, polarized, n, rho, sigma, tau, exc, vrho, vsigma, vtau);
+}
+
+} // extern "C"
