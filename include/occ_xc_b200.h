@@ -1,0 +1,143 @@
+/*
+ * occ_xc_b200.h — C ABI of the B200-native (sm_100a) DFT exchange-correlation build.
+ *
+ * Drop-in boundary for ONE path of peterspackman/occ (v0.9.3):
+ *     Mat occ::dft::DFT::compute_K_dft<derivative_order, spinorbital_kind>(mo, Schwarz)
+ *     /root/reference/include/occ/dft/dft.h:190-388
+ * i.e. the per-SCF-iteration Vxc / Exc / electron-count build over the Becke/Lebedev molecular grid.
+ * The reference has no FFI for this path (it is a C++ member template); these entry points are what a
+ * cgo/ctypes/C++ shim replacing the body of that member (dft.h:216-382) binds.  Plain pointers and
+ * sizes only, no C++/torch types.  Every function returns 0 on success, nonzero on failure with a
+ * thread-local message in occ_xc_last_error() (the reference throws std::runtime_error:
+ * dft.h:409,422,427; functional.cpp:32,61 — the C++ adapter in adapter/ rethrows).
+ *
+ * There is NO CPU fallback: create() fails when no CUDA device is usable.
+ */
+#ifndef OCC_XC_B200_H
+#define OCC_XC_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCC_XC_B200_ABI_VERSION 1
+
+/* occ::gto::AOBasis as plain arrays (include/occ/gto/shell.h:18-191): one entry per Shell in
+ * AOBasis::shells() order; coefficients AFTER Shell::incorporate_shell_norm (src/gto/shell.cpp:180-186);
+ * basis-function order within a shell is the reference's (gau2grid CCA Cartesian / spherical). */
+typedef struct {
+  int nsh;
+  int pure;              /* AOBasis::kind(): 0 Cartesian (CLI default, io/occ_input.h:104), 1 spherical */
+  const int *l;          /* [nsh] Shell::l */
+  const double *origin;  /* [3*nsh] Shell::origin, Bohr */
+  const int *nprim;      /* [nsh] Shell::num_primitives() */
+  const int *prim_off;   /* [nsh] offset of the shell's primitives in exps/coefs */
+  const double *exps;    /* Shell::exponents */
+  const double *coefs;   /* Shell::contraction_coefficients (column 0), normalised */
+  const int *shell_atom; /* [nsh] AOBasis::shell_to_atom(); may be NULL (only used for diagnostics) */
+} occ_xc_basis_t;
+
+/* occ::numint::GridBatchLeaf + GridBoundingSphere (include/occ/numint/spatial_grid_hierarchy.h:8-30) */
+typedef struct {
+  size_t offset, count;
+  double center[3];
+  double radius;
+} occ_xc_leaf_t;
+
+/* libxc ids the reference's enum carries (include/occ/dft/functional.h:22-383) that this library implements */
+enum {
+  OCC_XC_LDA_X = 1,
+  OCC_XC_LDA_C_VWN = 7,
+  OCC_XC_LDA_C_VWN_RPA = 8,
+  OCC_XC_LDA_C_VWN_3 = 30,
+  OCC_XC_GGA_X_PBE = 101,
+  OCC_XC_GGA_X_B88 = 106,
+  OCC_XC_GGA_C_PBE = 130,
+  OCC_XC_GGA_C_LYP = 131,
+  OCC_XC_HYB_GGA_XC_B3LYP = 402,
+  OCC_XC_MGGA_X_R2SCAN = 497,
+  OCC_XC_MGGA_C_R2SCAN = 498
+};
+
+typedef struct {
+  int device;            /* CUDA device ordinal; -1 = current device */
+  int rank, world_size;  /* grid-leaf shard of this handle: leaves are split by predicted cost over world_size
+                            handles (one per GPU / process); every handle returns a PARTIAL K, Exc, N that the
+                            caller sums (NCCL all-reduce).  world_size <= 1: whole grid. */
+  size_t batch_bytes;    /* AO-value workspace per batch of leaves (0 = default 256 MiB) */
+  int reserved[8];
+} occ_xc_options_t;
+
+typedef struct occ_xc_handle occ_xc_handle;
+
+/* Once per geometry/method (what DFT::DFT + set_integration_grid + set_method establish: src/dft/dft.cpp:19-117).
+ *   pts_xyz       3 x npts, xyz interleaved (Mat3N column-major), in SpatialGridHierarchy::sorted_points() order
+ *   weights       npts, sorted_weights()
+ *   leaves        SpatialGridHierarchy::leaves(); every point must belong to exactly one leaf
+ *   shell_extents nsh values of gto::evaluate_decay_cutoff(basis, screening_threshold) (src/gto/gto.cpp:18-67),
+ *                 or NULL: computed here by the same probe rule
+ *   func_ids      DensityFunctional::id() of m_method.functionals (nspin == 1) / functionals_polarized (nspin == 2)
+ *   nspin         1 Restricted, 2 Unrestricted
+ *   density_threshold / screening_threshold   DFT::m_density_threshold / m_xc_screening_threshold (1e-10 both);
+ *                 screening_threshold <= 0 keeps every shell in every leaf (OCC_XC_NO_SCREEN analogue)
+ * Everything is copied; no pointer is retained. */
+int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xyz, const double *weights,
+                  size_t nleaves, const occ_xc_leaf_t *leaves, const double *shell_extents, int nfunc,
+                  const int *func_ids, int nspin, double density_threshold, double screening_threshold,
+                  const occ_xc_options_t *options, occ_xc_handle **out);
+
+/* One compute_K_dft call with HOST buffers (borrowed for the duration of the call).
+ *   D2  (nspin*nbf) x nbf column-major, ld = nspin*nbf, already doubled (dft.h:205: D2 = 2*mo.D)
+ *   K   same shape, overwritten with the Vxc matrix (alpha block rows [0,nbf), beta rows [nbf,2nbf))
+ *   exc, n_alpha, n_beta   m_exc_dft and the two total densities (dft.h:375-385)
+ * Synchronous: returns when K is on the host. */
+int occ_xc_build(occ_xc_handle *h, const double *D2, double *K, double *exc, double *n_alpha, double *n_beta);
+
+/* Same with DEVICE buffers on `cuda_stream` (a cudaStream_t; NULL = the handle's own stream); asynchronous.
+ * scalars_dev receives {exc, n_alpha, n_beta}.  D2_dev / K_dev as above but resident in HBM. */
+int occ_xc_build_device(occ_xc_handle *h, const double *D2_dev, double *K_dev, double *scalars_dev,
+                        void *cuda_stream);
+
+/* Geometry-only facts of the handle (this rank's shard) */
+typedef struct {
+  int nbf, nspin, deriv, nsh;
+  size_t npts, nleaves, ntiles, nbatches;
+  double sum_n_nb2;          /* sum over leaves of n * nb^2 — the algorithmic-flop figure */
+  double flops_per_build;    /* g * nspin * sum_n_nb2, g = 4 (LDA/GGA) or 16 (meta-GGA) */
+  int nb_min, nb_max;
+  size_t workspace_bytes;    /* device memory held by the handle */
+  size_t launches_per_build; /* kernel launches one build issues */
+} occ_xc_info_t;
+int occ_xc_get_info(const occ_xc_handle *h, occ_xc_info_t *info);
+
+/* Per-phase device times (ms, CUDA events on the build stream) of the LAST build when profiling is on.
+ * phases: 0 prepare-D, 1 collocation, 2 density contraction, 3 functional, 4 Vxc contraction, 5 finalise */
+#define OCC_XC_NPHASES 6
+int occ_xc_set_profiling(occ_xc_handle *h, int on);
+int occ_xc_get_phase_ms(occ_xc_handle *h, double *ms /* [OCC_XC_NPHASES] */);
+
+/* Pieces of the path exposed for parity tests and for callers that want them on their own. */
+/* gto::evaluate_decay_cutoff (src/gto/gto.cpp:18-67) */
+int occ_xc_decay_cutoff(const occ_xc_basis_t *basis, double threshold, double *extents);
+/* DensityFunctional::evaluate on libxc-layout arrays (src/dft/functional.cpp:18-65): n points on the GPU.
+ * rho[n*s], sigma[n*(1|3)], tau[n*s] -> exc[n], vrho[n*s], vsigma[n*(1|3)], vtau[n*s]; HOST buffers. */
+int occ_xc_eval_functional(int func_id, int polarized, size_t n, const double *rho, const double *sigma,
+                           const double *tau, double *exc, double *vrho, double *vsigma, double *vtau);
+/* gto::evaluate_basis_subset for ONE leaf of the handle (src/gto/gto.cpp:212-287): phi (and grad) as
+ * (count x nb_local) column-major HOST arrays; returns nb_local through *nb. deriv 0 or 1. */
+int occ_xc_leaf_collocation(occ_xc_handle *h, size_t leaf, int deriv, int *nb, double *phi, double *phi_x,
+                            double *phi_y, double *phi_z, size_t capacity_doubles);
+
+int occ_xc_family(int func_id);          /* 0 LDA, 1 GGA, 2 meta-GGA, -1 unknown (DensityFunctional::family) */
+double occ_xc_exact_exchange(int func_id); /* DensityFunctional::exact_exchange_factor (functional.h:557-579) */
+
+void occ_xc_destroy(occ_xc_handle *h);
+const char *occ_xc_last_error(void);
+int occ_xc_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCC_XC_B200_H */

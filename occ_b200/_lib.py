@@ -1,0 +1,92 @@
+"""ctypes binding of the C ABI (include/occ_xc_b200.h) exported by occ_b200/libocc_xc_b200.so.
+
+The product path has no CPU fallback: if the CUDA library is missing or cannot be loaded this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libocc_xc_b200.so")
+
+# every symbol include/occ_xc_b200.h declares
+SYMBOLS = ["occ_xc_create", "occ_xc_build", "occ_xc_build_device", "occ_xc_get_info", "occ_xc_set_profiling",
+           "occ_xc_get_phase_ms", "occ_xc_decay_cutoff", "occ_xc_eval_functional", "occ_xc_leaf_collocation",
+           "occ_xc_family", "occ_xc_exact_exchange", "occ_xc_destroy", "occ_xc_last_error", "occ_xc_abi_version"
+           ]
+
+
+class BasisT(C.Structure):
+    _fields_ = [("nsh", C.c_int), ("pure", C.c_int), ("l", C.c_void_p), ("origin", C.c_void_p), ("nprim", C.c_void_p),
+                ("prim_off", C.c_void_p), ("exps", C.c_void_p), ("coefs", C.c_void_p), ("shell_atom", C.c_void_p)]
+
+
+class LeafT(C.Structure):
+    _fields_ = [("offset", C.c_size_t), ("count", C.c_size_t), ("center", C.c_double * 3), ("radius", C.c_double)]
+
+
+class OptionsT(C.Structure):
+    _fields_ = [("device", C.c_int), ("rank", C.c_int), ("world_size", C.c_int), ("batch_bytes", C.c_size_t),
+                ("reserved", C.c_int * 8)]
+
+
+class InfoT(C.Structure):
+    _fields_ = [("nbf", C.c_int), ("nspin", C.c_int), ("deriv", C.c_int), ("nsh", C.c_int), ("npts", C.c_size_t),
+                ("nleaves", C.c_size_t), ("ntiles", C.c_size_t), ("nbatches", C.c_size_t), ("sum_n_nb2", C.c_double),
+                ("flops_per_build", C.c_double), ("nb_min", C.c_int), ("nb_max", C.c_int),
+                ("workspace_bytes", C.c_size_t), ("launches_per_build", C.c_size_t)]
+
+
+LEAF_DTYPE = np.dtype([("offset", np.uint64), ("count", np.uint64), ("center", np.float64, 3), ("radius", np.float64)])
+NPHASES = 6
+PHASE_NAMES = ["prepare_D", "collocation", "density", "functional", "vxc", "finalise"]
+
+_lib = None
+
+
+def lib():
+    """Load libocc_xc_b200.so; raise loudly if it is not built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                               "g.build()'` (make -C occ_b200/csrc). occ_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.occ_xc_last_error.restype = C.c_char_p
+        L.occ_xc_exact_exchange.restype = C.c_double
+        L.occ_xc_destroy.restype = None
+        L.occ_xc_destroy.argtypes = [C.c_void_p]
+        L.occ_xc_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.occ_xc_build_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.occ_xc_get_info.argtypes = [C.c_void_p, C.c_void_p]
+        L.occ_xc_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.occ_xc_get_phase_ms.argtypes = [C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise RuntimeError(lib().occ_xc_last_error().decode())
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class BasisArrays:
+    """Keeps the numpy arrays behind an occ_xc_basis_t alive."""
+
+    def __init__(self, arrays: dict):
+        self.a = {k: (np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v) for k, v in arrays.items()}
+        a = self.a
+        self.t = BasisT(a["nsh"], a["pure"], ptr(a["l"]).value, ptr(a["origin"]).value, ptr(a["nprim"]).value,
+                        ptr(a["prim_off"]).value, ptr(a["exps"]).value, ptr(a["coefs"]).value,
+                        ptr(a["shell_atom"]).value)
+
+    @property
+    def ref(self):
+        return C.byref(self.t)

@@ -1,0 +1,172 @@
+// k_collocate.cu — phase 1 of the XC build: AO values and gradients of the significant shells of each grid
+// tile (reference: gto::evaluate_basis_subset, src/gto/gto.cpp:212-287, whose arithmetic is gau2grid's
+// gg_collocation / gg_collocation_deriv1, src/3rdparty/gau2grid/gau2grid_phi.c, gau2grid_deriv1.c, followed
+// by the common_fac scaling of gto.cpp:7-16).
+//
+// B200 mapping: one thread per grid point (128-thread CTAs, one CTA per (tile, run of 16 shells)), so the
+// shell parameters are warp-uniform broadcast loads and every store of a basis-function column is a fully
+// coalesced 1 KiB line burst into the batch workspace (SoA points, column-major 128 x nbp slabs).
+// Radial part: S0 = sum_p c_p exp(-a_p r^2), S1 = sum_p (-2 a_p) c_p exp(-a_p r^2); angular part: Cartesian
+// monomials in CCA order (lx descending, then ly), product rule for the gradient; optional real-solid-harmonic
+// transform (CCA order m = -l..l) from a constant-memory table.
+#include "xc_internal.h"
+#include <cuda_runtime.h>
+
+namespace xcb {
+
+__constant__ C2STable c_c2s;
+
+void upload_c2s_table(const C2STable &t) { cudaMemcpyToSymbol(c_c2s, &t, sizeof(C2STable)); }
+
+__device__ __forceinline__ double common_fac_dev(int l, int pure) {
+  // gto.cpp:7-16
+  if (l == 0) return 0.282094791773878143;
+  if (l == 1) return 0.488602511902919921;
+  return pure ? sqrt((2 * l + 1) / (4.0 * 3.14159265358979323846)) : 1.0;
+}
+
+template <int L, bool DERIV, bool PURE>
+__device__ __forceinline__ void shell_angular(double x, double y, double z, double S0, double S1, double fac,
+                                              double *__restrict__ o0, double *__restrict__ ox,
+                                              double *__restrict__ oy, double *__restrict__ oz) {
+  constexpr int NC = (L + 1) * (L + 2) / 2;
+  double xp[L + 1], yp[L + 1], zp[L + 1];
+  xp[0] = yp[0] = zp[0] = 1.0;
+#pragma unroll
+  for (int i = 1; i <= L; ++i) {
+    xp[i] = xp[i - 1] * x;
+    yp[i] = yp[i - 1] * y;
+    zp[i] = zp[i - 1] * z;
+  }
+  const double SX = S1 * x, SY = S1 * y, SZ = S1 * z;
+  double c0[NC], cx[DERIV ? NC : 1], cy[DERIV ? NC : 1], cz[DERIV ? NC : 1];
+  int idx = 0;
+#pragma unroll
+  for (int lx = L; lx >= 0; --lx) {
+#pragma unroll
+    for (int ly = L - lx; ly >= 0; --ly) {
+      const int lz = L - lx - ly;
+      const double A = xp[lx] * yp[ly] * zp[lz];
+      c0[idx] = S0 * A;
+      if (DERIV) {
+        const double AX = lx ? lx * (xp[lx ? lx - 1 : 0] * yp[ly] * zp[lz]) : 0.0;
+        const double AY = ly ? ly * (xp[lx] * yp[ly ? ly - 1 : 0] * zp[lz]) : 0.0;
+        const double AZ = lz ? lz * (xp[lx] * yp[ly] * zp[lz ? lz - 1 : 0]) : 0.0;
+        cx[idx] = SX * A + S0 * AX;
+        cy[idx] = SY * A + S0 * AY;
+        cz[idx] = SZ * A + S0 * AZ;
+      }
+      ++idx;
+    }
+  }
+  if (!PURE || L == 0) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      o0[i * TILE_P] = c0[i] * fac;
+      if (DERIV) {
+        ox[i * TILE_P] = cx[i] * fac;
+        oy[i * TILE_P] = cy[i] * fac;
+        oz[i * TILE_P] = cz[i] * fac;
+      }
+    }
+  } else {
+    constexpr int NS = 2 * L + 1;
+    const double *tab = c_c2s.coef + c_c2s.off[L];
+#pragma unroll
+    for (int m = 0; m < NS; ++m) {
+      double v = 0.0, vx = 0.0, vy = 0.0, vz = 0.0;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        const double t = tab[m * NC + i];
+        v += t * c0[i];
+        if (DERIV) {
+          vx += t * cx[i];
+          vy += t * cy[i];
+          vz += t * cz[i];
+        }
+      }
+      o0[m * TILE_P] = v * fac;
+      if (DERIV) {
+        ox[m * TILE_P] = vx * fac;
+        oy[m * TILE_P] = vy * fac;
+        oz[m * TILE_P] = vz * fac;
+      }
+    }
+  }
+}
+
+template <bool DERIV, bool PURE>
+__device__ __forceinline__ void shell_dispatch(int L, double x, double y, double z, double S0, double S1, double fac,
+                                               double *o0, double *ox, double *oy, double *oz) {
+  switch (L) {
+  case 0: shell_angular<0, DERIV, PURE>(x, y, z, S0, S1, fac, o0, ox, oy, oz); break;
+  case 1: shell_angular<1, DERIV, PURE>(x, y, z, S0, S1, fac, o0, ox, oy, oz); break;
+  case 2: shell_angular<2, DERIV, PURE>(x, y, z, S0, S1, fac, o0, ox, oy, oz); break;
+  case 3: shell_angular<3, DERIV, PURE>(x, y, z, S0, S1, fac, o0, ox, oy, oz); break;
+  case 4: shell_angular<4, DERIV, PURE>(x, y, z, S0, S1, fac, o0, ox, oy, oz); break;
+  case 5: shell_angular<5, DERIV, PURE>(x, y, z, S0, S1, fac, o0, ox, oy, oz); break;
+  case 6: shell_angular<6, DERIV, PURE>(x, y, z, S0, S1, fac, o0, ox, oy, oz); break;
+  default: break;
+  }
+}
+
+template <bool DERIV, bool PURE>
+__global__ void __launch_bounds__(TILE_P) k_collocate(BuildParams P, const CollocItem *__restrict__ items) {
+  const CollocItem it = items[blockIdx.x];
+  const TileDesc t = P.tiles[it.tile];
+  const int p = threadIdx.x;
+  const bool valid = p < t.count;
+  const double px = P.px[t.pt0 + p], py = P.py[t.pt0 + p], pz = P.pz[t.pt0 + p];
+  const size_t slab = static_cast<size_t>(t.nbp) * TILE_P;
+  double *base = P.scratch + t.scr_off + p;
+  const DeviceBasis &B = P.basis;
+  for (int s = it.s0; s < it.s1; ++s) {
+    const int sh = __ldg(P.shell_list + t.sh_off + s);
+    const int col = __ldg(P.shell_col + t.sh_off + s);
+    const int L = __ldg(B.l + sh);
+    const int np = __ldg(B.nprim + sh);
+    const int po = __ldg(B.prim_off + sh);
+    const double x = px - __ldg(B.origin + 3 * sh), y = py - __ldg(B.origin + 3 * sh + 1),
+                 z = pz - __ldg(B.origin + 3 * sh + 2);
+    double r2 = x * x;
+    r2 += y * y;
+    r2 += z * z;
+    double S0 = 0.0, S1 = 0.0;
+    for (int k = 0; k < np; ++k) {
+      const double a = __ldg(B.exps + po + k);
+      const double T1 = __ldg(B.coefs + po + k) * exp(-a * r2);
+      S0 += T1;
+      if (DERIV) S1 += (-2.0 * a) * T1;
+    }
+    if (!valid) {
+      S0 = 0.0;
+      S1 = 0.0;
+    }
+    double *o0 = base + static_cast<size_t>(col) * TILE_P;
+    shell_dispatch<DERIV, PURE>(L, x, y, z, S0, S1, common_fac_dev(L, PURE), o0, o0 + slab, o0 + 2 * slab,
+                                o0 + 3 * slab);
+  }
+  if (it.last) {
+    for (int col = t.nb; col < t.nbp; ++col) {
+      double *o0 = base + static_cast<size_t>(col) * TILE_P;
+      o0[0] = 0.0;
+      if (DERIV) {
+        o0[slab] = 0.0;
+        o0[2 * slab] = 0.0;
+        o0[3 * slab] = 0.0;
+      }
+    }
+  }
+}
+
+void launch_collocate(const BuildParams &P, const CollocItem *items, int nitems, void *stream) {
+  if (nitems <= 0) return;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool deriv = P.ncomp > 1;
+  if (deriv && P.basis.pure) k_collocate<true, true><<<nitems, TILE_P, 0, st>>>(P, items);
+  else if (deriv) k_collocate<true, false><<<nitems, TILE_P, 0, st>>>(P, items);
+  else if (P.basis.pure) k_collocate<false, true><<<nitems, TILE_P, 0, st>>>(P, items);
+  else k_collocate<false, false><<<nitems, TILE_P, 0, st>>>(P, items);
+}
+
+} // namespace xcb

@@ -1,0 +1,325 @@
+// k_gemm.cu — the two FP64 tensor-core contractions of the XC build.
+//
+//   density  (reference: occ::density::evaluate_density, src/gto/density.cpp:8-166)
+//       X = phi_a . D_loc  (128 points x nb, K = nb), immediately row-dotted with the AO slabs:
+//       rho = rowsum(phi o X), d_k rho = 2 rowsum(phi_k o X), tau = 1/2 sum_k rowsum(phi_k o (phi_k D))
+//       D_loc is never materialised: the B operand is gathered from the full density matrix through the
+//       leaf's local->global index list while it is staged into shared memory (reference gathers Dloc
+//       on the host, include/occ/dft/dft.h:340-348).
+//   vxc      (reference: xc_potential_matrix, src/dft/xc_potential_matrix.cpp:8-135)
+//       Ktmp_loc = phi_a^T . B  (nb x nb, K = 128 points), B = G (the weighted AO combination) or phi_k
+//       scaled by the tau coefficient; scattered with red.global.add.f64 straight into the full-size
+//       matrix (reference scatters Kblk on the host, dft.h:361-369).  K = Ktmp + Ktmp^T afterwards.
+//
+// Both run on the FP64 tensor pipe: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4 — the only f64 MMA shape sm_100a
+// has in hardware; tcgen05/UMMA has no f64 kind).  CTA tile 128 x 64, K chunks of 16, 8 warps in a 4 x 2
+// arrangement with 32 x 32 warp tiles (16 DMMA per 8 conflict-free 64-bit LDS), a 3-stage cp.async pipeline,
+// 2 CTAs per SM.  Shared-memory leading dimensions are = 4 (mod 16) doubles, which makes every fragment
+// load bank-conflict free for the (groupID, threadID_in_group) access pattern of the f64 MMA.
+#include "xc_internal.h"
+#include <cuda_runtime.h>
+
+namespace xcb {
+
+constexpr int GM = 128, GN = 64, GK = 16, GSTAGES = 3;
+constexpr int NTHREADS = 256;
+// density: A stage is [k][m] (m contiguous), ld 132; B stage is [n][k] (k contiguous), ld 20
+constexpr int D_LDA = GM + 4, D_LDB = GK + 4;
+constexpr int D_ASZ = GK * D_LDA, D_BSZ = GN * D_LDB, D_STAGE = D_ASZ + D_BSZ;
+// vxc: A stage is [m][k] (k contiguous), ld 20; B stage is [n][k], ld 20
+constexpr int V_LDA = GK + 4, V_LDB = GK + 4;
+constexpr int V_ASZ = GM * V_LDA, V_BSZ = GN * V_LDB, V_STAGE = V_ASZ + V_BSZ;
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool pred) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  const int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem, bool pred) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  const int sz = pred ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+__device__ __forceinline__ void red_add_f64(double *addr, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(addr), "d"(v) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// density
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 2) k_density(BuildParams P, const DensItem *__restrict__ items) {
+  extern __shared__ __align__(16) double smem[];
+  const DensItem it = items[blockIdx.x];
+  const TileDesc t = P.tiles[it.tile];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int wm = warp & 3, wn = warp >> 2;
+  const int nb = t.nb;
+  const int nk = (nb + GK - 1) / GK;
+  const size_t slab = static_cast<size_t>(t.nbp) * TILE_P;
+  const double *Ag = P.scratch + t.scr_off + static_cast<size_t>(it.acomp) * slab;
+  const double *Dm = (it.acomp == 0 ? P.Drho : P.Dtau)[it.spin];
+  const int *gidx = P.bf_index + t.bf_off;
+  const int n0 = it.jb * GN;
+
+  // B loader assignment: this thread stages k = kk of every chunk for 4 columns
+  const int kk = tid & 15, nn = tid >> 4;
+  size_t coloff[4];
+  bool nvalid[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int n = n0 + nn + 16 * r;
+    nvalid[r] = n < nb;
+    coloff[r] = nvalid[r] ? static_cast<size_t>(__ldg(gidx + n)) * P.ldD : 0;
+  }
+
+  auto load_stage = [&](int kc, int stage) {
+    double *As = smem + stage * D_STAGE;
+    double *Bs = As + D_ASZ;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int seg = tid + NTHREADS * r;
+      const int col = seg >> 6, s2 = (seg & 63) * 2;
+      cp_async16(As + col * D_LDA + s2, Ag + static_cast<size_t>(kc * GK + col) * TILE_P + s2, true);
+    }
+    const int k = kc * GK + kk;
+    const bool kvalid = k < nb;
+    const int grow = kvalid ? __ldg(gidx + k) : 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      cp_async8(Bs + (nn + 16 * r) * D_LDB + kk, Dm + coloff[r] + grow, kvalid && nvalid[r]);
+  };
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < GSTAGES - 1; ++s) {
+    if (s < nk) load_stage(s, s);
+    cp_async_commit();
+  }
+  for (int kc = 0; kc < nk; ++kc) {
+    cp_async_wait<GSTAGES - 2>();
+    __syncthreads();
+    if (kc + GSTAGES - 1 < nk) load_stage(kc + GSTAGES - 1, (kc + GSTAGES - 1) % GSTAGES);
+    cp_async_commit();
+    const double *As = smem + (kc % GSTAGES) * D_STAGE;
+    const double *Bs = As + D_ASZ;
+#pragma unroll
+    for (int k4 = 0; k4 < GK / 4; ++k4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) a[mi] = As[(k4 * 4 + tig) * D_LDA + wm * 32 + mi * 8 + gid];
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[(wn * 32 + ni * 8 + gid) * D_LDB + k4 * 4 + tig];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: row-dot the X tile (registers) with the AO slabs of the same columns
+  double *accp = P.acc + (static_cast<size_t>(it.tile) * P.nspin + it.spin) * NACC * TILE_P;
+  const int c_begin = it.acomp == 0 ? 0 : it.acomp;
+  const int c_end = it.acomp == 0 ? P.ncomp : it.acomp + 1;
+  const double *phib = P.scratch + t.scr_off + static_cast<size_t>(n0 + wn * 32 + 2 * tig) * TILE_P + wm * 32 + gid;
+  for (int c = c_begin; c < c_end; ++c) {
+    const double *pc = phib + static_cast<size_t>(c) * slab;
+    const int row = it.acomp == 0 ? c : 4;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      double s = 0.0;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        s += pc[(ni * 8) * TILE_P + mi * 8] * acc[mi][ni][0];
+        s += pc[(ni * 8 + 1) * TILE_P + mi * 8] * acc[mi][ni][1];
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (tig == 0) red_add_f64(accp + row * TILE_P + wm * 32 + mi * 8 + gid, s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// G slab: G_s = c0 phi + cx phi_x + cy phi_y + cz phi_z  (the bracket of xc_potential_matrix.cpp:33-39 / :86-99)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE_P) k_gbuild(BuildParams P, const DensItem *__restrict__ items) {
+  const DensItem it = items[blockIdx.x];
+  const TileDesc t = P.tiles[it.tile];
+  if (P.leaf_skip[t.leaf]) return;
+  const int p = threadIdx.x;
+  const size_t slab = static_cast<size_t>(t.nbp) * TILE_P;
+  const double *phi = P.scratch + t.scr_off + static_cast<size_t>(it.jb) * GN * TILE_P + p;
+  for (int s = 0; s < P.nspin; ++s) {
+    const double *cf = P.coef + (static_cast<size_t>(it.tile) * P.nspin + s) * NCOEF * TILE_P + p;
+    const double c0 = cf[0];
+    double *G = const_cast<double *>(phi) + static_cast<size_t>(P.ncomp + s) * slab;
+    if (P.ncomp > 1) {
+      const double cx = cf[TILE_P], cy = cf[2 * TILE_P], cz = cf[3 * TILE_P];
+#pragma unroll 4
+      for (int j = 0; j < GN; ++j) {
+        const double *q = phi + j * TILE_P;
+        G[j * TILE_P] = c0 * q[0] + cx * q[slab] + cy * q[2 * slab] + cz * q[3 * slab];
+      }
+    } else {
+#pragma unroll 4
+      for (int j = 0; j < GN; ++j) G[j * TILE_P] = c0 * phi[j * TILE_P];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// vxc
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 2) k_vxc(BuildParams P, const VxcItem *__restrict__ items) {
+  extern __shared__ __align__(16) double smem[];
+  const VxcItem it = items[blockIdx.x];
+  const TileDesc t = P.tiles[it.tile];
+  if (P.leaf_skip[t.leaf]) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int wm = warp & 3, wn = warp >> 2;
+  const int nb = t.nb, nbp = t.nbp;
+  const size_t slab = static_cast<size_t>(nbp) * TILE_P;
+  const double *base = P.scratch + t.scr_off;
+  const double *Ag = base + static_cast<size_t>(it.acomp) * slab; // phi_a[i*128 + p]
+  const double *Bg = (it.acomp == 0 ? base + static_cast<size_t>(P.ncomp + it.spin) * slab : Ag) +
+                     static_cast<size_t>(it.jb) * GN * TILE_P; // B[j*128 + p]
+  const int *gidx = P.bf_index + t.bf_off;
+  double *Kt = P.Ktmp[it.spin];
+  const int n0 = it.jb * GN;
+  const int nib = (nb + GM - 1) / GM;
+  const int nq = nib * (TILE_P / GK); // flattened (ib, kc) chunks
+  double *sct = smem + GSTAGES * V_STAGE; // [128] tau coefficient (acomp != 0)
+  if (tid < TILE_P)
+    sct[tid] = it.acomp == 0
+                   ? 1.0
+                   : P.coef[((static_cast<size_t>(it.tile) * P.nspin + it.spin) * NCOEF + 4) * TILE_P + tid];
+
+  auto load_stage = [&](int q, int stage) {
+    double *As = smem + stage * V_STAGE;
+    double *Bs = As + V_ASZ;
+    const int ib = q >> 3, kc = q & 7;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int seg = tid + NTHREADS * r; // 1024 segments: row = seg >> 3, 8 x 16 B per row
+      const int row = seg >> 3, s2 = (seg & 7) * 2;
+      const int i = ib * GM + row;
+      cp_async16(As + row * V_LDA + s2, Ag + static_cast<size_t>(i < nbp ? i : 0) * TILE_P + kc * GK + s2, i < nbp);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int seg = tid + NTHREADS * r; // 512 segments
+      const int row = seg >> 3, s2 = (seg & 7) * 2;
+      cp_async16(Bs + row * V_LDB + s2, Bg + static_cast<size_t>(row) * TILE_P + kc * GK + s2, true);
+    }
+  };
+
+  // global column offsets of this thread's 8 output columns
+  size_t coloff[4][2];
+  bool cvalid[4][2];
+#pragma unroll
+  for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = n0 + wn * 32 + ni * 8 + 2 * tig + e;
+      cvalid[ni][e] = j < nb;
+      coloff[ni][e] = cvalid[ni][e] ? static_cast<size_t>(__ldg(gidx + j)) * P.ldD : 0;
+    }
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int s = 0; s < GSTAGES - 1; ++s) {
+    if (s < nq) load_stage(s, s);
+    cp_async_commit();
+  }
+  for (int q = 0; q < nq; ++q) {
+    const int kc = q & 7;
+    if (kc == 0) {
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    }
+    cp_async_wait<GSTAGES - 2>();
+    __syncthreads();
+    if (q + GSTAGES - 1 < nq) load_stage(q + GSTAGES - 1, (q + GSTAGES - 1) % GSTAGES);
+    cp_async_commit();
+    const double *As = smem + (q % GSTAGES) * V_STAGE;
+    const double *Bs = As + V_ASZ;
+#pragma unroll
+    for (int k4 = 0; k4 < GK / 4; ++k4) {
+      double a[4], b[4];
+      const double sc = sct[kc * GK + k4 * 4 + tig];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) a[mi] = As[(wm * 32 + mi * 8 + gid) * V_LDA + k4 * 4 + tig] * sc;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[(wn * 32 + ni * 8 + gid) * V_LDB + k4 * 4 + tig];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+    if (kc == 7) {
+      // scatter-add this 128 x 64 block of Ktmp_loc into the full matrix (dft.h:361-369)
+      const int ib = q >> 3;
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        const int i = ib * GM + wm * 32 + mi * 8 + gid;
+        if (i < nb) {
+          double *dst = Kt + __ldg(gidx + i);
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) {
+            if (cvalid[ni][0]) red_add_f64(dst + coloff[ni][0], acc[mi][ni][0]);
+            if (cvalid[ni][1]) red_add_f64(dst + coloff[ni][1], acc[mi][ni][1]);
+          }
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
+void launch_density(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
+  if (nitems <= 0) return;
+  static bool configured = false;
+  const int smem_bytes = GSTAGES * D_STAGE * sizeof(double);
+  if (!configured) {
+    cudaFuncSetAttribute(k_density, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    configured = true;
+  }
+  k_density<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
+}
+
+void launch_gbuild(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
+  if (nitems <= 0) return;
+  k_gbuild<<<nitems, TILE_P, 0, static_cast<cudaStream_t>(stream)>>>(P, items);
+}
+
+void launch_vxc(const BuildParams &P, const VxcItem *items, int nitems, void *stream) {
+  if (nitems <= 0) return;
+  static bool configured = false;
+  const int smem_bytes = (GSTAGES * V_STAGE + TILE_P) * sizeof(double);
+  if (!configured) {
+    cudaFuncSetAttribute(k_vxc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    configured = true;
+  }
+  k_vxc<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
+}
+
+} // namespace xcb

@@ -1,0 +1,429 @@
+// xc_functionals.cuh — the LDA / GGA / meta-GGA exchange-correlation functionals of the XC build, written
+// for the device (and callable on the host for table checks).  They replace the libxc 6.2.2 calls the
+// reference makes per grid block (src/dft/functional.cpp:18-65: xc_lda_exc_vxc / xc_gga_exc_vxc /
+// xc_mgga_exc_vxc) for the functional ids reachable from src/dft/dft_method.cpp:14-37:
+//   lda_x(1) lda_c_vwn(7) lda_c_vwn_rpa(8) lda_c_vwn_3(30) gga_x_pbe(101) gga_x_b88(106) gga_c_pbe(130)
+//   gga_c_lyp(131) hyb_gga_xc_b3lyp(402) mgga_x_r2scan(497) mgga_c_r2scan(498)
+// libxc conventions: exc = energy per particle; vrho = d(rho*exc)/d rho_s; vsigma = d(rho*exc)/d sigma with
+// sigma = grad rho . grad rho (polarized order aa, ab, bb); vtau = d(rho*exc)/d tau_s, tau = 1/2 sum |grad psi|^2.
+// Each functional is a single energy density in (rho_a, rho_b, sigma_aa, sigma_ab, sigma_bb, tau_a, tau_b);
+// the potentials come from the dual-number derivatives (xc_dual.cuh).  No libxc, no CPU fallback.
+#pragma once
+#include "xc_dual.cuh"
+
+namespace xcb {
+
+enum : int {
+  ID_LDA_X = 1, ID_LDA_C_VWN = 7, ID_LDA_C_VWN_RPA = 8, ID_LDA_C_VWN_3 = 30, ID_GGA_X_PBE = 101,
+  ID_GGA_X_B88 = 106, ID_GGA_C_PBE = 130, ID_GGA_C_LYP = 131, ID_HYB_GGA_XC_B3LYP = 402,
+  ID_MGGA_X_R2SCAN = 497, ID_MGGA_C_R2SCAN = 498
+};
+
+XC_HD int xc_family_of(int id) {
+  switch (id) {
+  case ID_LDA_X: case ID_LDA_C_VWN: case ID_LDA_C_VWN_RPA: case ID_LDA_C_VWN_3: return 0;
+  case ID_GGA_X_PBE: case ID_GGA_X_B88: case ID_GGA_C_PBE: case ID_GGA_C_LYP: case ID_HYB_GGA_XC_B3LYP: return 1;
+  case ID_MGGA_X_R2SCAN: case ID_MGGA_C_R2SCAN: return 2;
+  default: return -1;
+  }
+}
+
+// thresholds (libxc-style): nothing is evaluated below DENS_THR total density; spin densities, sigma and
+// tau are floored so that every expression stays differentiable
+#define XC_DENS_THR 1e-15
+#define XC_SPIN_FLOOR 1e-15
+#define XC_SIGMA_FLOOR 1e-40
+#define XC_TAU_FLOOR 1e-20
+
+#define XC_PI 3.14159265358979323846
+#define XC_LDAX_C (-0.9305257363491)          /* -(3/4)(6/pi)^(1/3) */
+#define XC_TWO43M2 0.5198420997897464         /* 2^(4/3) - 2 */
+#define XC_FPP0 1.7099209341613653            /* f''(0) = 4/(9(2^(1/3)-1)) */
+#define XC_B88_CX 0.9305257363491             /* (3/8)(3/pi)^(1/3) 4^(2/3) */
+#define XC_CF 2.871234000188191               /* (3/10)(3 pi^2)^(2/3) */
+#define XC_TWO113 12.699208415745595          /* 2^(11/3) */
+#define XC_EXU_C (-0.7385587663820223)        /* -(3/4)(3/pi)^(1/3) */
+#define XC_S2_C 38.283120002509214            /* 4 (3 pi^2)^(2/3) */
+#define XC_GAMMA 0.0310906908696549           /* (1 - ln 2)/pi^2 */
+#define XC_3PI2 29.608813203268074
+#define XC_RS_C 0.238732414637843             /* 3/(4 pi) */
+
+template <class T> struct XV {
+  T ra, rb, saa, sab, sbb, ta, tb;
+};
+
+// ---------------------------------------------------------------------------------------------
+template <class T> XC_HD T e_lda_x(const XV<T> &v) { // Dirac exchange, spin-resolved
+  return XC_LDAX_C * (v.ra * cbrt(v.ra) + v.rb * cbrt(v.rb));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Vosko-Wilk-Nusair 1980. Parameter sets: 0 paramagnetic, 1 ferromagnetic, 2 spin stiffness;
+// MC = fit to Ceperley-Alder (VWN5), RPA = fit to RPA data.
+struct VwnP { double A, b, c, x0; };
+XC_HD VwnP vwn_mc(int k) {
+  switch (k) {
+  case 0: return {0.0310907, 3.72744, 12.9352, -0.10498};
+  case 1: return {0.01554535, 7.06042, 18.0578, -0.32500};
+  default: return {-1.0 / (6.0 * XC_PI * XC_PI), 1.13107, 13.0045, -0.0047584};
+  }
+}
+XC_HD VwnP vwn_rpa(int k) {
+  switch (k) {
+  case 0: return {0.0310907, 13.0720, 42.7198, -0.409286};
+  case 1: return {0.01554535, 20.1231, 101.578, -0.743294};
+  default: return {-1.0 / (6.0 * XC_PI * XC_PI), 1.06835, 11.4813, -0.228344};
+  }
+}
+template <class T> XC_HD T vwn_q(const VwnP p, const T &rs, const T &x) {
+  const double Q = ::sqrt(4.0 * p.c - p.b * p.b);
+  const double X0 = p.x0 * p.x0 + p.b * p.x0 + p.c;
+  const T X = rs + p.b * x + p.c;
+  const T at = atan(Q / (2.0 * x + p.b));
+  const T xm = x - p.x0;
+  return p.A * (log(rs / X) + (2.0 * p.b / Q) * at -
+                (p.b * p.x0 / X0) * (log(xm * xm / X) + (2.0 * (p.b + 2.0 * p.x0) / Q) * at));
+}
+template <class T> XC_HD T f_zeta(const T &z) {
+  const T p = 1.0 + z, m = 1.0 - z;
+  return (p * cbrt(p) + m * cbrt(m) - 2.0) / XC_TWO43M2;
+}
+template <class T> XC_HD void rs_zeta(const XV<T> &v, T &rho, T &rs, T &z) {
+  rho = v.ra + v.rb;
+  rs = cbrt(XC_RS_C / rho);
+  z = (v.ra - v.rb) / rho;
+}
+// VARIANT 0: lda_c_vwn (VWN5), 1: lda_c_vwn_rpa, 2: lda_c_vwn_3
+template <int VARIANT, class T> XC_HD T e_vwn(const XV<T> &v) {
+  T rho, rs, z;
+  rs_zeta(v, rho, rs, z);
+  const T x = sqrt(rs);
+  const T fz = f_zeta(z);
+  if (VARIANT == 1) {
+    const T eP = vwn_q(vwn_rpa(0), rs, x), eF = vwn_q(vwn_rpa(1), rs, x);
+    return rho * (eP + (eF - eP) * fz);
+  }
+  const T z2 = z * z;
+  const T z4 = z2 * z2;
+  const T eP = vwn_q(vwn_mc(0), rs, x), eF = vwn_q(vwn_mc(1), rs, x);
+  const T dmc = eF - eP;
+  if (VARIANT == 0) {
+    const T ac = vwn_q(vwn_mc(2), rs, x);
+    return rho * (eP + ac * fz * (1.0 - z4) / XC_FPP0 + dmc * fz * z4);
+  }
+  const T ePr = vwn_q(vwn_rpa(0), rs, x), eFr = vwn_q(vwn_rpa(1), rs, x), acr = vwn_q(vwn_rpa(2), rs, x);
+  return rho * (eP + (dmc / (eFr - ePr)) * acr * fz * (1.0 - z4) / XC_FPP0 + dmc * fz * z4);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Becke 1988 exchange, beta = 0.0042, gamma = 6
+template <class T> XC_HD T b88_spin(const T &r, const T &s) {
+  const double beta = 0.0042, gam = 6.0;
+  const T r43 = r * cbrt(r);
+  const T x = sqrt(s) / r43;
+  return -(r43 * (XC_B88_CX + beta * (x * x) / (1.0 + gam * beta * x * asinh(x))));
+}
+template <class T> XC_HD T e_b88(const XV<T> &v) { return b88_spin(v.ra, v.saa) + b88_spin(v.rb, v.sbb); }
+
+// ---------------------------------------------------------------------------------------------
+// Lee-Yang-Parr correlation in the Miehlich-Savin-Stoll-Preuss gradient form
+template <class T> XC_HD T e_lyp(const XV<T> &v) {
+  const double a = 0.04918, b = 0.132, c = 0.2533, d = 0.349;
+  const T rho = v.ra + v.rb;
+  const T rm13 = 1.0 / cbrt(rho);
+  const T den = 1.0 + d * rm13;
+  const T omega = exp(-c * rm13) / den * pow(rho, -11.0 / 3.0);
+  const T delta = c * rm13 + d * rm13 / den;
+  const T stot = v.saa + 2.0 * v.sab + v.sbb;
+  const T ra2 = v.ra * v.ra, rb2 = v.rb * v.rb;
+  const T ra83 = ra2 * cbrt(ra2), rb83 = rb2 * cbrt(rb2);
+  const T rho2 = rho * rho;
+  const T t1 = -4.0 * a / den * v.ra * v.rb / rho;
+  const T brack = (XC_TWO113 * XC_CF) * (ra83 + rb83) + (47.0 / 18.0 - 7.0 * delta / 18.0) * stot -
+                  (2.5 - delta / 18.0) * (v.saa + v.sbb) -
+                  (delta - 11.0) / 9.0 * (v.ra / rho * v.saa + v.rb / rho * v.sbb);
+  const T t2 = -(a * b) * omega *
+               (v.ra * v.rb * brack - (2.0 / 3.0) * rho2 * stot + ((2.0 / 3.0) * rho2 - ra2) * v.sbb +
+                ((2.0 / 3.0) * rho2 - rb2) * v.saa);
+  return t1 + t2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PBE 1996
+template <class T> XC_HD T ex_unif(const T &n) { return XC_EXU_C * (n * cbrt(n)); }
+template <class T> XC_HD T red_grad2(const T &n, const T &sigma) { // s^2 = sigma / (4 (3 pi^2)^(2/3) n^(8/3))
+  const T n2 = n * n;
+  return sigma / (XC_S2_C * (n2 * cbrt(n2)));
+}
+template <class T> XC_HD T pbe_x_total(const T &n, const T &sigma) {
+  const double kappa = 0.804, mu = 0.2195149727645171;
+  const T s2 = red_grad2(n, sigma);
+  return ex_unif(n) * (1.0 + kappa - kappa / (1.0 + mu * s2 / kappa));
+}
+template <class T> XC_HD T e_pbe_x(const XV<T> &v) { // E[ra, rb] = (E[2 ra] + E[2 rb]) / 2
+  return 0.5 * (pbe_x_total(2.0 * v.ra, 4.0 * v.saa) + pbe_x_total(2.0 * v.rb, 4.0 * v.sbb));
+}
+
+// Perdew-Wang 1992 LSDA correlation, "modified" (more-digit) constants
+struct PwP { double A, a1, b1, b2, b3, b4; };
+XC_HD PwP pw_set(int k) {
+  switch (k) {
+  case 0: return {0.0310907, 0.21370, 7.5957, 3.5876, 1.6382, 0.49294};
+  case 1: return {0.01554535, 0.20548, 14.1189, 6.1977, 3.3662, 0.62517};
+  default: return {0.0168869, 0.11125, 10.357, 3.6231, 0.88026, 0.49671};
+  }
+}
+template <class T> XC_HD T pw_g(const PwP p, const T &rs, const T &srs) {
+  const T q1 = 2.0 * p.A * (p.b1 * srs + p.b2 * rs + p.b3 * rs * srs + p.b4 * (rs * rs));
+  return -2.0 * p.A * (1.0 + p.a1 * rs) * log(1.0 + 1.0 / q1);
+}
+template <class T> XC_HD T pw_dg(const PwP p, const T &rs, const T &srs) { // d pw_g / d rs
+  const T q1 = 2.0 * p.A * (p.b1 * srs + p.b2 * rs + p.b3 * rs * srs + p.b4 * (rs * rs));
+  const T dq1 = p.A * (p.b1 / srs + 2.0 * p.b2 + 3.0 * p.b3 * srs + 4.0 * p.b4 * rs);
+  return -2.0 * p.A * p.a1 * log(1.0 + 1.0 / q1) + 2.0 * p.A * (1.0 + p.a1 * rs) * dq1 / (q1 * q1 + q1);
+}
+template <class T> XC_HD T eps_pw(const T &rs, const T &z) {
+  const T srs = sqrt(rs);
+  const T e0 = pw_g(pw_set(0), rs, srs), e1 = pw_g(pw_set(1), rs, srs), mac = pw_g(pw_set(2), rs, srs);
+  const T fz = f_zeta(z);
+  const T z2 = z * z;
+  const T z4 = z2 * z2;
+  return e0 - mac * fz * (1.0 - z4) / XC_FPP0 + (e1 - e0) * fz * z4;
+}
+template <class T> XC_HD T deps_pw_drs(const T &rs, const T &z) {
+  const T srs = sqrt(rs);
+  const T e0 = pw_dg(pw_set(0), rs, srs), e1 = pw_dg(pw_set(1), rs, srs), mac = pw_dg(pw_set(2), rs, srs);
+  const T fz = f_zeta(z);
+  const T z2 = z * z;
+  const T z4 = z2 * z2;
+  return e0 - mac * fz * (1.0 - z4) / XC_FPP0 + (e1 - e0) * fz * z4;
+}
+template <class T> XC_HD T phi_zeta(const T &z) {
+  const T p = 1.0 + z, m = 1.0 - z;
+  return 0.5 * (cbrt(p * p) + cbrt(m * m));
+}
+template <class T> XC_HD T e_pbe_c(const XV<T> &v) {
+  const double beta = 0.06672455060314922;
+  T rho, rs, z;
+  rs_zeta(v, rho, rs, z);
+  const T ec = eps_pw(rs, z);
+  const T phi = phi_zeta(z);
+  const T phi2 = phi * phi;
+  const T phi3 = phi * phi2;
+  const T stot = v.saa + 2.0 * v.sab + v.sbb;
+  const T kF = cbrt(XC_3PI2 * rho);
+  const T t2 = stot * XC_PI / (16.0 * phi2 * kF * (rho * rho));
+  const T A = (beta / XC_GAMMA) / expm1(-ec / (XC_GAMMA * phi3));
+  const T At2 = A * t2;
+  const T H = XC_GAMMA * phi3 * log(1.0 + (beta / XC_GAMMA) * t2 * (1.0 + At2) / (1.0 + At2 + At2 * At2));
+  return rho * (ec + H);
+}
+
+// ---------------------------------------------------------------------------------------------
+// r2SCAN (Furness, Kaplan, Ning, Perdew, Sun 2020)
+#define XC_R2_ETA 0.001
+#define XC_R2_DP24 0.016983563041 /* dp2^4, dp2 = 0.361 */
+template <class T> XC_HD T r2_poly(const T &a, const double c0, const double c1, const double c2, const double c3,
+                                   const double c4, const double c5, const double c6, const double c7) {
+  T r = c7 * a + c6;
+  r = r * a + c5;
+  r = r * a + c4;
+  r = r * a + c3;
+  r = r * a + c2;
+  r = r * a + c1;
+  r = r * a + c0;
+  return r;
+}
+template <class T> XC_HD T r2_fx(const T &alpha) {
+  if (val(alpha) < 0.0) return exp(-0.667 * alpha / (1.0 - alpha));
+  if (val(alpha) <= 2.5)
+    return r2_poly(alpha, 1.0, -0.667, -0.4445555, -0.663086601049, 1.451297044490, -0.887998041597,
+                   0.234528941479, -0.023185843322);
+  return -1.24 * exp(0.8 / (1.0 - alpha));
+}
+template <class T> XC_HD T r2_fc(const T &alpha) {
+  if (val(alpha) < 0.0) return exp(-0.64 * alpha / (1.0 - alpha));
+  if (val(alpha) <= 2.5)
+    return r2_poly(alpha, 1.0, -0.64, -0.4352, -1.535685604549, 3.061560252175, -1.915710236206, 0.516884468372,
+                   -0.051848879792);
+  return -0.7 * exp(1.5 / (1.0 - alpha));
+}
+template <class T> XC_HD T r2scan_x_total(const T &n, const T &sigma_in, const T &tau) {
+  const double k0 = 0.174, k1 = 0.065, mu = 10.0 / 81.0, a1 = 4.9479;
+  const double C2 = -0.9353000875519996 * k0; // sum_i i c_xi times k0
+  const double Ceta = 20.0 / 27.0 + XC_R2_ETA * 5.0 / 3.0;
+  T sigma = sigma_in;
+  if (val(sigma) > 8.0 * val(n) * val(tau)) sigma = 8.0 * n * tau; // Fermi-hole-curvature bound
+  const T p = red_grad2(n, sigma);
+  const T tauW = sigma / (8.0 * n);
+  const T n2 = n * n;
+  const T tauU = XC_CF * (n * cbrt(n2));
+  const T alpha = (tau - tauW) / (tauU + XC_R2_ETA * tauW);
+  const T x = (Ceta * C2 * exp(-(p * p) / XC_R2_DP24) + mu) * p;
+  const T h1 = 1.0 + k1 - k1 / (1.0 + x / k1);
+  const double h0 = 1.0 + k0;
+  const T fx = r2_fx(alpha);
+  const T gx = 1.0 - exp(-a1 / sqrt(sqrt(p)));
+  return ex_unif(n) * (h1 + fx * (h0 - h1)) * gx;
+}
+template <class T> XC_HD T e_r2scan_x(const XV<T> &v) {
+  return 0.5 * (r2scan_x_total(2.0 * v.ra, 4.0 * v.saa, 2.0 * v.ta) +
+                r2scan_x_total(2.0 * v.rb, 4.0 * v.sbb, 2.0 * v.tb));
+}
+template <class T> XC_HD T e_r2scan_c(const XV<T> &v) {
+  const double b1c = 0.0285764, b2c = 0.0889, b3c = 0.125541, chi_inf = 0.128026;
+  const double dfc2 = -0.7114023342889984; // sum_i i c_ci
+  T rho, rs, z;
+  rs_zeta(v, rho, rs, z);
+  T stot = v.saa + 2.0 * v.sab + v.sbb;
+  const T tau = v.ta + v.tb;
+  if (val(stot) > 8.0 * val(rho) * val(tau)) stot = 8.0 * rho * tau;
+  const T p = red_grad2(rho, stot);
+  const T zp = 1.0 + z, zm = 1.0 - z;
+  const T ds = 0.5 * (zp * cbrt(zp * zp) + zm * cbrt(zm * zm));
+  const T dxz = 0.5 * (zp * cbrt(zp) + zm * cbrt(zm));
+  const T phi = phi_zeta(z);
+  const T phi2 = phi * phi;
+  const T phi3 = phi * phi2;
+  const T tauW = stot / (8.0 * rho);
+  const T rho2 = rho * rho;
+  const T tauU = XC_CF * (rho * cbrt(rho2)) * ds;
+  const T alpha = (tau - tauW) / (tauU + XC_R2_ETA * tauW);
+  const T fc = r2_fc(alpha);
+
+  // alpha -> 0 limit
+  const T srs = sqrt(rs);
+  const T den0 = 1.0 + b2c * srs + b3c * rs;
+  const T e_lda0 = -b1c / den0;
+  const T de_lda0 = b1c * (0.5 * b2c / srs + b3c) / (den0 * den0);
+  const T z2 = z * z;
+  const T z4 = z2 * z2;
+  const T z12 = z4 * z4 * z4;
+  const T gc = (1.0 - 2.3631 * (dxz - 1.0)) * (1.0 - z12);
+  const T w0 = expm1(-e_lda0 / b1c);
+  const T ginf = 1.0 / sqrt(sqrt(1.0 + 4.0 * chi_inf * p));
+  const T H0 = b1c * log(1.0 + w0 * (1.0 - ginf));
+  const T eps0 = (e_lda0 + H0) * gc;
+
+  // alpha = 1 limit
+  const T e_lsda1 = eps_pw(rs, z);
+  const T de_lsda1 = deps_pw_drs(rs, z);
+  const T beta = 0.066725 * (1.0 + 0.1 * rs) / (1.0 + 0.1778 * rs);
+  const T t2 = 1.5073033983379012 * p / (phi2 * rs); // (3 pi^2/16)^(2/3)
+  const T w1 = expm1(-e_lsda1 / (XC_GAMMA * phi3));
+  const T y = beta * t2 / (XC_GAMMA * w1);
+  const T e_lsda0 = e_lda0 * gc;
+  const T de_lsda0 = de_lda0 * gc;
+  const T dy = dfc2 / (27.0 * XC_GAMMA * ds * phi3 * w1) *
+               (20.0 * rs * (de_lsda0 - de_lsda1) - 45.0 * XC_R2_ETA * (e_lsda0 - e_lsda1)) * p *
+               exp(-(p * p) / XC_R2_DP24);
+  const T g1 = 1.0 / sqrt(sqrt(1.0 + 4.0 * (y - dy)));
+  const T H1 = XC_GAMMA * phi3 * log(1.0 + w1 * (1.0 - g1));
+  const T eps1 = e_lsda1 + H1;
+  return rho * (eps1 + fc * (eps0 - eps1));
+}
+
+// ---------------------------------------------------------------------------------------------
+template <class T> XC_HD T e_b3lyp(const XV<T> &v) { // libxc hyb_gga_xc_b3lyp: a0 = 0.20, ax = 0.72, ac = 0.81
+  return 0.08 * e_lda_x(v) + 0.72 * e_b88(v) + 0.19 * e_vwn<1>(v) + 0.81 * e_lyp(v);
+}
+
+template <class T> XC_HD T xc_energy_density(int id, const XV<T> &v) {
+  switch (id) {
+  case ID_LDA_X: return e_lda_x(v);
+  case ID_LDA_C_VWN: return e_vwn<0>(v);
+  case ID_LDA_C_VWN_RPA: return e_vwn<1>(v);
+  case ID_LDA_C_VWN_3: return e_vwn<2>(v);
+  case ID_GGA_X_B88: return e_b88(v);
+  case ID_GGA_C_LYP: return e_lyp(v);
+  case ID_GGA_X_PBE: return e_pbe_x(v);
+  case ID_GGA_C_PBE: return e_pbe_c(v);
+  case ID_HYB_GGA_XC_B3LYP: return e_b3lyp(v);
+  case ID_MGGA_X_R2SCAN: return e_r2scan_x(v);
+  case ID_MGGA_C_R2SCAN: return e_r2scan_c(v);
+  default: return T(0.0);
+  }
+}
+
+struct XCPoint { // one grid point, summed over the functional components (functional.h:438-459 Result::operator+=)
+  double exc;
+  double vrho[2], vsigma[3], vtau[2];
+};
+
+// Unpolarized point. FAM: 0 LDA, 1 GGA, 2 meta-GGA = family of the BUILD (max over components); components of a
+// lower family simply ignore the extra inputs, exactly like libxc called through Params of the build's family.
+template <int FAM> XC_HD void xc_eval_unpolarized(int nfunc, const int *ids, double rho, double sigma, double tau,
+                                                  XCPoint &o) {
+  o.exc = 0.0;
+  o.vrho[0] = o.vrho[1] = o.vsigma[0] = o.vsigma[1] = o.vsigma[2] = o.vtau[0] = o.vtau[1] = 0.0;
+  if (!(rho > XC_DENS_THR)) return;
+  constexpr int N = FAM + 1;
+  typedef Dual<N> D;
+  const D R = D::seed(rho, 0);
+  const D S = FAM >= 1 ? D::seed(fmax(sigma, XC_SIGMA_FLOOR), FAM >= 1 ? 1 : 0) : D(XC_SIGMA_FLOOR);
+  const D Tt = FAM >= 2 ? D::seed(fmax(tau, XC_TAU_FLOOR), FAM >= 2 ? 2 : 0) : D(XC_TAU_FLOOR);
+  XV<D> v;
+  v.ra = 0.5 * R;
+  v.rb = v.ra;
+  v.saa = 0.25 * S;
+  v.sab = v.saa;
+  v.sbb = v.saa;
+  v.ta = 0.5 * Tt;
+  v.tb = v.ta;
+  for (int f = 0; f < nfunc; ++f) {
+    const D F = xc_energy_density(ids[f], v);
+    o.exc += F.v / rho;
+    o.vrho[0] += F.d[0];
+    if (FAM >= 1) o.vsigma[0] += F.d[FAM >= 1 ? 1 : 0];
+    if (FAM >= 2) o.vtau[0] += F.d[FAM >= 2 ? 2 : 0];
+  }
+}
+
+template <int FAM> XC_HD void xc_eval_polarized(int nfunc, const int *ids, double ra0, double rb0, double saa0,
+                                                double sab0, double sbb0, double ta0, double tb0, XCPoint &o) {
+  o.exc = 0.0;
+  o.vrho[0] = o.vrho[1] = o.vsigma[0] = o.vsigma[1] = o.vsigma[2] = o.vtau[0] = o.vtau[1] = 0.0;
+  if (!(ra0 + rb0 > XC_DENS_THR)) return;
+  constexpr int N = FAM == 0 ? 2 : (FAM == 1 ? 5 : 7);
+  typedef Dual<N> D;
+  const double ra = fmax(ra0, XC_SPIN_FLOOR), rb = fmax(rb0, XC_SPIN_FLOOR);
+  XV<D> v;
+  v.ra = D::seed(ra, 0);
+  v.rb = D::seed(rb, 1);
+  if (FAM >= 1) {
+    const double saa = fmax(saa0, XC_SIGMA_FLOOR), sbb = fmax(sbb0, XC_SIGMA_FLOOR);
+    const double lim = 0.5 * (saa + sbb); // |sigma_ab| <= (sigma_aa + sigma_bb)/2
+    const double sab = fmin(fmax(sab0, -lim), lim);
+    v.saa = D::seed(saa, N > 2 ? 2 : 0);
+    v.sab = D::seed(sab, N > 3 ? 3 : 0);
+    v.sbb = D::seed(sbb, N > 4 ? 4 : 0);
+  } else {
+    v.saa = D(XC_SIGMA_FLOOR);
+    v.sab = D(0.0);
+    v.sbb = D(XC_SIGMA_FLOOR);
+  }
+  if (FAM >= 2) {
+    v.ta = D::seed(fmax(ta0, XC_TAU_FLOOR), N > 5 ? 5 : 0);
+    v.tb = D::seed(fmax(tb0, XC_TAU_FLOOR), N > 6 ? 6 : 0);
+  } else {
+    v.ta = D(XC_TAU_FLOOR);
+    v.tb = D(XC_TAU_FLOOR);
+  }
+  for (int f = 0; f < nfunc; ++f) {
+    const D F = xc_energy_density(ids[f], v);
+    o.exc += F.v / (ra + rb);
+    o.vrho[0] += F.d[0];
+    o.vrho[1] += F.d[1];
+    if (FAM >= 1) {
+      o.vsigma[0] += F.d[N > 2 ? 2 : 0];
+      o.vsigma[1] += F.d[N > 3 ? 3 : 0];
+      o.vsigma[2] += F.d[N > 4 ? 4 : 0];
+    }
+    if (FAM >= 2) {
+      o.vtau[0] += F.d[N > 5 ? 5 : 0];
+      o.vtau[1] += F.d[N > 6 ? 6 : 0];
+    }
+  }
+}
+
+} // namespace xcb

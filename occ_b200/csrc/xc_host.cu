@@ -1,0 +1,724 @@
+// xc_host.cu — host orchestration behind the C ABI (include/occ_xc_b200.h): what DFT::compute_K_dft
+// (/root/reference include/occ/dft/dft.h:190-388) does around its leaf loop, re-designed for one B200:
+//   create : shell screening per Morton leaf (dft.h:313-335), tiles, batches and the per-phase work lists —
+//            all geometry-only, so built ONCE instead of every SCF iteration; everything uploaded to HBM
+//   build  : D -> device, then per batch of leaves  collocate -> density (DMMA) -> functional -> G -> vxc (DMMA),
+//            finally K = Ktmp + Ktmp^T and the fixed-order reduction of Exc / N_alpha / N_beta
+// No CPU fallback: every phase is a CUDA kernel; create() fails without a device.
+#include "../../include/occ_xc_b200.h"
+#include "xc_functionals.cuh"
+#include "xc_internal.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <cuda_runtime.h>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace xcb {
+void launch_gbuild(const BuildParams &P, const DensItem *items, int nitems, void *stream);
+}
+
+using namespace xcb;
+
+static thread_local std::string g_last_error;
+static int fail(const std::string &msg) {
+  g_last_error = msg;
+  return 1;
+}
+#define CUDA_TRY(expr)                                                                                       \
+  do {                                                                                                       \
+    cudaError_t e__ = (expr);                                                                                \
+    if (e__ != cudaSuccess)                                                                                  \
+      return fail(std::string("CUDA error: ") + cudaGetErrorString(e__) + " in " #expr);                    \
+  } while (0)
+
+static inline int shell_size(int l, int pure) { return pure ? 2 * l + 1 : (l + 1) * (l + 2) / 2; }
+static inline double common_fac_host(int l, int pure) { // gto.cpp:7-16
+  if (l == 0) return 0.282094791773878143;
+  if (l == 1) return 0.488602511902919921;
+  return pure ? std::sqrt((2 * l + 1) / (4.0 * M_PI)) : 1.0;
+}
+
+// ---- real solid harmonics in Cartesian monomials (CCA order m = -l..l, Cartesian order lx desc then ly desc),
+// the table gau2grid's GG_SPHERICAL_CCA transform applies (src/3rdparty/gau2grid/gau2grid_transform.c:44-196).
+// Closed form: Helgaker, Jorgensen, Olsen, "Molecular Electronic-Structure Theory", eqs. 6.4.47-6.4.50. ----
+static double binomial(int n, int k) {
+  if (k < 0 || k > n) return 0.0;
+  double r = 1.0;
+  for (int i = 1; i <= k; ++i) r = r * (n - k + i) / i;
+  return r;
+}
+static double factorial(int n) {
+  double r = 1.0;
+  for (int i = 2; i <= n; ++i) r *= i;
+  return r;
+}
+static int cart_index(int l, int lx, int ly) {
+  // position of x^lx y^ly z^(l-lx-ly) in the CCA ordering
+  int idx = 0;
+  for (int a = l; a > lx; --a) idx += l - a + 1;
+  return idx + (l - lx - ly);
+}
+static void solid_harmonic_table(int l, double *M /* (2l+1) x ncart */) {
+  const int nc = (l + 1) * (l + 2) / 2;
+  std::fill(M, M + static_cast<size_t>(2 * l + 1) * nc, 0.0);
+  for (int m = -l; m <= l; ++m) {
+    const int am = std::abs(m);
+    const double norm = std::sqrt(2.0 * factorial(l + am) * factorial(l - am) / (m == 0 ? 2.0 : 1.0)) /
+                        (std::pow(2.0, am) * factorial(l));
+    const int twovm = m < 0 ? 1 : 0; // 2 v_m
+    for (int t = 0; 2 * t <= l - am; ++t)
+      for (int u = 0; u <= t; ++u)
+        for (int k = 0; 2 * k + twovm <= am; ++k) { // v = v_m + k
+          const int twov = 2 * k + twovm;
+          const double c = ((t + k) % 2 ? -1.0 : 1.0) * std::pow(0.25, t) * binomial(l, t) *
+                           binomial(l - t, am + t) * binomial(t, u) * binomial(am, twov);
+          const int lx = 2 * t + am - 2 * u - twov, ly = 2 * u + twov, lz = l - 2 * t - am;
+          if (lx < 0 || ly < 0 || lz < 0) continue;
+          M[static_cast<size_t>(m + l) * nc + cart_index(l, lx, ly)] += norm * c;
+        }
+  }
+}
+static const C2STable &c2s_table() {
+  static C2STable t;
+  static bool built = false;
+  if (!built) {
+    int off = 0;
+    for (int l = 0; l <= MAX_L; ++l) {
+      t.off[l] = off;
+      solid_harmonic_table(l, t.coef + off);
+      off += (2 * l + 1) * (l + 1) * (l + 2) / 2;
+    }
+    t.off[MAX_L + 1] = off;
+    built = true;
+  }
+  return t;
+}
+
+// value of every function of one shell at a point relative to its centre (host; used for the decay extents)
+static void shell_values_host(int l, int pure, int np, const double *coefs, const double *exps, double x, double y,
+                              double z, double *out) {
+  const double r2 = x * x + y * y + z * z;
+  double S0 = 0.0;
+  for (int k = 0; k < np; ++k) S0 += coefs[k] * std::exp(-exps[k] * r2);
+  const int nc = (l + 1) * (l + 2) / 2;
+  double cart[(MAX_L + 1) * (MAX_L + 2) / 2];
+  int idx = 0;
+  for (int lx = l; lx >= 0; --lx)
+    for (int ly = l - lx; ly >= 0; --ly) cart[idx++] = S0 * std::pow(x, lx) * std::pow(y, ly) * std::pow(z, l - lx - ly);
+  if (!pure || l == 0) {
+    for (int i = 0; i < nc; ++i) out[i] = cart[i];
+    return;
+  }
+  const C2STable &t = c2s_table();
+  for (int m = 0; m < 2 * l + 1; ++m) {
+    double v = 0.0;
+    for (int i = 0; i < nc; ++i) v += t.coef[t.off[l] + m * nc + i] * cart[i];
+    out[m] = v;
+  }
+}
+
+// gto::evaluate_decay_cutoff (src/gto/gto.cpp:18-67): first probe radius on the 0.1-Bohr ladder along +x where
+// every component of the shell is below the threshold.  The probe points are carried through the same
+// "pts += origin ... pts -= origin" shuttle as the reference, shell after shell.
+static int decay_cutoff_host(const occ_xc_basis_t *b, double threshold, double *extents) {
+  const double max_radius = 30.0, increment = 0.1, min_radius = 0.5;
+  const int npts = static_cast<int>((max_radius - min_radius) / increment) + 1;
+  std::vector<double> px(npts), py(npts, 0.0), pz(npts, 0.0);
+  const double step = (max_radius - min_radius) / (npts - 1);
+  for (int i = 0; i < npts; ++i) px[i] = (i == npts - 1) ? max_radius : min_radius + i * step;
+  // atom_to_shell order: shells grouped by atom, atoms ascending (shells are stored atom by atom)
+  std::vector<int> order(b->nsh);
+  std::iota(order.begin(), order.end(), 0);
+  if (b->shell_atom)
+    std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return b->shell_atom[a] < b->shell_atom[c]; });
+  double vals[2 * MAX_L + 1 > (MAX_L + 1) * (MAX_L + 2) / 2 ? 2 * MAX_L + 1 : (MAX_L + 1) * (MAX_L + 2) / 2];
+  for (int s : order) {
+    const double *o = b->origin + 3 * s;
+    const int l = b->l[s];
+    if (l > MAX_L) return fail("shell angular momentum above the supported maximum");
+    for (int i = 0; i < npts; ++i) {
+      px[i] += o[0];
+      py[i] += o[1];
+      pz[i] += o[2];
+    }
+    const int size = shell_size(l, b->pure);
+    const double fac = common_fac_host(l, b->pure);
+    for (int i = 0; i < npts; ++i) {
+      extents[s] = i * increment + min_radius;
+      shell_values_host(l, b->pure, b->nprim[s], b->coefs + b->prim_off[s], b->exps + b->prim_off[s], px[i] - o[0],
+                        py[i] - o[1], pz[i] - o[2], vals);
+      double v = 0.0;
+      for (int c = 0; c < size; ++c) v = std::max(v, std::fabs(vals[c] * fac));
+      if (v < threshold) break;
+    }
+    for (int i = 0; i < npts; ++i) {
+      px[i] -= o[0];
+      py[i] -= o[1];
+      pz[i] -= o[2];
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct Batch {
+  int tile0, ntiles, leaf0, nleaves;
+  size_t colloc_off, ncolloc, dens_off, ndens, g_off, ng, vxc_off, nvxc;
+};
+
+struct occ_xc_handle {
+  int device = 0;
+  int nbf = 0, nsh = 0, nspin = 1, deriv = 0, ncomp = 1, pure = 0;
+  size_t npts = 0;
+  int nleaves = 0, ntiles = 0;
+  double sum_n_nb2 = 0.0;
+  int nb_min = 0, nb_max = 0;
+  std::vector<Batch> batches;
+  std::vector<TileDesc> h_tiles;
+  std::vector<LeafDesc> h_leaves;
+  std::vector<size_t> leaf_global; // caller's leaf index of each local leaf
+  std::vector<int> h_bf_index;
+  BuildParams P;
+  std::vector<void *> allocs;
+  size_t alloc_bytes = 0;
+  CollocItem *d_colloc = nullptr;
+  DensItem *d_dens = nullptr, *d_g = nullptr;
+  VxcItem *d_vxc = nullptr;
+  double *d_D = nullptr, *d_Dsym = nullptr, *d_Ktmp = nullptr, *d_K = nullptr, *d_scalars = nullptr;
+  cudaStream_t stream = nullptr;
+  bool profiling = false;
+  double phase_ms[OCC_XC_NPHASES] = {0, 0, 0, 0, 0, 0};
+  size_t launches = 0;
+};
+
+template <class T> static int dev_alloc(occ_xc_handle *h, T **ptr, size_t count) {
+  void *p = nullptr;
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  CUDA_TRY(cudaMalloc(&p, bytes));
+  h->allocs.push_back(p);
+  h->alloc_bytes += bytes;
+  *ptr = static_cast<T *>(p);
+  return 0;
+}
+template <class T> static int dev_upload(occ_xc_handle *h, const T **ptr, const std::vector<T> &v) {
+  T *p = nullptr;
+  if (dev_alloc(h, &p, v.size())) return 1;
+  if (!v.empty()) CUDA_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *ptr = p;
+  return 0;
+}
+
+extern "C" {
+
+const char *occ_xc_last_error(void) { return g_last_error.c_str(); }
+int occ_xc_abi_version(void) { return OCC_XC_B200_ABI_VERSION; }
+int occ_xc_family(int id) { return xc_family_of(id); }
+double occ_xc_exact_exchange(int id) { return id == ID_HYB_GGA_XC_B3LYP ? 0.20 : 0.0; }
+
+int occ_xc_decay_cutoff(const occ_xc_basis_t *basis, double threshold, double *extents) {
+  if (!basis || !extents) return fail("occ_xc_decay_cutoff: null argument");
+  return decay_cutoff_host(basis, threshold, extents);
+}
+
+int occ_xc_eval_functional(int func_id, int polarized, size_t n, const double *rho, const double *sigma,
+                           const double *tau, double *exc, double *vrho, double *vsigma, double *vtau) {
+  const int rc = eval_functional_device(func_id, polarized, n, rho, sigma, tau, exc, vrho, vsigma, vtau);
+  if (rc == 1) return fail("functional with id = " + std::to_string(func_id) + " not found");
+  if (rc) return fail(std::string("CUDA error in occ_xc_eval_functional: ") + cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
+
+void occ_xc_destroy(occ_xc_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (void *p : h->allocs) cudaFree(p);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xyz, const double *weights,
+                  size_t nleaves_in, const occ_xc_leaf_t *leaves_in, const double *shell_extents, int nfunc,
+                  const int *func_ids, int nspin, double density_threshold, double screening_threshold,
+                  const occ_xc_options_t *opt, occ_xc_handle **out) {
+  if (!basis || !pts_xyz || !weights || !leaves_in || !func_ids || !out)
+    return fail("occ_xc_create: null argument");
+  if (nspin != 1 && nspin != 2) return fail("occ_xc_create: nspin must be 1 (restricted) or 2 (unrestricted)");
+  if (nfunc < 1 || nfunc > MAX_FUNC) return fail("occ_xc_create: between 1 and 4 functional components are supported");
+  int deriv = 0;
+  for (int f = 0; f < nfunc; ++f) {
+    const int fam = xc_family_of(func_ids[f]);
+    if (fam < 0) return fail("functional with id = " + std::to_string(func_ids[f]) + " not found");
+    deriv = std::max(deriv, fam); // DFT::density_derivative (src/dft/dft.cpp:11-17)
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("occ_xc_create: no CUDA device available (this library has no CPU fallback)");
+  int device = (opt && opt->device >= 0) ? opt->device : -1;
+  if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+  if (device >= ndev) return fail("occ_xc_create: device ordinal out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  const int world = (opt && opt->world_size > 1) ? opt->world_size : 1;
+  const int rank = world > 1 ? opt->rank : 0;
+  if (rank < 0 || rank >= world) return fail("occ_xc_create: rank outside [0, world_size)");
+  const size_t batch_bytes = (opt && opt->batch_bytes) ? opt->batch_bytes : (size_t(256) << 20);
+
+  const int nsh = basis->nsh, pure = basis->pure ? 1 : 0;
+  std::vector<int> first_bf(nsh);
+  int nbf = 0;
+  for (int s = 0; s < nsh; ++s) {
+    if (basis->l[s] < 0 || basis->l[s] > MAX_L) return fail("occ_xc_create: shell angular momentum outside 0..6");
+    first_bf[s] = nbf;
+    nbf += shell_size(basis->l[s], pure);
+  }
+  for (size_t l = 0; l < nleaves_in; ++l)
+    if (leaves_in[l].offset + leaves_in[l].count > npts) return fail("occ_xc_create: leaf exceeds the point array");
+
+  // ---- shell extents (dft.h:293-294) ----
+  const bool screen = screening_threshold > 0.0;
+  std::vector<double> extents(nsh, 0.0);
+  if (screen) {
+    if (shell_extents) std::copy(shell_extents, shell_extents + nsh, extents.begin());
+    else if (decay_cutoff_host(basis, screening_threshold, extents.data())) return 1;
+  }
+
+  // ---- significant shells per leaf (dft.h:313-335) ----
+  struct HostLeaf {
+    size_t src;
+    int sh_off, nshl, nb;
+    double cost;
+  };
+  std::vector<HostLeaf> hl;
+  std::vector<int> shell_list, shell_col;
+  for (size_t l = 0; l < nleaves_in; ++l) {
+    const occ_xc_leaf_t &lf = leaves_in[l];
+    if (lf.count == 0) continue;
+    HostLeaf e;
+    e.src = l;
+    e.sh_off = static_cast<int>(shell_list.size());
+    e.nb = 0;
+    for (int s = 0; s < nsh; ++s) {
+      bool keep = true;
+      if (screen) {
+        const double dx = basis->origin[3 * s] - lf.center[0], dy = basis->origin[3 * s + 1] - lf.center[1],
+                     dz = basis->origin[3 * s + 2] - lf.center[2];
+        const double dist = std::sqrt(dx * dx + dy * dy + dz * dz);
+        keep = dist - extents[s] < lf.radius;
+      }
+      if (keep) {
+        shell_list.push_back(s);
+        shell_col.push_back(e.nb);
+        e.nb += shell_size(basis->l[s], pure);
+      }
+    }
+    e.nshl = static_cast<int>(shell_list.size()) - e.sh_off;
+    if (e.nshl == 0) {
+      continue; // dft.h:320-321
+    }
+    e.cost = static_cast<double>(lf.count) * e.nb * e.nb;
+    hl.push_back(e);
+  }
+  // ---- shard: contiguous Morton runs of equal predicted cost (n * nb^2) ----
+  size_t l_lo = 0, l_hi = hl.size();
+  if (world > 1) {
+    double total = 0.0;
+    for (auto &e : hl) total += e.cost;
+    std::vector<size_t> cut(world + 1, hl.size());
+    cut[0] = 0;
+    double run = 0.0;
+    int r = 1;
+    for (size_t i = 0; i < hl.size() && r < world; ++i) {
+      run += hl[i].cost;
+      while (r < world && run >= total * r / world) cut[r++] = i + 1;
+    }
+    l_lo = cut[rank];
+    l_hi = cut[rank + 1];
+  }
+
+  occ_xc_handle *h = new occ_xc_handle();
+  h->device = device;
+  h->nbf = nbf;
+  h->nsh = nsh;
+  h->nspin = nspin;
+  h->deriv = deriv;
+  h->ncomp = deriv >= 1 ? 4 : 1;
+  h->pure = pure;
+  h->nb_min = 1 << 30;
+  h->nb_max = 0;
+  const int nslab = h->ncomp + nspin;
+
+  // ---- tiles, padded points, per-leaf index lists ----
+  std::vector<double> px, py, pz, pw;
+  std::vector<int> my_shell_list, my_shell_col;
+  for (size_t i = l_lo; i < l_hi; ++i) {
+    const HostLeaf &e = hl[i];
+    const occ_xc_leaf_t &lf = leaves_in[e.src];
+    LeafDesc ld;
+    ld.tile0 = static_cast<int>(h->h_tiles.size());
+    ld.ntiles = static_cast<int>((lf.count + TILE_P - 1) / TILE_P);
+    ld.nb = e.nb;
+    ld.pad = 0;
+    if (ld.ntiles > 2) {
+      delete h;
+      return fail("occ_xc_create: leaf with more than 256 points (max_leaf_size, spatial_grid_hierarchy.h:26-30)");
+    }
+    const int sh_off = static_cast<int>(my_shell_list.size());
+    const int bf_off = static_cast<int>(h->h_bf_index.size());
+    for (int k = 0; k < e.nshl; ++k) {
+      const int s = shell_list[e.sh_off + k];
+      my_shell_list.push_back(s);
+      my_shell_col.push_back(shell_col[e.sh_off + k]);
+      for (int c = 0; c < shell_size(basis->l[s], pure); ++c) h->h_bf_index.push_back(first_bf[s] + c);
+    }
+    const int nbp = (e.nb + NB_PAD - 1) / NB_PAD * NB_PAD;
+    for (int k = 0; k < ld.ntiles; ++k) {
+      TileDesc t;
+      t.leaf = static_cast<int>(h->h_leaves.size());
+      t.pt0 = static_cast<int>(h->h_tiles.size()) * TILE_P;
+      t.count = static_cast<int>(std::min<size_t>(TILE_P, lf.count - static_cast<size_t>(k) * TILE_P));
+      t.nb = e.nb;
+      t.nbp = nbp;
+      t.bf_off = bf_off;
+      t.sh_off = sh_off;
+      t.nsh = e.nshl;
+      t.scr_off = 0;
+      for (int p = 0; p < TILE_P; ++p) {
+        const bool valid = p < t.count;
+        const size_t src = lf.offset + static_cast<size_t>(k) * TILE_P + (valid ? p : 0);
+        px.push_back(pts_xyz[3 * src]);
+        py.push_back(pts_xyz[3 * src + 1]);
+        pz.push_back(pts_xyz[3 * src + 2]);
+        pw.push_back(valid ? weights[src] : 0.0);
+      }
+      h->h_tiles.push_back(t);
+    }
+    h->h_leaves.push_back(ld);
+    h->leaf_global.push_back(e.src);
+    h->npts += lf.count;
+    h->sum_n_nb2 += e.cost;
+    h->nb_min = std::min(h->nb_min, e.nb);
+    h->nb_max = std::max(h->nb_max, e.nb);
+  }
+  h->nleaves = static_cast<int>(h->h_leaves.size());
+  h->ntiles = static_cast<int>(h->h_tiles.size());
+  if (h->nleaves == 0) h->nb_min = 0;
+
+  // ---- batches of consecutive leaves under the workspace budget; per-phase work lists ----
+  std::vector<CollocItem> colloc;
+  std::vector<DensItem> dens, gitems;
+  std::vector<VxcItem> vxc;
+  size_t max_scratch = 0;
+  {
+    int leaf = 0;
+    while (leaf < h->nleaves) {
+      Batch b;
+      b.leaf0 = leaf;
+      b.tile0 = h->h_leaves[leaf].tile0;
+      size_t used = 0;
+      int nl = 0, nt = 0;
+      while (leaf + nl < h->nleaves) {
+        const LeafDesc &ld = h->h_leaves[leaf + nl];
+        const size_t need = static_cast<size_t>(ld.ntiles) * nslab * h->h_tiles[ld.tile0].nbp * TILE_P;
+        if (nl > 0 && (used + need) * sizeof(double) > batch_bytes) break;
+        for (int k = 0; k < ld.ntiles; ++k) {
+          h->h_tiles[ld.tile0 + k].scr_off = static_cast<long long>(used);
+          used += static_cast<size_t>(nslab) * h->h_tiles[ld.tile0 + k].nbp * TILE_P;
+        }
+        nt += ld.ntiles;
+        ++nl;
+      }
+      b.nleaves = nl;
+      b.ntiles = nt;
+      max_scratch = std::max(max_scratch, used);
+      // tiles of the batch, most expensive first (cost of one CTA of either contraction grows with nb)
+      std::vector<int> order(nt);
+      std::iota(order.begin(), order.end(), b.tile0);
+      std::stable_sort(order.begin(), order.end(),
+                       [&](int a, int c) { return h->h_tiles[a].nb > h->h_tiles[c].nb; });
+      b.colloc_off = colloc.size();
+      b.dens_off = dens.size();
+      b.g_off = gitems.size();
+      b.vxc_off = vxc.size();
+      for (int ti : order) {
+        const TileDesc &t = h->h_tiles[ti];
+        for (int s0 = 0; s0 < t.nsh; s0 += 16) {
+          CollocItem ci;
+          ci.tile = ti;
+          ci.s0 = s0;
+          ci.s1 = std::min(t.nsh, s0 + 16);
+          ci.last = ci.s1 == t.nsh;
+          colloc.push_back(ci);
+        }
+        const int njb = t.nbp / 64;
+        const int nac = deriv >= 2 ? 4 : 1;
+        for (int sp = 0; sp < nspin; ++sp)
+          for (int ac = 0; ac < nac; ++ac)
+            for (int jb = 0; jb < njb; ++jb) {
+              DensItem di;
+              di.tile = ti;
+              di.jb = static_cast<short>(jb);
+              di.spin = static_cast<signed char>(sp);
+              di.acomp = static_cast<signed char>(ac);
+              dens.push_back(di);
+              VxcItem vi;
+              vi.tile = ti;
+              vi.jb = static_cast<short>(jb);
+              vi.spin = static_cast<signed char>(sp);
+              vi.acomp = static_cast<signed char>(ac);
+              vxc.push_back(vi);
+            }
+        for (int jb = 0; jb < njb; ++jb) {
+          DensItem gi;
+          gi.tile = ti;
+          gi.jb = static_cast<short>(jb);
+          gi.spin = 0;
+          gi.acomp = 0;
+          gitems.push_back(gi);
+        }
+      }
+      b.ncolloc = colloc.size() - b.colloc_off;
+      b.ndens = dens.size() - b.dens_off;
+      b.ng = gitems.size() - b.g_off;
+      b.nvxc = vxc.size() - b.vxc_off;
+      h->batches.push_back(b);
+      leaf += nl;
+    }
+  }
+
+  // ---- upload ----
+  BuildParams &P = h->P;
+  std::memset(&P, 0, sizeof(P));
+  {
+    std::vector<int> vl(basis->l, basis->l + nsh), vnp(basis->nprim, basis->nprim + nsh),
+        vpo(basis->prim_off, basis->prim_off + nsh);
+    size_t nprim_total = 0;
+    for (int s = 0; s < nsh; ++s) nprim_total = std::max<size_t>(nprim_total, size_t(basis->prim_off[s]) + basis->nprim[s]);
+    std::vector<double> vo(basis->origin, basis->origin + 3 * nsh), ve(basis->exps, basis->exps + nprim_total),
+        vc(basis->coefs, basis->coefs + nprim_total);
+    int rc = 0;
+    rc |= dev_upload(h, &P.basis.l, vl);
+    rc |= dev_upload(h, &P.basis.nprim, vnp);
+    rc |= dev_upload(h, &P.basis.prim_off, vpo);
+    rc |= dev_upload(h, &P.basis.first_bf, first_bf);
+    rc |= dev_upload(h, &P.basis.origin, vo);
+    rc |= dev_upload(h, &P.basis.exps, ve);
+    rc |= dev_upload(h, &P.basis.coefs, vc);
+    P.basis.pure = pure;
+    rc |= dev_upload(h, &P.tiles, h->h_tiles);
+    rc |= dev_upload(h, &P.leaves, h->h_leaves);
+    rc |= dev_upload(h, &P.shell_list, my_shell_list);
+    rc |= dev_upload(h, &P.shell_col, my_shell_col);
+    rc |= dev_upload(h, &P.bf_index, h->h_bf_index);
+    rc |= dev_upload(h, &P.px, px);
+    rc |= dev_upload(h, &P.py, py);
+    rc |= dev_upload(h, &P.pz, pz);
+    rc |= dev_upload(h, &P.pw, pw);
+    const CollocItem *dc = nullptr;
+    const DensItem *dd = nullptr, *dg = nullptr;
+    const VxcItem *dv = nullptr;
+    rc |= dev_upload(h, &dc, colloc);
+    rc |= dev_upload(h, &dd, dens);
+    rc |= dev_upload(h, &dg, gitems);
+    rc |= dev_upload(h, &dv, vxc);
+    h->d_colloc = const_cast<CollocItem *>(dc);
+    h->d_dens = const_cast<DensItem *>(dd);
+    h->d_g = const_cast<DensItem *>(dg);
+    h->d_vxc = const_cast<VxcItem *>(dv);
+    const size_t nt = std::max(h->ntiles, 1);
+    const size_t ksz = static_cast<size_t>(nspin) * nbf * nbf;
+    rc |= dev_alloc(h, &P.scratch, max_scratch);
+    rc |= dev_alloc(h, &P.acc, nt * nspin * NACC * TILE_P);
+    rc |= dev_alloc(h, &P.coef, nt * nspin * NCOEF * TILE_P);
+    rc |= dev_alloc(h, &P.leaf_skip, std::max(h->nleaves, 1));
+    rc |= dev_alloc(h, &P.leaf_sums, 3 * static_cast<size_t>(std::max(h->nleaves, 1)));
+    rc |= dev_alloc(h, &h->d_D, ksz);
+    rc |= dev_alloc(h, &h->d_Dsym, nspin == 1 ? ksz : 1);
+    rc |= dev_alloc(h, &h->d_Ktmp, ksz);
+    rc |= dev_alloc(h, &h->d_K, ksz);
+    rc |= dev_alloc(h, &h->d_scalars, 4);
+    if (rc) {
+      occ_xc_destroy(h);
+      return 1;
+    }
+  }
+  upload_c2s_table(c2s_table());
+  P.ldD = nspin * nbf;
+  P.nbf = nbf;
+  P.nspin = nspin;
+  P.deriv = deriv;
+  P.ncomp = h->ncomp;
+  P.nfunc = nfunc;
+  for (int f = 0; f < nfunc; ++f) P.func_ids[f] = func_ids[f];
+  P.density_threshold = density_threshold;
+  for (int s = 0; s < nspin; ++s) P.Ktmp[s] = h->d_Ktmp + static_cast<size_t>(s) * nbf;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    occ_xc_destroy(h);
+    return fail("occ_xc_create: cudaStreamCreate failed");
+  }
+  h->launches = 0;
+  for (const Batch &b : h->batches)
+    h->launches += (b.ncolloc > 0) + (b.ndens > 0) + (b.nleaves > 0) + (b.ng > 0) + (b.nvxc > 0);
+  h->launches += 2 + (nspin == 1 ? 1 : 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    occ_xc_destroy(h);
+    return fail(std::string("occ_xc_create: ") + cudaGetErrorString(e));
+  }
+  *out = h;
+  return 0;
+}
+
+int occ_xc_build_device(occ_xc_handle *h, const double *D2_dev, double *K_dev, double *scalars_dev,
+                        void *cuda_stream) {
+  if (!h || !D2_dev || !K_dev || !scalars_dev) return fail("occ_xc_build_device: null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
+  BuildParams P = h->P;
+  const size_t ksz = static_cast<size_t>(h->nspin) * h->nbf * h->nbf;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  const bool prof = h->profiling;
+  float ms = 0.f;
+  if (prof) {
+    CUDA_TRY(cudaEventCreate(&ev[0]));
+    CUDA_TRY(cudaEventCreate(&ev[1]));
+    for (double &x : h->phase_ms) x = 0.0;
+  }
+#define PHASE_BEGIN() do { if (prof) cudaEventRecord(ev[0], st); } while (0)
+#define PHASE_END(k) do { if (prof) { cudaEventRecord(ev[1], st); cudaEventSynchronize(ev[1]); \
+    cudaEventElapsedTime(&ms, ev[0], ev[1]); h->phase_ms[k] += ms; } } while (0)
+
+  PHASE_BEGIN();
+  if (h->nspin == 1) {
+    launch_prepare_density(D2_dev, h->d_Dsym, h->nbf, 1, st);
+    P.Drho[0] = h->d_Dsym;
+    P.Dtau[0] = D2_dev;
+  } else {
+    for (int s = 0; s < 2; ++s) P.Drho[s] = P.Dtau[s] = D2_dev + static_cast<size_t>(s) * h->nbf;
+  }
+  CUDA_TRY(cudaMemsetAsync(h->d_Ktmp, 0, ksz * sizeof(double), st));
+  PHASE_END(0);
+  for (const Batch &b : h->batches) {
+    PHASE_BEGIN();
+    launch_collocate(P, h->d_colloc + b.colloc_off, static_cast<int>(b.ncolloc), st);
+    PHASE_END(1);
+    PHASE_BEGIN();
+    CUDA_TRY(cudaMemsetAsync(P.acc + static_cast<size_t>(b.tile0) * h->nspin * NACC * TILE_P, 0,
+                             static_cast<size_t>(b.ntiles) * h->nspin * NACC * TILE_P * sizeof(double), st));
+    launch_density(P, h->d_dens + b.dens_off, static_cast<int>(b.ndens), st);
+    PHASE_END(2);
+    PHASE_BEGIN();
+    launch_functional(P, b.leaf0, b.nleaves, st);
+    PHASE_END(3);
+    PHASE_BEGIN();
+    launch_gbuild(P, h->d_g + b.g_off, static_cast<int>(b.ng), st);
+    launch_vxc(P, h->d_vxc + b.vxc_off, static_cast<int>(b.nvxc), st);
+    PHASE_END(4);
+  }
+  PHASE_BEGIN();
+  launch_finalize(P, h->nleaves, K_dev, scalars_dev, st);
+  PHASE_END(5);
+#undef PHASE_BEGIN
+#undef PHASE_END
+  if (prof) {
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int occ_xc_build(occ_xc_handle *h, const double *D2, double *K, double *exc, double *n_alpha, double *n_beta) {
+  if (!h || !D2 || !K) return fail("occ_xc_build: null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t ksz = static_cast<size_t>(h->nspin) * h->nbf * h->nbf;
+  CUDA_TRY(cudaMemcpyAsync(h->d_D, D2, ksz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (occ_xc_build_device(h, h->d_D, h->d_K, h->d_scalars, h->stream)) return 1;
+  CUDA_TRY(cudaMemcpyAsync(K, h->d_K, ksz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  double sc[3];
+  CUDA_TRY(cudaMemcpyAsync(sc, h->d_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (exc) *exc = sc[0];
+  if (n_alpha) *n_alpha = sc[1];
+  if (n_beta) *n_beta = sc[2];
+  return 0;
+}
+
+int occ_xc_get_info(const occ_xc_handle *h, occ_xc_info_t *info) {
+  if (!h || !info) return fail("occ_xc_get_info: null argument");
+  info->nbf = h->nbf;
+  info->nspin = h->nspin;
+  info->deriv = h->deriv;
+  info->nsh = h->nsh;
+  info->npts = h->npts;
+  info->nleaves = static_cast<size_t>(h->nleaves);
+  info->ntiles = static_cast<size_t>(h->ntiles);
+  info->nbatches = h->batches.size();
+  info->sum_n_nb2 = h->sum_n_nb2;
+  info->flops_per_build = (h->deriv >= 2 ? 16.0 : 4.0) * h->nspin * h->sum_n_nb2;
+  info->nb_min = h->nb_min;
+  info->nb_max = h->nb_max;
+  info->workspace_bytes = h->alloc_bytes;
+  info->launches_per_build = h->launches;
+  return 0;
+}
+
+int occ_xc_set_profiling(occ_xc_handle *h, int on) {
+  if (!h) return fail("occ_xc_set_profiling: null handle");
+  h->profiling = on != 0;
+  return 0;
+}
+int occ_xc_get_phase_ms(occ_xc_handle *h, double *ms) {
+  if (!h || !ms) return fail("occ_xc_get_phase_ms: null argument");
+  for (int k = 0; k < OCC_XC_NPHASES; ++k) ms[k] = h->phase_ms[k];
+  return 0;
+}
+
+int occ_xc_leaf_collocation(occ_xc_handle *h, size_t leaf, int deriv, int *nb_out, double *phi, double *phi_x,
+                            double *phi_y, double *phi_z, size_t capacity) {
+  if (!h || !nb_out || !phi) return fail("occ_xc_leaf_collocation: null argument");
+  int li = -1;
+  for (size_t i = 0; i < h->leaf_global.size(); ++i)
+    if (h->leaf_global[i] == leaf) li = static_cast<int>(i);
+  if (li < 0) return fail("occ_xc_leaf_collocation: leaf is empty, screened out, or not on this shard");
+  if (deriv > 0 && h->ncomp < 4) return fail("occ_xc_leaf_collocation: handle was created without AO gradients");
+  if (deriv > 0 && (!phi_x || !phi_y || !phi_z)) return fail("occ_xc_leaf_collocation: null gradient buffer");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const LeafDesc &ld = h->h_leaves[li];
+  size_t count = 0;
+  for (int k = 0; k < ld.ntiles; ++k) count += h->h_tiles[ld.tile0 + k].count;
+  *nb_out = ld.nb;
+  if (capacity < count * ld.nb) return fail("occ_xc_leaf_collocation: output capacity too small");
+  std::vector<CollocItem> items;
+  for (int k = 0; k < ld.ntiles; ++k) {
+    const TileDesc &t = h->h_tiles[ld.tile0 + k];
+    for (int s0 = 0; s0 < t.nsh; s0 += 16)
+      items.push_back({ld.tile0 + k, s0, std::min(t.nsh, s0 + 16), std::min(t.nsh, s0 + 16) == t.nsh});
+  }
+  CollocItem *d_items = nullptr;
+  CUDA_TRY(cudaMalloc(&d_items, items.size() * sizeof(CollocItem)));
+  CUDA_TRY(cudaMemcpy(d_items, items.data(), items.size() * sizeof(CollocItem), cudaMemcpyHostToDevice));
+  launch_collocate(h->P, d_items, static_cast<int>(items.size()), h->stream);
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  cudaFree(d_items);
+  double *outs[4] = {phi, phi_x, phi_y, phi_z};
+  std::vector<double> buf;
+  size_t row0 = 0;
+  for (int k = 0; k < ld.ntiles; ++k) {
+    const TileDesc &t = h->h_tiles[ld.tile0 + k];
+    const size_t slab = static_cast<size_t>(t.nbp) * TILE_P;
+    buf.resize(slab);
+    for (int c = 0; c < (deriv > 0 ? 4 : 1); ++c) {
+      CUDA_TRY(cudaMemcpy(buf.data(), h->P.scratch + t.scr_off + c * slab, slab * sizeof(double),
+                          cudaMemcpyDeviceToHost));
+      for (int j = 0; j < t.nb; ++j)
+        for (int p = 0; p < t.count; ++p) outs[c][static_cast<size_t>(j) * count + row0 + p] = buf[j * TILE_P + p];
+    }
+    row0 += t.count;
+  }
+  return 0;
+}
+
+} // extern "C"

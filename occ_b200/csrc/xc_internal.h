@@ -1,0 +1,112 @@
+// xc_internal.h — device-side data layout of the B200 XC build (shared by the host orchestration and the kernels).
+//
+// Work decomposition (all of it geometry-only, built once in occ_xc_create):
+//   leaf   = one Morton leaf of the reference's SpatialGridHierarchy (the semantic unit: shell list, density skip)
+//   tile   = <=128 points of one leaf (every leaf but the last is exactly one tile)
+//   batch  = a run of consecutive leaves whose AO-value workspace fits the batch budget; the four phase
+//            kernels (collocate -> density -> functional -> vxc) are launched once per batch
+// AO values of a tile live in the batch workspace as NCOMP column-major (128 x nbp) slabs
+//   phi_c[col * 128 + p],  c = 0 value, 1..3 d/dx,d/dy,d/dz;  nbp = nb rounded up to 64, padding columns zero.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace xcb {
+
+constexpr int TILE_P = 128; // points per tile (the reference's leaf size, spatial_grid_hierarchy.h:26-30)
+constexpr int NB_PAD = 64;  // local basis functions padded to a multiple of this
+constexpr int MAX_L = 6;
+constexpr int MAX_FUNC = 4;
+
+struct TileDesc {
+  int leaf;          // local leaf index
+  int pt0;           // first padded point slot (= tile * 128)
+  int count;         // valid points
+  int nb, nbp;       // local basis functions, padded
+  int bf_off;        // offset of the leaf's local->global bf map in bf_index[]
+  int sh_off, nsh;   // the leaf's significant shells in shell_list[] / shell_col[]
+  long long scr_off; // offset (doubles) of phi_0 in the batch workspace; phi_c at scr_off + c * nbp * 128
+};
+
+struct LeafDesc {
+  int tile0, ntiles; // tiles of this leaf
+  int nb;
+  int pad;
+};
+
+// one CTA of the collocation kernel: shells [s0, s1) of the tile's list; `last` also zeroes padding columns
+struct CollocItem {
+  int tile;
+  int s0, s1;
+  int last;
+};
+// one CTA of the density kernel: X(:, 64*jb..) = phi_acomp . D_spin, row-dotted with the AO slabs
+struct DensItem {
+  int tile;
+  short jb;
+  signed char spin, acomp;
+};
+// one CTA of the Vxc kernel: Ktmp[:, 64*jb..] += phi_acomp^T . B_jb
+struct VxcItem {
+  int tile;
+  short jb;
+  signed char spin, acomp;
+};
+
+struct DeviceBasis {
+  const int *l;          // [nsh]
+  const int *nprim;      // [nsh]
+  const int *prim_off;   // [nsh]
+  const int *first_bf;   // [nsh]
+  const double *origin;  // [3*nsh]
+  const double *exps;
+  const double *coefs;
+  int pure;
+};
+
+// per-point accumulators written by the density kernel, read by the functional kernel: [tile][spin][NACC][128]
+constexpr int NACC = 5; // rho, 2 x (drho/dx,dy,dz)/2 ... stored raw: sum phi X, sum phi_x X, .., sum_d phi_d (phi_d D)
+// per-point Vxc coefficients written by the functional kernel: [tile][spin][NCOEF][128]
+constexpr int NCOEF = 5; // c0 (phi), cx, cy, cz (grad phi), ct (tau term)
+
+struct BuildParams {
+  DeviceBasis basis;
+  const TileDesc *tiles;
+  const LeafDesc *leaves;
+  const int *shell_list; // CSR per leaf: global shell index
+  const int *shell_col;  // CSR per leaf: first local column of that shell
+  const int *bf_index;   // CSR per leaf: local column -> global basis function
+  const double *px, *py, *pz, *pw; // [ntiles*128] padded SoA points / weights (w = 0 in padding)
+  double *scratch;       // batch workspace
+  double *acc;           // [ntiles][nspin][NACC][128]
+  double *coef;          // [ntiles][nspin][NCOEF][128]
+  int *leaf_skip;        // [nleaves] 1 = leaf failed the density threshold (dft_kernels.cpp:38-40)
+  double *leaf_sums;     // [nleaves][3] exc, n_alpha, n_beta
+  const double *Drho[2]; // density matrices for the phi.D product (restricted: upper-symmetrised copy)
+  const double *Dtau[2]; // for the tau products (restricted: D as given, density.cpp:90-96)
+  double *Ktmp[2];       // accumulation target, K = Ktmp + Ktmp^T at the end
+  int ldD;               // leading dimension of D / K = nspin * nbf
+  int nbf, nspin, deriv, ncomp;
+  int nfunc;
+  int func_ids[MAX_FUNC];
+  double density_threshold;
+};
+
+// spherical transform tables (real solid harmonics, CCA order m = -l..l) in constant memory
+struct C2STable {
+  // coef[off[l] + m * ncart(l) + c]
+  int off[MAX_L + 2];
+  double coef[1 + 9 + 30 + 70 + 135 + 231 + 364];
+};
+
+void launch_collocate(const BuildParams &P, const CollocItem *items, int nitems, void *stream);
+void launch_density(const BuildParams &P, const DensItem *items, int nitems, void *stream);
+void launch_functional(const BuildParams &P, int leaf0, int nleaves, void *stream);
+void launch_vxc(const BuildParams &P, const VxcItem *items, int nitems, void *stream);
+void launch_prepare_density(const double *D2, double *Dsym, int nbf, int nspin, void *stream);
+void launch_finalize(const BuildParams &P, int nleaves, double *K, double *scalars, void *stream);
+void upload_c2s_table(const C2STable &t);
+int eval_functional_device(int func_id, int polarized, size_t n, const double *rho, const double *sigma,
+                           const double *tau, double *exc, double *vrho, double *vsigma, double *vtau);
+
+} // namespace xcb

@@ -1,0 +1,192 @@
+"""Host-side mirror of occ::dft::DFT for the exchange-correlation build (reference: include/occ/dft/dft.h:36-763).
+
+Same names and argument meaning as the reference's interface for this path:
+  DFT(method, basis, grid, spinorbital_kind)   ~ DFT::DFT (src/dft/dft.cpp:19-35) + set_integration_grid + set_method
+  DFT.compute_K_dft(D)                         ~ DFT::compute_K_dft<deriv, kind>(mo, Schwarz) (dft.h:190-388); takes mo.D
+  DFT.compute_vxc(D)                           ~ DFT::compute_vxc (dft.h:395-429)
+  DFT.exchange_correlation_energy()            ~ m_exc_dft
+  DFT.density_derivative(), exact_exchange_factor(), set_density_threshold ... as in the reference
+All arithmetic runs in the CUDA library behind the C ABI (include/occ_xc_b200.h); PyTorch is used only for device
+buffers / streams in the device-resident entry (build_device) and torch.distributed for the multi-GPU sum.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import LEAF_DTYPE, BasisArrays, InfoT, OptionsT, check, lib, ptr
+from .aobasis import AOBasis
+
+FUNCTIONAL_IDS = {"lda_x": 1, "lda_c_vwn": 7, "lda_c_vwn_rpa": 8, "lda_c_vwn_3": 30, "gga_x_pbe": 101,
+                  "gga_x_b88": 106, "gga_c_pbe": 130, "gga_c_lyp": 131, "hyb_gga_xc_b3lyp": 402,
+                  "mgga_x_r2scan": 497, "mgga_c_r2scan": 498}
+
+# src/dft/dft_method.cpp:14-37 (builtin_definitions), restricted to components this library implements
+METHOD_DEFINITIONS = {
+    "b3lyp": ["hyb_gga_xc_b3lyp"],
+    "pbe": ["gga_x_pbe", "gga_c_pbe"],
+    "pbepbe": ["gga_x_pbe", "gga_c_pbe"],
+    "svwn": ["lda_x", "lda_c_vwn_3"],
+    "lda": ["lda_x", "lda_c_vwn_3"],
+    "lsda": ["lda_x", "lda_c_vwn_3"],
+    "svwn5": ["lda_x", "lda_c_vwn"],
+    "blyp": ["gga_x_b88", "gga_c_lyp"],
+    "bpbe": ["gga_x_b88", "gga_c_pbe"],
+    "r2scan": ["mgga_x_r2scan", "mgga_c_r2scan"],
+}
+
+RESTRICTED, UNRESTRICTED = "restricted", "unrestricted"
+
+
+def get_dft_method(method_string: str) -> list[int]:
+    """get_dft_method (src/dft/dft_method.cpp:161-227): space-separated tokens, each a method name or a libxc
+    functional name; a leading 'u' marks the polarized variant (the spin kind is chosen by the caller here)."""
+    ids = []
+    for token in method_string.strip().lower().split():
+        m = token[1:] if token.startswith("u") and token[1:] in METHOD_DEFINITIONS else token
+        if m in METHOD_DEFINITIONS:
+            ids += [FUNCTIONAL_IDS[c] for c in METHOD_DEFINITIONS[m]]
+        elif m in FUNCTIONAL_IDS:
+            ids.append(FUNCTIONAL_IDS[m])
+        else:
+            raise RuntimeError(f"functional {m} not found")  # functional.cpp:32 analogue
+    return ids
+
+
+@dataclass
+class GridHierarchy:
+    """SpatialGridHierarchy (include/occ/numint/spatial_grid_hierarchy.h:33-78): Morton-sorted points/weights + leaves."""
+    sorted_points: np.ndarray    # (npts, 3) C-order == Mat3N column-major
+    sorted_weights: np.ndarray   # (npts,)
+    leaves: np.ndarray           # LEAF_DTYPE
+
+    @property
+    def num_leaves(self):
+        return len(self.leaves)
+
+
+class DFT:
+    def __init__(self, method: str, basis: AOBasis, grid: GridHierarchy, spinorbital_kind: str = RESTRICTED,
+                 device: int = -1, rank: int = 0, world_size: int = 1, batch_bytes: int = 0,
+                 density_threshold: float = 1e-10, xc_screening_threshold: float = 1e-10, shell_extents=None):
+        self.basis = basis
+        self.method = method
+        self.func_ids = np.array(get_dft_method(method), dtype=np.int32)
+        self.nspin = 2 if spinorbital_kind == UNRESTRICTED else 1
+        self.nbf = basis.nbf
+        self._basis_arrays = BasisArrays(basis.as_arrays())
+        pts = np.ascontiguousarray(grid.sorted_points, dtype=np.float64).reshape(-1, 3)
+        w = np.ascontiguousarray(grid.sorted_weights, dtype=np.float64)
+        leaves = np.ascontiguousarray(grid.leaves, dtype=LEAF_DTYPE)
+        ext = None if shell_extents is None else np.ascontiguousarray(shell_extents, dtype=np.float64)
+        opt = OptionsT(device, rank, world_size, batch_bytes)
+        self._h = C.c_void_p()
+        check(lib().occ_xc_create(self._basis_arrays.ref, C.c_size_t(len(w)), ptr(pts), ptr(w), C.c_size_t(len(leaves)),
+                                  ptr(leaves), ptr(ext) if ext is not None else None, C.c_int(len(self.func_ids)),
+                                  ptr(self.func_ids), C.c_int(self.nspin), C.c_double(density_threshold),
+                                  C.c_double(xc_screening_threshold), C.byref(opt), C.byref(self._h)))
+        self.rank, self.world_size = rank, world_size
+        self.m_exc_dft = 0.0
+        self.total_density = (0.0, 0.0)
+
+    # ---- reference-named accessors ----
+    def density_derivative(self) -> int:
+        return max(lib().occ_xc_family(int(f)) for f in self.func_ids)
+
+    def exact_exchange_factor(self) -> float:
+        return float(sum(lib().occ_xc_exact_exchange(int(f)) for f in self.func_ids))
+
+    def exchange_correlation_energy(self) -> float:
+        return self.m_exc_dft
+
+    def info(self) -> dict:
+        i = InfoT()
+        check(lib().occ_xc_get_info(self._h, C.byref(i)))
+        return {f: getattr(i, f) for f, _ in InfoT._fields_}
+
+    # ---- the hot path ----
+    def compute_K_dft(self, D: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """D = mo.D, (nspin*nbf, nbf); returns K like the reference (the caller negates: jk.K = -compute_vxc)."""
+        D2 = np.asfortranarray(2.0 * np.asarray(D, dtype=np.float64))  # dft.h:205
+        return self.build(D2, out)
+
+    compute_vxc = compute_K_dft
+
+    def build(self, D2: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """occ_xc_build: D2 already doubled, column-major host buffers."""
+        n = self.nspin * self.nbf
+        D2 = np.asfortranarray(D2, dtype=np.float64)
+        if D2.shape != (n, self.nbf):
+            raise RuntimeError(f"density matrix has shape {D2.shape}, expected {(n, self.nbf)}")
+        K = out if out is not None else np.zeros((n, self.nbf), order="F")
+        exc, na, nb = C.c_double(), C.c_double(), C.c_double()
+        check(lib().occ_xc_build(self._h, ptr(D2), ptr(K), C.byref(exc), C.byref(na), C.byref(nb)))
+        self.m_exc_dft = exc.value
+        self.total_density = (na.value, nb.value)
+        return K
+
+    def build_raw(self, d2_ptr: int, k_ptr: int):
+        """occ_xc_build on raw host pointers (pinned buffers owned by the caller); returns (exc, n_alpha, n_beta)."""
+        exc, na, nb = C.c_double(), C.c_double(), C.c_double()
+        check(lib().occ_xc_build(self._h, C.c_void_p(d2_ptr), C.c_void_p(k_ptr), C.byref(exc), C.byref(na),
+                                 C.byref(nb)))
+        return exc.value, na.value, nb.value
+
+    def build_device(self, d2_dev_ptr: int, k_dev_ptr: int, scalars_dev_ptr: int, stream: int = 0):
+        """occ_xc_build_device: everything resident in HBM, asynchronous on `stream` (a cudaStream_t value)."""
+        check(lib().occ_xc_build_device(self._h, C.c_void_p(d2_dev_ptr), C.c_void_p(k_dev_ptr),
+                                        C.c_void_p(scalars_dev_ptr), C.c_void_p(stream)))
+
+    def set_profiling(self, on: bool):
+        check(lib().occ_xc_set_profiling(self._h, C.c_int(int(on))))
+
+    def phase_ms(self) -> dict:
+        ms = (C.c_double * _lib.NPHASES)()
+        check(lib().occ_xc_get_phase_ms(self._h, ms))
+        return dict(zip(_lib.PHASE_NAMES, list(ms)))
+
+    def leaf_collocation(self, leaf: int, count: int, deriv: int = 1):
+        cap = count * self.nbf
+        outs = [np.zeros(cap) for _ in range(4 if deriv else 1)]
+        nb = C.c_int()
+        check(lib().occ_xc_leaf_collocation(self._h, C.c_size_t(leaf), C.c_int(deriv), C.byref(nb), ptr(outs[0]),
+                                            ptr(outs[1]) if deriv else None, ptr(outs[2]) if deriv else None,
+                                            ptr(outs[3]) if deriv else None, C.c_size_t(cap)))
+        return [o[:count * nb.value].reshape(nb.value, count).T for o in outs]
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().occ_xc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def decay_cutoff(basis: AOBasis, threshold: float = 1e-10) -> np.ndarray:
+    """gto::evaluate_decay_cutoff (src/gto/gto.cpp:18-67)"""
+    ba = BasisArrays(basis.as_arrays())
+    ext = np.zeros(basis.nsh)
+    check(lib().occ_xc_decay_cutoff(ba.ref, C.c_double(threshold), ptr(ext)))
+    return ext
+
+
+def eval_functional(func, polarized: bool, rho, sigma=None, tau=None) -> dict:
+    """DensityFunctional::evaluate (src/dft/functional.cpp:18-65) on libxc-layout arrays, on the GPU."""
+    fid = FUNCTIONAL_IDS[func] if isinstance(func, str) else int(func)
+    s = 2 if polarized else 1
+    rho = np.ascontiguousarray(rho, dtype=np.float64).ravel()
+    n = rho.size // s
+    ns = 3 if polarized else 1
+    sigma = np.ascontiguousarray(sigma if sigma is not None else np.zeros(n * ns), dtype=np.float64).ravel()
+    tau = np.ascontiguousarray(tau if tau is not None else np.zeros(n * s), dtype=np.float64).ravel()
+    exc, vrho, vsigma, vtau = np.zeros(n), np.zeros(n * s), np.zeros(n * ns), np.zeros(n * s)
+    check(lib().occ_xc_eval_functional(C.c_int(fid), C.c_int(int(polarized)), C.c_size_t(n), ptr(rho), ptr(sigma),
+                                       ptr(tau), ptr(exc), ptr(vrho), ptr(vsigma), ptr(vtau)))
+    return {"exc": exc, "vrho": vrho.reshape(n, s), "vsigma": vsigma.reshape(n, ns), "vtau": vtau.reshape(n, s)}
