@@ -130,8 +130,43 @@ int occ_xc_eval_functional(int func_id, int polarized, size_t n, const double *r
 int occ_xc_leaf_collocation(occ_xc_handle *h, size_t leaf, int deriv, int *nb, double *phi, double *phi_x,
                             double *phi_y, double *phi_z, size_t capacity_doubles);
 
+/* The leaf -> rank map occ_xc_create applies for a given world_size (pure host code, no device needed):
+ * leaf_rank[l] = owning rank, or -1 for leaves that are empty or keep no shell (dft.h:309-321);
+ * leaf_nb[l] (may be NULL) = nbf_local of the leaf under the screening rule of dft.h:313-320. */
+int occ_xc_partition_leaves(const occ_xc_basis_t *basis, size_t nleaves, const occ_xc_leaf_t *leaves,
+                            const double *shell_extents, double screening_threshold, int world_size,
+                            int *leaf_rank, int *leaf_nb);
+
 int occ_xc_family(int func_id);          /* 0 LDA, 1 GGA, 2 meta-GGA, -1 unknown (DensityFunctional::family) */
 double occ_xc_exact_exchange(int func_id); /* DensityFunctional::exact_exchange_factor (functional.h:557-579) */
+
+/* ---- once-per-geometry input producers (not on the per-iteration clock) --------------------------------
+ * occ::numint::MolecularGrid + MolecularGridPoints + SpatialGridHierarchy
+ * (src/numint/molecular_grid.cpp:11-131,183-256; src/numint/grid_utils.cpp:149-200,234-274,398-514,576-758;
+ *  src/numint/spatial_grid_hierarchy.cpp:40-147).  LMG radial grids, NWChem pruning, Lebedev shells, Becke
+ * weights with Treutler-Ahlrichs adjustment (a CUDA kernel), Morton-ordered leaves of 128 points. */
+typedef struct {
+  int max_angular_points;  /* GridSettings defaults (include/occ/numint/grid_settings.h:81-95): 302 */
+  int min_angular_points;  /* 110 */
+  double radial_precision; /* 1e-12 */
+  int reduced_first_row_element_grid; /* 1 */
+  int treutler_alrichs_adjustment;    /* 1 */
+} occ_xc_grid_settings_t;
+typedef struct occ_xc_grid occ_xc_grid;
+/* Lebedev-Laikov tables are data (src/numint/lebedev.cpp): rows of x, y, z, w; register each order once */
+int occ_xc_register_lebedev(int npoints, const double *xyzw);
+int occ_xc_grid_create(int natoms, const int *atomic_numbers, const double *positions_bohr /* 3*natoms */,
+                       const occ_xc_basis_t *basis, const occ_xc_grid_settings_t *settings, occ_xc_grid **out);
+/* SpatialGridHierarchy over caller-supplied points/weights (any order) */
+int occ_xc_grid_from_points(size_t npts, const double *pts_xyz, const double *weights, occ_xc_grid **out);
+size_t occ_xc_grid_npts(const occ_xc_grid *g);
+size_t occ_xc_grid_nleaves(const occ_xc_grid *g);
+int occ_xc_grid_atom_info(const occ_xc_grid *g, int atom, size_t *npts, int *nradial);
+/* any output may be NULL: Morton-sorted points (3 x npts) / weights, leaves, the sort permutation
+ * (sorted[i] = original[perm[i]]), and the atom-ordered points / weights */
+int occ_xc_grid_copy(const occ_xc_grid *g, double *sorted_pts, double *sorted_w, occ_xc_leaf_t *leaves, size_t *perm,
+                     double *pts, double *w);
+void occ_xc_grid_destroy(occ_xc_grid *g);
 
 void occ_xc_destroy(occ_xc_handle *h);
 const char *occ_xc_last_error(void);

@@ -15,8 +15,9 @@ LIB_PATH = os.path.join(HERE, "libocc_xc_b200.so")
 # every symbol include/occ_xc_b200.h declares
 SYMBOLS = ["occ_xc_create", "occ_xc_build", "occ_xc_build_device", "occ_xc_get_info", "occ_xc_set_profiling",
            "occ_xc_get_phase_ms", "occ_xc_decay_cutoff", "occ_xc_eval_functional", "occ_xc_leaf_collocation",
-           "occ_xc_family", "occ_xc_exact_exchange", "occ_xc_destroy", "occ_xc_last_error", "occ_xc_abi_version"
-           ]
+           "occ_xc_family", "occ_xc_exact_exchange", "occ_xc_destroy", "occ_xc_last_error", "occ_xc_abi_version",
+           "occ_xc_partition_leaves", "occ_xc_register_lebedev", "occ_xc_grid_create", "occ_xc_grid_from_points", "occ_xc_grid_npts",
+           "occ_xc_grid_nleaves", "occ_xc_grid_atom_info", "occ_xc_grid_copy", "occ_xc_grid_destroy"]
 
 
 class BasisT(C.Structure):
@@ -38,6 +39,11 @@ class InfoT(C.Structure):
                 ("nleaves", C.c_size_t), ("ntiles", C.c_size_t), ("nbatches", C.c_size_t), ("sum_n_nb2", C.c_double),
                 ("flops_per_build", C.c_double), ("nb_min", C.c_int), ("nb_max", C.c_int),
                 ("workspace_bytes", C.c_size_t), ("launches_per_build", C.c_size_t)]
+
+
+class GridSettingsT(C.Structure):
+    _fields_ = [("max_angular_points", C.c_int), ("min_angular_points", C.c_int), ("radial_precision", C.c_double),
+                ("reduced_first_row_element_grid", C.c_int), ("treutler_alrichs_adjustment", C.c_int)]
 
 
 LEAF_DTYPE = np.dtype([("offset", np.uint64), ("count", np.uint64), ("center", np.float64, 3), ("radius", np.float64)])
@@ -64,8 +70,25 @@ def lib():
         L.occ_xc_get_info.argtypes = [C.c_void_p, C.c_void_p]
         L.occ_xc_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.occ_xc_get_phase_ms.argtypes = [C.c_void_p, C.c_void_p]
+        L.occ_xc_grid_npts.restype = C.c_size_t
+        L.occ_xc_grid_nleaves.restype = C.c_size_t
+        L.occ_xc_grid_npts.argtypes = [C.c_void_p]
+        L.occ_xc_grid_nleaves.argtypes = [C.c_void_p]
+        L.occ_xc_grid_destroy.restype = None
+        L.occ_xc_grid_destroy.argtypes = [C.c_void_p]
+        L.occ_xc_grid_copy.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        L.occ_xc_grid_atom_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        tables = np.load(os.path.join(HERE, "data", "lebedev_tables.npz"))
+        for k in tables.files:
+            a = np.ascontiguousarray(tables[k], dtype=np.float64)
+            check_rc(L, L.occ_xc_register_lebedev(C.c_int(a.shape[0]), a.ctypes.data_as(C.c_void_p)))
         _lib = L
     return _lib
+
+
+def check_rc(L, rc: int):
+    if rc != 0:
+        raise RuntimeError(L.occ_xc_last_error().decode())
 
 
 def check(rc: int):

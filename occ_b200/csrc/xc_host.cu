@@ -28,6 +28,7 @@ static int fail(const std::string &msg) {
   g_last_error = msg;
   return 1;
 }
+int occ_xc_set_error(const char *msg) { return fail(msg); } // shared with grid.cu
 #define CUDA_TRY(expr)                                                                                       \
   do {                                                                                                       \
     cudaError_t e__ = (expr);                                                                                \
@@ -164,6 +165,22 @@ static int decay_cutoff_host(const occ_xc_basis_t *b, double threshold, double *
   return 0;
 }
 
+// cut[r] .. cut[r+1] = the run of (non-empty, unscreened) leaves rank r owns: prefix sums of the predicted
+// cost split at multiples of total/world, so every rank gets a Morton-contiguous, spatially compact shard
+static std::vector<size_t> partition_by_cost(const std::vector<double> &costs, int world) {
+  double total = 0.0;
+  for (double c : costs) total += c;
+  std::vector<size_t> cut(world + 1, costs.size());
+  cut[0] = 0;
+  double run = 0.0;
+  int r = 1;
+  for (size_t i = 0; i < costs.size() && r < world; ++i) {
+    run += costs[i];
+    while (r < world && run >= total * r / world) cut[r++] = i + 1;
+  }
+  return cut;
+}
+
 // ------------------------------------------------------------------------------------------------
 struct Batch {
   int tile0, ntiles, leaf0, nleaves;
@@ -222,6 +239,42 @@ double occ_xc_exact_exchange(int id) { return id == ID_HYB_GGA_XC_B3LYP ? 0.20 :
 int occ_xc_decay_cutoff(const occ_xc_basis_t *basis, double threshold, double *extents) {
   if (!basis || !extents) return fail("occ_xc_decay_cutoff: null argument");
   return decay_cutoff_host(basis, threshold, extents);
+}
+
+int occ_xc_partition_leaves(const occ_xc_basis_t *basis, size_t nleaves, const occ_xc_leaf_t *leaves,
+                            const double *shell_extents, double screening_threshold, int world_size,
+                            int *leaf_rank, int *leaf_nb) {
+  if (!basis || !leaves || !leaf_rank) return fail("occ_xc_partition_leaves: null argument");
+  if (world_size < 1) return fail("occ_xc_partition_leaves: world_size must be positive");
+  const int nsh = basis->nsh, pure = basis->pure ? 1 : 0;
+  const bool screen = screening_threshold > 0.0;
+  std::vector<double> extents(nsh, 0.0);
+  if (screen) {
+    if (shell_extents) std::copy(shell_extents, shell_extents + nsh, extents.begin());
+    else if (decay_cutoff_host(basis, screening_threshold, extents.data())) return 1;
+  }
+  std::vector<double> costs;
+  std::vector<size_t> src;
+  for (size_t l = 0; l < nleaves; ++l) {
+    leaf_rank[l] = -1;
+    int nb = 0;
+    if (leaves[l].count > 0)
+      for (int s = 0; s < nsh; ++s) {
+        const double dx = basis->origin[3 * s] - leaves[l].center[0], dy = basis->origin[3 * s + 1] - leaves[l].center[1],
+                     dz = basis->origin[3 * s + 2] - leaves[l].center[2];
+        if (!screen || std::sqrt(dx * dx + dy * dy + dz * dz) - extents[s] < leaves[l].radius)
+          nb += shell_size(basis->l[s], pure);
+      }
+    if (leaf_nb) leaf_nb[l] = nb;
+    if (nb > 0) {
+      costs.push_back(static_cast<double>(leaves[l].count) * nb * nb);
+      src.push_back(l);
+    }
+  }
+  const std::vector<size_t> cut = partition_by_cost(costs, world_size);
+  for (int r = 0; r < world_size; ++r)
+    for (size_t i = cut[r]; i < cut[r + 1]; ++i) leaf_rank[src[i]] = r;
+  return 0;
 }
 
 int occ_xc_eval_functional(int func_id, int polarized, size_t n, const double *rho, const double *sigma,
@@ -324,16 +377,9 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
   // ---- shard: contiguous Morton runs of equal predicted cost (n * nb^2) ----
   size_t l_lo = 0, l_hi = hl.size();
   if (world > 1) {
-    double total = 0.0;
-    for (auto &e : hl) total += e.cost;
-    std::vector<size_t> cut(world + 1, hl.size());
-    cut[0] = 0;
-    double run = 0.0;
-    int r = 1;
-    for (size_t i = 0; i < hl.size() && r < world; ++i) {
-      run += hl[i].cost;
-      while (r < world && run >= total * r / world) cut[r++] = i + 1;
-    }
+    std::vector<double> costs(hl.size());
+    for (size_t i = 0; i < hl.size(); ++i) costs[i] = hl[i].cost;
+    std::vector<size_t> cut = partition_by_cost(costs, world);
     l_lo = cut[rank];
     l_hi = cut[rank + 1];
   }

@@ -190,3 +190,17 @@ def eval_functional(func, polarized: bool, rho, sigma=None, tau=None) -> dict:
     check(lib().occ_xc_eval_functional(C.c_int(fid), C.c_int(int(polarized)), C.c_size_t(n), ptr(rho), ptr(sigma),
                                        ptr(tau), ptr(exc), ptr(vrho), ptr(vsigma), ptr(vtau)))
     return {"exc": exc, "vrho": vrho.reshape(n, s), "vsigma": vsigma.reshape(n, ns), "vtau": vtau.reshape(n, s)}
+
+
+def partition_leaves(basis: AOBasis, leaves: np.ndarray, world_size: int, screening_threshold: float = 1e-10,
+                     shell_extents=None):
+    """Leaf -> rank map of the multi-GPU build (occ_xc_partition_leaves; host only). Returns (leaf_rank, leaf_nb)."""
+    ba = BasisArrays(basis.as_arrays())
+    leaves = np.ascontiguousarray(leaves, dtype=LEAF_DTYPE)
+    rank = np.zeros(len(leaves), dtype=np.int32)
+    nb = np.zeros(len(leaves), dtype=np.int32)
+    ext = None if shell_extents is None else np.ascontiguousarray(shell_extents, dtype=np.float64)
+    check(lib().occ_xc_partition_leaves(ba.ref, C.c_size_t(len(leaves)), ptr(leaves),
+                                        ptr(ext) if ext is not None else None, C.c_double(screening_threshold),
+                                        C.c_int(world_size), ptr(rank), ptr(nb)))
+    return rank, nb

@@ -1,0 +1,71 @@
+"""Multi-GPU XC build: grid leaves sharded over ranks, density matrix replicated, partial K / Exc / N summed.
+
+Reference analogue: the thread-local accumulators of DFT::compute_K_dft and their serial reduction
+(include/occ/dft/dft.h:221-232,375-380) — here one process per GPU (torch.distributed, NCCL over NVLink) instead of
+TBB threads, and ONE all-reduce of the packed buffer [K | exc, n_alpha, n_beta] instead of nthreads matrix adds.
+The partition itself (contiguous Morton runs of equal predicted cost n*nb^2) lives in the native library
+(occ_xc_create, options.rank / world_size).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .dft import DFT, RESTRICTED, UNRESTRICTED, GridHierarchy
+
+
+def pack_len(nspin: int, nbf: int) -> int:
+    """K (nspin*nbf x nbf, column-major) followed by exc, n_alpha, n_beta and one pad double"""
+    return nspin * nbf * nbf + 4
+
+
+def allreduce_partial(buf: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum the packed partial results over ranks (NCCL on device tensors, gloo on CPU tensors in the tests)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return buf
+
+
+def unpack(buf: torch.Tensor, nspin: int, nbf: int):
+    n = nspin * nbf * nbf
+    K = buf[:n].view(nbf, nspin * nbf).t()  # column-major (nspin*nbf, nbf) seen as a strided view
+    return K, buf[n:n + 3]
+
+
+class DistributedDFT:
+    """One DFT handle per rank on its own GPU; build() leaves the SUMMED packed result on every rank's device."""
+
+    def __init__(self, method: str, basis, grid: GridHierarchy, spinorbital_kind: str = RESTRICTED, group=None,
+                 device: int | None = None, **kw):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = torch.cuda.current_device() if device is None else device
+        self.dft = DFT(method, basis, grid, spinorbital_kind, device=self.device, rank=self.rank,
+                       world_size=self.world, **kw)
+        self.nspin, self.nbf = self.dft.nspin, self.dft.nbf
+        dev = torch.device("cuda", self.device)
+        self.d_D = torch.empty(self.nspin * self.nbf * self.nbf, dtype=torch.float64, device=dev)
+        self.d_out = torch.zeros(pack_len(self.nspin, self.nbf), dtype=torch.float64, device=dev)
+
+    def build_device(self, stream: torch.cuda.Stream | None = None) -> torch.Tensor:
+        """D already in self.d_D (column-major). Returns the packed, all-reduced device buffer."""
+        st = stream or torch.cuda.current_stream(self.device)
+        n = self.nspin * self.nbf * self.nbf
+        self.dft.build_device(self.d_D.data_ptr(), self.d_out.data_ptr(), self.d_out.data_ptr() + 8 * n, st.cuda_stream)
+        with torch.cuda.stream(st):
+            allreduce_partial(self.d_out, self.group)
+        return self.d_out
+
+    def build(self, D2_host: torch.Tensor, K_host: torch.Tensor):
+        """Host-to-host build: D2_host / K_host are (pinned) CPU tensors holding column-major matrices."""
+        n = self.nspin * self.nbf * self.nbf
+        self.d_D.copy_(D2_host.view(-1), non_blocking=True)
+        out = self.build_device()
+        K_host.view(-1)[:n].copy_(out[:n], non_blocking=True)
+        sc = out[n:n + 3].cpu()
+        return float(sc[0]), float(sc[1]), float(sc[2])
+
+    def close(self):
+        self.dft.close()

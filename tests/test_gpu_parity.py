@@ -1,0 +1,260 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and with the committed golden vectors.
+North-star tolerances: Exc within 1e-8 Eh, Vxc within 1e-9 max-abs (floating point; stated in every assert)."""
+import os
+
+import numpy as np
+import pytest
+
+from occ_b200 import aobasis, dft, grid, molecules
+
+pytestmark = pytest.mark.gpu
+
+TOL_VXC = 1e-9   # max-abs, Hartree
+TOL_EXC = 1e-8   # Hartree
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "xc_golden.npz")
+
+
+def _names(method, O):
+    return [n for i in dft.get_dft_method(method) for n, v in O.FUNC_IDS.items() if v == i]
+
+
+def _build_both(c, method, nspin, O, D2=None, **kw):
+    b = c["basis"]
+    D2 = molecules.synthetic_density(b, nspin) if D2 is None else D2
+    d = dft.DFT(method, b, dft.GridHierarchy(c["spts"], c["sw"], c["leaves"]),
+                dft.UNRESTRICTED if nspin == 2 else dft.RESTRICTED, **kw)
+    K = d.build(D2)
+    res = {"K": K, "exc": d.exchange_correlation_energy(), "n": d.total_density, "info": d.info()}
+    d.close()
+    thr = kw.get("xc_screening_threshold", 1e-10)
+    ref = O.xc_build(c["obasis"], c["spts"], c["sw"], c["leaves"], _names(method, O), nspin, D2,
+                     screening_threshold=thr, density_threshold=kw.get("density_threshold", 1e-10))
+    return res, ref
+
+
+def _assert_parity(res, ref):
+    assert np.abs(res["K"] - ref["K"]).max() < TOL_VXC
+    assert abs(res["exc"] - ref["exc"]) < TOL_EXC
+    assert abs(res["n"][0] - ref["n_alpha"]) < 1e-9 and abs(res["n"][1] - ref["n_beta"]) < 1e-9
+
+
+@pytest.mark.parametrize("method", ["svwn", "svwn5", "pbe", "blyp", "b3lyp", "bpbe", "r2scan", "lda_c_vwn_rpa"])
+@pytest.mark.parametrize("nspin", [1, 2])
+def test_water_every_functional_restricted_and_unrestricted(case, oracle, method, nspin):
+    res, ref = _build_both(case("water", "def2-svp"), method, nspin, oracle)
+    _assert_parity(res, ref)
+    assert res["info"]["sum_n_nb2"] == ref["stats"]["sum_n_nb2"]     # same shell lists as dft.h:313-320
+
+
+@pytest.mark.parametrize("mol,bas,method,nspin,pure", [
+    ("water", "def2-svp", "pbe", 1, True),
+    ("water", "def2-qzvp", "pbe", 1, True),        # g functions
+    ("water", "def2-qzvp", "b3lyp", 2, False),
+    ("benzene", "def2-tzvp", "pbe", 1, False),     # BASELINE configs[1]
+    ("benzene", "def2-tzvp", "r2scan", 2, True),
+    ("water_isolated", "3-21g", "blyp", 1, True),
+])
+def test_molecule_matrix(case, oracle, mol, bas, method, nspin, pure):
+    res, ref = _build_both(case(mol, bas, pure), method, nspin, oracle)
+    _assert_parity(res, ref)
+    assert res["info"]["nb_max"] == ref["stats"]["nb_max"] and res["info"]["nb_min"] == ref["stats"]["nb_min"]
+
+
+def test_golden_vectors(case):
+    g = np.load(GOLD)
+    for key in [k[:-2] for k in g.files if k.endswith("_K") and not k.startswith("fx_")]:
+        mol, bas, method, nspin, pure = key.rsplit("_", 4)
+        mol = "_".join(key.split("_")[:-4])
+        c = case(mol, bas, bool(int(pure)))
+        b = c["basis"]
+        D2 = molecules.synthetic_density(b, int(nspin))
+        # inputs from the PRODUCT's own grid producer: the golden outputs then also pin occ_b200.grid
+        h = grid.MolecularGrid(b).hierarchy()
+        d = dft.DFT(method, b, h, dft.UNRESTRICTED if int(nspin) == 2 else dft.RESTRICTED)
+        K = d.build(D2)
+        sc = g[key + "_scalars"]
+        assert len(h.sorted_weights) == int(sc[3])
+        assert abs(h.sorted_weights.sum() - sc[4]) < 1e-9 * abs(sc[4])
+        assert np.abs(K - g[key + "_K"]).max() < TOL_VXC
+        assert abs(d.exchange_correlation_energy() - sc[0]) < TOL_EXC
+        assert abs(d.total_density[0] - sc[1]) < 1e-9
+        d.close()
+
+
+def test_pointwise_functionals_against_golden_and_reference_kat():
+    g = np.load(GOLD)
+    # the reference's own known answers (tests/dft_tests.cpp:71-111), 1e-6 as there
+    r = dft.eval_functional("gga_x_pbe", False, g["pbe_x_kat_rho"], (g["pbe_x_kat_grad"] ** 2).sum(1))
+    assert np.abs(r["exc"] - g["pbe_x_kat_exc"]).max() < 1e-6
+    rho, sig, tau = g["fx_rho"], g["fx_sigma"], g["fx_tau"]
+    for name in dft.FUNCTIONAL_IDS:
+        u = dft.eval_functional(name, False, rho.sum(1), sig[:, 0] + 2 * sig[:, 1] + sig[:, 2], tau.sum(1))
+        p = dft.eval_functional(name, True, rho, sig, tau)
+        for got, ref in ((u, g[f"fx_{name}_u"]), (p, g[f"fx_{name}_p"])):
+            cat = np.concatenate([got["exc"][:, None], got["vrho"], got["vsigma"], got["vtau"]], 1)
+            assert np.allclose(cat, ref, rtol=1e-11, atol=1e-13), name
+    with pytest.raises(RuntimeError):
+        dft.eval_functional(424242, False, np.ones(3))
+
+
+def test_collocation_against_oracle_and_reference_gau2grid(case, oracle):
+    c = case("benzene", "def2-tzvp", True)
+    b = c["basis"]
+    d = dft.DFT("pbe", b, dft.GridHierarchy(c["spts"], c["sw"], c["leaves"]))
+    ext = oracle.decay_cutoff(c["obasis"])
+    import ctypes
+    for li in (0, len(c["leaves"]) // 2, len(c["leaves"]) - 1):   # includes the ragged last leaf
+        lf = c["leaves"][li]
+        cnt, off = int(lf["count"]), int(lf["offset"])
+        phis = d.leaf_collocation(li, cnt, deriv=1)
+        leaf_t = oracle.LeafT(off, cnt, (ctypes.c_double * 3)(*lf["center"]), float(lf["radius"]))
+        buf = np.zeros(b.nsh, dtype=np.int32)
+        n = oracle.lib().orc_leaf_shell_list(c["obasis"].ref, ext.ctypes.data_as(ctypes.c_void_p), ctypes.byref(leaf_t),
+                                             buf.ctypes.data_as(ctypes.c_void_p))
+        col = 0
+        pts = c["spts"][off:off + cnt]
+        for s in buf[:n]:
+            sh = b.shells[s]
+            fac = oracle.lib().orc_common_fac(int(sh.l), 1)
+            ref = oracle.collocate_shell(sh.l, 1, pts, sh.coefficients, sh.exponents, sh.origin, 1)
+            width = 2 * sh.l + 1
+            for k in range(4):
+                got = phis[k][:, col:col + width]
+                want = ref[k].T * fac
+                assert np.abs(got - want).max() <= 1e-13 * max(1.0, np.abs(want).max())
+            if oracle.ref_lib() is not None:   # the reference's own gau2grid, when oracle/_ref travelled
+                gg = oracle.ref_collocate_shell(sh.l, 1, pts, sh.coefficients, sh.exponents, sh.origin, 1)
+                for k in range(4):
+                    assert np.abs(phis[k][:, col:col + width] - gg[k].T * fac).max() <= 1e-13 * max(1.0, np.abs(gg[k]).max())
+            col += width
+        assert col == phis[0].shape[1]
+    d.close()
+
+
+def test_product_grid_producer_matches_oracle(case):
+    """occ_b200.grid (host C++ + CUDA Becke kernel) vs the oracle's restatement of MolecularGrid / SpatialGridHierarchy"""
+    for mol, bas in (("water", "def2-svp"), ("benzene", "def2-tzvp")):
+        c = case(mol, bas)
+        mg = grid.MolecularGrid(c["basis"])
+        pts, w = mg.points()
+        assert pts.shape == c["pts"].shape
+        assert np.array_equal(pts, c["pts"])                                   # same arithmetic on the host
+        assert np.abs(w - c["w"]).max() <= 1e-13 * np.abs(c["w"]).max()        # Becke weights: GPU vs CPU
+        h, perm = mg.hierarchy(with_permutation=True)
+        assert np.array_equal(perm, c["perm"])
+        assert np.array_equal(h.sorted_points, c["spts"])
+        assert np.array_equal(h.leaves["count"], c["leaves"]["count"])
+        assert np.allclose(h.leaves["center"], c["leaves"]["center"], atol=1e-13)
+        assert np.allclose(h.leaves["radius"], c["leaves"]["radius"], atol=1e-13)
+        for a in range(len(c["Z"])):
+            assert mg.atom_info(a) == (c["info"]["atom_npts"][a], c["info"]["atom_nradial"][a])
+
+
+def test_veryfine_grid_size_from_product_grid():
+    Z, pos = molecules.water_isolated_xc()
+    b = aobasis.AOBasis.load(Z, pos, "3-21g", pure=True)
+    mg = grid.MolecularGrid(b, grid.GridSettings.from_grid_quality("veryfine"))
+    assert mg.num_points() == 38652            # tests/isolated_xc_tests.cpp:271
+
+
+def test_edge_cases(case, oracle):
+    c = case("water", "def2-svp")
+    b = c["basis"]
+    # (1) dense path: screening off keeps every shell in every leaf (OCC_XC_NO_SCREEN analogue)
+    res, ref = _build_both(c, "pbe", 1, oracle, xc_screening_threshold=0.0)
+    _assert_parity(res, ref)
+    assert res["info"]["nb_min"] == b.nbf
+    # (2) screened == dense to 1e-8 (the reference's own check, tests/dft_tests.cpp:904-931)
+    res_s, _ = _build_both(c, "pbe", 1, oracle)
+    assert np.abs(res_s["K"] - res["K"]).max() < 1e-8
+    # (3) a density threshold so high that every leaf is skipped: K = 0, Exc = 0, but N_el is still counted
+    res, ref = _build_both(c, "pbe", 1, oracle, density_threshold=1e6)
+    assert np.abs(res["K"]).max() == 0.0 and res["exc"] == 0.0 and ref["exc"] == 0.0
+    assert abs(res["n"][0] - ref["n_alpha"]) < 1e-9 and res["n"][0] > 1.0
+    # (4) zero density matrix
+    res, ref = _build_both(c, "b3lyp", 2, oracle, D2=np.zeros((2 * b.nbf, b.nbf), order="F"))
+    assert np.abs(res["K"]).max() == 0.0 and res["exc"] == 0.0
+    # (5) non-symmetric D: restricted builds read the upper triangle only (density.cpp:14,38,78)
+    D2 = molecules.synthetic_density(b, 1)
+    Dl = D2.copy(order="F")
+    Dl[np.tril_indices(b.nbf, -1)] += 0.37
+    res, ref = _build_both(c, "pbe", 1, oracle, D2=Dl)
+    _assert_parity(res, ref)
+    res0, _ = _build_both(c, "pbe", 1, oracle, D2=D2)
+    assert np.abs(res["K"] - res0["K"]).max() < 1e-12
+    # (6) unrestricted with a non-symmetric D uses D as given (density.cpp:45-70)
+    D2u = molecules.synthetic_density(b, 2)
+    D2u[:b.nbf][np.triu_indices(b.nbf, 1)] *= 1.01
+    res, ref = _build_both(c, "pbe", 2, oracle, D2=np.asfortranarray(D2u))
+    _assert_parity(res, ref)
+    # (7) empty leaves and a single ragged leaf
+    leaves = np.concatenate([c["leaves"][:3], np.zeros(1, dtype=c["leaves"].dtype), c["leaves"][-1:]])
+    d = dft.DFT("pbe", b, dft.GridHierarchy(c["spts"], c["sw"], leaves))
+    K = d.build(D2)
+    ref = oracle.xc_build(c["obasis"], c["spts"], c["sw"], leaves, ["gga_x_pbe", "gga_c_pbe"], 1, D2)
+    assert np.abs(K - ref["K"]).max() < TOL_VXC and abs(d.exchange_correlation_energy() - ref["exc"]) < TOL_EXC
+    d.close()
+    # (8) errors surface as exceptions with the library's message
+    with pytest.raises(RuntimeError):
+        dft.DFT("pbe", b, dft.GridHierarchy(c["spts"][:10], c["sw"][:10], c["leaves"]))
+    with pytest.raises(RuntimeError):
+        d2 = dft.DFT("pbe", b, dft.GridHierarchy(c["spts"], c["sw"], c["leaves"]))
+        d2.build(np.zeros((3, 3)))
+
+
+def test_batching_and_sharding_do_not_change_the_result(case, oracle):
+    c = case("benzene", "def2-tzvp")
+    b = c["basis"]
+    D2 = molecules.synthetic_density(b, 1)
+    h = dft.GridHierarchy(c["spts"], c["sw"], c["leaves"])
+    d = dft.DFT("b3lyp", b, h)
+    K0, e0, n0 = d.build(D2).copy(), d.exchange_correlation_energy(), d.total_density[0]
+    d.close()
+    d = dft.DFT("b3lyp", b, h, batch_bytes=8 << 20)
+    assert d.info()["nbatches"] > 10
+    K1 = d.build(D2)
+    assert np.abs(K1 - K0).max() < 1e-12 and abs(d.exchange_correlation_energy() - e0) < 1e-12
+    d.close()
+    # 4 shards on one device: the partial results must sum to the whole (what the NCCL all-reduce does)
+    Ks, es, ns, npts = np.zeros_like(K0), 0.0, 0.0, 0
+    for r in range(4):
+        d = dft.DFT("b3lyp", b, h, rank=r, world_size=4)
+        Ks += d.build(D2)
+        es += d.exchange_correlation_energy()
+        ns += d.total_density[0]
+        npts += d.info()["npts"]
+        d.close()
+    assert npts == len(c["sw"])
+    assert np.abs(Ks - K0).max() < 1e-12 and abs(es - e0) < 1e-12 and abs(ns - n0) < 1e-12
+    # repeatability: same handle, same input -> same output to round-off of the atomic scatter order
+    d = dft.DFT("b3lyp", b, h)
+    Ka = d.build(D2).copy()
+    Kb = d.build(D2)
+    assert np.abs(Ka - Kb).max() < 1e-13
+    assert np.abs(Ka - Ka.T).max() == 0.0      # K = Ktmp + Ktmp^T exactly symmetric
+    d.close()
+
+
+def test_size_independent_properties_at_full_size():
+    """(H2O)32 B3LYP/def2-SVP UKS (BASELINE configs[2], 965 504 points) without the oracle: electron count is linear in
+    D, alpha = beta input gives alpha = beta output and equals the restricted build, K is symmetric."""
+    Z, pos = molecules.water_cluster_32()
+    b = aobasis.AOBasis.load(Z, pos, "def2-svp")
+    h = grid.MolecularGrid(b).hierarchy()
+    assert len(h.sorted_weights) == 965504
+    P = molecules.synthetic_density(b, 1)
+    dr = dft.DFT("b3lyp", b, h)
+    Kr = dr.build(P).copy()
+    er, nr = dr.exchange_correlation_energy(), dr.total_density[0]
+    Kr2 = dr.build(np.asfortranarray(2.0 * P))
+    assert abs(dr.total_density[0] - 2.0 * nr) < 1e-9 * nr          # linearity of the electron count
+    dr.close()
+    du = dft.DFT("b3lyp", b, h, dft.UNRESTRICTED)
+    Ku = du.build(np.asfortranarray(np.vstack([0.5 * P, 0.5 * P])))
+    nbf = b.nbf
+    assert np.abs(Ku[:nbf] - Ku[nbf:]).max() < 1e-12
+    assert np.abs(Ku[:nbf] - Kr).max() < TOL_VXC                     # UKS(zeta = 0) == RKS
+    assert abs(du.exchange_correlation_energy() - er) < TOL_EXC
+    assert abs(du.total_density[0] + du.total_density[1] - nr) < 1e-9
+    assert np.abs(Kr - Kr.T).max() == 0.0
+    du.close()

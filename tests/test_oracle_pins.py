@@ -1,0 +1,221 @@
+"""Pins of the CPU oracle (test infrastructure) against everything the reference offers for this path:
+its own gau2grid compiled into oracle/_ref, the PBE-x known-answer test of tests/dft_tests.cpp:71-111, the grid size
+quoted at tests/isolated_xc_tests.cpp:271, the Lebedev tables produced by its lebedev.cpp, and the Morton-hierarchy
+invariants of tests/dft_tests.cpp:1287-1462."""
+import os
+
+import numpy as np
+import pytest
+
+from occ_b200 import aobasis, molecules
+
+
+# ---------------------------------------------------------------- collocation vs the reference's gau2grid
+@pytest.mark.parametrize("pure", [0, 1])
+@pytest.mark.parametrize("l", [0, 1, 2, 3, 4])
+def test_collocation_matches_reference_gau2grid(oracle, l, pure):
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref/libocc_ref.so not built (needs /root/reference)")
+    rng = np.random.default_rng(100 + l)
+    pts = rng.normal(size=(67, 3)) * 1.5
+    exps = np.array([4.1, 1.3, 0.35])
+    coefs = rng.normal(size=3)
+    center = np.array([0.1, -0.2, 0.3])
+    for deriv in (0, 1):
+        ours = oracle.collocate_shell(l, pure, pts, coefs, exps, center, deriv)
+        ref = oracle.ref_collocate_shell(l, pure, pts, coefs, exps, center, deriv)
+        for a, b in zip(ours, ref):
+            scale = max(1.0, np.abs(b).max())
+            assert np.abs(a - b).max() <= 2e-14 * scale
+
+
+def test_shell_normalisation_matches_host_mirror(oracle):
+    """src/gto/shell.cpp:20-64,180-186 restated twice (oracle C++, occ_b200.aobasis Python)"""
+    exps = np.array([130.70932, 23.808861, 6.4436083])
+    c = np.array([0.15432897, 0.53532814, 0.44463454])
+    for l in range(4):
+        a = oracle.incorporate_shell_norm(l, exps, c)
+        b = aobasis.incorporate_shell_norm(l, exps, c)
+        assert np.allclose(a, b, rtol=1e-14, atol=0)
+
+
+# ---------------------------------------------------------------- functionals
+def test_pbe_exchange_known_answers(oracle):
+    """tests/dft_tests.cpp:71-111 (restricted): exc of gga_x_pbe at four (rho, grad rho) points, 1e-6"""
+    rho = np.array([0.030097001731591706, 0.030097001731591706, 0.15085916775597902, 0.17751228531944346])
+    grad = np.array([[-0.063735860841572081, 0.0, 0.018656553309952275], [-0.063735860841572081, 0.0, 0.018656553309952275],
+                     [0.0, 0.0, 0.13035149660035189], [0.0, 0.0, 0.078426011080503066]])
+    sigma = (grad ** 2).sum(1)
+    r = oracle.xc_eval("gga_x_pbe", False, rho, sigma)
+    expected = np.array([-0.27851489, -0.27851489, -0.39899553, -0.41654061])
+    assert np.abs(r["exc"] - expected).max() < 1e-6
+
+
+FUNCS = ["lda_x", "lda_c_vwn", "lda_c_vwn_rpa", "lda_c_vwn_3", "gga_x_pbe", "gga_x_b88", "gga_c_pbe", "gga_c_lyp",
+         "hyb_gga_xc_b3lyp", "mgga_x_r2scan", "mgga_c_r2scan"]
+
+
+def _sample(n, seed, polarized):
+    rng = np.random.default_rng(seed)
+    s = 2 if polarized else 1
+    rho = 10 ** rng.uniform(-3, 0.5, size=(n, s))
+    g = rng.normal(size=(n, s, 3))
+    g *= (rng.uniform(0.3, 2.0, size=(n, s)) * rho ** (4 / 3) / np.linalg.norm(g, axis=2))[..., None]
+    if polarized:
+        sigma = np.stack([(g[:, 0] ** 2).sum(1), (g[:, 0] * g[:, 1]).sum(1), (g[:, 1] ** 2).sum(1)], 1)
+    else:
+        sigma = (g[:, 0] ** 2).sum(1)[:, None]
+    # tau above the von Weizsaecker bound so the Fermi-hole clamp is inactive
+    tw = np.stack([(g[:, k] ** 2).sum(1) / (8 * rho[:, k]) for k in range(s)], 1)
+    tau = tw * (1.0 + rng.uniform(0.05, 3.0, size=(n, s)))
+    return rho, sigma, tau
+
+
+@pytest.mark.parametrize("func", FUNCS)
+def test_potentials_are_derivatives_of_the_energy_density(oracle, func):
+    """vrho/vsigma/vtau vs central finite differences of rho*exc (unpolarized) — the potentials are not pinned by
+    any reference test, so they are secured against the pinned energies"""
+    rho, sigma, tau = _sample(40, 7, False)
+    r0 = oracle.xc_eval(func, False, rho, sigma, tau)
+    fam = r0["family"]
+
+    def F(rh, sg, ta):
+        return oracle.xc_eval(func, False, rh, sg, ta)["exc"] * rh[:, 0]
+
+    h = 1e-5
+    d = (F(rho * (1 + h), sigma, tau) - F(rho * (1 - h), sigma, tau)) / (2 * h * rho[:, 0])
+    assert np.allclose(d, r0["vrho"][:, 0], rtol=2e-6, atol=1e-9)
+    if fam >= 1:
+        d = (F(rho, sigma * (1 + h), tau) - F(rho, sigma * (1 - h), tau)) / (2 * h * sigma[:, 0])
+        assert np.allclose(d, r0["vsigma"][:, 0], rtol=2e-5, atol=1e-9)
+    if fam >= 2:
+        d = (F(rho, sigma, tau * (1 + h)) - F(rho, sigma, tau * (1 - h))) / (2 * h * tau[:, 0])
+        assert np.allclose(d, r0["vtau"][:, 0], rtol=2e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("func", FUNCS)
+def test_polarized_at_zero_polarisation_equals_unpolarized(oracle, func):
+    rho, sigma, tau = _sample(40, 11, False)
+    ru = oracle.xc_eval(func, False, rho, sigma, tau)
+    rp = oracle.xc_eval(func, True, np.repeat(rho / 2, 2, 1), np.repeat(sigma / 4, 3, 1), np.repeat(tau / 2, 2, 1))
+    assert np.allclose(rp["exc"], ru["exc"], rtol=1e-12, atol=1e-14)
+    assert np.allclose(rp["vrho"][:, 0], ru["vrho"][:, 0], rtol=1e-10, atol=1e-12)
+    assert np.allclose(rp["vrho"][:, 1], ru["vrho"][:, 0], rtol=1e-10, atol=1e-12)
+    if ru["family"] >= 1:
+        # d/d sigma_total = (vaa + vab + vbb) / 4 * ... : total-sigma derivative from the spin-resolved ones
+        vs = (rp["vsigma"][:, 0] + rp["vsigma"][:, 1] + rp["vsigma"][:, 2]) / 4.0
+        assert np.allclose(vs, ru["vsigma"][:, 0], rtol=1e-9, atol=1e-12)
+    if ru["family"] >= 2:
+        assert np.allclose(rp["vtau"][:, 0], ru["vtau"][:, 0], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("func", FUNCS)
+def test_polarized_potentials_by_finite_differences(oracle, func):
+    rho, sigma, tau = _sample(30, 13, True)
+    r0 = oracle.xc_eval(func, True, rho, sigma, tau)
+    fam = r0["family"]
+
+    def F(rh, sg, ta):
+        return oracle.xc_eval(func, True, rh, sg, ta)["exc"] * rh.sum(1)
+
+    h = 1e-5
+    for k in range(2):
+        up, dn = rho.copy(), rho.copy()
+        up[:, k] *= 1 + h
+        dn[:, k] *= 1 - h
+        d = (F(up, sigma, tau) - F(dn, sigma, tau)) / (2 * h * rho[:, k])
+        assert np.allclose(d, r0["vrho"][:, k], rtol=5e-6, atol=1e-8)
+    if fam >= 1:
+        for k in range(3):
+            up, dn = sigma.copy(), sigma.copy()
+            step = h * (sigma[:, k] if k != 1 else 0.5 * (sigma[:, 0] + sigma[:, 2]))
+            up[:, k] += step
+            dn[:, k] -= step
+            d = (F(rho, up, tau) - F(rho, dn, tau)) / (2 * step)
+            # FD round-off floor: a few ulp of F divided by the step (matters when one spin channel is tiny)
+            noise = 3e-14 * np.abs(F(rho, sigma, tau)) / step
+            assert (np.abs(d - r0["vsigma"][:, k]) <= 5e-5 * np.abs(r0["vsigma"][:, k]) + 1e-8 + noise).all()
+    if fam >= 2:
+        for k in range(2):
+            up, dn = tau.copy(), tau.copy()
+            up[:, k] *= 1 + h
+            dn[:, k] *= 1 - h
+            d = (F(rho, sigma, up) - F(rho, sigma, dn)) / (2 * h * tau[:, k])
+            assert np.allclose(d, r0["vtau"][:, k], rtol=5e-5, atol=1e-8)
+
+
+def test_b3lyp_is_its_libxc_mixture(oracle):
+    rho, sigma, tau = _sample(25, 5, False)
+    mix = {"lda_x": 0.08, "gga_x_b88": 0.72, "lda_c_vwn_rpa": 0.19, "gga_c_lyp": 0.81}
+    tot = oracle.xc_eval("hyb_gga_xc_b3lyp", False, rho, sigma)
+    acc = sum(c * oracle.xc_eval(f, False, rho, sigma)["exc"] for f, c in mix.items())
+    assert np.allclose(tot["exc"], acc, rtol=1e-13)
+    assert oracle.lib().orc_xc_exx(402) == 0.20
+
+
+def test_unknown_functional_raises(oracle):
+    with pytest.raises(RuntimeError):
+        oracle.xc_eval(12345, False, np.ones(2))
+
+
+# ---------------------------------------------------------------- grids
+def test_lebedev_tables_are_the_references(oracle):
+    t = np.load(os.path.join(os.path.dirname(__file__), "golden", "lebedev_tables.npz"))
+    assert {"n110", "n302", "n266", "n590", "n50", "n74"} <= set(t.files)
+    for k in t.files:
+        a = t[k]
+        assert a.shape == (int(k[1:]), 4)       # tests/dft_tests.cpp:196-200 pins the 110 shape
+        assert abs(a[:, 3].sum() - 1.0) < 1e-13
+        assert np.allclose((a[:, :3] ** 2).sum(1), 1.0, atol=1e-14)
+    if oracle.ref_lib() is not None:
+        import ctypes
+        R = oracle.ref_lib()
+        for n in (110, 302):
+            a = np.zeros((n, 4))
+            R.occ_ref_lebedev(ctypes.c_int(n), a.ctypes.data_as(ctypes.c_void_p))
+            assert np.array_equal(a, t["n%d" % n])
+
+
+def test_veryfine_water_grid_size_quoted_by_the_reference(oracle):
+    """tests/isolated_xc_tests.cpp:271: 38 652 points for water/3-21G (spherical) at GridQuality::VeryFine"""
+    Z, pos = molecules.water_isolated_xc()
+    b = aobasis.AOBasis.load(Z, pos, "3-21g", pure=True)
+    ob = oracle.Basis(b.as_arrays())
+    s = oracle.default_grid_settings(max_angular_points=590, min_angular_points=302)  # grid_settings.cpp:50-54
+    pts, w, info = oracle.molecular_grid(Z, pos, ob, s)
+    assert len(w) == 38652
+    assert info["atom_npts"] == [13732, 12460, 12460]
+    assert info["atom_nradial"] == [86, 74, 74]
+
+
+def test_default_grid_sizes_of_the_baseline_configs(oracle):
+    for mol, bas, n in (("water", "def2-svp", 30172), ("benzene", "def2-tzvp", 139236)):
+        Z, pos = molecules.MOLECULES[mol]()
+        b = aobasis.AOBasis.load(Z, pos, bas)
+        pts, w, info = oracle.molecular_grid(Z, pos, oracle.Basis(b.as_arrays()))
+        assert len(w) == n
+
+
+def test_morton_hierarchy_invariants(oracle, case):
+    """tests/dft_tests.cpp:1287-1462: all points preserved, sum of weights preserved, leaf sizes, spheres contain points"""
+    c = case("water", "def2-svp")
+    spts, sw, perm, leaves = c["spts"], c["sw"], c["perm"], c["leaves"]
+    assert sorted(perm.tolist()) == list(range(len(sw)))
+    assert np.array_equal(spts, c["pts"][perm.astype(np.int64)])
+    assert abs(sw.sum() - c["w"].sum()) < 1e-12 * abs(c["w"].sum())
+    assert leaves["count"].sum() == len(sw)
+    assert (leaves["count"][:-1] == 128).all() and 1 <= leaves["count"][-1] <= 256
+    assert (leaves["offset"] == np.concatenate([[0], np.cumsum(leaves["count"])[:-1]])).all()
+    for lf in leaves[:: max(1, len(leaves) // 40)]:
+        p = spts[int(lf["offset"]): int(lf["offset"] + lf["count"])]
+        assert np.allclose(p.mean(0), lf["center"], atol=1e-12)
+        assert np.linalg.norm(p - lf["center"], axis=1).max() <= lf["radius"] + 1e-10
+
+
+def test_basis_function_counts_of_the_baseline_configs():
+    for mol, bas, cart, sph in (("water", "def2-svp", 25, 24), ("benzene", "def2-tzvp", 252, 222),
+                                ("h2o_32", "def2-svp", 800, 768), ("valinomycin", "def2-tzvp", 3348, 2958),
+                                ("taxol", "def2-tzvp", 2538, 2228)):
+        Z, pos = molecules.MOLECULES[mol]()
+        assert aobasis.AOBasis.load(Z, pos, bas).nbf == cart
+        assert aobasis.AOBasis.load(Z, pos, bas, pure=True).nbf == sph
