@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py — the Vxc+Exc build per SCF iteration (BASELINE.json metric) on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W [--workload NAME] [--impl reference]
+  (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...)
+
+A step = one DFT::compute_K_dft-equivalent build (include/occ/dft/dft.h:190-388) on a fixed synthetic density matrix.
+  value  : grid-points/s with D resident in HBM at the start and K left in HBM (device events, max over ranks,
+           the N>1 number includes the NCCL all-reduce of the packed [K | Exc, N_a, N_b] buffer)
+  e2e    : the same through the host-facing call: pinned host D -> H2D -> build -> (all-reduce) -> D2H K + scalars
+  roofline: dominant kernel (the FP64 DMMA contractions) against the FP64 tensor peak measured on this pool's B200
+           (profiles/r01_fp64_peaks_b200.jsonl: 36.9 TFLOP/s DMMA.8x8x4; MEASURED_PEAKS.json carries no FP64 entry)
+  cpu_baseline / --impl reference: the CPU restatement of the reference algorithm (oracle/, OpenMP over leaves +
+           OpenBLAS) on the box's host cores, on a bounded sample of the same workload (every s-th Morton leaf).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FP64_TENSOR_PEAK_TFLOPS = 36.9  # profiles/r01_fp64_peaks_b200.jsonl (dmma_m8n8k4, measured on this pool's B200)
+
+WORKLOADS = {
+    # name: (molecule, basis, method, nspin, grid quality or None for the reference default)
+    "water_b3lyp_svp": ("water", "def2-svp", "b3lyp", 1, None),
+    "benzene_pbe_tzvp": ("benzene", "def2-tzvp", "pbe", 1, None),
+    "h2o32_b3lyp_svp_uks": ("h2o_32", "def2-svp", "b3lyp", 2, None),
+    "valinomycin_b3lyp_tzvp": ("valinomycin", "def2-tzvp", "b3lyp", 1, None),
+    "taxol_r2scan_tzvp": ("taxol", "def2-tzvp", "r2scan", 1, None),
+}
+DEFAULT_WORKLOAD = "valinomycin_b3lyp_tzvp"
+
+
+def make_inputs(workload):
+    from occ_b200 import aobasis, molecules
+    mol, bas, method, nspin, quality = WORKLOADS[workload]
+    Z, pos = molecules.MOLECULES[mol]()
+    basis = aobasis.AOBasis.load(Z, pos, bas)
+    D2 = molecules.synthetic_density(basis, nspin)
+    return basis, method, nspin, quality, D2
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_build_sample(basis, method, nspin, D2, hierarchy, target_seconds=15.0, nthreads=None, repeats=1):
+    """Time the CPU restatement of the reference algorithm on every `stride`-th Morton leaf; returns points/s etc."""
+    from occ_b200 import dft
+    from oracle import oracle as O
+    ob = O.Basis(basis.as_arrays())
+    names = [n for i in dft.get_dft_method(method) for n, v in O.FUNC_IDS.items() if v == i]
+    leaves = hierarchy.leaves
+    nthreads = nthreads or os.cpu_count() or 1
+    # probe with a thin sample to pick the stride
+    stride = max(1, len(leaves) // 64)
+    probe = leaves[::stride]
+    t0 = time.perf_counter()
+    O.xc_build(ob, hierarchy.sorted_points, hierarchy.sorted_weights, probe, names, nspin, D2, nthreads=nthreads)
+    t_probe = time.perf_counter() - t0
+    full_est = t_probe * len(leaves) / max(1, len(probe))
+    stride = max(1, int(np.ceil(full_est / target_seconds)))
+    sample = leaves[::stride]
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        r = O.xc_build(ob, hierarchy.sorted_points, hierarchy.sorted_weights, sample, names, nspin, D2, nthreads=nthreads)
+        times.append(time.perf_counter() - t0)
+    npts = int(sample["count"].sum())
+    return {"seconds": times, "npts": npts, "stride": stride, "nleaves": len(sample), "cores": nthreads,
+            "flops": (16.0 if O.method_deriv(names) >= 2 else 4.0) * nspin * r["stats"]["sum_n_nb2"]}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle restatement; the reference binary cannot be built
+    here — Eigen/libxc/oneTBB are network-fetched) on the host cores, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from occ_b200 import grid
+    basis, method, nspin, quality, D2 = make_inputs(args.workload)
+    try:
+        g = grid.MolecularGrid(basis, grid.GridSettings.from_grid_quality(quality) if quality else None)
+        h = g.hierarchy()
+    except RuntimeError:
+        # no usable GPU for the (GPU-accelerated) grid producer: fall back to the oracle's own grid code
+        from occ_b200 import dft
+        from oracle import oracle as O
+        ob = O.Basis(basis.as_arrays())
+        pts, w, _ = O.molecular_grid(basis.atomic_numbers, basis.positions, ob)
+        spts, sw, perm, leaves = O.hierarchy(pts, w)
+        h = dft.GridHierarchy(spts, sw, leaves)
+    cores = os.cpu_count() or 1
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    res = cpu_build_sample(basis, method, nspin, D2, h, target_seconds=min(20.0, budget), nthreads=cores,
+                           repeats=args.steps + args.warmup)
+    t = res["seconds"][args.warmup:]
+    ms = 1e3 * sum(t) / len(t)
+    value = res["npts"] / (ms * 1e-3)
+    sample = f"every {res['stride']}-th Morton leaf ({res['nleaves']} leaves, {res['npts']} points) of {args.workload}"
+    line = {"impl": "reference", "metric": "xc_build_grid_points_per_s", "value": value, "unit": "grid-points/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "basis_functions": basis.nbf, "grid_points": len(h.sorted_weights),
+                       "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "grid-points/s", "cores": cores, "kind": "port", "sample": sample,
+                             "gflops": res["flops"] / (ms * 1e-3) / 1e9},
+            "e2e": {"value": value, "unit": "grid-points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from occ_b200 import dft, grid, parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    t_setup = time.perf_counter()
+    basis, method, nspin, quality, D2 = make_inputs(args.workload)
+    g = grid.MolecularGrid(basis, grid.GridSettings.from_grid_quality(quality) if quality else None)
+    h = g.hierarchy()
+    npts_total = len(h.sorted_weights)
+    kind = dft.UNRESTRICTED if nspin == 2 else dft.RESTRICTED
+    ddft = parallel.DistributedDFT(method, basis, h, kind, device=local, batch_bytes=args.batch_mb << 20)
+    info = ddft.dft.info()
+    nbf = basis.nbf
+    n = nspin * nbf * nbf
+    # normalise the synthetic density to N_electrons with one build (the electron count is linear in D)
+    hD = torch.from_numpy(np.ascontiguousarray(D2.ravel(order="F"))).pin_memory()
+    hK = torch.empty(n, dtype=torch.float64).pin_memory()
+    exc, na, nb_ = ddft.build(hD, hK)
+    nel = float(basis.num_electrons())
+    hD.mul_(nel / (na + nb_ if nspin == 2 else na))
+    t_setup = time.perf_counter() - t_setup
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ddft.stream)          # the stream the library launches on (not torch's current stream)
+        for _ in range(steps):
+            fn()
+        e1.record(ddft.stream)
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        sync_all()
+        return float(ms.item()) / steps
+
+    # ---- device-resident arm ----
+    with torch.cuda.stream(ddft.stream):
+        ddft.d_D.copy_(hD, non_blocking=True)
+
+    def step_dev():
+        ddft.build_device()
+
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(step_dev, args.steps)
+
+    # ---- end-to-end arm (host buffers through the public call) ----
+    def step_e2e():
+        ddft.build(hD, hK)
+
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    exc, na, nb_ = ddft.build(hD, hK)
+
+    # ---- per-kernel times of this rank's shard (CUDA events on the build stream, profiled pass) ----
+    ddft.dft.set_profiling(True)
+    phases = {}
+    nprof = max(1, min(3, args.steps))
+    for _ in range(nprof):
+        ddft.build_device()
+        torch.cuda.synchronize()
+        for k, v in ddft.dft.phase_ms().items():
+            phases[k] = phases.get(k, 0.0) + v / nprof
+    ddft.dft.set_profiling(False)
+
+    flops_total = info["flops_per_build"]
+    if world > 1:
+        ft = torch.tensor([flops_total, float(info["launches_per_build"])], dtype=torch.float64, device=dev)
+        dist.all_reduce(ft)
+        flops_total, launches_total = float(ft[0]), float(ft[1])
+    else:
+        launches_total = float(info["launches_per_build"])
+
+    if rank == 0:
+        g_fac = 16.0 if info["deriv"] >= 2 else 4.0
+        # the two DMMA contractions do g/2 * nspin * sum(n nb^2) algorithmic flops each
+        kern = {}
+        for name in ("density", "vxc"):
+            fl = 0.5 * info["flops_per_build"]
+            ms_launch = phases[name] / max(1, info["nbatches"])
+            kern[name] = {"ms_per_build": phases[name], "launches_per_build": info["nbatches"],
+                          "avg_launch_ms": ms_launch, "tflops": fl / (phases[name] * 1e-3) / 1e12 if phases[name] > 0 else 0.0}
+        dom = max(kern, key=lambda k: kern[k]["ms_per_build"])
+        achieved = kern[dom]["tflops"]
+        cpu = None
+        if not args.no_cpu_baseline:
+            res = cpu_build_sample(basis, method, nspin, np.asfortranarray(hD.numpy().reshape(nbf, nspin * nbf).T), h,
+                                   target_seconds=args.cpu_seconds)
+            t = res["seconds"][0]
+            cpu = {"value": res["npts"] / t, "unit": "grid-points/s", "cores": res["cores"], "kind": "port",
+                   "sample": f"every {res['stride']}-th Morton leaf ({res['nleaves']} leaves, {res['npts']} points) of "
+                             f"{args.workload}, one build, {t:.1f} s",
+                   "gflops": res["flops"] / t / 1e9}
+        line = {
+            "metric": "xc_build_grid_points_per_s", "value": npts_total / (ms_dev * 1e-3), "unit": "grid-points/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "molecule": WORKLOADS[args.workload][0],
+                       "basis": WORKLOADS[args.workload][1], "functional": method, "nspin": nspin,
+                       "basis_functions": nbf, "grid_points": npts_total, "leaves": int(h.num_leaves),
+                       "nb_local_min_max": [info["nb_min"], info["nb_max"]], "batch_mb": args.batch_mb,
+                       "parallelism": f"grid leaves sharded over {world} GPU(s), D replicated, NCCL all-reduce of K",
+                       "l2": "per-step working set (AO workspace, %.1f GB streamed per build) exceeds the 126 MB L2; "
+                             "no explicit flush" % _workspace_gb(info, nspin)},
+            "xc_energy": exc, "n_electrons": na + (nb_ if nspin == 2 else 0.0),
+            "algorithmic_tflops": flops_total / (ms_dev * 1e-3) / 1e12,
+            "fp64_tensor_frac_whole_build": flops_total / (ms_dev * 1e-3) / 1e12 / (FP64_TENSOR_PEAK_TFLOPS * world),
+            "roofline": {"bound": "tensor", "kernel": "k_" + dom, "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS,
+                         "unit": "TFLOP/s", "frac": achieved / FP64_TENSOR_PEAK_TFLOPS, "traffic": None,
+                         "peak_source": "measured DMMA.8x8x4 microbenchmark on this pool's B200 "
+                                        "(profiles/r01_fp64_peaks_b200.jsonl); MEASURED_PEAKS.json has no FP64 entry",
+                         "kernels": kern},
+            "phases_ms": phases,
+            "cpu_baseline": cpu,
+            "e2e": {"value": npts_total / (ms_e2e * 1e-3), "unit": "grid-points/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": 8 * n * world, "d2h_bytes_per_step": 8 * (n + 3) * world},
+            "gpu_launches": int(launches_total * args.steps),
+            "clocks": clocks, "setup_seconds": t_setup,
+        }
+        print(json.dumps(line), flush=True)
+    ddft.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _workspace_gb(info, nspin):
+    # AO slabs streamed per build: (ncomp + nspin) slabs of 128 x nb doubles per tile ~ sum over leaves
+    ncomp = 4 if info["deriv"] >= 1 else 1
+    mean_nb = (info["sum_n_nb2"] / max(1.0, float(info["npts"]))) ** 0.5
+    return 8.0 * (ncomp + nspin) * info["npts"] * mean_nb / 1e9
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--batch-mb", type=int, default=1024)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -47,8 +47,8 @@ class GridSettingsT(C.Structure):
 
 
 LEAF_DTYPE = np.dtype([("offset", np.uint64), ("count", np.uint64), ("center", np.float64, 3), ("radius", np.float64)])
-NPHASES = 6
-PHASE_NAMES = ["prepare_D", "collocation", "density", "functional", "vxc", "finalise"]
+NPHASES = 7
+PHASE_NAMES = ["prepare_D", "collocation", "density", "functional", "gbuild", "vxc", "finalise"]
 
 _lib = None
 

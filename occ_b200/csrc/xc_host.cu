@@ -208,7 +208,7 @@ struct occ_xc_handle {
   double *d_D = nullptr, *d_Dsym = nullptr, *d_Ktmp = nullptr, *d_K = nullptr, *d_scalars = nullptr;
   cudaStream_t stream = nullptr;
   bool profiling = false;
-  double phase_ms[OCC_XC_NPHASES] = {0, 0, 0, 0, 0, 0};
+  double phase_ms[OCC_XC_NPHASES] = {0, 0, 0, 0, 0, 0, 0};
   size_t launches = 0;
 };
 
@@ -660,12 +660,14 @@ int occ_xc_build_device(occ_xc_handle *h, const double *D2_dev, double *K_dev, d
     PHASE_END(3);
     PHASE_BEGIN();
     launch_gbuild(P, h->d_g + b.g_off, static_cast<int>(b.ng), st);
-    launch_vxc(P, h->d_vxc + b.vxc_off, static_cast<int>(b.nvxc), st);
     PHASE_END(4);
+    PHASE_BEGIN();
+    launch_vxc(P, h->d_vxc + b.vxc_off, static_cast<int>(b.nvxc), st);
+    PHASE_END(5);
   }
   PHASE_BEGIN();
   launch_finalize(P, h->nleaves, K_dev, scalars_dev, st);
-  PHASE_END(5);
+  PHASE_END(6);
 #undef PHASE_BEGIN
 #undef PHASE_END
   if (prof) {

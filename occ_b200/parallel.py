@@ -45,27 +45,35 @@ class DistributedDFT:
         self.dft = DFT(method, basis, grid, spinorbital_kind, device=self.device, rank=self.rank,
                        world_size=self.world, **kw)
         self.nspin, self.nbf = self.dft.nspin, self.dft.nbf
+        self._sc_host = torch.zeros(3, dtype=torch.float64).pin_memory()
         dev = torch.device("cuda", self.device)
         self.d_D = torch.empty(self.nspin * self.nbf * self.nbf, dtype=torch.float64, device=dev)
         self.d_out = torch.zeros(pack_len(self.nspin, self.nbf), dtype=torch.float64, device=dev)
+        # a dedicated non-default stream: the C ABI reads a NULL stream as "the handle's own stream", so the legacy
+        # default stream (value 0) can never be passed through it; copies, build and all-reduce all run here
+        self.stream = torch.cuda.Stream(device=dev)
 
-    def build_device(self, stream: torch.cuda.Stream | None = None) -> torch.Tensor:
-        """D already in self.d_D (column-major). Returns the packed, all-reduced device buffer."""
-        st = stream or torch.cuda.current_stream(self.device)
+    def build_device(self) -> torch.Tensor:
+        """D already in self.d_D (column-major). Enqueues build + all-reduce on self.stream; returns the packed
+        device buffer [K | exc, n_alpha, n_beta] (valid once self.stream has been synchronised / waited on)."""
         n = self.nspin * self.nbf * self.nbf
-        self.dft.build_device(self.d_D.data_ptr(), self.d_out.data_ptr(), self.d_out.data_ptr() + 8 * n, st.cuda_stream)
-        with torch.cuda.stream(st):
-            allreduce_partial(self.d_out, self.group)
+        self.dft.build_device(self.d_D.data_ptr(), self.d_out.data_ptr(), self.d_out.data_ptr() + 8 * n,
+                              self.stream.cuda_stream)
+        if self.world > 1:
+            with torch.cuda.stream(self.stream):
+                allreduce_partial(self.d_out, self.group)
         return self.d_out
 
     def build(self, D2_host: torch.Tensor, K_host: torch.Tensor):
         """Host-to-host build: D2_host / K_host are (pinned) CPU tensors holding column-major matrices."""
         n = self.nspin * self.nbf * self.nbf
-        self.d_D.copy_(D2_host.view(-1), non_blocking=True)
-        out = self.build_device()
-        K_host.view(-1)[:n].copy_(out[:n], non_blocking=True)
-        sc = out[n:n + 3].cpu()
-        return float(sc[0]), float(sc[1]), float(sc[2])
+        with torch.cuda.stream(self.stream):
+            self.d_D.copy_(D2_host.view(-1), non_blocking=True)
+            out = self.build_device()
+            K_host.view(-1)[:n].copy_(out[:n], non_blocking=True)
+            self._sc_host.copy_(out[n:n + 3], non_blocking=True)
+        self.stream.synchronize()
+        return float(self._sc_host[0]), float(self._sc_host[1]), float(self._sc_host[2])
 
     def close(self):
         self.dft.close()
