@@ -66,7 +66,7 @@ typedef struct {
   int rank, world_size;  /* grid-leaf shard of this handle: leaves are split by predicted cost over world_size
                             handles (one per GPU / process); every handle returns a PARTIAL K, Exc, N that the
                             caller sums (NCCL all-reduce).  world_size <= 1: whole grid. */
-  size_t batch_bytes;    /* AO-value workspace per batch of leaves (0 = default 256 MiB) */
+  size_t batch_bytes;    /* AO-value workspace per batch of leaves (0 = default 4 GiB) */
   int reserved[8];
 } occ_xc_options_t;
 

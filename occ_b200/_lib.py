@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libocc_xc_b200.so")
+LIB_PATH = os.environ.get("OCC_XC_B200_LIB", os.path.join(HERE, "libocc_xc_b200.so"))  # override: kernel-variant experiments
 
 # every symbol include/occ_xc_b200.h declares
 SYMBOLS = ["occ_xc_create", "occ_xc_build", "occ_xc_build_device", "occ_xc_get_info", "occ_xc_set_profiling",

@@ -21,7 +21,13 @@
 
 namespace xcb {
 
-constexpr int GM = 128, GN = 64, GK = 16, GSTAGES = 3;
+#ifndef XC_GK
+#define XC_GK 16
+#endif
+#ifndef XC_STAGES
+#define XC_STAGES 3
+#endif
+constexpr int GM = 128, GN = 64, GK = XC_GK, GSTAGES = XC_STAGES;
 constexpr int NTHREADS = 256;
 // density: A stage is [k][m] (m contiguous), ld 132; B stage is [n][k] (k contiguous), ld 20
 constexpr int D_LDA = GM + 4, D_LDB = GK + 4;
@@ -71,32 +77,36 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_density(BuildParams P, const De
   const int *gidx = P.bf_index + t.bf_off;
   const int n0 = it.jb * GN;
 
-  // B loader assignment: this thread stages k = kk of every chunk for 4 columns
-  const int kk = tid & 15, nn = tid >> 4;
-  size_t coloff[4];
-  bool nvalid[4];
+  // B loader assignment: this thread stages k = kk of every chunk for NBR columns
+  constexpr int NROWT = NTHREADS / GK;   // columns covered per pass
+  constexpr int NBR = GN / NROWT;        // passes
+  const int kk = tid % GK, nn = tid / GK;
+  size_t coloff[NBR];
+  bool nvalid[NBR];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int n = n0 + nn + 16 * r;
+  for (int r = 0; r < NBR; ++r) {
+    const int n = n0 + nn + NROWT * r;
     nvalid[r] = n < nb;
     coloff[r] = nvalid[r] ? static_cast<size_t>(__ldg(gidx + n)) * P.ldD : 0;
   }
+  // 8-column groups of this warp's 32 columns that hold real basis functions (the rest is padding: no DMMA)
+  const int ni_valid = min(4, max(0, (nb - (n0 + wn * 32) + 7) >> 3));
 
   auto load_stage = [&](int kc, int stage) {
     double *As = smem + stage * D_STAGE;
     double *Bs = As + D_ASZ;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < GK * 64 / NTHREADS; ++r) {
       const int seg = tid + NTHREADS * r;
       const int col = seg >> 6, s2 = (seg & 63) * 2;
-      cp_async16(As + col * D_LDA + s2, Ag + static_cast<size_t>(kc * GK + col) * TILE_P + s2, true);
+      cp_async16(As + col * D_LDA + s2, Ag + static_cast<size_t>(kc * GK + col) * TILE_P + s2, kc * GK + col < t.nbp);
     }
     const int k = kc * GK + kk;
     const bool kvalid = k < nb;
     const int grow = kvalid ? __ldg(gidx + k) : 0;
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-      cp_async8(Bs + (nn + 16 * r) * D_LDB + kk, Dm + coloff[r] + grow, kvalid && nvalid[r]);
+    for (int r = 0; r < NBR; ++r)
+      cp_async8(Bs + (nn + NROWT * r) * D_LDB + kk, Dm + coloff[r] + grow, kvalid && nvalid[r]);
   };
 
   double acc[4][4][2];
@@ -110,24 +120,42 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_density(BuildParams P, const De
     if (s < nk) load_stage(s, s);
     cp_async_commit();
   }
+  // interior warps (all 32 columns real) run the branch-free 16-DMMA step; edge warps skip padded 8-column groups
+  const bool full = ni_valid == 4;
   for (int kc = 0; kc < nk; ++kc) {
     cp_async_wait<GSTAGES - 2>();
     __syncthreads();
     if (kc + GSTAGES - 1 < nk) load_stage(kc + GSTAGES - 1, (kc + GSTAGES - 1) % GSTAGES);
     cp_async_commit();
-    const double *As = smem + (kc % GSTAGES) * D_STAGE;
-    const double *Bs = As + D_ASZ;
+    const double *As = smem + (kc % GSTAGES) * D_STAGE + wm * 32 + gid;
+    const double *Bs = smem + (kc % GSTAGES) * D_STAGE + D_ASZ + (wn * 32 + gid) * D_LDB;
+    if (full) {
 #pragma unroll
-    for (int k4 = 0; k4 < GK / 4; ++k4) {
-      double a[4], b[4];
+      for (int k4 = 0; k4 < GK / 4; ++k4) {
+        double a[4], b[4];
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi) a[mi] = As[(k4 * 4 + tig) * D_LDA + wm * 32 + mi * 8 + gid];
+        for (int mi = 0; mi < 4; ++mi) a[mi] = As[(k4 * 4 + tig) * D_LDA + mi * 8];
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[(wn * 32 + ni * 8 + gid) * D_LDB + k4 * 4 + tig];
+        for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[ni * 8 * D_LDB + k4 * 4 + tig];
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
+        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+          for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+      }
+    } else if (ni_valid > 0) {
+#pragma unroll
+      for (int k4 = 0; k4 < GK / 4; ++k4) {
+        double a[4];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) a[mi] = As[(k4 * 4 + tig) * D_LDA + mi * 8];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+          if (ni < ni_valid) {
+            const double b = Bs[ni * 8 * D_LDB + k4 * 4 + tig];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b);
+          }
+      }
     }
   }
   cp_async_wait<0>();
@@ -137,7 +165,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_density(BuildParams P, const De
   const int c_begin = it.acomp == 0 ? 0 : it.acomp;
   const int c_end = it.acomp == 0 ? P.ncomp : it.acomp + 1;
   const double *phib = P.scratch + t.scr_off + static_cast<size_t>(n0 + wn * 32 + 2 * tig) * TILE_P + wm * 32 + gid;
-  for (int c = c_begin; c < c_end; ++c) {
+  for (int c = c_begin; c < ((P.debug & 2) ? c_begin : c_end); ++c) {
     const double *pc = phib + static_cast<size_t>(c) * slab;
     const int row = it.acomp == 0 ? c : 4;
 #pragma unroll
@@ -204,7 +232,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_vxc(BuildParams P, const VxcIte
   double *Kt = P.Ktmp[it.spin];
   const int n0 = it.jb * GN;
   const int nib = (nb + GM - 1) / GM;
-  const int nq = nib * (TILE_P / GK); // flattened (ib, kc) chunks
+  constexpr int NKC = TILE_P / GK;
+  const int nq = nib * NKC; // flattened (ib, kc) chunks
+  const int ni_valid = min(4, max(0, (nb - (n0 + wn * 32) + 7) >> 3));
   double *sct = smem + GSTAGES * V_STAGE; // [128] tau coefficient (acomp != 0)
   if (tid < TILE_P)
     sct[tid] = it.acomp == 0
@@ -214,18 +244,19 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_vxc(BuildParams P, const VxcIte
   auto load_stage = [&](int q, int stage) {
     double *As = smem + stage * V_STAGE;
     double *Bs = As + V_ASZ;
-    const int ib = q >> 3, kc = q & 7;
+    const int ib = q / NKC, kc = q % NKC;
+    constexpr int SPR = GK / 2; // 16-byte segments per row
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int seg = tid + NTHREADS * r; // 1024 segments: row = seg >> 3, 8 x 16 B per row
-      const int row = seg >> 3, s2 = (seg & 7) * 2;
+    for (int r = 0; r < GM * SPR / NTHREADS; ++r) {
+      const int seg = tid + NTHREADS * r;
+      const int row = seg / SPR, s2 = (seg % SPR) * 2;
       const int i = ib * GM + row;
       cp_async16(As + row * V_LDA + s2, Ag + static_cast<size_t>(i < nbp ? i : 0) * TILE_P + kc * GK + s2, i < nbp);
     }
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int seg = tid + NTHREADS * r; // 512 segments
-      const int row = seg >> 3, s2 = (seg & 7) * 2;
+    for (int r = 0; r < GN * SPR / NTHREADS; ++r) {
+      const int seg = tid + NTHREADS * r;
+      const int row = seg / SPR, s2 = (seg % SPR) * 2;
       cp_async16(Bs + row * V_LDB + s2, Bg + static_cast<size_t>(row) * TILE_P + kc * GK + s2, true);
     }
   };
@@ -248,9 +279,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_vxc(BuildParams P, const VxcIte
     if (s < nq) load_stage(s, s);
     cp_async_commit();
   }
+  int ib = 0, kc = 0;
+  bool full = false;
+  int mi_valid = 0;
   for (int q = 0; q < nq; ++q) {
-    const int kc = q & 7;
     if (kc == 0) {
+      mi_valid = min(4, max(0, (nb - (ib * GM + wm * 32) + 7) >> 3));
+      full = mi_valid == 4 && ni_valid == 4;
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -260,24 +295,42 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_vxc(BuildParams P, const VxcIte
     __syncthreads();
     if (q + GSTAGES - 1 < nq) load_stage(q + GSTAGES - 1, (q + GSTAGES - 1) % GSTAGES);
     cp_async_commit();
-    const double *As = smem + (q % GSTAGES) * V_STAGE;
-    const double *Bs = As + V_ASZ;
+    const double *As = smem + (q % GSTAGES) * V_STAGE + (wm * 32 + gid) * V_LDA;
+    const double *Bs = smem + (q % GSTAGES) * V_STAGE + V_ASZ + (wn * 32 + gid) * V_LDB;
+    const double *sc = sct + kc * GK + tig;
+    if (full) {
 #pragma unroll
-    for (int k4 = 0; k4 < GK / 4; ++k4) {
-      double a[4], b[4];
-      const double sc = sct[kc * GK + k4 * 4 + tig];
+      for (int k4 = 0; k4 < GK / 4; ++k4) {
+        double a[4], b[4];
+        const double f = sc[k4 * 4];
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi) a[mi] = As[(wm * 32 + mi * 8 + gid) * V_LDA + k4 * 4 + tig] * sc;
+        for (int mi = 0; mi < 4; ++mi) a[mi] = As[mi * 8 * V_LDA + k4 * 4 + tig] * f;
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[(wn * 32 + ni * 8 + gid) * V_LDB + k4 * 4 + tig];
+        for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[ni * 8 * V_LDB + k4 * 4 + tig];
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
+        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+          for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+      }
+    } else if (mi_valid > 0 && ni_valid > 0) {
+#pragma unroll
+      for (int k4 = 0; k4 < GK / 4; ++k4) {
+        double b[4];
+        const double f = sc[k4 * 4];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[ni * 8 * V_LDB + k4 * 4 + tig];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+          if (mi < mi_valid) {
+            const double a = As[mi * 8 * V_LDA + k4 * 4 + tig] * f;
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+              if (ni < ni_valid) dmma884(acc[mi][ni][0], acc[mi][ni][1], a, b[ni]);
+          }
+      }
     }
-    if (kc == 7) {
+    if (kc == NKC - 1 && !(P.debug & 1)) {
       // scatter-add this 128 x 64 block of Ktmp_loc into the full matrix (dft.h:361-369)
-      const int ib = q >> 3;
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi) {
         const int i = ib * GM + wm * 32 + mi * 8 + gid;
@@ -290,6 +343,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_vxc(BuildParams P, const VxcIte
           }
         }
       }
+    }
+    if (++kc == NKC) {
+      kc = 0;
+      ++ib;
     }
   }
   cp_async_wait<0>();

@@ -317,7 +317,7 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
   const int world = (opt && opt->world_size > 1) ? opt->world_size : 1;
   const int rank = world > 1 ? opt->rank : 0;
   if (rank < 0 || rank >= world) return fail("occ_xc_create: rank outside [0, world_size)");
-  const size_t batch_bytes = (opt && opt->batch_bytes) ? opt->batch_bytes : (size_t(256) << 20);
+  const size_t batch_bytes = (opt && opt->batch_bytes) ? opt->batch_bytes : (size_t(4096) << 20);
 
   const int nsh = basis->nsh, pure = basis->pure ? 1 : 0;
   std::vector<int> first_bf(nsh);
@@ -599,6 +599,7 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
   P.nfunc = nfunc;
   for (int f = 0; f < nfunc; ++f) P.func_ids[f] = func_ids[f];
   P.density_threshold = density_threshold;
+  P.debug = opt ? opt->reserved[0] : 0;
   for (int s = 0; s < nspin; ++s) P.Ktmp[s] = h->d_Ktmp + static_cast<size_t>(s) * nbf;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
     occ_xc_destroy(h);

@@ -90,6 +90,7 @@ struct BuildParams {
   int nfunc;
   int func_ids[MAX_FUNC];
   double density_threshold;
+  int debug; // developer switches for timing experiments (options.reserved[0]): 1 = no Vxc scatter, 2 = no density epilogue
 };
 
 // spherical transform tables (real solid harmonics, CCA order m = -l..l) in constant memory

@@ -1,0 +1,17 @@
+#!/usr/bin/env python
+"""Developer experiment: time the DMMA kernels for each prebuilt kernel variant (OCC_XC_B200_LIB override)."""
+import os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+code = r'''
+import sys; sys.path.insert(0, %r)
+from scripts.gpu_experiments import run
+run("valinomycin", "def2-tzvp", "b3lyp", 1, 4096)
+run("benzene", "def2-tzvp", "pbe", 1, 2048)
+run("h2o_32", "def2-svp", "b3lyp", 2, 4096)
+''' % ROOT
+libs = [None] + sorted(os.path.join(ROOT, "occ_b200", "variants", f) for f in os.listdir(os.path.join(ROOT, "occ_b200", "variants")))
+for lib in libs:
+    env = dict(os.environ)
+    if lib: env["OCC_XC_B200_LIB"] = lib
+    print("=== variant", lib or "default (GK16, 3 stages)", flush=True)
+    subprocess.run([sys.executable, "-c", code], env=env)
