@@ -1,0 +1,115 @@
+// adapter/occ_dft_b200.h — header-only C++17 host side over the C ABI (include/occ_xc_b200.h).
+//
+// Mirrors the piece of occ::dft::DFT that owns the XC build (reference: include/occ/dft/dft.h:36-763):
+//   XCBuild::compute_K_dft(D, K)            <->  Mat DFT::compute_K_dft<deriv, kind>(mo, Schwarz)   dft.h:190-388
+//   XCBuild::exchange_correlation_energy()  <->  m_exc_dft (dft.h:202,377)
+//   XCBuild::total_density_alpha/beta()     <->  the debug totals of dft.h:384-385
+//   errors                                  <->  std::runtime_error, as dft.h:409,422,427 / functional.cpp:32,61
+// No Eigen dependency: matrices cross as raw column-major pointers, which is what Eigen's Mat::data() gives
+// (core/linear_algebra.h:23).  INTEGRATION.md shows the ~25-line body that replaces dft.h:216-382 with this class.
+#pragma once
+#include "../include/occ_xc_b200.h"
+#include <cstddef>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace occ_b200 {
+
+enum class SpinorbitalKind { Restricted = 1, Unrestricted = 2 }; // occ::qm::SpinorbitalKind (qm/spinorbital.h)
+
+// Flat copy of occ::gto::AOBasis: fill from basis.shells() (Shell::l, origin, exponents,
+// contraction_coefficients.col(0)) and basis.shell_to_atom(); kind() == Spherical -> pure = true.
+struct BasisArrays {
+  bool pure = false;
+  std::vector<int> l, nprim, prim_off, shell_atom;
+  std::vector<double> origin, exps, coefs;
+
+  void add_shell(int L, const double *xyz, int np, const double *alpha, const double *c, int atom) {
+    l.push_back(L);
+    nprim.push_back(np);
+    prim_off.push_back(static_cast<int>(exps.size()));
+    shell_atom.push_back(atom);
+    origin.insert(origin.end(), xyz, xyz + 3);
+    exps.insert(exps.end(), alpha, alpha + np);
+    coefs.insert(coefs.end(), c, c + np);
+  }
+  occ_xc_basis_t view() const {
+    occ_xc_basis_t b;
+    b.nsh = static_cast<int>(l.size());
+    b.pure = pure ? 1 : 0;
+    b.l = l.data();
+    b.origin = origin.data();
+    b.nprim = nprim.data();
+    b.prim_off = prim_off.data();
+    b.exps = exps.data();
+    b.coefs = coefs.data();
+    b.shell_atom = shell_atom.data();
+    return b;
+  }
+  int nbf() const {
+    int n = 0;
+    for (int L : l) n += pure ? 2 * L + 1 : (L + 1) * (L + 2) / 2;
+    return n;
+  }
+};
+
+inline void check(int rc) {
+  if (rc != 0) throw std::runtime_error(occ_xc_last_error());
+}
+
+// Owns one occ_xc_handle: everything geometry-only (grid, shell lists, work lists) is uploaded once, when the
+// reference would (re)build its grid (DFT::set_integration_grid / set_method, src/dft/dft.cpp:56-117).
+class XCBuild {
+public:
+  // sorted_points (3 x npts, column-major), sorted_weights and leaves come from
+  // m_grid.get_molecular_grid_points().get_hierarchy() (dft.h:295-298); func_ids from
+  // m_method.functionals[_polarized][i].id() (dft.h:207-209).
+  XCBuild(const BasisArrays &basis, size_t npts, const double *sorted_points, const double *sorted_weights,
+          const std::vector<occ_xc_leaf_t> &leaves, const std::vector<int> &func_ids, SpinorbitalKind kind,
+          double density_threshold = 1e-10, double xc_screening_threshold = 1e-10, int device = -1, int rank = 0,
+          int world_size = 1)
+      : m_nspin(static_cast<int>(kind)), m_nbf(basis.nbf()) {
+    occ_xc_options_t opt{};
+    opt.device = device;
+    opt.rank = rank;
+    opt.world_size = world_size;
+    const occ_xc_basis_t b = basis.view();
+    check(occ_xc_create(&b, npts, sorted_points, sorted_weights, leaves.size(), leaves.data(), nullptr,
+                        static_cast<int>(func_ids.size()), func_ids.data(), m_nspin, density_threshold,
+                        xc_screening_threshold, &opt, &m_handle));
+  }
+  ~XCBuild() { occ_xc_destroy(m_handle); }
+  XCBuild(const XCBuild &) = delete;
+  XCBuild &operator=(const XCBuild &) = delete;
+
+  // D = mo.D ((nspin*nbf) x nbf column-major). Writes K (same shape). Doubles D like dft.h:205.
+  void compute_K_dft(const double *D, double *K) {
+    const size_t n = static_cast<size_t>(m_nspin) * m_nbf * m_nbf;
+    m_D2.resize(n);
+    for (size_t i = 0; i < n; ++i) m_D2[i] = 2 * D[i];
+    check(occ_xc_build(m_handle, m_D2.data(), K, &m_exc_dft, &m_total_density_a, &m_total_density_b));
+  }
+  double exchange_correlation_energy() const { return m_exc_dft; }
+  double total_density_alpha() const { return m_total_density_a; }
+  double total_density_beta() const { return m_total_density_b; }
+  int density_derivative() const { // DFT::density_derivative, src/dft/dft.cpp:11-17
+    occ_xc_info_t info;
+    check(occ_xc_get_info(m_handle, &info));
+    return info.deriv;
+  }
+  occ_xc_info_t info() const {
+    occ_xc_info_t i;
+    check(occ_xc_get_info(m_handle, &i));
+    return i;
+  }
+  occ_xc_handle *handle() { return m_handle; }
+
+private:
+  occ_xc_handle *m_handle = nullptr;
+  int m_nspin, m_nbf;
+  double m_exc_dft = 0.0, m_total_density_a = 0.0, m_total_density_b = 0.0;
+  std::vector<double> m_D2;
+};
+
+} // namespace occ_b200

@@ -1,0 +1,59 @@
+// Test driver for adapter/occ_dft_b200.h: reads a case written by tests/test_adapter_cpp.py, runs
+// XCBuild::compute_K_dft through the C ABI and writes K, Exc, N back.  With --expect-error it checks that a
+// failure inside the library surfaces as std::runtime_error (the reference's error convention).
+#include "../../adapter/occ_dft_b200.h"
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+
+template <class T> static std::vector<T> read_vec(std::ifstream &f) {
+  long long n = 0;
+  f.read(reinterpret_cast<char *>(&n), sizeof(n));
+  std::vector<T> v(static_cast<size_t>(n));
+  f.read(reinterpret_cast<char *>(v.data()), sizeof(T) * v.size());
+  return v;
+}
+
+int main(int argc, char **argv) {
+  if (argc < 3) return 2;
+  const bool expect_error = argc > 3 && std::strcmp(argv[3], "--expect-error") == 0;
+  std::ifstream f(argv[1], std::ios::binary);
+  auto meta = read_vec<int>(f); // pure, nspin, nfunc ids...
+  occ_b200::BasisArrays basis;
+  basis.pure = meta[0] != 0;
+  const int nspin = meta[1];
+  std::vector<int> func_ids(meta.begin() + 2, meta.end());
+  auto l = read_vec<int>(f), nprim = read_vec<int>(f), atom = read_vec<int>(f);
+  auto origin = read_vec<double>(f), exps = read_vec<double>(f), coefs = read_vec<double>(f);
+  size_t off = 0;
+  for (size_t s = 0; s < l.size(); ++s) {
+    basis.add_shell(l[s], &origin[3 * s], nprim[s], &exps[off], &coefs[off], atom[s]);
+    off += nprim[s];
+  }
+  auto pts = read_vec<double>(f), w = read_vec<double>(f);
+  auto leaf_raw = read_vec<double>(f); // offset, count, cx, cy, cz, radius per leaf
+  std::vector<occ_xc_leaf_t> leaves(leaf_raw.size() / 6);
+  for (size_t i = 0; i < leaves.size(); ++i) {
+    leaves[i].offset = static_cast<size_t>(leaf_raw[6 * i]);
+    leaves[i].count = static_cast<size_t>(leaf_raw[6 * i + 1]);
+    for (int d = 0; d < 3; ++d) leaves[i].center[d] = leaf_raw[6 * i + 2 + d];
+    leaves[i].radius = leaf_raw[6 * i + 5];
+  }
+  auto D = read_vec<double>(f);
+  try {
+    occ_b200::XCBuild xc(basis, w.size(), pts.data(), w.data(), leaves, func_ids,
+                         nspin == 2 ? occ_b200::SpinorbitalKind::Unrestricted : occ_b200::SpinorbitalKind::Restricted);
+    std::vector<double> K(D.size());
+    xc.compute_K_dft(D.data(), K.data());
+    std::ofstream o(argv[2], std::ios::binary);
+    const double sc[3] = {xc.exchange_correlation_energy(), xc.total_density_alpha(), xc.total_density_beta()};
+    o.write(reinterpret_cast<const char *>(sc), sizeof(sc));
+    o.write(reinterpret_cast<const char *>(K.data()), sizeof(double) * K.size());
+    std::printf("ok deriv=%d exc=%.12f\n", xc.density_derivative(), sc[0]);
+    return expect_error ? 1 : 0;
+  } catch (const std::runtime_error &e) {
+    std::printf("runtime_error: %s\n", e.what());
+    return expect_error ? 0 : 1;
+  }
+}

@@ -1,0 +1,84 @@
+"""The C++ host side (adapter/occ_dft_b200.h) over the C ABI: compiled with g++ against libocc_xc_b200.so.
+CPU: it builds, links and turns a library failure (no device) into std::runtime_error. GPU: K/Exc parity with the oracle."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "adapter_driver")
+
+
+def _compile():
+    src = os.path.join(ROOT, "tests", "cpp", "adapter_driver.cpp")
+    lib = os.path.join(ROOT, "occ_b200")
+    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(src), os.path.getmtime(
+            os.path.join(ROOT, "adapter", "occ_dft_b200.h"))):
+        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-o", EXE, src, "-L" + lib, "-locc_xc_b200",
+                               "-Wl,-rpath," + lib])
+    return EXE
+
+
+def _write_case(path, basis, nspin, func_ids, spts, sw, leaves, D):
+    a = basis.as_arrays()
+
+    def vec(f, arr, fmt):
+        arr = np.ascontiguousarray(arr, dtype=fmt)
+        f.write(struct.pack("q", arr.size))
+        f.write(arr.tobytes())
+
+    with open(path, "wb") as f:
+        vec(f, [a["pure"], nspin] + list(func_ids), np.int32)
+        vec(f, a["l"], np.int32)
+        vec(f, a["nprim"], np.int32)
+        vec(f, a["shell_atom"], np.int32)
+        vec(f, a["origin"], np.float64)
+        vec(f, a["exps"], np.float64)
+        vec(f, a["coefs"], np.float64)
+        vec(f, spts, np.float64)
+        vec(f, sw, np.float64)
+        raw = np.stack([leaves["offset"].astype(float), leaves["count"].astype(float), leaves["center"][:, 0],
+                        leaves["center"][:, 1], leaves["center"][:, 2], leaves["radius"]], 1)
+        vec(f, raw, np.float64)
+        vec(f, np.asfortranarray(D).ravel(order="F"), np.float64)
+
+
+def test_adapter_compiles_and_reports_errors_as_exceptions(case, tmp_path):
+    import torch
+    exe = _compile()
+    c = case("water", "def2-svp")
+    b = c["basis"]
+    D = 0.5 * __import__("occ_b200").molecules.synthetic_density(b, 1)
+    p = str(tmp_path / "case.bin")
+    if torch.cuda.is_available():
+        # force a failure: a leaf that runs past the point array
+        leaves = c["leaves"].copy()
+        leaves["count"][-1] += 10_000
+        _write_case(p, b, 1, [101, 130], c["spts"], c["sw"], leaves, D)
+    else:
+        _write_case(p, b, 1, [101, 130], c["spts"], c["sw"], c["leaves"], D)   # fails: no CUDA device, no fallback
+    r = subprocess.run([exe, p, str(tmp_path / "out.bin"), "--expect-error"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "runtime_error" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,nspin", [("b3lyp", 1), ("pbe", 2)])
+def test_adapter_build_matches_oracle(case, oracle, tmp_path, method, nspin):
+    from occ_b200 import dft, molecules
+    exe = _compile()
+    c = case("water", "def2-svp")
+    b = c["basis"]
+    D2 = molecules.synthetic_density(b, nspin)
+    p, o = str(tmp_path / "case.bin"), str(tmp_path / "out.bin")
+    _write_case(p, b, nspin, dft.get_dft_method(method), c["spts"], c["sw"], c["leaves"], 0.5 * D2)  # mo.D = D2 / 2
+    r = subprocess.run([exe, p, o], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = np.fromfile(o)
+    K = raw[3:].reshape(b.nbf, nspin * b.nbf).T
+    names = [n for i in dft.get_dft_method(method) for n, v in oracle.FUNC_IDS.items() if v == i]
+    ref = oracle.xc_build(c["obasis"], c["spts"], c["sw"], c["leaves"], names, nspin, D2)
+    assert np.abs(K - ref["K"]).max() < 1e-9 and abs(raw[0] - ref["exc"]) < 1e-8
+    assert abs(raw[1] - ref["n_alpha"]) < 1e-9
