@@ -300,7 +300,9 @@ def run_b200(args):
             "phases_ms": phases,
             "cpu_baseline": cpu,
             "e2e": {"value": npts_total / (ms_e2e * 1e-3), "unit": "grid-points/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": 8 * n * world, "d2h_bytes_per_step": 8 * (n + 3) * world},
+                    "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n + 24 * world,
+                    "path": "rank 0: pinned host D -> H2D; NCCL broadcast of D; sharded build; NCCL all-reduce of "
+                            "[K|Exc,Na,Nb]; rank 0: D2H of K; every rank: D2H of the 3 scalars"},
             "gpu_launches": int(launches_total * args.steps),
             "clocks": clocks, "setup_seconds": t_setup,
         }

@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_density(BuildParams P, const De
   // 8-column groups of this warp's 32 columns that hold real basis functions (the rest is padding: no DMMA)
   const int ni_valid = min(4, max(0, (nb - (n0 + wn * 32) + 7) >> 3));
 
+  int grow_next = 0;
   auto load_stage = [&](int kc, int stage) {
     double *As = smem + stage * D_STAGE;
     double *Bs = As + D_ASZ;
@@ -101,13 +102,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_density(BuildParams P, const De
       const int col = seg >> 6, s2 = (seg & 63) * 2;
       cp_async16(As + col * D_LDA + s2, Ag + static_cast<size_t>(kc * GK + col) * TILE_P + s2, kc * GK + col < t.nbp);
     }
-    const int k = kc * GK + kk;
-    const bool kvalid = k < nb;
-    const int grow = kvalid ? __ldg(gidx + k) : 0;
+    // grow_next = global row of k = kc*GK + kk, fetched one iteration ahead so the gather never waits on it
+    const bool kvalid = kc * GK + kk < nb;
+    const int grow = grow_next;
 #pragma unroll
     for (int r = 0; r < NBR; ++r)
       cp_async8(Bs + (nn + NROWT * r) * D_LDB + kk, Dm + coloff[r] + grow, kvalid && nvalid[r]);
   };
+  auto fetch_row = [&](int kc) { grow_next = (kc * GK + kk < nb) ? __ldg(gidx + kc * GK + kk) : 0; };
 
   double acc[4][4][2];
 #pragma unroll
@@ -117,19 +119,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_density(BuildParams P, const De
 
 #pragma unroll
   for (int s = 0; s < GSTAGES - 1; ++s) {
+    fetch_row(s);
     if (s < nk) load_stage(s, s);
     cp_async_commit();
   }
+  fetch_row(GSTAGES - 1);
   // interior warps (all 32 columns real) run the branch-free 16-DMMA step; edge warps skip padded 8-column groups
   const bool full = ni_valid == 4;
   for (int kc = 0; kc < nk; ++kc) {
     cp_async_wait<GSTAGES - 2>();
     __syncthreads();
-    if (kc + GSTAGES - 1 < nk) load_stage(kc + GSTAGES - 1, (kc + GSTAGES - 1) % GSTAGES);
-    cp_async_commit();
     const double *As = smem + (kc % GSTAGES) * D_STAGE + wm * 32 + gid;
     const double *Bs = smem + (kc % GSTAGES) * D_STAGE + D_ASZ + (wn * 32 + gid) * D_LDB;
     if (full) {
+      // the refill of the stage consumed last iteration is issued in the MIDDLE of this chunk's DMMAs, so that the
+      // tensor pipe is fed immediately after the barrier instead of waiting behind 8 cp.async per thread
 #pragma unroll
       for (int k4 = 0; k4 < GK / 4; ++k4) {
         double a[4], b[4];
@@ -141,8 +145,18 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_density(BuildParams P, const De
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
           for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        if (k4 == GK / 8 - 1) {
+          if (kc + GSTAGES - 1 < nk) load_stage(kc + GSTAGES - 1, (kc + GSTAGES - 1) % GSTAGES);
+          cp_async_commit();
+          fetch_row(kc + GSTAGES);
+        }
       }
-    } else if (ni_valid > 0) {
+    } else {
+      if (kc + GSTAGES - 1 < nk) load_stage(kc + GSTAGES - 1, (kc + GSTAGES - 1) % GSTAGES);
+      cp_async_commit();
+      fetch_row(kc + GSTAGES);
+    }
+    if (!full && ni_valid > 0) {
 #pragma unroll
       for (int k4 = 0; k4 < GK / 4; ++k4) {
         double a[4];
@@ -282,10 +296,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_vxc(BuildParams P, const VxcIte
   int ib = 0, kc = 0;
   bool full = false;
   int mi_valid = 0;
+  const bool scaled = it.acomp != 0;
+  int grow[4] = {0, 0, 0, 0}; // global rows of this thread's 4 output rows, fetched at the start of every row block
   for (int q = 0; q < nq; ++q) {
     if (kc == 0) {
       mi_valid = min(4, max(0, (nb - (ib * GM + wm * 32) + 7) >> 3));
       full = mi_valid == 4 && ni_valid == 4;
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        const int i = ib * GM + wm * 32 + mi * 8 + gid;
+        grow[mi] = i < nb ? __ldg(gidx + i) : -1;
+      }
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -293,12 +314,28 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_vxc(BuildParams P, const VxcIte
     }
     cp_async_wait<GSTAGES - 2>();
     __syncthreads();
-    if (q + GSTAGES - 1 < nq) load_stage(q + GSTAGES - 1, (q + GSTAGES - 1) % GSTAGES);
-    cp_async_commit();
     const double *As = smem + (q % GSTAGES) * V_STAGE + (wm * 32 + gid) * V_LDA;
     const double *Bs = smem + (q % GSTAGES) * V_STAGE + V_ASZ + (wn * 32 + gid) * V_LDB;
     const double *sc = sct + kc * GK + tig;
-    if (full) {
+    if (full && !scaled) {
+      // B = G slab: no per-point factor on the A fragment (the DMUL would compete with DMMA for the FP64 pipe)
+#pragma unroll
+      for (int k4 = 0; k4 < GK / 4; ++k4) {
+        double a[4], b[4];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) a[mi] = As[mi * 8 * V_LDA + k4 * 4 + tig];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[ni * 8 * V_LDB + k4 * 4 + tig];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        if (k4 == GK / 8 - 1) { // refill issued mid-chunk: the pipe is fed right after the barrier
+          if (q + GSTAGES - 1 < nq) load_stage(q + GSTAGES - 1, (q + GSTAGES - 1) % GSTAGES);
+          cp_async_commit();
+        }
+      }
+    } else if (full) {
 #pragma unroll
       for (int k4 = 0; k4 < GK / 4; ++k4) {
         double a[4], b[4];
@@ -311,8 +348,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_vxc(BuildParams P, const VxcIte
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
           for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        if (k4 == GK / 8 - 1) {
+          if (q + GSTAGES - 1 < nq) load_stage(q + GSTAGES - 1, (q + GSTAGES - 1) % GSTAGES);
+          cp_async_commit();
+        }
       }
-    } else if (mi_valid > 0 && ni_valid > 0) {
+    } else {
+      if (q + GSTAGES - 1 < nq) load_stage(q + GSTAGES - 1, (q + GSTAGES - 1) % GSTAGES);
+      cp_async_commit();
+    }
+    if (!full && mi_valid > 0 && ni_valid > 0) {
 #pragma unroll
       for (int k4 = 0; k4 < GK / 4; ++k4) {
         double b[4];
@@ -333,9 +378,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_vxc(BuildParams P, const VxcIte
       // scatter-add this 128 x 64 block of Ktmp_loc into the full matrix (dft.h:361-369)
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi) {
-        const int i = ib * GM + wm * 32 + mi * 8 + gid;
-        if (i < nb) {
-          double *dst = Kt + __ldg(gidx + i);
+        if (grow[mi] >= 0) {
+          double *dst = Kt + grow[mi];
 #pragma unroll
           for (int ni = 0; ni < 4; ++ni) {
             if (cvalid[ni][0]) red_add_f64(dst + coloff[ni][0], acc[mi][ni][0]);

@@ -64,13 +64,20 @@ class DistributedDFT:
                 allreduce_partial(self.d_out, self.group)
         return self.d_out
 
-    def build(self, D2_host: torch.Tensor, K_host: torch.Tensor):
-        """Host-to-host build: D2_host / K_host are (pinned) CPU tensors holding column-major matrices."""
+    def build(self, D2_host: torch.Tensor | None, K_host: torch.Tensor | None):
+        """Host-to-host build as the reference's single-process SCF driver would see it: rank 0 owns the host
+        matrices (pinned CPU tensors, column-major).  Rank 0 copies D to its GPU, D is broadcast to the other GPUs over
+        NVLink (NCCL), every rank builds its shard, the packed result is all-reduced and rank 0 copies K back.
+        Other ranks pass None (or buffers that are ignored). Returns (exc, n_alpha, n_beta) on every rank."""
         n = self.nspin * self.nbf * self.nbf
         with torch.cuda.stream(self.stream):
-            self.d_D.copy_(D2_host.view(-1), non_blocking=True)
+            if self.rank == 0:
+                self.d_D.copy_(D2_host.view(-1), non_blocking=True)
+            if self.world > 1:
+                dist.broadcast(self.d_D, src=0, group=self.group)
             out = self.build_device()
-            K_host.view(-1)[:n].copy_(out[:n], non_blocking=True)
+            if self.rank == 0 and K_host is not None:
+                K_host.view(-1)[:n].copy_(out[:n], non_blocking=True)
             self._sc_host.copy_(out[n:n + 3], non_blocking=True)
         self.stream.synchronize()
         return float(self._sc_host[0]), float(self._sc_host[1]), float(self._sc_host[2])
