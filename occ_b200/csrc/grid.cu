@@ -147,10 +147,16 @@ constexpr int BECKE_THREADS = 64;
 // cell_k = prod_{j != k, ascending} s_kj with s_kj = (1 - v_kj)/2 for j < k, (1 + v_jk)/2 for j > k, where v_ij
 // (i > j) is the thrice-iterated Becke polynomial of the TA-adjusted confocal coordinate — the same factors,
 // in the same order, as calculate_atomic_grid_weights_impl (grid_utils.cpp:149-200) accumulates them.
+// grid = (blocks of the largest atom grid, natoms): blockIdx.y is the owning atom, atom_off its first point
 __global__ void k_becke(int natoms, const double *__restrict__ pos, const double *__restrict__ dist,
-                        const double *__restrict__ aij, int owner, int npts, const double *__restrict__ xyz,
-                        double *__restrict__ w) {
+                        const double *__restrict__ aij, const size_t *__restrict__ atom_off,
+                        const double *__restrict__ xyz_all, double *__restrict__ w_all) {
   extern __shared__ double gd[]; // [natoms][BECKE_THREADS]
+  const int owner = blockIdx.y;
+  const int npts = static_cast<int>(atom_off[owner + 1] - atom_off[owner]);
+  if (static_cast<int>(blockIdx.x) * BECKE_THREADS >= npts) return;
+  const double *xyz = xyz_all + 3 * atom_off[owner];
+  double *w = w_all + atom_off[owner];
   const int t = threadIdx.x;
   const int p = blockIdx.x * BECKE_THREADS + t;
   const bool valid = p < npts;
@@ -401,17 +407,23 @@ int occ_xc_grid_create(int natoms, const int *Z, const double *pos, const occ_xc
     if (e == cudaSuccess && smem > 220 * 1024) {
       e = cudaErrorInvalidValue;
     }
-    off = 0;
-    for (int a = 0; a < natoms && e == cudaSuccess; ++a) {
-      const int n = static_cast<int>(g->atom_npts[a]);
-      if (n > 0)
-        k_becke<<<(n + BECKE_THREADS - 1) / BECKE_THREADS, BECKE_THREADS, smem>>>(natoms, d_pos, d_dist, d_aij, a, n,
-                                                                                 d_xyz + 3 * off, d_w + off);
-      off += n;
+    std::vector<size_t> atom_off(natoms + 1, 0);
+    size_t max_n = 0;
+    for (int a = 0; a < natoms; ++a) {
+      atom_off[a + 1] = atom_off[a] + g->atom_npts[a];
+      max_n = std::max(max_n, g->atom_npts[a]);
+    }
+    size_t *d_off = nullptr;
+    chk(cudaMalloc(&d_off, atom_off.size() * sizeof(size_t)));
+    if (e == cudaSuccess)
+      chk(cudaMemcpy(d_off, atom_off.data(), atom_off.size() * sizeof(size_t), cudaMemcpyHostToDevice));
+    if (e == cudaSuccess && max_n > 0) {
+      const dim3 grid_dim(static_cast<unsigned>((max_n + BECKE_THREADS - 1) / BECKE_THREADS), natoms);
+      k_becke<<<grid_dim, BECKE_THREADS, smem>>>(natoms, d_pos, d_dist, d_aij, d_off, d_xyz, d_w);
     }
     if (e == cudaSuccess) chk(cudaGetLastError());
     if (e == cudaSuccess) chk(cudaMemcpy(g->w.data(), d_w, total * sizeof(double), cudaMemcpyDeviceToHost));
-    cudaFree(d_pos); cudaFree(d_dist); cudaFree(d_aij); cudaFree(d_xyz); cudaFree(d_w);
+    cudaFree(d_pos); cudaFree(d_dist); cudaFree(d_aij); cudaFree(d_xyz); cudaFree(d_w); cudaFree(d_off);
     if (e != cudaSuccess) {
       delete g;
       return occ_xc_set_error((std::string("occ_xc_grid_create: CUDA error in the Becke partition: ") +

@@ -206,7 +206,10 @@ struct occ_xc_handle {
   DensItem *d_dens = nullptr, *d_g = nullptr;
   VxcItem *d_vxc = nullptr;
   double *d_D = nullptr, *d_Dsym = nullptr, *d_Ktmp = nullptr, *d_K = nullptr, *d_scalars = nullptr;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  double *scratch2 = nullptr; // workspace of the second lane
+  int lanes = 1;
   bool profiling = false;
   double phase_ms[OCC_XC_NPHASES] = {0, 0, 0, 0, 0, 0, 0};
   size_t launches = 0;
@@ -290,6 +293,9 @@ void occ_xc_destroy(occ_xc_handle *h) {
   cudaSetDevice(h->device);
   for (void *p : h->allocs) cudaFree(p);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
 }
 
@@ -576,6 +582,10 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
     const size_t nt = std::max(h->ntiles, 1);
     const size_t ksz = static_cast<size_t>(nspin) * nbf * nbf;
     rc |= dev_alloc(h, &P.scratch, max_scratch);
+    // second lane is opt-in (options.reserved[1] == 2): measured on B200 it buys nothing, the block scheduler
+    // does not co-schedule the second lane's kernels while the first lane fills the SMs (profiles/r01_experiments.md)
+    h->lanes = (opt && opt->reserved[1] == 2 && h->batches.size() >= 2) ? 2 : 1;
+    if (h->lanes == 2) rc |= dev_alloc(h, &h->scratch2, max_scratch);
     rc |= dev_alloc(h, &P.acc, nt * nspin * NACC * TILE_P);
     rc |= dev_alloc(h, &P.coef, nt * nspin * NCOEF * TILE_P);
     rc |= dev_alloc(h, &P.leaf_skip, std::max(h->nleaves, 1));
@@ -601,7 +611,10 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
   P.density_threshold = density_threshold;
   P.debug = opt ? opt->reserved[0] : 0;
   for (int s = 0; s < nspin; ++s) P.Ktmp[s] = h->d_Ktmp + static_cast<size_t>(s) * nbf;
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
     occ_xc_destroy(h);
     return fail("occ_xc_create: cudaStreamCreate failed");
   }
@@ -647,7 +660,20 @@ int occ_xc_build_device(occ_xc_handle *h, const double *D2_dev, double *K_dev, d
   }
   CUDA_TRY(cudaMemsetAsync(h->d_Ktmp, 0, ksz * sizeof(double), st));
   PHASE_END(0);
-  for (const Batch &b : h->batches) {
+  // Two lanes: batches alternate between the caller's stream and an auxiliary stream, each lane with its own AO
+  // workspace.  The HBM-bound phases of one lane (collocation, G slab) and the tails of its DMMA kernels then overlap
+  // with the tensor-bound kernels of the other lane.  Profiling runs single-lane so phase times stay attributable.
+  const int lanes = prof ? 1 : h->lanes;
+  if (lanes == 2) {
+    CUDA_TRY(cudaEventRecord(h->ev_fork, st));
+    CUDA_TRY(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+  }
+  cudaStream_t main_st = st;
+  for (size_t bi = 0; bi < h->batches.size(); ++bi) {
+    const Batch &b = h->batches[bi];
+    const bool second = lanes == 2 && (bi & 1);
+    st = second ? h->aux_stream : main_st;
+    P.scratch = second ? h->scratch2 : h->P.scratch;
     PHASE_BEGIN();
     launch_collocate(P, h->d_colloc + b.colloc_off, static_cast<int>(b.ncolloc), st);
     PHASE_END(1);
@@ -665,6 +691,11 @@ int occ_xc_build_device(occ_xc_handle *h, const double *D2_dev, double *K_dev, d
     PHASE_BEGIN();
     launch_vxc(P, h->d_vxc + b.vxc_off, static_cast<int>(b.nvxc), st);
     PHASE_END(5);
+  }
+  st = main_st;
+  if (lanes == 2) {
+    CUDA_TRY(cudaEventRecord(h->ev_join, h->aux_stream));
+    CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join, 0));
   }
   PHASE_BEGIN();
   launch_finalize(P, h->nleaves, K_dev, scalars_dev, st);

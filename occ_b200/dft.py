@@ -72,7 +72,7 @@ class DFT:
     def __init__(self, method: str, basis: AOBasis, grid: GridHierarchy, spinorbital_kind: str = RESTRICTED,
                  device: int = -1, rank: int = 0, world_size: int = 1, batch_bytes: int = 0,
                  density_threshold: float = 1e-10, xc_screening_threshold: float = 1e-10, shell_extents=None,
-                 debug: int = 0):
+                 debug: int = 0, lanes: int = 1):
         self.basis = basis
         self.method = method
         self.func_ids = np.array(get_dft_method(method), dtype=np.int32)
@@ -85,6 +85,7 @@ class DFT:
         ext = None if shell_extents is None else np.ascontiguousarray(shell_extents, dtype=np.float64)
         opt = OptionsT(device, rank, world_size, batch_bytes)
         opt.reserved[0] = debug
+        opt.reserved[1] = lanes
         self._h = C.c_void_p()
         check(lib().occ_xc_create(self._basis_arrays.ref, C.c_size_t(len(w)), ptr(pts), ptr(w), C.c_size_t(len(leaves)),
                                   ptr(leaves), ptr(ext) if ext is not None else None, C.c_int(len(self.func_ids)),
