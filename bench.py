@@ -269,6 +269,13 @@ def run_b200(args):
                           "avg_launch_ms": ms_launch, "tflops": fl / (phases[name] * 1e-3) / 1e12 if phases[name] > 0 else 0.0}
         dom = max(kern, key=lambda k: kern[k]["ms_per_build"])
         achieved = kern[dom]["tflops"]
+        traffic = None
+        try:   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload)
+            if tj and tj.get("batch_mb") == args.batch_mb and world == 1:
+                traffic = tj.get("k_" + dom)
+        except Exception:
+            pass
         cpu = None
         if not args.no_cpu_baseline:
             res = cpu_build_sample(basis, method, nspin, np.asfortranarray(hD.numpy().reshape(nbf, nspin * nbf).T), h,
@@ -293,7 +300,8 @@ def run_b200(args):
             "algorithmic_tflops": flops_total / (ms_dev * 1e-3) / 1e12,
             "fp64_tensor_frac_whole_build": flops_total / (ms_dev * 1e-3) / 1e12 / (FP64_TENSOR_PEAK_TFLOPS * world),
             "roofline": {"bound": "tensor", "kernel": "k_" + dom, "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS,
-                         "unit": "TFLOP/s", "frac": achieved / FP64_TENSOR_PEAK_TFLOPS, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / FP64_TENSOR_PEAK_TFLOPS, "traffic": traffic,
+                         "algorithmic_flops_per_launch": 0.5 * info["flops_per_build"] / max(1, info["nbatches"]),
                          "peak_source": "measured DMMA.8x8x4 microbenchmark on this pool's B200 "
                                         "(profiles/r01_fp64_peaks_b200.jsonl); MEASURED_PEAKS.json has no FP64 entry",
                          "kernels": kern},

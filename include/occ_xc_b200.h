@@ -67,7 +67,8 @@ typedef struct {
                             handles (one per GPU / process); every handle returns a PARTIAL K, Exc, N that the
                             caller sums (NCCL all-reduce).  world_size <= 1: whole grid. */
   size_t batch_bytes;    /* AO-value workspace per batch of leaves (0 = default 4 GiB) */
-  int reserved[8];
+  int reserved[8];       /* [0] developer timing switches, [1] 2 = second stream lane, [2] 1 = handle can also run
+                            occ_xc_gradient (needs basis->shell_atom, l <= 4; larger workspace) */
 } occ_xc_options_t;
 
 typedef struct occ_xc_handle occ_xc_handle;
@@ -99,6 +100,12 @@ int occ_xc_build(occ_xc_handle *h, const double *D2, double *K, double *exc, dou
  * scalars_dev receives {exc, n_alpha, n_beta}.  D2_dev / K_dev as above but resident in HBM. */
 int occ_xc_build_device(occ_xc_handle *h, const double *D2_dev, double *K_dev, double *scalars_dev,
                         void *cuda_stream);
+
+/* SURVEY 8(f) rank 1 — the XC nuclear gradient, Mat3N DFT::compute_xc_gradient(mo, Schwarz) without the VV10 term
+ * (src/dft/dft_gradients.cpp:68-109 -> compute_xc_gradient_impl, include/occ/dft/dft.h:598-749,
+ * src/dft/dft_gradient_kernels.cpp).  HOST buffers; D2 as in occ_xc_build; gradient is 3 x natoms column-major
+ * (this rank's shard: partial sums add up over ranks).  The handle must have been created with options.reserved[2] = 1. */
+int occ_xc_gradient(occ_xc_handle *h, const double *D2, double *gradient);
 
 /* Geometry-only facts of the handle (this rank's shard) */
 typedef struct {

@@ -170,3 +170,173 @@ void launch_collocate(const BuildParams &P, const CollocItem *items, int nitems,
 }
 
 } // namespace xcb
+
+// ------------------------------------------------------------------------------------------------
+// Second pass for the XC nuclear gradient (reference: accumulate_gradient_contribution_{R,U}<1|2>,
+// src/dft/dft_gradient_kernels.cpp:47-157,214-470): the AO second derivatives are recomputed from the shell
+// parameters and immediately folded with the per-point functional coefficients, so that only the combinations
+//   H[s][d]  = c0_s phi_d + sum_e c_{s,e} phi_{d e}        (the "aow_d" of the reference, d = x, y, z)
+//   S[s][de] = 2 ct_s phi_{d e}                             (meta-GGA: vtau/2 phi_{d e})
+// reach HBM (3 or 9 slabs per spin) instead of the six raw second-derivative slabs.
+// ------------------------------------------------------------------------------------------------
+namespace xcb {
+
+template <int L, bool PURE>
+__device__ __forceinline__ void shell_hessian_combo(double x, double y, double z, double S0, double S1, double S2,
+                                                    double fac, const double *__restrict__ cf /* c0,cx,cy,cz,ct */,
+                                                    bool mgga, double *__restrict__ oH, size_t slab,
+                                                    double *__restrict__ oS) {
+  constexpr int NC = (L + 1) * (L + 2) / 2;
+  constexpr int NS = PURE && L > 0 ? 2 * L + 1 : NC;
+  double xp[L + 1], yp[L + 1], zp[L + 1];
+  xp[0] = yp[0] = zp[0] = 1.0;
+#pragma unroll
+  for (int i = 1; i <= L; ++i) {
+    xp[i] = xp[i - 1] * x;
+    yp[i] = yp[i - 1] * y;
+    zp[i] = zp[i - 1] * z;
+  }
+  const double q[3] = {x, y, z};
+  double h[3][NC], s2[6][NC];
+  int idx = 0;
+#pragma unroll
+  for (int lx = L; lx >= 0; --lx) {
+#pragma unroll
+    for (int ly = L - lx; ly >= 0; --ly) {
+      const int lz = L - lx - ly;
+      const int e[3] = {lx, ly, lz};
+      const double A = xp[lx] * yp[ly] * zp[lz];
+      // first derivatives of the monomial
+      const double A1[3] = {lx ? lx * (xp[lx ? lx - 1 : 0] * yp[ly] * zp[lz]) : 0.0,
+                            ly ? ly * (xp[lx] * yp[ly ? ly - 1 : 0] * zp[lz]) : 0.0,
+                            lz ? lz * (xp[lx] * yp[ly] * zp[lz ? lz - 1 : 0]) : 0.0};
+      double d1[3], d2[6];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) d1[k] = S1 * q[k] * A + S0 * A1[k];
+      // second derivatives of the monomial
+      const double Axx = lx > 1 ? lx * (lx - 1) * (xp[lx > 1 ? lx - 2 : 0] * yp[ly] * zp[lz]) : 0.0;
+      const double Ayy = ly > 1 ? ly * (ly - 1) * (xp[lx] * yp[ly > 1 ? ly - 2 : 0] * zp[lz]) : 0.0;
+      const double Azz = lz > 1 ? lz * (lz - 1) * (xp[lx] * yp[ly] * zp[lz > 1 ? lz - 2 : 0]) : 0.0;
+      const double Axy = (lx && ly) ? lx * ly * (xp[lx ? lx - 1 : 0] * yp[ly ? ly - 1 : 0] * zp[lz]) : 0.0;
+      const double Axz = (lx && lz) ? lx * lz * (xp[lx ? lx - 1 : 0] * yp[ly] * zp[lz ? lz - 1 : 0]) : 0.0;
+      const double Ayz = (ly && lz) ? ly * lz * (xp[lx] * yp[ly ? ly - 1 : 0] * zp[lz ? lz - 1 : 0]) : 0.0;
+      d2[0] = S2 * x * x * A + S1 * (2.0 * x * A1[0] + A) + S0 * Axx;
+      d2[1] = S2 * x * y * A + S1 * (x * A1[1] + y * A1[0]) + S0 * Axy;
+      d2[2] = S2 * x * z * A + S1 * (x * A1[2] + z * A1[0]) + S0 * Axz;
+      d2[3] = S2 * y * y * A + S1 * (2.0 * y * A1[1] + A) + S0 * Ayy;
+      d2[4] = S2 * y * z * A + S1 * (y * A1[2] + z * A1[1]) + S0 * Ayz;
+      d2[5] = S2 * z * z * A + S1 * (2.0 * z * A1[2] + A) + S0 * Azz;
+      (void)e;
+      h[0][idx] = cf[0] * d1[0] + cf[1] * d2[0] + cf[2] * d2[1] + cf[3] * d2[2];
+      h[1][idx] = cf[0] * d1[1] + cf[1] * d2[1] + cf[2] * d2[3] + cf[3] * d2[4];
+      h[2][idx] = cf[0] * d1[2] + cf[1] * d2[2] + cf[2] * d2[4] + cf[3] * d2[5];
+      if (mgga) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s2[k][idx] = 2.0 * cf[4] * d2[k];
+      }
+      ++idx;
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < NS; ++m) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      double v;
+      if (!PURE || L == 0) {
+        v = h[d][m < NC ? m : 0];
+      } else {
+        const double *tab = c_c2s.coef + c_c2s.off[L] + m * NC;
+        v = 0.0;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) v += tab[i] * h[d][i];
+      }
+      oH[d * slab + m * TILE_P] = v * fac;
+    }
+    if (mgga) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        double v;
+        if (!PURE || L == 0) {
+          v = s2[k][m < NC ? m : 0];
+        } else {
+          const double *tab = c_c2s.coef + c_c2s.off[L] + m * NC;
+          v = 0.0;
+#pragma unroll
+          for (int i = 0; i < NC; ++i) v += tab[i] * s2[k][i];
+        }
+        oS[k * slab + m * TILE_P] = v * fac;
+      }
+    }
+  }
+}
+
+template <bool PURE>
+__global__ void __launch_bounds__(TILE_P) k_collocate_h(BuildParams P, const CollocItem *__restrict__ items) {
+  const CollocItem it = items[blockIdx.x];
+  const TileDesc t = P.tiles[it.tile];
+  if (P.leaf_skip[t.leaf]) return;
+  const int p = threadIdx.x;
+  const bool valid = p < t.count;
+  const double px = P.px[t.pt0 + p], py = P.py[t.pt0 + p], pz = P.pz[t.pt0 + p];
+  const size_t slab = static_cast<size_t>(t.nbp) * TILE_P;
+  double *base = P.scratch + t.scr_off + p;
+  const DeviceBasis &B = P.basis;
+  const bool mgga = P.deriv >= 2;
+  for (int sp = 0; sp < P.nspin; ++sp) {
+    double cf[5];
+    const double *cg = P.coef + (static_cast<size_t>(it.tile) * P.nspin + sp) * NCOEF * TILE_P + p;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) cf[k] = cg[k * TILE_P];
+    if (!mgga) cf[4] = 0.0;
+    double *oH0 = base + static_cast<size_t>(P.slab_H + 3 * sp) * slab;
+    double *oS0 = base + static_cast<size_t>(P.slab_S + 6 * sp) * slab;
+    for (int s = it.s0; s < it.s1; ++s) {
+      const int sh = __ldg(P.shell_list + t.sh_off + s);
+      const int col = __ldg(P.shell_col + t.sh_off + s);
+      const int L = __ldg(B.l + sh);
+      const int np = __ldg(B.nprim + sh);
+      const int po = __ldg(B.prim_off + sh);
+      const double x = px - __ldg(B.origin + 3 * sh), y = py - __ldg(B.origin + 3 * sh + 1),
+                   z = pz - __ldg(B.origin + 3 * sh + 2);
+      const double r2 = x * x + y * y + z * z;
+      double S0 = 0.0, S1 = 0.0, S2 = 0.0;
+      for (int k = 0; k < np; ++k) {
+        const double a = __ldg(B.exps + po + k);
+        const double T1 = __ldg(B.coefs + po + k) * exp(-a * r2);
+        const double a2 = -2.0 * a;
+        S0 += T1;
+        S1 += a2 * T1;
+        S2 += a2 * a2 * T1;
+      }
+      if (!valid) S0 = S1 = S2 = 0.0;
+      const double fac = common_fac_dev(L, PURE);
+      double *oH = oH0 + static_cast<size_t>(col) * TILE_P;
+      double *oS = oS0 + static_cast<size_t>(col) * TILE_P;
+      switch (L) {
+      case 0: shell_hessian_combo<0, PURE>(x, y, z, S0, S1, S2, fac, cf, mgga, oH, slab, oS); break;
+      case 1: shell_hessian_combo<1, PURE>(x, y, z, S0, S1, S2, fac, cf, mgga, oH, slab, oS); break;
+      case 2: shell_hessian_combo<2, PURE>(x, y, z, S0, S1, S2, fac, cf, mgga, oH, slab, oS); break;
+      case 3: shell_hessian_combo<3, PURE>(x, y, z, S0, S1, S2, fac, cf, mgga, oH, slab, oS); break;
+      case 4: shell_hessian_combo<4, PURE>(x, y, z, S0, S1, S2, fac, cf, mgga, oH, slab, oS); break;
+      default: break; // l > 4 is rejected at create() for gradient handles
+      }
+    }
+    if (it.last) {
+      const int nsl = mgga ? 9 : 3;
+      for (int col = t.nb; col < t.nbp; ++col)
+        for (int k = 0; k < nsl; ++k) {
+          double *o = (k < 3 ? oH0 + k * slab : oS0 + (k - 3) * slab) + static_cast<size_t>(col) * TILE_P;
+          o[0] = 0.0;
+        }
+    }
+  }
+}
+
+void launch_collocate_h(const BuildParams &P, const CollocItem *items, int nitems, void *stream) {
+  if (nitems <= 0) return;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (P.basis.pure) k_collocate_h<true><<<nitems, TILE_P, 0, st>>>(P, items);
+  else k_collocate_h<false><<<nitems, TILE_P, 0, st>>>(P, items);
+}
+
+} // namespace xcb

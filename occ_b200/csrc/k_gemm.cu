@@ -62,18 +62,23 @@ __device__ __forceinline__ void red_add_f64(double *addr, double v) {
 // ------------------------------------------------------------------------------------------------
 // density
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 2) k_density(BuildParams P, const DensItem *__restrict__ items) {
-  extern __shared__ __align__(16) double smem[];
-  const DensItem it = items[blockIdx.x];
+// MODE 0: density (epilogue = row-dots with the AO slabs).  MODE 1: XC nuclear gradient:
+// acc = A . D_s^T with A = phi (acomp 0), G_s (acomp 1) or phi_e (acomp 2+e, meta-GGA); the epilogue multiplies by
+// the companion slabs (H_s,d / phi_d / S_s,de), sums over the 128 points and scatters per atom:
+//   grad[A][d] += f * sum_p sum_{mu in A} companion_d[p, mu] * acc[p, mu]
+// which is  -2 sum_{mu in A, nu} D_{mu nu} V_d(mu, nu)  of dft_gradient_kernels.cpp:540-592 without ever forming V_d.
+template <int MODE> __device__ __forceinline__ void gemm_xd_body(const BuildParams &P, const DensItem it, double *smem) {
   const TileDesc t = P.tiles[it.tile];
+  if (MODE == 1 && P.leaf_skip[t.leaf]) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;
   const int wm = warp & 3, wn = warp >> 2;
   const int nb = t.nb;
   const int nk = (nb + GK - 1) / GK;
   const size_t slab = static_cast<size_t>(t.nbp) * TILE_P;
-  const double *Ag = P.scratch + t.scr_off + static_cast<size_t>(it.acomp) * slab;
-  const double *Dm = (it.acomp == 0 ? P.Drho : P.Dtau)[it.spin];
+  const int a_slab = MODE == 0 ? it.acomp : (it.acomp == 0 ? 0 : (it.acomp == 1 ? P.slab_G + it.spin : it.acomp - 1));
+  const double *Ag = P.scratch + t.scr_off + static_cast<size_t>(a_slab) * slab;
+  const double *Dm = MODE == 0 ? (it.acomp == 0 ? P.Drho : P.Dtau)[it.spin] : P.DT[it.spin];
   const int *gidx = P.bf_index + t.bf_off;
   const int n0 = it.jb * GN;
 
@@ -174,6 +179,42 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_density(BuildParams P, const De
   }
   cp_async_wait<0>();
 
+  if (MODE == 1) {
+    // gradient epilogue
+    const double *cbase = P.scratch + t.scr_off + static_cast<size_t>(n0 + wn * 32 + 2 * tig) * TILE_P + wm * 32 + gid;
+    const int *batom = P.bf_atom + t.bf_off + n0 + wn * 32 + 2 * tig;
+#pragma unroll 1
+    for (int d = 0; d < 3; ++d) {
+      int cslab;
+      if (it.acomp == 0) cslab = P.slab_H + 3 * it.spin + d;
+      else if (it.acomp == 1) cslab = 1 + d;
+      else {
+        const int e = it.acomp - 2, lo = d < e ? d : e, hi = d < e ? e : d;
+        cslab = P.slab_S + 6 * it.spin + (lo == 0 ? hi : (lo == 1 ? 2 + hi : 5)); // xx xy xz yy yz zz
+      }
+      const double *pc = cbase + static_cast<size_t>(cslab) * slab;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+          s0 += pc[(ni * 8) * TILE_P + mi * 8] * acc[mi][ni][0];
+          s1 += pc[(ni * 8 + 1) * TILE_P + mi * 8] * acc[mi][ni][1];
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        if (gid == 0) {
+          const int col = n0 + wn * 32 + ni * 8 + 2 * tig;
+          if (col < nb) red_add_f64(P.grad + 3 * __ldg(batom + ni * 8) + d, P.grad_factor * s0);
+          if (col + 1 < nb) red_add_f64(P.grad + 3 * __ldg(batom + ni * 8 + 1) + d, P.grad_factor * s1);
+        }
+      }
+    }
+    return;
+  }
   // epilogue: row-dot the X tile (registers) with the AO slabs of the same columns
   double *accp = P.acc + (static_cast<size_t>(it.tile) * P.nspin + it.spin) * NACC * TILE_P;
   const int c_begin = it.acomp == 0 ? 0 : it.acomp;
@@ -197,6 +238,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_density(BuildParams P, const De
   }
 }
 
+__global__ void __launch_bounds__(NTHREADS, 2) k_density(BuildParams P, const DensItem *__restrict__ items) {
+  extern __shared__ __align__(16) double smem[];
+  gemm_xd_body<0>(P, items[blockIdx.x], smem);
+}
+__global__ void __launch_bounds__(NTHREADS, 2) k_xc_gradient(BuildParams P, const DensItem *__restrict__ items) {
+  extern __shared__ __align__(16) double smem[];
+  gemm_xd_body<1>(P, items[blockIdx.x], smem);
+}
+
 // ------------------------------------------------------------------------------------------------
 // G slab: G_s = c0 phi + cx phi_x + cy phi_y + cz phi_z  (the bracket of xc_potential_matrix.cpp:33-39 / :86-99)
 // ------------------------------------------------------------------------------------------------
@@ -211,7 +261,7 @@ __global__ void __launch_bounds__(TILE_P) k_gbuild(BuildParams P, const DensItem
     const double *cf = P.coef + (static_cast<size_t>(it.tile) * P.nspin + s) * NCOEF * TILE_P + p;
     const double c0 = cf[0];
     double *G = const_cast<double *>(phi) + static_cast<size_t>(P.ncomp + s) * slab;
-    if (P.ncomp > 1) {
+    if (P.deriv >= 1) {
       const double cx = cf[TILE_P], cy = cf[2 * TILE_P], cz = cf[3 * TILE_P];
 #pragma unroll 4
       for (int j = 0; j < GN; ++j) {
@@ -405,6 +455,35 @@ void launch_density(const BuildParams &P, const DensItem *items, int nitems, voi
     configured = true;
   }
   k_density<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
+}
+
+void launch_grad_gemm(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
+  if (nitems <= 0) return;
+  static bool configured = false;
+  const int smem_bytes = GSTAGES * D_STAGE * sizeof(double);
+  if (!configured) {
+    cudaFuncSetAttribute(k_xc_gradient, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    configured = true;
+  }
+  k_xc_gradient<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
+}
+
+__global__ void k_transpose(const double *__restrict__ D, double *__restrict__ DT, int n, int ld) {
+  __shared__ double tl[32][33];
+  const int bi = blockIdx.x * 32, bj = blockIdx.y * 32, tx = threadIdx.x, ty = threadIdx.y;
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi + tx, j = bj + r;
+    tl[r][tx] = (i < n && j < n) ? D[static_cast<size_t>(j) * ld + i] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bj + tx, j = bi + r; // DT(i, j) = D(j, i)
+    if (i < n && j < n) DT[static_cast<size_t>(j) * ld + i] = tl[tx][r];
+  }
+}
+void launch_transpose(const double *D, double *DT, int nbf, int ld, void *stream) {
+  dim3 grid((nbf + 31) / 32, (nbf + 31) / 32);
+  k_transpose<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(D, DT, nbf, ld);
 }
 
 void launch_gbuild(const BuildParams &P, const DensItem *items, int nitems, void *stream) {

@@ -17,10 +17,6 @@
 #include <string>
 #include <vector>
 
-namespace xcb {
-void launch_gbuild(const BuildParams &P, const DensItem *items, int nitems, void *stream);
-}
-
 using namespace xcb;
 
 static thread_local std::string g_last_error;
@@ -184,7 +180,7 @@ static std::vector<size_t> partition_by_cost(const std::vector<double> &costs, i
 // ------------------------------------------------------------------------------------------------
 struct Batch {
   int tile0, ntiles, leaf0, nleaves;
-  size_t colloc_off, ncolloc, dens_off, ndens, g_off, ng, vxc_off, nvxc;
+  size_t colloc_off, ncolloc, dens_off, ndens, g_off, ng, vxc_off, nvxc, grad_off, ngrad;
 };
 
 struct occ_xc_handle {
@@ -203,7 +199,10 @@ struct occ_xc_handle {
   std::vector<void *> allocs;
   size_t alloc_bytes = 0;
   CollocItem *d_colloc = nullptr;
-  DensItem *d_dens = nullptr, *d_g = nullptr;
+  DensItem *d_dens = nullptr, *d_g = nullptr, *d_gradit = nullptr;
+  bool gradient = false;
+  int natoms = 0;
+  double *d_DT = nullptr, *d_grad = nullptr;
   VxcItem *d_vxc = nullptr;
   double *d_D = nullptr, *d_Dsym = nullptr, *d_Ktmp = nullptr, *d_K = nullptr, *d_scalars = nullptr;
   cudaStream_t stream = nullptr, aux_stream = nullptr;
@@ -324,12 +323,15 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
   const int rank = world > 1 ? opt->rank : 0;
   if (rank < 0 || rank >= world) return fail("occ_xc_create: rank outside [0, world_size)");
   const size_t batch_bytes = (opt && opt->batch_bytes) ? opt->batch_bytes : (size_t(4096) << 20);
+  const bool want_grad = opt && opt->reserved[2] == 1; // handle can also run occ_xc_gradient
+  if (want_grad && !basis->shell_atom) return fail("occ_xc_create: the gradient option needs basis->shell_atom");
 
   const int nsh = basis->nsh, pure = basis->pure ? 1 : 0;
   std::vector<int> first_bf(nsh);
   int nbf = 0;
   for (int s = 0; s < nsh; ++s) {
     if (basis->l[s] < 0 || basis->l[s] > MAX_L) return fail("occ_xc_create: shell angular momentum outside 0..6");
+    if (want_grad && basis->l[s] > 4) return fail("occ_xc_create: the gradient option supports l <= 4");
     first_bf[s] = nbf;
     nbf += shell_size(basis->l[s], pure);
   }
@@ -396,11 +398,15 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
   h->nsh = nsh;
   h->nspin = nspin;
   h->deriv = deriv;
-  h->ncomp = deriv >= 1 ? 4 : 1;
+  h->ncomp = (deriv >= 1 || want_grad) ? 4 : 1;
   h->pure = pure;
+  h->gradient = want_grad;
+  if (want_grad)
+    for (int s = 0; s < nsh; ++s) h->natoms = std::max(h->natoms, basis->shell_atom[s] + 1);
   h->nb_min = 1 << 30;
   h->nb_max = 0;
-  const int nslab = h->ncomp + nspin;
+  const int nslab = h->ncomp + nspin + (want_grad && deriv >= 1 ? 3 * nspin : 0) + (want_grad && deriv >= 2 ? 6 * nspin : 0);
+  std::vector<int> bf_atom;
 
   // ---- tiles, padded points, per-leaf index lists ----
   std::vector<double> px, py, pz, pw;
@@ -423,7 +429,10 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
       const int s = shell_list[e.sh_off + k];
       my_shell_list.push_back(s);
       my_shell_col.push_back(shell_col[e.sh_off + k]);
-      for (int c = 0; c < shell_size(basis->l[s], pure); ++c) h->h_bf_index.push_back(first_bf[s] + c);
+      for (int c = 0; c < shell_size(basis->l[s], pure); ++c) {
+        h->h_bf_index.push_back(first_bf[s] + c);
+        bf_atom.push_back(basis->shell_atom ? basis->shell_atom[s] : 0);
+      }
     }
     const int nbp = (e.nb + NB_PAD - 1) / NB_PAD * NB_PAD;
     for (int k = 0; k < ld.ntiles; ++k) {
@@ -460,7 +469,7 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
 
   // ---- batches of consecutive leaves under the workspace budget; per-phase work lists ----
   std::vector<CollocItem> colloc;
-  std::vector<DensItem> dens, gitems;
+  std::vector<DensItem> dens, gitems, gradit;
   std::vector<VxcItem> vxc;
   size_t max_scratch = 0;
   {
@@ -494,6 +503,7 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
       b.dens_off = dens.size();
       b.g_off = gitems.size();
       b.vxc_off = vxc.size();
+      b.grad_off = gradit.size();
       for (int ti : order) {
         const TileDesc &t = h->h_tiles[ti];
         for (int s0 = 0; s0 < t.nsh; s0 += 16) {
@@ -522,6 +532,20 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
               vi.acomp = static_cast<signed char>(ac);
               vxc.push_back(vi);
             }
+        if (want_grad) {
+          // acomp: 0 A = phi (companions H), 1 A = G (companions grad phi), 2..4 A = phi_e (companions S), see k_gemm.cu
+          const int w0 = deriv == 0 ? 1 : 0, w1 = deriv == 0 ? 1 : (deriv == 1 ? 1 : 4);
+          for (int sp = 0; sp < nspin; ++sp)
+            for (int wh = w0; wh <= w1; ++wh)
+              for (int jb = 0; jb < njb; ++jb) {
+                DensItem gi;
+                gi.tile = ti;
+                gi.jb = static_cast<short>(jb);
+                gi.spin = static_cast<signed char>(sp);
+                gi.acomp = static_cast<signed char>(wh);
+                gradit.push_back(gi);
+              }
+        }
         for (int jb = 0; jb < njb; ++jb) {
           DensItem gi;
           gi.tile = ti;
@@ -535,6 +559,7 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
       b.ndens = dens.size() - b.dens_off;
       b.ng = gitems.size() - b.g_off;
       b.nvxc = vxc.size() - b.vxc_off;
+      b.ngrad = gradit.size() - b.grad_off;
       h->batches.push_back(b);
       leaf += nl;
     }
@@ -564,17 +589,20 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
     rc |= dev_upload(h, &P.shell_list, my_shell_list);
     rc |= dev_upload(h, &P.shell_col, my_shell_col);
     rc |= dev_upload(h, &P.bf_index, h->h_bf_index);
+    rc |= dev_upload(h, &P.bf_atom, bf_atom);
     rc |= dev_upload(h, &P.px, px);
     rc |= dev_upload(h, &P.py, py);
     rc |= dev_upload(h, &P.pz, pz);
     rc |= dev_upload(h, &P.pw, pw);
     const CollocItem *dc = nullptr;
-    const DensItem *dd = nullptr, *dg = nullptr;
+    const DensItem *dd = nullptr, *dg = nullptr, *dgr = nullptr;
     const VxcItem *dv = nullptr;
     rc |= dev_upload(h, &dc, colloc);
     rc |= dev_upload(h, &dd, dens);
     rc |= dev_upload(h, &dg, gitems);
     rc |= dev_upload(h, &dv, vxc);
+    rc |= dev_upload(h, &dgr, gradit);
+    h->d_gradit = const_cast<DensItem *>(dgr);
     h->d_colloc = const_cast<CollocItem *>(dc);
     h->d_dens = const_cast<DensItem *>(dd);
     h->d_g = const_cast<DensItem *>(dg);
@@ -595,6 +623,10 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
     rc |= dev_alloc(h, &h->d_Ktmp, ksz);
     rc |= dev_alloc(h, &h->d_K, ksz);
     rc |= dev_alloc(h, &h->d_scalars, 4);
+    if (want_grad) {
+      rc |= dev_alloc(h, &h->d_DT, ksz);
+      rc |= dev_alloc(h, &h->d_grad, 3 * static_cast<size_t>(std::max(h->natoms, 1)));
+    }
     if (rc) {
       occ_xc_destroy(h);
       return 1;
@@ -609,6 +641,11 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
   P.nfunc = nfunc;
   for (int f = 0; f < nfunc; ++f) P.func_ids[f] = func_ids[f];
   P.density_threshold = density_threshold;
+  P.slab_G = h->ncomp;
+  P.slab_H = h->ncomp + nspin;
+  P.slab_S = P.slab_H + 3 * nspin;
+  P.grad = h->d_grad;
+  P.grad_factor = deriv == 0 ? -4.0 : -2.0;
   P.debug = opt ? opt->reserved[0] : 0;
   for (int s = 0; s < nspin; ++s) P.Ktmp[s] = h->d_Ktmp + static_cast<size_t>(s) * nbf;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -723,6 +760,43 @@ int occ_xc_build(occ_xc_handle *h, const double *D2, double *K, double *exc, dou
   if (exc) *exc = sc[0];
   if (n_alpha) *n_alpha = sc[1];
   if (n_beta) *n_beta = sc[2];
+  return 0;
+}
+
+int occ_xc_gradient(occ_xc_handle *h, const double *D2, double *gradient) {
+  if (!h || !D2 || !gradient) return fail("occ_xc_gradient: null argument");
+  if (!h->gradient) return fail("occ_xc_gradient: handle was created without the gradient option");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  BuildParams P = h->P;
+  const size_t ksz = static_cast<size_t>(h->nspin) * h->nbf * h->nbf;
+  CUDA_TRY(cudaMemcpyAsync(h->d_D, D2, ksz * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (h->nspin == 1) {
+    launch_prepare_density(h->d_D, h->d_Dsym, h->nbf, 1, st);
+    P.Drho[0] = h->d_Dsym;
+    P.Dtau[0] = h->d_D;
+  } else {
+    for (int s = 0; s < 2; ++s) P.Drho[s] = P.Dtau[s] = h->d_D + static_cast<size_t>(s) * h->nbf;
+  }
+  for (int s = 0; s < h->nspin; ++s) {
+    launch_transpose(h->d_D + static_cast<size_t>(s) * h->nbf, h->d_DT + static_cast<size_t>(s) * h->nbf, h->nbf, P.ldD, st);
+    P.DT[s] = h->d_DT + static_cast<size_t>(s) * h->nbf;
+  }
+  CUDA_TRY(cudaMemsetAsync(h->d_grad, 0, 3 * static_cast<size_t>(h->natoms) * sizeof(double), st));
+  for (const Batch &b : h->batches) {
+    launch_collocate(P, h->d_colloc + b.colloc_off, static_cast<int>(b.ncolloc), st);
+    CUDA_TRY(cudaMemsetAsync(P.acc + static_cast<size_t>(b.tile0) * h->nspin * NACC * TILE_P, 0,
+                             static_cast<size_t>(b.ntiles) * h->nspin * NACC * TILE_P * sizeof(double), st));
+    launch_density(P, h->d_dens + b.dens_off, static_cast<int>(b.ndens), st);
+    launch_functional(P, b.leaf0, b.nleaves, st);
+    launch_gbuild(P, h->d_g + b.g_off, static_cast<int>(b.ng), st);
+    if (h->deriv >= 1) launch_collocate_h(P, h->d_colloc + b.colloc_off, static_cast<int>(b.ncolloc), st);
+    launch_grad_gemm(P, h->d_gradit + b.grad_off, static_cast<int>(b.ngrad), st);
+  }
+  CUDA_TRY(cudaMemcpyAsync(gradient, h->d_grad, 3 * static_cast<size_t>(h->natoms) * sizeof(double),
+                           cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 

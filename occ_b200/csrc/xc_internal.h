@@ -90,6 +90,14 @@ struct BuildParams {
   int nfunc;
   int func_ids[MAX_FUNC];
   double density_threshold;
+  // ---- XC nuclear gradient (handles created with the gradient option) ----
+  const int *bf_atom;    // CSR per leaf: local column -> atom
+  const double *DT[2];   // D_s^T, so that (A . D_s^T) gathers contiguously like the density contraction
+  double *grad;          // [3 * natoms] accumulation target
+  int slab_G;            // first G slab (= ncomp), then nspin slabs
+  int slab_H;            // first H slab: H[s][d] at slab_H + 3 s + d      (GGA / meta-GGA)
+  int slab_S;            // first S slab: S[s][de] at slab_S + 6 s + de    (meta-GGA), de in xx,xy,xz,yy,yz,zz order
+  double grad_factor;    // -2, or -4 for LDA (dft_gradient_kernels.cpp:27-45 carries no 1/2 on vrho)
   int debug; // developer switches for timing experiments (options.reserved[0]): 1 = no Vxc scatter, 2 = no density epilogue
 };
 
@@ -104,6 +112,10 @@ void launch_collocate(const BuildParams &P, const CollocItem *items, int nitems,
 void launch_density(const BuildParams &P, const DensItem *items, int nitems, void *stream);
 void launch_functional(const BuildParams &P, int leaf0, int nleaves, void *stream);
 void launch_vxc(const BuildParams &P, const VxcItem *items, int nitems, void *stream);
+void launch_gbuild(const BuildParams &P, const DensItem *items, int nitems, void *stream);
+void launch_collocate_h(const BuildParams &P, const CollocItem *items, int nitems, void *stream);
+void launch_grad_gemm(const BuildParams &P, const DensItem *items, int nitems, void *stream);
+void launch_transpose(const double *D, double *DT, int nbf, int ld, void *stream);
 void launch_prepare_density(const double *D2, double *Dsym, int nbf, int nspin, void *stream);
 void launch_finalize(const BuildParams &P, int nleaves, double *K, double *scalars, void *stream);
 void upload_c2s_table(const C2STable &t);

@@ -72,7 +72,7 @@ class DFT:
     def __init__(self, method: str, basis: AOBasis, grid: GridHierarchy, spinorbital_kind: str = RESTRICTED,
                  device: int = -1, rank: int = 0, world_size: int = 1, batch_bytes: int = 0,
                  density_threshold: float = 1e-10, xc_screening_threshold: float = 1e-10, shell_extents=None,
-                 debug: int = 0, lanes: int = 1):
+                 debug: int = 0, lanes: int = 1, gradient: bool = False):
         self.basis = basis
         self.method = method
         self.func_ids = np.array(get_dft_method(method), dtype=np.int32)
@@ -86,6 +86,7 @@ class DFT:
         opt = OptionsT(device, rank, world_size, batch_bytes)
         opt.reserved[0] = debug
         opt.reserved[1] = lanes
+        opt.reserved[2] = int(gradient)
         self._h = C.c_void_p()
         check(lib().occ_xc_create(self._basis_arrays.ref, C.c_size_t(len(w)), ptr(pts), ptr(w), C.c_size_t(len(leaves)),
                                   ptr(leaves), ptr(ext) if ext is not None else None, C.c_int(len(self.func_ids)),
@@ -142,6 +143,20 @@ class DFT:
         """occ_xc_build_device: everything resident in HBM, asynchronous on `stream` (a cudaStream_t value)."""
         check(lib().occ_xc_build_device(self._h, C.c_void_p(d2_dev_ptr), C.c_void_p(k_dev_ptr),
                                         C.c_void_p(scalars_dev_ptr), C.c_void_p(stream)))
+
+    def compute_xc_gradient(self, D: np.ndarray) -> np.ndarray:
+        """DFT::compute_xc_gradient(mo) without the VV10 term (src/dft/dft_gradients.cpp:68-109); D = mo.D.
+        Returns (natoms, 3) — the bytes of the reference's 3 x natoms column-major Mat3N."""
+        return self.gradient(np.asfortranarray(2.0 * np.asarray(D, dtype=np.float64)))
+
+    def gradient(self, D2: np.ndarray) -> np.ndarray:
+        n = self.nspin * self.nbf
+        D2 = np.asfortranarray(D2, dtype=np.float64)
+        if D2.shape != (n, self.nbf):
+            raise RuntimeError(f"density matrix has shape {D2.shape}, expected {(n, self.nbf)}")
+        g = np.zeros((len(self.basis.atomic_numbers), 3))
+        check(lib().occ_xc_gradient(self._h, ptr(D2), ptr(g)))
+        return g
 
     def set_profiling(self, on: bool):
         check(lib().occ_xc_set_profiling(self._h, C.c_int(int(on))))

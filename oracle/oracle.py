@@ -232,6 +232,55 @@ def xc_build(basis: Basis, spts, sw, leaves, func_names, nspin, D2, density_thre
     return {"K": K, "exc": exc.value, "n_alpha": na.value, "n_beta": nb.value, "stats": stats}
 
 
+def collocate_shell_deriv2(l, pure, pts, coefs, exps, center):
+    """value, x, y, z, xx, xy, xz, yy, yz, zz of one shell: array (10, nout, npts), no common_fac"""
+    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+    n = pts.shape[0]
+    nout = lib().orc_nbf_shell(C.c_int(l), C.c_int(pure))
+    out = np.zeros((10, nout, n))
+    coefs = np.ascontiguousarray(coefs, dtype=np.float64)
+    exps = np.ascontiguousarray(exps, dtype=np.float64)
+    center = np.ascontiguousarray(center, dtype=np.float64)
+    lib().orc_collocate_shell_deriv2(C.c_int(l), C.c_int(pure), C.c_size_t(n), _p(pts), C.c_int(len(exps)), _p(coefs),
+                                     _p(exps), _p(center), _p(out))
+    return out
+
+
+def xc_gradient(basis: Basis, spts, sw, leaves, func_names, nspin, D2, natoms, density_threshold=1e-10,
+                screening_threshold=1e-10, nthreads=None):
+    """compute_xc_gradient_impl restatement: returns (natoms, 3)"""
+    ids = np.array([FUNC_IDS[f] for f in func_names], dtype=np.int32)
+    deriv = method_deriv(func_names)
+    D2 = np.asfortranarray(D2, dtype=np.float64)
+    spts = np.ascontiguousarray(spts, dtype=np.float64)
+    sw = np.ascontiguousarray(sw, dtype=np.float64)
+    leaves = np.ascontiguousarray(leaves)
+    grad = np.zeros((natoms, 3))
+    rc = lib().orc_xc_gradient(basis.ref, C.c_size_t(len(sw)), _p(spts), _p(sw), C.c_size_t(len(leaves)), _p(leaves),
+                               C.c_int(len(ids)), _p(ids), C.c_int(nspin), C.c_int(deriv), C.c_double(density_threshold),
+                               C.c_double(screening_threshold), _p(D2), C.c_int(natoms), _p(grad),
+                               C.c_int(nthreads or os.cpu_count() or 1))
+    if rc:
+        raise RuntimeError("orc_xc_gradient failed")
+    return grad
+
+
+def ref_collocate_shell_deriv2(l, pure, pts, coefs, exps, center):
+    """gg_collocation_deriv2 from the compiled reference gau2grid: (10, nout, npts)"""
+    R = ref_lib()
+    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+    n = pts.shape[0]
+    nout = (2 * l + 1) if pure else (l + 1) * (l + 2) // 2
+    order = 300 if pure else 400
+    out = np.zeros((10, nout, n))
+    coefs = np.ascontiguousarray(coefs, dtype=np.float64)
+    exps = np.ascontiguousarray(exps, dtype=np.float64)
+    center = np.ascontiguousarray(center, dtype=np.float64)
+    R.gg_collocation_deriv2(C.c_int(l), C.c_ulong(n), _p(pts), C.c_ulong(3), C.c_int(len(exps)), _p(coefs), _p(exps),
+                            _p(center), C.c_int(order), *[_p(out[k]) for k in range(10)])
+    return out
+
+
 # ---- the real reference (gau2grid) for cross-checks ----
 _ref = None
 

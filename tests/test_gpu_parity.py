@@ -258,3 +258,29 @@ def test_size_independent_properties_at_full_size():
     assert abs(du.total_density[0] + du.total_density[1] - nr) < 1e-9
     assert np.abs(Kr - Kr.T).max() == 0.0
     du.close()
+
+
+@pytest.mark.parametrize("mol,bas,method,nspin,stride", [
+    ("h2o_32", "def2-svp", "b3lyp", 2, 12),          # BASELINE configs[2]
+    ("valinomycin", "def2-tzvp", "b3lyp", 1, 40),    # configs[3] (includes leaves that keep all 3348 functions)
+    ("taxol", "def2-tzvp", "r2scan", 1, 60),         # configs[4]
+])
+def test_baseline_configs_at_full_size_on_a_leaf_sample(oracle, mol, bas, method, nspin, stride):
+    """Full-size molecules, grids and density matrices; the oracle (seconds per 100 leaves on a CPU) checks every
+    stride-th Morton leaf, the CUDA build is run on exactly the same leaf subset."""
+    Z, pos = molecules.MOLECULES[mol]()
+    b = aobasis.AOBasis.load(Z, pos, bas)
+    h = grid.MolecularGrid(b).hierarchy()
+    sample = np.concatenate([h.leaves[::stride], h.leaves[-1:]])     # keep the ragged last leaf
+    D2 = molecules.synthetic_density(b, nspin)
+    d = dft.DFT(method, b, dft.GridHierarchy(h.sorted_points, h.sorted_weights, sample),
+                dft.UNRESTRICTED if nspin == 2 else dft.RESTRICTED)
+    K = d.build(D2)
+    ref = oracle.xc_build(oracle.Basis(b.as_arrays()), h.sorted_points, h.sorted_weights, sample, _names(method, oracle),
+                          nspin, D2)
+    assert d.info()["sum_n_nb2"] == ref["stats"]["sum_n_nb2"]
+    assert d.info()["nb_max"] == ref["stats"]["nb_max"]
+    assert np.abs(K - ref["K"]).max() < TOL_VXC
+    assert abs(d.exchange_correlation_energy() - ref["exc"]) < TOL_EXC
+    assert abs(d.total_density[0] - ref["n_alpha"]) < 1e-8
+    d.close()
