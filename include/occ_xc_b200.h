@@ -58,7 +58,15 @@ enum {
   OCC_XC_GGA_C_LYP = 131,
   OCC_XC_HYB_GGA_XC_B3LYP = 402,
   OCC_XC_MGGA_X_R2SCAN = 497,
-  OCC_XC_MGGA_C_R2SCAN = 498
+  OCC_XC_MGGA_C_R2SCAN = 498,
+  OCC_XC_LDA_C_PW = 12,
+  OCC_XC_LDA_C_PW_MOD = 13,
+  OCC_XC_MGGA_X_TPSS = 202,
+  OCC_XC_MGGA_C_TPSS = 231,
+  OCC_XC_HYB_GGA_XC_PBEH = 406,
+  OCC_XC_HYB_GGA_XC_BHANDH = 435,
+  OCC_XC_HYB_GGA_XC_BHANDHLYP = 436,
+  OCC_XC_HYB_GGA_XC_B3LYP5 = 475
 };
 
 typedef struct {

@@ -3,7 +3,9 @@
 // reference makes per grid block (src/dft/functional.cpp:18-65: xc_lda_exc_vxc / xc_gga_exc_vxc /
 // xc_mgga_exc_vxc) for the functional ids reachable from src/dft/dft_method.cpp:14-37:
 //   lda_x(1) lda_c_vwn(7) lda_c_vwn_rpa(8) lda_c_vwn_3(30) gga_x_pbe(101) gga_x_b88(106) gga_c_pbe(130)
-//   gga_c_lyp(131) hyb_gga_xc_b3lyp(402) mgga_x_r2scan(497) mgga_c_r2scan(498)
+//   gga_c_lyp(131) hyb_gga_xc_b3lyp(402) mgga_x_r2scan(497) mgga_c_r2scan(498) mgga_x_tpss(202) mgga_c_tpss(231)
+//   hyb_gga_xc_b3lyp5(475) hyb_gga_xc_pbeh(406) hyb_gga_xc_bhandh(435) hyb_gga_xc_bhandhlyp(436) lda_c_pw(12)
+//   lda_c_pw_mod(13)
 // libxc conventions: exc = energy per particle; vrho = d(rho*exc)/d rho_s; vsigma = d(rho*exc)/d sigma with
 // sigma = grad rho . grad rho (polarized order aa, ab, bb); vtau = d(rho*exc)/d tau_s, tau = 1/2 sum |grad psi|^2.
 // Each functional is a single energy density in (rho_a, rho_b, sigma_aa, sigma_ab, sigma_bb, tau_a, tau_b);
@@ -16,14 +18,27 @@ namespace xcb {
 enum : int {
   ID_LDA_X = 1, ID_LDA_C_VWN = 7, ID_LDA_C_VWN_RPA = 8, ID_LDA_C_VWN_3 = 30, ID_GGA_X_PBE = 101,
   ID_GGA_X_B88 = 106, ID_GGA_C_PBE = 130, ID_GGA_C_LYP = 131, ID_HYB_GGA_XC_B3LYP = 402,
-  ID_MGGA_X_R2SCAN = 497, ID_MGGA_C_R2SCAN = 498
+  ID_MGGA_X_R2SCAN = 497, ID_MGGA_C_R2SCAN = 498, ID_LDA_C_PW = 12, ID_LDA_C_PW_MOD = 13, ID_MGGA_X_TPSS = 202,
+  ID_MGGA_C_TPSS = 231, ID_HYB_GGA_XC_PBEH = 406, ID_HYB_GGA_XC_BHANDH = 435, ID_HYB_GGA_XC_BHANDHLYP = 436,
+  ID_HYB_GGA_XC_B3LYP5 = 475
 };
+
+XC_HD double xc_exx_of(int id) { // xc_hyb_exx_coef (include/occ/dft/functional.h:557-579)
+  switch (id) {
+  case ID_HYB_GGA_XC_B3LYP: case ID_HYB_GGA_XC_B3LYP5: return 0.20;
+  case ID_HYB_GGA_XC_PBEH: return 0.25;
+  case ID_HYB_GGA_XC_BHANDH: case ID_HYB_GGA_XC_BHANDHLYP: return 0.50;
+  default: return 0.0;
+  }
+}
 
 XC_HD int xc_family_of(int id) {
   switch (id) {
-  case ID_LDA_X: case ID_LDA_C_VWN: case ID_LDA_C_VWN_RPA: case ID_LDA_C_VWN_3: return 0;
-  case ID_GGA_X_PBE: case ID_GGA_X_B88: case ID_GGA_C_PBE: case ID_GGA_C_LYP: case ID_HYB_GGA_XC_B3LYP: return 1;
-  case ID_MGGA_X_R2SCAN: case ID_MGGA_C_R2SCAN: return 2;
+  case ID_LDA_X: case ID_LDA_C_VWN: case ID_LDA_C_VWN_RPA: case ID_LDA_C_VWN_3: case ID_LDA_C_PW:
+  case ID_LDA_C_PW_MOD: return 0;
+  case ID_GGA_X_PBE: case ID_GGA_X_B88: case ID_GGA_C_PBE: case ID_GGA_C_LYP: case ID_HYB_GGA_XC_B3LYP:
+  case ID_HYB_GGA_XC_B3LYP5: case ID_HYB_GGA_XC_PBEH: case ID_HYB_GGA_XC_BHANDH: case ID_HYB_GGA_XC_BHANDHLYP: return 1;
+  case ID_MGGA_X_R2SCAN: case ID_MGGA_C_R2SCAN: case ID_MGGA_X_TPSS: case ID_MGGA_C_TPSS: return 2;
   default: return -1;
   }
 }
@@ -252,8 +267,7 @@ template <class T> XC_HD T r2scan_x_total(const T &n, const T &sigma_in, const T
   const double k0 = 0.174, k1 = 0.065, mu = 10.0 / 81.0, a1 = 4.9479;
   const double C2 = -0.9353000875519996 * k0; // sum_i i c_xi times k0
   const double Ceta = 20.0 / 27.0 + XC_R2_ETA * 5.0 / 3.0;
-  T sigma = sigma_in;
-  if (val(sigma) > 8.0 * val(n) * val(tau)) sigma = 8.0 * n * tau; // Fermi-hole-curvature bound
+  const T &sigma = sigma_in; // sigma <= 8 n tau already holds (input-stage bound in xc_eval_*)
   const T p = red_grad2(n, sigma);
   const T tauW = sigma / (8.0 * n);
   const T n2 = n * n;
@@ -275,9 +289,8 @@ template <class T> XC_HD T e_r2scan_c(const XV<T> &v) {
   const double dfc2 = -0.7114023342889984; // sum_i i c_ci
   T rho, rs, z;
   rs_zeta(v, rho, rs, z);
-  T stot = v.saa + 2.0 * v.sab + v.sbb;
+  const T stot = v.saa + 2.0 * v.sab + v.sbb;
   const T tau = v.ta + v.tb;
-  if (val(stot) > 8.0 * val(rho) * val(tau)) stot = 8.0 * rho * tau;
   const T p = red_grad2(rho, stot);
   const T zp = 1.0 + z, zm = 1.0 - z;
   const T ds = 0.5 * (zp * cbrt(zp * zp) + zm * cbrt(zm * zm));
@@ -324,6 +337,84 @@ template <class T> XC_HD T e_r2scan_c(const XV<T> &v) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Perdew-Wang 1992 with the constants as printed in 1992 (libxc lda_c_pw); eps_pw above is lda_c_pw_mod
+template <class T> XC_HD T e_pw92(const XV<T> &v, bool mod) {
+  T rho, rs, z;
+  rs_zeta(v, rho, rs, z);
+  if (mod) return rho * eps_pw(rs, z);
+  const T srs = sqrt(rs);
+  const PwP p0 = {0.031091, 0.21370, 7.5957, 3.5876, 1.6382, 0.49294};
+  const PwP p1 = {0.015545, 0.20548, 14.1189, 6.1977, 3.3662, 0.62517};
+  const PwP p2 = {0.016887, 0.11125, 10.357, 3.6231, 0.88026, 0.49671};
+  const T e0 = pw_g(p0, rs, srs), e1 = pw_g(p1, rs, srs), mac = pw_g(p2, rs, srs);
+  const T fz = f_zeta(z);
+  const T z2 = z * z;
+  const T z4 = z2 * z2;
+  return rho * (e0 - mac * fz * (1.0 - z4) / 1.709921 + (e1 - e0) * fz * z4);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TPSS (Tao, Perdew, Staroverov, Scuseria 2003); known answers: tests/dft_tests.cpp:138-191 of the reference
+template <class T> XC_HD T tpss_x_total(const T &n, const T &sigma, const T &tau) {
+  const double kappa = 0.804, b = 0.40, c = 1.59096, e = 1.537, mu = 0.21951;
+  const double sqe = 1.2397580409095959; // sqrt(e)
+  const double m = 10.0 / 81.0;
+  const T p = red_grad2(n, sigma);
+  const T tauW = sigma / (8.0 * n);
+  const T z = tauW / tau;
+  const T n2 = n * n;
+  const T alpha = (tau - tauW) / (XC_CF * (n * cbrt(n2)));
+  const T am1 = alpha - 1.0;
+  const T qb = 0.45 * am1 / sqrt(1.0 + b * alpha * am1) + (2.0 / 3.0) * p;
+  const T z2 = z * z, p2 = p * p;
+  const T opz2 = 1.0 + z2;
+  const T num = (m + c * z2 / (opz2 * opz2)) * p + (146.0 / 2025.0) * (qb * qb) -
+                (73.0 / 405.0) * qb * sqrt(0.18 * z2 + 0.5 * p2) + (m * m / kappa) * p2 + (2.0 * sqe * m * 0.36) * z2 +
+                (e * mu) * (p * p2);
+  const T den = 1.0 + sqe * p;
+  const T x = num / (den * den);
+  return ex_unif(n) * (1.0 + kappa - kappa / (1.0 + x / kappa));
+}
+template <class T> XC_HD T e_tpss_x(const XV<T> &v) {
+  return 0.5 * (tpss_x_total(2.0 * v.ra, 4.0 * v.saa, 2.0 * v.ta) + tpss_x_total(2.0 * v.rb, 4.0 * v.sbb, 2.0 * v.tb));
+}
+template <class T> XC_HD T pbe_c_eps_one_spin(const T &n, const T &sigma) { // eps_c^PBE(n, 0, grad n, 0): zeta = 1
+  const double beta = 0.06672455060314922;
+  const double phi2 = 0.3968502629920499, phi3 = 0.25; // phi(1) = 2^(-1/3)
+  const T rs = cbrt(XC_RS_C / n);
+  const T ec = pw_g(pw_set(1), rs, sqrt(rs));
+  const T kF = cbrt(XC_3PI2 * n);
+  const T t2 = sigma * XC_PI / (16.0 * phi2 * kF * (n * n));
+  const T A = (beta / XC_GAMMA) / expm1(-ec / (XC_GAMMA * phi3));
+  const T At2 = A * t2;
+  return ec + XC_GAMMA * phi3 * log(1.0 + (beta / XC_GAMMA) * t2 * (1.0 + At2) / (1.0 + At2 + At2 * At2));
+}
+template <class T> XC_HD T e_tpss_c(const XV<T> &v) {
+  const T rho = v.ra + v.rb;
+  const T zeta = (v.ra - v.rb) / rho;
+  const T stot = v.saa + 2.0 * v.sab + v.sbb;
+  const T z = stot / (8.0 * rho * (v.ta + v.tb));
+  const T zt2 = zeta * zeta;
+  const T zt4 = zt2 * zt2;
+  const T C0 = 0.53 + 0.87 * zt2 + 0.50 * zt4 + 2.26 * (zt2 * zt4);
+  const T rho2 = rho * rho;
+  // xi^2 = |grad zeta|^2 / (4 (3 pi^2 n)^(2/3)), |grad zeta|^2 = 4 |nb grad na - na grad nb|^2 / n^4
+  const T kF = cbrt(XC_3PI2 * rho);
+  const T xi2 = (v.rb * v.rb * v.saa - 2.0 * (v.ra * v.rb) * v.sab + v.ra * v.ra * v.sbb) / (rho2 * rho2 * (kF * kF));
+  const T zp = 1.0 + zeta, zm = 1.0 - zeta;
+  const T w = 1.0 + 0.5 * xi2 * (1.0 / (zp * cbrt(zp)) + 1.0 / (zm * cbrt(zm)));
+  const T w2 = w * w;
+  const T C = C0 / (w2 * w2);
+  const T e_pbe = e_pbe_c(v) / rho;
+  T ea = pbe_c_eps_one_spin(v.ra, v.saa), eb = pbe_c_eps_one_spin(v.rb, v.sbb);
+  if (val(ea) < val(e_pbe)) ea = e_pbe;
+  if (val(eb) < val(e_pbe)) eb = e_pbe;
+  const T z2 = z * z;
+  const T pkzb = e_pbe * (1.0 + C * z2) - (1.0 + C) * z2 * ((v.ra * ea + v.rb * eb) / rho);
+  return rho * pkzb * (1.0 + 2.8 * pkzb * (z2 * z));
+}
+
+// ---------------------------------------------------------------------------------------------
 template <class T> XC_HD T e_b3lyp(const XV<T> &v) { // libxc hyb_gga_xc_b3lyp: a0 = 0.20, ax = 0.72, ac = 0.81
   return 0.08 * e_lda_x(v) + 0.72 * e_b88(v) + 0.19 * e_vwn<1>(v) + 0.81 * e_lyp(v);
 }
@@ -341,6 +432,14 @@ template <class T> XC_HD T xc_energy_density(int id, const XV<T> &v) {
   case ID_HYB_GGA_XC_B3LYP: return e_b3lyp(v);
   case ID_MGGA_X_R2SCAN: return e_r2scan_x(v);
   case ID_MGGA_C_R2SCAN: return e_r2scan_c(v);
+  case ID_MGGA_X_TPSS: return e_tpss_x(v);
+  case ID_MGGA_C_TPSS: return e_tpss_c(v);
+  case ID_LDA_C_PW: return e_pw92(v, false);
+  case ID_LDA_C_PW_MOD: return e_pw92(v, true);
+  case ID_HYB_GGA_XC_B3LYP5: return 0.08 * e_lda_x(v) + 0.72 * e_b88(v) + 0.19 * e_vwn<0>(v) + 0.81 * e_lyp(v);
+  case ID_HYB_GGA_XC_PBEH: return 0.75 * e_pbe_x(v) + e_pbe_c(v);
+  case ID_HYB_GGA_XC_BHANDH: return 0.5 * e_lda_x(v) + e_lyp(v);
+  case ID_HYB_GGA_XC_BHANDHLYP: return 0.5 * e_b88(v) + e_lyp(v);
   default: return T(0.0);
   }
 }
@@ -370,8 +469,18 @@ template <int FAM> XC_HD void xc_eval_unpolarized(int nfunc, const int *ids, dou
   v.sbb = v.saa;
   v.ta = 0.5 * Tt;
   v.tb = v.ta;
+  // meta-GGA components see sigma bounded by 8 rho tau (libxc XC_FLAGS_ENFORCE_FHC): the bound changes the input
+  // VALUE only, the potentials remain the plain partials there (pinned by tests/dft_tests.cpp:138-191, z = 1 + 1 ulp)
+  XV<D> vm = v;
+  if (FAM >= 2) {
+    D Sm = S;
+    Sm.v = fmin(S.v, 8.0 * rho * Tt.v);
+    vm.saa = 0.25 * Sm;
+    vm.sab = vm.saa;
+    vm.sbb = vm.saa;
+  }
   for (int f = 0; f < nfunc; ++f) {
-    const D F = xc_energy_density(ids[f], v);
+    const D F = xc_energy_density(ids[f], (FAM >= 2 && xc_family_of(ids[f]) == 2) ? vm : v);
     o.exc += F.v / rho;
     o.vrho[0] += F.d[0];
     if (FAM >= 1) o.vsigma[0] += F.d[FAM >= 1 ? 1 : 0];
@@ -409,8 +518,15 @@ template <int FAM> XC_HD void xc_eval_polarized(int nfunc, const int *ids, doubl
     v.ta = D(XC_TAU_FLOOR);
     v.tb = D(XC_TAU_FLOOR);
   }
+  XV<D> vm = v;
+  if (FAM >= 2) { // per-spin-channel Fermi-hole-curvature bound, value only (see xc_eval_unpolarized)
+    vm.saa.v = fmin(v.saa.v, 8.0 * ra * v.ta.v);
+    vm.sbb.v = fmin(v.sbb.v, 8.0 * rb * v.tb.v);
+    const double lim2 = 0.5 * (vm.saa.v + vm.sbb.v);
+    vm.sab.v = fmin(fmax(v.sab.v, -lim2), lim2);
+  }
   for (int f = 0; f < nfunc; ++f) {
-    const D F = xc_energy_density(ids[f], v);
+    const D F = xc_energy_density(ids[f], (FAM >= 2 && xc_family_of(ids[f]) == 2) ? vm : v);
     o.exc += F.v / (ra + rb);
     o.vrho[0] += F.d[0];
     o.vrho[1] += F.d[1];

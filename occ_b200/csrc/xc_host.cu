@@ -236,7 +236,7 @@ extern "C" {
 const char *occ_xc_last_error(void) { return g_last_error.c_str(); }
 int occ_xc_abi_version(void) { return OCC_XC_B200_ABI_VERSION; }
 int occ_xc_family(int id) { return xc_family_of(id); }
-double occ_xc_exact_exchange(int id) { return id == ID_HYB_GGA_XC_B3LYP ? 0.20 : 0.0; }
+double occ_xc_exact_exchange(int id) { return xc_exx_of(id); }
 
 int occ_xc_decay_cutoff(const occ_xc_basis_t *basis, double threshold, double *extents) {
   if (!basis || !extents) return fail("occ_xc_decay_cutoff: null argument");

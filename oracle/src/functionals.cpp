@@ -222,9 +222,7 @@ template <class T> T r2scan_x_n(const T &n, const T &sigma_in, const T &tau) {
   for (int i = 1; i < 8; ++i) sum_icx += i * r2_cx[i];
   const double C2 = sum_icx * k0; // = -sum i c_xi (1 - h0x) = -0.162742
   const double Ceta = 20.0 / 27.0 + r2_eta * 5.0 / 3.0;
-  // Fermi-hole-curvature bound sigma <= 8 n tau (libxc XC_FLAGS_ENFORCE_FHC)
-  T sigma = sigma_in;
-  if (value(sigma) > 8.0 * value(n) * value(tau)) sigma = 8.0 * n * tau;
+  const T &sigma = sigma_in; // already bounded by 8 n tau at the input stage (xc_eval_add)
   const T p = s2_of(n, sigma);
   const T tauW = sigma / (8.0 * n);
   const T tauU = 0.3 * std::pow(3.0 * kPi * kPi, 2.0 / 3.0) * n * cbrt(sq(n));
@@ -248,9 +246,8 @@ template <class T> T F_r2scan_c(const Vars<T> &v) {
   for (int i = 1; i < 8; ++i) dfc2 += i * r2_cc[i];
   T rho, rs, z;
   rs_zeta(v, rho, rs, z);
-  T stot = v.saa + 2.0 * v.sab + v.sbb;
+  const T stot = v.saa + 2.0 * v.sab + v.sbb;
   const T tau = v.ta + v.tb;
-  if (value(stot) > 8.0 * value(rho) * value(tau)) stot = 8.0 * rho * tau;
   const T p = s2_of(rho, stot);
   const T zp = 1.0 + z, zm = 1.0 - z;
   const T ds = 0.5 * (zp * cbrt(sq(zp)) + zm * cbrt(sq(zm)));   // ((1+z)^(5/3) + (1-z)^(5/3))/2
@@ -296,12 +293,102 @@ template <class T> T F_r2scan_c(const Vars<T> &v) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Perdew-Wang 1992 LSDA correlation as libxc's lda_c_pw (original 1992 constants) / lda_c_pw_mod
+const PwSet pw_orig[3] = {{0.031091, 0.21370, 7.5957, 3.5876, 1.6382, 0.49294},
+                          {0.015545, 0.20548, 14.1189, 6.1977, 3.3662, 0.62517},
+                          {0.016887, 0.11125, 10.357, 3.6231, 0.88026, 0.49671}};
+template <class T, int MOD> T F_pw(const Vars<T> &v) {
+  T rho, rs, z;
+  rs_zeta(v, rho, rs, z);
+  if (MOD) return rho * eps_pw(rs, z);
+  const T e0 = pw_G(pw_orig[0], rs), e1 = pw_G(pw_orig[1], rs), mac = pw_G(pw_orig[2], rs);
+  const T fz = f_zeta(z), z4 = sq(sq(z));
+  return rho * (e0 - mac * fz * (1.0 - z4) / 1.709921 + (e1 - e0) * fz * z4);
+}
+
+// ------------------------------------------------------------------------------------------------
+// TPSS: Tao, Perdew, Staroverov, Scuseria, Phys. Rev. Lett. 91, 146401 (2003).
+// Pinned by the reference's own known-answer test (tests/dft_tests.cpp:138-191: eps of x and c, and
+// vrho / vsigma / vtau of c at four points, 1e-6).
+template <class T> T tpss_x_n(const T &n, const T &sigma_in, const T &tau) {
+  const double kappa = 0.804, b = 0.40, c = 1.59096, e = 1.537, mu = 0.21951;
+  const double se = std::sqrt(e);
+  const T &sigma = sigma_in; // z = tau_W / tau <= 1 through the input-stage bound sigma <= 8 n tau
+  const T p = s2_of(n, sigma);
+  const T z = sigma / (8.0 * n * tau);
+  const T tauU = 0.3 * std::pow(3.0 * kPi * kPi, 2.0 / 3.0) * n * cbrt(sq(n));
+  const T alpha = (tau - sigma / (8.0 * n)) / tauU;
+  const T qb = 0.45 * (alpha - 1.0) / sqrt(1.0 + b * alpha * (alpha - 1.0)) + (2.0 / 3.0) * p;
+  const T z2 = sq(z);
+  const T num = (10.0 / 81.0 + c * z2 / sq(1.0 + z2)) * p + (146.0 / 2025.0) * sq(qb) -
+                (73.0 / 405.0) * qb * sqrt(0.5 * sq(0.6 * z) + 0.5 * sq(p)) + sq(10.0 / 81.0) / kappa * sq(p) +
+                2.0 * se * (10.0 / 81.0) * sq(0.6 * z) + e * mu * p * sq(p);
+  const T x = num / sq(1.0 + se * p);
+  return ex_unif(n) * (1.0 + kappa - kappa / (1.0 + x / kappa));
+}
+template <class T> T F_tpss_x(const Vars<T> &v) {
+  return 0.5 * (tpss_x_n(2.0 * v.ra, 4.0 * v.saa, 2.0 * v.ta) + tpss_x_n(2.0 * v.rb, 4.0 * v.sbb, 2.0 * v.tb));
+}
+// PBE correlation energy per particle of a fully spin-polarised density n with gradient square sigma
+template <class T> T pbe_c_eps_ferro(const T &n, const T &sigma) {
+  const double beta = 0.06672455060314922, gamma = (1.0 - std::log(2.0)) / (kPi * kPi);
+  const double phi = 0.5 * std::cbrt(4.0), phi3 = phi * phi * phi; // phi(zeta = 1) = 2^(-1/3)
+  const T rs = cbrt(3.0 / (4.0 * kPi * n));
+  const T ec = pw_G(pw_mod[1], rs);
+  const T kF = cbrt(3.0 * kPi * kPi * n);
+  const T t2 = sigma * kPi / (16.0 * phi * phi * kF * sq(n));
+  const T A = (beta / gamma) / expm1(-ec / (gamma * phi3));
+  const T At2 = A * t2;
+  return ec + gamma * phi3 * log(1.0 + (beta / gamma) * t2 * (1.0 + At2) / (1.0 + At2 + sq(At2)));
+}
+template <class T> T F_tpss_c(const Vars<T> &v) {
+  const double d = 2.8;
+  const T rho = v.ra + v.rb;
+  const T zeta = (v.ra - v.rb) / rho;
+  const T stot = v.saa + 2.0 * v.sab + v.sbb;
+  const T tau = v.ta + v.tb;
+  const T z = stot / (8.0 * rho * tau);
+  // C(zeta, xi): xi = |grad zeta| / (2 (3 pi^2 n)^(1/3)), |grad zeta|^2 = 4 (nb^2 saa - 2 na nb sab + na^2 sbb) / n^4
+  const T zeta2 = sq(zeta);
+  const T C0 = 0.53 + 0.87 * zeta2 + 0.50 * sq(zeta2) + 2.26 * zeta2 * sq(zeta2);
+  const T gz2 = 4.0 * (sq(v.rb) * v.saa - 2.0 * v.ra * v.rb * v.sab + sq(v.ra) * v.sbb) / sq(sq(rho));
+  const T xi2 = gz2 / (4.0 * cbrt(sq(3.0 * kPi * kPi * rho)));
+  const T zp = 1.0 + zeta, zm = 1.0 - zeta;
+  const T inv43 = 0.5 * (1.0 / (zp * cbrt(zp)) + 1.0 / (zm * cbrt(zm)));
+  const T C = C0 / sq(sq(1.0 + xi2 * inv43));
+  const T e_pbe = F_pbe_c(v) / rho;
+  T ea = pbe_c_eps_ferro(v.ra, v.saa), eb = pbe_c_eps_ferro(v.rb, v.sbb);
+  if (value(ea) < value(e_pbe)) ea = e_pbe; // eps~_sigma = max(eps_PBE(n_sigma, 0), eps_PBE(na, nb))
+  if (value(eb) < value(e_pbe)) eb = e_pbe;
+  const T z2 = sq(z);
+  const T pkzb = e_pbe * (1.0 + C * z2) - (1.0 + C) * z2 * (v.ra * ea + v.rb * eb) / rho;
+  return rho * pkzb * (1.0 + d * pkzb * z2 * z);
+}
+
+// ------------------------------------------------------------------------------------------------
 template <class T> T F_b3lyp(const Vars<T> &v) { // libxc hyb_gga_xc_b3lyp: a0 = 0.20, ax = 0.72, ac = 0.81
   return 0.08 * F_lda_x(v) + 0.72 * F_b88(v) + 0.19 * F_vwn<T, 1>(v) + 0.81 * F_lyp(v);
 }
 
+// libxc hyb_gga_xc_b3lyp5 (VWN5 in place of VWN-RPA), hyb_gga_xc_pbeh (PBE0: 0.75 PBE-x + PBE-c, exx 0.25),
+// hyb_gga_xc_bhandh (0.5 LDA-x + LYP, exx 0.5), hyb_gga_xc_bhandhlyp (0.5 B88 + LYP, exx 0.5)
+template <class T> T F_b3lyp5(const Vars<T> &v) {
+  return 0.08 * F_lda_x(v) + 0.72 * F_b88(v) + 0.19 * F_vwn<T, 0>(v) + 0.81 * F_lyp(v);
+}
+template <class T> T F_pbeh(const Vars<T> &v) { return 0.75 * F_pbe_x(v) + F_pbe_c(v); }
+template <class T> T F_bhandh(const Vars<T> &v) { return 0.5 * F_lda_x(v) + F_lyp(v); }
+template <class T> T F_bhandhlyp(const Vars<T> &v) { return 0.5 * F_b88(v) + F_lyp(v); }
+
 template <class T> bool F_dispatch(int id, const Vars<T> &v, T &out) {
   switch (id) {
+  case ORC_LDA_C_PW: out = F_pw<T, 0>(v); return true;
+  case ORC_LDA_C_PW_MOD: out = F_pw<T, 1>(v); return true;
+  case ORC_MGGA_X_TPSS: out = F_tpss_x(v); return true;
+  case ORC_MGGA_C_TPSS: out = F_tpss_c(v); return true;
+  case ORC_HYB_GGA_XC_B3LYP5: out = F_b3lyp5(v); return true;
+  case ORC_HYB_GGA_XC_PBEH: out = F_pbeh(v); return true;
+  case ORC_HYB_GGA_XC_BHANDH: out = F_bhandh(v); return true;
+  case ORC_HYB_GGA_XC_BHANDHLYP: out = F_bhandhlyp(v); return true;
   case ORC_LDA_X: out = F_lda_x(v); return true;
   case ORC_LDA_C_VWN: out = F_vwn<T, 0>(v); return true;
   case ORC_LDA_C_VWN_RPA: out = F_vwn<T, 1>(v); return true;
@@ -329,8 +416,14 @@ int xc_eval_add(int id, int polarized, size_t n, const double *rho, const double
       if (!(r > kDensThreshold)) continue;
       using D = Dual<3>;
       const D R = D::var(r, 0);
-      const D S = D::var(fam >= 1 ? std::max(sigma[i], kSigmaFloor) : kSigmaFloor, 1);
-      const D Tt = D::var(fam >= 2 ? std::max(tau[i], kTauFloor) : kTauFloor, 2);
+      const double t0 = fam >= 2 ? std::max(tau[i], kTauFloor) : kTauFloor;
+      double s0 = fam >= 1 ? std::max(sigma[i], kSigmaFloor) : kSigmaFloor;
+      // libxc meta-GGAs (XC_FLAGS_ENFORCE_FHC): the Fermi-hole-curvature bound sigma <= 8 rho tau is applied to the
+      // INPUT VALUE; the potentials stay the plain partial derivatives at the bounded point (no chain rule through
+      // the bound) — this is what reproduces vrho/vsigma/vtau of tests/dft_tests.cpp:138-191, where z = 1 + 1 ulp
+      if (fam >= 2) s0 = std::min(s0, 8.0 * r * t0);
+      const D S = D::var(s0, 1);
+      const D Tt = D::var(t0, 2);
       Vars<D> v{0.5 * R, 0.5 * R, 0.25 * S, 0.25 * S, 0.25 * S, 0.5 * Tt, 0.5 * Tt};
       D F;
       F_dispatch(id, v, F);
@@ -354,6 +447,11 @@ int xc_eval_add(int id, int polarized, size_t n, const double *rho, const double
       if (fam >= 2) {
         ta = std::max(tau[2 * i], kTauFloor);
         tb = std::max(tau[2 * i + 1], kTauFloor);
+        // per-spin-channel Fermi-hole-curvature bound, value only (see the unpolarized branch)
+        saa = std::min(saa, 8.0 * ra * ta);
+        sbb = std::min(sbb, 8.0 * rb * tb);
+        const double lim2 = 0.5 * (saa + sbb);
+        sab = std::min(std::max(sab, -lim2), lim2);
       }
       Vars<D> v{D::var(ra, 0), D::var(rb, 1), D::var(saa, 2), D::var(sab, 3), D::var(sbb, 4), D::var(ta, 5), D::var(tb, 6)};
       D F;
@@ -385,22 +483,43 @@ int orc_xc_family(int id) {
   case ORC_LDA_C_VWN:
   case ORC_LDA_C_VWN_RPA:
   case ORC_LDA_C_VWN_3:
+  case ORC_LDA_C_PW:
+  case ORC_LDA_C_PW_MOD:
     return 0;
   case ORC_GGA_X_B88:
   case ORC_GGA_C_LYP:
   case ORC_GGA_X_PBE:
   case ORC_GGA_C_PBE:
   case ORC_HYB_GGA_XC_B3LYP:
+  case ORC_HYB_GGA_XC_B3LYP5:
+  case ORC_HYB_GGA_XC_PBEH:
+  case ORC_HYB_GGA_XC_BHANDH:
+  case ORC_HYB_GGA_XC_BHANDHLYP:
     return 1;
   case ORC_MGGA_X_R2SCAN:
   case ORC_MGGA_C_R2SCAN:
+  case ORC_MGGA_X_TPSS:
+  case ORC_MGGA_C_TPSS:
     return 2;
   default:
     return -1;
   }
 }
 
-double orc_xc_exx(int id) { return id == ORC_HYB_GGA_XC_B3LYP ? 0.20 : 0.0; }
+double orc_xc_exx(int id) { // xc_hyb_exx_coef (include/occ/dft/functional.h:557-579)
+  switch (id) {
+  case ORC_HYB_GGA_XC_B3LYP:
+  case ORC_HYB_GGA_XC_B3LYP5:
+    return 0.20;
+  case ORC_HYB_GGA_XC_PBEH:
+    return 0.25;
+  case ORC_HYB_GGA_XC_BHANDH:
+  case ORC_HYB_GGA_XC_BHANDHLYP:
+    return 0.50;
+  default:
+    return 0.0;
+  }
+}
 
 int orc_xc_eval(int id, int polarized, size_t n, const double *rho, const double *sigma, const double *tau,
                 double *exc, double *vrho, double *vsigma, double *vtau) {

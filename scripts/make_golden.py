@@ -14,7 +14,8 @@ from occ_b200 import aobasis, molecules  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 CASES = [("water", "def2-svp", "b3lyp", 1, False), ("water", "def2-svp", "pbe", 2, False),
-         ("water", "def2-svp", "r2scan", 1, True), ("water", "def2-svp", "svwn", 1, False)]
+         ("water", "def2-svp", "r2scan", 1, True), ("water", "def2-svp", "svwn", 1, False),
+         ("water", "def2-svp", "tpss", 2, False)]
 
 
 def main():
@@ -48,6 +49,17 @@ def main():
                                       [-0.063735860841572081, 0.0, 0.018656553309952275],
                                       [0.0, 0.0, 0.13035149660035189], [0.0, 0.0, 0.078426011080503066]])
     out["pbe_x_kat_exc"] = np.array([-0.27851489, -0.27851489, -0.39899553, -0.41654061])
+    # tests/dft_tests.cpp:138-191: TPSS known answers (energies of x and c, potentials of c)
+    out["tpss_kat_rows"] = np.array([
+        [0.06019401627252133, -0.12747174847145987, 0.0, 0.03731311973522952, 0.09472176570942804, 0.036634279981580156],
+        [0.06019401627252133, 0.0, -0.12747174847145987, 0.03731311973522952, 0.09472176570942804, 0.036634279981580156],
+        [0.30171849914696935, 0.0, 0.0, 0.26070301592021455, -2.594981941107205, 0.02815789498408782],
+        [0.3550246251878335, 0.0, 0.0, 0.15685208520532756, -6.307746108179051, 0.008662278222335566]])
+    out["tpss_kat_x_exc"] = np.array([-0.33175882, -0.33175882, -0.56154382, -0.59257418])
+    out["tpss_kat_c"] = np.array([[-0.02276044, -0.02276044, -0.04168478, -0.04268936],
+                                  [-5.57565777e-02, -5.57565777e-02, -8.00593613e-02, -8.53775165e-02],
+                                  [3.91761083e-02, 3.91761083e-02, 1.47458233e-01, 5.51608074e-01],
+                                  [1.10283011e-03, 1.10283011e-03, -3.50002323e-01, -1.56487879e+00]])
     p = os.path.join(ROOT, "tests", "golden", "xc_golden.npz")
     np.savez_compressed(p, **out)
     print("wrote", p, os.path.getsize(p), "bytes", len(out), "arrays")

@@ -38,7 +38,8 @@ def _assert_parity(res, ref):
     assert abs(res["n"][0] - ref["n_alpha"]) < 1e-9 and abs(res["n"][1] - ref["n_beta"]) < 1e-9
 
 
-@pytest.mark.parametrize("method", ["svwn", "svwn5", "pbe", "blyp", "b3lyp", "bpbe", "r2scan", "lda_c_vwn_rpa"])
+@pytest.mark.parametrize("method", ["svwn", "svwn5", "pbe", "blyp", "b3lyp", "bpbe", "r2scan", "lda_c_vwn_rpa",
+                                    "tpss", "b3lyp5", "pbeh", "pbe0", "hyb_gga_xc_bhandhlyp", "lda_x lda_c_pw"])
 @pytest.mark.parametrize("nspin", [1, 2])
 def test_water_every_functional_restricted_and_unrestricted(case, oracle, method, nspin):
     res, ref = _build_both(case("water", "def2-svp"), method, nspin, oracle)
@@ -86,6 +87,14 @@ def test_pointwise_functionals_against_golden_and_reference_kat():
     # the reference's own known answers (tests/dft_tests.cpp:71-111), 1e-6 as there
     r = dft.eval_functional("gga_x_pbe", False, g["pbe_x_kat_rho"], (g["pbe_x_kat_grad"] ** 2).sum(1))
     assert np.abs(r["exc"] - g["pbe_x_kat_exc"]).max() < 1e-6
+    # tests/dft_tests.cpp:138-191: TPSS exchange eps; TPSS correlation eps, vrho, vsigma, vtau (1e-6 as there)
+    rows = g["tpss_kat_rows"]
+    ksig = (rows[:, 1:4] ** 2).sum(1)
+    x = dft.eval_functional("mgga_x_tpss", False, rows[:, 0], ksig, rows[:, 5])
+    c = dft.eval_functional("mgga_c_tpss", False, rows[:, 0], ksig, rows[:, 5])
+    assert np.abs(x["exc"] - g["tpss_kat_x_exc"]).max() < 1e-6
+    for got, want in zip((c["exc"], c["vrho"][:, 0], c["vsigma"][:, 0], c["vtau"][:, 0]), g["tpss_kat_c"]):
+        assert np.abs(got - want).max() < 1e-6
     rho, sig, tau = g["fx_rho"], g["fx_sigma"], g["fx_tau"]
     for name in dft.FUNCTIONAL_IDS:
         u = dft.eval_functional(name, False, rho.sum(1), sig[:, 0] + 2 * sig[:, 1] + sig[:, 2], tau.sum(1))

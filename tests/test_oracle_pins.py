@@ -51,8 +51,44 @@ def test_pbe_exchange_known_answers(oracle):
     assert np.abs(r["exc"] - expected).max() < 1e-6
 
 
+# tests/dft_tests.cpp:138-191: rho, grad rho (3), laplacian, tau at four points; TPSS known answers (1e-6)
+TPSS_KAT_ROWS = np.array([
+    [0.06019401627252133, -0.12747174847145987, 0.0, 0.03731311973522952, 0.09472176570942804, 0.036634279981580156],
+    [0.06019401627252133, 0.0, -0.12747174847145987, 0.03731311973522952, 0.09472176570942804, 0.036634279981580156],
+    [0.30171849914696935, 0.0, 0.0, 0.26070301592021455, -2.594981941107205, 0.02815789498408782],
+    [0.3550246251878335, 0.0, 0.0, 0.15685208520532756, -6.307746108179051, 0.008662278222335566]])
+TPSS_KAT = {
+    "exc_x": [-0.33175882, -0.33175882, -0.56154382, -0.59257418],
+    "exc_c": [-0.02276044, -0.02276044, -0.04168478, -0.04268936],
+    "vrho_c": [-5.57565777e-02, -5.57565777e-02, -8.00593613e-02, -8.53775165e-02],
+    "vsigma_c": [3.91761083e-02, 3.91761083e-02, 1.47458233e-01, 5.51608074e-01],
+    "vtau_c": [1.10283011e-03, 1.10283011e-03, -3.50002323e-01, -1.56487879e+00],
+}
+
+
+def tpss_kat_inputs():
+    rho = TPSS_KAT_ROWS[:, 0].copy()
+    sigma = (TPSS_KAT_ROWS[:, 1:4] ** 2).sum(1)
+    tau = TPSS_KAT_ROWS[:, 5].copy()
+    return rho, sigma, tau
+
+
+def test_tpss_known_answers_energies_and_potentials(oracle):
+    """tests/dft_tests.cpp:138-191: mgga_x_tpss eps; mgga_c_tpss eps AND vrho / vsigma / vtau — the one place the
+    reference pins libxc POTENTIALS, so it also pins the dual-number derivative machinery of the oracle"""
+    rho, sigma, tau = tpss_kat_inputs()
+    x = oracle.xc_eval("mgga_x_tpss", False, rho, sigma, tau)
+    c = oracle.xc_eval("mgga_c_tpss", False, rho, sigma, tau)
+    assert np.abs(x["exc"] - TPSS_KAT["exc_x"]).max() < 1e-6
+    assert np.abs(c["exc"] - TPSS_KAT["exc_c"]).max() < 1e-6
+    assert np.abs(c["vrho"][:, 0] - TPSS_KAT["vrho_c"]).max() < 1e-6
+    assert np.abs(c["vsigma"][:, 0] - TPSS_KAT["vsigma_c"]).max() < 1e-6
+    assert np.abs(c["vtau"][:, 0] - TPSS_KAT["vtau_c"]).max() < 1e-6
+
+
 FUNCS = ["lda_x", "lda_c_vwn", "lda_c_vwn_rpa", "lda_c_vwn_3", "gga_x_pbe", "gga_x_b88", "gga_c_pbe", "gga_c_lyp",
-         "hyb_gga_xc_b3lyp", "mgga_x_r2scan", "mgga_c_r2scan"]
+         "hyb_gga_xc_b3lyp", "mgga_x_r2scan", "mgga_c_r2scan", "lda_c_pw", "lda_c_pw_mod", "mgga_x_tpss",
+         "mgga_c_tpss", "hyb_gga_xc_b3lyp5", "hyb_gga_xc_pbeh", "hyb_gga_xc_bhandh", "hyb_gga_xc_bhandhlyp"]
 
 
 def _sample(n, seed, polarized):
