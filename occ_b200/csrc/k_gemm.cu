@@ -446,6 +446,191 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_vxc(BuildParams P, const VxcIte
   cp_async_wait<0>();
 }
 
+// ------------------------------------------------------------------------------------------------
+// vxc, resident-B form (the one the build launches).  A CTA owns (tile, 64 output columns): its B operand — the
+// 128-point x 64-column block of G_s = c0 phi + cx phi_x + cy phi_y + cz phi_z (xc_potential_matrix.cpp:33-39 /
+// :86-99), or c_tau phi_k for the meta-GGA terms (:52-56) — is the same for every row block, so it is BUILT ONCE IN
+// SHARED MEMORY straight from the AO slabs (no G slab in HBM, no k_gbuild pass, no per-chunk B traffic, no per-point
+// DMUL in the MMA loop).  Only the A operand (phi_a^T) streams, and it streams PER WARP: warp w owns rows
+// [16 w, 16 w + 16) of every 128-row block and all 64 columns (2 x 8 DMMA tiles), stages its own 16 x RK slices
+// through a private cp.async ring and synchronises with __syncwarp only — the main loop has no CTA-wide barrier.
+// Shared memory: B 64 x 132 doubles (66 KiB) + 8 warps x RS stages x 16 x 20 doubles (40 KiB) -> 2 CTAs / SM.
+#ifndef XC_RK
+#define XC_RK 16
+#endif
+#ifndef XC_RS
+#define XC_RS 2
+#endif
+constexpr int RK = XC_RK, RS = XC_RS;
+constexpr int R_LDA = RK + 4;          // = 4 (mod 8): conflict-free (groupID, threadInGroup) fragment loads
+constexpr int R_LDB = TILE_P + 4;
+constexpr int R_WROWS = GM / 8;        // rows of a row block owned by one warp
+constexpr int R_ASZ = R_WROWS * R_LDA, R_BSZ = GN * R_LDB;
+constexpr int R_SMEM_DOUBLES = R_BSZ + 8 * RS * R_ASZ + GN / 2; // + 64 ints: global column of each output column
+
+__global__ void __launch_bounds__(NTHREADS, 2) k_vxc_resident(BuildParams P, const VxcItem *__restrict__ items) {
+  extern __shared__ __align__(16) double smem[];
+  const VxcItem it = items[blockIdx.x];
+  const TileDesc t = P.tiles[it.tile];
+  if (P.leaf_skip[t.leaf]) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int nb = t.nb, nbp = t.nbp;
+  const size_t slab = static_cast<size_t>(nbp) * TILE_P;
+  const double *base = P.scratch + t.scr_off;
+  const double *Ag = base + static_cast<size_t>(it.acomp) * slab; // phi_a[i*128 + p]
+  const int *gidx = P.bf_index + t.bf_off;
+  double *Kt = P.Ktmp[it.spin];
+  const int n0 = it.jb * GN;
+  const int nib = (nb + GM - 1) / GM;
+  constexpr int NKC = TILE_P / RK;
+  const int nq = nib * NKC; // flattened (ib, kc) chunks
+  const int ni_valid = min(8, max(0, (nb - n0 + 7) >> 3));
+  double *Bres = smem;                                   // [64][R_LDB]
+  double *Aw = smem + R_BSZ + warp * (RS * R_ASZ);       // this warp's ring: RS x [16][R_LDA]
+  int *scol = reinterpret_cast<int *>(smem + R_BSZ + 8 * RS * R_ASZ);
+
+  auto load_stage = [&](int q, int stage) {
+    double *As = Aw + stage * R_ASZ;
+    const int ib = q / NKC, kc = q % NKC;
+    constexpr int SPR = RK / 2; // 16-byte segments per row
+#pragma unroll
+    for (int r = 0; r < R_WROWS * SPR / 32; ++r) {
+      const int seg = lane + 32 * r;
+      const int row = seg / SPR, s2 = (seg % SPR) * 2;
+      const int i = ib * GM + warp * R_WROWS + row;
+      cp_async16(As + row * R_LDA + s2, Ag + static_cast<size_t>(i < nbp ? i : 0) * TILE_P + kc * RK + s2, i < nbp);
+    }
+  };
+  // the A rings start filling while the B block is being built
+#pragma unroll
+  for (int s = 0; s < RS - 1; ++s) {
+    if (s < nq) load_stage(s, s);
+    cp_async_commit();
+  }
+
+  { // resident B block: thread = (point, 32-column half)
+    const int p = tid & (TILE_P - 1), half = tid >> 7;
+    const double *cf = P.coef + (static_cast<size_t>(it.tile) * P.nspin + it.spin) * NCOEF * TILE_P + p;
+    const double *q0 = base + static_cast<size_t>(n0 + half * 32) * TILE_P + p;
+    double *dst = Bres + (half * 32) * R_LDB + p;
+    if (it.acomp == 0) {
+      const double c0 = cf[0];
+      if (P.deriv >= 1) {
+        const double cx = cf[TILE_P], cy = cf[2 * TILE_P], cz = cf[3 * TILE_P];
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+          const double *q = q0 + j * TILE_P;
+          dst[j * R_LDB] = c0 * q[0] + cx * q[slab] + cy * q[2 * slab] + cz * q[3 * slab];
+        }
+      } else {
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) dst[j * R_LDB] = c0 * q0[j * TILE_P];
+      }
+    } else {
+      const double ct = cf[4 * TILE_P];
+      const double *qk = q0 + static_cast<size_t>(it.acomp) * slab;
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) dst[j * R_LDB] = ct * qk[j * TILE_P];
+    }
+    if (tid < GN) scol[tid] = n0 + tid < nb ? __ldg(gidx + n0 + tid) : -1;
+  }
+  __syncthreads(); // the only CTA-wide barrier: B block and column map complete
+
+  double acc[2][8][2];
+  int ib = 0, kc = 0;
+  bool full = false;
+  int mi_valid = 0;
+  int grow[2] = {0, 0};
+  const double *Bw = Bres + gid * R_LDB + tig;
+  for (int q = 0; q < nq; ++q) {
+    if (kc == 0) {
+      mi_valid = min(2, max(0, (nb - (ib * GM + warp * R_WROWS) + 7) >> 3));
+      full = mi_valid == 2 && ni_valid == 8;
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int i = ib * GM + warp * R_WROWS + mi * 8 + gid;
+        grow[mi] = i < nb ? __ldg(gidx + i) : -1;
+      }
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    }
+    cp_async_wait<RS - 2>();
+    __syncwarp(); // this warp's stage q has landed for all its lanes; its stage q-1 is free again
+    const double *As = Aw + (q % RS) * R_ASZ + gid * R_LDA + tig;
+    const double *Bs = Bw + kc * RK;
+    if (full) {
+#pragma unroll
+      for (int k4 = 0; k4 < RK / 4; ++k4) {
+        double a[2], b[8];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) a[mi] = As[mi * 8 * R_LDA + k4 * 4];
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) b[ni] = Bs[ni * 8 * R_LDB + k4 * 4];
+        if (k4 == 0) { // refill as soon as the first fragments are in flight
+          if (q + RS - 1 < nq) load_stage(q + RS - 1, (q + RS - 1) % RS);
+          cp_async_commit();
+        }
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+      }
+    } else {
+      if (q + RS - 1 < nq) load_stage(q + RS - 1, (q + RS - 1) % RS);
+      cp_async_commit();
+      if (mi_valid > 0 && ni_valid > 0) {
+#pragma unroll
+        for (int k4 = 0; k4 < RK / 4; ++k4) {
+          double a[2];
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) a[mi] = As[mi * 8 * R_LDA + k4 * 4];
+#pragma unroll
+          for (int ni = 0; ni < 8; ++ni)
+            if (ni < ni_valid) {
+              const double b = Bs[ni * 8 * R_LDB + k4 * 4];
+#pragma unroll
+              for (int mi = 0; mi < 2; ++mi)
+                if (mi < mi_valid) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b);
+            }
+        }
+      }
+    }
+    if (kc == NKC - 1 && !(P.debug & 1)) {
+      // scatter-add this warp's 16 x 64 block of Ktmp_loc into the full matrix (dft.h:361-369)
+#pragma unroll
+      for (int ni = 0; ni < 8; ++ni) {
+        const int2 gc = *reinterpret_cast<const int2 *>(scol + ni * 8 + 2 * tig);
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+          if (grow[mi] >= 0) {
+            if (gc.x >= 0) red_add_f64(Kt + static_cast<size_t>(gc.x) * P.ldD + grow[mi], acc[mi][ni][0]);
+            if (gc.y >= 0) red_add_f64(Kt + static_cast<size_t>(gc.y) * P.ldD + grow[mi], acc[mi][ni][1]);
+          }
+        }
+      }
+    }
+    if (++kc == NKC) {
+      kc = 0;
+      ++ib;
+    }
+  }
+  cp_async_wait<0>();
+}
+
+void launch_vxc_resident(const BuildParams &P, const VxcItem *items, int nitems, void *stream) {
+  if (nitems <= 0) return;
+  static bool configured = false;
+  const int smem_bytes = R_SMEM_DOUBLES * sizeof(double);
+  if (!configured) {
+    cudaFuncSetAttribute(k_vxc_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    configured = true;
+  }
+  k_vxc_resident<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
+}
+
 void launch_density(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
   if (nitems <= 0) return;
   static bool configured = false;

@@ -723,10 +723,11 @@ int occ_xc_build_device(occ_xc_handle *h, const double *D2_dev, double *K_dev, d
     launch_functional(P, b.leaf0, b.nleaves, st);
     PHASE_END(3);
     PHASE_BEGIN();
-    launch_gbuild(P, h->d_g + b.g_off, static_cast<int>(b.ng), st);
+    if (P.debug & 4) launch_gbuild(P, h->d_g + b.g_off, static_cast<int>(b.ng), st);
     PHASE_END(4);
     PHASE_BEGIN();
-    launch_vxc(P, h->d_vxc + b.vxc_off, static_cast<int>(b.nvxc), st);
+    if (P.debug & 4) launch_vxc(P, h->d_vxc + b.vxc_off, static_cast<int>(b.nvxc), st);
+    else launch_vxc_resident(P, h->d_vxc + b.vxc_off, static_cast<int>(b.nvxc), st);
     PHASE_END(5);
   }
   st = main_st;
