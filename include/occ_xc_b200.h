@@ -128,7 +128,8 @@ typedef struct {
 int occ_xc_get_info(const occ_xc_handle *h, occ_xc_info_t *info);
 
 /* Per-phase device times (ms, CUDA events on the build stream) of the LAST build when profiling is on.
- * phases: 0 prepare-D, 1 collocation, 2 density contraction, 3 functional, 4 G slab, 5 Vxc contraction, 6 finalise */
+ * phases: 0 prepare-D, 1 collocation, 2 density contraction, 3 functional, 4 (G slab: always 0 in the build since the
+ * Vxc kernel forms its G block in shared memory; index kept stable), 5 Vxc contraction, 6 finalise */
 #define OCC_XC_NPHASES 7
 int occ_xc_set_profiling(occ_xc_handle *h, int on);
 int occ_xc_get_phase_ms(occ_xc_handle *h, double *ms /* [OCC_XC_NPHASES] */);

@@ -7,8 +7,8 @@
 //       leaf's local->global index list while it is staged into shared memory (reference gathers Dloc
 //       on the host, include/occ/dft/dft.h:340-348).
 //   vxc      (reference: xc_potential_matrix, src/dft/xc_potential_matrix.cpp:8-135)
-//       Ktmp_loc = phi_a^T . B  (nb x nb, K = 128 points), B = G (the weighted AO combination) or phi_k
-//       scaled by the tau coefficient; scattered with red.global.add.f64 straight into the full-size
+//       Ktmp_loc = phi_a^T . B  (nb x nb, K = 128 points), B = G (the weighted AO combination) or c_tau phi_k,
+//       built per CTA in shared memory; scattered with red.global.add.f64 straight into the full-size
 //       matrix (reference scatters Kblk on the host, dft.h:361-369).  K = Ktmp + Ktmp^T afterwards.
 //
 // Both run on the FP64 tensor pipe: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4 — the only f64 MMA shape sm_100a
@@ -32,9 +32,6 @@ constexpr int NTHREADS = 256;
 // density: A stage is [k][m] (m contiguous), ld 132; B stage is [n][k] (k contiguous), ld 20
 constexpr int D_LDA = GM + 4, D_LDB = GK + 4;
 constexpr int D_ASZ = GK * D_LDA, D_BSZ = GN * D_LDB, D_STAGE = D_ASZ + D_BSZ;
-// vxc: A stage is [m][k] (k contiguous), ld 20; B stage is [n][k], ld 20
-constexpr int V_LDA = GK + 4, V_LDB = GK + 4;
-constexpr int V_ASZ = GM * V_LDA, V_BSZ = GN * V_LDB, V_STAGE = V_ASZ + V_BSZ;
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -248,7 +245,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_xc_gradient(BuildParams P, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// G slab: G_s = c0 phi + cx phi_x + cy phi_y + cz phi_z  (the bracket of xc_potential_matrix.cpp:33-39 / :86-99)
+// G slab: G_s = c0 phi + cx phi_x + cy phi_y + cz phi_z  (the bracket of xc_potential_matrix.cpp:33-39 / :86-99),
+// materialised in HBM only for the XC nuclear gradient (A operand of k_xc_gradient); the Vxc build forms its G block
+// in shared memory inside k_vxc_resident.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TILE_P) k_gbuild(BuildParams P, const DensItem *__restrict__ items) {
   const DensItem it = items[blockIdx.x];
@@ -273,177 +272,6 @@ __global__ void __launch_bounds__(TILE_P) k_gbuild(BuildParams P, const DensItem
       for (int j = 0; j < GN; ++j) G[j * TILE_P] = c0 * phi[j * TILE_P];
     }
   }
-}
-
-// ------------------------------------------------------------------------------------------------
-// vxc
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 2) k_vxc(BuildParams P, const VxcItem *__restrict__ items) {
-  extern __shared__ __align__(16) double smem[];
-  const VxcItem it = items[blockIdx.x];
-  const TileDesc t = P.tiles[it.tile];
-  if (P.leaf_skip[t.leaf]) return;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int gid = lane >> 2, tig = lane & 3;
-  const int wm = warp & 3, wn = warp >> 2;
-  const int nb = t.nb, nbp = t.nbp;
-  const size_t slab = static_cast<size_t>(nbp) * TILE_P;
-  const double *base = P.scratch + t.scr_off;
-  const double *Ag = base + static_cast<size_t>(it.acomp) * slab; // phi_a[i*128 + p]
-  const double *Bg = (it.acomp == 0 ? base + static_cast<size_t>(P.ncomp + it.spin) * slab : Ag) +
-                     static_cast<size_t>(it.jb) * GN * TILE_P; // B[j*128 + p]
-  const int *gidx = P.bf_index + t.bf_off;
-  double *Kt = P.Ktmp[it.spin];
-  const int n0 = it.jb * GN;
-  const int nib = (nb + GM - 1) / GM;
-  constexpr int NKC = TILE_P / GK;
-  const int nq = nib * NKC; // flattened (ib, kc) chunks
-  const int ni_valid = min(4, max(0, (nb - (n0 + wn * 32) + 7) >> 3));
-  double *sct = smem + GSTAGES * V_STAGE; // [128] tau coefficient (acomp != 0)
-  if (tid < TILE_P)
-    sct[tid] = it.acomp == 0
-                   ? 1.0
-                   : P.coef[((static_cast<size_t>(it.tile) * P.nspin + it.spin) * NCOEF + 4) * TILE_P + tid];
-
-  auto load_stage = [&](int q, int stage) {
-    double *As = smem + stage * V_STAGE;
-    double *Bs = As + V_ASZ;
-    const int ib = q / NKC, kc = q % NKC;
-    constexpr int SPR = GK / 2; // 16-byte segments per row
-#pragma unroll
-    for (int r = 0; r < GM * SPR / NTHREADS; ++r) {
-      const int seg = tid + NTHREADS * r;
-      const int row = seg / SPR, s2 = (seg % SPR) * 2;
-      const int i = ib * GM + row;
-      cp_async16(As + row * V_LDA + s2, Ag + static_cast<size_t>(i < nbp ? i : 0) * TILE_P + kc * GK + s2, i < nbp);
-    }
-#pragma unroll
-    for (int r = 0; r < GN * SPR / NTHREADS; ++r) {
-      const int seg = tid + NTHREADS * r;
-      const int row = seg / SPR, s2 = (seg % SPR) * 2;
-      cp_async16(Bs + row * V_LDB + s2, Bg + static_cast<size_t>(row) * TILE_P + kc * GK + s2, true);
-    }
-  };
-
-  // global column offsets of this thread's 8 output columns
-  size_t coloff[4][2];
-  bool cvalid[4][2];
-#pragma unroll
-  for (int ni = 0; ni < 4; ++ni)
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int j = n0 + wn * 32 + ni * 8 + 2 * tig + e;
-      cvalid[ni][e] = j < nb;
-      coloff[ni][e] = cvalid[ni][e] ? static_cast<size_t>(__ldg(gidx + j)) * P.ldD : 0;
-    }
-
-  double acc[4][4][2];
-#pragma unroll
-  for (int s = 0; s < GSTAGES - 1; ++s) {
-    if (s < nq) load_stage(s, s);
-    cp_async_commit();
-  }
-  int ib = 0, kc = 0;
-  bool full = false;
-  int mi_valid = 0;
-  const bool scaled = it.acomp != 0;
-  int grow[4] = {0, 0, 0, 0}; // global rows of this thread's 4 output rows, fetched at the start of every row block
-  for (int q = 0; q < nq; ++q) {
-    if (kc == 0) {
-      mi_valid = min(4, max(0, (nb - (ib * GM + wm * 32) + 7) >> 3));
-      full = mi_valid == 4 && ni_valid == 4;
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi) {
-        const int i = ib * GM + wm * 32 + mi * 8 + gid;
-        grow[mi] = i < nb ? __ldg(gidx + i) : -1;
-      }
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-    }
-    cp_async_wait<GSTAGES - 2>();
-    __syncthreads();
-    const double *As = smem + (q % GSTAGES) * V_STAGE + (wm * 32 + gid) * V_LDA;
-    const double *Bs = smem + (q % GSTAGES) * V_STAGE + V_ASZ + (wn * 32 + gid) * V_LDB;
-    const double *sc = sct + kc * GK + tig;
-    if (full && !scaled) {
-      // B = G slab: no per-point factor on the A fragment (the DMUL would compete with DMMA for the FP64 pipe)
-#pragma unroll
-      for (int k4 = 0; k4 < GK / 4; ++k4) {
-        double a[4], b[4];
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi) a[mi] = As[mi * 8 * V_LDA + k4 * 4 + tig];
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[ni * 8 * V_LDB + k4 * 4 + tig];
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-        if (k4 == GK / 8 - 1) { // refill issued mid-chunk: the pipe is fed right after the barrier
-          if (q + GSTAGES - 1 < nq) load_stage(q + GSTAGES - 1, (q + GSTAGES - 1) % GSTAGES);
-          cp_async_commit();
-        }
-      }
-    } else if (full) {
-#pragma unroll
-      for (int k4 = 0; k4 < GK / 4; ++k4) {
-        double a[4], b[4];
-        const double f = sc[k4 * 4];
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi) a[mi] = As[mi * 8 * V_LDA + k4 * 4 + tig] * f;
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[ni * 8 * V_LDB + k4 * 4 + tig];
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-        if (k4 == GK / 8 - 1) {
-          if (q + GSTAGES - 1 < nq) load_stage(q + GSTAGES - 1, (q + GSTAGES - 1) % GSTAGES);
-          cp_async_commit();
-        }
-      }
-    } else {
-      if (q + GSTAGES - 1 < nq) load_stage(q + GSTAGES - 1, (q + GSTAGES - 1) % GSTAGES);
-      cp_async_commit();
-    }
-    if (!full && mi_valid > 0 && ni_valid > 0) {
-#pragma unroll
-      for (int k4 = 0; k4 < GK / 4; ++k4) {
-        double b[4];
-        const double f = sc[k4 * 4];
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[ni * 8 * V_LDB + k4 * 4 + tig];
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-          if (mi < mi_valid) {
-            const double a = As[mi * 8 * V_LDA + k4 * 4 + tig] * f;
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni)
-              if (ni < ni_valid) dmma884(acc[mi][ni][0], acc[mi][ni][1], a, b[ni]);
-          }
-      }
-    }
-    if (kc == NKC - 1 && !(P.debug & 1)) {
-      // scatter-add this 128 x 64 block of Ktmp_loc into the full matrix (dft.h:361-369)
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi) {
-        if (grow[mi] >= 0) {
-          double *dst = Kt + grow[mi];
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni) {
-            if (cvalid[ni][0]) red_add_f64(dst + coloff[ni][0], acc[mi][ni][0]);
-            if (cvalid[ni][1]) red_add_f64(dst + coloff[ni][1], acc[mi][ni][1]);
-          }
-        }
-      }
-    }
-    if (++kc == NKC) {
-      kc = 0;
-      ++ib;
-    }
-  }
-  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -674,17 +502,6 @@ void launch_transpose(const double *D, double *DT, int nbf, int ld, void *stream
 void launch_gbuild(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
   if (nitems <= 0) return;
   k_gbuild<<<nitems, TILE_P, 0, static_cast<cudaStream_t>(stream)>>>(P, items);
-}
-
-void launch_vxc(const BuildParams &P, const VxcItem *items, int nitems, void *stream) {
-  if (nitems <= 0) return;
-  static bool configured = false;
-  const int smem_bytes = (GSTAGES * V_STAGE + TILE_P) * sizeof(double);
-  if (!configured) {
-    cudaFuncSetAttribute(k_vxc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    configured = true;
-  }
-  k_vxc<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
 }
 
 } // namespace xcb

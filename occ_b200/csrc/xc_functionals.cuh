@@ -380,7 +380,7 @@ template <class T> XC_HD T e_tpss_x(const XV<T> &v) {
 }
 template <class T> XC_HD T pbe_c_eps_one_spin(const T &n, const T &sigma) { // eps_c^PBE(n, 0, grad n, 0): zeta = 1
   const double beta = 0.06672455060314922;
-  const double phi2 = 0.3968502629920499, phi3 = 0.25; // phi(1) = 2^(-1/3)
+  const double phi2 = 0.6299605249474366, phi3 = 0.5; // phi(1) = 2^(-1/3)
   const T rs = cbrt(XC_RS_C / n);
   const T ec = pw_g(pw_set(1), rs, sqrt(rs));
   const T kF = cbrt(XC_3PI2 * n);

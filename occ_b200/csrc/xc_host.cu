@@ -405,7 +405,10 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
     for (int s = 0; s < nsh; ++s) h->natoms = std::max(h->natoms, basis->shell_atom[s] + 1);
   h->nb_min = 1 << 30;
   h->nb_max = 0;
-  const int nslab = h->ncomp + nspin + (want_grad && deriv >= 1 ? 3 * nspin : 0) + (want_grad && deriv >= 2 ? 6 * nspin : 0);
+  // AO slabs per tile: phi (, grad phi); handles that also serve occ_xc_gradient add the G_s, H_s,d and S_s,de slabs.
+  // The Vxc build itself needs no G slab: k_vxc_resident forms its G block in shared memory.
+  const int nslab = h->ncomp + (want_grad ? nspin : 0) + (want_grad && deriv >= 1 ? 3 * nspin : 0) +
+                    (want_grad && deriv >= 2 ? 6 * nspin : 0);
   std::vector<int> bf_atom;
 
   // ---- tiles, padded points, per-leaf index lists ----
@@ -657,7 +660,7 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
   }
   h->launches = 0;
   for (const Batch &b : h->batches)
-    h->launches += (b.ncolloc > 0) + (b.ndens > 0) + (b.nleaves > 0) + (b.ng > 0) + (b.nvxc > 0);
+    h->launches += (b.ncolloc > 0) + (b.ndens > 0) + (b.nleaves > 0) + (b.nvxc > 0);
   h->launches += 2 + (nspin == 1 ? 1 : 0);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
@@ -723,11 +726,7 @@ int occ_xc_build_device(occ_xc_handle *h, const double *D2_dev, double *K_dev, d
     launch_functional(P, b.leaf0, b.nleaves, st);
     PHASE_END(3);
     PHASE_BEGIN();
-    if (P.debug & 4) launch_gbuild(P, h->d_g + b.g_off, static_cast<int>(b.ng), st);
-    PHASE_END(4);
-    PHASE_BEGIN();
-    if (P.debug & 4) launch_vxc(P, h->d_vxc + b.vxc_off, static_cast<int>(b.nvxc), st);
-    else launch_vxc_resident(P, h->d_vxc + b.vxc_off, static_cast<int>(b.nvxc), st);
+    launch_vxc_resident(P, h->d_vxc + b.vxc_off, static_cast<int>(b.nvxc), st);
     PHASE_END(5);
   }
   st = main_st;

@@ -111,7 +111,6 @@ struct C2STable {
 void launch_collocate(const BuildParams &P, const CollocItem *items, int nitems, void *stream);
 void launch_density(const BuildParams &P, const DensItem *items, int nitems, void *stream);
 void launch_functional(const BuildParams &P, int leaf0, int nleaves, void *stream);
-void launch_vxc(const BuildParams &P, const VxcItem *items, int nitems, void *stream);
 void launch_vxc_resident(const BuildParams &P, const VxcItem *items, int nitems, void *stream);
 void launch_gbuild(const BuildParams &P, const DensItem *items, int nitems, void *stream);
 void launch_collocate_h(const BuildParams &P, const CollocItem *items, int nitems, void *stream);

@@ -62,3 +62,64 @@ def test_synthetic_density_is_symmetric_psd():
     assert np.allclose(D, D.T) and np.linalg.eigvalsh(D).min() > -1e-12
     D2 = molecules.synthetic_density(b, 2)
     assert D2.shape == (2 * b.nbf, b.nbf)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The product's DEVICE functionals (occ_b200/csrc/xc_functionals.cuh, __host__ __device__) compiled for the host by a
+# test harness (tests/cpp/functional_table.cu): the CPU suite can then check them against the oracle and the
+# reference's known answers before any GPU time is spent.
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FT_EXE = os.path.join(ROOT, "tests", "cpp", "functional_table")
+
+
+def _functional_table_exe():
+    src = os.path.join(ROOT, "tests", "cpp", "functional_table.cu")
+    inc = os.path.join(ROOT, "occ_b200", "csrc")
+    deps = [src] + [os.path.join(inc, f) for f in ("xc_functionals.cuh", "xc_dual.cuh")]
+    if not os.path.exists(FT_EXE) or os.path.getmtime(FT_EXE) < max(os.path.getmtime(d) for d in deps):
+        nvcc = "/usr/local/cuda/bin/nvcc"
+        if not os.path.exists(nvcc):
+            pytest.skip("nvcc not available and tests/cpp/functional_table not prebuilt")
+        subprocess.check_call([nvcc, "-std=c++17", "-O1", "-w", "-ccbin", "/usr/bin/g++", "-I" + inc, "-o", FT_EXE, src])
+    return FT_EXE
+
+
+def _device_functional_on_host(fid, polarized, fam, rho, sigma, tau):
+    n = len(rho)
+    s, g = (2, 3) if polarized else (1, 1)
+    buf = b"".join(np.ascontiguousarray(a, dtype=np.float64).tobytes() for a in (rho, sigma, tau))
+    out = subprocess.run([_functional_table_exe(), str(fid), str(int(polarized)), str(fam), str(n)], input=buf,
+                         capture_output=True, check=True).stdout
+    r = np.frombuffer(out, dtype=np.float64).reshape(n, 1 + s + g + s)
+    return {"exc": r[:, 0], "vrho": r[:, 1:1 + s], "vsigma": r[:, 1 + s:1 + s + g], "vtau": r[:, 1 + s + g:]}
+
+
+def test_device_functionals_on_host_match_oracle_and_reference_kat(oracle):
+    gk = np.load(os.path.join(ROOT, "tests", "golden", "xc_golden.npz"))
+    rows = gk["tpss_kat_rows"]
+    rho, sigma, tau = rows[:, 0], (rows[:, 1:4] ** 2).sum(1), rows[:, 5]
+    TPSS_KAT = {"exc_x": gk["tpss_kat_x_exc"], "exc_c": gk["tpss_kat_c"][0], "vrho_c": gk["tpss_kat_c"][1],
+                "vsigma_c": gk["tpss_kat_c"][2], "vtau_c": gk["tpss_kat_c"][3]}
+    x = _device_functional_on_host(202, False, 2, rho, sigma, tau)
+    c = _device_functional_on_host(231, False, 2, rho, sigma, tau)
+    assert np.abs(x["exc"] - TPSS_KAT["exc_x"]).max() < 1e-6          # tests/dft_tests.cpp:138-191
+    assert np.abs(c["exc"] - TPSS_KAT["exc_c"]).max() < 1e-6
+    assert np.abs(c["vrho"][:, 0] - TPSS_KAT["vrho_c"]).max() < 1e-6
+    assert np.abs(c["vsigma"][:, 0] - TPSS_KAT["vsigma_c"]).max() < 1e-6
+    assert np.abs(c["vtau"][:, 0] - TPSS_KAT["vtau_c"]).max() < 1e-6
+    g = np.load(os.path.join(ROOT, "tests", "golden", "xc_golden.npz"))
+    rho, sig, tau = g["fx_rho"], g["fx_sigma"], g["fx_tau"]
+    for name, fid in dft.FUNCTIONAL_IDS.items():
+        fam = oracle.lib().orc_xc_family(fid)
+        u = _device_functional_on_host(fid, False, fam, rho.sum(1), sig[:, 0] + 2 * sig[:, 1] + sig[:, 2], tau.sum(1))
+        p = _device_functional_on_host(fid, True, fam, rho, sig, tau)
+        for got, ref in ((u, g[f"fx_{name}_u"]), (p, g[f"fx_{name}_p"])):
+            s = got["vrho"].shape[1]
+            nsig = got["vsigma"].shape[1]
+            want = {"exc": ref[:, 0], "vrho": ref[:, 1:1 + s], "vsigma": ref[:, 1 + s:1 + s + nsig], "vtau": ref[:, 1 + s + nsig:]}
+            keys = ["exc", "vrho"] + (["vsigma"] if fam >= 1 else []) + (["vtau"] if fam >= 2 else [])
+            for k in keys:
+                assert np.allclose(got[k], want[k], rtol=1e-10, atol=1e-13), (name, k)
