@@ -40,6 +40,7 @@ WORKLOADS = {
     "taxol_r2scan_tzvp": ("taxol", "def2-tzvp", "r2scan", 1, None),
 }
 DEFAULT_WORKLOAD = "valinomycin_b3lyp_tzvp"
+KERNEL_NAMES = {"density": "k_density", "vxc": "k_vxc_resident"}
 
 
 def make_inputs(workload):
@@ -273,7 +274,7 @@ def run_b200(args):
         try:   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
             tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload)
             if tj and tj.get("batch_mb") == args.batch_mb and world == 1:
-                traffic = tj.get("k_" + dom)
+                traffic = tj.get(KERNEL_NAMES[dom])
         except Exception:
             pass
         cpu = None
@@ -299,7 +300,7 @@ def run_b200(args):
             "xc_energy": exc, "n_electrons": na + (nb_ if nspin == 2 else 0.0),
             "algorithmic_tflops": flops_total / (ms_dev * 1e-3) / 1e12,
             "fp64_tensor_frac_whole_build": flops_total / (ms_dev * 1e-3) / 1e12 / (FP64_TENSOR_PEAK_TFLOPS * world),
-            "roofline": {"bound": "tensor", "kernel": "k_" + dom, "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS,
+            "roofline": {"bound": "tensor", "kernel": KERNEL_NAMES[dom], "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS,
                          "unit": "TFLOP/s", "frac": achieved / FP64_TENSOR_PEAK_TFLOPS, "traffic": traffic,
                          "algorithmic_flops_per_launch": 0.5 * info["flops_per_build"] / max(1, info["nbatches"]),
                          "peak_source": "measured DMMA.8x8x4 microbenchmark on this pool's B200 "
