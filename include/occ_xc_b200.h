@@ -115,6 +115,20 @@ int occ_xc_build_device(occ_xc_handle *h, const double *D2_dev, double *K_dev, d
  * (this rank's shard: partial sums add up over ranks).  The handle must have been created with options.reserved[2] = 1. */
 int occ_xc_gradient(occ_xc_handle *h, const double *D2, double *gradient);
 
+/* SURVEY 8(f) rank 4 — post-SCF VV10 non-local correlation, NonLocalCorrelationFunctional::vv10(basis, mo)
+ * (src/dft/nonlocal_correlation.cpp:38-118 vv10_kernel, :367-420 vv10; called from DFT::post_scf_nlc_correction,
+ * include/occ/dft/dft.h:477-483).  The handle is created over the NLC grid (the reference's default NLC GridSettings
+ * are {110, 50, 50, 1e-7, no first-row reduction}, nonlocal_correlation.h:38-41) with nspin = 1, a GGA functional list
+ * (only rho / grad rho are used), world_size 1, and screening_threshold <= 0 to reproduce the reference's dense
+ * evaluate_basis (a positive threshold screens shells per leaf like the XC build: a ~1e-10 change).
+ *   D2          nbf x nbf column-major, doubled (2 * mo.D)
+ *   orig_index  [npts] for each point in the handle's (Morton-sorted) order its index in the order the reference
+ *               concatenates its atom grids — the reference's pair sum runs over j < i in THAT order; NULL = identity
+ *   K           nbf x nbf, overwritten with Result::Vxc;   *energy = Result::energy
+ * HOST buffers; synchronous.  Restricted only ("Only restricted NLC functional implemented right now"). */
+int occ_xc_vv10(occ_xc_handle *h, const double *D2, const size_t *orig_index, double vv10_b, double vv10_C, double *K,
+                double *energy);
+
 /* Geometry-only facts of the handle (this rank's shard) */
 typedef struct {
   int nbf, nspin, deriv, nsh;

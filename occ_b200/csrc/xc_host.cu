@@ -212,6 +212,13 @@ struct occ_xc_handle {
   bool profiling = false;
   double phase_ms[OCC_XC_NPHASES] = {0, 0, 0, 0, 0, 0, 0};
   size_t launches = 0;
+  // post-SCF VV10 (allocated on first use)
+  std::vector<size_t> h_tile_src; // sorted index of the first point of each tile
+  size_t npts_total = 0;          // points of the caller's whole grid (orig_index range)
+  VV10Params vv = {};
+  int2 *d_vv_items = nullptr;
+  int n_vv_items = 0;
+  size_t *d_vv_orig = nullptr;
 };
 
 template <class T> static int dev_alloc(occ_xc_handle *h, T **ptr, size_t count) {
@@ -449,6 +456,7 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
       t.sh_off = sh_off;
       t.nsh = e.nshl;
       t.scr_off = 0;
+      h->h_tile_src.push_back(lf.offset + static_cast<size_t>(k) * TILE_P);
       for (int p = 0; p < TILE_P; ++p) {
         const bool valid = p < t.count;
         const size_t src = lf.offset + static_cast<size_t>(k) * TILE_P + (valid ? p : 0);
@@ -468,6 +476,7 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
   }
   h->nleaves = static_cast<int>(h->h_leaves.size());
   h->ntiles = static_cast<int>(h->h_tiles.size());
+  h->npts_total = npts;
   if (h->nleaves == 0) h->nb_min = 0;
 
   // ---- batches of consecutive leaves under the workspace budget; per-phase work lists ----
@@ -760,6 +769,84 @@ int occ_xc_build(occ_xc_handle *h, const double *D2, double *K, double *exc, dou
   if (exc) *exc = sc[0];
   if (n_alpha) *n_alpha = sc[1];
   if (n_beta) *n_beta = sc[2];
+  return 0;
+}
+
+int occ_xc_vv10(occ_xc_handle *h, const double *D2, const size_t *orig_index, double vv10_b, double vv10_C, double *K,
+                double *energy) {
+  if (!h || !D2 || !K || !energy) return fail("occ_xc_vv10: null argument");
+  if (h->nspin != 1)
+    return fail("Only restricted NLC functional implemented right now"); // nonlocal_correlation.cpp:370-372
+  if (h->deriv != 1) return fail("occ_xc_vv10: the handle must be created with a GGA functional list (rho and grad rho)");
+  if (h->npts != h->npts_total)
+    return fail("occ_xc_vv10: the handle must hold the whole NLC grid (world_size 1, no leaf dropped by screening)");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  BuildParams P = h->P;
+  const size_t n = h->npts_total;
+  const size_t ksz = static_cast<size_t>(h->nbf) * h->nbf;
+  if (!h->vv.X) { // first use: per-point arrays in the reference's order + the triangular work list
+    size_t *d_src = nullptr;
+    double *buf = nullptr;
+    if (dev_alloc(h, &d_src, h->h_tile_src.size()) || dev_alloc(h, &buf, 9 * n) || dev_alloc(h, &h->d_vv_orig, n)) return 1;
+    CUDA_TRY(cudaMemcpy(d_src, h->h_tile_src.data(), h->h_tile_src.size() * sizeof(size_t), cudaMemcpyHostToDevice));
+    h->vv.n = n;
+    h->vv.tile_src = d_src;
+    h->vv.X = buf;
+    h->vv.Y = buf + n;
+    h->vv.Z = buf + 2 * n;
+    h->vv.rw2 = buf + 3 * n;
+    h->vv.om = buf + 4 * n;
+    h->vv.kap = buf + 5 * n;
+    h->vv.F = buf + 6 * n;
+    h->vv.U = buf + 7 * n;
+    h->vv.W = buf + 8 * n;
+    std::vector<int2> items;
+    const int nblk = static_cast<int>((n + TILE_P - 1) / TILE_P), jc = vv10_jchunk();
+    for (int bi = nblk - 1; bi >= 0; --bi) // longest rows first
+      for (int c = 0; c * jc <= bi; ++c) items.push_back(make_int2(bi, c));
+    h->n_vv_items = static_cast<int>(items.size());
+    if (dev_alloc(h, &h->d_vv_items, items.size())) return 1;
+    CUDA_TRY(cudaMemcpy(h->d_vv_items, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  }
+  VV10Params V = h->vv;
+  if (orig_index) {
+    CUDA_TRY(cudaMemcpyAsync(h->d_vv_orig, orig_index, n * sizeof(size_t), cudaMemcpyHostToDevice, st));
+    V.orig = h->d_vv_orig;
+  } else {
+    V.orig = nullptr;
+  }
+  const double pi = 3.14159265358979323846;
+  V.kappa_factor = vv10_b * 1.5 * pi * std::pow(9.0 * pi, -1.0 / 6.0);
+  V.beta = std::pow(3.0 / (vv10_b * vv10_b), 0.75) / 32.0;
+  V.C = vv10_C;
+  CUDA_TRY(cudaMemcpyAsync(h->d_D, D2, ksz * sizeof(double), cudaMemcpyHostToDevice, st));
+  launch_prepare_density(h->d_D, h->d_Dsym, h->nbf, 1, st);
+  P.Drho[0] = h->d_Dsym;
+  P.Dtau[0] = h->d_D;
+  CUDA_TRY(cudaMemsetAsync(h->d_Ktmp, 0, ksz * sizeof(double), st));
+  // pass 1: rho, grad rho on every tile (the accumulators persist across batches)
+  for (const Batch &b : h->batches) {
+    launch_collocate(P, h->d_colloc + b.colloc_off, static_cast<int>(b.ncolloc), st);
+    CUDA_TRY(cudaMemsetAsync(P.acc + static_cast<size_t>(b.tile0) * NACC * TILE_P, 0,
+                             static_cast<size_t>(b.ntiles) * NACC * TILE_P * sizeof(double), st));
+    launch_density(P, h->d_dens + b.dens_off, static_cast<int>(b.ndens), st);
+  }
+  launch_vv10_prepare(P, V, h->ntiles, st);
+  launch_vv10_pairs(V, h->d_vv_items, h->n_vv_items, st);
+  launch_vv10_coef(P, V, h->nleaves, st);
+  // pass 2: Vxc contraction with the VV10 coefficients (AO values are recomputed: one batch of workspace)
+  for (const Batch &b : h->batches) {
+    if (h->batches.size() > 1) launch_collocate(P, h->d_colloc + b.colloc_off, static_cast<int>(b.ncolloc), st);
+    launch_vxc_resident(P, h->d_vxc + b.vxc_off, static_cast<int>(b.nvxc), st);
+  }
+  launch_finalize(P, h->nleaves, h->d_K, h->d_scalars, st);
+  CUDA_TRY(cudaMemcpyAsync(K, h->d_K, ksz * sizeof(double), cudaMemcpyDeviceToHost, st));
+  double sc[3];
+  CUDA_TRY(cudaMemcpyAsync(sc, h->d_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  *energy = sc[0];
   return 0;
 }
 

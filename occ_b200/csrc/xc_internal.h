@@ -10,6 +10,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <vector_types.h>
 
 namespace xcb {
 
@@ -101,6 +102,18 @@ struct BuildParams {
   int debug; // developer switches for timing experiments (options.reserved[0]): 1 = no Vxc scatter, 2 = no density epilogue
 };
 
+// ---- post-SCF VV10: per-point arrays in the REFERENCE's point order ----
+struct VV10Params {
+  size_t n;               // points of the NLC grid
+  const size_t *tile_src; // [ntiles] sorted index of the tile's first point
+  const size_t *orig;     // [n] sorted index -> index in the reference's (atom-grid) order; NULL = identity
+  double *X, *Y, *Z;      // coordinates
+  double *rw2;            // 2 rho w (0 for points below the 1e-8 density cut)
+  double *om, *kap;       // omega_0, kappa (kappa < 0 marks an inactive point)
+  double *F, *U, *W;      // pair sums
+  double kappa_factor, beta, C;
+};
+
 // spherical transform tables (real solid harmonics, CCA order m = -l..l) in constant memory
 struct C2STable {
   // coef[off[l] + m * ncart(l) + c]
@@ -118,6 +131,10 @@ void launch_grad_gemm(const BuildParams &P, const DensItem *items, int nitems, v
 void launch_transpose(const double *D, double *DT, int nbf, int ld, void *stream);
 void launch_prepare_density(const double *D2, double *Dsym, int nbf, int nspin, void *stream);
 void launch_finalize(const BuildParams &P, int nleaves, double *K, double *scalars, void *stream);
+void launch_vv10_prepare(const BuildParams &P, const VV10Params &V, int ntiles, void *stream);
+void launch_vv10_pairs(const VV10Params &V, const int2 *items, int nitems, void *stream);
+void launch_vv10_coef(const BuildParams &P, const VV10Params &V, int nleaves, void *stream);
+int vv10_jchunk();
 void upload_c2s_table(const C2STable &t);
 int eval_functional_device(int func_id, int polarized, size_t n, const double *rho, const double *sigma,
                            const double *tau, double *exc, double *vrho, double *vsigma, double *vtau);

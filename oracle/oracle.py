@@ -324,3 +324,24 @@ def ref_collocate_shell(l, pure, pts, coefs, exps, center, deriv):
     else:
         R.gg_collocation(*args, _p(out[0]))
     return out
+
+
+def vv10(basis: Basis, pts, w, D2, b=6.0, Cpar=0.01, nthreads=None):
+    """NonLocalCorrelationFunctional::vv10 restatement (src/dft/nonlocal_correlation.cpp:38-118, 367-420).
+    pts/w in the reference's NLC atom-grid order; D2 (nbf, nbf) doubled.  Returns energy, Vxc, rho (n x 4), F/U/W."""
+    nbf = basis.nbf
+    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    n = len(w)
+    D2 = np.asfortranarray(D2, dtype=np.float64)
+    assert D2.shape == (nbf, nbf)
+    K = np.zeros((nbf, nbf), order="F")
+    e = C.c_double(0)
+    rho4 = np.zeros((n, 4))
+    fuw = np.zeros((3, n))
+    lib().orc_vv10.restype = C.c_int
+    rc = lib().orc_vv10(basis.ref, C.c_size_t(n), _p(pts), _p(w), _p(D2), C.c_double(b), C.c_double(Cpar), _p(K),
+                        C.byref(e), _p(rho4), _p(fuw), C.c_int(nthreads or os.cpu_count() or 1))
+    if rc:
+        raise RuntimeError("orc_vv10 failed")
+    return {"energy": e.value, "K": K, "rho": rho4, "F": fuw[0], "U": fuw[1], "W": fuw[2]}
