@@ -115,6 +115,16 @@ int occ_xc_build_device(occ_xc_handle *h, const double *D2_dev, double *K_dev, d
  * (this rank's shard: partial sums add up over ranks).  The handle must have been created with options.reserved[2] = 1. */
 int occ_xc_gradient(occ_xc_handle *h, const double *D2, double *gradient);
 
+/* SURVEY 8(f) rank 4 (density-on-grid consumers: Hirshfeld, XDM, cube files) —
+ * occ::density::evaluate_density_on_grid<max_derivative, kind>(basis, D, grid_pts), include/occ/gto/density.h:67-107.
+ * The handle is created over the caller's points (occ_xc_grid_from_points + occ_xc_create; the functional list only
+ * selects max_derivative: LDA 0, GGA 1, meta-GGA 2) with world_size 1.
+ *   D2   as in occ_xc_build
+ *   rho  (nspin * npts) x {1, 4, 6} column-major, alpha rows [0, npts) then beta, in the handle's (sorted) point order;
+ *        columns rho, rho_x, rho_y, rho_z, laplacian (NOT evaluated: 0), tau.  HOST buffers; synchronous.
+ * Points of leaves that keep no shell under the screening rule (dft.h:309-321) stay 0. */
+int occ_xc_density_on_grid(occ_xc_handle *h, const double *D2, double *rho);
+
 /* SURVEY 8(f) rank 4 — post-SCF VV10 non-local correlation, NonLocalCorrelationFunctional::vv10(basis, mo)
  * (src/dft/nonlocal_correlation.cpp:38-118 vv10_kernel, :367-420 vv10; called from DFT::post_scf_nlc_correction,
  * include/occ/dft/dft.h:477-483).  The handle is created over the NLC grid (the reference's default NLC GridSettings

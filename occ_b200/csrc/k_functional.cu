@@ -213,6 +213,34 @@ void launch_finalize(const BuildParams &P, int nleaves, double *K, double *scala
   k_reduce_scalars<<<1, 256, 0, st>>>(P.leaf_sums, nleaves, scalars);
 }
 
+// ---- density on the grid (occ::density::evaluate_density_on_grid, include/occ/gto/density.h:67-107): turn the
+// density-kernel accumulators into the reference's rho matrix, (nspin * npts) x {1, 4, 6} column-major with the
+// alpha rows first; columns rho, rho_x, rho_y, rho_z, laplacian (NOT evaluated: written as 0), tau ----
+__global__ void __launch_bounds__(TILE_P) k_gather_rho(BuildParams P, const size_t *__restrict__ tile_src, size_t npts,
+                                                       double *__restrict__ out) {
+  const int tile = blockIdx.x, p = threadIdx.x;
+  if (p >= P.tiles[tile].count) return;
+  const size_t si = tile_src[tile] + p;
+  const size_t ld = static_cast<size_t>(P.nspin) * npts;
+  for (int s = 0; s < P.nspin; ++s) {
+    const double *a = P.acc + (static_cast<size_t>(tile) * P.nspin + s) * NACC * TILE_P + p;
+    double *o = out + static_cast<size_t>(s) * npts + si;
+    o[0] = a[0];
+    if (P.deriv >= 1) {
+      o[ld] = 2.0 * a[TILE_P];
+      o[2 * ld] = 2.0 * a[2 * TILE_P];
+      o[3 * ld] = 2.0 * a[3 * TILE_P];
+    }
+    if (P.deriv >= 2) {
+      o[4 * ld] = 0.0;
+      o[5 * ld] = 0.5 * a[4 * TILE_P];
+    }
+  }
+}
+void launch_gather_rho(const BuildParams &P, const size_t *tile_src, size_t npts, int ntiles, double *out, void *stream) {
+  if (ntiles > 0) k_gather_rho<<<ntiles, TILE_P, 0, static_cast<cudaStream_t>(stream)>>>(P, tile_src, npts, out);
+}
+
 // ---- standalone pointwise evaluation (DensityFunctional::evaluate analogue for tests / callers) ----
 template <int FAM, bool POL>
 __global__ void k_eval_points(int id, size_t n, const double *__restrict__ rho, const double *__restrict__ sigma,

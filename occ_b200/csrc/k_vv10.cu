@@ -15,6 +15,17 @@ namespace xcb {
 
 constexpr int VV_JCHUNK = 32; // j-blocks (of 128 points) per work item
 
+// every point starts inactive: points of leaves that keep no shell (dropped at create, dft.h:309-321) have no tile
+__global__ void k_vv10_init(VV10Params V) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= V.n) return;
+  V.X[i] = V.Y[i] = V.Z[i] = 0.0;
+  V.rw2[i] = 0.0;
+  V.om[i] = 1.0;
+  V.kap[i] = -1.0;
+  V.F[i] = V.U[i] = V.W[i] = 0.0;
+}
+
 __global__ void __launch_bounds__(TILE_P) k_vv10_prepare(BuildParams P, VV10Params V) {
   const int tile = blockIdx.x, p = threadIdx.x;
   const TileDesc t = P.tiles[tile];
@@ -177,6 +188,7 @@ __global__ void __launch_bounds__(TILE_P) k_vv10_coef(BuildParams P, VV10Params 
 }
 
 void launch_vv10_prepare(const BuildParams &P, const VV10Params &V, int ntiles, void *stream) {
+  k_vv10_init<<<static_cast<unsigned>((V.n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(V);
   if (ntiles > 0) k_vv10_prepare<<<ntiles, TILE_P, 0, static_cast<cudaStream_t>(stream)>>>(P, V);
 }
 void launch_vv10_pairs(const VV10Params &V, const int2 *items, int nitems, void *stream) {

@@ -215,6 +215,8 @@ struct occ_xc_handle {
   // post-SCF VV10 (allocated on first use)
   std::vector<size_t> h_tile_src; // sorted index of the first point of each tile
   size_t npts_total = 0;          // points of the caller's whole grid (orig_index range)
+  int world = 1;
+  size_t *d_tile_src = nullptr;
   VV10Params vv = {};
   int2 *d_vv_items = nullptr;
   int n_vv_items = 0;
@@ -235,6 +237,13 @@ template <class T> static int dev_upload(occ_xc_handle *h, const T **ptr, const 
   if (dev_alloc(h, &p, v.size())) return 1;
   if (!v.empty()) CUDA_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
   *ptr = p;
+  return 0;
+}
+
+static int ensure_tile_src(occ_xc_handle *h) {
+  if (h->d_tile_src) return 0;
+  if (dev_alloc(h, &h->d_tile_src, h->h_tile_src.size())) return 1;
+  CUDA_TRY(cudaMemcpy(h->d_tile_src, h->h_tile_src.data(), h->h_tile_src.size() * sizeof(size_t), cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -477,6 +486,7 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
   h->nleaves = static_cast<int>(h->h_leaves.size());
   h->ntiles = static_cast<int>(h->h_tiles.size());
   h->npts_total = npts;
+  h->world = world;
   if (h->nleaves == 0) h->nb_min = 0;
 
   // ---- batches of consecutive leaves under the workspace budget; per-phase work lists ----
@@ -772,26 +782,60 @@ int occ_xc_build(occ_xc_handle *h, const double *D2, double *K, double *exc, dou
   return 0;
 }
 
+int occ_xc_density_on_grid(occ_xc_handle *h, const double *D2, double *rho) {
+  if (!h || !D2 || !rho) return fail("occ_xc_density_on_grid: null argument");
+  if (h->world != 1) return fail("occ_xc_density_on_grid: the handle must hold the whole grid (world_size 1)");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (ensure_tile_src(h)) return 1;
+  cudaStream_t st = h->stream;
+  BuildParams P = h->P;
+  const size_t ksz = static_cast<size_t>(h->nspin) * h->nbf * h->nbf;
+  const int ncol = h->deriv == 0 ? 1 : (h->deriv == 1 ? 4 : 6);
+  const size_t nout = static_cast<size_t>(h->nspin) * h->npts_total * ncol;
+  double *d_out = nullptr;
+  CUDA_TRY(cudaMalloc(&d_out, nout * sizeof(double)));
+  cudaMemsetAsync(d_out, 0, nout * sizeof(double), st);
+  cudaMemcpyAsync(h->d_D, D2, ksz * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (h->nspin == 1) {
+    launch_prepare_density(h->d_D, h->d_Dsym, h->nbf, 1, st);
+    P.Drho[0] = h->d_Dsym;
+    P.Dtau[0] = h->d_D;
+  } else {
+    for (int s = 0; s < 2; ++s) P.Drho[s] = P.Dtau[s] = h->d_D + static_cast<size_t>(s) * h->nbf;
+  }
+  for (const Batch &b : h->batches) {
+    launch_collocate(P, h->d_colloc + b.colloc_off, static_cast<int>(b.ncolloc), st);
+    cudaMemsetAsync(P.acc + static_cast<size_t>(b.tile0) * h->nspin * NACC * TILE_P, 0,
+                    static_cast<size_t>(b.ntiles) * h->nspin * NACC * TILE_P * sizeof(double), st);
+    launch_density(P, h->d_dens + b.dens_off, static_cast<int>(b.ndens), st);
+  }
+  launch_gather_rho(P, h->d_tile_src, h->npts_total, h->ntiles, d_out, st);
+  cudaMemcpyAsync(rho, d_out, nout * sizeof(double), cudaMemcpyDeviceToHost, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return fail(std::string("occ_xc_density_on_grid: ") + cudaGetErrorString(e));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int occ_xc_vv10(occ_xc_handle *h, const double *D2, const size_t *orig_index, double vv10_b, double vv10_C, double *K,
                 double *energy) {
   if (!h || !D2 || !K || !energy) return fail("occ_xc_vv10: null argument");
   if (h->nspin != 1)
     return fail("Only restricted NLC functional implemented right now"); // nonlocal_correlation.cpp:370-372
   if (h->deriv != 1) return fail("occ_xc_vv10: the handle must be created with a GGA functional list (rho and grad rho)");
-  if (h->npts != h->npts_total)
-    return fail("occ_xc_vv10: the handle must hold the whole NLC grid (world_size 1, no leaf dropped by screening)");
+  if (h->world != 1) return fail("occ_xc_vv10: the handle must hold the whole NLC grid (world_size 1)");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   BuildParams P = h->P;
   const size_t n = h->npts_total;
   const size_t ksz = static_cast<size_t>(h->nbf) * h->nbf;
+  if (ensure_tile_src(h)) return 1;
   if (!h->vv.X) { // first use: per-point arrays in the reference's order + the triangular work list
-    size_t *d_src = nullptr;
     double *buf = nullptr;
-    if (dev_alloc(h, &d_src, h->h_tile_src.size()) || dev_alloc(h, &buf, 9 * n) || dev_alloc(h, &h->d_vv_orig, n)) return 1;
-    CUDA_TRY(cudaMemcpy(d_src, h->h_tile_src.data(), h->h_tile_src.size() * sizeof(size_t), cudaMemcpyHostToDevice));
+    if (dev_alloc(h, &buf, 9 * n) || dev_alloc(h, &h->d_vv_orig, n)) return 1;
     h->vv.n = n;
-    h->vv.tile_src = d_src;
+    h->vv.tile_src = h->d_tile_src;
     h->vv.X = buf;
     h->vv.Y = buf + n;
     h->vv.Z = buf + 2 * n;

@@ -131,6 +131,7 @@ void launch_grad_gemm(const BuildParams &P, const DensItem *items, int nitems, v
 void launch_transpose(const double *D, double *DT, int nbf, int ld, void *stream);
 void launch_prepare_density(const double *D2, double *Dsym, int nbf, int nspin, void *stream);
 void launch_finalize(const BuildParams &P, int nleaves, double *K, double *scalars, void *stream);
+void launch_gather_rho(const BuildParams &P, const size_t *tile_src, size_t npts, int ntiles, double *out, void *stream);
 void launch_vv10_prepare(const BuildParams &P, const VV10Params &V, int ntiles, void *stream);
 void launch_vv10_pairs(const VV10Params &V, const int2 *items, int nitems, void *stream);
 void launch_vv10_coef(const BuildParams &P, const VV10Params &V, int nleaves, void *stream);

@@ -233,3 +233,35 @@ def partition_leaves(basis: AOBasis, leaves: np.ndarray, world_size: int, screen
                                         ptr(ext) if ext is not None else None, C.c_double(screening_threshold),
                                         C.c_int(world_size), ptr(rank), ptr(nb)))
     return rank, nb
+
+
+def evaluate_density_on_grid(basis: AOBasis, D: np.ndarray, grid_pts: np.ndarray, max_derivative: int = 0,
+                             spinorbital_kind: str = RESTRICTED, device: int = -1,
+                             screening_threshold: float = 0.0) -> np.ndarray:
+    """occ::density::evaluate_density_on_grid<max_derivative, kind>(basis, D, grid_pts) (include/occ/gto/density.h:67-107).
+    D is the matrix evaluate_density receives (callers pass 2 * mo.D, density.h:84-87); grid_pts (npts, 3) in Bohr.
+    Returns (nspin * npts, {1, 4, 6}) in the CALLER's point order: rho, grad rho, laplacian (not evaluated: 0), tau.
+    screening_threshold 0 = every shell at every point, like the reference's evaluate_basis."""
+    from .grid import MolecularGrid          # local import: grid.py imports this module
+    nspin = 2 if spinorbital_kind == UNRESTRICTED else 1
+    method = {0: "lda_x", 1: "gga_x_b88", 2: "mgga_x_tpss"}[int(max_derivative)]
+    pts = np.ascontiguousarray(grid_pts, dtype=np.float64).reshape(-1, 3)
+    mg = MolecularGrid.from_points(pts, np.ones(len(pts)))
+    h, perm = mg.hierarchy(with_permutation=True)
+    mg.close()
+    d = DFT(method, basis, h, spinorbital_kind, device=device, xc_screening_threshold=screening_threshold)
+    try:
+        ncol = {0: 1, 1: 4, 2: 6}[int(max_derivative)]
+        n = len(pts)
+        D2 = np.asfortranarray(D, dtype=np.float64)
+        if D2.shape != (nspin * basis.nbf, basis.nbf):
+            raise RuntimeError(f"density matrix has shape {D2.shape}, expected {(nspin * basis.nbf, basis.nbf)}")
+        out = np.zeros((nspin * n, ncol), order="F")
+        check(lib().occ_xc_density_on_grid(d._h, ptr(D2), ptr(out)))
+    finally:
+        d.close()
+    res = np.zeros_like(out)
+    idx = perm.astype(np.int64)
+    for s in range(nspin):
+        res[s * n + idx] = out[s * n:(s + 1) * n]
+    return res

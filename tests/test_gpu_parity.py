@@ -293,3 +293,40 @@ def test_baseline_configs_at_full_size_on_a_leaf_sample(oracle, mol, bas, method
     assert abs(d.exchange_correlation_energy() - ref["exc"]) < TOL_EXC
     assert abs(d.total_density[0] - ref["n_alpha"]) < 1e-8
     d.close()
+
+
+@pytest.mark.parametrize("nspin,deriv", [(1, 0), (1, 1), (1, 2), (2, 2)])
+def test_density_on_grid_matches_dense_numpy_evaluation(oracle, nspin, deriv):
+    """occ::density::evaluate_density_on_grid (include/occ/gto/density.h:67-107) for arbitrary caller points:
+    the CUDA collocation + DMMA density against evaluate_density (src/gto/density.cpp:8-166) written out in numpy
+    over the oracle's (gau2grid-pinned) collocation; 1e-10 absolute on rho ~ O(1)."""
+    Z, pos = molecules.MOLECULES["benzene"]()
+    b = aobasis.AOBasis.load(Z, pos, "def2-svp")
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(-6.0, 6.0, size=(1000, 3))
+    D = molecules.synthetic_density(b, nspin)
+    if nspin == 2:
+        D[:b.nbf] *= 1.3
+    got = dft.evaluate_density_on_grid(b, D, pts, deriv, dft.UNRESTRICTED if nspin == 2 else dft.RESTRICTED)
+    phi = [np.zeros((len(pts), b.nbf)) for _ in range(4)]
+    col = 0
+    for sh in b.shells:
+        fac = oracle.lib().orc_common_fac(int(sh.l), int(b.pure))
+        vals = oracle.collocate_shell(sh.l, int(b.pure), pts, sh.coefficients, sh.exponents, sh.origin, 1)
+        width = vals[0].shape[0]
+        for k in range(4):
+            phi[k][:, col:col + width] = vals[k].T * fac
+        col += width
+    n = len(pts)
+    for s in range(nspin):
+        Ds = D[s * b.nbf:(s + 1) * b.nbf]
+        Dr = np.triu(Ds) + np.triu(Ds, 1).T if nspin == 1 else Ds      # restricted reads the upper triangle
+        X = phi[0] @ Dr
+        assert np.abs((phi[0] * X).sum(1) - got[s * n:(s + 1) * n, 0]).max() < 1e-10
+        if deriv >= 1:
+            for k in range(3):
+                want = 2 * (phi[1 + k] * X).sum(1)          # density.cpp:38-43 (R) and :45-70 (U): 2 rowsum(phi_k o (phi D))
+                assert np.abs(want - got[s * n:(s + 1) * n, 1 + k]).max() < 1e-10
+        if deriv >= 2:
+            tau = 0.5 * sum((phi[1 + k] * (phi[1 + k] @ Ds)).sum(1) for k in range(3))
+            assert np.abs(tau - got[s * n:(s + 1) * n, 5]).max() < 1e-10
