@@ -8,6 +8,10 @@ The partition itself (contiguous Morton runs of equal predicted cost n*nb^2) liv
 """
 from __future__ import annotations
 
+import os
+import time
+from multiprocessing import resource_tracker, shared_memory
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -33,11 +37,54 @@ def unpack(buf: torch.Tensor, nspin: int, nbf: int):
     return K, buf[n:n + 3]
 
 
+def slice_len(nspin: int, nbf: int, world: int) -> int:
+    """length of one rank's slice of the packed buffer padded to a multiple of world (reduce-scatter granularity)"""
+    return -(-pack_len(nspin, nbf) // world)
+
+
+class SharedHostArray:
+    """A float64 (or int64) array in POSIX shared memory, mapped by every rank of the node and registered with CUDA as
+    pinned memory in each process: the HOST side of the multi-GPU build.  The reference's SCF is one host process that
+    owns D and K (include/occ/qm/scf_impl.h:504-572); here that process is rank 0 and the other ranks map the same
+    pages, so each GPU copies D over its OWN PCIe link and writes its slice of K back the same way — no GPU broadcast."""
+
+    def __init__(self, name: str, nelem: int, create: bool, dtype=np.float64, register: bool = True):
+        nbytes = max(1, nelem) * np.dtype(dtype).itemsize
+        self.shm = shared_memory.SharedMemory(name=name, create=create, size=nbytes)
+        if not create:   # the creating rank unlinks; keep this process's resource tracker out of it (Python < 3.13)
+            try:
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.owner = create
+        self.array = np.ndarray((nelem,), dtype=dtype, buffer=self.shm.buf)
+        self.tensor = torch.from_numpy(self.array)
+        self.registered = False
+        if register and torch.cuda.is_available():
+            rc = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), nbytes, 1)   # cudaHostRegisterPortable
+            if int(rc) != 0:
+                raise RuntimeError(f"cudaHostRegister failed with code {int(rc)}")
+            self.registered = True
+
+    def close(self):
+        if self.registered:
+            torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
+            self.registered = False
+        self.tensor = None
+        self.array = None
+        try:
+            self.shm.close()
+            if self.owner:
+                self.shm.unlink()
+        except Exception:
+            pass
+
+
 class DistributedDFT:
     """One DFT handle per rank on its own GPU; build() leaves the SUMMED packed result on every rank's device."""
 
     def __init__(self, method: str, basis, grid: GridHierarchy, spinorbital_kind: str = RESTRICTED, group=None,
-                 device: int | None = None, **kw):
+                 device: int | None = None, shared_host: bool = True, shared_tag: str = "0", **kw):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -52,6 +99,25 @@ class DistributedDFT:
         # a dedicated non-default stream: the C ABI reads a NULL stream as "the handle's own stream", so the legacy
         # default stream (value 0) can never be passed through it; copies, build and all-reduce all run here
         self.stream = torch.cuda.Stream(device=dev)
+        # ---- host side of the N > 1 end-to-end path: D, K and a few control words in node-shared pinned memory ----
+        self.host_D = self.host_K = self._ctl = None
+        self._epoch = 0
+        if self.world > 1 and shared_host:
+            n = self.nspin * self.nbf * self.nbf
+            self._slice = slice_len(self.nspin, self.nbf, self.world)
+            tag = f"occb200_{os.environ.get('MASTER_PORT', '0')}_{shared_tag}"
+            create = self.rank == 0
+            if not create:
+                dist.barrier(group)          # rank 0 has created the segments
+            self.host_D = SharedHostArray(tag + "_D", n, create)
+            self.host_K = SharedHostArray(tag + "_K", self._slice * self.world, create)
+            self._ctl = SharedHostArray(tag + "_c", 2 + self.world, create, dtype=np.int64, register=False)
+            if create:
+                self._ctl.array[:] = 0
+                dist.barrier(group)
+            dist.barrier(group)              # everyone has attached
+            self.d_red = torch.zeros(self._slice * self.world, dtype=torch.float64, device=dev)
+            self.d_slice = torch.zeros(self._slice, dtype=torch.float64, device=dev)
 
     def build_device(self) -> torch.Tensor:
         """D already in self.d_D (column-major). Enqueues build + all-reduce on self.stream; returns the packed
@@ -82,5 +148,43 @@ class DistributedDFT:
         self.stream.synchronize()
         return float(self._sc_host[0]), float(self._sc_host[1]), float(self._sc_host[2])
 
+    def _spin_until(self, index: int, value: int, timeout: float = 120.0):
+        a = self._ctl.array
+        t0 = time.perf_counter()
+        while a[index] < value:
+            if time.perf_counter() - t0 > timeout:
+                raise RuntimeError("DistributedDFT: a rank did not reach the shared-memory rendezvous")
+
+    def build_shared(self):
+        """Host-to-host build for N > 1 with the host matrices in node-shared pinned memory (self.host_D / self.host_K,
+        column-major, owned by rank 0's caller — the SCF process).  Every rank: H2D of D over its own PCIe link ->
+        sharded build -> NCCL reduce-scatter of the packed [K | exc, n_alpha, n_beta] -> D2H of its 1/N slice into
+        host_K.  Rank 0 publishes "D is ready" and collects "slice written" through control words in the same shared
+        segment (no collective on the host path).  Returns (exc, n_alpha, n_beta) on every rank."""
+        n = self.nspin * self.nbf * self.nbf
+        self._epoch += 1
+        ep = self._epoch
+        if self.rank == 0:
+            self._ctl.array[0] = ep                      # D in host_D is complete
+        else:
+            self._spin_until(0, ep)
+        with torch.cuda.stream(self.stream):
+            self.d_D.copy_(self.host_D.tensor, non_blocking=True)
+            self.dft.build_device(self.d_D.data_ptr(), self.d_red.data_ptr(), self.d_red.data_ptr() + 8 * n,
+                                  self.stream.cuda_stream)
+            dist.reduce_scatter_tensor(self.d_slice, self.d_red, op=dist.ReduceOp.SUM, group=self.group)
+            lo = self.rank * self._slice
+            self.host_K.tensor[lo:lo + self._slice].copy_(self.d_slice, non_blocking=True)
+        self.stream.synchronize()
+        self._ctl.array[2 + self.rank] = ep              # this rank's slice of K is in host memory
+        for r in range(self.world):
+            self._spin_until(2 + r, ep)
+        sc = self.host_K.array[n:n + 3]
+        return float(sc[0]), float(sc[1]), float(sc[2])
+
     def close(self):
+        for b in (self.host_D, self.host_K, self._ctl):
+            if b is not None:
+                b.close()
+        self.host_D = self.host_K = self._ctl = None
         self.dft.close()

@@ -56,3 +56,59 @@ def test_two_rank_gloo_sum_equals_unsharded_build():
         assert p.exitcode == 0
     assert n0 > 0 and n1 > 0
     assert dk < 1e-12 and de < 1e-12 and dna < 1e-12 and dnb < 1e-12
+
+
+def _shared_worker(rank, tag, q):
+    sys.path.insert(0, ROOT)
+    import time
+    from occ_b200 import parallel
+    n = 1000
+    if rank == 0:
+        d = parallel.SharedHostArray(tag + "_D", n, True)
+        c = parallel.SharedHostArray(tag + "_c", 4, True, dtype=np.int64, register=False)
+        c.array[:] = 0
+        d.array[:] = np.arange(n)
+        c.array[0] = 1                              # "D is ready"
+        t0 = time.time()
+        while c.array[3] < 1 and time.time() - t0 < 60:
+            pass
+        q.put(("r0", float(d.array[-1]), int(c.array[3])))
+        d.close()
+        c.close()
+    else:
+        t0 = time.time()
+        d = c = None
+        while time.time() - t0 < 60:                # rank 0 may not have created the segments yet
+            try:
+                c = parallel.SharedHostArray(tag + "_c", 4, False, dtype=np.int64, register=False)
+                d = parallel.SharedHostArray(tag + "_D", n, False)
+                break
+            except FileNotFoundError:
+                time.sleep(0.01)
+        while c.array[0] < 1 and time.time() - t0 < 60:
+            pass
+        s = float(d.array.sum())
+        d.array[-1] = -7.0                          # this rank's "slice of K"
+        c.array[3] = 1
+        q.put(("r1", s, 0))
+        d.close()
+        c.close()
+
+
+def test_shared_host_array_rendezvous_between_two_processes():
+    """the host side of DistributedDFT.build_shared: node-shared buffers + control words (no collective on the host path)"""
+    from occ_b200 import parallel
+    assert parallel.slice_len(1, 10, 8) * 8 >= parallel.pack_len(1, 10)
+    assert parallel.slice_len(2, 3348, 8) == -(-(2 * 3348 * 3348 + 4) // 8)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    tag = f"occb200_test_{os.getpid()}"
+    procs = [ctx.Process(target=_shared_worker, args=(r, tag, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict((k, (a, b)) for k, a, b in (q.get(timeout=120), q.get(timeout=120)))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got["r1"][0] == 999 * 1000 / 2            # rank 1 saw rank 0's D
+    assert got["r0"] == (-7.0, 1)                    # rank 0 saw rank 1's slice and its completion word
