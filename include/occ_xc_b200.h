@@ -104,6 +104,15 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
  * Synchronous: returns when K is on the host. */
 int occ_xc_build(occ_xc_handle *h, const double *D2, double *K, double *exc, double *n_alpha, double *n_beta);
 
+/* Host-memory helpers for callers without the CUDA headers.  occ_xc_build copies D2 and K with cudaMemcpyAsync: with
+ * PAGEABLE buffers (plain Eigen matrices) the driver stages every byte through its own bounce buffer (measured: +27 ms
+ * on a 211 ms valinomycin build for the two 90 MB matrices); with page-locked buffers the copies run at PCIe speed
+ * (+3 ms).  Either allocate the matrices' storage here and Eigen::Map it, or register existing storage once. */
+int occ_xc_pinned_alloc(size_t bytes, void **out);
+int occ_xc_pinned_free(void *p);
+int occ_xc_host_register(void *p, size_t bytes);   /* cudaHostRegister(portable); idempotent per pointer is NOT assumed */
+int occ_xc_host_unregister(void *p);
+
 /* Same with DEVICE buffers on `cuda_stream` (a cudaStream_t; NULL = the handle's own stream); asynchronous.
  * scalars_dev receives {exc, n_alpha, n_beta}.  D2_dev / K_dev as above but resident in HBM. */
 int occ_xc_build_device(occ_xc_handle *h, const double *D2_dev, double *K_dev, double *scalars_dev,

@@ -894,6 +894,25 @@ int occ_xc_vv10(occ_xc_handle *h, const double *D2, const size_t *orig_index, do
   return 0;
 }
 
+int occ_xc_pinned_alloc(size_t bytes, void **out) {
+  if (!out) return fail("occ_xc_pinned_alloc: null argument");
+  CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+  return 0;
+}
+int occ_xc_pinned_free(void *p) {
+  if (p) CUDA_TRY(cudaFreeHost(p));
+  return 0;
+}
+int occ_xc_host_register(void *p, size_t bytes) {
+  if (!p) return fail("occ_xc_host_register: null argument");
+  CUDA_TRY(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+  return 0;
+}
+int occ_xc_host_unregister(void *p) {
+  if (p) CUDA_TRY(cudaHostUnregister(p));
+  return 0;
+}
+
 int occ_xc_gradient(occ_xc_handle *h, const double *D2, double *gradient) {
   if (!h || !D2 || !gradient) return fail("occ_xc_gradient: null argument");
   if (!h->gradient) return fail("occ_xc_gradient: handle was created without the gradient option");
