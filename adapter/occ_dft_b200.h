@@ -79,16 +79,23 @@ public:
                         static_cast<int>(func_ids.size()), func_ids.data(), m_nspin, density_threshold,
                         xc_screening_threshold, &opt, &m_handle));
   }
-  ~XCBuild() { occ_xc_destroy(m_handle); }
+  ~XCBuild() {
+    occ_xc_pinned_free(m_D2);
+    occ_xc_destroy(m_handle);
+  }
   XCBuild(const XCBuild &) = delete;
   XCBuild &operator=(const XCBuild &) = delete;
 
   // D = mo.D ((nspin*nbf) x nbf column-major). Writes K (same shape). Doubles D like dft.h:205.
   void compute_K_dft(const double *D, double *K) {
     const size_t n = static_cast<size_t>(m_nspin) * m_nbf * m_nbf;
-    m_D2.resize(n);
+    if (!m_D2) { // the doubled copy lives in page-locked memory: its H2D then runs at PCIe speed
+      void *p = nullptr;
+      check(occ_xc_pinned_alloc(n * sizeof(double), &p));
+      m_D2 = static_cast<double *>(p);
+    }
     for (size_t i = 0; i < n; ++i) m_D2[i] = 2 * D[i];
-    check(occ_xc_build(m_handle, m_D2.data(), K, &m_exc_dft, &m_total_density_a, &m_total_density_b));
+    check(occ_xc_build(m_handle, m_D2, K, &m_exc_dft, &m_total_density_a, &m_total_density_b));
   }
   double exchange_correlation_energy() const { return m_exc_dft; }
   double total_density_alpha() const { return m_total_density_a; }
@@ -109,7 +116,7 @@ private:
   occ_xc_handle *m_handle = nullptr;
   int m_nspin, m_nbf;
   double m_exc_dft = 0.0, m_total_density_a = 0.0, m_total_density_b = 0.0;
-  std::vector<double> m_D2;
+  double *m_D2 = nullptr;
 };
 
 } // namespace occ_b200
