@@ -54,6 +54,14 @@ def benzene():
     return np.array(Z, dtype=np.int32), np.array(pos) * ANGSTROM_TO_BOHR
 
 
+def thionyl_chloride_like():
+    """SOCl2-like test molecule with second-row atoms (Z > 10: the third alpha set of the NWChem pruning and the larger
+    Bragg radii, src/numint/grid_utils.cpp:22-41,234-274), plus a sodium to reach the s/p-only Z = 11 row"""
+    Z = np.array([16, 8, 17, 17, 11], dtype=np.int32)
+    pos = np.array([[0.0, 0.0, 0.0], [0.0, 0.0, 1.44], [1.62, 0.0, -0.95], [-0.81, 1.40, -0.95], [-2.6, -2.3, 0.4]])
+    return Z, pos * ANGSTROM_TO_BOHR
+
+
 def _random_rotation(rng):
     q = rng.normal(size=4)
     q /= np.linalg.norm(q)
@@ -144,7 +152,7 @@ def taxol():
     return read_xyz(os.path.join(GEOM_DIR, "taxol_standin.xyz"))
 
 
-MOLECULES = {"water": water, "water_isolated": water_isolated_xc, "benzene": benzene, "h2o_32": water_cluster_32,
+MOLECULES = {"socl2_na": thionyl_chloride_like, "water": water, "water_isolated": water_isolated_xc, "benzene": benzene, "h2o_32": water_cluster_32,
              "valinomycin": valinomycin, "taxol": taxol}
 
 

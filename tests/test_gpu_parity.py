@@ -54,6 +54,8 @@ def test_water_every_functional_restricted_and_unrestricted(case, oracle, method
     ("benzene", "def2-tzvp", "pbe", 1, False),     # BASELINE configs[1]
     ("benzene", "def2-tzvp", "r2scan", 2, True),
     ("water_isolated", "3-21g", "blyp", 1, True),
+    ("socl2_na", "def2-svp", "pbe", 2, False),     # second-row atoms: Z > 10 pruning thresholds, Na/S/Cl Bragg radii
+    ("socl2_na", "def2-tzvp", "tpss", 1, True),
 ])
 def test_molecule_matrix(case, oracle, mol, bas, method, nspin, pure):
     res, ref = _build_both(case(mol, bas, pure), method, nspin, oracle)
@@ -142,7 +144,7 @@ def test_collocation_against_oracle_and_reference_gau2grid(case, oracle):
 
 def test_product_grid_producer_matches_oracle(case):
     """occ_b200.grid (host C++ + CUDA Becke kernel) vs the oracle's restatement of MolecularGrid / SpatialGridHierarchy"""
-    for mol, bas in (("water", "def2-svp"), ("benzene", "def2-tzvp")):
+    for mol, bas in (("water", "def2-svp"), ("benzene", "def2-tzvp"), ("socl2_na", "def2-svp")):
         c = case(mol, bas)
         mg = grid.MolecularGrid(c["basis"])
         pts, w = mg.points()

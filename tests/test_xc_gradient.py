@@ -79,7 +79,8 @@ def test_oracle_gradient_is_the_derivative_of_exc_for_a_frozen_density_matrix(or
     ("water", "def2-svp", "pbe", 1, False), ("water", "def2-svp", "b3lyp", 2, True),
     ("water", "def2-svp", "r2scan", 1, False), ("water", "def2-svp", "r2scan", 2, True),
     ("water", "def2-qzvp", "blyp", 1, True), ("benzene", "def2-tzvp", "pbe", 1, False),
-    ("benzene", "def2-tzvp", "r2scan", 2, True),
+    ("benzene", "def2-tzvp", "r2scan", 2, True), ("socl2_na", "def2-svp", "tpss", 2, False),
+    ("water", "def2-svp", "tpss", 1, False),
 ])
 def test_cuda_gradient_matches_oracle(case, oracle, mol, bas, method, nspin, pure):
     from occ_b200 import dft
