@@ -290,8 +290,14 @@ __global__ void __launch_bounds__(TILE_P) k_gbuild(BuildParams P, const DensItem
 #define XC_RS 2
 #endif
 constexpr int RK = XC_RK, RS = XC_RS;
-constexpr int R_LDA = RK + 4;          // = 4 (mod 8): conflict-free (groupID, threadInGroup) fragment loads
-constexpr int R_LDB = TILE_P + 4;
+#ifndef XC_SWZ
+#define XC_SWZ 0
+#endif
+// XC_SWZ = 0: padded rows (ld = 4 mod 16).  XC_SWZ = 1: dense rows, element (row, k) stored at k ^ ((row & 3) << 2): the
+// same conflict-free fragment pattern without padding, which makes room for a third stage of the A rings.
+constexpr int R_LDA = XC_SWZ ? RK : RK + 4;
+constexpr int R_LDB = XC_SWZ ? TILE_P : TILE_P + 4;
+#define R_SW(row) (XC_SWZ ? (((row) & 3) << 2) : 0)
 constexpr int R_WROWS = GM / 8;        // rows of a row block owned by one warp
 constexpr int R_ASZ = R_WROWS * R_LDA, R_BSZ = GN * R_LDB;
 constexpr int R_SMEM_DOUBLES = R_BSZ + 8 * RS * R_ASZ + GN / 2; // + 64 ints: global column of each output column
@@ -327,7 +333,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_vxc_resident(BuildParams P, con
       const int seg = lane + 32 * r;
       const int row = seg / SPR, s2 = (seg % SPR) * 2;
       const int i = ib * GM + warp * R_WROWS + row;
-      cp_async16(As + row * R_LDA + s2, Ag + static_cast<size_t>(i < nbp ? i : 0) * TILE_P + kc * RK + s2, i < nbp);
+      cp_async16(As + row * R_LDA + (s2 ^ R_SW(row)), Ag + static_cast<size_t>(i < nbp ? i : 0) * TILE_P + kc * RK + s2,
+                 i < nbp);
     }
   };
   // the A rings start filling while the B block is being built
@@ -341,25 +348,27 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_vxc_resident(BuildParams P, con
     const int p = tid & (TILE_P - 1), half = tid >> 7;
     const double *cf = P.coef + (static_cast<size_t>(it.tile) * P.nspin + it.spin) * NCOEF * TILE_P + p;
     const double *q0 = base + static_cast<size_t>(n0 + half * 32) * TILE_P + p;
-    double *dst = Bres + (half * 32) * R_LDB + p;
-    if (it.acomp == 0) {
+    double *dst = Bres + (half * 32) * R_LDB;
+    if (P.debug & 16) { // timing experiment: B block without the slab loads
+      for (int j = 0; j < 32; ++j) dst[j * R_LDB + (p ^ R_SW(j))] = 1e-3 * j;
+    } else if (it.acomp == 0) {
       const double c0 = cf[0];
       if (P.deriv >= 1) {
         const double cx = cf[TILE_P], cy = cf[2 * TILE_P], cz = cf[3 * TILE_P];
 #pragma unroll 8
         for (int j = 0; j < 32; ++j) {
           const double *q = q0 + j * TILE_P;
-          dst[j * R_LDB] = c0 * q[0] + cx * q[slab] + cy * q[2 * slab] + cz * q[3 * slab];
+          dst[j * R_LDB + (p ^ R_SW(j))] = c0 * q[0] + cx * q[slab] + cy * q[2 * slab] + cz * q[3 * slab];
         }
       } else {
 #pragma unroll 8
-        for (int j = 0; j < 32; ++j) dst[j * R_LDB] = c0 * q0[j * TILE_P];
+        for (int j = 0; j < 32; ++j) dst[j * R_LDB + (p ^ R_SW(j))] = c0 * q0[j * TILE_P];
       }
     } else {
       const double ct = cf[4 * TILE_P];
       const double *qk = q0 + static_cast<size_t>(it.acomp) * slab;
 #pragma unroll 8
-      for (int j = 0; j < 32; ++j) dst[j * R_LDB] = ct * qk[j * TILE_P];
+      for (int j = 0; j < 32; ++j) dst[j * R_LDB + (p ^ R_SW(j))] = ct * qk[j * TILE_P];
     }
     if (tid < GN) scol[tid] = n0 + tid < nb ? __ldg(gidx + n0 + tid) : -1;
   }
@@ -371,6 +380,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_vxc_resident(BuildParams P, con
   int mi_valid = 0;
   int grow[2] = {0, 0};
   const double *Bw = Bres + gid * R_LDB + tig;
+  const int g3 = gid & 3; // every row / column index this thread touches is = gid (mod 8): one swizzle term
   for (int q = 0; q < nq; ++q) {
     if (kc == 0) {
       mi_valid = min(2, max(0, (nb - (ib * GM + warp * R_WROWS) + 7) >> 3));
@@ -393,12 +403,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_vxc_resident(BuildParams P, con
 #pragma unroll
       for (int k4 = 0; k4 < RK / 4; ++k4) {
         double a[2], b[8];
+        const int ko = XC_SWZ ? ((k4 ^ g3) << 2) : k4 * 4;
 #pragma unroll
-        for (int mi = 0; mi < 2; ++mi) a[mi] = As[mi * 8 * R_LDA + k4 * 4];
+        for (int mi = 0; mi < 2; ++mi) a[mi] = As[mi * 8 * R_LDA + ko];
 #pragma unroll
-        for (int ni = 0; ni < 8; ++ni) b[ni] = Bs[ni * 8 * R_LDB + k4 * 4];
+        for (int ni = 0; ni < 8; ++ni) b[ni] = Bs[ni * 8 * R_LDB + ko];
         if (k4 == 0) { // refill as soon as the first fragments are in flight
-          if (q + RS - 1 < nq) load_stage(q + RS - 1, (q + RS - 1) % RS);
+          if (q + RS - 1 < nq && !(P.debug & 8)) load_stage(q + RS - 1, (q + RS - 1) % RS);
           cp_async_commit();
         }
 #pragma unroll
@@ -413,12 +424,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_vxc_resident(BuildParams P, con
 #pragma unroll
         for (int k4 = 0; k4 < RK / 4; ++k4) {
           double a[2];
+          const int ko = XC_SWZ ? ((k4 ^ g3) << 2) : k4 * 4;
 #pragma unroll
-          for (int mi = 0; mi < 2; ++mi) a[mi] = As[mi * 8 * R_LDA + k4 * 4];
+          for (int mi = 0; mi < 2; ++mi) a[mi] = As[mi * 8 * R_LDA + ko];
 #pragma unroll
           for (int ni = 0; ni < 8; ++ni)
             if (ni < ni_valid) {
-              const double b = Bs[ni * 8 * R_LDB + k4 * 4];
+              const double b = Bs[ni * 8 * R_LDB + ko];
 #pragma unroll
               for (int mi = 0; mi < 2; ++mi)
                 if (mi < mi_valid) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b);

@@ -5,9 +5,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 code = r'''
 import sys; sys.path.insert(0, %r)
 from scripts.gpu_experiments import run
-run("valinomycin", "def2-tzvp", "b3lyp", 1, 4096)
-run("benzene", "def2-tzvp", "pbe", 1, 2048)
-run("h2o_32", "def2-svp", "b3lyp", 2, 4096)
+run("valinomycin", "def2-tzvp", "b3lyp", 1, 4096, lanes=1)
+run("taxol", "def2-tzvp", "r2scan", 1, 4096, lanes=1)
+run("h2o_32", "def2-svp", "b3lyp", 2, 4096, lanes=1)
 ''' % ROOT
 libs = [None] + sorted(os.path.join(ROOT, "occ_b200", "variants", f) for f in os.listdir(os.path.join(ROOT, "occ_b200", "variants")))
 for lib in libs:
