@@ -5,13 +5,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 code = r'''
 import sys; sys.path.insert(0, %r)
 from scripts.gpu_experiments import run
-run("valinomycin", "def2-tzvp", "b3lyp", 1, 4096, lanes=1)
-run("taxol", "def2-tzvp", "r2scan", 1, 4096, lanes=1)
-run("h2o_32", "def2-svp", "b3lyp", 2, 4096, lanes=1)
+run("valinomycin", "def2-tzvp", "b3lyp", 1, 4096, lanes=1, reps=1)
+run("h2o_32", "def2-svp", "b3lyp", 2, 4096, lanes=1, reps=1)
 ''' % ROOT
-libs = [None] + sorted(os.path.join(ROOT, "occ_b200", "variants", f) for f in os.listdir(os.path.join(ROOT, "occ_b200", "variants")))
+vdir = os.path.join(ROOT, "occ_b200", "variants")
+libs = [None] + sorted(os.path.join(vdir, f) for f in os.listdir(vdir))
 for lib in libs:
     env = dict(os.environ)
     if lib: env["OCC_XC_B200_LIB"] = lib
-    print("=== variant", lib or "default (GK16, 3 stages)", flush=True)
+    print("=== variant", lib or "default", flush=True)
     subprocess.run([sys.executable, "-c", code], env=env)

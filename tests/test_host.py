@@ -123,3 +123,16 @@ def test_device_functionals_on_host_match_oracle_and_reference_kat(oracle):
             keys = ["exc", "vrho"] + (["vsigma"] if fam >= 1 else []) + (["vtau"] if fam >= 2 else [])
             for k in keys:
                 assert np.allclose(got[k], want[k], rtol=1e-10, atol=1e-13), (name, k)
+
+
+def test_device_functionals_on_host_hydrogen_atom_constraints():
+    """the same published hydrogen-atom values / exact constraints as tests/test_oracle_pins.py, evaluated with the
+    PRODUCT's device functionals (polarized branch) compiled for the host"""
+    from test_oracle_pins import HYDROGEN, hydrogen_atom_quadrature
+    rho, sigma, tau, qw = hydrogen_atom_quadrature()
+    keep = rho[:, 0] > 1e-14                      # below the functionals' density threshold nothing is evaluated
+    for func, (want, tol) in HYDROGEN.items():
+        fid = dft.FUNCTIONAL_IDS[func]
+        fam = 0 if func.startswith("lda") else (1 if func.startswith("gga") else 2)
+        o = _device_functional_on_host(fid, True, fam, rho[keep], sigma[keep], tau[keep])
+        assert abs(float((o["exc"] * qw[keep]).sum()) - want) < max(tol, 1e-9), func
