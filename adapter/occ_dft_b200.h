@@ -80,6 +80,7 @@ public:
                         xc_screening_threshold, &opt, &m_handle));
   }
   ~XCBuild() {
+    occ_xc_pinned_free(m_K);
     occ_xc_pinned_free(m_D2);
     occ_xc_destroy(m_handle);
   }
@@ -96,6 +97,19 @@ public:
     }
     for (size_t i = 0; i < n; ++i) m_D2[i] = 2 * D[i];
     check(occ_xc_build(m_handle, m_D2, K, &m_exc_dft, &m_total_density_a, &m_total_density_b));
+  }
+  // Same, but K stays in a page-locked buffer owned by this object (valid until the next call): the caller maps it
+  // (Eigen::Map<const Mat>(ptr, nspin * nbf, nbf)) — the reference negates / copies K anyway (dft.h:435) — so neither
+  // matrix crosses PCIe through pageable memory.
+  const double *compute_K_dft(const double *D) {
+    const size_t n = static_cast<size_t>(m_nspin) * m_nbf * m_nbf;
+    if (!m_K) {
+      void *p = nullptr;
+      check(occ_xc_pinned_alloc(n * sizeof(double), &p));
+      m_K = static_cast<double *>(p);
+    }
+    compute_K_dft(D, m_K);
+    return m_K;
   }
   double exchange_correlation_energy() const { return m_exc_dft; }
   double total_density_alpha() const { return m_total_density_a; }
@@ -116,7 +130,7 @@ private:
   occ_xc_handle *m_handle = nullptr;
   int m_nspin, m_nbf;
   double m_exc_dft = 0.0, m_total_density_a = 0.0, m_total_density_b = 0.0;
-  double *m_D2 = nullptr;
+  double *m_D2 = nullptr, *m_K = nullptr;
 };
 
 } // namespace occ_b200

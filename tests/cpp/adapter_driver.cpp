@@ -2,6 +2,7 @@
 // XCBuild::compute_K_dft through the C ABI and writes K, Exc, N back.  With --expect-error it checks that a
 // failure inside the library surfaces as std::runtime_error (the reference's error convention).
 #include "../../adapter/occ_dft_b200.h"
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -46,6 +47,12 @@ int main(int argc, char **argv) {
                          nspin == 2 ? occ_b200::SpinorbitalKind::Unrestricted : occ_b200::SpinorbitalKind::Restricted);
     std::vector<double> K(D.size());
     xc.compute_K_dft(D.data(), K.data());
+    const double *Kp = xc.compute_K_dft(D.data());   // page-locked variant must give the same matrix
+    for (size_t i = 0; i < K.size(); ++i)
+      if (std::fabs(Kp[i] - K[i]) > 1e-12) {
+        std::printf("pinned K differs at %zu\n", i);
+        return 1;
+      }
     std::ofstream o(argv[2], std::ios::binary);
     const double sc[3] = {xc.exchange_correlation_energy(), xc.total_density_alpha(), xc.total_density_beta()};
     o.write(reinterpret_cast<const char *>(sc), sizeof(sc));
