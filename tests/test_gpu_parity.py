@@ -332,3 +332,20 @@ def test_density_on_grid_matches_dense_numpy_evaluation(oracle, nspin, deriv):
         if deriv >= 2:
             tau = 0.5 * sum((phi[1 + k] * (phi[1 + k] @ Ds)).sum(1) for k in range(3))
             assert np.abs(tau - got[s * n:(s + 1) * n, 5]).max() < 1e-10
+
+
+def test_density_on_grid_far_points_and_screening():
+    """points far outside every shell's extent: with per-leaf screening (1e-10) their leaves keep no shell and are
+    dropped like dft.h:309-321 (rows stay exactly 0); near points agree with the unscreened evaluation to 1e-9"""
+    Z, pos = molecules.MOLECULES["water"]()
+    b = aobasis.AOBasis.load(Z, pos, "def2-svp")
+    rng = np.random.default_rng(9)
+    near = rng.uniform(-4.0, 4.0, size=(700, 3))
+    far = rng.uniform(-4.0, 4.0, size=(300, 3)) + np.array([400.0, 0.0, 0.0])
+    pts = np.concatenate([near, far])
+    D = molecules.synthetic_density(b, 1)
+    dense = dft.evaluate_density_on_grid(b, D, pts, 1)
+    scr = dft.evaluate_density_on_grid(b, D, pts, 1, screening_threshold=1e-10)
+    assert np.abs(dense[:700] - scr[:700]).max() < 1e-9
+    assert np.abs(scr[700:]).max() == 0.0 and np.abs(dense[700:]).max() < 1e-30
+    assert dense[:700, 0].max() > 0.1

@@ -132,3 +132,31 @@ def test_cuda_vv10_errors():
         check.check(check.lib().occ_xc_vv10(d._h, check.ptr(np.zeros((nbf, nbf))), None, C.c_double(6.0),
                                             C.c_double(0.01), check.ptr(K), C.byref(e)))
     d.close()
+
+
+@pytest.mark.gpu
+def test_cuda_vv10_identity_order_and_low_density_points(oracle):
+    """orig_index = NULL means 'the handle's own point order is the reference order'; points below the 1e-8 density cut
+    (here: a shell of far-away points appended to the grid) neither receive nor contribute"""
+    import ctypes as C
+    from occ_b200 import dft, grid
+    from occ_b200._lib import check, lib, ptr
+    Z, pos = molecules.water()
+    b = aobasis.AOBasis.load(Z, pos, "def2-svp")
+    ob = oracle.Basis(b.as_arrays())
+    mg = grid.MolecularGrid(b, grid.GridSettings(**NLC_GRID))
+    pts, w = mg.points()
+    rng = np.random.default_rng(3)
+    far = rng.normal(size=(256, 3))
+    far = 40.0 * far / np.linalg.norm(far, axis=1)[:, None]
+    pts2, w2 = np.concatenate([pts, far]), np.concatenate([w, np.full(256, 0.5)])
+    h = grid.MolecularGrid.from_points(pts2, w2).hierarchy()
+    D2 = molecules.synthetic_density(b, 1)
+    d = dft.DFT("gga_x_b88", b, h, xc_screening_threshold=0.0)
+    K = np.zeros((b.nbf, b.nbf), order="F")
+    e = C.c_double()
+    check(lib().occ_xc_vv10(d._h, ptr(np.asfortranarray(D2)), None, C.c_double(6.0), C.c_double(0.01), ptr(K), C.byref(e)))
+    d.close()
+    r = oracle.vv10(ob, h.sorted_points, h.sorted_weights, D2)      # same (sorted) order on both sides
+    assert (r["rho"][:, 0] < 1e-8).sum() >= 256
+    assert abs(e.value - r["energy"]) < 1e-8 and np.abs(K - r["K"]).max() < 1e-9
