@@ -136,3 +136,16 @@ def test_device_functionals_on_host_hydrogen_atom_constraints():
         fam = 0 if func.startswith("lda") else (1 if func.startswith("gga") else 2)
         o = _device_functional_on_host(fid, True, fam, rho[keep], sigma[keep], tau[keep])
         assert abs(float((o["exc"] * qw[keep]).sum()) - want) < max(tol, 1e-9), func
+
+
+def test_device_functionals_on_host_lithium_atom():
+    """partial spin polarization (0 < zeta < 1): the product's device functionals on the UHF lithium density against
+    the published energies of tests/test_oracle_pins.py (PBE Table I, Becke 88, LYP)"""
+    from test_oracle_pins import ATOMS, atom_quadrature
+    res, rho, sigma, tau, vol = atom_quadrature("Li")
+    keep = rho.sum(1) > 1e-14
+    for func, want in ATOMS["Li"][3].items():
+        fam = 0 if func.startswith("lda") else 1
+        o = _device_functional_on_host(dft.FUNCTIONAL_IDS[func], True, fam, rho[keep], sigma[keep], tau[keep])
+        got = float((o["exc"] * rho.sum(1)[keep] * vol[keep]).sum())
+        assert abs(got - want) < 1.5e-4, (func, got, want)

@@ -313,3 +313,40 @@ def test_unpolarized_lda_correlation_fits_agree_with_ceperley_alder(oracle):
     # VWN3 == VWN5 at zeta = 0; the RPA fit lies below both (RPA overcorrelates)
     assert np.abs(oracle.xc_eval("lda_c_vwn_3", False, rho)["exc"] - vwn).max() < 1e-14
     assert (oracle.xc_eval("lda_c_vwn_rpa", False, rho)["exc"] < vwn - 0.01).all()
+
+
+# ---------------------------------------------------------------- published atomic energies (He, Li, Be)
+# Table I of Perdew, Burke, Ernzerhof, PRL 77, 3865 (1996) (LSD = Slater + PW92, PBE), Becke, PRA 38, 3098 (1988) (B88)
+# and Lee, Yang, Parr / Miehlich et al. (LYP), all on Hartree-Fock densities.  Lithium is spin-polarized with
+# 0 < zeta < 1 in the valence region: it pins the zeta interpolation of PW92 and phi(zeta) of PBE correlation, the
+# spin-scaling of the exchange functionals and the open-shell LYP form — none of which any reference test covers.
+ATOMS = {
+    "He": (2, 1, 1, {"lda_x": -0.8840, "gga_x_pbe": -1.0136, "lda_c_pw_mod": -0.1125, "gga_c_pbe": -0.0420,
+                     "gga_x_b88": -1.0255, "gga_c_lyp": -0.0438}),
+    "Li": (3, 2, 1, {"lda_x": -1.5379, "gga_x_pbe": -1.7572, "lda_c_pw_mod": -0.1508, "gga_c_pbe": -0.0514,
+                     "gga_x_b88": -1.7753, "gga_c_lyp": -0.0534}),
+    "Be": (4, 2, 2, {"lda_x": -2.3124, "gga_x_pbe": -2.6358, "lda_c_pw_mod": -0.2240, "gga_c_pbe": -0.0856,
+                     "gga_x_b88": -2.6578, "gga_c_lyp": -0.0946}),
+}
+
+
+def atom_quadrature(name):
+    import atoms_uhf
+    Z, na, nb, _ = ATOMS[name]
+    res = atoms_uhf.uhf(Z, na, nb)
+    x, wq = np.polynomial.legendre.leggauss(600)
+    r, w = (1 + x) / (1 - x), wq * 2 / (1 - x) ** 2
+    rho, sigma, tau = atoms_uhf.radial_densities(res, r)
+    return res, rho, sigma, tau, 4 * np.pi * r ** 2 * w
+
+
+@pytest.mark.parametrize("atom", sorted(ATOMS))
+def test_published_atomic_exchange_and_correlation_energies(oracle, atom):
+    res, rho, sigma, tau, vol = atom_quadrature(atom)
+    hf_limit = {"He": -2.86168, "Li": -7.43273, "Be": -14.57302}[atom]
+    assert abs(res["energy"] - hf_limit) < 5e-5                     # the helper's own density is at the HF limit
+    assert abs(float((rho.sum(1) * vol).sum()) - ATOMS[atom][0]) < 1e-9
+    for func, want in ATOMS[atom][3].items():
+        o = oracle.xc_eval(func, True, rho, sigma, tau)
+        got = float((o["exc"] * rho.sum(1) * vol).sum())
+        assert abs(got - want) < 1.5e-4, (atom, func, got, want)
