@@ -145,7 +145,7 @@ def test_device_functionals_on_host_lithium_atom():
     res, rho, sigma, tau, vol = atom_quadrature("Li")
     keep = rho.sum(1) > 1e-14
     for func, want in ATOMS["Li"][3].items():
-        fam = 0 if func.startswith("lda") else 1
+        fam = 0 if func.startswith("lda") else (1 if func.startswith("gga") else 2)
         o = _device_functional_on_host(dft.FUNCTIONAL_IDS[func], True, fam, rho[keep], sigma[keep], tau[keep])
         got = float((o["exc"] * rho.sum(1)[keep] * vol[keep]).sum())
         assert abs(got - want) < 1.5e-4, (func, got, want)

@@ -317,16 +317,17 @@ def test_unpolarized_lda_correlation_fits_agree_with_ceperley_alder(oracle):
 
 # ---------------------------------------------------------------- published atomic energies (He, Li, Be)
 # Table I of Perdew, Burke, Ernzerhof, PRL 77, 3865 (1996) (LSD = Slater + PW92, PBE), Becke, PRA 38, 3098 (1988) (B88)
-# and Lee, Yang, Parr / Miehlich et al. (LYP), all on Hartree-Fock densities.  Lithium is spin-polarized with
+# Lee, Yang, Parr / Miehlich et al. (LYP) and Table II of Tao, Perdew, Staroverov, Scuseria, PRL 91, 146401 (2003)
+# (TPSS correlation: its zeta / xi dependent C(zeta, xi) is exercised by lithium), all on Hartree-Fock densities.  Lithium is spin-polarized with
 # 0 < zeta < 1 in the valence region: it pins the zeta interpolation of PW92 and phi(zeta) of PBE correlation, the
 # spin-scaling of the exchange functionals and the open-shell LYP form — none of which any reference test covers.
 ATOMS = {
     "He": (2, 1, 1, {"lda_x": -0.8840, "gga_x_pbe": -1.0136, "lda_c_pw_mod": -0.1125, "gga_c_pbe": -0.0420,
-                     "gga_x_b88": -1.0255, "gga_c_lyp": -0.0438}),
+                     "gga_x_b88": -1.0255, "gga_c_lyp": -0.0438, "mgga_c_tpss": -0.0430}),
     "Li": (3, 2, 1, {"lda_x": -1.5379, "gga_x_pbe": -1.7572, "lda_c_pw_mod": -0.1508, "gga_c_pbe": -0.0514,
-                     "gga_x_b88": -1.7753, "gga_c_lyp": -0.0534}),
+                     "gga_x_b88": -1.7753, "gga_c_lyp": -0.0534, "mgga_c_tpss": -0.0493}),
     "Be": (4, 2, 2, {"lda_x": -2.3124, "gga_x_pbe": -2.6358, "lda_c_pw_mod": -0.2240, "gga_c_pbe": -0.0856,
-                     "gga_x_b88": -2.6578, "gga_c_lyp": -0.0946}),
+                     "gga_x_b88": -2.6578, "gga_c_lyp": -0.0946, "mgga_c_tpss": -0.0869}),
 }
 
 
