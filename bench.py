@@ -234,7 +234,8 @@ def run_b200(args):
     # N = 1: pinned host D -> H2D -> build -> D2H K.  N > 1: the host matrices live in node-shared pinned memory owned
     # by rank 0 (the SCF process); every rank copies D over its own PCIe link, the packed result is reduce-scattered over
     # NVLink and every rank writes its 1/N slice of K back to the host buffer (occ_b200/parallel.py: build_shared).
-    if world > 1:
+    shared = world > 1 and ddft.host_D is not None     # False when /dev/shm cannot hold the two matrices
+    if shared:
         if rank == 0:
             ddft.host_D.tensor.copy_(hD)
 
@@ -242,19 +243,19 @@ def run_b200(args):
             ddft.build_shared()
     else:
         def step_e2e():
-            ddft.build(hD, hK)
+            ddft.build(hD if rank == 0 else None, hK if rank == 0 else None)
 
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    exc, na, nb_ = ddft.build_shared() if world > 1 else ddft.build(hD, hK)
-    if world > 1 and rank == 0:     # the shared-memory path must reproduce the broadcast / all-reduce path
+    exc, na, nb_ = ddft.build_shared() if shared else ddft.build(hD, hK)
+    if shared and rank == 0:        # the shared-memory path must reproduce the broadcast / all-reduce path
         exc_b, na_b, nb_b = ddft.build(hD, hK)
         kdiff = float((ddft.host_K.tensor[:n] - hK).abs().max())
         if not (kdiff < 1e-9 and abs(exc - exc_b) < 1e-8):
             raise RuntimeError(f"shared-host e2e path disagrees with the all-reduce path: dK={kdiff} dExc={abs(exc - exc_b)}")
-    elif world > 1:
+    elif shared:
         ddft.build(None, None)
 
     # ---- per-kernel times of this rank's shard (CUDA events on the build stream, profiled pass) ----
@@ -326,8 +327,10 @@ def run_b200(args):
             "phases_ms": phases,
             "cpu_baseline": cpu,
             "e2e": {"value": npts_total / (ms_e2e * 1e-3), "unit": "grid-points/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": 8 * n * world, "d2h_bytes_per_step": 8 * n + 32 * world,
+                    "h2d_bytes_per_step": 8 * n * (world if shared else 1), "d2h_bytes_per_step": 8 * n + 32 * world,
                     "path": ("pinned host D -> H2D -> build -> D2H of K and the 3 scalars" if world == 1 else
+                             "rank 0: pinned host D -> H2D; NCCL broadcast of D; sharded build; NCCL all-reduce of [K|Exc,Na,Nb]; "
+                             "rank 0: D2H of K (no room in /dev/shm for the shared-host path)" if not shared else
                              "host D / K in node-shared pinned memory owned by rank 0; every rank: H2D of D over its own "
                              "PCIe link; sharded build; NCCL reduce-scatter of [K|Exc,Na,Nb]; every rank: D2H of its 1/N "
                              "slice into the host K")},

@@ -105,6 +105,18 @@ class DistributedDFT:
         if self.world > 1 and shared_host:
             n = self.nspin * self.nbf * self.nbf
             self._slice = slice_len(self.nspin, self.nbf, self.world)
+            # /dev/shm must hold both matrices (a container may cap it at 64 MB; writing past the cap is a SIGBUS, not an
+            # exception): rank 0 checks, every rank takes rank 0's verdict; without room the broadcast path stays
+            need = 8 * (n + self._slice * self.world) + (1 << 20)
+            try:
+                st = os.statvfs("/dev/shm")
+                ok = st.f_bavail * st.f_frsize >= need
+            except OSError:
+                ok = False
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.broadcast(flag, src=0, group=group)
+            shared_host = bool(int(flag.item()))
+        if self.world > 1 and shared_host:
             tag = f"occb200_{os.environ.get('MASTER_PORT', '0')}_{shared_tag}"
             create = self.rank == 0
             if not create:
