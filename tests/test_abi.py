@@ -65,3 +65,15 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower().replace("# oracle", ""), os.path.join(dirpath, f)
+
+
+def test_header_is_plain_c_and_links_from_c99():
+    """include/occ_xc_b200.h compiled by gcc -std=c99 -pedantic and linked against the library: the boundary is a C ABI"""
+    import subprocess
+    src = os.path.join(ROOT, "tests", "cpp", "abi_c99.c")
+    exe = os.path.join(ROOT, "tests", "cpp", "abi_c99")
+    lib = os.path.join(ROOT, "occ_b200")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-o", exe, src, "-L" + lib,
+                           "-locc_xc_b200", "-Wl,-rpath," + lib])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", (out.returncode, out.stdout, out.stderr)

@@ -349,3 +349,44 @@ def test_density_on_grid_far_points_and_screening():
     assert np.abs(dense[:700] - scr[:700]).max() < 1e-9
     assert np.abs(scr[700:]).max() == 0.0 and np.abs(dense[700:]).max() < 1e-30
     assert dense[:700, 0].max() > 0.1
+
+
+def test_handle_lifecycle_interleaving_and_threads(case):
+    """SURVEY 8(b) ownership / threading: handles are independent (two methods interleaved on one device, and two host
+    threads each driving its own handle give the single-handle results); create / destroy cycles do not leak device
+    memory"""
+    import threading
+    import torch
+    c = case("benzene", "def2-tzvp")
+    b = c["basis"]
+    h = dft.GridHierarchy(c["spts"], c["sw"], c["leaves"])
+    D1, D2u = molecules.synthetic_density(b, 1), molecules.synthetic_density(b, 2)
+    d1, d2 = dft.DFT("pbe", b, h), dft.DFT("tpss", b, h, dft.UNRESTRICTED)
+    K1 = d1.build(D1).copy()
+    K2 = d2.build(D2u).copy()
+    for _ in range(3):                                   # interleaved use of two live handles
+        assert np.abs(d2.build(D2u) - K2).max() < 1e-12
+        assert np.abs(d1.build(D1) - K1).max() < 1e-12
+    out = {}
+
+    def worker(name, d, D, n):
+        for _ in range(n):
+            out[name] = d.build(D).copy()
+
+    ts = [threading.Thread(target=worker, args=("a", d1, D1, 5)), threading.Thread(target=worker, args=("b", d2, D2u, 3))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert np.abs(out["a"] - K1).max() < 1e-12 and np.abs(out["b"] - K2).max() < 1e-12
+    d1.close()
+    d2.close()
+    free = []
+    for cycle in range(6):       # cycle 0 pays the one-time costs (lazy module load, local-memory pool of the driver)
+        d = dft.DFT("b3lyp", b, h, gradient=True)
+        d.build(D1)
+        d.gradient(D1)
+        d.close()
+        torch.cuda.synchronize()
+        free.append(torch.cuda.mem_get_info()[0])
+    assert abs(free[-1] - free[0]) < (8 << 20), free      # nothing of the workspaces is left behind per cycle
