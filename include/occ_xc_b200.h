@@ -76,7 +76,9 @@ typedef struct {
                             caller sums (NCCL all-reduce).  world_size <= 1: whole grid. */
   size_t batch_bytes;    /* AO-value workspace per batch of leaves (0 = default 4 GiB) */
   int reserved[8];       /* [0] developer timing switches, [1] 2 = second stream lane, [2] 1 = handle can also run
-                            occ_xc_gradient (needs basis->shell_atom, l <= 4; larger workspace) */
+                            occ_xc_gradient (needs basis->shell_atom, l <= 4; larger workspace), [3] / [4] number of
+                            occupied alpha / beta orbitals: enables occ_xc_build_mo (adds one 128 x nocc slab per
+                            spin to every tile's workspace); [4] = 0 with nspin = 2 means "same as alpha" */
 } occ_xc_options_t;
 
 typedef struct occ_xc_handle occ_xc_handle;
@@ -103,6 +105,20 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
  *   exc, n_alpha, n_beta   m_exc_dft and the two total densities (dft.h:375-385)
  * Synchronous: returns when K is on the host. */
 int occ_xc_build(occ_xc_handle *h, const double *D2, double *K, double *exc, double *n_alpha, double *n_beta);
+
+/* The same build for callers that also hand over the occupied orbitals (the reference's seam receives `mo`, which holds
+ * both mo.D and mo.Cocc, include/occ/qm/mo.h): D2_s = C_s C_s^T with C_s = sqrt(2) Cocc (restricted; the occupation
+ * square roots folded into the columns in general).  Same K, Exc and electron counts as occ_xc_build up to the
+ * rounding of C C^T, but the density phase runs in the factorised form  psi = phi C, X = psi C^T  (4 n nb nocc flops
+ * instead of 2 n nb^2; tau: 6 n nb nocc instead of 6 n nb^2) wherever that is cheaper for a leaf — about 40 % less
+ * tensor work in the density phase of valinomycin/def2-TZVP, 4x less in the tau phase of a meta-GGA.
+ *   D2  as in occ_xc_build (still used for leaves with few basis functions)
+ *   C   nspin blocks, block s is nbf x nocc_s column-major (ld = nbf); the beta block follows the alpha block
+ * The handle must have been created with options.reserved[3] (and [4]) = the occupied counts. */
+int occ_xc_build_mo(occ_xc_handle *h, const double *D2, const double *C, double *K, double *exc, double *n_alpha,
+                    double *n_beta);
+int occ_xc_build_mo_device(occ_xc_handle *h, const double *D2_dev, const double *C_dev, double *K_dev,
+                           double *scalars_dev, void *cuda_stream);
 
 /* Host-memory helpers for callers without the CUDA headers.  occ_xc_build copies D2 and K with cudaMemcpyAsync: with
  * PAGEABLE buffers (plain Eigen matrices) the driver stages every byte through its own bounce buffer (measured: +27 ms
@@ -157,6 +173,8 @@ typedef struct {
   int nb_min, nb_max;
   size_t workspace_bytes;    /* device memory held by the handle */
   size_t launches_per_build; /* kernel launches one build issues */
+  double mo_density_flops;   /* tensor flops the density phase of occ_xc_build_mo really issues (0 without MO mode);
+                                the D-form density phase issues flops_per_build / 2 */
 } occ_xc_info_t;
 int occ_xc_get_info(const occ_xc_handle *h, occ_xc_info_t *info);
 

@@ -64,18 +64,33 @@ __device__ __forceinline__ void red_add_f64(double *addr, double v) {
 // the companion slabs (H_s,d / phi_d / S_s,de), sums over the 128 points and scatters per atom:
 //   grad[A][d] += f * sum_p sum_{mu in A} companion_d[p, mu] * acc[p, mu]
 // which is  -2 sum_{mu in A, nu} D_{mu nu} V_d(mu, nu)  of dft_gradient_kernels.cpp:540-592 without ever forming V_d.
+// MODE 2 / 3: the factorised ("MO") form of the density for callers that also hand over the occupied orbitals
+// (D2_s = C_s C_s^T; the reference's seam receives `mo`, which carries both):
+//   MODE 2   psi_a = phi_a . C_loc   (128 x nocc, K = nb; B gathered along k through the leaf's index list)
+//            a = 0: stored to the tile's psi slab;  a = 1..3 (meta-GGA): epilogue sum_i psi_a,i^2 = the tau row sums
+//   MODE 3   X = psi . C_loc^T       (128 x nb, K = nocc; B gathered along n), then the row-dot epilogue of MODE 0
+// 4 n nb nocc flops instead of 2 n nb^2 for rho / grad rho, 6 n nb nocc instead of 6 n nb^2 for tau; the host picks
+// the form per leaf and spin (nb > 2 nocc, resp. nb > nocc).  Same numbers as MODE 0 up to the rounding of C C^T.
 template <int MODE> __device__ __forceinline__ void gemm_xd_body(const BuildParams &P, const DensItem it, double *smem) {
   const TileDesc t = P.tiles[it.tile];
   if (MODE == 1 && P.leaf_skip[t.leaf]) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;
   const int wm = warp & 3, wn = warp >> 2;
-  const int nb = t.nb;
-  const int nk = (nb + GK - 1) / GK;
+  const int nbK = MODE == 3 ? P.mo_nocc[it.spin] : t.nb;   // valid extent of the contraction index
+  const int nbKp = MODE == 3 ? P.mo_noccp : t.nbp;         // columns the A slab really has
+  const int nb = MODE == 2 ? P.mo_nocc[it.spin] : t.nb;    // valid extent of the output columns
+  const int nk = (nbK + GK - 1) / GK;
   const size_t slab = static_cast<size_t>(t.nbp) * TILE_P;
-  const int a_slab = MODE == 0 ? it.acomp : (it.acomp == 0 ? 0 : (it.acomp == 1 ? P.slab_G + it.spin : it.acomp - 1));
-  const double *Ag = P.scratch + t.scr_off + static_cast<size_t>(a_slab) * slab;
-  const double *Dm = MODE == 0 ? (it.acomp == 0 ? P.Drho : P.Dtau)[it.spin] : P.DT[it.spin];
+  const size_t psi_slab = static_cast<size_t>(P.mo_noccp) * TILE_P;
+  const int a_slab = (MODE == 0 || MODE == 2)
+                         ? it.acomp
+                         : (it.acomp == 0 ? 0 : (it.acomp == 1 ? P.slab_G + it.spin : it.acomp - 1));
+  const double *Ag = MODE == 3 ? P.scratch + t.psi_off + static_cast<size_t>(it.spin) * psi_slab
+                               : P.scratch + t.scr_off + static_cast<size_t>(a_slab) * slab;
+  const double *Dm = MODE == 0 ? (it.acomp == 0 ? P.Drho : P.Dtau)[it.spin]
+                               : (MODE == 1 ? P.DT[it.spin] : (MODE == 2 ? P.moC[it.spin] : P.moCT[it.spin]));
+  const int ldB = MODE == 2 ? P.ldC : (MODE == 3 ? P.ldCT : P.ldD);
   const int *gidx = P.bf_index + t.bf_off;
   const int n0 = it.jb * GN;
 
@@ -89,7 +104,7 @@ template <int MODE> __device__ __forceinline__ void gemm_xd_body(const BuildPara
   for (int r = 0; r < NBR; ++r) {
     const int n = n0 + nn + NROWT * r;
     nvalid[r] = n < nb;
-    coloff[r] = nvalid[r] ? static_cast<size_t>(__ldg(gidx + n)) * P.ldD : 0;
+    coloff[r] = nvalid[r] ? static_cast<size_t>(MODE == 2 ? n : __ldg(gidx + n)) * ldB : 0;
   }
   // 8-column groups of this warp's 32 columns that hold real basis functions (the rest is padding: no DMMA)
   const int ni_valid = min(4, max(0, (nb - (n0 + wn * 32) + 7) >> 3));
@@ -102,16 +117,19 @@ template <int MODE> __device__ __forceinline__ void gemm_xd_body(const BuildPara
     for (int r = 0; r < GK * 64 / NTHREADS; ++r) {
       const int seg = tid + NTHREADS * r;
       const int col = seg >> 6, s2 = (seg & 63) * 2;
-      cp_async16(As + col * D_LDA + s2, Ag + static_cast<size_t>(kc * GK + col) * TILE_P + s2, kc * GK + col < t.nbp);
+      cp_async16(As + col * D_LDA + s2, Ag + static_cast<size_t>(kc * GK + col) * TILE_P + s2, kc * GK + col < nbKp);
     }
     // grow_next = global row of k = kc*GK + kk, fetched one iteration ahead so the gather never waits on it
-    const bool kvalid = kc * GK + kk < nb;
+    const bool kvalid = kc * GK + kk < nbK;
     const int grow = grow_next;
 #pragma unroll
     for (int r = 0; r < NBR; ++r)
       cp_async8(Bs + (nn + NROWT * r) * D_LDB + kk, Dm + coloff[r] + grow, kvalid && nvalid[r]);
   };
-  auto fetch_row = [&](int kc) { grow_next = (kc * GK + kk < nb) ? __ldg(gidx + kc * GK + kk) : 0; };
+  auto fetch_row = [&](int kc) {
+    const int k = kc * GK + kk;
+    grow_next = k < nbK ? (MODE == 3 ? k : __ldg(gidx + k)) : 0;
+  };
 
   double acc[4][4][2];
 #pragma unroll
@@ -176,6 +194,31 @@ template <int MODE> __device__ __forceinline__ void gemm_xd_body(const BuildPara
   }
   cp_async_wait<0>();
 
+  if (MODE == 2) {
+    if (it.acomp == 0) { // psi tile -> the tile's psi slab (padding columns carry exact zeros)
+      double *ps = P.scratch + t.psi_off + static_cast<size_t>(it.spin) * psi_slab +
+                   static_cast<size_t>(n0 + wn * 32 + 2 * tig) * TILE_P + wm * 32 + gid;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+          ps[(ni * 8) * TILE_P + mi * 8] = acc[mi][ni][0];
+          ps[(ni * 8 + 1) * TILE_P + mi * 8] = acc[mi][ni][1];
+        }
+    } else { // tau: sum_k sum_i (phi_k C)_i^2 accumulates in row 4 (the functional kernel applies the 1/2)
+      double *accp = P.acc + (static_cast<size_t>(it.tile) * P.nspin + it.spin) * NACC * TILE_P + 4 * TILE_P;
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        double sq = 0.0;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) sq += acc[mi][ni][0] * acc[mi][ni][0] + acc[mi][ni][1] * acc[mi][ni][1];
+        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+        if (tig == 0) red_add_f64(accp + wm * 32 + mi * 8 + gid, sq);
+      }
+    }
+    return;
+  }
   if (MODE == 1) {
     // gradient epilogue
     const double *cbase = P.scratch + t.scr_off + static_cast<size_t>(n0 + wn * 32 + 2 * tig) * TILE_P + wm * 32 + gid;
@@ -238,6 +281,14 @@ template <int MODE> __device__ __forceinline__ void gemm_xd_body(const BuildPara
 __global__ void __launch_bounds__(NTHREADS, 2) k_density(BuildParams P, const DensItem *__restrict__ items) {
   extern __shared__ __align__(16) double smem[];
   gemm_xd_body<0>(P, items[blockIdx.x], smem);
+}
+__global__ void __launch_bounds__(NTHREADS, 2) k_mo_psi(BuildParams P, const DensItem *__restrict__ items) {
+  extern __shared__ __align__(16) double smem[];
+  gemm_xd_body<2>(P, items[blockIdx.x], smem);
+}
+__global__ void __launch_bounds__(NTHREADS, 2) k_mo_density(BuildParams P, const DensItem *__restrict__ items) {
+  extern __shared__ __align__(16) double smem[];
+  gemm_xd_body<3>(P, items[blockIdx.x], smem);
 }
 __global__ void __launch_bounds__(NTHREADS, 2) k_xc_gradient(BuildParams P, const DensItem *__restrict__ items) {
   extern __shared__ __align__(16) double smem[];
@@ -480,6 +531,48 @@ void launch_density(const BuildParams &P, const DensItem *items, int nitems, voi
     configured = true;
   }
   k_density<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
+}
+
+void launch_mo_psi(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
+  if (nitems <= 0) return;
+  static bool configured = false;
+  const int smem_bytes = GSTAGES * D_STAGE * sizeof(double);
+  if (!configured) {
+    cudaFuncSetAttribute(k_mo_psi, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    configured = true;
+  }
+  k_mo_psi<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
+}
+void launch_mo_density(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
+  if (nitems <= 0) return;
+  static bool configured = false;
+  const int smem_bytes = GSTAGES * D_STAGE * sizeof(double);
+  if (!configured) {
+    cudaFuncSetAttribute(k_mo_density, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    configured = true;
+  }
+  k_mo_density<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
+}
+
+// rectangular transpose: out (ncol x nrow, ld_out) = in (nrow x ncol, ld_in)^T, column-major
+__global__ void k_transpose_rect(const double *__restrict__ in, double *__restrict__ out, int nrow, int ncol, int ld_in,
+                                 int ld_out) {
+  __shared__ double tl[32][33];
+  const int bi = blockIdx.x * 32, bj = blockIdx.y * 32, tx = threadIdx.x, ty = threadIdx.y;
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi + tx, j = bj + r;
+    tl[r][tx] = (i < nrow && j < ncol) ? in[static_cast<size_t>(j) * ld_in + i] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int j = bj + tx, i = bi + r; // out(j, i) = in(i, j)
+    if (i < nrow && j < ncol) out[static_cast<size_t>(i) * ld_out + j] = tl[tx][r];
+  }
+}
+void launch_transpose_rect(const double *in, double *out, int nrow, int ncol, int ld_in, int ld_out, void *stream) {
+  if (nrow <= 0 || ncol <= 0) return;
+  dim3 grid((nrow + 31) / 32, (ncol + 31) / 32);
+  k_transpose_rect<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(in, out, nrow, ncol, ld_in, ld_out);
 }
 
 void launch_grad_gemm(const BuildParams &P, const DensItem *items, int nitems, void *stream) {

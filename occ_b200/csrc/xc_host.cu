@@ -181,6 +181,7 @@ static std::vector<size_t> partition_by_cost(const std::vector<double> &costs, i
 struct Batch {
   int tile0, ntiles, leaf0, nleaves;
   size_t colloc_off, ncolloc, dens_off, ndens, g_off, ng, vxc_off, nvxc, grad_off, ngrad;
+  size_t densmo_off, ndensmo, psi_off, npsi, xpsi_off, nxpsi; // MO-form density work lists
 };
 
 struct occ_xc_handle {
@@ -212,6 +213,12 @@ struct occ_xc_handle {
   bool profiling = false;
   double phase_ms[OCC_XC_NPHASES] = {0, 0, 0, 0, 0, 0, 0};
   size_t launches = 0;
+  // MO-form density (options.reserved[3..4] = occupied-orbital counts at create)
+  bool mo = false;
+  int nocc[2] = {0, 0}, noccp = 0;
+  DensItem *d_densmo = nullptr, *d_psi = nullptr, *d_xpsi = nullptr;
+  double *d_C = nullptr, *d_CT = nullptr;
+  double mo_executed_flops = 0.0; // DMMA flops one MO-form build really issues (density side)
   // post-SCF VV10 (allocated on first use)
   std::vector<size_t> h_tile_src; // sorted index of the first point of each tile
   size_t npts_total = 0;          // points of the caller's whole grid (orig_index range)
@@ -426,6 +433,17 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
   const int nslab = h->ncomp + (want_grad ? nspin : 0) + (want_grad && deriv >= 1 ? 3 * nspin : 0) +
                     (want_grad && deriv >= 2 ? 6 * nspin : 0);
   std::vector<int> bf_atom;
+  if (opt && opt->reserved[3] > 0) {
+    h->mo = true;
+    h->nocc[0] = opt->reserved[3];
+    h->nocc[1] = nspin == 2 ? (opt->reserved[4] > 0 ? opt->reserved[4] : opt->reserved[3]) : 0;
+    if (h->nocc[0] > nbf || h->nocc[1] > nbf) {
+      delete h;
+      return fail("occ_xc_create: more occupied orbitals than basis functions");
+    }
+    h->noccp = (std::max(h->nocc[0], h->nocc[1]) + NB_PAD - 1) / NB_PAD * NB_PAD;
+  }
+  const size_t psi_doubles = h->mo ? static_cast<size_t>(nspin) * h->noccp * TILE_P : 0; // per tile
 
   // ---- tiles, padded points, per-leaf index lists ----
   std::vector<double> px, py, pz, pw;
@@ -491,7 +509,7 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
 
   // ---- batches of consecutive leaves under the workspace budget; per-phase work lists ----
   std::vector<CollocItem> colloc;
-  std::vector<DensItem> dens, gitems, gradit;
+  std::vector<DensItem> dens, gitems, gradit, densmo, psi, xpsi;
   std::vector<VxcItem> vxc;
   size_t max_scratch = 0;
   {
@@ -504,11 +522,14 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
       int nl = 0, nt = 0;
       while (leaf + nl < h->nleaves) {
         const LeafDesc &ld = h->h_leaves[leaf + nl];
-        const size_t need = static_cast<size_t>(ld.ntiles) * nslab * h->h_tiles[ld.tile0].nbp * TILE_P;
+        const size_t need =
+            static_cast<size_t>(ld.ntiles) * (static_cast<size_t>(nslab) * h->h_tiles[ld.tile0].nbp * TILE_P + psi_doubles);
         if (nl > 0 && (used + need) * sizeof(double) > batch_bytes) break;
         for (int k = 0; k < ld.ntiles; ++k) {
           h->h_tiles[ld.tile0 + k].scr_off = static_cast<long long>(used);
           used += static_cast<size_t>(nslab) * h->h_tiles[ld.tile0 + k].nbp * TILE_P;
+          h->h_tiles[ld.tile0 + k].psi_off = static_cast<long long>(used);
+          used += psi_doubles;
         }
         nt += ld.ntiles;
         ++nl;
@@ -526,6 +547,9 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
       b.g_off = gitems.size();
       b.vxc_off = vxc.size();
       b.grad_off = gradit.size();
+      b.densmo_off = densmo.size();
+      b.psi_off = psi.size();
+      b.xpsi_off = xpsi.size();
       for (int ti : order) {
         const TileDesc &t = h->h_tiles[ti];
         for (int s0 = 0; s0 < t.nsh; s0 += 16) {
@@ -554,6 +578,41 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
               vi.acomp = static_cast<signed char>(ac);
               vxc.push_back(vi);
             }
+        if (h->mo) {
+          // per tile and spin: rho / grad rho in the factorised form when 4 n nb nocc < 2 n nb^2, tau when nocc < nb
+          const int npsib = h->noccp / 64;
+          for (int sp = 0; sp < nspin; ++sp) {
+            const int no = h->nocc[sp];
+            auto push = [&](std::vector<DensItem> &list, int nblocks, int ac) {
+              for (int jb = 0; jb < nblocks; ++jb) {
+                DensItem di;
+                di.tile = ti;
+                di.jb = static_cast<short>(jb);
+                di.spin = static_cast<signed char>(sp);
+                di.acomp = static_cast<signed char>(ac);
+                list.push_back(di);
+              }
+            };
+            const double n_pts = t.count;
+            if (t.nb > 2 * no) {
+              push(psi, npsib, 0);
+              push(xpsi, njb, 0);
+              h->mo_executed_flops += 4.0 * n_pts * t.nb * no;
+            } else {
+              push(densmo, njb, 0);
+              h->mo_executed_flops += 2.0 * n_pts * t.nb * t.nb;
+            }
+            for (int ac = 1; ac < nac; ++ac) {
+              if (t.nb > no) {
+                push(psi, npsib, ac);
+                h->mo_executed_flops += 2.0 * n_pts * t.nb * no;
+              } else {
+                push(densmo, njb, ac);
+                h->mo_executed_flops += 2.0 * n_pts * t.nb * t.nb;
+              }
+            }
+          }
+        }
         if (want_grad) {
           // acomp: 0 A = phi (companions H), 1 A = G (companions grad phi), 2..4 A = phi_e (companions S), see k_gemm.cu
           const int w0 = deriv == 0 ? 1 : 0, w1 = deriv == 0 ? 1 : (deriv == 1 ? 1 : 4);
@@ -582,6 +641,9 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
       b.ng = gitems.size() - b.g_off;
       b.nvxc = vxc.size() - b.vxc_off;
       b.ngrad = gradit.size() - b.grad_off;
+      b.ndensmo = densmo.size() - b.densmo_off;
+      b.npsi = psi.size() - b.psi_off;
+      b.nxpsi = xpsi.size() - b.xpsi_off;
       h->batches.push_back(b);
       leaf += nl;
     }
@@ -624,6 +686,17 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
     rc |= dev_upload(h, &dg, gitems);
     rc |= dev_upload(h, &dv, vxc);
     rc |= dev_upload(h, &dgr, gradit);
+    if (h->mo) {
+      const DensItem *d1 = nullptr, *d2 = nullptr, *d3 = nullptr;
+      rc |= dev_upload(h, &d1, densmo);
+      rc |= dev_upload(h, &d2, psi);
+      rc |= dev_upload(h, &d3, xpsi);
+      h->d_densmo = const_cast<DensItem *>(d1);
+      h->d_psi = const_cast<DensItem *>(d2);
+      h->d_xpsi = const_cast<DensItem *>(d3);
+      rc |= dev_alloc(h, &h->d_C, static_cast<size_t>(nbf) * (h->nocc[0] + h->nocc[1]));
+      rc |= dev_alloc(h, &h->d_CT, static_cast<size_t>(nspin) * h->noccp * nbf);
+    }
     h->d_gradit = const_cast<DensItem *>(dgr);
     h->d_colloc = const_cast<CollocItem *>(dc);
     h->d_dens = const_cast<DensItem *>(dd);
@@ -669,6 +742,14 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
   P.grad = h->d_grad;
   P.grad_factor = deriv == 0 ? -4.0 : -2.0;
   P.debug = opt ? opt->reserved[0] : 0;
+  P.ldC = nbf;
+  P.ldCT = h->noccp;
+  P.mo_noccp = h->noccp;
+  for (int sp = 0; sp < 2; ++sp) {
+    P.mo_nocc[sp] = h->nocc[sp];
+    P.moC[sp] = h->d_C ? h->d_C + static_cast<size_t>(sp) * nbf * h->nocc[0] : nullptr;
+    P.moCT[sp] = h->d_CT ? h->d_CT + static_cast<size_t>(sp) * h->noccp * nbf : nullptr;
+  }
   for (int s = 0; s < nspin; ++s) P.Ktmp[s] = h->d_Ktmp + static_cast<size_t>(s) * nbf;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -690,9 +771,24 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
   return 0;
 }
 
+static int build_device_impl(occ_xc_handle *h, const double *D2_dev, const double *C_dev, double *K_dev,
+                             double *scalars_dev, void *cuda_stream);
+
 int occ_xc_build_device(occ_xc_handle *h, const double *D2_dev, double *K_dev, double *scalars_dev,
                         void *cuda_stream) {
   if (!h || !D2_dev || !K_dev || !scalars_dev) return fail("occ_xc_build_device: null argument");
+  return build_device_impl(h, D2_dev, nullptr, K_dev, scalars_dev, cuda_stream);
+}
+
+int occ_xc_build_mo_device(occ_xc_handle *h, const double *D2_dev, const double *C_dev, double *K_dev,
+                           double *scalars_dev, void *cuda_stream) {
+  if (!h || !D2_dev || !C_dev || !K_dev || !scalars_dev) return fail("occ_xc_build_mo_device: null argument");
+  if (!h->mo) return fail("occ_xc_build_mo_device: the handle was created without occupied-orbital counts");
+  return build_device_impl(h, D2_dev, C_dev, K_dev, scalars_dev, cuda_stream);
+}
+
+static int build_device_impl(occ_xc_handle *h, const double *D2_dev, const double *C_dev, double *K_dev,
+                             double *scalars_dev, void *cuda_stream) {
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
   BuildParams P = h->P;
@@ -718,6 +814,15 @@ int occ_xc_build_device(occ_xc_handle *h, const double *D2_dev, double *K_dev, d
     for (int s = 0; s < 2; ++s) P.Drho[s] = P.Dtau[s] = D2_dev + static_cast<size_t>(s) * h->nbf;
   }
   CUDA_TRY(cudaMemsetAsync(h->d_Ktmp, 0, ksz * sizeof(double), st));
+  const bool mo = C_dev != nullptr;
+  if (mo) { // C_s^T once per build: the X = psi C^T contraction gathers whole rows of it
+    for (int sp = 0; sp < h->nspin; ++sp) {
+      const double *Cs = C_dev + static_cast<size_t>(sp) * h->nbf * h->nocc[0];
+      P.moC[sp] = Cs;
+      launch_transpose_rect(Cs, h->d_CT + static_cast<size_t>(sp) * h->noccp * h->nbf, h->nbf, h->nocc[sp], h->nbf,
+                            h->noccp, st);
+    }
+  }
   PHASE_END(0);
   // Two lanes: batches alternate between the caller's stream and an auxiliary stream, each lane with its own AO
   // workspace.  The HBM-bound phases of one lane (collocation, G slab) and the tails of its DMMA kernels then overlap
@@ -739,7 +844,13 @@ int occ_xc_build_device(occ_xc_handle *h, const double *D2_dev, double *K_dev, d
     PHASE_BEGIN();
     CUDA_TRY(cudaMemsetAsync(P.acc + static_cast<size_t>(b.tile0) * h->nspin * NACC * TILE_P, 0,
                              static_cast<size_t>(b.ntiles) * h->nspin * NACC * TILE_P * sizeof(double), st));
-    launch_density(P, h->d_dens + b.dens_off, static_cast<int>(b.ndens), st);
+    if (mo) {
+      launch_mo_psi(P, h->d_psi + b.psi_off, static_cast<int>(b.npsi), st);
+      launch_density(P, h->d_densmo + b.densmo_off, static_cast<int>(b.ndensmo), st);
+      launch_mo_density(P, h->d_xpsi + b.xpsi_off, static_cast<int>(b.nxpsi), st);
+    } else {
+      launch_density(P, h->d_dens + b.dens_off, static_cast<int>(b.ndens), st);
+    }
     PHASE_END(2);
     PHASE_BEGIN();
     launch_functional(P, b.leaf0, b.nleaves, st);
@@ -894,6 +1005,26 @@ int occ_xc_vv10(occ_xc_handle *h, const double *D2, const size_t *orig_index, do
   return 0;
 }
 
+int occ_xc_build_mo(occ_xc_handle *h, const double *D2, const double *C, double *K, double *exc, double *n_alpha,
+                    double *n_beta) {
+  if (!h || !D2 || !C || !K) return fail("occ_xc_build_mo: null argument");
+  if (!h->mo) return fail("occ_xc_build_mo: the handle was created without occupied-orbital counts");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t ksz = static_cast<size_t>(h->nspin) * h->nbf * h->nbf;
+  const size_t csz = static_cast<size_t>(h->nbf) * (h->nocc[0] + h->nocc[1]);
+  CUDA_TRY(cudaMemcpyAsync(h->d_D, D2, ksz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_C, C, csz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (build_device_impl(h, h->d_D, h->d_C, h->d_K, h->d_scalars, h->stream)) return 1;
+  CUDA_TRY(cudaMemcpyAsync(K, h->d_K, ksz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  double sc[3];
+  CUDA_TRY(cudaMemcpyAsync(sc, h->d_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (exc) *exc = sc[0];
+  if (n_alpha) *n_alpha = sc[1];
+  if (n_beta) *n_beta = sc[2];
+  return 0;
+}
+
 int occ_xc_pinned_alloc(size_t bytes, void **out) {
   if (!out) return fail("occ_xc_pinned_alloc: null argument");
   CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
@@ -966,6 +1097,7 @@ int occ_xc_get_info(const occ_xc_handle *h, occ_xc_info_t *info) {
   info->nb_max = h->nb_max;
   info->workspace_bytes = h->alloc_bytes;
   info->launches_per_build = h->launches;
+  info->mo_density_flops = h->mo_executed_flops;
   return 0;
 }
 

@@ -27,6 +27,7 @@ struct TileDesc {
   int bf_off;        // offset of the leaf's local->global bf map in bf_index[]
   int sh_off, nsh;   // the leaf's significant shells in shell_list[] / shell_col[]
   long long scr_off; // offset (doubles) of phi_0 in the batch workspace; phi_c at scr_off + c * nbp * 128
+  long long psi_off; // offset of the tile's psi slabs (MO-form density): psi_s at psi_off + s * noccp * 128
 };
 
 struct LeafDesc {
@@ -99,6 +100,12 @@ struct BuildParams {
   int slab_H;            // first H slab: H[s][d] at slab_H + 3 s + d      (GGA / meta-GGA)
   int slab_S;            // first S slab: S[s][de] at slab_S + 6 s + de    (meta-GGA), de in xx,xy,xz,yy,yz,zz order
   double grad_factor;    // -2, or -4 for LDA (dft_gradient_kernels.cpp:27-45 carries no 1/2 on vrho)
+  // ---- MO-form density (handles created with the occupied-orbital counts) ----
+  const double *moC[2];  // C_s: nbf x nocc_s column-major (ld = ldC), D2_s = C_s C_s^T
+  const double *moCT[2]; // C_s^T: nocc_s x nbf column-major (ld = ldCT)
+  int ldC, ldCT;
+  int mo_nocc[2];
+  int mo_noccp;          // psi slab width: max nocc rounded up to 64
   int debug; // developer switches for timing experiments (options.reserved[0]): 1 = no Vxc scatter, 2 = no density epilogue
 };
 
@@ -127,6 +134,9 @@ void launch_functional(const BuildParams &P, int leaf0, int nleaves, void *strea
 void launch_vxc_resident(const BuildParams &P, const VxcItem *items, int nitems, void *stream);
 void launch_gbuild(const BuildParams &P, const DensItem *items, int nitems, void *stream);
 void launch_collocate_h(const BuildParams &P, const CollocItem *items, int nitems, void *stream);
+void launch_mo_psi(const BuildParams &P, const DensItem *items, int nitems, void *stream);
+void launch_mo_density(const BuildParams &P, const DensItem *items, int nitems, void *stream);
+void launch_transpose_rect(const double *in, double *out, int nrow, int ncol, int ld_in, int ld_out, void *stream);
 void launch_grad_gemm(const BuildParams &P, const DensItem *items, int nitems, void *stream);
 void launch_transpose(const double *D, double *DT, int nbf, int ld, void *stream);
 void launch_prepare_density(const double *D2, double *Dsym, int nbf, int nspin, void *stream);

@@ -12,6 +12,7 @@ buffers / streams in the device-resident entry (build_device) and torch.distribu
 from __future__ import annotations
 
 import ctypes as C
+import ctypes as C_
 from dataclasses import dataclass
 
 import numpy as np
@@ -83,7 +84,7 @@ class DFT:
     def __init__(self, method: str, basis: AOBasis, grid: GridHierarchy, spinorbital_kind: str = RESTRICTED,
                  device: int = -1, rank: int = 0, world_size: int = 1, batch_bytes: int = 0,
                  density_threshold: float = 1e-10, xc_screening_threshold: float = 1e-10, shell_extents=None,
-                 debug: int = 0, lanes: int = 1, gradient: bool = False):
+                 debug: int = 0, lanes: int = 1, gradient: bool = False, nocc=None):
         self.basis = basis
         self.method = method
         self.func_ids = np.array(get_dft_method(method), dtype=np.int32)
@@ -98,6 +99,11 @@ class DFT:
         opt.reserved[0] = debug
         opt.reserved[1] = lanes
         opt.reserved[2] = int(gradient)
+        self.nocc = None
+        if nocc is not None:        # enables build_mo: occupied-orbital counts (alpha[, beta])
+            na, nb_ = (nocc, nocc) if np.isscalar(nocc) else (nocc[0], nocc[-1])
+            opt.reserved[3], opt.reserved[4] = int(na), int(nb_)
+            self.nocc = (int(na), int(nb_))
         self._h = C.c_void_p()
         check(lib().occ_xc_create(self._basis_arrays.ref, C.c_size_t(len(w)), ptr(pts), ptr(w), C.c_size_t(len(leaves)),
                                   ptr(leaves), ptr(ext) if ext is not None else None, C.c_int(len(self.func_ids)),
@@ -142,6 +148,30 @@ class DFT:
         self.m_exc_dft = exc.value
         self.total_density = (na.value, nb.value)
         return K
+
+    def build_mo(self, D2: np.ndarray, C, out: np.ndarray | None = None) -> np.ndarray:
+        """occ_xc_build_mo: D2 as in build(); C = list of nspin matrices (nbf x nocc_s) with D2_s = C_s C_s^T
+        (restricted: sqrt(2) * mo.Cocc).  Same results as build() up to the rounding of C C^T."""
+        if self.nocc is None:
+            raise RuntimeError("DFT was created without nocc: build_mo is not available")
+        n = self.nspin * self.nbf
+        D2 = np.asfortranarray(D2, dtype=np.float64)
+        if D2.shape != (n, self.nbf):
+            raise RuntimeError(f"density matrix has shape {D2.shape}, expected {(n, self.nbf)}")
+        Cs = [C] if isinstance(C, np.ndarray) else list(C)
+        if len(Cs) != self.nspin or any(c.shape != (self.nbf, self.nocc[s]) for s, c in enumerate(Cs)):
+            raise RuntimeError("orbital coefficients do not match (nbf, nocc) of the handle")
+        packed = np.concatenate([np.asfortranarray(c, dtype=np.float64).ravel(order="F") for c in Cs])
+        K = out if out is not None else np.zeros((n, self.nbf), order="F")
+        exc, na, nb = C_.c_double(), C_.c_double(), C_.c_double()
+        check(lib().occ_xc_build_mo(self._h, ptr(D2), ptr(packed), ptr(K), C_.byref(exc), C_.byref(na), C_.byref(nb)))
+        self.m_exc_dft = exc.value
+        self.total_density = (na.value, nb.value)
+        return K
+
+    def build_mo_device(self, d2_dev_ptr: int, c_dev_ptr: int, k_dev_ptr: int, scalars_dev_ptr: int, stream: int = 0):
+        check(lib().occ_xc_build_mo_device(self._h, C_.c_void_p(d2_dev_ptr), C_.c_void_p(c_dev_ptr),
+                                           C_.c_void_p(k_dev_ptr), C_.c_void_p(scalars_dev_ptr), C_.c_void_p(stream)))
 
     def build_raw(self, d2_ptr: int, k_ptr: int):
         """occ_xc_build on raw host pointers (pinned buffers owned by the caller); returns (exc, n_alpha, n_beta)."""

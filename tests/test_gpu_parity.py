@@ -390,3 +390,55 @@ def test_handle_lifecycle_interleaving_and_threads(case):
         torch.cuda.synchronize()
         free.append(torch.cuda.mem_get_info()[0])
     assert abs(free[-1] - free[0]) < (8 << 20), free      # nothing of the workspaces is left behind per cycle
+
+
+@pytest.mark.parametrize("mol,bas,method,nspin,nocc", [
+    ("water", "def2-svp", "b3lyp", 1, None),        # nb = 25 > 2 nocc = 10: factorised form everywhere
+    ("water", "def2-svp", "tpss", 1, 15),           # nb <= 2 nocc: D form for rho, factorised form for tau
+    ("water", "def2-svp", "svwn", 2, 7),
+    ("benzene", "def2-tzvp", "pbe", 1, 100),        # leaves with nb from 65 to 252 around 2 nocc = 200: both forms mixed
+    ("benzene", "def2-tzvp", "r2scan", 2, None),
+    ("socl2_na", "def2-svp", "tpss", 2, 30),
+])
+def test_mo_form_density_matches_oracle_and_d_form(case, oracle, mol, bas, method, nspin, nocc):
+    """occ_xc_build_mo (psi = phi C, X = psi C^T; tau from phi_k C) against the D-based oracle and against the D-form
+    build of the same handle: Vxc 1e-9, Exc 1e-8 (the only difference is the rounding of C C^T)"""
+    c = case(mol, bas)
+    b = c["basis"]
+    Cs = molecules.synthetic_orbitals(b, nspin, nocc=nocc)
+    D2 = molecules.synthetic_density(b, nspin, nocc=nocc)
+    no = Cs[0].shape[1]
+    d = dft.DFT(method, b, dft.GridHierarchy(c["spts"], c["sw"], c["leaves"]),
+                dft.UNRESTRICTED if nspin == 2 else dft.RESTRICTED, nocc=no)
+    Kd = d.build(D2).copy()
+    ed = d.exchange_correlation_energy()
+    Km = d.build_mo(D2, Cs)
+    em, nm = d.exchange_correlation_energy(), d.total_density
+    info = d.info()
+    d.close()
+    ref = oracle.xc_build(c["obasis"], c["spts"], c["sw"], c["leaves"], _names(method, oracle), nspin, D2)
+    assert np.abs(Km - ref["K"]).max() < TOL_VXC and abs(em - ref["exc"]) < TOL_EXC
+    assert np.abs(Km - Kd).max() < TOL_VXC and abs(em - ed) < TOL_EXC
+    assert abs(nm[0] - ref["n_alpha"]) < 1e-9 and abs(nm[1] - ref["n_beta"]) < 1e-9
+    assert 0.0 < info["mo_density_flops"]
+    if nocc is None:
+        assert info["mo_density_flops"] < 0.5 * info["flops_per_build"]      # less tensor work than the D form
+
+
+def test_mo_form_at_full_size_on_a_leaf_sample(oracle):
+    """valinomycin B3LYP/def2-TZVP (nocc = 300): the factorised density on every 40-th Morton leaf vs the oracle"""
+    Z, pos = molecules.MOLECULES["valinomycin"]()
+    b = aobasis.AOBasis.load(Z, pos, "def2-tzvp")
+    h = grid.MolecularGrid(b).hierarchy()
+    sample = np.concatenate([h.leaves[::40], h.leaves[-1:]])
+    Cs = molecules.synthetic_orbitals(b, 1)
+    D2 = molecules.synthetic_density(b, 1)
+    d = dft.DFT("b3lyp", b, dft.GridHierarchy(h.sorted_points, h.sorted_weights, sample), nocc=Cs[0].shape[1])
+    K = d.build_mo(D2, Cs)
+    ref = oracle.xc_build(oracle.Basis(b.as_arrays()), h.sorted_points, h.sorted_weights, sample, _names("b3lyp", oracle), 1, D2)
+    assert np.abs(K - ref["K"]).max() < TOL_VXC
+    assert abs(d.exchange_correlation_energy() - ref["exc"]) < TOL_EXC
+    assert abs(d.total_density[0] - ref["n_alpha"]) < 1e-8
+    info = d.info()
+    assert info["mo_density_flops"] < 0.35 * info["flops_per_build"]          # D form: 0.5
+    d.close()
