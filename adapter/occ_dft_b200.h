@@ -68,18 +68,22 @@ public:
   XCBuild(const BasisArrays &basis, size_t npts, const double *sorted_points, const double *sorted_weights,
           const std::vector<occ_xc_leaf_t> &leaves, const std::vector<int> &func_ids, SpinorbitalKind kind,
           double density_threshold = 1e-10, double xc_screening_threshold = 1e-10, int device = -1, int rank = 0,
-          int world_size = 1)
-      : m_nspin(static_cast<int>(kind)), m_nbf(basis.nbf()) {
+          int world_size = 1, int nocc_alpha = 0, int nocc_beta = 0)
+      : m_nspin(static_cast<int>(kind)), m_nbf(basis.nbf()), m_nocc{nocc_alpha, nocc_beta} {
     occ_xc_options_t opt{};
     opt.device = device;
     opt.rank = rank;
     opt.world_size = world_size;
+    opt.reserved[3] = nocc_alpha; // > 0: the handle can also run the factorised (MO-form) density, compute_K_dft_mo
+    opt.reserved[4] = nocc_beta;
+    if (m_nspin == 2 && nocc_beta == 0) m_nocc[1] = nocc_alpha;
     const occ_xc_basis_t b = basis.view();
     check(occ_xc_create(&b, npts, sorted_points, sorted_weights, leaves.size(), leaves.data(), nullptr,
                         static_cast<int>(func_ids.size()), func_ids.data(), m_nspin, density_threshold,
                         xc_screening_threshold, &opt, &m_handle));
   }
   ~XCBuild() {
+    occ_xc_pinned_free(m_C);
     occ_xc_pinned_free(m_K);
     occ_xc_pinned_free(m_D2);
     occ_xc_destroy(m_handle);
@@ -111,6 +115,30 @@ public:
     compute_K_dft(D, m_K);
     return m_K;
   }
+  // The same build with the occupied orbitals of `mo` as well (mo.Cocc; restricted: nbf x nocc, unrestricted: one
+  // nbf x nocc_s matrix per spin), column-major.  mo.D = Cocc Cocc^T (restricted) resp. 1/2 C_s C_s^T per spin block
+  // (include/occ/qm/orb.h:64-82), so D2_s = C~ C~^T with C~ = sqrt(2) Cocc resp. C_s: the scaling is applied here.
+  void compute_K_dft_mo(const double *D, const double *Cocc_alpha, const double *Cocc_beta, double *K) {
+    const size_t n = static_cast<size_t>(m_nspin) * m_nbf * m_nbf;
+    const size_t nc = static_cast<size_t>(m_nbf) * (m_nocc[0] + (m_nspin == 2 ? m_nocc[1] : 0));
+    if (!m_D2) {
+      void *p = nullptr;
+      check(occ_xc_pinned_alloc(n * sizeof(double), &p));
+      m_D2 = static_cast<double *>(p);
+    }
+    if (!m_C) {
+      void *p = nullptr;
+      check(occ_xc_pinned_alloc(nc * sizeof(double), &p));
+      m_C = static_cast<double *>(p);
+    }
+    for (size_t i = 0; i < n; ++i) m_D2[i] = 2 * D[i];
+    const double f = m_nspin == 1 ? 1.4142135623730951 : 1.0;
+    const size_t na = static_cast<size_t>(m_nbf) * m_nocc[0];
+    for (size_t i = 0; i < na; ++i) m_C[i] = f * Cocc_alpha[i];
+    if (m_nspin == 2)
+      for (size_t i = 0; i < nc - na; ++i) m_C[na + i] = Cocc_beta[i];
+    check(occ_xc_build_mo(m_handle, m_D2, m_C, K, &m_exc_dft, &m_total_density_a, &m_total_density_b));
+  }
   double exchange_correlation_energy() const { return m_exc_dft; }
   double total_density_alpha() const { return m_total_density_a; }
   double total_density_beta() const { return m_total_density_b; }
@@ -130,7 +158,8 @@ private:
   occ_xc_handle *m_handle = nullptr;
   int m_nspin, m_nbf;
   double m_exc_dft = 0.0, m_total_density_a = 0.0, m_total_density_b = 0.0;
-  double *m_D2 = nullptr, *m_K = nullptr;
+  int m_nocc[2];
+  double *m_D2 = nullptr, *m_K = nullptr, *m_C = nullptr;
 };
 
 } // namespace occ_b200

@@ -52,6 +52,13 @@ def make_inputs(workload):
     return basis, method, nspin, quality, D2
 
 
+def make_orbitals(basis, nspin):
+    """the orbitals behind the synthetic density (D2_s = C_s C_s^T), packed like occ_xc_build_mo wants them"""
+    from occ_b200 import molecules
+    Cs = molecules.synthetic_orbitals(basis, nspin)
+    return Cs[0].shape[1], np.concatenate([c.ravel(order="F") for c in Cs])
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -184,16 +191,22 @@ def run_b200(args):
     h = g.hierarchy()
     npts_total = len(h.sorted_weights)
     kind = dft.UNRESTRICTED if nspin == 2 else dft.RESTRICTED
-    ddft = parallel.DistributedDFT(method, basis, h, kind, device=local, batch_bytes=args.batch_mb << 20)
+    mo = args.density_form == "mo"
+    nocc, Cpacked = make_orbitals(basis, nspin)
+    ddft = parallel.DistributedDFT(method, basis, h, kind, device=local, batch_bytes=args.batch_mb << 20,
+                                   nocc=nocc if mo else None)
     info = ddft.dft.info()
     nbf = basis.nbf
     n = nspin * nbf * nbf
     # normalise the synthetic density to N_electrons with one build (the electron count is linear in D)
     hD = torch.from_numpy(np.ascontiguousarray(D2.ravel(order="F"))).pin_memory()
     hK = torch.empty(n, dtype=torch.float64).pin_memory()
+    hC = torch.from_numpy(np.ascontiguousarray(Cpacked)).pin_memory()
     exc, na, nb_ = ddft.build(hD, hK)
     nel = float(basis.num_electrons())
-    hD.mul_(nel / (na + nb_ if nspin == 2 else na))
+    scale = nel / (na + nb_ if nspin == 2 else na)
+    hD.mul_(scale)
+    hC.mul_(scale ** 0.5)
     t_setup = time.perf_counter() - t_setup
 
     def sync_all():
@@ -219,9 +232,11 @@ def run_b200(args):
     # ---- device-resident arm ----
     with torch.cuda.stream(ddft.stream):
         ddft.d_D.copy_(hD, non_blocking=True)
+        if mo:
+            ddft.d_C.copy_(hC, non_blocking=True)
 
     def step_dev():
-        ddft.build_device()
+        ddft.build_device(mo)
 
     for _ in range(args.warmup):
         step_dev()
@@ -229,6 +244,11 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     ms_dev = timed(step_dev, args.steps)
+    ms_dev_dform = None
+    if mo:      # the D-only build of the same handle, for reference beside the factorised form
+        for _ in range(2):
+            ddft.build_device(False)
+        ms_dev_dform = timed(lambda: ddft.build_device(False), args.steps)
 
     # ---- end-to-end arm (host buffers through the public call) ----
     # N = 1: pinned host D -> H2D -> build -> D2H K.  N > 1: the host matrices live in node-shared pinned memory owned
@@ -238,18 +258,20 @@ def run_b200(args):
     if shared:
         if rank == 0:
             ddft.host_D.tensor.copy_(hD)
+            if mo:
+                ddft.host_C.tensor.copy_(hC)
 
         def step_e2e():
-            ddft.build_shared()
+            ddft.build_shared(mo)
     else:
         def step_e2e():
-            ddft.build(hD if rank == 0 else None, hK if rank == 0 else None)
+            ddft.build(hD if rank == 0 else None, hK if rank == 0 else None, hC if rank == 0 else None, mo)
 
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    exc, na, nb_ = ddft.build_shared() if shared else ddft.build(hD, hK)
+    exc, na, nb_ = ddft.build_shared(mo) if shared else ddft.build(hD, hK, hC, mo)
     if shared and rank == 0:        # the shared-memory path must reproduce the broadcast / all-reduce path
         exc_b, na_b, nb_b = ddft.build(hD, hK)
         kdiff = float((ddft.host_K.tensor[:n] - hK).abs().max())
@@ -263,26 +285,30 @@ def run_b200(args):
     phases = {}
     nprof = max(1, min(3, args.steps))
     for _ in range(nprof):
-        ddft.build_device()
+        ddft.build_device(mo)
         torch.cuda.synchronize()
         for k, v in ddft.dft.phase_ms().items():
             phases[k] = phases.get(k, 0.0) + v / nprof
     ddft.dft.set_profiling(False)
 
     flops_total = info["flops_per_build"]
+    exec_total = 0.5 * info["flops_per_build"] + (info["mo_density_flops"] if mo else 0.5 * info["flops_per_build"])
+    nlaunch = float(info["launches_per_build_mo"] if mo else info["launches_per_build"])
     if world > 1:
-        ft = torch.tensor([flops_total, float(info["launches_per_build"])], dtype=torch.float64, device=dev)
+        ft = torch.tensor([flops_total, nlaunch, exec_total], dtype=torch.float64, device=dev)
         dist.all_reduce(ft)
-        flops_total, launches_total = float(ft[0]), float(ft[1])
+        flops_total, launches_total, exec_total = float(ft[0]), float(ft[1]), float(ft[2])
     else:
-        launches_total = float(info["launches_per_build"])
+        launches_total = nlaunch
 
     if rank == 0:
         g_fac = 16.0 if info["deriv"] >= 2 else 4.0
         # the two DMMA contractions do g/2 * nspin * sum(n nb^2) algorithmic flops each
         kern = {}
+        executed = {"density": info["mo_density_flops"] if mo else 0.5 * info["flops_per_build"],
+                    "vxc": 0.5 * info["flops_per_build"]}
         for name in ("density", "vxc"):
-            fl = 0.5 * info["flops_per_build"]
+            fl = executed[name]      # tensor flops the phase really issues (the factorised density issues fewer)
             ms_launch = phases[name] / max(1, info["nbatches"])
             kern[name] = {"ms_per_build": phases[name], "launches_per_build": info["nbatches"],
                           "avg_launch_ms": ms_launch, "tflops": fl / (phases[name] * 1e-3) / 1e12 if phases[name] > 0 else 0.0}
@@ -317,7 +343,19 @@ def run_b200(args):
                              "no explicit flush" % _workspace_gb(info, nspin)},
             "xc_energy": exc, "n_electrons": na + (nb_ if nspin == 2 else 0.0),
             "algorithmic_tflops": flops_total / (ms_dev * 1e-3) / 1e12,
+            "executed_tensor_tflops": exec_total / (ms_dev * 1e-3) / 1e12,
+            # the whole-build fraction is quoted against the D-based algorithmic count even when the density
+            # runs in the factorised form; the fraction of the peak the tensor pipe really sustained is given beside it
             "fp64_tensor_frac_whole_build": flops_total / (ms_dev * 1e-3) / 1e12 / (FP64_TENSOR_PEAK_TFLOPS * world),
+            "executed_tensor_frac_whole_build": exec_total / (ms_dev * 1e-3) / 1e12 / (FP64_TENSOR_PEAK_TFLOPS * world),
+            "density_form": ("factorised where cheaper: psi = phi C, X = psi C^T (4 n nb nocc instead of 2 n nb^2 flops; "
+                             "occ_xc_build_mo, the seam's `mo` carries C); algorithmic_tflops / fp64_tensor_frac_whole_build count the "
+                             "D-based 4 n nb^2 of SURVEY 8d, executed_tensor_* the DMMA flops really issued"
+                             if mo else "D form (phi D)"),
+            "d_form": None if ms_dev_dform is None else {
+                "ms_per_step": ms_dev_dform, "value": npts_total / (ms_dev_dform * 1e-3),
+                "algorithmic_tflops": flops_total / (ms_dev_dform * 1e-3) / 1e12,
+                "fp64_tensor_frac_whole_build": flops_total / (ms_dev_dform * 1e-3) / 1e12 / (FP64_TENSOR_PEAK_TFLOPS * world)},
             "roofline": {"bound": "tensor", "kernel": KERNEL_NAMES[dom], "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS,
                          "unit": "TFLOP/s", "frac": achieved / FP64_TENSOR_PEAK_TFLOPS, "traffic": traffic,
                          "algorithmic_flops_per_launch": 0.5 * info["flops_per_build"] / max(1, info["nbatches"]),
@@ -327,7 +365,8 @@ def run_b200(args):
             "phases_ms": phases,
             "cpu_baseline": cpu,
             "e2e": {"value": npts_total / (ms_e2e * 1e-3), "unit": "grid-points/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": 8 * n * (world if shared else 1), "d2h_bytes_per_step": 8 * n + 32 * world,
+                    "h2d_bytes_per_step": 8 * (n + (hC.numel() if mo else 0)) * (world if shared else 1),
+                    "d2h_bytes_per_step": 8 * n + 32 * world,
                     "path": ("pinned host D -> H2D -> build -> D2H of K and the 3 scalars" if world == 1 else
                              "rank 0: pinned host D -> H2D; NCCL broadcast of D; sharded build; NCCL all-reduce of [K|Exc,Na,Nb]; "
                              "rank 0: D2H of K (no room in /dev/shm for the shared-host path)" if not shared else
@@ -361,6 +400,8 @@ def main():
     ap.add_argument("--batch-mb", type=int, default=4096)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--density-form", default="mo", choices=["mo", "d"],
+                    help="mo: factorised density where cheaper (occ_xc_build_mo, needs the occupied orbitals); d: D only")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1098,6 +1098,13 @@ int occ_xc_get_info(const occ_xc_handle *h, occ_xc_info_t *info) {
   info->workspace_bytes = h->alloc_bytes;
   info->launches_per_build = h->launches;
   info->mo_density_flops = h->mo_executed_flops;
+  size_t lm = 0;
+  if (h->mo) {
+    for (const Batch &b : h->batches)
+      lm += (b.ncolloc > 0) + (b.npsi > 0) + (b.ndensmo > 0) + (b.nxpsi > 0) + (b.nleaves > 0) + (b.nvxc > 0);
+    lm += 2 + (h->nspin == 1 ? 1 : 0) + h->nspin;
+  }
+  info->launches_per_build_mo = lm;
   return 0;
 }
 

@@ -95,6 +95,11 @@ class DistributedDFT:
         self._sc_host = torch.zeros(3, dtype=torch.float64).pin_memory()
         dev = torch.device("cuda", self.device)
         self.d_D = torch.empty(self.nspin * self.nbf * self.nbf, dtype=torch.float64, device=dev)
+        # occupied orbitals for the factorised (MO-form) density: nspin blocks nbf x nocc_s, packed
+        self.nocc = self.dft.nocc
+        self.nC = self.nbf * (self.nocc[0] + (self.nocc[1] if self.nspin == 2 else 0)) if self.nocc else 0
+        self.d_C = torch.empty(max(self.nC, 1), dtype=torch.float64, device=dev)
+        self.host_C = None
         self.d_out = torch.zeros(pack_len(self.nspin, self.nbf), dtype=torch.float64, device=dev)
         # a dedicated non-default stream: the C ABI reads a NULL stream as "the handle's own stream", so the legacy
         # default stream (value 0) can never be passed through it; copies, build and all-reduce all run here
@@ -107,7 +112,7 @@ class DistributedDFT:
             self._slice = slice_len(self.nspin, self.nbf, self.world)
             # /dev/shm must hold both matrices (a container may cap it at 64 MB; writing past the cap is a SIGBUS, not an
             # exception): rank 0 checks, every rank takes rank 0's verdict; without room the broadcast path stays
-            need = 8 * (n + self._slice * self.world) + (1 << 20)
+            need = 8 * (n + self._slice * self.world + self.nC) + (1 << 20)
             try:
                 st = os.statvfs("/dev/shm")
                 ok = st.f_bavail * st.f_frsize >= need
@@ -123,6 +128,8 @@ class DistributedDFT:
                 dist.barrier(group)          # rank 0 has created the segments
             self.host_D = SharedHostArray(tag + "_D", n, create)
             self.host_K = SharedHostArray(tag + "_K", self._slice * self.world, create)
+            if self.nC:
+                self.host_C = SharedHostArray(tag + "_C", self.nC, create)
             self._ctl = SharedHostArray(tag + "_c", 2 + self.world, create, dtype=np.int64, register=False)
             if create:
                 self._ctl.array[:] = 0
@@ -131,18 +138,26 @@ class DistributedDFT:
             self.d_red = torch.zeros(self._slice * self.world, dtype=torch.float64, device=dev)
             self.d_slice = torch.zeros(self._slice, dtype=torch.float64, device=dev)
 
-    def build_device(self) -> torch.Tensor:
-        """D already in self.d_D (column-major). Enqueues build + all-reduce on self.stream; returns the packed
-        device buffer [K | exc, n_alpha, n_beta] (valid once self.stream has been synchronised / waited on)."""
+    def _launch(self, out: torch.Tensor, mo: bool):
         n = self.nspin * self.nbf * self.nbf
-        self.dft.build_device(self.d_D.data_ptr(), self.d_out.data_ptr(), self.d_out.data_ptr() + 8 * n,
-                              self.stream.cuda_stream)
+        if mo:
+            self.dft.build_mo_device(self.d_D.data_ptr(), self.d_C.data_ptr(), out.data_ptr(), out.data_ptr() + 8 * n,
+                                     self.stream.cuda_stream)
+        else:
+            self.dft.build_device(self.d_D.data_ptr(), out.data_ptr(), out.data_ptr() + 8 * n, self.stream.cuda_stream)
+
+    def build_device(self, mo: bool = False) -> torch.Tensor:
+        """D already in self.d_D (and, with mo=True, the orbitals in self.d_C), column-major. Enqueues build +
+        all-reduce on self.stream; returns the packed device buffer [K | exc, n_alpha, n_beta] (valid once self.stream
+        has been synchronised / waited on)."""
+        self._launch(self.d_out, mo)
         if self.world > 1:
             with torch.cuda.stream(self.stream):
                 allreduce_partial(self.d_out, self.group)
         return self.d_out
 
-    def build(self, D2_host: torch.Tensor | None, K_host: torch.Tensor | None):
+    def build(self, D2_host: torch.Tensor | None, K_host: torch.Tensor | None, C_host: torch.Tensor | None = None,
+              mo: bool = False):
         """Host-to-host build as the reference's single-process SCF driver would see it: rank 0 owns the host
         matrices (pinned CPU tensors, column-major).  Rank 0 copies D to its GPU, D is broadcast to the other GPUs over
         NVLink (NCCL), every rank builds its shard, the packed result is all-reduced and rank 0 copies K back.
@@ -151,9 +166,13 @@ class DistributedDFT:
         with torch.cuda.stream(self.stream):
             if self.rank == 0:
                 self.d_D.copy_(D2_host.view(-1), non_blocking=True)
+                if mo:
+                    self.d_C.copy_(C_host.view(-1), non_blocking=True)
             if self.world > 1:
                 dist.broadcast(self.d_D, src=0, group=self.group)
-            out = self.build_device()
+                if mo:
+                    dist.broadcast(self.d_C, src=0, group=self.group)
+            out = self.build_device(mo)
             if self.rank == 0 and K_host is not None:
                 K_host.view(-1)[:n].copy_(out[:n], non_blocking=True)
             self._sc_host.copy_(out[n:n + 3], non_blocking=True)
@@ -167,7 +186,7 @@ class DistributedDFT:
             if time.perf_counter() - t0 > timeout:
                 raise RuntimeError("DistributedDFT: a rank did not reach the shared-memory rendezvous")
 
-    def build_shared(self):
+    def build_shared(self, mo: bool = False):
         """Host-to-host build for N > 1 with the host matrices in node-shared pinned memory (self.host_D / self.host_K,
         column-major, owned by rank 0's caller — the SCF process).  Every rank: H2D of D over its own PCIe link ->
         sharded build -> NCCL reduce-scatter of the packed [K | exc, n_alpha, n_beta] -> D2H of its 1/N slice into
@@ -182,8 +201,9 @@ class DistributedDFT:
             self._spin_until(0, ep)
         with torch.cuda.stream(self.stream):
             self.d_D.copy_(self.host_D.tensor, non_blocking=True)
-            self.dft.build_device(self.d_D.data_ptr(), self.d_red.data_ptr(), self.d_red.data_ptr() + 8 * n,
-                                  self.stream.cuda_stream)
+            if mo:
+                self.d_C.copy_(self.host_C.tensor, non_blocking=True)
+            self._launch(self.d_red, mo)
             dist.reduce_scatter_tensor(self.d_slice, self.d_red, op=dist.ReduceOp.SUM, group=self.group)
             lo = self.rank * self._slice
             self.host_K.tensor[lo:lo + self._slice].copy_(self.d_slice, non_blocking=True)
@@ -195,8 +215,8 @@ class DistributedDFT:
         return float(sc[0]), float(sc[1]), float(sc[2])
 
     def close(self):
-        for b in (self.host_D, self.host_K, self._ctl):
+        for b in (self.host_D, self.host_K, self.host_C, self._ctl):
             if b is not None:
                 b.close()
-        self.host_D = self.host_K = self._ctl = None
+        self.host_D = self.host_K = self.host_C = self._ctl = None
         self.dft.close()
