@@ -159,6 +159,10 @@ MOLECULES = {"socl2_na": thionyl_chloride_like, "water": water, "water_isolated"
 def synthetic_orbitals(basis: AOBasis, nspin: int = 1, seed: int | None = None, nocc: int | None = None):
     """The localised, orthonormalised random orbitals behind synthetic_density: a list of nspin matrices C_s
     (nbf x nocc, Fortran order) with D2_s = C_s C_s^T (the 1/2 of the unrestricted blocks folded in as 1/sqrt 2)."""
+    return [np.asfortranarray(Q * np.sqrt(0.5)) if nspin == 2 else Q for Q in _orthonormal_orbitals(basis, nspin, seed, nocc)]
+
+
+def _orthonormal_orbitals(basis, nspin, seed, nocc):
     nbf = basis.nbf
     natoms = len(basis.atomic_numbers)
     nocc = basis.num_electrons() // 2 if nocc is None else nocc
@@ -171,8 +175,6 @@ def synthetic_orbitals(basis: AOBasis, nspin: int = 1, seed: int | None = None, 
         d2 = ((centres[:, None, :] - basis.positions[c][None, :, :]) ** 2).sum(-1)
         A *= np.exp(-d2 / 16.0)
         Q, _ = np.linalg.qr(A)
-        if nspin == 2:
-            Q = Q * np.sqrt(0.5)
         out.append(np.asfortranarray(Q))
     return out
 
@@ -181,7 +183,10 @@ def synthetic_density(basis: AOBasis, nspin: int = 1, seed: int | None = None, n
     """SURVEY.md §8d recipe. Returns D2 with shape (nspin*nbf, nbf), Fortran (column-major) order,
     un-normalised (callers rescale by N_el / integral(rho), which is linear in D)."""
     blocks = []
-    for Q in synthetic_orbitals(basis, nspin, seed, nocc):
+    for Q in _orthonormal_orbitals(basis, nspin, seed, nocc):
         P = Q @ Q.T
-        blocks.append(0.5 * (P + P.T))
+        P = 0.5 * (P + P.T)
+        if nspin == 2:
+            P *= 0.5
+        blocks.append(P)
     return np.asfortranarray(np.vstack(blocks))
