@@ -164,6 +164,10 @@ int occ_xc_density_on_grid(occ_xc_handle *h, const double *D2, double *rho);
 int occ_xc_vv10(occ_xc_handle *h, const double *D2, const size_t *orig_index, double vv10_b, double vv10_C, double *K,
                 double *energy);
 
+/* occ_xc_gradient with the occupied orbitals as well (D2_s = C_s C_s^T, C packed as in occ_xc_build_mo): the density and
+ * the A . D^T products of the gradient run in the factorised form where cheaper.  Same gradient to rounding. */
+int occ_xc_gradient_mo(occ_xc_handle *h, const double *D2, const double *C, double *gradient);
+
 /* Geometry-only facts of the handle (this rank's shard) */
 typedef struct {
   int nbf, nspin, deriv, nsh;

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("OCC_XC_B200_LIB", os.path.join(HERE, "libocc_xc_b200.so"))  # override: kernel-variant experiments
 
 # every symbol include/occ_xc_b200.h declares
-SYMBOLS = ["occ_xc_create", "occ_xc_build", "occ_xc_build_device", "occ_xc_build_mo", "occ_xc_build_mo_device", "occ_xc_gradient", "occ_xc_vv10", "occ_xc_density_on_grid", "occ_xc_pinned_alloc",
+SYMBOLS = ["occ_xc_create", "occ_xc_build", "occ_xc_build_device", "occ_xc_build_mo", "occ_xc_build_mo_device", "occ_xc_gradient", "occ_xc_gradient_mo", "occ_xc_vv10", "occ_xc_density_on_grid", "occ_xc_pinned_alloc",
            "occ_xc_pinned_free", "occ_xc_host_register", "occ_xc_host_unregister", "occ_xc_get_info", "occ_xc_set_profiling",
            "occ_xc_get_phase_ms", "occ_xc_decay_cutoff", "occ_xc_eval_functional", "occ_xc_leaf_collocation",
            "occ_xc_family", "occ_xc_exact_exchange", "occ_xc_destroy", "occ_xc_last_error", "occ_xc_abi_version",

@@ -71,26 +71,31 @@ __device__ __forceinline__ void red_add_f64(double *addr, double v) {
 //   MODE 3   X = psi . C_loc^T       (128 x nb, K = nocc; B gathered along n), then the row-dot epilogue of MODE 0
 // 4 n nb nocc flops instead of 2 n nb^2 for rho / grad rho, 6 n nb nocc instead of 6 n nb^2 for tau; the host picks
 // the form per leaf and spin (nb > 2 nocc, resp. nb > nocc).  Same numbers as MODE 0 up to the rounding of C C^T.
+// MODE 4 / 5: the same factorisation for the XC nuclear gradient (acc = A . D_s^T = (A C)(C^T) for the symmetric D2 = C C^T):
+//   MODE 4   psi_A = A . C_loc with A = G_s or phi_e (stored to the tile's psi slab; A = phi reuses the density's psi)
+//   MODE 5   X = psi_A . C_loc^T followed by the per-atom gradient epilogue of MODE 1
 template <int MODE> __device__ __forceinline__ void gemm_xd_body(const BuildParams &P, const DensItem it, double *smem) {
   const TileDesc t = P.tiles[it.tile];
-  if (MODE == 1 && P.leaf_skip[t.leaf]) return;
+  if ((MODE == 1 || MODE == 4 || MODE == 5) && P.leaf_skip[t.leaf]) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;
   const int wm = warp & 3, wn = warp >> 2;
-  const int nbK = MODE == 3 ? P.mo_nocc[it.spin] : t.nb;   // valid extent of the contraction index
-  const int nbKp = MODE == 3 ? P.mo_noccp : t.nbp;         // columns the A slab really has
-  const int nb = MODE == 2 ? P.mo_nocc[it.spin] : t.nb;    // valid extent of the output columns
+  constexpr bool TO_PSI = MODE == 2 || MODE == 4;   // output columns are orbitals, B = C
+  constexpr bool FROM_PSI = MODE == 3 || MODE == 5; // A = psi slab, contraction over orbitals, B = C^T
+  const int nbK = FROM_PSI ? P.mo_nocc[it.spin] : t.nb;   // valid extent of the contraction index
+  const int nbKp = FROM_PSI ? P.mo_noccp : t.nbp;         // columns the A slab really has
+  const int nb = TO_PSI ? P.mo_nocc[it.spin] : t.nb;      // valid extent of the output columns
   const int nk = (nbK + GK - 1) / GK;
   const size_t slab = static_cast<size_t>(t.nbp) * TILE_P;
   const size_t psi_slab = static_cast<size_t>(P.mo_noccp) * TILE_P;
   const int a_slab = (MODE == 0 || MODE == 2)
                          ? it.acomp
                          : (it.acomp == 0 ? 0 : (it.acomp == 1 ? P.slab_G + it.spin : it.acomp - 1));
-  const double *Ag = MODE == 3 ? P.scratch + t.psi_off + static_cast<size_t>(it.spin) * psi_slab
-                               : P.scratch + t.scr_off + static_cast<size_t>(a_slab) * slab;
+  const double *Ag = FROM_PSI ? P.scratch + t.psi_off + static_cast<size_t>(it.spin) * psi_slab
+                              : P.scratch + t.scr_off + static_cast<size_t>(a_slab) * slab;
   const double *Dm = MODE == 0 ? (it.acomp == 0 ? P.Drho : P.Dtau)[it.spin]
-                               : (MODE == 1 ? P.DT[it.spin] : (MODE == 2 ? P.moC[it.spin] : P.moCT[it.spin]));
-  const int ldB = MODE == 2 ? P.ldC : (MODE == 3 ? P.ldCT : P.ldD);
+                               : (MODE == 1 ? P.DT[it.spin] : (TO_PSI ? P.moC[it.spin] : P.moCT[it.spin]));
+  const int ldB = TO_PSI ? P.ldC : (FROM_PSI ? P.ldCT : P.ldD);
   const int *gidx = P.bf_index + t.bf_off;
   const int n0 = it.jb * GN;
 
@@ -104,7 +109,7 @@ template <int MODE> __device__ __forceinline__ void gemm_xd_body(const BuildPara
   for (int r = 0; r < NBR; ++r) {
     const int n = n0 + nn + NROWT * r;
     nvalid[r] = n < nb;
-    coloff[r] = nvalid[r] ? static_cast<size_t>(MODE == 2 ? n : __ldg(gidx + n)) * ldB : 0;
+    coloff[r] = nvalid[r] ? static_cast<size_t>(TO_PSI ? n : __ldg(gidx + n)) * ldB : 0;
   }
   // 8-column groups of this warp's 32 columns that hold real basis functions (the rest is padding: no DMMA)
   const int ni_valid = min(4, max(0, (nb - (n0 + wn * 32) + 7) >> 3));
@@ -128,7 +133,7 @@ template <int MODE> __device__ __forceinline__ void gemm_xd_body(const BuildPara
   };
   auto fetch_row = [&](int kc) {
     const int k = kc * GK + kk;
-    grow_next = k < nbK ? (MODE == 3 ? k : __ldg(gidx + k)) : 0;
+    grow_next = k < nbK ? (FROM_PSI ? k : __ldg(gidx + k)) : 0;
   };
 
   double acc[4][4][2];
@@ -194,8 +199,8 @@ template <int MODE> __device__ __forceinline__ void gemm_xd_body(const BuildPara
   }
   cp_async_wait<0>();
 
-  if (MODE == 2) {
-    if (it.acomp == 0) { // psi tile -> the tile's psi slab (padding columns carry exact zeros)
+  if (TO_PSI) {
+    if (MODE == 4 || it.acomp == 0) { // psi tile -> the tile's psi slab (padding columns carry exact zeros)
       double *ps = P.scratch + t.psi_off + static_cast<size_t>(it.spin) * psi_slab +
                    static_cast<size_t>(n0 + wn * 32 + 2 * tig) * TILE_P + wm * 32 + gid;
 #pragma unroll
@@ -219,7 +224,7 @@ template <int MODE> __device__ __forceinline__ void gemm_xd_body(const BuildPara
     }
     return;
   }
-  if (MODE == 1) {
+  if (MODE == 1 || MODE == 5) {
     // gradient epilogue
     const double *cbase = P.scratch + t.scr_off + static_cast<size_t>(n0 + wn * 32 + 2 * tig) * TILE_P + wm * 32 + gid;
     const int *batom = P.bf_atom + t.bf_off + n0 + wn * 32 + 2 * tig;
@@ -289,6 +294,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_mo_psi(BuildParams P, const Den
 __global__ void __launch_bounds__(NTHREADS, 2) k_mo_density(BuildParams P, const DensItem *__restrict__ items) {
   extern __shared__ __align__(16) double smem[];
   gemm_xd_body<3>(P, items[blockIdx.x], smem);
+}
+__global__ void __launch_bounds__(NTHREADS, 2) k_mo_grad_psi(BuildParams P, const DensItem *__restrict__ items) {
+  extern __shared__ __align__(16) double smem[];
+  gemm_xd_body<4>(P, items[blockIdx.x], smem);
+}
+__global__ void __launch_bounds__(NTHREADS, 2) k_mo_xc_gradient(BuildParams P, const DensItem *__restrict__ items) {
+  extern __shared__ __align__(16) double smem[];
+  gemm_xd_body<5>(P, items[blockIdx.x], smem);
 }
 __global__ void __launch_bounds__(NTHREADS, 2) k_xc_gradient(BuildParams P, const DensItem *__restrict__ items) {
   extern __shared__ __align__(16) double smem[];
@@ -552,6 +565,27 @@ void launch_mo_density(const BuildParams &P, const DensItem *items, int nitems, 
     configured = true;
   }
   k_mo_density<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
+}
+
+void launch_mo_grad_psi(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
+  if (nitems <= 0) return;
+  static bool configured = false;
+  const int smem_bytes = GSTAGES * D_STAGE * sizeof(double);
+  if (!configured) {
+    cudaFuncSetAttribute(k_mo_grad_psi, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    configured = true;
+  }
+  k_mo_grad_psi<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
+}
+void launch_mo_grad_gemm(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
+  if (nitems <= 0) return;
+  static bool configured = false;
+  const int smem_bytes = GSTAGES * D_STAGE * sizeof(double);
+  if (!configured) {
+    cudaFuncSetAttribute(k_mo_xc_gradient, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    configured = true;
+  }
+  k_mo_xc_gradient<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
 }
 
 // rectangular transpose: out (ncol x nrow, ld_out) = in (nrow x ncol, ld_in)^T, column-major

@@ -182,6 +182,8 @@ struct Batch {
   int tile0, ntiles, leaf0, nleaves;
   size_t colloc_off, ncolloc, dens_off, ndens, g_off, ng, vxc_off, nvxc, grad_off, ngrad;
   size_t densmo_off, ndensmo, psi_off, npsi, xpsi_off, nxpsi; // MO-form density work lists
+  // MO-form gradient: per A operand wh (0 phi, 1 G, 2..4 phi_e) the psi_A items and the X items; D-form remainder
+  size_t gpsi_off[5], ngpsi[5], gx_off[5], ngx[5], gradd_off, ngradd;
 };
 
 struct occ_xc_handle {
@@ -217,6 +219,8 @@ struct occ_xc_handle {
   bool mo = false;
   int nocc[2] = {0, 0}, noccp = 0;
   DensItem *d_densmo = nullptr, *d_psi = nullptr, *d_xpsi = nullptr;
+  DensItem *d_gpsi[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *d_gx[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  DensItem *d_gradd = nullptr;
   double *d_C = nullptr, *d_CT = nullptr;
   double mo_executed_flops = 0.0; // DMMA flops one MO-form build really issues (density side)
   // post-SCF VV10 (allocated on first use)
@@ -405,11 +409,16 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
     e.cost = static_cast<double>(lf.count) * e.nb * e.nb;
     hl.push_back(e);
   }
-  // ---- shard: contiguous Morton runs of equal predicted cost (n * nb^2) ----
+  // ---- shard: contiguous Morton runs of equal predicted cost (n * nb^2; with the factorised density the density half
+  // of a leaf costs n * nb * min(nb, 2 nocc) instead of n * nb^2) ----
   size_t l_lo = 0, l_hi = hl.size();
   if (world > 1) {
     std::vector<double> costs(hl.size());
-    for (size_t i = 0; i < hl.size(); ++i) costs[i] = hl[i].cost;
+    const int mo_nocc = (opt && opt->reserved[3] > 0) ? opt->reserved[3] : 0;
+    for (size_t i = 0; i < hl.size(); ++i) {
+      costs[i] = hl[i].cost;
+      if (mo_nocc > 0 && hl[i].nb > 2 * mo_nocc) costs[i] *= 0.5 * (1.0 + 2.0 * mo_nocc / hl[i].nb);
+    }
     std::vector<size_t> cut = partition_by_cost(costs, world);
     l_lo = cut[rank];
     l_hi = cut[rank + 1];
@@ -509,7 +518,7 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
 
   // ---- batches of consecutive leaves under the workspace budget; per-phase work lists ----
   std::vector<CollocItem> colloc;
-  std::vector<DensItem> dens, gitems, gradit, densmo, psi, xpsi;
+  std::vector<DensItem> dens, gitems, gradit, densmo, psi, xpsi, gpsi_w[5], gx_w[5], gradd;
   std::vector<VxcItem> vxc;
   size_t max_scratch = 0;
   {
@@ -550,6 +559,11 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
       b.densmo_off = densmo.size();
       b.psi_off = psi.size();
       b.xpsi_off = xpsi.size();
+      b.gradd_off = gradd.size();
+      for (int wh = 0; wh < 5; ++wh) {
+        b.gpsi_off[wh] = gpsi_w[wh].size();
+        b.gx_off[wh] = gx_w[wh].size();
+      }
       for (int ti : order) {
         const TileDesc &t = h->h_tiles[ti];
         for (int s0 = 0; s0 < t.nsh; s0 += 16) {
@@ -625,7 +639,27 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
                 gi.spin = static_cast<signed char>(sp);
                 gi.acomp = static_cast<signed char>(wh);
                 gradit.push_back(gi);
+                if (h->mo && t.nb <= 2 * h->nocc[sp]) gradd.push_back(gi);
               }
+          if (h->mo)
+            for (int sp = 0; sp < nspin; ++sp) {
+              if (t.nb <= 2 * h->nocc[sp]) continue;
+              for (int wh = w0; wh <= w1; ++wh) {
+                DensItem gi;
+                gi.tile = ti;
+                gi.spin = static_cast<signed char>(sp);
+                gi.acomp = static_cast<signed char>(wh);
+                if (wh != 0) // A = phi: the density phase left psi = phi C in the tile's psi slab
+                  for (int jb = 0; jb < h->noccp / 64; ++jb) {
+                    gi.jb = static_cast<short>(jb);
+                    gpsi_w[wh].push_back(gi);
+                  }
+                for (int jb = 0; jb < njb; ++jb) {
+                  gi.jb = static_cast<short>(jb);
+                  gx_w[wh].push_back(gi);
+                }
+              }
+            }
         }
         for (int jb = 0; jb < njb; ++jb) {
           DensItem gi;
@@ -641,6 +675,11 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
       b.ng = gitems.size() - b.g_off;
       b.nvxc = vxc.size() - b.vxc_off;
       b.ngrad = gradit.size() - b.grad_off;
+      b.ngradd = gradd.size() - b.gradd_off;
+      for (int wh = 0; wh < 5; ++wh) {
+        b.ngpsi[wh] = gpsi_w[wh].size() - b.gpsi_off[wh];
+        b.ngx[wh] = gx_w[wh].size() - b.gx_off[wh];
+      }
       b.ndensmo = densmo.size() - b.densmo_off;
       b.npsi = psi.size() - b.psi_off;
       b.nxpsi = xpsi.size() - b.xpsi_off;
@@ -694,6 +733,18 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
       h->d_densmo = const_cast<DensItem *>(d1);
       h->d_psi = const_cast<DensItem *>(d2);
       h->d_xpsi = const_cast<DensItem *>(d3);
+      if (want_grad) {
+        const DensItem *dq = nullptr;
+        rc |= dev_upload(h, &dq, gradd);
+        h->d_gradd = const_cast<DensItem *>(dq);
+        for (int wh = 0; wh < 5; ++wh) {
+          const DensItem *d4 = nullptr, *d5 = nullptr;
+          rc |= dev_upload(h, &d4, gpsi_w[wh]);
+          rc |= dev_upload(h, &d5, gx_w[wh]);
+          h->d_gpsi[wh] = const_cast<DensItem *>(d4);
+          h->d_gx[wh] = const_cast<DensItem *>(d5);
+        }
+      }
       rc |= dev_alloc(h, &h->d_C, static_cast<size_t>(nbf) * (h->nocc[0] + h->nocc[1]));
       rc |= dev_alloc(h, &h->d_CT, static_cast<size_t>(nspin) * h->noccp * nbf);
     }
@@ -1044,14 +1095,38 @@ int occ_xc_host_unregister(void *p) {
   return 0;
 }
 
+static int gradient_impl(occ_xc_handle *h, const double *D2, const double *C, double *gradient);
+
 int occ_xc_gradient(occ_xc_handle *h, const double *D2, double *gradient) {
   if (!h || !D2 || !gradient) return fail("occ_xc_gradient: null argument");
   if (!h->gradient) return fail("occ_xc_gradient: handle was created without the gradient option");
+  return gradient_impl(h, D2, nullptr, gradient);
+}
+
+int occ_xc_gradient_mo(occ_xc_handle *h, const double *D2, const double *C, double *gradient) {
+  if (!h || !D2 || !C || !gradient) return fail("occ_xc_gradient_mo: null argument");
+  if (!h->gradient) return fail("occ_xc_gradient_mo: handle was created without the gradient option");
+  if (!h->mo) return fail("occ_xc_gradient_mo: the handle was created without occupied-orbital counts");
+  return gradient_impl(h, D2, C, gradient);
+}
+
+static int gradient_impl(occ_xc_handle *h, const double *D2, const double *C, double *gradient) {
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   BuildParams P = h->P;
   const size_t ksz = static_cast<size_t>(h->nspin) * h->nbf * h->nbf;
+  const bool mo = C != nullptr;
   CUDA_TRY(cudaMemcpyAsync(h->d_D, D2, ksz * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (mo) {
+    const size_t csz = static_cast<size_t>(h->nbf) * (h->nocc[0] + h->nocc[1]);
+    CUDA_TRY(cudaMemcpyAsync(h->d_C, C, csz * sizeof(double), cudaMemcpyHostToDevice, st));
+    for (int sp = 0; sp < h->nspin; ++sp) {
+      const double *Cs = h->d_C + static_cast<size_t>(sp) * h->nbf * h->nocc[0];
+      P.moC[sp] = Cs;
+      launch_transpose_rect(Cs, h->d_CT + static_cast<size_t>(sp) * h->noccp * h->nbf, h->nbf, h->nocc[sp], h->nbf,
+                            h->noccp, st);
+    }
+  }
   if (h->nspin == 1) {
     launch_prepare_density(h->d_D, h->d_Dsym, h->nbf, 1, st);
     P.Drho[0] = h->d_Dsym;
@@ -1068,11 +1143,25 @@ int occ_xc_gradient(occ_xc_handle *h, const double *D2, double *gradient) {
     launch_collocate(P, h->d_colloc + b.colloc_off, static_cast<int>(b.ncolloc), st);
     CUDA_TRY(cudaMemsetAsync(P.acc + static_cast<size_t>(b.tile0) * h->nspin * NACC * TILE_P, 0,
                              static_cast<size_t>(b.ntiles) * h->nspin * NACC * TILE_P * sizeof(double), st));
-    launch_density(P, h->d_dens + b.dens_off, static_cast<int>(b.ndens), st);
+    if (mo) {
+      launch_mo_psi(P, h->d_psi + b.psi_off, static_cast<int>(b.npsi), st);
+      launch_density(P, h->d_densmo + b.densmo_off, static_cast<int>(b.ndensmo), st);
+      launch_mo_density(P, h->d_xpsi + b.xpsi_off, static_cast<int>(b.nxpsi), st);
+    } else {
+      launch_density(P, h->d_dens + b.dens_off, static_cast<int>(b.ndens), st);
+    }
     launch_functional(P, b.leaf0, b.nleaves, st);
     launch_gbuild(P, h->d_g + b.g_off, static_cast<int>(b.ng), st);
     if (h->deriv >= 1) launch_collocate_h(P, h->d_colloc + b.colloc_off, static_cast<int>(b.ncolloc), st);
-    launch_grad_gemm(P, h->d_gradit + b.grad_off, static_cast<int>(b.ngrad), st);
+    if (mo) {
+      launch_grad_gemm(P, h->d_gradd + b.gradd_off, static_cast<int>(b.ngradd), st);
+      for (int wh = 0; wh < 5; ++wh) { // one psi slab per spin: the A operands take turns
+        launch_mo_grad_psi(P, h->d_gpsi[wh] + b.gpsi_off[wh], static_cast<int>(b.ngpsi[wh]), st);
+        launch_mo_grad_gemm(P, h->d_gx[wh] + b.gx_off[wh], static_cast<int>(b.ngx[wh]), st);
+      }
+    } else {
+      launch_grad_gemm(P, h->d_gradit + b.grad_off, static_cast<int>(b.ngrad), st);
+    }
   }
   CUDA_TRY(cudaMemcpyAsync(gradient, h->d_grad, 3 * static_cast<size_t>(h->natoms) * sizeof(double),
                            cudaMemcpyDeviceToHost, st));

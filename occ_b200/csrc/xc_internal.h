@@ -136,6 +136,8 @@ void launch_gbuild(const BuildParams &P, const DensItem *items, int nitems, void
 void launch_collocate_h(const BuildParams &P, const CollocItem *items, int nitems, void *stream);
 void launch_mo_psi(const BuildParams &P, const DensItem *items, int nitems, void *stream);
 void launch_mo_density(const BuildParams &P, const DensItem *items, int nitems, void *stream);
+void launch_mo_grad_psi(const BuildParams &P, const DensItem *items, int nitems, void *stream);
+void launch_mo_grad_gemm(const BuildParams &P, const DensItem *items, int nitems, void *stream);
 void launch_transpose_rect(const double *in, double *out, int nrow, int ncol, int ld_in, int ld_out, void *stream);
 void launch_grad_gemm(const BuildParams &P, const DensItem *items, int nitems, void *stream);
 void launch_transpose(const double *D, double *DT, int nbf, int ld, void *stream);

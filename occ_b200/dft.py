@@ -199,6 +199,17 @@ class DFT:
         check(lib().occ_xc_gradient(self._h, ptr(D2), ptr(g)))
         return g
 
+    def gradient_mo(self, D2: np.ndarray, C) -> np.ndarray:
+        """occ_xc_gradient_mo: the gradient with the factorised density / A.D^T products (C as in build_mo)"""
+        if self.nocc is None:
+            raise RuntimeError("DFT was created without nocc: gradient_mo is not available")
+        D2 = np.asfortranarray(D2, dtype=np.float64)
+        Cs = [C] if isinstance(C, np.ndarray) else list(C)
+        packed = np.concatenate([np.asfortranarray(c, dtype=np.float64).ravel(order="F") for c in Cs])
+        g = np.zeros((len(self.basis.atomic_numbers), 3))
+        check(lib().occ_xc_gradient_mo(self._h, ptr(D2), ptr(packed), ptr(g)))
+        return g
+
     def set_profiling(self, on: bool):
         check(lib().occ_xc_set_profiling(self._h, C.c_int(int(on))))
 

@@ -114,3 +114,29 @@ def test_cuda_gradient_against_pyscf_values_quoted_by_the_reference():
     with pytest.raises(RuntimeError):
         d = dft.DFT("pbe", b, h)            # no gradient option
         d.gradient(P)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mol,bas,method,nspin,nocc", [
+    ("water", "def2-svp", "pbe", 1, None), ("water", "def2-svp", "svwn5", 2, None),   # (not svwn UKS: VWN3 pole)
+    ("water", "def2-svp", "tpss", 1, 15),            # nb <= 2 nocc: D form throughout
+    ("benzene", "def2-tzvp", "b3lyp", 1, 100),       # both forms mixed
+    ("benzene", "def2-tzvp", "r2scan", 2, None),
+])
+def test_cuda_gradient_mo_form_matches_oracle_and_d_form(case, oracle, mol, bas, method, nspin, nocc):
+    """occ_xc_gradient_mo: the factorised density and A.D^T products give the D-form gradient (1e-9) and the oracle's (1e-8)"""
+    from occ_b200 import dft
+    c = case(mol, bas)
+    b = c["basis"]
+    Cs = molecules.synthetic_orbitals(b, nspin, nocc=nocc)
+    D2 = molecules.synthetic_density(b, nspin, nocc=nocc)
+    names = [n for i in dft.get_dft_method(method) for n, v in oracle.FUNC_IDS.items() if v == i]
+    ref = oracle.xc_gradient(c["obasis"], c["spts"], c["sw"], c["leaves"], names, nspin, D2, len(c["Z"]))
+    d = dft.DFT(method, b, dft.GridHierarchy(c["spts"], c["sw"], c["leaves"]),
+                dft.UNRESTRICTED if nspin == 2 else dft.RESTRICTED, gradient=True, nocc=Cs[0].shape[1])
+    gd = d.gradient(D2)
+    gm = d.gradient_mo(D2, Cs)
+    d.close()
+    assert np.abs(gm - gd).max() < 1e-9
+    assert np.abs(gm - ref).max() < 1e-8
+    assert np.abs(ref).max() > 1e-3
