@@ -380,7 +380,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_vxc_resident(BuildParams P, con
   const int *gidx = P.bf_index + t.bf_off;
   double *Kt = P.Ktmp[it.spin];
   const int n0 = it.jb * GN;
-  const int nib = (nb + GM - 1) / GM;
+  // Symmetric terms — phi_k^T diag(c_tau) phi_k of a meta-GGA (acomp != 0) and phi^T diag(c0) phi of an LDA build —
+  // need only their upper triangle, because the build returns K = Ktmp + Ktmp^T: row blocks strictly below the CTA's
+  // 64 columns are skipped, blocks strictly above count twice, blocks that straddle the diagonal are computed whole.
+  const bool symmetric = it.acomp != 0 || P.deriv == 0;
+  const int nib_all = (nb + GM - 1) / GM;
+  const int nib = symmetric ? min(nib_all, (n0 + GN + GM - 1) / GM) : nib_all;
   constexpr int NKC = TILE_P / RK;
   const int nq = nib * NKC; // flattened (ib, kc) chunks
   const int ni_valid = min(8, max(0, (nb - n0 + 7) >> 3));
@@ -504,14 +509,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_vxc_resident(BuildParams P, con
     }
     if (kc == NKC - 1 && !(P.debug & 1)) {
       // scatter-add this warp's 16 x 64 block of Ktmp_loc into the full matrix (dft.h:361-369)
+      const double sf = (symmetric && (ib + 1) * GM <= n0) ? 2.0 : 1.0; // strictly above the diagonal: stands for both halves
 #pragma unroll
       for (int ni = 0; ni < 8; ++ni) {
         const int2 gc = *reinterpret_cast<const int2 *>(scol + ni * 8 + 2 * tig);
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi) {
           if (grow[mi] >= 0) {
-            if (gc.x >= 0) red_add_f64(Kt + static_cast<size_t>(gc.x) * P.ldD + grow[mi], acc[mi][ni][0]);
-            if (gc.y >= 0) red_add_f64(Kt + static_cast<size_t>(gc.y) * P.ldD + grow[mi], acc[mi][ni][1]);
+            if (gc.x >= 0) red_add_f64(Kt + static_cast<size_t>(gc.x) * P.ldD + grow[mi], sf * acc[mi][ni][0]);
+            if (gc.y >= 0) red_add_f64(Kt + static_cast<size_t>(gc.y) * P.ldD + grow[mi], sf * acc[mi][ni][1]);
           }
         }
       }
