@@ -16,54 +16,13 @@
 // arrangement with 32 x 32 warp tiles (16 DMMA per 8 conflict-free 64-bit LDS), a 3-stage cp.async pipeline,
 // 2 CTAs per SM.  Shared-memory leading dimensions are = 4 (mod 16) doubles, which makes every fragment
 // load bank-conflict free for the (groupID, threadID_in_group) access pattern of the f64 MMA.
-#include "xc_internal.h"
-#include <cuda_runtime.h>
+#include "gemm_common.cuh"
 
 namespace xcb {
 
-#ifndef XC_GK
-#define XC_GK 16
-#endif
-#ifndef XC_STAGES
-#define XC_STAGES 3
-#endif
-constexpr int GM = 128, GN = 64, GK = XC_GK, GSTAGES = XC_STAGES;
-constexpr int NTHREADS = 256;
-// density: A stage is [k][m] (m contiguous), ld 132; B stage is [n][k] (k contiguous), ld 20
-constexpr int D_LDA = GM + 4, D_LDB = GK + 4;
-constexpr int D_ASZ = GK * D_LDA, D_BSZ = GN * D_LDB, D_STAGE = D_ASZ + D_BSZ;
-
-__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
-}
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool pred) {
-  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
-  const int sz = pred ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
-}
-__device__ __forceinline__ void cp_async8(void *smem, const void *gmem, bool pred) {
-  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
-  const int sz = pred ? 8 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
-}
-__device__ __forceinline__ void red_add_f64(double *addr, double v) {
-  asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(addr), "d"(v) : "memory");
-}
-
-// ------------------------------------------------------------------------------------------------
-// density
-// ------------------------------------------------------------------------------------------------
-// MODE 0: density (epilogue = row-dots with the AO slabs).  MODE 1: XC nuclear gradient:
-// acc = A . D_s^T with A = phi (acomp 0), G_s (acomp 1) or phi_e (acomp 2+e, meta-GGA); the epilogue multiplies by
-// the companion slabs (H_s,d / phi_d / S_s,de), sums over the 128 points and scatters per atom:
-//   grad[A][d] += f * sum_p sum_{mu in A} companion_d[p, mu] * acc[p, mu]
-// which is  -2 sum_{mu in A, nu} D_{mu nu} V_d(mu, nu)  of dft_gradient_kernels.cpp:540-592 without ever forming V_d.
+// The factorised forms below run on a COPY of gemm_xd_body (k_density.cu) rather than on more MODE branches of it:
+// folding them into gemm_xd_body changed nothing in its SASS instruction mix but cost the tuned D-form density kernel
+// 2.5 % (101.4 -> 103.9 ms on valinomycin) through a different instruction order.
 // MODE 2 / 3: the factorised ("MO") form of the density for callers that also hand over the occupied orbitals
 // (D2_s = C_s C_s^T; the reference's seam receives `mo`, which carries both):
 //   MODE 2   psi_a = phi_a . C_loc   (128 x nocc, K = nb; B gathered along k through the leaf's index list)
@@ -74,7 +33,7 @@ __device__ __forceinline__ void red_add_f64(double *addr, double v) {
 // MODE 4 / 5: the same factorisation for the XC nuclear gradient (acc = A . D_s^T = (A C)(C^T) for the symmetric D2 = C C^T):
 //   MODE 4   psi_A = A . C_loc with A = G_s or phi_e (stored to the tile's psi slab; A = phi reuses the density's psi)
 //   MODE 5   X = psi_A . C_loc^T followed by the per-atom gradient epilogue of MODE 1
-template <int MODE> __device__ __forceinline__ void gemm_xd_body(const BuildParams &P, const DensItem it, double *smem) {
+template <int MODE> __device__ __forceinline__ void gemm_mo_body(const BuildParams &P, const DensItem it, double *smem) {
   const TileDesc t = P.tiles[it.tile];
   if ((MODE == 1 || MODE == 4 || MODE == 5) && P.leaf_skip[t.leaf]) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -91,7 +50,8 @@ template <int MODE> __device__ __forceinline__ void gemm_xd_body(const BuildPara
   const int a_slab = (MODE == 0 || MODE == 2)
                          ? it.acomp
                          : (it.acomp == 0 ? 0 : (it.acomp == 1 ? P.slab_G + it.spin : it.acomp - 1));
-  const double *Ag = FROM_PSI ? P.scratch + t.psi_off + static_cast<size_t>(it.spin) * psi_slab
+  const long long psi_off = (TO_PSI || FROM_PSI) ? P.tile_psi_off[it.tile] : 0;
+  const double *Ag = FROM_PSI ? P.scratch + psi_off + static_cast<size_t>(it.spin) * psi_slab
                               : P.scratch + t.scr_off + static_cast<size_t>(a_slab) * slab;
   const double *Dm = MODE == 0 ? (it.acomp == 0 ? P.Drho : P.Dtau)[it.spin]
                                : (MODE == 1 ? P.DT[it.spin] : (TO_PSI ? P.moC[it.spin] : P.moCT[it.spin]));
@@ -201,7 +161,7 @@ template <int MODE> __device__ __forceinline__ void gemm_xd_body(const BuildPara
 
   if (TO_PSI) {
     if (MODE == 4 || it.acomp == 0) { // psi tile -> the tile's psi slab (padding columns carry exact zeros)
-      double *ps = P.scratch + t.psi_off + static_cast<size_t>(it.spin) * psi_slab +
+      double *ps = P.scratch + psi_off + static_cast<size_t>(it.spin) * psi_slab +
                    static_cast<size_t>(n0 + wn * 32 + 2 * tig) * TILE_P + wm * 32 + gid;
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni)
@@ -283,29 +243,21 @@ template <int MODE> __device__ __forceinline__ void gemm_xd_body(const BuildPara
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2) k_density(BuildParams P, const DensItem *__restrict__ items) {
-  extern __shared__ __align__(16) double smem[];
-  gemm_xd_body<0>(P, items[blockIdx.x], smem);
-}
 __global__ void __launch_bounds__(NTHREADS, 2) k_mo_psi(BuildParams P, const DensItem *__restrict__ items) {
   extern __shared__ __align__(16) double smem[];
-  gemm_xd_body<2>(P, items[blockIdx.x], smem);
+  gemm_mo_body<2>(P, items[blockIdx.x], smem);
 }
 __global__ void __launch_bounds__(NTHREADS, 2) k_mo_density(BuildParams P, const DensItem *__restrict__ items) {
   extern __shared__ __align__(16) double smem[];
-  gemm_xd_body<3>(P, items[blockIdx.x], smem);
+  gemm_mo_body<3>(P, items[blockIdx.x], smem);
 }
 __global__ void __launch_bounds__(NTHREADS, 2) k_mo_grad_psi(BuildParams P, const DensItem *__restrict__ items) {
   extern __shared__ __align__(16) double smem[];
-  gemm_xd_body<4>(P, items[blockIdx.x], smem);
+  gemm_mo_body<4>(P, items[blockIdx.x], smem);
 }
 __global__ void __launch_bounds__(NTHREADS, 2) k_mo_xc_gradient(BuildParams P, const DensItem *__restrict__ items) {
   extern __shared__ __align__(16) double smem[];
-  gemm_xd_body<5>(P, items[blockIdx.x], smem);
-}
-__global__ void __launch_bounds__(NTHREADS, 2) k_xc_gradient(BuildParams P, const DensItem *__restrict__ items) {
-  extern __shared__ __align__(16) double smem[];
-  gemm_xd_body<1>(P, items[blockIdx.x], smem);
+  gemm_mo_body<5>(P, items[blockIdx.x], smem);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -509,15 +461,23 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_vxc_resident(BuildParams P, con
     }
     if (kc == NKC - 1 && !(P.debug & 1)) {
       // scatter-add this warp's 16 x 64 block of Ktmp_loc into the full matrix (dft.h:361-369)
-      const double sf = (symmetric && (ib + 1) * GM <= n0) ? 2.0 : 1.0; // strictly above the diagonal: stands for both halves
+      if (symmetric && (ib + 1) * GM <= n0) { // strictly above the diagonal: the block stands for both halves
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) {
+            acc[mi][ni][0] *= 2.0;
+            acc[mi][ni][1] *= 2.0;
+          }
+      }
 #pragma unroll
       for (int ni = 0; ni < 8; ++ni) {
         const int2 gc = *reinterpret_cast<const int2 *>(scol + ni * 8 + 2 * tig);
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi) {
           if (grow[mi] >= 0) {
-            if (gc.x >= 0) red_add_f64(Kt + static_cast<size_t>(gc.x) * P.ldD + grow[mi], sf * acc[mi][ni][0]);
-            if (gc.y >= 0) red_add_f64(Kt + static_cast<size_t>(gc.y) * P.ldD + grow[mi], sf * acc[mi][ni][1]);
+            if (gc.x >= 0) red_add_f64(Kt + static_cast<size_t>(gc.x) * P.ldD + grow[mi], acc[mi][ni][0]);
+            if (gc.y >= 0) red_add_f64(Kt + static_cast<size_t>(gc.y) * P.ldD + grow[mi], acc[mi][ni][1]);
           }
         }
       }
@@ -541,16 +501,6 @@ void launch_vxc_resident(const BuildParams &P, const VxcItem *items, int nitems,
   k_vxc_resident<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
 }
 
-void launch_density(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
-  if (nitems <= 0) return;
-  static bool configured = false;
-  const int smem_bytes = GSTAGES * D_STAGE * sizeof(double);
-  if (!configured) {
-    cudaFuncSetAttribute(k_density, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    configured = true;
-  }
-  k_density<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
-}
 
 void launch_mo_psi(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
   if (nitems <= 0) return;
@@ -615,16 +565,6 @@ void launch_transpose_rect(const double *in, double *out, int nrow, int ncol, in
   k_transpose_rect<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(in, out, nrow, ncol, ld_in, ld_out);
 }
 
-void launch_grad_gemm(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
-  if (nitems <= 0) return;
-  static bool configured = false;
-  const int smem_bytes = GSTAGES * D_STAGE * sizeof(double);
-  if (!configured) {
-    cudaFuncSetAttribute(k_xc_gradient, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    configured = true;
-  }
-  k_xc_gradient<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
-}
 
 __global__ void k_transpose(const double *__restrict__ D, double *__restrict__ DT, int n, int ld) {
   __shared__ double tl[32][33];

@@ -225,6 +225,7 @@ struct occ_xc_handle {
   double mo_executed_flops = 0.0; // DMMA flops one MO-form build really issues (density side)
   // post-SCF VV10 (allocated on first use)
   std::vector<size_t> h_tile_src; // sorted index of the first point of each tile
+  std::vector<long long> h_tile_psi_off;
   size_t npts_total = 0;          // points of the caller's whole grid (orig_index range)
   int world = 1;
   size_t *d_tile_src = nullptr;
@@ -516,6 +517,7 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
   h->world = world;
   if (h->nleaves == 0) h->nb_min = 0;
 
+  h->h_tile_psi_off.assign(std::max(h->ntiles, 1), 0);
   // ---- batches of consecutive leaves under the workspace budget; per-phase work lists ----
   std::vector<CollocItem> colloc;
   std::vector<DensItem> dens, gitems, gradit, densmo, psi, xpsi, gpsi_w[5], gx_w[5], gradd;
@@ -537,7 +539,7 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
         for (int k = 0; k < ld.ntiles; ++k) {
           h->h_tiles[ld.tile0 + k].scr_off = static_cast<long long>(used);
           used += static_cast<size_t>(nslab) * h->h_tiles[ld.tile0 + k].nbp * TILE_P;
-          h->h_tiles[ld.tile0 + k].psi_off = static_cast<long long>(used);
+          h->h_tile_psi_off[ld.tile0 + k] = static_cast<long long>(used);
           used += psi_doubles;
         }
         nt += ld.ntiles;
@@ -725,6 +727,7 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
     rc |= dev_upload(h, &dg, gitems);
     rc |= dev_upload(h, &dv, vxc);
     rc |= dev_upload(h, &dgr, gradit);
+    rc |= dev_upload(h, &P.tile_psi_off, h->h_tile_psi_off);
     if (h->mo) {
       const DensItem *d1 = nullptr, *d2 = nullptr, *d3 = nullptr;
       rc |= dev_upload(h, &d1, densmo);

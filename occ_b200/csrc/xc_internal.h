@@ -27,7 +27,6 @@ struct TileDesc {
   int bf_off;        // offset of the leaf's local->global bf map in bf_index[]
   int sh_off, nsh;   // the leaf's significant shells in shell_list[] / shell_col[]
   long long scr_off; // offset (doubles) of phi_0 in the batch workspace; phi_c at scr_off + c * nbp * 128
-  long long psi_off; // offset of the tile's psi slabs (MO-form density): psi_s at psi_off + s * noccp * 128
 };
 
 struct LeafDesc {
@@ -100,13 +99,15 @@ struct BuildParams {
   int slab_H;            // first H slab: H[s][d] at slab_H + 3 s + d      (GGA / meta-GGA)
   int slab_S;            // first S slab: S[s][de] at slab_S + 6 s + de    (meta-GGA), de in xx,xy,xz,yy,yz,zz order
   double grad_factor;    // -2, or -4 for LDA (dft_gradient_kernels.cpp:27-45 carries no 1/2 on vrho)
+  int debug; // developer switches for timing experiments (options.reserved[0]): 1 = no Vxc scatter, 2 = no density epilogue
   // ---- MO-form density (handles created with the occupied-orbital counts) ----
   const double *moC[2];  // C_s: nbf x nocc_s column-major (ld = ldC), D2_s = C_s C_s^T
   const double *moCT[2]; // C_s^T: nocc_s x nbf column-major (ld = ldCT)
   int ldC, ldCT;
   int mo_nocc[2];
   int mo_noccp;          // psi slab width: max nocc rounded up to 64
-  int debug; // developer switches for timing experiments (options.reserved[0]): 1 = no Vxc scatter, 2 = no density epilogue
+  const long long *tile_psi_off; // [ntiles] offset of the tile's psi slabs: psi_s at tile_psi_off[tile] + s * noccp * 128
+                                 // (kept out of TileDesc: its layout feeds the register allocation of the tuned D-form kernel)
 };
 
 // ---- post-SCF VV10: per-point arrays in the REFERENCE's point order ----

@@ -6,10 +6,10 @@ code = r'''
 import sys; sys.path.insert(0, %r)
 from scripts.gpu_experiments import run
 run("valinomycin", "def2-tzvp", "b3lyp", 1, 4096, lanes=1, reps=1)
-run("h2o_32", "def2-svp", "b3lyp", 2, 4096, lanes=1, reps=1)
+run("valinomycin", "def2-tzvp", "b3lyp", 1, 4096, lanes=1, reps=1)
 ''' % ROOT
 vdir = os.path.join(ROOT, "occ_b200", "variants")
-libs = [None] + sorted(os.path.join(vdir, f) for f in os.listdir(vdir))
+libs = [None] + sorted(os.path.join(vdir, f) for f in os.listdir(vdir)) + [None]
 for lib in libs:
     env = dict(os.environ)
     if lib: env["OCC_XC_B200_LIB"] = lib
