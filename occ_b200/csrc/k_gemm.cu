@@ -1,4 +1,5 @@
-// k_gemm.cu — the two FP64 tensor-core contractions of the XC build.
+// k_gemm.cu — the Vxc contraction (k_vxc_resident) and small matrix helpers.  The density contraction described
+// below lives in k_density.cu (D form) and k_mo.cu (factorised form); the overview is kept here.
 //
 //   density  (reference: occ::density::evaluate_density, src/gto/density.cpp:8-166)
 //       X = phi_a . D_loc  (128 points x nb, K = nb), immediately row-dotted with the AO slabs:
@@ -243,22 +244,6 @@ template <int MODE> __device__ __forceinline__ void gemm_mo_body(const BuildPara
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2) k_mo_psi(BuildParams P, const DensItem *__restrict__ items) {
-  extern __shared__ __align__(16) double smem[];
-  gemm_mo_body<2>(P, items[blockIdx.x], smem);
-}
-__global__ void __launch_bounds__(NTHREADS, 2) k_mo_density(BuildParams P, const DensItem *__restrict__ items) {
-  extern __shared__ __align__(16) double smem[];
-  gemm_mo_body<3>(P, items[blockIdx.x], smem);
-}
-__global__ void __launch_bounds__(NTHREADS, 2) k_mo_grad_psi(BuildParams P, const DensItem *__restrict__ items) {
-  extern __shared__ __align__(16) double smem[];
-  gemm_mo_body<4>(P, items[blockIdx.x], smem);
-}
-__global__ void __launch_bounds__(NTHREADS, 2) k_mo_xc_gradient(BuildParams P, const DensItem *__restrict__ items) {
-  extern __shared__ __align__(16) double smem[];
-  gemm_mo_body<5>(P, items[blockIdx.x], smem);
-}
 
 // ------------------------------------------------------------------------------------------------
 // G slab: G_s = c0 phi + cx phi_x + cy phi_y + cz phi_z  (the bracket of xc_potential_matrix.cpp:33-39 / :86-99),
@@ -502,68 +487,8 @@ void launch_vxc_resident(const BuildParams &P, const VxcItem *items, int nitems,
 }
 
 
-void launch_mo_psi(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
-  if (nitems <= 0) return;
-  static bool configured = false;
-  const int smem_bytes = GSTAGES * D_STAGE * sizeof(double);
-  if (!configured) {
-    cudaFuncSetAttribute(k_mo_psi, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    configured = true;
-  }
-  k_mo_psi<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
-}
-void launch_mo_density(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
-  if (nitems <= 0) return;
-  static bool configured = false;
-  const int smem_bytes = GSTAGES * D_STAGE * sizeof(double);
-  if (!configured) {
-    cudaFuncSetAttribute(k_mo_density, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    configured = true;
-  }
-  k_mo_density<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
-}
 
-void launch_mo_grad_psi(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
-  if (nitems <= 0) return;
-  static bool configured = false;
-  const int smem_bytes = GSTAGES * D_STAGE * sizeof(double);
-  if (!configured) {
-    cudaFuncSetAttribute(k_mo_grad_psi, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    configured = true;
-  }
-  k_mo_grad_psi<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
-}
-void launch_mo_grad_gemm(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
-  if (nitems <= 0) return;
-  static bool configured = false;
-  const int smem_bytes = GSTAGES * D_STAGE * sizeof(double);
-  if (!configured) {
-    cudaFuncSetAttribute(k_mo_xc_gradient, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    configured = true;
-  }
-  k_mo_xc_gradient<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
-}
 
-// rectangular transpose: out (ncol x nrow, ld_out) = in (nrow x ncol, ld_in)^T, column-major
-__global__ void k_transpose_rect(const double *__restrict__ in, double *__restrict__ out, int nrow, int ncol, int ld_in,
-                                 int ld_out) {
-  __shared__ double tl[32][33];
-  const int bi = blockIdx.x * 32, bj = blockIdx.y * 32, tx = threadIdx.x, ty = threadIdx.y;
-  for (int r = ty; r < 32; r += 8) {
-    const int i = bi + tx, j = bj + r;
-    tl[r][tx] = (i < nrow && j < ncol) ? in[static_cast<size_t>(j) * ld_in + i] : 0.0;
-  }
-  __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    const int j = bj + tx, i = bi + r; // out(j, i) = in(i, j)
-    if (i < nrow && j < ncol) out[static_cast<size_t>(i) * ld_out + j] = tl[tx][r];
-  }
-}
-void launch_transpose_rect(const double *in, double *out, int nrow, int ncol, int ld_in, int ld_out, void *stream) {
-  if (nrow <= 0 || ncol <= 0) return;
-  dim3 grid((nrow + 31) / 32, (ncol + 31) / 32);
-  k_transpose_rect<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(in, out, nrow, ncol, ld_in, ld_out);
-}
 
 
 __global__ void k_transpose(const double *__restrict__ D, double *__restrict__ DT, int n, int ld) {
