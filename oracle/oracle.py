@@ -345,3 +345,143 @@ def vv10(basis: Basis, pts, w, D2, b=6.0, Cpar=0.01, nthreads=None):
     if rc:
         raise RuntimeError("orc_vv10 failed")
     return {"energy": e.value, "K": K, "rho": rho4, "F": fuw[0], "U": fuw[1], "W": fuw[2]}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# COSX seminumerical exchange (oracle/src/cosx.cpp): SURVEY 8(f) rank 2
+# ---------------------------------------------------------------------------------------------------------
+class CosxStatsT(C.Structure):
+    _fields_ = [("nbatches", C.c_size_t), ("nskipped_batches", C.c_size_t), ("pair_evals", C.c_size_t),
+                ("dense_flops", C.c_double), ("npairs", C.c_size_t)]
+
+
+def cosx_boys(x, m):
+    lib().orc_cosx_boys.restype = C.c_double
+    return lib().orc_cosx_boys(C.c_double(x), C.c_int(m))
+
+
+def cosx_boys_reference(x, m):
+    lib().orc_cosx_boys_reference.restype = C.c_double
+    return lib().orc_cosx_boys_reference(C.c_double(x), C.c_int(m))
+
+
+def cosx_ecoeffs_1d(la, lb, a, b, XAB):
+    out = np.zeros((la + 1, lb + 1, la + lb + 1))
+    lib().orc_cosx_ecoeffs_1d(C.c_int(la), C.c_int(lb), C.c_double(a), C.c_double(b), C.c_double(XAB), _p(out))
+    return out
+
+
+def cosx_rints(L, p, PC):
+    out = np.zeros((L + 1) * (L + 2) * (L + 3) // 6)
+    lib().orc_cosx_rints(C.c_int(L), C.c_double(p), C.c_double(PC[0]), C.c_double(PC[1]), C.c_double(PC[2]), _p(out))
+    return out
+
+
+def cosx_esp_pair(la, lb, ea, eb, ca, cb, A, B, spherical, pts, omega=0.0):
+    """ESPEvaluator::evaluate for one shell pair: V (npts, na, nb)"""
+    ea, eb, ca, cb, A, B = (np.ascontiguousarray(x, dtype=np.float64) for x in (ea, eb, ca, cb, A, B))
+    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+    na = lib().orc_nbf_shell(C.c_int(la), C.c_int(int(spherical)))
+    nb = lib().orc_nbf_shell(C.c_int(lb), C.c_int(int(spherical)))
+    V = np.zeros((len(pts), na, nb))
+    lib().orc_cosx_esp_pair(C.c_int(la), C.c_int(lb), C.c_int(len(ea)), C.c_int(len(eb)), _p(ea), _p(eb), _p(ca), _p(cb),
+                            _p(A), _p(B), C.c_int(int(spherical)), C.c_size_t(len(pts)), _p(pts), C.c_double(omega),
+                            _p(V))
+    return V
+
+
+def cosx_pairs(basis: Basis):
+    """significant shell pairs (p >= q) in the reference's registration order, with centre and extent"""
+    lib().orc_cosx_pairs.restype = C.c_size_t
+    n = lib().orc_cosx_pairs(basis.ref, None, None, None)
+    pq = np.zeros((n, 2), dtype=np.int32)
+    cen = np.zeros((n, 3))
+    ext = np.zeros(n)
+    lib().orc_cosx_pairs(basis.ref, _p(pq), _p(cen), _p(ext))
+    return pq, cen, ext
+
+
+def cosx_overlap(basis: Basis):
+    S = np.zeros((basis.nbf, basis.nbf), order="F")
+    lib().orc_cosx_overlap(basis.ref, _p(S))
+    return S
+
+
+def cosx_atom_grids(pts, info):
+    """atom offsets (natoms + 1) of a grid in atom-grid order (the layout of SemiNumericalExchange::m_atom_grids)"""
+    return np.concatenate([[0], np.cumsum(info["atom_npts"])]).astype(np.uint64)
+
+
+def cosx_numerical_overlap(basis: Basis, atom_off, pts, w):
+    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    atom_off = np.ascontiguousarray(atom_off, dtype=np.uint64)
+    Sn = np.zeros((basis.nbf, basis.nbf), order="F")
+    lib().orc_cosx_numerical_overlap(basis.ref, C.c_int(len(atom_off) - 1), _p(atom_off), _p(pts), _p(w), _p(Sn))
+    return Sn
+
+
+def cosx_overlap_projector(basis: Basis, atom_off, pts, w):
+    """m_overlap_projector = Sn.ldlt().solve(S)  (seminumerical_exchange.cpp:258-262)"""
+    S = cosx_overlap(basis)
+    Sn = cosx_numerical_overlap(basis, atom_off, pts, w)
+    return np.asfortranarray(np.linalg.solve(Sn, S)), S, Sn
+
+
+def cosx_K_for_density(basis: Basis, atom_off, pts, w, D2q, precision=np.finfo(float).eps, omega=0.0, margin=1.0):
+    """compute_K_for_density (seminumerical_exchange.cpp:817-828): raw K of one projected density"""
+    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    atom_off = np.ascontiguousarray(atom_off, dtype=np.uint64)
+    D2q = np.asfortranarray(D2q, dtype=np.float64)
+    K = np.zeros((basis.nbf, basis.nbf), order="F")
+    st = CosxStatsT()
+    rc = lib().orc_cosx_K_for_density(basis.ref, C.c_int(len(atom_off) - 1), _p(atom_off), _p(pts), _p(w), _p(D2q),
+                                      C.c_double(precision), C.c_double(omega), C.c_double(margin), _p(K), C.byref(st))
+    if rc:
+        raise RuntimeError("orc_cosx_K_for_density failed")
+    return K, {f: getattr(st, f) for f, _ in CosxStatsT._fields_}
+
+
+def cosx_compute_K(basis: Basis, atom_off, pts, w, projector, D, unrestricted=False, precision=np.finfo(float).eps,
+                   omega=0.0, margin=1.0):
+    """SemiNumericalExchange::compute_K, ESP mode (seminumerical_exchange.cpp:517-545 restricted, 617-660
+    unrestricted). D is mo.D: (nbf, nbf), or (2 nbf, nbf) with the alpha block on top."""
+    nbf = basis.nbf
+    stats = []
+    if not unrestricted:
+        K, st = cosx_K_for_density(basis, atom_off, pts, w, projector @ (2.0 * D), precision, omega, margin)
+        return np.asfortranarray(0.25 * (K + K.T)), [st]
+    out = np.zeros((2 * nbf, nbf), order="F")
+    for s in range(2):
+        Ds = 2.0 * D[s * nbf:(s + 1) * nbf]
+        K, st = cosx_K_for_density(basis, atom_off, pts, w, projector @ Ds, precision, omega, margin)
+        out[s * nbf:(s + 1) * nbf] = 0.5 * (K + K.T)
+        stats.append(st)
+    return out, stats
+
+
+def ref_boys_table():
+    R = ref_lib()
+    n = R.occ_ref_boys_table(None)
+    t = np.zeros(n)
+    R.occ_ref_boys_table(_p(t))
+    return t
+
+
+def ref_boys(x, m):
+    R = ref_lib()
+    R.occ_ref_boys.restype = C.c_double
+    return R.occ_ref_boys(C.c_double(x), C.c_int(m))
+
+
+def ref_ecoeffs_1d(la, lb, a, b, XAB):
+    out = np.zeros((la + 1, lb + 1, la + lb + 1))
+    ref_lib().occ_ref_ecoeffs_1d(C.c_int(la), C.c_int(lb), C.c_double(a), C.c_double(b), C.c_double(XAB), _p(out))
+    return out
+
+
+def ref_rints(L, p, PC):
+    out = np.zeros((L + 1) * (L + 2) * (L + 3) // 6)
+    ref_lib().occ_ref_rints(C.c_int(L), C.c_double(p), C.c_double(PC[0]), C.c_double(PC[1]), C.c_double(PC[2]), _p(out))
+    return out
