@@ -1,0 +1,166 @@
+"""Host-side mirror of occ::qm::cosx::SemiNumericalExchange (include/occ/qm/seminumerical_exchange.h:104-205,
+src/qm/seminumerical_exchange.cpp), ESP mode: the seminumerical (COSX) exchange build, SURVEY.md 8(f) rank 2.
+
+    sgx = SemiNumericalExchange(basis, GridSettings.for_sgx(50))     # or atom_grids=(offsets, points, weights)
+    K = sgx.compute_K(D)                                             # D = mo.D (restricted: nbf x nbf)
+    K = sgx.compute_K(D, unrestricted=True)                          # D: (2 nbf x nbf), alpha block on top
+    sgx.set_range_separated_omega(0.3); K_lr = sgx.compute_K(D)      # erf(omega r)/r
+    K = sgx.compute_K_range_separated(D, alpha, beta, omega)         # fused two-operator sweep
+
+Everything numerical runs in the CUDA library (include/occ_cosx_b200.h); the overlap projector is formed here from
+the library's numerical and analytic overlaps (seminumerical_exchange.cpp:258-262). No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import BasisArrays, check, lib, ptr
+from .aobasis import AOBasis
+from .grid import GridSettings, MolecularGrid
+
+
+class CosxOptionsT(C.Structure):
+    _fields_ = [("margin", C.c_double), ("density_threshold", C.c_double), ("pair_threshold", C.c_double),
+                ("batch_bytes", C.c_size_t), ("device", C.c_int), ("collect_stats", C.c_int), ("rank", C.c_int),
+                ("world_size", C.c_int), ("reserved", C.c_int * 4)]
+
+
+class CosxInfoT(C.Structure):
+    _fields_ = [("nbf", C.c_int), ("nsh", C.c_int), ("natoms", C.c_int), ("npts", C.c_size_t), ("nbatches", C.c_size_t),
+                ("npairs", C.c_size_t), ("nprimitive_pairs", C.c_size_t), ("device_bytes", C.c_size_t),
+                ("pair_evals", C.c_size_t), ("skipped_batches", C.c_size_t), ("dense_flops", C.c_double),
+                ("gemm_flops", C.c_double), ("ms_collocate", C.c_double), ("ms_fgemm", C.c_double),
+                ("ms_esp", C.c_double), ("ms_kgemm", C.c_double), ("launches", C.c_size_t), ("gemm_calls", C.c_size_t)]
+
+
+def sgx_grid_settings(angular_points: int = 50, radial_precision: float = 1e-5) -> GridSettings:
+    """GridSettings::for_sgx (src/numint/grid_settings.cpp:59-69): one angular order for every shell, loose radial
+    precision, no first-row reduction. The native producer prunes with the NWChem scheme, which is uniform below 50
+    points (grid_utils.cpp:240-243); at 50 and above the innermost shells are thinned."""
+    return GridSettings(angular_points, angular_points, radial_precision, False, True)
+
+
+class SemiNumericalExchange:
+    def __init__(self, basis: AOBasis, settings: GridSettings | None = None, atom_grids=None, device: int = -1,
+                 margin: float = 1.0, collect_stats: bool = False, batch_bytes: int = 0, rank: int = 0,
+                 world_size: int = 1, projector: np.ndarray | None | str = "auto"):
+        """SemiNumericalExchange(basis, grid settings) (seminumerical_exchange.cpp:245-275). atom_grids, when given, is
+        (offsets[natoms+1], points (N,3), weights (N,)) — the reference's m_atom_grids."""
+        L = lib()
+        self.basis = basis
+        self.omega = 0.0
+        if atom_grids is None:
+            mg = MolecularGrid(basis, settings or sgx_grid_settings())
+            pts, w = mg.points()
+            counts = [mg.atom_info(a)[0] for a in range(mg.natoms)]
+            mg.close()
+            offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint64)
+        else:
+            offs, pts, w = atom_grids
+        self.atom_offsets = np.ascontiguousarray(offs, dtype=np.uint64)
+        self.points = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+        self.weights = np.ascontiguousarray(w, dtype=np.float64)
+        self._ba = BasisArrays(basis.as_arrays())
+        opt = CosxOptionsT(margin, 0.0, 0.0, batch_bytes, device, int(collect_stats), rank, world_size)
+        self._h = C.c_void_p()
+        L.occ_cosx_destroy.restype = None
+        L.occ_cosx_destroy.argtypes = [C.c_void_p]
+        for f in ("occ_cosx_compute_K", "occ_cosx_K_for_density", "occ_cosx_compute_K_range_separated",
+                  "occ_cosx_numerical_overlap", "occ_cosx_analytic_overlap", "occ_cosx_set_projector",
+                  "occ_cosx_get_info"):
+            getattr(L, f).restype = C.c_int
+        L.occ_cosx_compute_K.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_void_p]
+        L.occ_cosx_K_for_density.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]
+        L.occ_cosx_compute_K_range_separated.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double,
+                                                         C.c_double, C.c_void_p]
+        L.occ_cosx_numerical_overlap.argtypes = [C.c_void_p, C.c_void_p]
+        L.occ_cosx_analytic_overlap.argtypes = [C.c_void_p, C.c_void_p]
+        L.occ_cosx_set_projector.argtypes = [C.c_void_p, C.c_void_p]
+        L.occ_cosx_get_info.argtypes = [C.c_void_p, C.c_void_p]
+        P0 = None if isinstance(projector, str) or projector is None else np.asfortranarray(projector, dtype=np.float64)
+        check(L.occ_cosx_create(self._ba.ref, C.c_int(len(self.atom_offsets) - 1), ptr(self.atom_offsets),
+                                ptr(self.points), ptr(self.weights), ptr(P0) if P0 is not None else None,
+                                C.byref(opt), C.byref(self._h)))
+        self.overlap_projector = P0
+        if isinstance(projector, str):
+            # m_overlap_projector = m_numerical_overlap.ldlt().solve(m_overlap)  (seminumerical_exchange.cpp:258-262);
+            # with sharded batches the numerical overlap has to be summed over ranks by the caller first
+            if world_size > 1:
+                raise RuntimeError("SemiNumericalExchange: pass the overlap projector explicitly when sharding")
+            S, Sn = self.analytic_overlap(), self.compute_overlap_matrix()
+            self.set_projector(np.linalg.solve(Sn, S))
+
+    # -- reference API -------------------------------------------------------------------------------------
+    def set_range_separated_omega(self, omega: float):
+        self.omega = float(omega)
+
+    def range_separated_omega(self) -> float:
+        return self.omega
+
+    def compute_K(self, D: np.ndarray, precision: float = np.finfo(np.float64).eps, unrestricted: bool = False):
+        nbf = self.basis.nbf
+        nspin = 2 if unrestricted else 1
+        D = np.asfortranarray(D, dtype=np.float64)
+        if D.shape != (nspin * nbf, nbf):
+            raise RuntimeError(f"compute_K: density matrix of shape {D.shape}, expected {(nspin * nbf, nbf)}")
+        K = np.zeros((nspin * nbf, nbf), order="F")
+        check(lib().occ_cosx_compute_K(self._h, nspin - 1, ptr(D), precision, self.omega, ptr(K)))
+        return K
+
+    def compute_K_range_separated(self, D, alpha: float, beta: float, omega: float,
+                                  precision: float = np.finfo(np.float64).eps):
+        nbf = self.basis.nbf
+        D = np.asfortranarray(D, dtype=np.float64)
+        if D.shape != (nbf, nbf):
+            raise RuntimeError("compute_K_range_separated is restricted only")
+        K = np.zeros((nbf, nbf), order="F")
+        check(lib().occ_cosx_compute_K_range_separated(self._h, ptr(D), alpha, beta, omega, precision, ptr(K)))
+        return K
+
+    def compute_K_for_density(self, D2q, precision: float = np.finfo(np.float64).eps):
+        nbf = self.basis.nbf
+        D2q = np.asfortranarray(D2q, dtype=np.float64)
+        K = np.zeros((nbf, nbf), order="F")
+        check(lib().occ_cosx_K_for_density(self._h, ptr(D2q), precision, self.omega, ptr(K)))
+        return K
+
+    def compute_overlap_matrix(self):
+        S = np.zeros((self.basis.nbf, self.basis.nbf), order="F")
+        check(lib().occ_cosx_numerical_overlap(self._h, ptr(S)))
+        return S
+
+    def analytic_overlap(self):
+        S = np.zeros((self.basis.nbf, self.basis.nbf), order="F")
+        check(lib().occ_cosx_analytic_overlap(self._h, ptr(S)))
+        return S
+
+    def set_projector(self, P):
+        self.overlap_projector = None if P is None else np.asfortranarray(P, dtype=np.float64)
+        check(lib().occ_cosx_set_projector(self._h, ptr(self.overlap_projector) if P is not None else None))
+
+    def num_grid_points(self) -> int:
+        return len(self.weights)
+
+    def num_batches(self) -> int:
+        return int(self.info()["nbatches"])
+
+    def num_atoms(self) -> int:
+        return len(self.atom_offsets) - 1
+
+    def info(self) -> dict:
+        t = CosxInfoT()
+        check(lib().occ_cosx_get_info(self._h, C.byref(t)))
+        return {f: getattr(t, f) for f, _ in CosxInfoT._fields_}
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().occ_cosx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

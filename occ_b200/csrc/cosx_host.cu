@@ -1,0 +1,764 @@
+// cosx_host.cu — host orchestration of the B200 seminumerical exchange (COSX) build; C ABI of include/occ_cosx_b200.h.
+//
+// Reference: occ::qm::cosx::SemiNumericalExchange (src/qm/seminumerical_exchange.cpp), ESP mode.
+//   create():   what the reference precomputes per geometry — significant shell pairs (integral_engine.h:250-281,
+//               seminumerical_exchange.cpp:293-331), their McMurchie-Davidson E tables, prefactors, centres and extents
+//               (include/occ/ints/ecoeffs.h:150-198, kernels.h:293-340, src/ints/esp.cpp:85-100), the grid batches with
+//               their bounding spheres (:676-720) and the Boys table (boys.h:191-330) — built on the host, once.
+//   compute():  per SCF iteration, per chunk of batches: AO values (k_collocate) -> batch skip flags -> F = Phi D2q
+//               (library DGEMM) -> ESP + contraction kernels, one launch per (la, lb) class (k_cosx_esp) -> K' += Phi^T G
+//               (library DGEMM) -> K = c (K' + K'^T).
+// The two dense products are plain GEMMs and go to cuBLAS (loaded with dlopen so that the XC entry points do not depend
+// on it); everything else is this library's own kernels. No CPU fallback.
+#include "../../include/occ_cosx_b200.h"
+#include "cosx_internal.h"
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <cublas_v2.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+
+using namespace xcb;
+
+int occ_xc_set_error(const char *msg); // xc_host.cu
+static int fail(const std::string &m) { return occ_xc_set_error(m.c_str()); }
+#define CUDA_TRY(expr)                                                                                       \
+  do {                                                                                                       \
+    cudaError_t e__ = (expr);                                                                                \
+    if (e__ != cudaSuccess)                                                                                  \
+      return fail(std::string("CUDA error: ") + cudaGetErrorString(e__) + " in " #expr);                    \
+  } while (0)
+
+namespace {
+
+constexpr double kPi = 3.14159265358979323846;
+
+// ---- cuBLAS through dlopen ----
+struct Blas {
+  void *lib = nullptr;
+  cublasHandle_t h = nullptr;
+  cublasStatus_t (*create)(cublasHandle_t *) = nullptr;
+  cublasStatus_t (*destroy)(cublasHandle_t) = nullptr;
+  cublasStatus_t (*set_stream)(cublasHandle_t, cudaStream_t) = nullptr;
+  cublasStatus_t (*dgemm)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int, const double *,
+                          const double *, int, const double *, int, const double *, double *, int) = nullptr;
+  cublasStatus_t (*dgemm_sb)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int, const double *,
+                             const double *, int, long long, const double *, int, long long, const double *, double *,
+                             int, long long, int) = nullptr;
+  int open() {
+    const char *names[] = {"libcublas.so.12", "/usr/local/cuda/lib64/libcublas.so.12", "libcublas.so", nullptr};
+    for (int i = 0; names[i] && !lib; ++i) lib = dlopen(names[i], RTLD_NOW | RTLD_LOCAL);
+    if (!lib) return fail("occ_cosx_create: cannot load libcublas (needed for the two dense products of the COSX build)");
+    create = reinterpret_cast<decltype(create)>(dlsym(lib, "cublasCreate_v2"));
+    destroy = reinterpret_cast<decltype(destroy)>(dlsym(lib, "cublasDestroy_v2"));
+    set_stream = reinterpret_cast<decltype(set_stream)>(dlsym(lib, "cublasSetStream_v2"));
+    dgemm = reinterpret_cast<decltype(dgemm)>(dlsym(lib, "cublasDgemm_v2"));
+    dgemm_sb = reinterpret_cast<decltype(dgemm_sb)>(dlsym(lib, "cublasDgemmStridedBatched"));
+    if (!create || !destroy || !set_stream || !dgemm || !dgemm_sb) return fail("occ_cosx_create: libcublas lacks a symbol");
+    if (create(&h) != CUBLAS_STATUS_SUCCESS) return fail("occ_cosx_create: cublasCreate failed");
+    return 0;
+  }
+  void close() {
+    if (h && destroy) destroy(h);
+    h = nullptr; // the library stays loaded for the life of the process
+  }
+};
+
+inline int ncart(int l) { return (l + 1) * (l + 2) / 2; }
+inline int nfun(int l, int pure) { return pure ? 2 * l + 1 : ncart(l); }
+
+// include/occ/ints/ecoeffs.h:150-198 — E_t^{ij} of one Cartesian direction, layout t + (la+lb+1) (j + (lb+1) i)
+void e_table(int la, int lb, double a, double b, double XAB, double *E) {
+  const int P1 = la + lb + 1;
+  auto at = [&](int i, int j, int t) -> double & { return E[t + P1 * (j + (lb + 1) * i)]; };
+  std::fill(E, E + (la + 1) * (lb + 1) * P1, 0.0);
+  const double p = a + b, mu = a * b / p, inv_2p = 0.5 / p;
+  const double XPA = b / p * XAB, XPB = -a / p * XAB;
+  at(0, 0, 0) = std::exp(-mu * XAB * XAB);
+  for (int j = 0; j < lb; ++j) {
+    for (int t = 0; t <= j; ++t) {
+      double val = XPB * at(0, j, t);
+      if (t > 0) val += inv_2p * at(0, j, t - 1);
+      if (t < j) val += (t + 1) * at(0, j, t + 1);
+      at(0, j + 1, t) += val;
+    }
+    at(0, j + 1, j + 1) = inv_2p * at(0, j, j);
+  }
+  for (int i = 0; i < la; ++i)
+    for (int j = 0; j <= lb; ++j) {
+      const int max_t = i + j;
+      for (int t = 0; t <= max_t; ++t) {
+        double val = XPA * at(i, j, t);
+        if (t > 0) val += inv_2p * at(i, j, t - 1);
+        if (t < max_t) val += (t + 1) * at(i, j, t + 1);
+        at(i + 1, j, t) += val;
+      }
+      at(i + 1, j, max_t + 1) = inv_2p * at(i, j, max_t);
+    }
+}
+
+// gto.cpp:289-400: fully normalised c2s (l >= 2: sqrt((2l+1)/4pi) x Racah table; l = 1: (y, z, x); l = 0: 1)
+std::vector<double> c2s_full(int l) {
+  const int ns = 2 * l + 1, nc = ncart(l);
+  std::vector<double> T(static_cast<size_t>(ns) * nc, 0.0);
+  const double *M = c2s_racah_table(l);
+  const double f = l >= 2 ? std::sqrt((2 * l + 1) / (4.0 * kPi)) : 1.0;
+  for (size_t i = 0; i < T.size(); ++i) T[i] = f * M[i];
+  return T;
+}
+
+// boys.h:142-160
+double boys_maclaurin(double T, int m) {
+  double denom = m + 0.5, term = std::exp(-T) / (2.0 * denom), old_term = 0.0, sum = term;
+  do {
+    denom += 1.0;
+    old_term = term;
+    term = old_term * T / denom;
+    sum += term;
+  } while (term > sum * 1e-17 || old_term < term);
+  return sum;
+}
+
+// boys.h:191-330: order-7 Chebyshev interpolant per segment of width 1/7 on [0, 36), 16 orders, stored as monomials in
+// xd = 7x - segment - 1/2. The Chebyshev coefficients come from the discrete orthogonality of the 8 Chebyshev nodes
+// (the reference solves the equivalent 8 x 8 collocation system by LU).
+std::vector<double> boys_table() {
+  constexpr int N = 8, MaxM = 16, Segments = 252;
+  const double Delta = 36.0 / Segments;
+  std::vector<double> t(static_cast<size_t>(N) * MaxM * (Segments + 1), 0.0);
+  double nodes[N], Tp[N][N] = {};
+  for (int k = 0; k < N; ++k) nodes[k] = std::cos(((2 * k + 1) * kPi) / (2.0 * N)) / 2.0;
+  Tp[0][0] = 1.0;
+  Tp[1][1] = 2.0; // T_1(2 x) = 2 x
+  for (int k = 2; k < N; ++k)
+    for (int j = 0; j < N; ++j) {
+      if (j > 0) Tp[k][j] += 4.0 * Tp[k - 1][j - 1];
+      Tp[k][j] -= Tp[k - 2][j];
+    }
+  for (int seg = 0; seg < Segments; ++seg)
+    for (int m = 0; m < MaxM; ++m) {
+      double f[N], cheb[N], mono[N] = {};
+      for (int n = 0; n < N; ++n) f[n] = boys_maclaurin(seg * Delta + (nodes[n] + 0.5) * Delta, m);
+      for (int k = 0; k < N; ++k) {
+        double s = 0.0;
+        for (int n = 0; n < N; ++n) s += f[n] * std::cos(k * (2 * n + 1) * kPi / (2.0 * N));
+        cheb[k] = s * (k == 0 ? 1.0 : 2.0) / N;
+      }
+      for (int k = 0; k < N; ++k)
+        for (int j = 0; j <= k; ++j) mono[j] += cheb[k] * Tp[k][j];
+      std::memcpy(&t[(static_cast<size_t>(seg) * MaxM + m) * N], mono, sizeof(mono));
+    }
+  return t;
+}
+
+struct HostPair {
+  CosxPair d;
+  int la, lb;
+};
+
+} // namespace
+
+struct occ_cosx_handle {
+  int device = 0, nbf = 0, nsh = 0, pure = 0, natoms = 0, nbp = 0;
+  size_t npts = 0;
+  int ntiles = 0, tiles_per_chunk = 1, nruns = 1;
+  double margin = 1.0, density_threshold = 1e-6;
+  bool collect = false;
+  std::vector<void *> allocs;
+  size_t alloc_bytes = 0;
+  BuildParams B = {};      // what k_collocate reads
+  CollocItem *d_items = nullptr;
+  int *d_counts = nullptr, *d_skip = nullptr, *d_shell_size = nullptr;
+  double *d_tc[4] = {nullptr, nullptr, nullptr, nullptr};
+  double *d_pw_ovl = nullptr; // weights with the last point of every atom grid zeroed (numerical overlap quirk)
+  CosxPair *d_pairs = nullptr;
+  double *d_pool = nullptr, *d_boys = nullptr, *d_c2s = nullptr;
+  unsigned char *d_active = nullptr;
+  unsigned long long *d_stats = nullptr;
+  double *d_phi = nullptr, *d_F = nullptr, *d_G = nullptr;
+  double *d_D = nullptr, *d_D2q = nullptr, *d_Kraw = nullptr, *d_K = nullptr, *d_proj = nullptr;
+  size_t npairs = 0, nprim_pairs = 0;
+  struct ClassRange {
+    int la, lb, pair0, npairs;
+  };
+  std::vector<ClassRange> classes;
+  std::vector<double> S_analytic;
+  std::vector<int> h_counts;
+  Blas blas;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  occ_cosx_info_t info = {};
+};
+
+template <class T> static int dev_alloc(occ_cosx_handle *h, T **ptr, size_t count) {
+  void *p = nullptr;
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  CUDA_TRY(cudaMalloc(&p, bytes));
+  h->allocs.push_back(p);
+  h->alloc_bytes += bytes;
+  *ptr = static_cast<T *>(p);
+  return 0;
+}
+template <class T> static int dev_upload(occ_cosx_handle *h, T **ptr, const std::vector<T> &v) {
+  if (dev_alloc(h, ptr, v.size())) return 1;
+  if (!v.empty()) CUDA_TRY(cudaMemcpy(*ptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" {
+
+void occ_cosx_destroy(occ_cosx_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  h->blas.close();
+  for (void *p : h->allocs) cudaFree(p);
+  for (auto &e : h->ev)
+    if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int occ_cosx_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_offsets, const double *pts_xyz,
+                    const double *weights, const double *overlap_projector, const occ_cosx_options_t *opt,
+                    occ_cosx_handle **out) {
+  if (!basis || !atom_offsets || !pts_xyz || !weights || !out || natoms < 1) return fail("occ_cosx_create: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("occ_cosx_create: no CUDA device available (this library has no CPU fallback)");
+  int device = (opt && opt->device >= 0) ? opt->device : -1;
+  if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+  if (device >= ndev) return fail("occ_cosx_create: device ordinal out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  const int world = (opt && opt->world_size > 1) ? opt->world_size : 1;
+  const int rank = world > 1 ? opt->rank : 0;
+  if (rank < 0 || rank >= world) return fail("occ_cosx_create: rank outside [0, world_size)");
+  const int nsh = basis->nsh, pure = basis->pure ? 1 : 0;
+  std::vector<int> first_bf(nsh), shell_size(nsh);
+  int nbf = 0;
+  for (int s = 0; s < nsh; ++s) {
+    if (basis->l[s] < 0 || basis->l[s] > COSX_MAX_L)
+      return fail("occ_cosx_create: shells up to l = 3 are supported by the COSX build");
+    first_bf[s] = nbf;
+    shell_size[s] = nfun(basis->l[s], pure);
+    nbf += shell_size[s];
+  }
+  occ_cosx_handle *h = new occ_cosx_handle;
+  h->device = device;
+  h->nbf = nbf;
+  h->nsh = nsh;
+  h->pure = pure;
+  h->natoms = natoms;
+  h->nbp = (nbf + NB_PAD - 1) / NB_PAD * NB_PAD;
+  h->margin = (opt && opt->margin > 0.0) ? opt->margin : 1.0;
+  h->density_threshold = (opt && opt->density_threshold > 0.0) ? opt->density_threshold : 1e-6;
+  h->collect = opt && opt->collect_stats;
+  const double pair_threshold = (opt && opt->pair_threshold > 0.0) ? opt->pair_threshold : 1e-12;
+  const size_t batch_bytes = (opt && opt->batch_bytes) ? opt->batch_bytes : (size_t(4096) << 20);
+  h->npts = atom_offsets[natoms] - atom_offsets[0];
+#define CHECK(x)                                                                                             \
+  do {                                                                                                       \
+    if (x) {                                                                                                 \
+      occ_cosx_destroy(h);                                                                                   \
+      return 1;                                                                                              \
+    }                                                                                                        \
+  } while (0)
+
+  // ---- shell pairs, grouped by (la, lb) class, registration order inside a class ----
+  std::vector<double> Tfull[COSX_MAX_L + 1];
+  for (int l = 0; l <= COSX_MAX_L; ++l) Tfull[l] = c2s_full(l);
+  std::vector<HostPair> hp[16];
+  std::vector<double> pool[16];
+  h->S_analytic.assign(static_cast<size_t>(nbf) * nbf, 0.0);
+  std::vector<double> Ex, Ey, Ez, Sc, Ss, tmp;
+  for (int p = 0; p < nsh; ++p)
+    for (int q = 0; q <= p; ++q) {
+      const int la = basis->l[p], lb = basis->l[q], L1 = la + lb + 1, ne = (la + 1) * (lb + 1) * L1;
+      const double *A = basis->origin + 3 * p, *Bc = basis->origin + 3 * q;
+      const int cls = la * 4 + lb, stride = COSX_PRIM_HDR + 3 * ne;
+      const int nca = ncart(la), ncb = ncart(lb);
+      const double sph_fac = (la == 0 ? 0.282094791773878143 : (la == 1 ? 0.488602511902919921 : 1.0)) *
+                             (lb == 0 ? 0.282094791773878143 : (lb == 1 ? 0.488602511902919921 : 1.0)); // kernels.h:11-18
+      std::vector<double> rec_all;
+      Sc.assign(static_cast<size_t>(nca) * ncb, 0.0);
+      double p_min = 1.0e300, cen[3] = {0, 0, 0};
+      Ex.resize(ne);
+      Ey.resize(ne);
+      Ez.resize(ne);
+      for (int ia = 0; ia < basis->nprim[p]; ++ia)
+        for (int ib = 0; ib < basis->nprim[q]; ++ib) {
+          const double a = basis->exps[basis->prim_off[p] + ia], b = basis->exps[basis->prim_off[q] + ib];
+          const double ca = basis->coefs[basis->prim_off[p] + ia], cb = basis->coefs[basis->prim_off[q] + ib];
+          const double pe = a + b;
+          const double P[3] = {(a * A[0] + b * Bc[0]) / pe, (a * A[1] + b * Bc[1]) / pe, (a * A[2] + b * Bc[2]) / pe};
+          const double pref = 2.0 * kPi / pe * sph_fac * ca * cb; // kernels.h:325
+          e_table(la, lb, a, b, Bc[0] - A[0], Ex.data());
+          e_table(la, lb, a, b, Bc[1] - A[1], Ey.data());
+          e_table(la, lb, a, b, Bc[2] - A[2], Ez.data());
+          if (pe < p_min) { // esp.cpp:85-100: first minimum wins
+            p_min = pe;
+            std::memcpy(cen, P, sizeof(cen));
+          }
+          // overlap block (esp.cpp:127-146): prefactor sqrt(pi/p)/2 E_000
+          const double of = pref * std::sqrt(kPi / pe) / 2.0;
+          int ra = 0;
+          for (int ax = la; ax >= 0; --ax)
+            for (int ay = la - ax; ay >= 0; --ay, ++ra) {
+              const int az = la - ax - ay;
+              int rb = 0;
+              for (int bx = lb; bx >= 0; --bx)
+                for (int by = lb - bx; by >= 0; --by, ++rb) {
+                  const int bz = lb - bx - by;
+                  Sc[ra * ncb + rb] += of * Ex[(ax * (lb + 1) + bx) * L1] * Ey[(ay * (lb + 1) + by) * L1] *
+                                       Ez[(az * (lb + 1) + bz) * L1];
+                }
+            }
+          const size_t o = rec_all.size();
+          rec_all.resize(o + stride);
+          rec_all[o] = pe;
+          rec_all[o + 1] = P[0];
+          rec_all[o + 2] = P[1];
+          rec_all[o + 3] = P[2];
+          rec_all[o + 4] = pref;
+          for (int i = 0; i < ne; ++i) {
+            rec_all[o + COSX_PRIM_HDR + i] = pref * Ex[i];
+            rec_all[o + COSX_PRIM_HDR + ne + i] = Ey[i];
+            rec_all[o + COSX_PRIM_HDR + 2 * ne + i] = Ez[i];
+          }
+        }
+      // block in the basis' own (Cartesian or spherical) functions
+      const int np = shell_size[p], nq = shell_size[q];
+      if (pure) {
+        const std::vector<double> &Ta = Tfull[la], &Tb = Tfull[lb];
+        tmp.assign(static_cast<size_t>(np) * ncb, 0.0);
+        for (int i = 0; i < np; ++i)
+          for (int k = 0; k < nca; ++k)
+            for (int j = 0; j < ncb; ++j) tmp[i * ncb + j] += Ta[i * nca + k] * Sc[k * ncb + j];
+        Ss.assign(static_cast<size_t>(np) * nq, 0.0);
+        for (int i = 0; i < np; ++i)
+          for (int j = 0; j < nq; ++j)
+            for (int k = 0; k < ncb; ++k) Ss[i * nq + j] += tmp[i * ncb + k] * Tb[j * ncb + k];
+      } else {
+        Ss = Sc;
+      }
+      double n2 = 0.0;
+      for (int i = 0; i < np; ++i)
+        for (int j = 0; j < nq; ++j) {
+          const double v = Ss[i * nq + j];
+          n2 += v * v;
+          h->S_analytic[(first_bf[p] + i) + static_cast<size_t>(first_bf[q] + j) * nbf] = v;
+          h->S_analytic[(first_bf[q] + j) + static_cast<size_t>(first_bf[p] + i) * nbf] = v;
+        }
+      const bool same = A[0] == Bc[0] && A[1] == Bc[1] && A[2] == Bc[2]; // integral_engine.h:262-266
+      if (!same && std::sqrt(n2) < pair_threshold) continue;
+      HostPair e;
+      e.la = la;
+      e.lb = lb;
+      e.d.p = p;
+      e.d.q = q;
+      e.d.bfp = first_bf[p];
+      e.d.bfq = first_bf[q];
+      e.d.nprim = basis->nprim[p] * basis->nprim[q];
+      e.d.off = static_cast<int>(pool[cls].size());
+      e.d.cx = cen[0];
+      e.d.cy = cen[1];
+      e.d.cz = cen[2];
+      e.d.extent = std::sqrt(27.631021115928547 / p_min);
+      pool[cls].insert(pool[cls].end(), rec_all.begin(), rec_all.end());
+      hp[cls].push_back(e);
+      h->nprim_pairs += e.d.nprim;
+    }
+  std::vector<CosxPair> pairs_all;
+  std::vector<double> pool_all;
+  for (int cls = 0; cls < 16; ++cls) {
+    if (hp[cls].empty()) continue;
+    occ_cosx_handle::ClassRange cr = {cls / 4, cls % 4, static_cast<int>(pairs_all.size()), static_cast<int>(hp[cls].size())};
+    const size_t base = pool_all.size();
+    if (base + pool[cls].size() > 0x7fffffffULL) {
+      occ_cosx_destroy(h);
+      return fail("occ_cosx_create: primitive pool exceeds 2^31 doubles");
+    }
+    for (auto &e : hp[cls]) {
+      e.d.off += static_cast<int>(base);
+      pairs_all.push_back(e.d);
+    }
+    pool_all.insert(pool_all.end(), pool[cls].begin(), pool[cls].end());
+    h->classes.push_back(cr);
+  }
+  h->npairs = pairs_all.size();
+
+  // ---- grid batches: blocks of 128 consecutive points of every atom grid (:676-699), dealt round-robin to ranks ----
+  std::vector<double> px, py, pz, pw, pwo, tc[4];
+  std::vector<TileDesc> tiles;
+  size_t gbatch = 0;
+  const size_t base0 = atom_offsets[0];
+  for (int a = 0; a < natoms; ++a) {
+    const size_t n = atom_offsets[a + 1] - atom_offsets[a];
+    for (size_t s0 = 0; s0 < n; s0 += TILE_P, ++gbatch) {
+      if (static_cast<int>(gbatch % world) != rank) continue;
+      const size_t cnt = std::min<size_t>(TILE_P, n - s0), g0 = atom_offsets[a] - base0 + s0;
+      double c[3] = {0, 0, 0};
+      for (size_t i = 0; i < cnt; ++i)
+        for (int d = 0; d < 3; ++d) c[d] += pts_xyz[3 * (g0 + i) + d];
+      for (int d = 0; d < 3; ++d) c[d] /= static_cast<double>(cnt);
+      double rad = 0.0;
+      for (size_t i = 0; i < cnt; ++i) {
+        const double dx = pts_xyz[3 * (g0 + i)] - c[0], dy = pts_xyz[3 * (g0 + i) + 1] - c[1],
+                     dz = pts_xyz[3 * (g0 + i) + 2] - c[2];
+        rad = std::max(rad, std::sqrt(dx * dx + dy * dy + dz * dz));
+      }
+      for (int d = 0; d < 3; ++d) tc[d].push_back(c[d]);
+      tc[3].push_back(rad);
+      for (size_t i = 0; i < TILE_P; ++i) {
+        const size_t g = g0 + (i < cnt ? i : 0);
+        px.push_back(pts_xyz[3 * g]);
+        py.push_back(pts_xyz[3 * g + 1]);
+        pz.push_back(pts_xyz[3 * g + 2]);
+        pw.push_back(i < cnt ? weights[g] : 0.0);
+        // compute_overlap_matrix (:349-352) never reaches the last point of an atom grid
+        pwo.push_back((i < cnt && s0 + i + 1 < n) ? weights[g] : 0.0);
+      }
+      TileDesc t = {};
+      t.leaf = static_cast<int>(tiles.size());
+      t.pt0 = static_cast<int>(tiles.size()) * TILE_P;
+      t.count = static_cast<int>(cnt);
+      t.nb = nbf;
+      t.nbp = h->nbp;
+      t.sh_off = 0;
+      t.nsh = nsh;
+      tiles.push_back(t);
+      h->h_counts.push_back(static_cast<int>(cnt));
+    }
+  }
+  h->ntiles = static_cast<int>(tiles.size());
+  const size_t slab_bytes = static_cast<size_t>(h->nbp) * TILE_P * sizeof(double);
+  h->tiles_per_chunk = static_cast<int>(std::max<size_t>(1, std::min<size_t>(batch_bytes / (3 * slab_bytes), std::max(h->ntiles, 1))));
+  for (int t = 0; t < h->ntiles; ++t)
+    tiles[t].scr_off = static_cast<long long>(t % h->tiles_per_chunk) * h->nbp * TILE_P;
+  h->nruns = (nsh + 15) / 16;
+  std::vector<CollocItem> items;
+  for (int t = 0; t < h->ntiles; ++t)
+    for (int r = 0; r < h->nruns; ++r) items.push_back({t, r * 16, std::min(nsh, (r + 1) * 16), r == h->nruns - 1 ? 1 : 0});
+
+  // ---- device state ----
+  CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess && fail("occ_cosx_create: stream"));
+  for (auto &e : h->ev) CHECK(cudaEventCreate(&e) != cudaSuccess && fail("occ_cosx_create: event"));
+  CHECK(h->blas.open());
+  h->blas.set_stream(h->blas.h, h->stream);
+  upload_default_c2s();
+  {
+    int *d_l = nullptr, *d_np = nullptr, *d_po = nullptr, *d_fb = nullptr, *d_list = nullptr;
+    double *d_or = nullptr, *d_ex = nullptr, *d_co = nullptr;
+    TileDesc *d_tiles = nullptr;
+    size_t nprim_tot = 0;
+    for (int s = 0; s < nsh; ++s) nprim_tot = std::max<size_t>(nprim_tot, basis->prim_off[s] + basis->nprim[s]);
+    std::vector<int> list(nsh);
+    for (int s = 0; s < nsh; ++s) list[s] = s;
+    CHECK(dev_upload(h, &d_l, std::vector<int>(basis->l, basis->l + nsh)));
+    CHECK(dev_upload(h, &d_np, std::vector<int>(basis->nprim, basis->nprim + nsh)));
+    CHECK(dev_upload(h, &d_po, std::vector<int>(basis->prim_off, basis->prim_off + nsh)));
+    CHECK(dev_upload(h, &d_fb, first_bf));
+    CHECK(dev_upload(h, &d_list, list));
+    CHECK(dev_upload(h, &d_or, std::vector<double>(basis->origin, basis->origin + 3 * nsh)));
+    CHECK(dev_upload(h, &d_ex, std::vector<double>(basis->exps, basis->exps + nprim_tot)));
+    CHECK(dev_upload(h, &d_co, std::vector<double>(basis->coefs, basis->coefs + nprim_tot)));
+    CHECK(dev_upload(h, &d_tiles, tiles));
+    h->B.basis = {d_l, d_np, d_po, d_fb, d_or, d_ex, d_co, pure};
+    h->B.tiles = d_tiles;
+    h->B.shell_list = d_list;
+    h->B.shell_col = d_fb;
+    h->B.nbf = nbf;
+    h->B.nspin = 1;
+    h->B.deriv = 0;
+    h->B.ncomp = 1;
+  }
+  {
+    double *d = nullptr;
+    CHECK(dev_upload(h, &d, px));
+    h->B.px = d;
+    CHECK(dev_upload(h, &d, py));
+    h->B.py = d;
+    CHECK(dev_upload(h, &d, pz));
+    h->B.pz = d;
+    CHECK(dev_upload(h, &d, pw));
+    h->B.pw = d;
+  }
+  CHECK(dev_upload(h, &h->d_pw_ovl, pwo));
+  for (int d = 0; d < 4; ++d) CHECK(dev_upload(h, &h->d_tc[d], tc[d]));
+  CHECK(dev_upload(h, &h->d_items, items));
+  CHECK(dev_upload(h, &h->d_counts, h->h_counts));
+  CHECK(dev_alloc(h, &h->d_skip, h->ntiles));
+  CHECK(dev_upload(h, &h->d_shell_size, shell_size));
+  CHECK(dev_upload(h, &h->d_pairs, pairs_all));
+  CHECK(dev_upload(h, &h->d_pool, pool_all));
+  CHECK(dev_upload(h, &h->d_boys, boys_table()));
+  {
+    std::vector<double> c2s(9 + 30 + 70, 0.0);
+    const double p1[9] = {0, 1, 0, 0, 0, 1, 1, 0, 0}; // gto.cpp:296-305: (py, pz, px)
+    std::copy(p1, p1 + 9, c2s.begin());
+    std::copy(Tfull[2].begin(), Tfull[2].end(), c2s.begin() + 9);
+    std::copy(Tfull[3].begin(), Tfull[3].end(), c2s.begin() + 39);
+    CHECK(dev_upload(h, &h->d_c2s, c2s));
+  }
+  CHECK(dev_alloc(h, &h->d_active, h->npairs));
+  CHECK(dev_alloc(h, &h->d_stats, 32));
+  const size_t slab_d = static_cast<size_t>(h->nbp) * TILE_P * h->tiles_per_chunk;
+  CHECK(dev_alloc(h, &h->d_phi, slab_d));
+  CHECK(dev_alloc(h, &h->d_F, slab_d));
+  CHECK(dev_alloc(h, &h->d_G, slab_d));
+  const size_t n2 = static_cast<size_t>(nbf) * nbf;
+  CHECK(dev_alloc(h, &h->d_D, 2 * n2));
+  CHECK(dev_alloc(h, &h->d_D2q, n2));
+  CHECK(dev_alloc(h, &h->d_Kraw, n2));
+  CHECK(dev_alloc(h, &h->d_K, 2 * n2));
+  CHECK(dev_alloc(h, &h->d_proj, n2));
+  h->B.scratch = h->d_phi;
+  *out = h;
+  if (occ_cosx_set_projector(h, overlap_projector)) {
+    *out = nullptr;
+    occ_cosx_destroy(h);
+    return 1;
+  }
+#undef CHECK
+  h->info.nbf = nbf;
+  h->info.nsh = nsh;
+  h->info.natoms = natoms;
+  h->info.npts = h->npts;
+  h->info.nbatches = h->ntiles;
+  h->info.npairs = h->npairs;
+  h->info.nprimitive_pairs = h->nprim_pairs;
+  h->info.device_bytes = h->alloc_bytes;
+  return 0;
+}
+
+int occ_cosx_set_projector(occ_cosx_handle *h, const double *P) {
+  if (!h) return fail("occ_cosx_set_projector: null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t n = h->nbf;
+  std::vector<double> I;
+  if (!P) {
+    I.assign(n * n, 0.0);
+    for (size_t i = 0; i < n; ++i) I[i + i * n] = 1.0;
+    P = I.data();
+  }
+  CUDA_TRY(cudaMemcpy(h->d_proj, P, n * n * sizeof(double), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// seminumerical_exchange_sweep (:660-815) for one projected density already on the device
+static int sweep(occ_cosx_handle *h, const double *D2q, double precision, double w_full, double w_lr, double omega,
+                 double *Kraw) {
+  const int nbf = h->nbf, nbp = h->nbp;
+  cudaStream_t st = h->stream;
+  const size_t n2 = static_cast<size_t>(nbf) * nbf;
+  CUDA_TRY(cudaMemsetAsync(Kraw, 0, n2 * sizeof(double), st));
+  launch_cosx_pair_flags(h->d_pairs, h->d_shell_size, static_cast<int>(h->npairs), D2q, nbf, h->density_threshold,
+                         h->d_active, st);
+  h->info.launches += 1;
+  if (h->collect) CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, 32 * sizeof(unsigned long long), st));
+  CosxParams P = {};
+  P.pairs = h->d_pairs;
+  P.pool = h->d_pool;
+  P.pair_active = h->d_active;
+  P.tile_skip = h->d_skip;
+  P.counts = h->d_counts;
+  P.tcx = h->d_tc[0];
+  P.tcy = h->d_tc[1];
+  P.tcz = h->d_tc[2];
+  P.trad = h->d_tc[3];
+  P.px = h->B.px;
+  P.py = h->B.py;
+  P.pz = h->B.pz;
+  P.pw = h->B.pw;
+  P.F = h->d_F;
+  P.G = h->d_G;
+  P.boys = h->d_boys;
+  P.c2s = h->d_c2s;
+  P.nbp = nbp;
+  P.pure = h->pure;
+  P.margin = h->margin;
+  P.w_full = w_full;
+  P.w_lr = w_lr;
+  P.omega = omega;
+  P.stats = h->collect ? h->d_stats : nullptr;
+  const double one = 1.0, zero = 0.0;
+  const long long slab = static_cast<long long>(nbp) * TILE_P;
+  float ms[4] = {0, 0, 0, 0};
+  for (int t0 = 0; t0 < h->ntiles; t0 += h->tiles_per_chunk) {
+    const int nt = std::min(h->tiles_per_chunk, h->ntiles - t0);
+    if (h->collect) cudaEventRecord(h->ev[0], st);
+    launch_collocate(h->B, h->d_items + static_cast<size_t>(t0) * h->nruns, nt * h->nruns, st);
+    launch_cosx_tile_flags(h->d_phi, h->d_counts + t0, nt, nbf, nbp, precision, h->d_skip + t0, st);
+    h->info.launches += 2;
+    if (h->collect) cudaEventRecord(h->ev[1], st);
+    // F_t = Phi_t . D2q for every batch of the chunk (:733-734, the weight is applied when F is read)
+    if (h->blas.dgemm_sb(h->blas.h, CUBLAS_OP_N, CUBLAS_OP_N, TILE_P, nbf, nbf, &one, h->d_phi, TILE_P, slab, D2q, nbf, 0,
+                         &zero, h->d_F, TILE_P, slab, nt) != CUBLAS_STATUS_SUCCESS)
+      return fail("occ_cosx: cublasDgemmStridedBatched failed");
+    h->info.gemm_calls += 1;
+    CUDA_TRY(cudaMemsetAsync(h->d_G, 0, static_cast<size_t>(nt) * slab * sizeof(double), st));
+    if (h->collect) cudaEventRecord(h->ev[2], st);
+    P.tile0 = t0;
+    for (const auto &c : h->classes) {
+      launch_cosx_esp(P, c.la, c.lb, c.pair0, c.npairs, nt, st);
+      h->info.launches += 1;
+    }
+    if (h->collect) cudaEventRecord(h->ev[3], st);
+    // K' += Phi_t^T . G_t (:797; G here is the reference's -Gg)
+    for (int t = 0; t < nt; ++t) {
+      if (h->blas.dgemm(h->blas.h, CUBLAS_OP_T, CUBLAS_OP_N, nbf, nbf, TILE_P, &one, h->d_phi + t * slab, TILE_P,
+                        h->d_G + t * slab, TILE_P, &one, Kraw, nbf) != CUBLAS_STATUS_SUCCESS)
+        return fail("occ_cosx: cublasDgemm failed");
+    }
+    h->info.gemm_calls += nt;
+    if (h->collect) {
+      cudaEventRecord(h->ev[4], st);
+      CUDA_TRY(cudaEventSynchronize(h->ev[4]));
+      for (int i = 0; i < 4; ++i) {
+        float m = 0;
+        cudaEventElapsedTime(&m, h->ev[i], h->ev[i + 1]);
+        ms[i] += m;
+      }
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  if (h->collect) {
+    unsigned long long st_h[32];
+    CUDA_TRY(cudaMemcpyAsync(st_h, h->d_stats, sizeof(st_h), cudaMemcpyDeviceToHost, st));
+    int skip_n = 0;
+    std::vector<int> sk(h->ntiles);
+    CUDA_TRY(cudaMemcpyAsync(sk.data(), h->d_skip, sizeof(int) * h->ntiles, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int v : sk) skip_n += v;
+    h->info.skipped_batches += skip_n;
+    for (int cls = 0; cls < 16; ++cls) {
+      const int la = cls / 4, lb = cls % 4, L = la + lb;
+      const double nherm = (L + 1) * (L + 2) * (L + 3) / 6.0, nab = static_cast<double>(nfun(la, h->pure)) * nfun(lb, h->pure);
+      h->info.pair_evals += st_h[2 * cls];
+      h->info.dense_flops += 2.0 * nherm * nab * static_cast<double>(st_h[2 * cls + 1]);
+    }
+    h->info.ms_collocate += ms[0];
+    h->info.ms_fgemm += ms[1];
+    h->info.ms_esp += ms[2];
+    h->info.ms_kgemm += ms[3];
+  }
+  double npt_local = 0.0;
+  for (int c : h->h_counts) npt_local += c;
+  h->info.gemm_flops += 4.0 * npt_local * nbf * nbf;
+  return 0;
+}
+
+static void reset_info(occ_cosx_handle *h) {
+  h->info.pair_evals = 0;
+  h->info.skipped_batches = 0;
+  h->info.dense_flops = h->info.gemm_flops = 0.0;
+  h->info.ms_collocate = h->info.ms_fgemm = h->info.ms_esp = h->info.ms_kgemm = 0.0;
+  h->info.launches = 0;
+  h->info.gemm_calls = 0;
+}
+
+int occ_cosx_K_for_density_device(occ_cosx_handle *h, const double *D2q_dev, double precision, double w_full,
+                                  double w_lr, double omega, double *K_dev) {
+  if (!h || !D2q_dev || !K_dev) return fail("occ_cosx_K_for_density_device: null argument");
+  if (w_lr != 0.0 && !(omega > 0.0)) return fail("occ_cosx: the long-range operator needs omega > 0");
+  CUDA_TRY(cudaSetDevice(h->device));
+  reset_info(h);
+  if (sweep(h, D2q_dev, precision, w_full, w_lr, omega, K_dev)) return 1;
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int occ_cosx_K_for_density(occ_cosx_handle *h, const double *D2q, double precision, double omega, double *K) {
+  if (!h || !D2q || !K) return fail("occ_cosx_K_for_density: null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t n2 = static_cast<size_t>(h->nbf) * h->nbf;
+  CUDA_TRY(cudaMemcpyAsync(h->d_D2q, D2q, n2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  reset_info(h);
+  if (sweep(h, h->d_D2q, precision, omega > 0.0 ? 0.0 : 1.0, omega > 0.0 ? 1.0 : 0.0, omega, h->d_Kraw)) return 1;
+  CUDA_TRY(cudaMemcpyAsync(K, h->d_Kraw, n2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// compute_K_restricted / compute_K_unrestricted (:517-545, 617-660) and compute_K_range_separated (:830-860)
+static int compute_K_impl(occ_cosx_handle *h, int kind, const double *D, double precision, double w_full, double w_lr,
+                          double omega, double *K) {
+  if (!h || !D || !K) return fail("occ_cosx_compute_K: null argument");
+  if (kind != 0 && kind != 1)
+    return fail("occ_cosx_compute_K: kind must be 0 (restricted) or 1 (unrestricted); general spinorbitals are not built");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int nbf = h->nbf, nspin = kind + 1, ld = nspin * nbf;
+  const size_t n2 = static_cast<size_t>(nbf) * nbf;
+  cudaStream_t st = h->stream;
+  CUDA_TRY(cudaMemcpyAsync(h->d_D, D, nspin * n2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  reset_info(h);
+  const double two = 2.0, zero = 0.0;
+  for (int s = 0; s < nspin; ++s) {
+    // D2q = P . (2 D_s): the factor 2 is D2 = 2 D for restricted (:524) and the stored 1/2 for unrestricted (:632-633)
+    if (h->blas.dgemm(h->blas.h, CUBLAS_OP_N, CUBLAS_OP_N, nbf, nbf, nbf, &two, h->d_proj, nbf, h->d_D + s * nbf, ld, &zero,
+                      h->d_D2q, nbf) != CUBLAS_STATUS_SUCCESS)
+      return fail("occ_cosx: cublasDgemm failed");
+    h->info.gemm_calls += 1;
+    if (sweep(h, h->d_D2q, precision, w_full, w_lr, omega, h->d_Kraw)) return 1;
+    launch_cosx_symmetrize(h->d_Kraw, nbf, kind == 0 ? 0.25 : 0.5, h->d_K + s * nbf, ld, st);
+    h->info.launches += 1;
+  }
+  CUDA_TRY(cudaMemcpyAsync(K, h->d_K, nspin * n2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int occ_cosx_compute_K(occ_cosx_handle *h, int kind, const double *D, double precision, double omega, double *K) {
+  if (omega < 0.0) return fail("occ_cosx_compute_K: omega must be >= 0");
+  return compute_K_impl(h, kind, D, precision, omega > 0.0 ? 0.0 : 1.0, omega > 0.0 ? 1.0 : 0.0, omega, K);
+}
+
+int occ_cosx_compute_K_range_separated(occ_cosx_handle *h, const double *D, double alpha, double beta, double omega,
+                                       double precision, double *K) {
+  if (!(omega > 0.0)) return fail("occ_cosx_compute_K_range_separated: omega must be > 0");
+  return compute_K_impl(h, 0, D, precision, alpha + beta, -beta, omega, K);
+}
+
+int occ_cosx_analytic_overlap(occ_cosx_handle *h, double *S) {
+  if (!h || !S) return fail("occ_cosx_analytic_overlap: null argument");
+  std::memcpy(S, h->S_analytic.data(), h->S_analytic.size() * sizeof(double));
+  return 0;
+}
+
+// compute_overlap_matrix (:336-380): Sn = sum_batches Phi^T (w Phi), the last point of every atom grid left out
+int occ_cosx_numerical_overlap(occ_cosx_handle *h, double *Sn) {
+  if (!h || !Sn) return fail("occ_cosx_numerical_overlap: null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int nbf = h->nbf, nbp = h->nbp;
+  const size_t n2 = static_cast<size_t>(nbf) * nbf;
+  cudaStream_t st = h->stream;
+  CUDA_TRY(cudaMemsetAsync(h->d_Kraw, 0, n2 * sizeof(double), st));
+  const double one = 1.0;
+  const long long slab = static_cast<long long>(nbp) * TILE_P;
+  for (int t0 = 0; t0 < h->ntiles; t0 += h->tiles_per_chunk) {
+    const int nt = std::min(h->tiles_per_chunk, h->ntiles - t0);
+    launch_collocate(h->B, h->d_items + static_cast<size_t>(t0) * h->nruns, nt * h->nruns, st);
+    launch_cosx_scale_weights(h->d_F, h->d_phi, h->d_pw_ovl + static_cast<size_t>(t0) * TILE_P, nt, nbf, nbp, st);
+    for (int t = 0; t < nt; ++t)
+      if (h->blas.dgemm(h->blas.h, CUBLAS_OP_T, CUBLAS_OP_N, nbf, nbf, TILE_P, &one, h->d_phi + t * slab, TILE_P,
+                        h->d_F + t * slab, TILE_P, &one, h->d_Kraw, nbf) != CUBLAS_STATUS_SUCCESS)
+        return fail("occ_cosx: cublasDgemm failed");
+  }
+  CUDA_TRY(cudaMemcpyAsync(Sn, h->d_Kraw, n2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int occ_cosx_get_info(const occ_cosx_handle *h, occ_cosx_info_t *info) {
+  if (!h || !info) return fail("occ_cosx_get_info: null argument");
+  *info = h->info;
+  return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,60 @@
+// cosx_internal.h — device-side layout of the B200 seminumerical exchange (COSX) build.
+//
+//   batch = tile = <=128 consecutive points of one atom grid (seminumerical_exchange.cpp:676-699)
+//   Phi / F / G of a tile are column-major 128 x nbp slabs (same layout as the XC build's AO slabs):
+//     Phi[col*128 + p] AO values, F = Phi . D2q (unweighted; the quadrature weight is applied when F is read),
+//     G = sum over shell pairs of (w F) . V  — the reference's -Gg (seminumerical_exchange.cpp:787-795)
+//   shell pairs are grouped by class (la, lb); each class is one launch of an ESP kernel instantiated for it.
+#pragma once
+#include "xc_internal.h"
+
+namespace xcb {
+
+constexpr int COSX_MAX_L = 3;
+
+struct CosxPair {
+  int p, q;       // shells, p >= q (registration order of seminumerical_exchange.cpp:293-331)
+  int bfp, bfq;   // first basis function of p / q
+  int nprim;      // primitive pairs
+  int off;        // first double of this pair in the primitive pool
+  double cx, cy, cz, extent; // esp.cpp:85-100
+};
+
+// primitive pool record of a class (la, lb), ne = (la+1)(lb+1)(la+lb+1):
+//   [0] p  [1..3] P  [4] unused  [5 .. 5+ne) prefactor * E^x  [5+ne ..) E^y  [5+2ne ..) E^z      (ecoeffs.h layout)
+constexpr int COSX_PRIM_HDR = 5;
+
+struct CosxParams {
+  const CosxPair *pairs;
+  const double *pool;
+  const unsigned char *pair_active; // density screen of the current D2q (1 = evaluate)
+  const int *tile_skip;             // 1 = batch failed max(phi) < precision
+  const int *counts;                // valid points per tile
+  const double *tcx, *tcy, *tcz, *trad; // batch bounding spheres
+  const double *px, *py, *pz, *pw;  // padded SoA points / weights of all tiles
+  const double *F;                  // chunk slabs
+  double *G;
+  const double *boys;               // Chebyshev table (boys.h layout: [segment][m][8])
+  const double *c2s;                // spherical tables: l = 1 at 0 (3x3), l = 2 at 9 (5x6), l = 3 at 39 (7x10)
+  int tile0;                        // first tile of the chunk (slabs are chunk-relative)
+  int nbp;
+  int pure;
+  double margin;
+  double w_full, w_lr, omega;
+  unsigned long long *stats;        // [0] pair evaluations, [1] sum npt*nprim*nherm*nab of them; may be NULL
+};
+
+void launch_cosx_esp(const CosxParams &P, int la, int lb, int pair0, int npairs, int ntiles, void *stream);
+void launch_cosx_tile_flags(const double *phi, const int *counts, int ntiles, int nbf, int nbp, double precision,
+                            int *tile_skip, void *stream);
+void launch_cosx_pair_flags(const CosxPair *pairs, const int *shell_size, int npairs, const double *D2q, int nbf,
+                            double threshold, unsigned char *active, void *stream);
+void launch_cosx_project_density(const double *P, const double *D, int ldD, int nbf, double scale, double *D2q,
+                                 void *stream); // not used when cuBLAS does the product
+void launch_cosx_symmetrize(const double *Kraw, int nbf, double factor, double *K, int ldK, void *stream);
+void launch_cosx_scale_weights(double *phi_w, const double *phi, const double *pw, int ntiles, int nbf, int nbp,
+                               void *stream);
+void upload_default_c2s();              // xc_host.cu: the collocation kernel's constant table
+const double *c2s_racah_table(int l);   // xc_host.cu: (2l+1) x ncart(l), Racah-normalised, CCA order
+
+} // namespace xcb

@@ -95,6 +95,11 @@ static const C2STable &c2s_table() {
   return t;
 }
 
+namespace xcb {
+void upload_default_c2s() { upload_c2s_table(c2s_table()); }
+const double *c2s_racah_table(int l) { return c2s_table().coef + c2s_table().off[l]; }
+} // namespace xcb
+
 // value of every function of one shell at a point relative to its centre (host; used for the decay extents)
 static void shell_values_host(int l, int pure, int np, const double *coefs, const double *exps, double x, double y,
                               double z, double *out) {

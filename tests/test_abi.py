@@ -77,3 +77,47 @@ def test_header_is_plain_c_and_links_from_c99():
                            "-locc_xc_b200", "-Wl,-rpath," + lib])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip() == "ok", (out.returncode, out.stdout, out.stderr)
+
+
+def cosx_header_symbols():
+    text = open(os.path.join(ROOT, "include", "occ_cosx_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(occ_cosx_[a-zA-Z_0-9]+)\s*\(", text)))
+
+
+def test_cosx_library_exports_every_declared_symbol():
+    from occ_b200 import _lib
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    syms = cosx_header_symbols()
+    assert "occ_cosx_create" in syms and "occ_cosx_compute_K" in syms
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+    assert sorted(_lib.COSX_SYMBOLS) == syms
+
+
+def test_cosx_header_is_plain_c():
+    import subprocess
+    src = os.path.join(ROOT, "tests", "cpp", "abi_cosx_c99.c")
+    exe = os.path.join(ROOT, "tests", "cpp", "abi_cosx_c99")
+    lib = os.path.join(ROOT, "occ_b200")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-o", exe, src, "-L" + lib,
+                           "-locc_xc_b200", "-Wl,-rpath," + lib])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", (out.returncode, out.stdout, out.stderr)
+
+
+def test_cosx_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        return
+    import numpy as np
+    from occ_b200 import aobasis, cosx, molecules
+    Z, pos = molecules.water()
+    b = aobasis.AOBasis.load(Z, pos, "def2-svp")
+    offs = np.array([0, 1, 2, 3], dtype=np.uint64)
+    try:
+        cosx.SemiNumericalExchange(b, atom_grids=(offs, np.zeros((3, 3)), np.ones(3)), projector=None)
+    except RuntimeError as e:
+        assert "CUDA" in str(e)
+    else:
+        raise AssertionError("SemiNumericalExchange() succeeded without a GPU")

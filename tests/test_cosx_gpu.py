@@ -1,0 +1,122 @@
+"""GPU parity of the COSX build (occ_cosx_*, include/occ_cosx_b200.h) against the CPU oracle (oracle/src/cosx.cpp) on
+the same basis, atom grids, projector and density. Tolerance: 1e-9 max-abs on K (north-star Vxc tolerance; the two
+sides differ by summation order, the Boys downward recursion and libm, all at the 1e-14 level)."""
+import numpy as np
+import pytest
+
+from occ_b200 import aobasis, molecules
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _setup(oracle, mol, basis_name, pure, angular=38, radial_precision=1e-5, seed=7, nspin=1):
+    from occ_b200 import cosx
+    O = oracle
+    Z, pos = molecules.MOLECULES[mol]()
+    b = aobasis.AOBasis.load(Z, pos, basis_name, pure=pure)
+    ob = O.Basis(b.as_arrays())
+    gs = O.default_grid_settings(max_angular_points=angular, min_angular_points=angular,
+                                 radial_precision=radial_precision, reduced_first_row_element_grid=0)
+    pts, w, info = O.molecular_grid(Z, pos, ob, gs)
+    off = O.cosx_atom_grids(pts, info)
+    P, S, Sn = O.cosx_overlap_projector(ob, off, pts, w)
+    D = molecules.synthetic_density(b, nspin=nspin, seed=seed) * 0.5   # mo.D carries the factor 1/2
+    sgx = cosx.SemiNumericalExchange(b, atom_grids=(off, pts, w), projector=P, collect_stats=True)
+    return O, b, ob, off, pts, w, P, S, Sn, D, sgx
+
+
+@pytest.mark.parametrize("mol,basis_name,pure", [("water", "3-21g", False), ("water", "def2-svp", False),
+                                                 ("water", "def2-svp", True), ("water", "def2-tzvp", False),
+                                                 ("water", "def2-tzvp", True), ("socl2_na", "def2-svp", True)])
+def test_cosx_K_matches_oracle(oracle, mol, basis_name, pure):
+    O, b, ob, off, pts, w, P, S, Sn, D, sgx = _setup(oracle, mol, basis_name, pure)
+    K = sgx.compute_K(D)
+    Kref, stats = O.cosx_compute_K(ob, off, pts, w, P, D)
+    assert np.abs(Kref).max() > 1e-3
+    assert np.abs(K - Kref).max() < TOL, np.abs(K - Kref).max()
+    info = sgx.info()
+    assert info["pair_evals"] == stats[0]["pair_evals"]
+    assert info["skipped_batches"] == stats[0]["nskipped_batches"]
+    assert info["dense_flops"] == pytest.approx(stats[0]["dense_flops"], rel=1e-12)
+    assert info["npairs"] == stats[0]["npairs"]
+    assert info["launches"] > 0
+    sgx.close()
+
+
+def test_cosx_raw_K_and_overlaps_match_oracle(oracle):
+    O, b, ob, off, pts, w, P, S, Sn, D, sgx = _setup(oracle, "water", "def2-svp", False)
+    assert np.abs(sgx.analytic_overlap() - S).max() < 1e-14
+    assert np.abs(sgx.compute_overlap_matrix() - Sn).max() < 1e-12
+    D2q = P @ (2.0 * D)
+    Kraw = sgx.compute_K_for_density(D2q)
+    Kref, _ = O.cosx_K_for_density(ob, off, pts, w, D2q)
+    assert np.abs(Kraw - Kref).max() < TOL
+    sgx.close()
+
+
+def test_cosx_projector_built_by_the_library(oracle):
+    from occ_b200 import cosx
+    O, b, ob, off, pts, w, P, S, Sn, D, sgx = _setup(oracle, "water", "def2-svp", True)
+    sgx.close()
+    sgx2 = cosx.SemiNumericalExchange(b, atom_grids=(off, pts, w))          # projector = solve(Sn, S) from the GPU overlaps
+    assert np.abs(sgx2.overlap_projector - P).max() < 1e-9
+    K = sgx2.compute_K(D)
+    Kref, _ = O.cosx_compute_K(ob, off, pts, w, P, D)
+    assert np.abs(K - Kref).max() < 1e-8
+    sgx2.close()
+
+
+def test_cosx_unrestricted_matches_oracle(oracle):
+    O, b, ob, off, pts, w, P, S, Sn, D, sgx = _setup(oracle, "water", "def2-svp", False, nspin=2)
+    assert D.shape == (2 * b.nbf, b.nbf)
+    K = sgx.compute_K(D, unrestricted=True)
+    Kref, _ = O.cosx_compute_K(ob, off, pts, w, P, D, unrestricted=True)
+    assert np.abs(K - Kref).max() < TOL
+    sgx.close()
+
+
+def test_cosx_long_range_and_fused_range_separated(oracle):
+    O, b, ob, off, pts, w, P, S, Sn, D, sgx = _setup(oracle, "water", "def2-svp", True)
+    omega, alpha, beta = 0.3, 1.0, -0.842294      # tests/dft_tests.cpp:434-436 (wB97X-style)
+    Kf = sgx.compute_K(D)
+    sgx.set_range_separated_omega(omega)
+    Klr = sgx.compute_K(D)
+    sgx.set_range_separated_omega(0.0)
+    Klr_ref, _ = O.cosx_compute_K(ob, off, pts, w, P, D, omega=omega)
+    assert np.abs(Klr - Klr_ref).max() < TOL
+    assert np.abs(Klr).max() < np.abs(Kf).max()       # erf attenuates (tests/dft_tests.cpp:392-394)
+    Kfused = sgx.compute_K_range_separated(D, alpha, beta, omega)
+    assert np.abs(Kfused - ((alpha + beta) * Kf - beta * Klr)).max() < 1e-10   # tests/dft_tests.cpp:452-456
+    sgx.close()
+
+
+def test_cosx_screens_follow_the_reference(oracle):
+    """A spread-out system so that the geometric pair screen and the density screen both fire; an empty density gives
+    K = 0 with every pair skipped."""
+    O, b, ob, off, pts, w, P, S, Sn, D, sgx = _setup(oracle, "h2o_32", "3-21g", False, angular=14, radial_precision=1e-3)
+    nb = b.nbf
+    Dloc = D.copy()
+    Dloc[np.abs(Dloc) < 2e-3] = 0.0          # sparse density: many pair blocks fall below 1e-6
+    K = sgx.compute_K(Dloc)
+    Kref, stats = O.cosx_compute_K(ob, off, pts, w, P, Dloc)
+    info = sgx.info()
+    assert info["pair_evals"] == stats[0]["pair_evals"]
+    assert info["pair_evals"] < info["npairs"] * info["nbatches"]
+    assert np.abs(K - Kref).max() < TOL
+    K0 = sgx.compute_K(np.zeros((nb, nb)))
+    assert np.abs(K0).max() == 0.0 and sgx.info()["pair_evals"] == 0
+    sgx.close()
+
+
+def test_cosx_sharded_partials_sum_to_K(oracle):
+    from occ_b200 import cosx
+    O, b, ob, off, pts, w, P, S, Sn, D, sgx = _setup(oracle, "water", "def2-svp", False)
+    K = sgx.compute_K(D)
+    sgx.close()
+    parts = []
+    for r in range(3):
+        s = cosx.SemiNumericalExchange(b, atom_grids=(off, pts, w), projector=P, rank=r, world_size=3)
+        parts.append(s.compute_K(D))
+        s.close()
+    assert np.abs(sum(parts) - K).max() < 1e-12
