@@ -1,0 +1,66 @@
+// adapter/occ_cosx_b200.h — header-only C++17 host side over the COSX C ABI (include/occ_cosx_b200.h).
+//
+// Mirrors occ::qm::cosx::SemiNumericalExchange in ESP mode (reference: include/occ/qm/seminumerical_exchange.h:104-205):
+//   SemiNumericalExchangeB200::compute_K(kind, D, K, precision)     <->  Mat compute_K(mo, precision, Schwarz)   :481-515
+//   ...::compute_K_range_separated(D, alpha, beta, omega, K)        <->  compute_K_range_separated               :830-860
+//   ...::set_range_separated_omega / range_separated_omega          <->  same names                              .h:157-158
+//   ...::num_grid_points / num_batches / num_atoms                  <->  same names                              :430-452
+//   errors                                                          <->  std::runtime_error (:489-493)
+// The constructor takes what the reference's constructor leaves in its members: the basis, the Becke-partitioned atom
+// grids (m_atom_grids) and m_overlap_projector.  Matrices cross as raw column-major pointers (Eigen's Mat::data()).
+#pragma once
+#include "../include/occ_cosx_b200.h"
+#include "occ_dft_b200.h"
+#include <cstddef>
+#include <limits>
+#include <stdexcept>
+#include <vector>
+
+namespace occ_b200 {
+
+class SemiNumericalExchangeB200 {
+public:
+  // atom_offsets: natoms + 1 entries delimiting the atom grids in pts (3 x N, column-major = xyz interleaved) / weights
+  SemiNumericalExchangeB200(const BasisArrays &basis, const std::vector<size_t> &atom_offsets, const double *pts,
+                            const double *weights, const double *overlap_projector, double margin = 1.0,
+                            int device = -1)
+      : m_nbf(basis.nbf()), m_natoms(static_cast<int>(atom_offsets.size()) - 1) {
+    occ_cosx_options_t opt = {};
+    opt.margin = margin;
+    opt.device = device;
+    occ_xc_basis_t b = basis.view();
+    check(occ_cosx_create(&b, m_natoms, atom_offsets.data(), pts, weights, overlap_projector, &opt, &m_h));
+  }
+  SemiNumericalExchangeB200(const SemiNumericalExchangeB200 &) = delete;
+  SemiNumericalExchangeB200 &operator=(const SemiNumericalExchangeB200 &) = delete;
+  ~SemiNumericalExchangeB200() { occ_cosx_destroy(m_h); }
+
+  // D = mo.D (nbf x nbf restricted, 2 nbf x nbf unrestricted), K of the same shape
+  void compute_K(SpinorbitalKind kind, const double *D, double *K,
+                 double precision = std::numeric_limits<double>::epsilon()) const {
+    check(occ_cosx_compute_K(m_h, kind == SpinorbitalKind::Unrestricted ? 1 : 0, D, precision, m_omega, K));
+  }
+  void compute_K_range_separated(const double *D, double alpha, double beta, double omega, double *K,
+                                 double precision = std::numeric_limits<double>::epsilon()) const {
+    check(occ_cosx_compute_K_range_separated(m_h, D, alpha, beta, omega, precision, K));
+  }
+  void set_range_separated_omega(double omega) { m_omega = omega; }
+  double range_separated_omega() const { return m_omega; }
+
+  size_t num_grid_points() const { return info().npts; }
+  size_t num_batches() const { return info().nbatches; }
+  size_t num_atoms() const { return static_cast<size_t>(m_natoms); }
+  int nbf() const { return m_nbf; }
+  occ_cosx_info_t info() const {
+    occ_cosx_info_t i;
+    check(occ_cosx_get_info(m_h, &i));
+    return i;
+  }
+
+private:
+  occ_cosx_handle *m_h = nullptr;
+  int m_nbf, m_natoms;
+  double m_omega = 0.0;
+};
+
+} // namespace occ_b200

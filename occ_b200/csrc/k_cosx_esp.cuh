@@ -112,38 +112,46 @@ __device__ __forceinline__ void add_seeds(const double *__restrict__ tab, double
 template <int L>
 __device__ __forceinline__ void hermite_R(const double (&S)[L + 1], double x, double y, double z,
                                           double (&R)[cx_nhermsum(L)]) {
+  // every loop has a template-constant trip count (guards select the live iterations) so that the unroller resolves
+  // all indices at compile time and the two level arrays stay in registers
   constexpr int NH = cx_nhermsum(L);
   double A[NH];
   A[0] = S[L];
 #pragma unroll
   for (int m = L - 1; m >= 0; --m) {
-    const int n = L - m;
     double B[NH];
     B[0] = S[m];
 #pragma unroll
-    for (int N = 1; N <= n; ++N) {
+    for (int N = 1; N <= L; ++N) {
+      if (N <= L - m) {
 #pragma unroll
-      for (int uv = 0; uv <= N; ++uv) {
+        for (int uv = 0; uv <= L; ++uv) {
+          if (uv <= N) {
 #pragma unroll
-        for (int v = 0; v <= uv; ++v) {
-          const int u = uv - v, t = N - uv;
-          double val;
-          if (v > 0) {
-            val = z * A[cx_hidx(t, u, v - 1)];
-            if (v > 1) val += (v - 1) * A[cx_hidx(t, u, v - 2)];
-          } else if (u > 0) {
-            val = y * A[cx_hidx(t, u - 1, 0)];
-            if (u > 1) val += (u - 1) * A[cx_hidx(t, u - 2, 0)];
-          } else {
-            val = x * A[cx_hidx(t - 1, 0, 0)];
-            if (t > 1) val += (t - 1) * A[cx_hidx(t - 2, 0, 0)];
+            for (int v = 0; v <= L; ++v) {
+              if (v <= uv) {
+                const int u = uv - v, t = N - uv;
+                double val;
+                if (v > 0) {
+                  val = z * A[cx_hidx(t, u, v - 1)];
+                  if (v > 1) val += (v - 1) * A[cx_hidx(t, u, v - 2)];
+                } else if (u > 0) {
+                  val = y * A[cx_hidx(t, u - 1, 0)];
+                  if (u > 1) val += (u - 1) * A[cx_hidx(t, u - 2, 0)];
+                } else {
+                  val = x * A[cx_hidx(t - 1, 0, 0)];
+                  if (t > 1) val += (t - 1) * A[cx_hidx(t - 2, 0, 0)];
+                }
+                B[cx_hidx(t, u, v)] = val;
+              }
+            }
           }
-          B[cx_hidx(t, u, v)] = val;
         }
       }
     }
 #pragma unroll
-    for (int i = 0; i < cx_nhermsum(n); ++i) A[i] = B[i];
+    for (int i = 0; i < NH; ++i)
+      if (i < cx_nhermsum(L - m)) A[i] = B[i];
   }
 #pragma unroll
   for (int i = 0; i < NH; ++i) R[i] = A[i];
@@ -156,43 +164,51 @@ __device__ __forceinline__ void contract(const double *__restrict__ Ex, const do
                                          const double *__restrict__ Ez, const double (&R)[cx_nhermsum(LA + LB)],
                                          const double (&Fp)[cx_ncart(LA)], const double (&Fq)[cx_ncart(LB)],
                                          double (&Gp)[cx_ncart(LA)], double (&Gq)[cx_ncart(LB)], bool offdiag) {
-  constexpr int L1 = LA + LB + 1;
-  int ia = 0;
+  // template-constant trip counts + guards: see hermite_R
+  constexpr int L = LA + LB, L1 = L + 1;
 #pragma unroll
   for (int ax = LA; ax >= 0; --ax) {
 #pragma unroll
-    for (int ay = LA - ax; ay >= 0; --ay) {
-      const int az = LA - ax - ay;
-      double gp = 0.0;
-      int jb = 0;
+    for (int ay = LA; ay >= 0; --ay) {
+      if (ay <= LA - ax) {
+        const int az = LA - ax - ay;
+        const int ia = (LA - ax) * (LA - ax + 1) / 2 + (LA - ax - ay); // CCA Cartesian index
+        double gp = 0.0;
 #pragma unroll
-      for (int bx = LB; bx >= 0; --bx) {
+        for (int bx = LB; bx >= 0; --bx) {
 #pragma unroll
-        for (int by = LB - bx; by >= 0; --by) {
-          const int bz = LB - bx - by;
-          const double *ex = Ex + (ax * (LB + 1) + bx) * L1;
-          const double *ey = Ey + (ay * (LB + 1) + by) * L1;
-          const double *ez = Ez + (az * (LB + 1) + bz) * L1;
-          double V = 0.0;
+          for (int by = LB; by >= 0; --by) {
+            if (by <= LB - bx) {
+              const int bz = LB - bx - by;
+              const int jb = (LB - bx) * (LB - bx + 1) / 2 + (LB - bx - by);
+              const double *ex = Ex + (ax * (LB + 1) + bx) * L1;
+              const double *ey = Ey + (ay * (LB + 1) + by) * L1;
+              const double *ez = Ez + (az * (LB + 1) + bz) * L1;
+              double V = 0.0;
 #pragma unroll
-          for (int t = 0; t <= ax + bx; ++t) {
-            double sy = 0.0;
+              for (int t = 0; t <= L; ++t) {
+                if (t <= ax + bx) {
+                  double sy = 0.0;
 #pragma unroll
-            for (int u = 0; u <= ay + by; ++u) {
-              double sz = 0.0;
+                  for (int u = 0; u <= L; ++u) {
+                    if (u <= ay + by) {
+                      double sz = 0.0;
 #pragma unroll
-              for (int v = 0; v <= az + bz; ++v) sz += ez[v] * R[cx_hidx(t, u, v)];
-              sy += ey[u] * sz;
+                      for (int v = 0; v <= L; ++v)
+                        if (v <= az + bz) sz += ez[v] * R[cx_hidx(t, u, v)];
+                      sy += ey[u] * sz;
+                    }
+                  }
+                  V += ex[t] * sy;
+                }
+              }
+              Gq[jb] += Fp[ia] * V;
+              gp += Fq[jb] * V;
             }
-            V += ex[t] * sy;
           }
-          Gq[jb] += Fp[ia] * V;
-          gp += Fq[jb] * V;
-          ++jb;
         }
+        if (offdiag) Gp[ia] += gp;
       }
-      if (offdiag) Gp[ia] += gp;
-      ++ia;
     }
   }
 }

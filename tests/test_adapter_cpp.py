@@ -82,3 +82,19 @@ def test_adapter_build_matches_oracle(case, oracle, tmp_path, method, nspin):
     ref = oracle.xc_build(c["obasis"], c["spts"], c["sw"], c["leaves"], names, nspin, D2)
     assert np.abs(K - ref["K"]).max() < 1e-9 and abs(raw[0] - ref["exc"]) < 1e-8
     assert abs(raw[1] - ref["n_alpha"]) < 1e-9
+
+
+def test_cosx_adapter_compiles_and_fails_loudly_without_device():
+    """adapter/occ_cosx_b200.h (SemiNumericalExchange mirror): g++ compile + link; no device -> std::runtime_error."""
+    src = os.path.join(ROOT, "tests", "cpp", "adapter_cosx_driver.cpp")
+    exe = os.path.join(ROOT, "tests", "cpp", "adapter_cosx_driver")
+    lib = os.path.join(ROOT, "occ_b200")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-o", exe, src, "-L" + lib, "-locc_xc_b200",
+                           "-Wl,-rpath," + lib])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, (out.stdout, out.stderr)
+    import torch
+    if torch.cuda.is_available():
+        assert out.stdout.startswith("ok K00=")
+    else:
+        assert "runtime_error" in out.stdout and "CUDA" in out.stdout

@@ -44,6 +44,18 @@ def test_cosx_K_matches_oracle(oracle, mol, basis_name, pure):
     sgx.close()
 
 
+def test_cosx_two_centre_f_pairs(oracle):
+    """benzene def2-TZVP: f shells on six carbons, so every (la, lb) class up to (3, 3) has two-centre pairs"""
+    for pure in (True, False):
+        O, b, ob, off, pts, w, P, S, Sn, D, sgx = _setup(oracle, "benzene", "def2-tzvp", pure, angular=14,
+                                                         radial_precision=1e-3)
+        K = sgx.compute_K(D)
+        Kref, stats = O.cosx_compute_K(ob, off, pts, w, P, D)
+        assert np.abs(K - Kref).max() < TOL, np.abs(K - Kref).max()
+        assert sgx.info()["pair_evals"] == stats[0]["pair_evals"]
+        sgx.close()
+
+
 def test_cosx_raw_K_and_overlaps_match_oracle(oracle):
     O, b, ob, off, pts, w, P, S, Sn, D, sgx = _setup(oracle, "water", "def2-svp", False)
     assert np.abs(sgx.analytic_overlap() - S).max() < 1e-14
