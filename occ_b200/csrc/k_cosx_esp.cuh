@@ -213,15 +213,199 @@ __device__ __forceinline__ void contract(const double *__restrict__ Ex, const do
   }
 }
 
+// Sliced form of hermite_R + contract for L = la + lb >= 4, where the 35-84 R_tuv no longer fit in registers next to F and
+// G. The Hermite integrals are generated slice by slice — rows R^m_{t00} in t (two rows live), rows R^m_{tu0} in u (two rows
+// live), then the 1D recursion in v for one (t, u) — and each (t, u) slice is contracted at once:
+//   S[az][bz] = sum_v Ez[az,bz,v] R_tuv,   G += F . (Ex[ax,bx,t] Ey[ay,by,u]) S[az][bz]
+// Same recurrences and the same products as the reference (rints.h:183-219, kernels.h:256-290), other summation order.
+template <int LA, int LB>
+__device__ __forceinline__ void prim_sliced(const double *__restrict__ Ex, const double *__restrict__ Ey,
+                                            const double *__restrict__ Ez, const double (&S)[LA + LB + 1], double x,
+                                            double y, double z, const double (&Fp)[cx_ncart(LA)],
+                                            const double (&Fq)[cx_ncart(LB)], double (&Gp)[cx_ncart(LA)],
+                                            double (&Gq)[cx_ncart(LB)], bool offdiag) {
+  constexpr int L = LA + LB, L1 = L + 1;
+  double Xc[L1], Xp[L1]; // R^m_{t00} and R^m_{t-1,00}
+#pragma unroll
+  for (int m = 0; m <= L; ++m) {
+    Xc[m] = S[m];
+    Xp[m] = 0.0;
+  }
+  double gp[cx_ncart(LA)];
+#pragma unroll
+  for (int i = 0; i < cx_ncart(LA); ++i) gp[i] = 0.0;
+#pragma unroll
+  for (int t = 0; t <= L; ++t) {
+    // rows in u for this t: Yc[m] = R^m_{t,u,0}, Yp[m] = R^m_{t,u-1,0}
+    double Yc[L1], Yp[L1];
+#pragma unroll
+    for (int m = 0; m <= L; ++m) {
+      Yc[m] = (m <= L - t) ? Xc[m] : 0.0;
+      Yp[m] = 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u <= L; ++u) {
+      if (u <= L - t) {
+        const int k = L - t - u; // v runs 0..k
+        // 1D recursion in v: c[m] = R^m_{t,u,v}
+        double Rv[L1], c[L1], cp[L1];
+#pragma unroll
+        for (int m = 0; m <= L; ++m) {
+          c[m] = (m <= k) ? Yc[m] : 0.0;
+          cp[m] = 0.0;
+        }
+        Rv[0] = c[0];
+#pragma unroll
+        for (int v = 0; v < L; ++v) {
+          if (v < k) {
+            double cn[L1];
+#pragma unroll
+            for (int m = 0; m <= L; ++m) {
+              cn[m] = 0.0;
+              if (m <= k - v - 1) {
+                cn[m] = z * c[m + 1];
+                if (v > 0) cn[m] += v * cp[m + 1];
+              }
+            }
+#pragma unroll
+            for (int m = 0; m <= L; ++m) {
+              cp[m] = c[m];
+              c[m] = cn[m];
+            }
+            Rv[v + 1] = c[0];
+          }
+        }
+        // S[az][bz]
+        double Sz[LA + 1][LB + 1];
+#pragma unroll
+        for (int az = 0; az <= LA; ++az) {
+#pragma unroll
+          for (int bz = 0; bz <= LB; ++bz) {
+            double s = 0.0;
+            if (t + u <= L - az - bz) {
+              const double *ez = Ez + (az * (LB + 1) + bz) * L1;
+#pragma unroll
+              for (int v = 0; v <= L; ++v)
+                if (v <= az + bz && v <= k) s += ez[v] * Rv[v];
+            }
+            Sz[az][bz] = s;
+          }
+        }
+#pragma unroll
+        for (int ax = 0; ax <= LA; ++ax) {
+#pragma unroll
+          for (int bx = 0; bx <= LB; ++bx) {
+            if (ax + bx >= t) {
+              const double ext = Ex[(ax * (LB + 1) + bx) * L1 + t];
+#pragma unroll
+              for (int ay = 0; ay <= LA; ++ay) {
+#pragma unroll
+                for (int by = 0; by <= LB; ++by) {
+                  if (ay <= LA - ax && by <= LB - bx && ay + by >= u) {
+                    const int az = LA - ax - ay, bz = LB - bx - by;
+                    const int ia = (LA - ax) * (LA - ax + 1) / 2 + (LA - ax - ay);
+                    const int jb = (LB - bx) * (LB - bx + 1) / 2 + (LB - bx - by);
+                    const double V = (ext * Ey[(ay * (LB + 1) + by) * L1 + u]) * Sz[az][bz];
+                    Gq[jb] += Fp[ia] * V;
+                    gp[ia] += Fq[jb] * V;
+                  }
+                }
+              }
+            }
+          }
+        }
+        // next row in u: R^m_{t,u+1,0} = y R^{m+1}_{t,u,0} + u R^{m+1}_{t,u-1,0}
+        if (u < L - t) {
+          double Yn[L1];
+#pragma unroll
+          for (int m = 0; m <= L; ++m) {
+            Yn[m] = 0.0;
+            if (m <= L - t - u - 1) {
+              Yn[m] = y * Yc[m + 1];
+              if (u > 0) Yn[m] += u * Yp[m + 1];
+            }
+          }
+#pragma unroll
+          for (int m = 0; m <= L; ++m) {
+            Yp[m] = Yc[m];
+            Yc[m] = Yn[m];
+          }
+        }
+      }
+    }
+    // next row in t: R^m_{t+1,00} = x R^{m+1}_{t00} + t R^{m+1}_{t-1,00}
+    if (t < L) {
+      double Xn[L1];
+#pragma unroll
+      for (int m = 0; m <= L; ++m) {
+        Xn[m] = 0.0;
+        if (m <= L - t - 1) {
+          Xn[m] = x * Xc[m + 1];
+          if (t > 0) Xn[m] += t * Xp[m + 1];
+        }
+      }
+#pragma unroll
+      for (int m = 0; m <= L; ++m) {
+        Xp[m] = Xc[m];
+        Xc[m] = Xn[m];
+      }
+    }
+  }
+  if (offdiag) {
+#pragma unroll
+    for (int i = 0; i < cx_ncart(LA); ++i) Gp[i] += gp[i];
+  }
+}
+
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+  const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// read the staged F columns of a shell: F~[c] = w sum_m T[m][c] F[m] (spherical) or w F[c]
+template <int L>
+__device__ __forceinline__ void take_F(double (&Ft)[cx_ncart(L)], const double *sF /* [col][128] + tid */, double w,
+                                       bool pure, const double *__restrict__ c2s) {
+  constexpr int NC = cx_ncart(L), NS = 2 * L + 1;
+  if (!pure || L == 0) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) Ft[c] = w * sF[c * TILE_P];
+  } else {
+    const double *T = c2s_of<L>(c2s);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) Ft[c] = 0.0;
+#pragma unroll
+    for (int m = 0; m < NS; ++m) {
+      const double f = w * sF[m * TILE_P];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) Ft[c] += __ldg(T + m * NC + c) * f;
+    }
+  }
+}
+
+// One CTA = one grid batch x one run of `chunk` shell pairs of class (LA, LB).
+//   round:    128 candidate pairs are screened in parallel (density flag, geometric test) and the survivors compacted,
+//             in order, into shared memory — one global-load latency per 128 pairs instead of one per pair;
+//   pipeline: the primitive records and the F columns of the surviving pairs stream through an NBUF-deep cp.async ring,
+//             so the loads of the next pairs are in flight while the current one is evaluated.
 template <int LA, int LB>
 __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, int npairs, int chunk, int cls) {
   constexpr int L = LA + LB, NE = (LA + 1) * (LB + 1) * (L + 1), STRIDE = COSX_PRIM_HDR + 3 * NE;
   constexpr int NCA = cx_ncart(LA), NCB = cx_ncart(LB), NH = cx_nhermsum(L);
-  constexpr int STAGE = (1024 / STRIDE) > 0 ? (1024 / STRIDE) : 1;
-  __shared__ double sm[STAGE * STRIDE];
+  constexpr int NBUF = L <= 1 ? 4 : 2;
+  constexpr int POOLCAP = L <= 1 ? 512 : 1024;
+  constexpr int STAGE = (POOLCAP / STRIDE) > 0 ? (POOLCAP / STRIDE) : 1;
+  __shared__ double s_pool[NBUF][STAGE * STRIDE];
+  __shared__ double s_F[NBUF][NCB][TILE_P];
+  __shared__ CosxPair s_pairs[TILE_P];
+  __shared__ int s_wcnt[TILE_P / 32];
   const int tile = P.tile0 + blockIdx.x;
   if (P.tile_skip[tile]) return;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int k0 = pair0 + blockIdx.y * chunk;
   const int k1 = min(k0 + chunk, pair0 + npairs);
   const double tcx = P.tcx[tile], tcy = P.tcy[tile], tcz = P.tcz[tile], lim = P.trad[tile] + P.margin;
@@ -231,39 +415,99 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
   const double *Fcol = P.F + slab;
   double *Gcol = P.G + slab;
   const bool pure = P.pure != 0;
+  const int nq_cols = (pure && LB > 0) ? 2 * LB + 1 : NCB;
   const double w2 = P.omega * P.omega;
 
-  double Fp[NCA], Gp[NCA];
+  double Fp[NCA], Gp[NCA], Fq[NCB], Gq[NCB];
   int cur_p = -1, cur_bfp = 0;
   bool gp_dirty = false;
-  for (int k = k0; k < k1; ++k) {
-    if (!P.pair_active[k]) continue; // seminumerical_exchange.cpp:758-764
-    const CosxPair pr = P.pairs[k];
-    const double dx = pr.cx - tcx, dy = pr.cy - tcy, dz = pr.cz - tcz;
-    if (sqrt(dx * dx + dy * dy + dz * dz) - pr.extent >= lim) continue; // :744-748
-    if (pr.p != cur_p) {
-      if (gp_dirty) flush_G<LA>(Gp, Gcol, cur_bfp, pure, P.c2s);
-      cur_p = pr.p;
-      cur_bfp = pr.bfp;
-      gp_dirty = false;
-      load_F<LA>(Fp, Fcol, pr.bfp, w, pure, P.c2s);
-#pragma unroll
-      for (int i = 0; i < NCA; ++i) Gp[i] = 0.0;
+  for (int kr = k0; kr < k1; kr += TILE_P) {
+    // ---- screen 128 candidates (seminumerical_exchange.cpp:744-748 geometric, :758-764 density) ----
+    const int k = kr + tid;
+    bool keep = false;
+    CosxPair cand;
+    if (k < k1 && P.pair_active[k]) {
+      cand = P.pairs[k];
+      const double dx = cand.cx - tcx, dy = cand.cy - tcy, dz = cand.cz - tcz;
+      keep = !(sqrt(dx * dx + dy * dy + dz * dz) - cand.extent >= lim);
     }
-    double Fq[NCB], Gq[NCB];
-    load_F<LB>(Fq, Fcol, pr.bfq, w, pure, P.c2s);
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    __syncthreads(); // previous round fully consumed (s_pairs, s_wcnt reuse)
+    if (lane == 0) s_wcnt[wid] = __popc(bal);
+    __syncthreads();
+    int base = 0, nsurv = 0;
 #pragma unroll
-    for (int j = 0; j < NCB; ++j) Gq[j] = 0.0;
-    const bool offdiag = pr.p != pr.q;
-    gp_dirty = gp_dirty || offdiag;
-    for (int i0 = 0; i0 < pr.nprim; i0 += STAGE) {
+    for (int i = 0; i < TILE_P / 32; ++i) {
+      if (i < wid) base += s_wcnt[i];
+      nsurv += s_wcnt[i];
+    }
+    if (keep) s_pairs[base + __popc(bal & ((1u << lane) - 1u))] = cand;
+    __syncthreads();
+    if (nsurv == 0) continue;
+
+    // ---- cp.async ring over (pair, primitive-chunk) units ----
+    auto issue = [&](int li, int i0, int buf) {
+      const CosxPair &pr = s_pairs[li];
       const int ns = min(STAGE, pr.nprim - i0);
-      __syncthreads();
       const double *src = P.pool + pr.off + static_cast<size_t>(i0) * STRIDE;
-      for (int i = tid; i < ns * STRIDE; i += TILE_P) sm[i] = __ldg(src + i);
+      for (int i = tid; i < ns * STRIDE; i += TILE_P) cp_async8(&s_pool[buf][i], src + i);
+      if (i0 == 0) {
+        const double *f = Fcol + static_cast<size_t>(pr.bfq) * TILE_P;
+        for (int c = 0; c < nq_cols; ++c) cp_async8(&s_F[buf][c][tid], f + static_cast<size_t>(c) * TILE_P);
+      }
+    };
+    int li_n = 0, i0_n = 0, issued = 0, consumed = 0;
+    auto advance_n = [&]() {
+      i0_n += STAGE;
+      if (i0_n >= s_pairs[li_n].nprim) {
+        i0_n = 0;
+        ++li_n;
+      }
+    };
+#pragma unroll
+    for (int j = 0; j < NBUF - 1; ++j) {
+      if (li_n < nsurv) {
+        issue(li_n, i0_n, issued % NBUF);
+        advance_n();
+      }
+      cp_async_commit();
+      ++issued;
+    }
+    int li = 0, i0 = 0;
+    while (li < nsurv) {
+      if (li_n < nsurv) {
+        issue(li_n, i0_n, issued % NBUF);
+        advance_n();
+      }
+      cp_async_commit();
+      ++issued;
+      cp_async_wait<NBUF - 1>();
       __syncthreads();
+      const int buf = consumed % NBUF;
+      const CosxPair &pr = s_pairs[li];
+      const bool offdiag = pr.p != pr.q;
+      if (i0 == 0) {
+        if (pr.p != cur_p) {
+          if (gp_dirty) flush_G<LA>(Gp, Gcol, cur_bfp, pure, P.c2s);
+          cur_p = pr.p;
+          cur_bfp = pr.bfp;
+          gp_dirty = false;
+          load_F<LA>(Fp, Fcol, pr.bfp, w, pure, P.c2s);
+#pragma unroll
+          for (int i = 0; i < NCA; ++i) Gp[i] = 0.0;
+        }
+        take_F<LB>(Fq, &s_F[buf][0][tid], w, pure, P.c2s);
+#pragma unroll
+        for (int j = 0; j < NCB; ++j) Gq[j] = 0.0;
+        gp_dirty = gp_dirty || offdiag;
+        if (P.stats && tid == 0) {
+          atomicAdd(P.stats + 2 * cls, 1ULL);
+          atomicAdd(P.stats + 2 * cls + 1, static_cast<unsigned long long>(pr.nprim) * P.counts[tile]);
+        }
+      }
+      const int ns = min(STAGE, pr.nprim - i0);
       for (int s = 0; s < ns; ++s) {
-        const double *rec = sm + s * STRIDE;
+        const double *rec = s_pool[buf] + s * STRIDE;
         const double pe = rec[0];
         const double PCx = rec[1] - X, PCy = rec[2] - Y, PCz = rec[3] - Z; // rints_specialized.h:1457-1460: P - C
         const double r2 = PCx * PCx + PCy * PCy + PCz * PCz;
@@ -275,17 +519,26 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
           const double sc = w2 / (pe + w2);
           add_seeds<L>(P.boys, pe * sc, r2, P.w_lr * sqrt(sc), S);
         }
-        double R[NH];
-        hermite_R<L>(S, PCx, PCy, PCz, R);
-        contract<LA, LB>(rec + COSX_PRIM_HDR, rec + COSX_PRIM_HDR + NE, rec + COSX_PRIM_HDR + 2 * NE, R, Fp, Fq, Gp, Gq,
-                         offdiag);
+        if constexpr (L >= 4) {
+          prim_sliced<LA, LB>(rec + COSX_PRIM_HDR, rec + COSX_PRIM_HDR + NE, rec + COSX_PRIM_HDR + 2 * NE, S, PCx, PCy, PCz,
+                              Fp, Fq, Gp, Gq, offdiag);
+        } else {
+          double R[NH];
+          hermite_R<L>(S, PCx, PCy, PCz, R);
+          contract<LA, LB>(rec + COSX_PRIM_HDR, rec + COSX_PRIM_HDR + NE, rec + COSX_PRIM_HDR + 2 * NE, R, Fp, Fq, Gp,
+                           Gq, offdiag);
+        }
       }
+      i0 += STAGE;
+      if (i0 >= pr.nprim) {
+        flush_G<LB>(Gq, Gcol, pr.bfq, pure, P.c2s);
+        i0 = 0;
+        ++li;
+      }
+      ++consumed;
+      __syncthreads(); // the buffer just read is the target of the next issue
     }
-    flush_G<LB>(Gq, Gcol, pr.bfq, pure, P.c2s);
-    if (P.stats && tid == 0) {
-      atomicAdd(P.stats + 2 * cls, 1ULL);
-      atomicAdd(P.stats + 2 * cls + 1, static_cast<unsigned long long>(pr.nprim) * P.counts[tile]);
-    }
+    cp_async_wait<0>();
   }
   if (gp_dirty) flush_G<LA>(Gp, Gcol, cur_bfp, pure, P.c2s);
 }
@@ -293,7 +546,7 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
 template <int LA, int LB>
 void launch_class(const CosxParams &P, int pair0, int npairs, int ntiles, cudaStream_t st) {
   constexpr int L = LA + LB;
-  int chunk = L == 0 ? 64 : (L == 1 ? 32 : (L == 2 ? 16 : (L == 3 ? 8 : 4)));
+  int chunk = L == 0 ? 512 : (L == 1 ? 256 : 128);
   while ((npairs + chunk - 1) / chunk > 65535) chunk *= 2;
   dim3 grid(ntiles, (npairs + chunk - 1) / chunk);
   k_cosx_esp<LA, LB><<<grid, TILE_P, 0, st>>>(P, pair0, npairs, chunk, LA * (COSX_MAX_L + 1) + LB);
