@@ -268,15 +268,19 @@ int occ_cosx_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_
     }                                                                                                        \
   } while (0)
 
-  // ---- shell pairs, grouped by (la, lb) class, registration order inside a class ----
+  // ---- shell pairs, grouped by (la >= lb) class, sorted by the resident shell inside a class ----
   std::vector<double> Tfull[COSX_MAX_L + 1];
   for (int l = 0; l <= COSX_MAX_L; ++l) Tfull[l] = c2s_full(l);
   std::vector<HostPair> hp[16];
   std::vector<double> pool[16];
   h->S_analytic.assign(static_cast<size_t>(nbf) * nbf, 0.0);
   std::vector<double> Ex, Ey, Ez, Sc, Ss, tmp;
-  for (int p = 0; p < nsh; ++p)
-    for (int q = 0; q <= p; ++q) {
+  for (int p0 = 0; p0 < nsh; ++p0)
+    for (int q0 = 0; q0 <= p0; ++q0) {
+      // roles: the higher-l shell is the "p" side of the kernel (its G row stays in registers across the run of pairs
+      // that share it; the per-pair column traffic is then that of the lower-l shell). V is symmetric under the swap.
+      const bool swap_roles = basis->l[p0] < basis->l[q0];
+      const int p = swap_roles ? q0 : p0, q = swap_roles ? p0 : q0;
       const int la = basis->l[p], lb = basis->l[q], L1 = la + lb + 1, ne = (la + 1) * (lb + 1) * L1;
       const double *A = basis->origin + 3 * p, *Bc = basis->origin + 3 * q;
       const int cls = la * 4 + lb, stride = COSX_PRIM_HDR + 3 * ne;
@@ -382,6 +386,9 @@ int occ_cosx_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_
       occ_cosx_destroy(h);
       return fail("occ_cosx_create: primitive pool exceeds 2^31 doubles");
     }
+    std::stable_sort(hp[cls].begin(), hp[cls].end(), [](const HostPair &a, const HostPair &b) {
+      return a.d.p != b.d.p ? a.d.p < b.d.p : a.d.q < b.d.q;
+    });
     for (auto &e : hp[cls]) {
       e.d.off += static_cast<int>(base);
       pairs_all.push_back(e.d);

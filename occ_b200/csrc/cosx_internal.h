@@ -11,6 +11,7 @@
 namespace xcb {
 
 constexpr int COSX_MAX_L = 3;
+constexpr int COSX_TILE_GROUP = 8; // batches whose F / G slabs share the L2 while all their pair runs execute
 
 struct CosxPair {
   int p, q;       // shells, p >= q (registration order of seminumerical_exchange.cpp:293-331)

@@ -393,7 +393,8 @@ __device__ __forceinline__ void take_F(double (&Ft)[cx_ncart(L)], const double *
 //   pipeline: the primitive records and the F columns of the surviving pairs stream through an NBUF-deep cp.async ring,
 //             so the loads of the next pairs are in flight while the current one is evaluated.
 template <int LA, int LB>
-__global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, int npairs, int chunk, int cls) {
+__global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, int npairs, int chunk, int cls, int ntiles,
+                                                     int nruns) {
   constexpr int L = LA + LB, NE = (LA + 1) * (LB + 1) * (L + 1), STRIDE = COSX_PRIM_HDR + 3 * NE;
   constexpr int NCA = cx_ncart(LA), NCB = cx_ncart(LB), NH = cx_nhermsum(L);
   constexpr int NBUF = L <= 1 ? 4 : 2;
@@ -403,15 +404,21 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
   __shared__ double s_F[NBUF][NCB][TILE_P];
   __shared__ CosxPair s_pairs[TILE_P];
   __shared__ int s_wcnt[TILE_P / 32];
-  const int tile = P.tile0 + blockIdx.x;
+  // 1D grid, group-major: the CTAs of COSX_TILE_GROUP batches x all pair runs are adjacent, so that the F and G slabs of
+  // a group (2 x 8 x 128 x nbp doubles) stay L2-resident while every pair run reads / accumulates into them
+  const int tl = blockIdx.x % COSX_TILE_GROUP;
+  const int yrun = (blockIdx.x / COSX_TILE_GROUP) % nruns;
+  const int ltile = (blockIdx.x / (COSX_TILE_GROUP * nruns)) * COSX_TILE_GROUP + tl; // chunk-relative batch
+  if (ltile >= ntiles) return;
+  const int tile = P.tile0 + ltile;
   if (P.tile_skip[tile]) return;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int k0 = pair0 + blockIdx.y * chunk;
+  const int k0 = pair0 + yrun * chunk;
   const int k1 = min(k0 + chunk, pair0 + npairs);
   const double tcx = P.tcx[tile], tcy = P.tcy[tile], tcz = P.tcz[tile], lim = P.trad[tile] + P.margin;
   const size_t pt = static_cast<size_t>(tile) * TILE_P + tid;
   const double X = P.px[pt], Y = P.py[pt], Z = P.pz[pt], w = P.pw[pt];
-  const size_t slab = static_cast<size_t>(blockIdx.x) * P.nbp * TILE_P + tid;
+  const size_t slab = static_cast<size_t>(ltile) * P.nbp * TILE_P + tid;
   const double *Fcol = P.F + slab;
   double *Gcol = P.G + slab;
   const bool pure = P.pure != 0;
@@ -547,9 +554,11 @@ template <int LA, int LB>
 void launch_class(const CosxParams &P, int pair0, int npairs, int ntiles, cudaStream_t st) {
   constexpr int L = LA + LB;
   int chunk = L == 0 ? 512 : (L == 1 ? 256 : 128);
-  while ((npairs + chunk - 1) / chunk > 65535) chunk *= 2;
-  dim3 grid(ntiles, (npairs + chunk - 1) / chunk);
-  k_cosx_esp<LA, LB><<<grid, TILE_P, 0, st>>>(P, pair0, npairs, chunk, LA * (COSX_MAX_L + 1) + LB);
+  const int ngroups = (ntiles + COSX_TILE_GROUP - 1) / COSX_TILE_GROUP;
+  while (static_cast<long long>(ngroups) * COSX_TILE_GROUP * ((npairs + chunk - 1) / chunk) > 0x7fffffffLL) chunk *= 2;
+  const int nruns = (npairs + chunk - 1) / chunk;
+  k_cosx_esp<LA, LB><<<ngroups * COSX_TILE_GROUP * nruns, TILE_P, 0, st>>>(P, pair0, npairs, chunk,
+                                                                            LA * (COSX_MAX_L + 1) + LB, ntiles, nruns);
 }
 
 } // namespace xcb

@@ -2,7 +2,4 @@
 #include "k_cosx_esp.cuh"
 namespace xcb {
 template void launch_class<0, 0>(const CosxParams &, int, int, int, cudaStream_t);
-template void launch_class<0, 1>(const CosxParams &, int, int, int, cudaStream_t);
-template void launch_class<0, 2>(const CosxParams &, int, int, int, cudaStream_t);
-template void launch_class<0, 3>(const CosxParams &, int, int, int, cudaStream_t);
 } // namespace xcb

@@ -3,6 +3,4 @@
 namespace xcb {
 template void launch_class<1, 0>(const CosxParams &, int, int, int, cudaStream_t);
 template void launch_class<1, 1>(const CosxParams &, int, int, int, cudaStream_t);
-template void launch_class<1, 2>(const CosxParams &, int, int, int, cudaStream_t);
-template void launch_class<1, 3>(const CosxParams &, int, int, int, cudaStream_t);
 } // namespace xcb

@@ -4,5 +4,4 @@ namespace xcb {
 template void launch_class<2, 0>(const CosxParams &, int, int, int, cudaStream_t);
 template void launch_class<2, 1>(const CosxParams &, int, int, int, cudaStream_t);
 template void launch_class<2, 2>(const CosxParams &, int, int, int, cudaStream_t);
-template void launch_class<2, 3>(const CosxParams &, int, int, int, cudaStream_t);
 } // namespace xcb

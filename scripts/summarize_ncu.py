@@ -20,7 +20,11 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_th
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio"]
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "sass__inst_executed_local_loads", "sass__inst_executed_local_stores",
+        "smsp__inst_executed_op_global_red.sum", "l1tex__throughput.avg.pct_of_peak_sustained_active",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
 
 
 def launches(path):
