@@ -126,6 +126,19 @@ class SemiNumericalExchange:
         check(lib().occ_cosx_K_for_density(self._h, ptr(D2q), precision, self.omega, ptr(K)))
         return K
 
+    def compute_K_for_density_device(self, D2q_dev, K_dev, precision: float = np.finfo(np.float64).eps,
+                                     w_full: float = 1.0, w_lr: float = 0.0, omega: float = 0.0):
+        """Device-resident compute_K_for_density: D2q_dev / K_dev are torch CUDA float64 tensors (nbf x nbf, column-major
+        = the transpose of a contiguous torch tensor) on this handle's device. With rank / world_size sharding K_dev is
+        this rank's partial sum; the caller adds the partials (one NCCL all-reduce, scripts/gpu_cosx_scaling.py)."""
+        L = lib()
+        L.occ_cosx_K_for_density_device.restype = C.c_int
+        L.occ_cosx_K_for_density_device.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double,
+                                                    C.c_double, C.c_void_p]
+        check(L.occ_cosx_K_for_density_device(self._h, C.c_void_p(D2q_dev.data_ptr()), precision, w_full, w_lr, omega,
+                                              C.c_void_p(K_dev.data_ptr())))
+        return K_dev
+
     def compute_overlap_matrix(self):
         S = np.zeros((self.basis.nbf, self.basis.nbf), order="F")
         check(lib().occ_cosx_numerical_overlap(self._h, ptr(S)))
