@@ -42,6 +42,20 @@ def sgx_grid_settings(angular_points: int = 50, radial_precision: float = 1e-5) 
     return GridSettings(angular_points, angular_points, radial_precision, False, True)
 
 
+def batch_shard(atom_offsets, rank: int, world_size: int):
+    """(start, count) of the grid batches rank `rank` owns: blocks of 128 consecutive points of each atom grid
+    (seminumerical_exchange.cpp:676-699), numbered over the whole molecule and dealt round-robin — the rule
+    occ_cosx_create applies for options.rank / world_size."""
+    out, g = [], 0
+    for a in range(len(atom_offsets) - 1):
+        n = int(atom_offsets[a + 1]) - int(atom_offsets[a])
+        for s in range(0, n, 128):
+            if g % world_size == rank:
+                out.append((int(atom_offsets[a]) + s, min(128, n - s)))
+            g += 1
+    return out
+
+
 class SemiNumericalExchange:
     def __init__(self, basis: AOBasis, settings: GridSettings | None = None, atom_grids=None, device: int = -1,
                  margin: float = 1.0, collect_stats: bool = False, batch_bytes: int = 0, rank: int = 0,

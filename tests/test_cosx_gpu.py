@@ -129,6 +129,7 @@ def test_cosx_sharded_partials_sum_to_K(oracle):
     parts = []
     for r in range(3):
         s = cosx.SemiNumericalExchange(b, atom_grids=(off, pts, w), projector=P, rank=r, world_size=3)
+        assert s.num_batches() == len(cosx.batch_shard(off, r, 3))      # the rule the CPU gloo test shards by
         parts.append(s.compute_K(D))
         s.close()
     assert np.abs(sum(parts) - K).max() < 1e-12

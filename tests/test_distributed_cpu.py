@@ -112,3 +112,51 @@ def test_shared_host_array_rendezvous_between_two_processes():
         assert p.exitcode == 0
     assert got["r1"][0] == 999 * 1000 / 2            # rank 1 saw rank 0's D
     assert got["r0"] == (-7.0, 1)                    # rank 0 saw rank 1's slice and its completion word
+
+
+def _cosx_worker(rank, world, port, q):
+    """COSX N>1 path on CPU: each gloo rank evaluates K' on the batches occ_b200.cosx.batch_shard gives it (the rule
+    the library applies for options.rank / world_size; stand-in builder: the CPU oracle, every batch passed as its own
+    atom grid), all-reduces the partial K' and must reproduce the unsharded sweep."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from occ_b200 import aobasis, cosx, molecules, parallel
+    from oracle import oracle as O
+    Z, pos = molecules.water()
+    b = aobasis.AOBasis.load(Z, pos, "def2-svp", pure=True)
+    ob = O.Basis(b.as_arrays())
+    gs = O.default_grid_settings(max_angular_points=26, min_angular_points=26, radial_precision=1e-4,
+                                 reduced_first_row_element_grid=0)
+    pts, w, info = O.molecular_grid(Z, pos, ob, gs, nthreads=1)
+    off = O.cosx_atom_grids(pts, info)
+    D2q = molecules.synthetic_density(b, 1)
+    mine = cosx.batch_shard(off, rank, world)
+    spts = np.concatenate([pts[s:s + c] for s, c in mine])
+    sw = np.concatenate([w[s:s + c] for s, c in mine])
+    soff = np.concatenate([[0], np.cumsum([c for _, c in mine])]).astype(np.uint64)
+    part, st = O.cosx_K_for_density(ob, soff, spts, sw, D2q)
+    buf = torch.from_numpy(part.ravel(order="F").copy())
+    parallel.allreduce_partial(buf)
+    if rank == 0:
+        full, stf = O.cosx_K_for_density(ob, off, pts, w, D2q)
+        nb_all = sum(len(cosx.batch_shard(off, r, world)) for r in range(world))
+        q.put((float(np.abs(buf.numpy().reshape(b.nbf, b.nbf).T - full).max()), len(mine), nb_all, stf["nbatches"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_cosx_two_rank_gloo_sum_equals_unsharded_sweep():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_cosx_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    dk, n0, nall, nfull = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert n0 > 0 and nall == nfull
+    assert dk < 1e-12
