@@ -330,6 +330,12 @@ def run_b200(args):
                    "sample": f"every {res['stride']}-th Morton leaf ({res['nleaves']} leaves, {res['npts']} points) of "
                              f"{args.workload}, one build, {t:.1f} s",
                    "gflops": res["flops"] / t / 1e9}
+        cosx_row = None
+        if world == 1 and not args.no_cosx:
+            try:     # SURVEY 8(f) rank 2, reported beside the headline (never allowed to break it)
+                cosx_row = cosx_next_row(basis, WORKLOADS[args.workload][0], WORKLOADS[args.workload][1])
+            except Exception as e:  # noqa: BLE001
+                cosx_row = {"error": str(e)[:200]}
         line = {
             "metric": "xc_build_grid_points_per_s", "value": npts_total / (ms_dev * 1e-3), "unit": "grid-points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
@@ -375,12 +381,39 @@ def run_b200(args):
                              "slice into the host K")},
             "gpu_launches": int(launches_total * args.steps),
             "clocks": clocks, "setup_seconds": t_setup,
+            "next_rows": {"cosx": cosx_row},
         }
         print(json.dumps(line), flush=True)
     ddft.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def cosx_next_row(basis, mol, bas, reps=2):
+    """SemiNumericalExchange.compute_K (occ_cosx_compute_K: host D -> K, H2D / D2H inside the timed region) of the same
+    molecule and basis on a 50-point sgx grid; restricted, full Coulomb operator."""
+    import time
+
+    from occ_b200 import cosx, molecules
+    t0 = time.perf_counter()
+    sgx = cosx.SemiNumericalExchange(basis, cosx.sgx_grid_settings(50, 1e-5))
+    t_setup = time.perf_counter() - t0
+    D = 0.5 * molecules.synthetic_density(basis, 1)
+    sgx.compute_K(D)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        K = sgx.compute_K(D)
+        ts.append(time.perf_counter() - t0)
+    info = sgx.info()
+    n = sgx.num_grid_points()
+    sgx.close()
+    return {"entry": "occ_cosx_compute_K", "workload": f"{mol}/{bas} RKS, sgx grid 50 angular / radial precision 1e-5",
+            "grid_points": n, "batches": info["nbatches"], "shell_pairs": info["npairs"], "ms_per_call": 1e3 * min(ts),
+            "grid_points_per_s": n / min(ts), "gemm_flops": info["gemm_flops"], "kernel_launches": info["launches"],
+            "library_gemm_calls": info["gemm_calls"], "h2d_bytes": 8 * basis.nbf ** 2, "d2h_bytes": 8 * basis.nbf ** 2,
+            "K_absmax": float(np.abs(K).max()), "setup_seconds": t_setup}
 
 
 def _workspace_gb(info, nspin):
@@ -400,6 +433,7 @@ def main():
     ap.add_argument("--batch-mb", type=int, default=4096)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cosx", action="store_true", help="skip the COSX next-row measurement at N = 1")
     ap.add_argument("--density-form", default="mo", choices=["mo", "d"],
                     help="mo: factorised density where cheaper (occ_xc_build_mo, needs the occupied orbitals); d: D only")
     args = ap.parse_args()

@@ -50,8 +50,6 @@ void launch_cosx_tile_flags(const double *phi, const int *counts, int ntiles, in
                             int *tile_skip, void *stream);
 void launch_cosx_pair_flags(const CosxPair *pairs, const int *shell_size, int npairs, const double *D2q, int nbf,
                             double threshold, unsigned char *active, void *stream);
-void launch_cosx_project_density(const double *P, const double *D, int ldD, int nbf, double scale, double *D2q,
-                                 void *stream); // not used when cuBLAS does the product
 void launch_cosx_symmetrize(const double *Kraw, int nbf, double factor, double *K, int ldK, void *stream);
 void launch_cosx_scale_weights(double *phi_w, const double *phi, const double *pw, int ntiles, int nbf, int nbp,
                                void *stream);

@@ -82,15 +82,10 @@ __device__ __forceinline__ void add_seeds(const double *__restrict__ tab, double
     const double xd = xod - static_cast<double>(seg) - 0.5;
     const double2 *c = reinterpret_cast<const double2 *>(tab + (static_cast<size_t>(seg) * 16 + L) * 8);
     const double2 c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2), c3 = __ldg(c + 3);
-    double r = c3.y;
-    r = r * xd + c3.x;
-    r = r * xd + c2.y;
-    r = r * xd + c2.x;
-    r = r * xd + c1.y;
-    r = r * xd + c1.x;
-    r = r * xd + c0.y;
-    r = r * xd + c0.x;
-    F[L] = r;
+    // Estrin evaluation of the degree-7 polynomial (dependency depth 4 instead of 8; boys.h:101-106 uses Horner)
+    const double x2 = xd * xd, x4 = x2 * x2;
+    const double q0 = fma(c0.y, xd, c0.x), q1 = fma(c1.y, xd, c1.x), q2 = fma(c2.y, xd, c2.x), q3 = fma(c3.y, xd, c3.x);
+    F[L] = fma(fma(q3, x2, q2), x4, fma(q1, x2, q0));
     if (L > 0) {
       const double e = exp(-T), T2 = 2.0 * T;
 #pragma unroll
@@ -513,6 +508,7 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
         }
       }
       const int ns = min(STAGE, pr.nprim - i0);
+#pragma unroll(L == 0 ? 4 : (L <= 2 ? 2 : 1))
       for (int s = 0; s < ns; ++s) {
         const double *rec = s_pool[buf] + s * STRIDE;
         const double pe = rec[0];
