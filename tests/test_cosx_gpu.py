@@ -133,3 +133,35 @@ def test_cosx_sharded_partials_sum_to_K(oracle):
         parts.append(s.compute_K(D))
         s.close()
     assert np.abs(sum(parts) - K).max() < 1e-12
+
+
+def test_cosx_rejects_g_shells_loudly():
+    from occ_b200 import cosx
+    Z, pos = molecules.MOLECULES["water"]()
+    b = aobasis.AOBasis.load(Z, pos, "def2-qzvp")          # g functions on oxygen
+    offs = np.array([0, 1, 2, 3], dtype=np.uint64)
+    with pytest.raises(RuntimeError, match="l = 3"):
+        cosx.SemiNumericalExchange(b, atom_grids=(offs, np.zeros((3, 3)), np.ones(3)), projector=None)
+
+
+def test_cosx_ragged_atom_grids(oracle):
+    """atom grids of 1, 129 and 300 points: a one-point batch, a batch boundary at 128 + 1, and the numerical overlap's
+    dropped last point per atom (seminumerical_exchange.cpp:349-352) on grids where that point matters"""
+    from occ_b200 import cosx
+    O = oracle
+    Z, pos = molecules.MOLECULES["water"]()
+    b = aobasis.AOBasis.load(Z, pos, "def2-svp", pure=True)
+    ob = O.Basis(b.as_arrays())
+    rng = np.random.default_rng(11)
+    counts = [1, 129, 300]
+    pts = np.concatenate([pos[a] + rng.normal(scale=1.2, size=(n, 3)) for a, n in enumerate(counts)])
+    w = rng.uniform(0.01, 0.2, size=len(pts))
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint64)
+    D = molecules.synthetic_density(b, 1, seed=3) * 0.5
+    sgx = cosx.SemiNumericalExchange(b, atom_grids=(off, pts, w), projector=None)
+    assert sgx.num_batches() == 1 + 2 + 3
+    assert np.abs(sgx.compute_overlap_matrix() - O.cosx_numerical_overlap(ob, off, pts, w)).max() < 1e-12
+    K = sgx.compute_K(D)
+    Kref, _ = O.cosx_compute_K(ob, off, pts, w, np.eye(b.nbf), D)
+    assert np.abs(K - Kref).max() < TOL
+    sgx.close()
