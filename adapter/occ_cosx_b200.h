@@ -40,6 +40,10 @@ public:
                  double precision = std::numeric_limits<double>::epsilon()) const {
     check(occ_cosx_compute_K(m_h, kind == SpinorbitalKind::Unrestricted ? 1 : 0, D, precision, m_omega, K));
   }
+  // general spinorbitals: D and K are 2 nbf x 2 nbf (compute_K_general, seminumerical_exchange.cpp:658-712)
+  void compute_K_general(const double *D, double *K, double precision = std::numeric_limits<double>::epsilon()) const {
+    check(occ_cosx_compute_K(m_h, 2, D, precision, m_omega, K));
+  }
   void compute_K_range_separated(const double *D, double alpha, double beta, double omega, double *K,
                                  double precision = std::numeric_limits<double>::epsilon()) const {
     check(occ_cosx_compute_K_range_separated(m_h, D, alpha, beta, omega, precision, K));

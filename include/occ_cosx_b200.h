@@ -47,7 +47,8 @@ int occ_cosx_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_
                     occ_cosx_handle **out);
 
 /* SemiNumericalExchange::compute_K.  kind 0 = restricted: D is mo.D (nbf x nbf), K = 0.25 (K' + K'^T) of D2q = P.(2D);
- * kind 1 = unrestricted: D is (2 nbf x nbf) with the alpha block on top, each spin block 0.5 (K' + K'^T) of P.(2 D_s).
+ * kind 1 = unrestricted: D is (2 nbf x nbf) with the alpha block on top, each spin block 0.5 (K' + K'^T) of P.(2 D_s);
+ * kind 2 = general: D and K are (2 nbf x 2 nbf) with blocks aa, ab / ba, bb (compute_K_general, :662-712).
  * omega = 0: full Coulomb operator; omega > 0: long-range erf(omega r)/r (set_range_separated_omega). */
 int occ_cosx_compute_K(occ_cosx_handle *h, int kind, const double *D, double precision, double omega, double *K);
 

@@ -113,14 +113,17 @@ class SemiNumericalExchange:
     def range_separated_omega(self) -> float:
         return self.omega
 
-    def compute_K(self, D: np.ndarray, precision: float = np.finfo(np.float64).eps, unrestricted: bool = False):
+    def compute_K(self, D: np.ndarray, precision: float = np.finfo(np.float64).eps, unrestricted: bool = False,
+                  general: bool = False):
+        """compute_K(mo): D = mo.D — (nbf, nbf) restricted, (2 nbf, nbf) unrestricted, (2 nbf, 2 nbf) general"""
         nbf = self.basis.nbf
-        nspin = 2 if unrestricted else 1
+        kind = 2 if general else (1 if unrestricted else 0)
+        shape = ((nbf, nbf), (2 * nbf, nbf), (2 * nbf, 2 * nbf))[kind]
         D = np.asfortranarray(D, dtype=np.float64)
-        if D.shape != (nspin * nbf, nbf):
-            raise RuntimeError(f"compute_K: density matrix of shape {D.shape}, expected {(nspin * nbf, nbf)}")
-        K = np.zeros((nspin * nbf, nbf), order="F")
-        check(lib().occ_cosx_compute_K(self._h, nspin - 1, ptr(D), precision, self.omega, ptr(K)))
+        if D.shape != shape:
+            raise RuntimeError(f"compute_K: density matrix of shape {D.shape}, expected {shape}")
+        K = np.zeros(shape, order="F")
+        check(lib().occ_cosx_compute_K(self._h, kind, ptr(D), precision, self.omega, ptr(K)))
         return K
 
     def compute_K_range_separated(self, D, alpha: float, beta: float, omega: float,

@@ -181,6 +181,7 @@ struct occ_cosx_handle {
   unsigned long long *d_stats = nullptr;
   double *d_phi = nullptr, *d_F = nullptr, *d_G = nullptr;
   double *d_D = nullptr, *d_D2q = nullptr, *d_Kraw = nullptr, *d_K = nullptr, *d_proj = nullptr;
+  double *d_Dg = nullptr, *d_Kg = nullptr, *d_Kraw4 = nullptr; // general spinorbitals (allocated on first use)
   size_t npairs = 0, nprim_pairs = 0;
   struct ClassRange {
     int la, lb, pair0, npairs;
@@ -691,30 +692,56 @@ int occ_cosx_K_for_density(occ_cosx_handle *h, const double *D2q, double precisi
   return 0;
 }
 
-// compute_K_restricted / compute_K_unrestricted (:517-545, 617-660) and compute_K_range_separated (:830-860)
+// compute_K_restricted / _unrestricted / _general (:517-545, 617-660, 662-712) and compute_K_range_separated (:830-860)
 static int compute_K_impl(occ_cosx_handle *h, int kind, const double *D, double precision, double w_full, double w_lr,
                           double omega, double *K) {
   if (!h || !D || !K) return fail("occ_cosx_compute_K: null argument");
-  if (kind != 0 && kind != 1)
-    return fail("occ_cosx_compute_K: kind must be 0 (restricted) or 1 (unrestricted); general spinorbitals are not built");
+  if (kind < 0 || kind > 2)
+    return fail("occ_cosx_compute_K: kind must be 0 (restricted), 1 (unrestricted) or 2 (general)");
   CUDA_TRY(cudaSetDevice(h->device));
-  const int nbf = h->nbf, nspin = kind + 1, ld = nspin * nbf;
+  const int nbf = h->nbf;
+  const int rows = kind == 0 ? nbf : 2 * nbf, cols = kind == 2 ? 2 * nbf : nbf; // qm::matrix_dimensions
   const size_t n2 = static_cast<size_t>(nbf) * nbf;
   cudaStream_t st = h->stream;
-  CUDA_TRY(cudaMemcpyAsync(h->d_D, D, nspin * n2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (kind == 2 && !h->d_Dg) { // general: 2 nbf x 2 nbf in / out, four raw K' blocks
+    if (dev_alloc(h, &h->d_Dg, 4 * n2) || dev_alloc(h, &h->d_Kg, 4 * n2) || dev_alloc(h, &h->d_Kraw4, 4 * n2)) return 1;
+  }
+  double *dD = kind == 2 ? h->d_Dg : h->d_D, *dK = kind == 2 ? h->d_Kg : h->d_K;
+  CUDA_TRY(cudaMemcpyAsync(dD, D, static_cast<size_t>(rows) * cols * sizeof(double), cudaMemcpyHostToDevice, st));
   reset_info(h);
   const double two = 2.0, zero = 0.0;
-  for (int s = 0; s < nspin; ++s) {
-    // D2q = P . (2 D_s): the factor 2 is D2 = 2 D for restricted (:524) and the stored 1/2 for unrestricted (:632-633)
-    if (h->blas.dgemm(h->blas.h, CUBLAS_OP_N, CUBLAS_OP_N, nbf, nbf, nbf, &two, h->d_proj, nbf, h->d_D + s * nbf, ld, &zero,
-                      h->d_D2q, nbf) != CUBLAS_STATUS_SUCCESS)
+  // D2q = P . (2 D_block): the factor 2 is D2 = 2 D for restricted (:524) and the stored 1/2 otherwise (:632-633, 676-679)
+  auto project = [&](const double *Dblk) -> int {
+    if (h->blas.dgemm(h->blas.h, CUBLAS_OP_N, CUBLAS_OP_N, nbf, nbf, nbf, &two, h->d_proj, nbf, Dblk, rows, &zero, h->d_D2q,
+                      nbf) != CUBLAS_STATUS_SUCCESS)
       return fail("occ_cosx: cublasDgemm failed");
     h->info.gemm_calls += 1;
-    if (sweep(h, h->d_D2q, precision, w_full, w_lr, omega, h->d_Kraw)) return 1;
-    launch_cosx_symmetrize(h->d_Kraw, nbf, kind == 0 ? 0.25 : 0.5, h->d_K + s * nbf, ld, st);
-    h->info.launches += 1;
+    return 0;
+  };
+  if (kind < 2) {
+    for (int s = 0; s <= kind; ++s) {
+      if (project(dD + s * nbf)) return 1;
+      if (sweep(h, h->d_D2q, precision, w_full, w_lr, omega, h->d_Kraw)) return 1;
+      launch_cosx_symmetrize(h->d_Kraw, h->d_Kraw, nbf, kind == 0 ? 0.25 : 0.5, dK + s * nbf, rows, st);
+      h->info.launches += 1;
+    }
+  } else {
+    // blocks aa, ab, ba, bb of the column-major 2 nbf x 2 nbf matrix as qm::block defines them (include/occ/qm/opmatrix.h:
+    // 14-28): ab is the BOTTOM-LEFT block (rows/2, 0), ba the TOP-RIGHT one (0, cols/2)
+    const size_t off[4] = {0, static_cast<size_t>(nbf), static_cast<size_t>(nbf) * rows,
+                           static_cast<size_t>(nbf) * rows + nbf};
+    for (int blk = 0; blk < 4; ++blk) {
+      if (project(dD + off[blk])) return 1;
+      if (sweep(h, h->d_D2q, precision, w_full, w_lr, omega, h->d_Kraw4 + blk * n2)) return 1;
+    }
+    const double *Kaa = h->d_Kraw4, *Kab = h->d_Kraw4 + n2, *Kba = h->d_Kraw4 + 2 * n2, *Kbb = h->d_Kraw4 + 3 * n2;
+    launch_cosx_symmetrize(Kaa, Kaa, nbf, 0.5, dK + off[0], rows, st); // :697-698
+    launch_cosx_symmetrize(Kab, Kba, nbf, 0.5, dK + off[1], rows, st); // :700  Kab_sym = 0.5 (Kab + Kba^T)
+    launch_cosx_symmetrize(Kba, Kab, nbf, 0.5, dK + off[2], rows, st); // :701  Kba_sym = 0.5 (Kba + Kab^T)
+    launch_cosx_symmetrize(Kbb, Kbb, nbf, 0.5, dK + off[3], rows, st);
+    h->info.launches += 4;
   }
-  CUDA_TRY(cudaMemcpyAsync(K, h->d_K, nspin * n2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(K, dK, static_cast<size_t>(rows) * cols * sizeof(double), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   CUDA_TRY(cudaGetLastError());
   return 0;

@@ -50,7 +50,8 @@ void launch_cosx_tile_flags(const double *phi, const int *counts, int ntiles, in
                             int *tile_skip, void *stream);
 void launch_cosx_pair_flags(const CosxPair *pairs, const int *shell_size, int npairs, const double *D2q, int nbf,
                             double threshold, unsigned char *active, void *stream);
-void launch_cosx_symmetrize(const double *Kraw, int nbf, double factor, double *K, int ldK, void *stream);
+void launch_cosx_symmetrize(const double *Kraw, const double *KrawT, int nbf, double factor, double *K, int ldK,
+                            void *stream); // K = factor (Kraw + KrawT^T)
 void launch_cosx_scale_weights(double *phi_w, const double *phi, const double *pw, int ntiles, int nbf, int nbp,
                                void *stream);
 void upload_default_c2s();              // xc_host.cu: the collocation kernel's constant table

@@ -10,10 +10,13 @@
 //
 // B200 mapping: FP64 CUDA-core work (B200's DFMA rate, 33.9 TFLOP/s measured, is within 10 % of its FP64 tensor rate, so
 // the sparse form on the FMA pipe beats the dense form on DMMA). One thread per grid point, one CTA per (batch, run of
-// shell pairs of one (la, lb) class): the pair data (primitive exponents, centres, E tables) is CTA-uniform and staged
-// through shared memory; Boys values come from the reference's Chebyshev table for the highest order and the stable
-// downward recursion for the lower ones; the Hermite integrals R_tuv live in registers (compile-time indexed, one
-// instantiation per class); F and G move as coalesced 1 KiB columns of the batch slabs, G through red.global.add.f64.
+// 128-512 shell pairs of one (la >= lb) class; the higher-l shell is the register-resident side). Per round the CTA
+// screens 128 candidate pairs in parallel and compacts the survivors in order; their primitive records (exponent, centre,
+// 1D E tables) and F columns stream through a cp.async ring in shared memory. Boys values come from the reference's
+// Chebyshev table for the highest order and the stable downward recursion for the lower ones; for L = la + lb <= 3 the
+// Hermite integrals R_tuv live in registers, for L >= 4 they are produced and contracted slice by slice (k_cosx_esp.cuh).
+// Every index is a compile-time constant (one instantiation per class, spread over k_cosx_la*.cu so that they compile in
+// parallel). F and G move as coalesced 1 KiB columns of the batch slabs, G through red.global.add.f64.
 #include "k_cosx_esp.cuh"
 
 namespace xcb {
@@ -92,20 +95,22 @@ void launch_cosx_pair_flags(const CosxPair *pairs, const int *shell_size, int np
                                                                                        nbf, threshold, active);
 }
 
-// K = factor * (K' + K'^T)   (seminumerical_exchange.cpp:529, 645-646)
-__global__ void k_cosx_symmetrize(const double *__restrict__ Kraw, int nbf, double factor, double *__restrict__ K,
-                                  int ldK) {
+// K = factor * (A + B^T): A = B = K' for the spin-diagonal blocks (seminumerical_exchange.cpp:529, 645-646), A = K'_ab,
+// B = K'_ba for the off-diagonal blocks of a general spinorbital build (:640-645 of compute_K_general)
+__global__ void k_cosx_symmetrize(const double *__restrict__ Kraw, const double *__restrict__ KrawT, int nbf,
+                                  double factor, double *__restrict__ K, int ldK) {
   const int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 32 + threadIdx.y;
   __shared__ double t[32][33];
   const int ti = blockIdx.y * 32 + threadIdx.x, tj = blockIdx.x * 32 + threadIdx.y;
-  t[threadIdx.y][threadIdx.x] = (ti < nbf && tj < nbf) ? Kraw[ti + static_cast<size_t>(tj) * nbf] : 0.0;
+  t[threadIdx.y][threadIdx.x] = (ti < nbf && tj < nbf) ? KrawT[ti + static_cast<size_t>(tj) * nbf] : 0.0;
   __syncthreads();
   if (i < nbf && j < nbf)
     K[i + static_cast<size_t>(j) * ldK] = factor * (Kraw[i + static_cast<size_t>(j) * nbf] + t[threadIdx.x][threadIdx.y]);
 }
-void launch_cosx_symmetrize(const double *Kraw, int nbf, double factor, double *K, int ldK, void *stream) {
+void launch_cosx_symmetrize(const double *Kraw, const double *KrawT, int nbf, double factor, double *K, int ldK,
+                            void *stream) {
   dim3 grid((nbf + 31) / 32, (nbf + 31) / 32), block(32, 32);
-  k_cosx_symmetrize<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(Kraw, nbf, factor, K, ldK);
+  k_cosx_symmetrize<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(Kraw, KrawT, nbf, factor, K, ldK);
 }
 
 // (w phi) for the numerical overlap (seminumerical_exchange.cpp:366-369)

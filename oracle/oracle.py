@@ -461,6 +461,23 @@ def cosx_compute_K(basis: Basis, atom_off, pts, w, projector, D, unrestricted=Fa
     return out, stats
 
 
+def cosx_compute_K_general(basis: Basis, atom_off, pts, w, projector, D, precision=np.finfo(float).eps, omega=0.0,
+                           margin=1.0):
+    """SemiNumericalExchange::compute_K_general (seminumerical_exchange.cpp:658-712): D, K are (2 nbf, 2 nbf); the blocks
+    follow qm::block (include/occ/qm/opmatrix.h:14-28): ab = bottom-left, ba = top-right."""
+    n = basis.nbf
+    blk = {"aa": (slice(0, n), slice(0, n)), "ab": (slice(n, 2 * n), slice(0, n)), "ba": (slice(0, n), slice(n, 2 * n)),
+           "bb": (slice(n, 2 * n), slice(n, 2 * n))}
+    Kr = {k: cosx_K_for_density(basis, atom_off, pts, w, projector @ (2.0 * D[v]), precision, omega, margin)[0]
+          for k, v in blk.items()}
+    K = np.zeros((2 * n, 2 * n), order="F")
+    K[blk["aa"]] = 0.5 * (Kr["aa"] + Kr["aa"].T)
+    K[blk["bb"]] = 0.5 * (Kr["bb"] + Kr["bb"].T)
+    K[blk["ab"]] = 0.5 * (Kr["ab"] + Kr["ba"].T)
+    K[blk["ba"]] = 0.5 * (Kr["ba"] + Kr["ab"].T)
+    return K
+
+
 def ref_boys_table():
     R = ref_lib()
     n = R.occ_ref_boys_table(None)

@@ -88,6 +88,19 @@ def test_cosx_unrestricted_matches_oracle(oracle):
     sgx.close()
 
 
+def test_cosx_general_spinorbitals_match_oracle(oracle):
+    O, b, ob, off, pts, w, P, S, Sn, D, sgx = _setup(oracle, "water", "def2-svp", True)
+    n = b.nbf
+    rng = np.random.default_rng(5)
+    C = rng.normal(size=(2 * n, 5)) * 0.3
+    Dg = 0.5 * (C @ C.T)                     # symmetric general density with non-zero ab / ba blocks
+    K = sgx.compute_K(Dg, general=True)
+    Kref = O.cosx_compute_K_general(ob, off, pts, w, P, Dg)
+    assert np.abs(Kref[n:, :n]).max() > 1e-4 and np.abs(Kref[:n, n:] - Kref[n:, :n].T).max() < 1e-12
+    assert np.abs(K - Kref).max() < TOL
+    sgx.close()
+
+
 def test_cosx_long_range_and_fused_range_separated(oracle):
     O, b, ob, off, pts, w, P, S, Sn, D, sgx = _setup(oracle, "water", "def2-svp", True)
     omega, alpha, beta = 0.3, 1.0, -0.842294      # tests/dft_tests.cpp:434-436 (wB97X-style)
