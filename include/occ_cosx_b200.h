@@ -31,7 +31,7 @@ typedef struct {
   int device;               /* CUDA ordinal, -1 = current */
   int collect_stats;        /* 1 = count evaluated (batch, pair) combinations (adds one atomic per combination) */
   int rank, world_size;     /* grid batches are dealt round-robin to ranks; each rank returns a partial K (sum = K) */
-  int reserved[4];
+  int reserved[4];          /* [0] & 1: K' += Phi^T G through one cuBLAS call per batch instead of k_cosx_kgemm (A/B timing) */
 } occ_cosx_options_t;
 
 typedef struct occ_cosx_handle occ_cosx_handle;
@@ -84,6 +84,7 @@ typedef struct {
   double ms_collocate, ms_fgemm, ms_esp, ms_kgemm; /* device time of the last compute, by phase */
   size_t launches;           /* kernels of this library launched by the last compute (cuBLAS GEMMs not counted) */
   size_t gemm_calls;         /* cuBLAS calls of the last compute */
+  size_t kgemm_blocks;       /* (batch, 64-column block)s of G that were not identically zero, i.e. executed by k_cosx_kgemm */
 } occ_cosx_info_t;
 int occ_cosx_get_info(const occ_cosx_handle *h, occ_cosx_info_t *info);
 

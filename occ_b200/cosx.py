@@ -32,7 +32,7 @@ class CosxInfoT(C.Structure):
                 ("npairs", C.c_size_t), ("nprimitive_pairs", C.c_size_t), ("device_bytes", C.c_size_t),
                 ("pair_evals", C.c_size_t), ("skipped_batches", C.c_size_t), ("dense_flops", C.c_double),
                 ("gemm_flops", C.c_double), ("ms_collocate", C.c_double), ("ms_fgemm", C.c_double),
-                ("ms_esp", C.c_double), ("ms_kgemm", C.c_double), ("launches", C.c_size_t), ("gemm_calls", C.c_size_t)]
+                ("ms_esp", C.c_double), ("ms_kgemm", C.c_double), ("launches", C.c_size_t), ("gemm_calls", C.c_size_t), ("kgemm_blocks", C.c_size_t)]
 
 
 def sgx_grid_settings(angular_points: int = 50, radial_precision: float = 1e-5) -> GridSettings:
@@ -59,7 +59,7 @@ def batch_shard(atom_offsets, rank: int, world_size: int):
 class SemiNumericalExchange:
     def __init__(self, basis: AOBasis, settings: GridSettings | None = None, atom_grids=None, device: int = -1,
                  margin: float = 1.0, collect_stats: bool = False, batch_bytes: int = 0, rank: int = 0,
-                 world_size: int = 1, projector: np.ndarray | None | str = "auto"):
+                 world_size: int = 1, projector: np.ndarray | None | str = "auto", kgemm_library: bool = False):
         """SemiNumericalExchange(basis, grid settings) (seminumerical_exchange.cpp:245-275). atom_grids, when given, is
         (offsets[natoms+1], points (N,3), weights (N,)) — the reference's m_atom_grids."""
         L = lib()
@@ -78,6 +78,7 @@ class SemiNumericalExchange:
         self.weights = np.ascontiguousarray(w, dtype=np.float64)
         self._ba = BasisArrays(basis.as_arrays())
         opt = CosxOptionsT(margin, 0.0, 0.0, batch_bytes, device, int(collect_stats), rank, world_size)
+        opt.reserved[0] = 1 if kgemm_library else 0   # A/B timing switch: cuBLAS per batch instead of k_cosx_kgemm
         self._h = C.c_void_p()
         L.occ_cosx_destroy.restype = None
         L.occ_cosx_destroy.argtypes = [C.c_void_p]

@@ -168,6 +168,7 @@ struct occ_cosx_handle {
   int ntiles = 0, tiles_per_chunk = 1, nruns = 1;
   double margin = 1.0, density_threshold = 1e-6;
   bool collect = false;
+  bool kgemm_library = false;
   std::vector<void *> allocs;
   size_t alloc_bytes = 0;
   BuildParams B = {};      // what k_collocate reads
@@ -258,6 +259,7 @@ int occ_cosx_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_
   h->margin = (opt && opt->margin > 0.0) ? opt->margin : 1.0;
   h->density_threshold = (opt && opt->density_threshold > 0.0) ? opt->density_threshold : 1e-6;
   h->collect = opt && opt->collect_stats;
+  h->kgemm_library = opt && (opt->reserved[0] & 1);
   const double pair_threshold = (opt && opt->pair_threshold > 0.0) ? opt->pair_threshold : 1e-12;
   const size_t batch_bytes = (opt && opt->batch_bytes) ? opt->batch_bytes : (size_t(4096) << 20);
   h->npts = atom_offsets[natoms] - atom_offsets[0];
@@ -513,7 +515,7 @@ int occ_cosx_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_
     CHECK(dev_upload(h, &h->d_c2s, c2s));
   }
   CHECK(dev_alloc(h, &h->d_active, h->npairs));
-  CHECK(dev_alloc(h, &h->d_stats, 32));
+  CHECK(dev_alloc(h, &h->d_stats, 40));
   const size_t slab_d = static_cast<size_t>(h->nbp) * TILE_P * h->tiles_per_chunk;
   CHECK(dev_alloc(h, &h->d_phi, slab_d));
   CHECK(dev_alloc(h, &h->d_F, slab_d));
@@ -567,7 +569,7 @@ static int sweep(occ_cosx_handle *h, const double *D2q, double precision, double
   launch_cosx_pair_flags(h->d_pairs, h->d_shell_size, static_cast<int>(h->npairs), D2q, nbf, h->density_threshold,
                          h->d_active, st);
   h->info.launches += 1;
-  if (h->collect) CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, 32 * sizeof(unsigned long long), st));
+  if (h->collect) CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, 40 * sizeof(unsigned long long), st));
   CosxParams P = {};
   P.pairs = h->d_pairs;
   P.pool = h->d_pool;
@@ -616,13 +618,18 @@ static int sweep(occ_cosx_handle *h, const double *D2q, double precision, double
       h->info.launches += 1;
     }
     if (h->collect) cudaEventRecord(h->ev[3], st);
-    // K' += Phi_t^T . G_t (:797; G here is the reference's -Gg)
-    for (int t = 0; t < nt; ++t) {
-      if (h->blas.dgemm(h->blas.h, CUBLAS_OP_T, CUBLAS_OP_N, nbf, nbf, TILE_P, &one, h->d_phi + t * slab, TILE_P,
-                        h->d_G + t * slab, TILE_P, &one, Kraw, nbf) != CUBLAS_STATUS_SUCCESS)
-        return fail("occ_cosx: cublasDgemm failed");
+    // K' += Phi_t^T . G_t (:797; G here is the reference's -Gg): k_cosx_kgemm, one launch per chunk
+    if (h->kgemm_library) { // A/B switch (options.reserved[0] & 1): one cuBLAS call per batch
+      for (int t = 0; t < nt; ++t) {
+        if (h->blas.dgemm(h->blas.h, CUBLAS_OP_T, CUBLAS_OP_N, nbf, nbf, TILE_P, &one, h->d_phi + t * slab, TILE_P,
+                          h->d_G + t * slab, TILE_P, &one, Kraw, nbf) != CUBLAS_STATUS_SUCCESS)
+          return fail("occ_cosx: cublasDgemm failed");
+      }
+      h->info.gemm_calls += nt;
+    } else {
+      launch_cosx_kgemm(h->d_phi, h->d_G, h->d_skip + t0, nt, nbf, nbp, Kraw, h->collect ? h->d_stats + 32 : nullptr, st);
+      h->info.launches += 1;
     }
-    h->info.gemm_calls += nt;
     if (h->collect) {
       cudaEventRecord(h->ev[4], st);
       CUDA_TRY(cudaEventSynchronize(h->ev[4]));
@@ -635,7 +642,7 @@ static int sweep(occ_cosx_handle *h, const double *D2q, double precision, double
   }
   CUDA_TRY(cudaGetLastError());
   if (h->collect) {
-    unsigned long long st_h[32];
+    unsigned long long st_h[40];
     CUDA_TRY(cudaMemcpyAsync(st_h, h->d_stats, sizeof(st_h), cudaMemcpyDeviceToHost, st));
     int skip_n = 0;
     std::vector<int> sk(h->ntiles);
@@ -649,6 +656,7 @@ static int sweep(occ_cosx_handle *h, const double *D2q, double precision, double
       h->info.pair_evals += st_h[2 * cls];
       h->info.dense_flops += 2.0 * nherm * nab * static_cast<double>(st_h[2 * cls + 1]);
     }
+    h->info.kgemm_blocks += st_h[32];
     h->info.ms_collocate += ms[0];
     h->info.ms_fgemm += ms[1];
     h->info.ms_esp += ms[2];
@@ -667,6 +675,7 @@ static void reset_info(occ_cosx_handle *h) {
   h->info.ms_collocate = h->info.ms_fgemm = h->info.ms_esp = h->info.ms_kgemm = 0.0;
   h->info.launches = 0;
   h->info.gemm_calls = 0;
+  h->info.kgemm_blocks = 0;
 }
 
 int occ_cosx_K_for_density_device(occ_cosx_handle *h, const double *D2q_dev, double precision, double w_full,

@@ -54,6 +54,9 @@ void launch_cosx_symmetrize(const double *Kraw, const double *KrawT, int nbf, do
                             void *stream); // K = factor (Kraw + KrawT^T)
 void launch_cosx_scale_weights(double *phi_w, const double *phi, const double *pw, int ntiles, int nbf, int nbp,
                                void *stream);
+// K' += Phi_t^T . G_t for the ntiles batches of a chunk (k_cosx_kgemm.cu); stats[0] += non-zero (batch, column block)s
+void launch_cosx_kgemm(const double *phi, const double *G, const int *tile_skip, int ntiles, int nbf, int nbp, double *K,
+                       unsigned long long *stats, void *stream);
 void upload_default_c2s();              // xc_host.cu: the collocation kernel's constant table
 const double *c2s_racah_table(int l);   // xc_host.cu: (2l+1) x ncart(l), Racah-normalised, CCA order
 

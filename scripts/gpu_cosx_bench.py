@@ -8,18 +8,20 @@ from occ_b200 import aobasis, molecules, cosx
 
 
 def run(mol, bas, pure, angular, cpu_batches=0, reps=3, radial_precision=1e-5):
+    lib_k = os.environ.get("COSX_KGEMM_LIBRARY", "0") == "1"   # A/B: K' += Phi^T G through cuBLAS per batch
     Z, pos = molecules.MOLECULES[mol]()
     b = aobasis.AOBasis.load(Z, pos, bas, pure=pure)
     D = molecules.synthetic_density(b, 1) * 0.5
     t0 = time.perf_counter()
-    sgx = cosx.SemiNumericalExchange(b, cosx.sgx_grid_settings(angular, radial_precision), collect_stats=True)
+    sgx = cosx.SemiNumericalExchange(b, cosx.sgx_grid_settings(angular, radial_precision), collect_stats=True,
+                                     kgemm_library=lib_k)
     t_setup = time.perf_counter() - t0
     K = sgx.compute_K(D)
     info = sgx.info()
     sgx.close()
     # timed handle without the per-pair counters (one atomic per evaluated pair) and without per-chunk event syncs
     sgx = cosx.SemiNumericalExchange(b, atom_grids=(sgx.atom_offsets, sgx.points, sgx.weights),
-                                     projector=sgx.overlap_projector)
+                                     projector=sgx.overlap_projector, kgemm_library=lib_k)
     sgx.compute_K(D)
     ts = []
     for _ in range(reps):
@@ -32,6 +34,8 @@ def run(mol, bas, pure, angular, cpu_batches=0, reps=3, radial_precision=1e-5):
            "phase_ms_profiled_call": {k: info[k] for k in ("ms_collocate", "ms_fgemm", "ms_esp", "ms_kgemm")},
            "dense_equivalent_esp_tflops": info["dense_flops"] / min(ts) / 1e12, "dense_esp_flops": info["dense_flops"],
            "gemm_flops": info["gemm_flops"], "launches": info["launches"], "gemm_calls": info["gemm_calls"],
+           "kgemm": "cublas per batch" if lib_k else "k_cosx_kgemm", "kgemm_blocks_executed": info["kgemm_blocks"],
+           "kgemm_blocks_total": info["nbatches"] * ((b.nbf + 63) // 64),
            "setup_s": t_setup, "device_bytes": info["device_bytes"], "K_absmax": float(np.abs(K).max()),
            "repeatability": float(np.abs(K - K2).max())}
     if cpu_batches:
