@@ -40,6 +40,13 @@ public:
                  double precision = std::numeric_limits<double>::epsilon()) const {
     check(occ_cosx_compute_K(m_h, kind == SpinorbitalKind::Unrestricted ? 1 : 0, D, precision, m_omega, K));
   }
+  // the same with the occupied orbitals (mo.Cocc) as well: C = [C_alpha | C_beta], nbf rows, scaled so that 2 D_s = C_s C_s^T
+  // (restricted: sqrt(2) Cocc; unrestricted: Cocc_s). F = Phi.D2q runs in the factorised form (occ_cosx_compute_K_mo).
+  void compute_K_mo(SpinorbitalKind kind, const double *D, const double *C, int nocc_alpha, int nocc_beta, double *K,
+                    double precision = std::numeric_limits<double>::epsilon()) const {
+    check(occ_cosx_compute_K_mo(m_h, kind == SpinorbitalKind::Unrestricted ? 1 : 0, D, C, nocc_alpha, nocc_beta, precision,
+                                m_omega, K));
+  }
   // general spinorbitals: D and K are 2 nbf x 2 nbf (compute_K_general, seminumerical_exchange.cpp:658-712)
   void compute_K_general(const double *D, double *K, double precision = std::numeric_limits<double>::epsilon()) const {
     check(occ_cosx_compute_K(m_h, 2, D, precision, m_omega, K));

@@ -57,6 +57,18 @@ int occ_cosx_compute_K(occ_cosx_handle *h, int kind, const double *D, double pre
 int occ_cosx_compute_K_range_separated(occ_cosx_handle *h, const double *D, double alpha, double beta, double omega,
                                        double precision, double *K);
 
+/* The same two builds for callers that also hand over the occupied orbitals — the reference's seam receives `mo`
+ * (compute_K(const MolecularOrbitals &mo, ...), include/occ/qm/seminumerical_exchange.h:108), which holds mo.D and
+ * mo.Cocc.  C holds one block per spin, block s nbf x nocc_s column-major (ld = nbf), beta after alpha, scaled so that
+ * 2 D_s = C_s C_s^T (restricted: C = sqrt(2) Cocc; unrestricted: C_s = Cocc_s, because mo.D stores the halved blocks —
+ * the convention of occ_xc_build_mo).  Same K up to the rounding of C C^T, but F = Phi.D2q runs in the factorised form
+ * F = (Phi . (P C)) . C^T: 4 n nbf nocc flops instead of 2 n nbf^2 (valinomycin def2-TZVP, nocc 300 of 3348: 215 -> ~45
+ * ms).  D is still required: the density screen of the shell pairs reads D2q = P.(2D) (:758-764).  kind 0 or 1. */
+int occ_cosx_compute_K_mo(occ_cosx_handle *h, int kind, const double *D, const double *C, int nocc_alpha, int nocc_beta,
+                          double precision, double omega, double *K);
+int occ_cosx_compute_K_range_separated_mo(occ_cosx_handle *h, const double *D, const double *C, int nocc, double alpha,
+                                          double beta, double omega, double precision, double *K);
+
 /* compute_K_for_density (:817-828): the raw, unsymmetrised K' of one projected density D2q (nbf x nbf); with
  * w_full / w_lr the fused two-operator form. Device-resident variant: pointers are device memory on h's device. */
 int occ_cosx_K_for_density(occ_cosx_handle *h, const double *D2q, double precision, double omega, double *K);
@@ -80,7 +92,7 @@ typedef struct {
   size_t pair_evals;         /* (batch, pair) combinations evaluated after both screens */
   size_t skipped_batches;    /* batches with max(phi) < precision (:729-730) */
   double dense_flops;        /* 2 npt nherm nab per evaluated primitive pair: the reference's R.E^T product (esp.cpp:113-121) */
-  double gemm_flops;         /* F = phi D2q and K = phi^T G: 4 npt nbf^2 per batch */
+  double gemm_flops;         /* F = phi D2q and K = phi^T G: 4 npt nbf^2 (factorised F: 2 npt nbf^2 + 4 npt nbf nocc) */
   double ms_collocate, ms_fgemm, ms_esp, ms_kgemm; /* device time of the last compute, by phase */
   size_t launches;           /* kernels of this library launched by the last compute (cuBLAS GEMMs not counted) */
   size_t gemm_calls;         /* cuBLAS calls of the last compute */

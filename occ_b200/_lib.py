@@ -20,7 +20,8 @@ SYMBOLS = ["occ_xc_create", "occ_xc_build", "occ_xc_build_device", "occ_xc_build
            "occ_xc_partition_leaves", "occ_xc_register_lebedev", "occ_xc_grid_create", "occ_xc_grid_from_points", "occ_xc_grid_npts",
            "occ_xc_grid_nleaves", "occ_xc_grid_atom_info", "occ_xc_grid_copy", "occ_xc_grid_destroy"]
 # every symbol include/occ_cosx_b200.h declares
-COSX_SYMBOLS = ["occ_cosx_create", "occ_cosx_compute_K", "occ_cosx_compute_K_range_separated", "occ_cosx_K_for_density",
+COSX_SYMBOLS = ["occ_cosx_create", "occ_cosx_compute_K", "occ_cosx_compute_K_range_separated", "occ_cosx_compute_K_mo",
+                "occ_cosx_compute_K_range_separated_mo", "occ_cosx_K_for_density",
                 "occ_cosx_K_for_density_device", "occ_cosx_numerical_overlap", "occ_cosx_analytic_overlap",
                 "occ_cosx_set_projector", "occ_cosx_get_info", "occ_cosx_destroy"]
 

@@ -127,6 +127,41 @@ class SemiNumericalExchange:
         check(lib().occ_cosx_compute_K(self._h, kind, ptr(D), precision, self.omega, ptr(K)))
         return K
 
+    def compute_K_mo(self, D: np.ndarray, Cocc, precision: float = np.finfo(np.float64).eps, unrestricted: bool = False):
+        """compute_K(mo) with the occupied orbitals as well (mo.D and mo.Cocc both live in `mo`): Cocc is the restricted
+        (nbf, nocc) block with 2 D = C C^T, or the pair (C_alpha, C_beta) with 2 D_s = C_s C_s^T. F = Phi.D2q then runs in
+        the factorised form (occ_cosx_compute_K_mo)."""
+        nbf = self.basis.nbf
+        kind = 1 if unrestricted else 0
+        shape = ((nbf, nbf), (2 * nbf, nbf))[kind]
+        D = np.asfortranarray(D, dtype=np.float64)
+        if D.shape != shape:
+            raise RuntimeError(f"compute_K_mo: density matrix of shape {D.shape}, expected {shape}")
+        blocks = [np.asarray(c, dtype=np.float64).reshape(nbf, -1) for c in (Cocc if unrestricted else (Cocc,))]
+        nocc = [b.shape[1] for b in blocks] + [0]
+        Cp = np.asfortranarray(np.concatenate(blocks, axis=1)) if sum(nocc) else np.zeros((nbf, 1), order="F")
+        K = np.zeros(shape, order="F")
+        L = lib()
+        L.occ_cosx_compute_K_mo.restype = C.c_int
+        L.occ_cosx_compute_K_mo.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                            C.c_double, C.c_double, C.c_void_p]
+        check(L.occ_cosx_compute_K_mo(self._h, kind, ptr(D), ptr(Cp), nocc[0], nocc[1], precision, self.omega, ptr(K)))
+        return K
+
+    def compute_K_range_separated_mo(self, D, Cocc, alpha: float, beta: float, omega: float,
+                                     precision: float = np.finfo(np.float64).eps):
+        nbf = self.basis.nbf
+        D = np.asfortranarray(D, dtype=np.float64)
+        Cp = np.asfortranarray(np.asarray(Cocc, dtype=np.float64).reshape(nbf, -1))
+        K = np.zeros((nbf, nbf), order="F")
+        L = lib()
+        L.occ_cosx_compute_K_range_separated_mo.restype = C.c_int
+        L.occ_cosx_compute_K_range_separated_mo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double,
+                                                            C.c_double, C.c_double, C.c_double, C.c_void_p]
+        check(L.occ_cosx_compute_K_range_separated_mo(self._h, ptr(D), ptr(Cp), Cp.shape[1], alpha, beta, omega,
+                                                      precision, ptr(K)))
+        return K
+
     def compute_K_range_separated(self, D, alpha: float, beta: float, omega: float,
                                   precision: float = np.finfo(np.float64).eps):
         nbf = self.basis.nbf

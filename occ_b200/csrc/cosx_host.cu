@@ -183,6 +183,8 @@ struct occ_cosx_handle {
   double *d_phi = nullptr, *d_F = nullptr, *d_G = nullptr;
   double *d_D = nullptr, *d_D2q = nullptr, *d_Kraw = nullptr, *d_K = nullptr, *d_proj = nullptr;
   double *d_Dg = nullptr, *d_Kg = nullptr, *d_Kraw4 = nullptr; // general spinorbitals (allocated on first use)
+  double *d_C = nullptr, *d_Cq = nullptr, *d_psi = nullptr;    // factorised F (occ_cosx_compute_K_mo; allocated on first use)
+  int mo_cap = 0;                                               // orbitals per spin the three buffers hold
   size_t npairs = 0, nprim_pairs = 0;
   struct ClassRange {
     int la, lb, pair0, npairs;
@@ -560,8 +562,10 @@ int occ_cosx_set_projector(occ_cosx_handle *h, const double *P) {
 }
 
 // seminumerical_exchange_sweep (:660-815) for one projected density already on the device
+// Cq / Cs (nbf x nocc each, or NULL): the factorised form D2q = Cq . Cs^T of the same matrix — F_t = (Phi_t Cq) Cs^T then
+// costs 4 n nbf nocc flops instead of 2 n nbf^2; D2q itself is still read by the density screen of the pairs (:758-764)
 static int sweep(occ_cosx_handle *h, const double *D2q, double precision, double w_full, double w_lr, double omega,
-                 double *Kraw) {
+                 double *Kraw, const double *Cq = nullptr, const double *Cs = nullptr, int nocc = 0) {
   const int nbf = h->nbf, nbp = h->nbp;
   cudaStream_t st = h->stream;
   const size_t n2 = static_cast<size_t>(nbf) * nbf;
@@ -606,10 +610,22 @@ static int sweep(occ_cosx_handle *h, const double *D2q, double precision, double
     h->info.launches += 2;
     if (h->collect) cudaEventRecord(h->ev[1], st);
     // F_t = Phi_t . D2q for every batch of the chunk (:733-734, the weight is applied when F is read)
-    if (h->blas.dgemm_sb(h->blas.h, CUBLAS_OP_N, CUBLAS_OP_N, TILE_P, nbf, nbf, &one, h->d_phi, TILE_P, slab, D2q, nbf, 0,
-                         &zero, h->d_F, TILE_P, slab, nt) != CUBLAS_STATUS_SUCCESS)
-      return fail("occ_cosx: cublasDgemmStridedBatched failed");
-    h->info.gemm_calls += 1;
+    if (Cq && nocc > 0) {
+      const long long pslab = static_cast<long long>(nocc) * TILE_P;
+      if (h->blas.dgemm_sb(h->blas.h, CUBLAS_OP_N, CUBLAS_OP_N, TILE_P, nocc, nbf, &one, h->d_phi, TILE_P, slab, Cq, nbf, 0,
+                           &zero, h->d_psi, TILE_P, pslab, nt) != CUBLAS_STATUS_SUCCESS ||
+          h->blas.dgemm_sb(h->blas.h, CUBLAS_OP_N, CUBLAS_OP_T, TILE_P, nbf, nocc, &one, h->d_psi, TILE_P, pslab, Cs, nbf, 0,
+                           &zero, h->d_F, TILE_P, slab, nt) != CUBLAS_STATUS_SUCCESS)
+        return fail("occ_cosx: cublasDgemmStridedBatched failed");
+      h->info.gemm_calls += 2;
+    } else if (Cq) { // no occupied orbital of this spin: D2q = 0
+      CUDA_TRY(cudaMemsetAsync(h->d_F, 0, static_cast<size_t>(nt) * slab * sizeof(double), st));
+    } else {
+      if (h->blas.dgemm_sb(h->blas.h, CUBLAS_OP_N, CUBLAS_OP_N, TILE_P, nbf, nbf, &one, h->d_phi, TILE_P, slab, D2q, nbf, 0,
+                           &zero, h->d_F, TILE_P, slab, nt) != CUBLAS_STATUS_SUCCESS)
+        return fail("occ_cosx: cublasDgemmStridedBatched failed");
+      h->info.gemm_calls += 1;
+    }
     CUDA_TRY(cudaMemsetAsync(h->d_G, 0, static_cast<size_t>(nt) * slab * sizeof(double), st));
     if (h->collect) cudaEventRecord(h->ev[2], st);
     P.tile0 = t0;
@@ -664,7 +680,7 @@ static int sweep(occ_cosx_handle *h, const double *D2q, double precision, double
   }
   double npt_local = 0.0;
   for (int c : h->h_counts) npt_local += c;
-  h->info.gemm_flops += 4.0 * npt_local * nbf * nbf;
+  h->info.gemm_flops += 2.0 * npt_local * nbf * nbf + (Cq ? 4.0 * npt_local * nbf * nocc : 2.0 * npt_local * nbf * nbf);
   return 0;
 }
 
@@ -703,8 +719,11 @@ int occ_cosx_K_for_density(occ_cosx_handle *h, const double *D2q, double precisi
 
 // compute_K_restricted / _unrestricted / _general (:517-545, 617-660, 662-712) and compute_K_range_separated (:830-860)
 static int compute_K_impl(occ_cosx_handle *h, int kind, const double *D, double precision, double w_full, double w_lr,
-                          double omega, double *K) {
+                          double omega, double *K, const double *C = nullptr, int nocc_a = 0, int nocc_b = 0) {
   if (!h || !D || !K) return fail("occ_cosx_compute_K: null argument");
+  if (C && kind == 2) return fail("occ_cosx_compute_K_mo: restricted (0) or unrestricted (1) only");
+  if (C && (nocc_a < 0 || nocc_b < 0 || nocc_a > h->nbf || nocc_b > h->nbf))
+    return fail("occ_cosx_compute_K_mo: occupied counts outside [0, nbf]");
   if (kind < 0 || kind > 2)
     return fail("occ_cosx_compute_K: kind must be 0 (restricted), 1 (unrestricted) or 2 (general)");
   CUDA_TRY(cudaSetDevice(h->device));
@@ -718,7 +737,28 @@ static int compute_K_impl(occ_cosx_handle *h, int kind, const double *D, double 
   double *dD = kind == 2 ? h->d_Dg : h->d_D, *dK = kind == 2 ? h->d_Kg : h->d_K;
   CUDA_TRY(cudaMemcpyAsync(dD, D, static_cast<size_t>(rows) * cols * sizeof(double), cudaMemcpyHostToDevice, st));
   reset_info(h);
-  const double two = 2.0, zero = 0.0;
+  const double two = 2.0, zero = 0.0, one = 1.0;
+  const int nocc_s[2] = {nocc_a, kind == 1 ? nocc_b : 0};
+  if (C) { // orbitals on the device: [C_alpha | C_beta], nbf rows
+    const int cap = std::max(1, std::max(nocc_s[0], nocc_s[1]));
+    if (cap > h->mo_cap) {
+      if (dev_alloc(h, &h->d_C, 2 * static_cast<size_t>(nbf) * cap) || dev_alloc(h, &h->d_Cq, static_cast<size_t>(nbf) * cap) ||
+          dev_alloc(h, &h->d_psi, static_cast<size_t>(h->tiles_per_chunk) * TILE_P * cap))
+        return 1;
+      h->mo_cap = cap;
+    }
+    const size_t ncol = static_cast<size_t>(nocc_s[0]) + nocc_s[1];
+    if (ncol) CUDA_TRY(cudaMemcpyAsync(h->d_C, C, ncol * nbf * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  // Cq = P . C_s, so that Cq C_s^T = P (2 D_s)
+  auto project_orbitals = [&](const double *Cs, int nocc) -> int {
+    if (nocc == 0) return 0;
+    if (h->blas.dgemm(h->blas.h, CUBLAS_OP_N, CUBLAS_OP_N, nbf, nocc, nbf, &one, h->d_proj, nbf, Cs, nbf, &zero, h->d_Cq,
+                      nbf) != CUBLAS_STATUS_SUCCESS)
+      return fail("occ_cosx: cublasDgemm failed");
+    h->info.gemm_calls += 1;
+    return 0;
+  };
   // D2q = P . (2 D_block): the factor 2 is D2 = 2 D for restricted (:524) and the stored 1/2 otherwise (:632-633, 676-679)
   auto project = [&](const double *Dblk) -> int {
     if (h->blas.dgemm(h->blas.h, CUBLAS_OP_N, CUBLAS_OP_N, nbf, nbf, nbf, &two, h->d_proj, nbf, Dblk, rows, &zero, h->d_D2q,
@@ -730,7 +770,9 @@ static int compute_K_impl(occ_cosx_handle *h, int kind, const double *D, double 
   if (kind < 2) {
     for (int s = 0; s <= kind; ++s) {
       if (project(dD + s * nbf)) return 1;
-      if (sweep(h, h->d_D2q, precision, w_full, w_lr, omega, h->d_Kraw)) return 1;
+      const double *Cs = C ? h->d_C + static_cast<size_t>(s) * nocc_s[0] * nbf : nullptr;
+      if (C && project_orbitals(Cs, nocc_s[s])) return 1;
+      if (sweep(h, h->d_D2q, precision, w_full, w_lr, omega, h->d_Kraw, C ? h->d_Cq : nullptr, Cs, nocc_s[s])) return 1;
       launch_cosx_symmetrize(h->d_Kraw, h->d_Kraw, nbf, kind == 0 ? 0.25 : 0.5, dK + s * nbf, rows, st);
       h->info.launches += 1;
     }
@@ -767,6 +809,21 @@ int occ_cosx_compute_K_range_separated(occ_cosx_handle *h, const double *D, doub
   return compute_K_impl(h, 0, D, precision, alpha + beta, -beta, omega, K);
 }
 
+int occ_cosx_compute_K_mo(occ_cosx_handle *h, int kind, const double *D, const double *C, int nocc_alpha, int nocc_beta,
+                          double precision, double omega, double *K) {
+  if (!C) return fail("occ_cosx_compute_K_mo: null argument");
+  if (omega < 0.0) return fail("occ_cosx_compute_K_mo: omega must be >= 0");
+  return compute_K_impl(h, kind, D, precision, omega > 0.0 ? 0.0 : 1.0, omega > 0.0 ? 1.0 : 0.0, omega, K, C, nocc_alpha,
+                        nocc_beta);
+}
+
+int occ_cosx_compute_K_range_separated_mo(occ_cosx_handle *h, const double *D, const double *C, int nocc, double alpha,
+                                          double beta, double omega, double precision, double *K) {
+  if (!C) return fail("occ_cosx_compute_K_range_separated_mo: null argument");
+  if (!(omega > 0.0)) return fail("occ_cosx_compute_K_range_separated_mo: omega must be > 0");
+  return compute_K_impl(h, 0, D, precision, alpha + beta, -beta, omega, K, C, nocc, 0);
+}
+
 int occ_cosx_analytic_overlap(occ_cosx_handle *h, double *S) {
   if (!h || !S) return fail("occ_cosx_analytic_overlap: null argument");
   std::memcpy(S, h->S_analytic.data(), h->S_analytic.size() * sizeof(double));
@@ -781,16 +838,12 @@ int occ_cosx_numerical_overlap(occ_cosx_handle *h, double *Sn) {
   const size_t n2 = static_cast<size_t>(nbf) * nbf;
   cudaStream_t st = h->stream;
   CUDA_TRY(cudaMemsetAsync(h->d_Kraw, 0, n2 * sizeof(double), st));
-  const double one = 1.0;
-  const long long slab = static_cast<long long>(nbp) * TILE_P;
+  CUDA_TRY(cudaMemsetAsync(h->d_skip, 0, sizeof(int) * h->ntiles, st)); // no batch is skipped here (:352-377)
   for (int t0 = 0; t0 < h->ntiles; t0 += h->tiles_per_chunk) {
     const int nt = std::min(h->tiles_per_chunk, h->ntiles - t0);
     launch_collocate(h->B, h->d_items + static_cast<size_t>(t0) * h->nruns, nt * h->nruns, st);
     launch_cosx_scale_weights(h->d_F, h->d_phi, h->d_pw_ovl + static_cast<size_t>(t0) * TILE_P, nt, nbf, nbp, st);
-    for (int t = 0; t < nt; ++t)
-      if (h->blas.dgemm(h->blas.h, CUBLAS_OP_T, CUBLAS_OP_N, nbf, nbf, TILE_P, &one, h->d_phi + t * slab, TILE_P,
-                        h->d_F + t * slab, TILE_P, &one, h->d_Kraw, nbf) != CUBLAS_STATUS_SUCCESS)
-        return fail("occ_cosx: cublasDgemm failed");
+    launch_cosx_kgemm(h->d_phi, h->d_F, h->d_skip + t0, nt, nbf, nbp, h->d_Kraw, nullptr, st);
   }
   CUDA_TRY(cudaMemcpyAsync(Sn, h->d_Kraw, n2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));

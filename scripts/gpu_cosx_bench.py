@@ -18,6 +18,9 @@ def run(mol, bas, pure, angular, cpu_batches=0, reps=3, radial_precision=1e-5):
     t_setup = time.perf_counter() - t0
     K = sgx.compute_K(D)
     info = sgx.info()
+    Cocc = molecules.synthetic_orbitals(b, 1)[0]          # 2 D = Cocc Cocc^T (the orbitals behind synthetic_density)
+    Kmo = sgx.compute_K_mo(D, Cocc)
+    info_mo = sgx.info()
     sgx.close()
     # timed handle without the per-pair counters (one atomic per evaluated pair) and without per-chunk event syncs
     sgx = cosx.SemiNumericalExchange(b, atom_grids=(sgx.atom_offsets, sgx.points, sgx.weights),
@@ -26,6 +29,10 @@ def run(mol, bas, pure, angular, cpu_batches=0, reps=3, radial_precision=1e-5):
     ts = []
     for _ in range(reps):
         t0 = time.perf_counter(); K2 = sgx.compute_K(D); ts.append(time.perf_counter() - t0)
+    sgx.compute_K_mo(D, Cocc)
+    ts_mo = []
+    for _ in range(reps):
+        t0 = time.perf_counter(); sgx.compute_K_mo(D, Cocc); ts_mo.append(time.perf_counter() - t0)
     n = sgx.num_grid_points()
     out = {"row": "f-2 COSX compute_K", "workload": f"{mol}/{bas} {'spherical' if pure else 'cartesian'} RKS, sgx grid {angular} angular, radial precision {radial_precision:g}",
            "nbf": b.nbf, "grid_points": n, "batches": info["nbatches"], "shell_pairs": info["npairs"],
@@ -36,6 +43,10 @@ def run(mol, bas, pure, angular, cpu_batches=0, reps=3, radial_precision=1e-5):
            "gemm_flops": info["gemm_flops"], "launches": info["launches"], "gemm_calls": info["gemm_calls"],
            "kgemm": "cublas per batch" if lib_k else "k_cosx_kgemm", "kgemm_blocks_executed": info["kgemm_blocks"],
            "kgemm_blocks_total": info["nbatches"] * ((b.nbf + 63) // 64),
+           "mo_form": {"entry": "occ_cosx_compute_K_mo (F = (Phi.(P C)).C^T)", "nocc": int(Cocc.shape[1]),
+                       "ms_per_call": 1e3 * min(ts_mo), "grid_points_per_s": n / min(ts_mo),
+                       "phase_ms_profiled_call": {k: info_mo[k] for k in ("ms_collocate", "ms_fgemm", "ms_esp", "ms_kgemm")},
+                       "gemm_flops": info_mo["gemm_flops"], "max_abs_diff_vs_D_form": float(np.abs(Kmo - K).max())},
            "setup_s": t_setup, "device_bytes": info["device_bytes"], "K_absmax": float(np.abs(K).max()),
            "repeatability": float(np.abs(K - K2).max())}
     if cpu_batches:

@@ -14,6 +14,7 @@ int main(void) {
   if (occ_cosx_create(NULL, 0, NULL, NULL, NULL, NULL, &opt, &h) == 0) return 1;
   if (strstr(occ_xc_last_error(), "null") == NULL) return 2;
   if (occ_cosx_compute_K(NULL, 0, NULL, 1e-16, 0.0, NULL) == 0) return 3;
+  if (occ_cosx_compute_K_mo(NULL, 0, NULL, NULL, 0, 0, 1e-16, 0.0, NULL) == 0) return 3;
   if (occ_cosx_get_info(NULL, &info) == 0) return 4;
   occ_cosx_destroy(NULL);
   printf("ok\n");

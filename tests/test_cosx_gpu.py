@@ -88,6 +88,47 @@ def test_cosx_unrestricted_matches_oracle(oracle):
     sgx.close()
 
 
+@pytest.mark.parametrize("mol,basis_name,pure", [("water", "def2-svp", False), ("water", "def2-tzvp", True)])
+def test_cosx_mo_form_restricted(oracle, mol, basis_name, pure):
+    """occ_cosx_compute_K_mo: F = (Phi.(P C)).C^T instead of Phi.(P 2D) — same K as the D form and as the oracle"""
+    O, b, ob, off, pts, w, P, S, Sn, D, sgx = _setup(oracle, mol, basis_name, pure)
+    C = molecules.synthetic_orbitals(b, 1, seed=7)[0]
+    assert np.abs(C @ C.T - 2.0 * D).max() < 1e-14
+    K = sgx.compute_K(D)
+    Kmo = sgx.compute_K_mo(D, C)
+    Kref, _ = O.cosx_compute_K(ob, off, pts, w, P, D)
+    assert np.abs(Kmo - K).max() < 1e-12, np.abs(Kmo - K).max()
+    assert np.abs(Kmo - Kref).max() < TOL
+    assert sgx.info()["gemm_flops"] < 0.5 * 4.0 * len(w) * b.nbf ** 2 + 4.0 * len(w) * b.nbf * C.shape[1] + 1
+    # long-range and fused range-separated through the same factorisation
+    omega, alpha, beta = 0.3, 1.0, -0.842294
+    Kf = sgx.compute_K_range_separated_mo(D, C, alpha, beta, omega)
+    assert np.abs(Kf - sgx.compute_K_range_separated(D, alpha, beta, omega)).max() < 1e-12
+    sgx.set_range_separated_omega(omega)
+    assert np.abs(sgx.compute_K_mo(D, C) - sgx.compute_K(D)).max() < 1e-12
+    sgx.close()
+
+
+def test_cosx_mo_form_unrestricted_and_empty_spin(oracle):
+    O, b, ob, off, pts, w, P, S, Sn, D, sgx = _setup(oracle, "water", "def2-svp", False, nspin=2)
+    Ca, Cb = molecules.synthetic_orbitals(b, 2, seed=7)
+    n = b.nbf
+    assert np.abs(Ca @ Ca.T - 2.0 * D[:n]).max() < 1e-14 and np.abs(Cb @ Cb.T - 2.0 * D[n:]).max() < 1e-14
+    K = sgx.compute_K(D, unrestricted=True)
+    Kmo = sgx.compute_K_mo(D, (Ca, Cb), unrestricted=True)
+    assert np.abs(Kmo - K).max() < 1e-12
+    Kref, _ = O.cosx_compute_K(ob, off, pts, w, P, D, unrestricted=True)
+    assert np.abs(Kmo - Kref).max() < TOL
+    # different occupied counts per spin, and a spin without electrons (hydrogen-atom-like): K_beta = 0
+    D1 = D.copy()
+    D1[:n] = 0.5 * Ca[:, :3] @ Ca[:, :3].T
+    D1[n:] = 0.0
+    K1 = sgx.compute_K_mo(D1, (Ca[:, :3], np.zeros((n, 0))), unrestricted=True)
+    assert np.abs(K1 - sgx.compute_K(D1, unrestricted=True)).max() < 1e-12
+    assert np.abs(K1[n:]).max() == 0.0 and np.abs(K1[:n]).max() > 1e-3
+    sgx.close()
+
+
 def test_cosx_general_spinorbitals_match_oracle(oracle):
     O, b, ob, off, pts, w, P, S, Sn, D, sgx = _setup(oracle, "water", "def2-svp", True)
     n = b.nbf
