@@ -392,11 +392,18 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
                                                      int nruns) {
   constexpr int L = LA + LB, NE = (LA + 1) * (LB + 1) * (L + 1), STRIDE = COSX_PRIM_HDR + 3 * NE;
   constexpr int NCA = cx_ncart(LA), NCB = cx_ncart(LB), NH = cx_nhermsum(L);
-  constexpr int NBUF = L <= 1 ? 4 : 2;
+#ifndef COSX_GROUPED
+#define COSX_GROUPED 1
+#endif
+  // classes whose q side is an s shell have so little work per pair (often one or two primitives) that the two CTA
+  // barriers of a pipeline step weigh as much as the integrals: there a step carries up to U consecutive pairs
+  constexpr bool GROUPED = COSX_GROUPED && LB == 0;
+  constexpr int U = GROUPED ? 4 : 1;
+  constexpr int NBUF = GROUPED ? (L <= 1 ? 3 : 2) : (L <= 1 ? 4 : 2);
   constexpr int POOLCAP = L <= 1 ? 512 : 1024;
   constexpr int STAGE = (POOLCAP / STRIDE) > 0 ? (POOLCAP / STRIDE) : 1;
   __shared__ double s_pool[NBUF][STAGE * STRIDE];
-  __shared__ double s_F[NBUF][NCB][TILE_P];
+  __shared__ double s_F[NBUF][U][NCB][TILE_P];
   __shared__ CosxPair s_pairs[TILE_P];
   __shared__ int s_wcnt[TILE_P / 32];
   // 1D grid, group-major: the CTAs of COSX_TILE_GROUP batches x all pair runs are adjacent, so that the F and G slabs of
@@ -447,6 +454,102 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
     __syncthreads();
     if (nsurv == 0) continue;
 
+    if constexpr (GROUPED) {
+      // ---- cp.async ring over steps of up to U consecutive (pair, primitive-range) segments ----
+      // producer and consumer walk the compacted pair list with the same deterministic packing rule, so no segment
+      // descriptors need to be stored: a step takes segments while fewer than U are in it and its pool has room; a pair
+      // whose primitives do not fit continues in the next step (Gq stays in registers across steps)
+      int li_n = 0, i0_n = 0, li = 0, i0 = 0, issued = 0, consumed = 0;
+      auto issue_step = [&](int buf) {
+        int used = 0;
+#pragma unroll 1
+        for (int j = 0; j < U && li_n < nsurv && used < STAGE; ++j) {
+          const CosxPair &pr = s_pairs[li_n];
+          const int ns = min(pr.nprim - i0_n, STAGE - used);
+          const double *src = P.pool + pr.off + static_cast<size_t>(i0_n) * STRIDE;
+          double *dst = &s_pool[buf][used * STRIDE];
+          for (int i = tid; i < ns * STRIDE; i += TILE_P) cp_async8(dst + i, src + i);
+          if (i0_n == 0) {
+            const double *f = Fcol + static_cast<size_t>(pr.bfq) * TILE_P;
+            for (int c = 0; c < nq_cols; ++c) cp_async8(&s_F[buf][j][c][tid], f + static_cast<size_t>(c) * TILE_P);
+          }
+          used += ns;
+          i0_n += ns;
+          if (i0_n < pr.nprim) break; // pool full: the pair continues in the next step
+          i0_n = 0;
+          ++li_n;
+        }
+      };
+#pragma unroll
+      for (int j = 0; j < NBUF - 1; ++j) {
+        if (li_n < nsurv) issue_step(issued % NBUF);
+        cp_async_commit();
+        ++issued;
+      }
+      while (li < nsurv) {
+        if (li_n < nsurv) issue_step(issued % NBUF);
+        cp_async_commit();
+        ++issued;
+        cp_async_wait<NBUF - 1>();
+        __syncthreads();
+        const int buf = consumed % NBUF;
+        int used = 0;
+#pragma unroll 1
+        for (int j = 0; j < U && li < nsurv && used < STAGE; ++j) {
+          const CosxPair &pr = s_pairs[li];
+          const bool offdiag = pr.p != pr.q;
+          const int ns = min(pr.nprim - i0, STAGE - used);
+          if (i0 == 0) {
+            if (pr.p != cur_p) {
+              if (gp_dirty) flush_G<LA>(Gp, Gcol, cur_bfp, pure, P.c2s);
+              cur_p = pr.p;
+              cur_bfp = pr.bfp;
+              gp_dirty = false;
+              load_F<LA>(Fp, Fcol, pr.bfp, w, pure, P.c2s);
+#pragma unroll
+              for (int i = 0; i < NCA; ++i) Gp[i] = 0.0;
+            }
+            take_F<LB>(Fq, &s_F[buf][j][0][tid], w, pure, P.c2s);
+#pragma unroll
+            for (int jj = 0; jj < NCB; ++jj) Gq[jj] = 0.0;
+            gp_dirty = gp_dirty || offdiag;
+            if (P.stats && tid == 0) {
+              atomicAdd(P.stats + 2 * cls, 1ULL);
+              atomicAdd(P.stats + 2 * cls + 1, static_cast<unsigned long long>(pr.nprim) * P.counts[tile]);
+            }
+          }
+#pragma unroll(L == 0 ? 4 : (L <= 2 ? 2 : 1))
+          for (int sidx = 0; sidx < ns; ++sidx) {
+            const double *rec = s_pool[buf] + (used + sidx) * STRIDE;
+            const double pe = rec[0];
+            const double PCx = rec[1] - X, PCy = rec[2] - Y, PCz = rec[3] - Z; // rints_specialized.h:1457-1460: P - C
+            const double r2 = PCx * PCx + PCy * PCy + PCz * PCz;
+            double S[L + 1];
+#pragma unroll
+            for (int m = 0; m <= L; ++m) S[m] = 0.0;
+            if (P.w_full != 0.0) add_seeds<L>(P.boys, pe, r2, P.w_full, S);
+            if (P.w_lr != 0.0) { // rints_specialized.h:1462-1500
+              const double sc = w2 / (pe + w2);
+              add_seeds<L>(P.boys, pe * sc, r2, P.w_lr * sqrt(sc), S);
+            }
+            double R[NH];
+            hermite_R<L>(S, PCx, PCy, PCz, R);
+            contract<LA, LB>(rec + COSX_PRIM_HDR, rec + COSX_PRIM_HDR + NE, rec + COSX_PRIM_HDR + 2 * NE, R, Fp, Fq, Gp, Gq,
+                             offdiag);
+          }
+          used += ns;
+          i0 += ns;
+          if (i0 < pr.nprim) break;
+          flush_G<LB>(Gq, Gcol, pr.bfq, pure, P.c2s);
+          i0 = 0;
+          ++li;
+        }
+        ++consumed;
+        __syncthreads(); // the buffer just read is the target of the next issue
+      }
+      cp_async_wait<0>();
+      continue;
+    }
     // ---- cp.async ring over (pair, primitive-chunk) units ----
     auto issue = [&](int li, int i0, int buf) {
       const CosxPair &pr = s_pairs[li];
@@ -455,7 +558,7 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
       for (int i = tid; i < ns * STRIDE; i += TILE_P) cp_async8(&s_pool[buf][i], src + i);
       if (i0 == 0) {
         const double *f = Fcol + static_cast<size_t>(pr.bfq) * TILE_P;
-        for (int c = 0; c < nq_cols; ++c) cp_async8(&s_F[buf][c][tid], f + static_cast<size_t>(c) * TILE_P);
+        for (int c = 0; c < nq_cols; ++c) cp_async8(&s_F[buf][0][c][tid], f + static_cast<size_t>(c) * TILE_P);
       }
     };
     int li_n = 0, i0_n = 0, issued = 0, consumed = 0;
@@ -498,7 +601,7 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
 #pragma unroll
           for (int i = 0; i < NCA; ++i) Gp[i] = 0.0;
         }
-        take_F<LB>(Fq, &s_F[buf][0][tid], w, pure, P.c2s);
+        take_F<LB>(Fq, &s_F[buf][0][0][tid], w, pure, P.c2s);
 #pragma unroll
         for (int j = 0; j < NCB; ++j) Gq[j] = 0.0;
         gp_dirty = gp_dirty || offdiag;
