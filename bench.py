@@ -391,8 +391,9 @@ def run_b200(args):
 
 
 def cosx_next_row(basis, mol, bas, reps=2):
-    """SemiNumericalExchange.compute_K (occ_cosx_compute_K: host D -> K, H2D / D2H inside the timed region) of the same
-    molecule and basis on a 50-point sgx grid; restricted, full Coulomb operator."""
+    """SemiNumericalExchange.compute_K (host D [+ C_occ] -> K, H2D / D2H inside the timed region) of the same molecule and
+    basis on a 50-point sgx grid; restricted, full Coulomb operator. Headline: the factorised-F entry
+    occ_cosx_compute_K_mo; the D-only occ_cosx_compute_K beside it."""
     import time
 
     from occ_b200 import cosx, molecules
@@ -400,20 +401,30 @@ def cosx_next_row(basis, mol, bas, reps=2):
     sgx = cosx.SemiNumericalExchange(basis, cosx.sgx_grid_settings(50, 1e-5))
     t_setup = time.perf_counter() - t0
     D = 0.5 * molecules.synthetic_density(basis, 1)
-    sgx.compute_K(D)
-    ts = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        K = sgx.compute_K(D)
-        ts.append(time.perf_counter() - t0)
-    info = sgx.info()
+    Cocc = molecules.synthetic_orbitals(basis, 1)[0]      # 2 D = Cocc Cocc^T: the orbitals behind synthetic_density
+    out = {}
+    for name, call in (("occ_cosx_compute_K_mo", lambda: sgx.compute_K_mo(D, Cocc)),
+                       ("occ_cosx_compute_K", lambda: sgx.compute_K(D))):
+        call()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            K = call()
+            ts.append(time.perf_counter() - t0)
+        info = sgx.info()
+        out[name] = {"ms_per_call": 1e3 * min(ts), "gemm_flops": info["gemm_flops"], "kernel_launches": info["launches"],
+                     "library_gemm_calls": info["gemm_calls"], "K_absmax": float(np.abs(K).max())}
     n = sgx.num_grid_points()
     sgx.close()
-    return {"entry": "occ_cosx_compute_K", "workload": f"{mol}/{bas} RKS, sgx grid 50 angular / radial precision 1e-5",
-            "grid_points": n, "batches": info["nbatches"], "shell_pairs": info["npairs"], "ms_per_call": 1e3 * min(ts),
-            "grid_points_per_s": n / min(ts), "gemm_flops": info["gemm_flops"], "kernel_launches": info["launches"],
-            "library_gemm_calls": info["gemm_calls"], "h2d_bytes": 8 * basis.nbf ** 2, "d2h_bytes": 8 * basis.nbf ** 2,
-            "K_absmax": float(np.abs(K).max()), "setup_seconds": t_setup}
+    head = out["occ_cosx_compute_K_mo"]
+    return {"entry": "occ_cosx_compute_K_mo", "workload": f"{mol}/{bas} RKS, sgx grid 50 angular / radial precision 1e-5",
+            "grid_points": n, "batches": info["nbatches"], "shell_pairs": info["npairs"], "nocc": int(Cocc.shape[1]),
+            "ms_per_call": head["ms_per_call"], "grid_points_per_s": n / (1e-3 * head["ms_per_call"]),
+            "gemm_flops": head["gemm_flops"], "kernel_launches": head["kernel_launches"],
+            "library_gemm_calls": head["library_gemm_calls"],
+            "h2d_bytes": 8 * basis.nbf ** 2 + 8 * basis.nbf * int(Cocc.shape[1]), "d2h_bytes": 8 * basis.nbf ** 2,
+            "K_absmax": head["K_absmax"], "d_form": dict(out["occ_cosx_compute_K"], entry="occ_cosx_compute_K"),
+            "setup_seconds": t_setup}
 
 
 def _workspace_gb(info, nspin):
