@@ -288,7 +288,7 @@ int occ_cosx_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_
       const int p = swap_roles ? q0 : p0, q = swap_roles ? p0 : q0;
       const int la = basis->l[p], lb = basis->l[q], L1 = la + lb + 1, ne = (la + 1) * (lb + 1) * L1;
       const double *A = basis->origin + 3 * p, *Bc = basis->origin + 3 * q;
-      const int nep = cosx_ne_padded(ne), cls = la * 4 + lb, stride = COSX_PRIM_HDR + 3 * nep;
+      const int cls = la * 4 + lb, stride = COSX_PRIM_HDR + 3 * ne;
       const int nca = ncart(la), ncb = ncart(lb);
       const double sph_fac = (la == 0 ? 0.282094791773878143 : (la == 1 ? 0.488602511902919921 : 1.0)) *
                              (lb == 0 ? 0.282094791773878143 : (lb == 1 ? 0.488602511902919921 : 1.0)); // kernels.h:11-18
@@ -335,8 +335,8 @@ int occ_cosx_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_
           rec_all[o + 4] = pref;
           for (int i = 0; i < ne; ++i) {
             rec_all[o + COSX_PRIM_HDR + i] = pref * Ex[i];
-            rec_all[o + COSX_PRIM_HDR + nep + i] = Ey[i];
-            rec_all[o + COSX_PRIM_HDR + 2 * nep + i] = Ez[i];
+            rec_all[o + COSX_PRIM_HDR + ne + i] = Ey[i];
+            rec_all[o + COSX_PRIM_HDR + 2 * ne + i] = Ez[i];
           }
         }
       // block in the basis' own (Cartesian or spherical) functions

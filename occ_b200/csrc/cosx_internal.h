@@ -21,12 +21,9 @@ struct CosxPair {
   double cx, cy, cz, extent; // esp.cpp:85-100
 };
 
-// primitive pool record of a class (la, lb), ne = (la+1)(lb+1)(la+lb+1), nep = ne rounded up to even:
-//   [0] p  [1..3] P  [4] prefactor  [5] pad  [6 .. 6+ne) prefactor * E^x  [6+nep ..) E^y  [6+2nep ..) E^z   (ecoeffs.h layout)
-// header and table starts are 16-byte aligned (even offsets, even record stride), so that neighbouring table entries
-// load as one 128-bit shared-memory access
-constexpr int COSX_PRIM_HDR = 6;
-__host__ __device__ constexpr int cosx_ne_padded(int ne) { return (ne + 1) & ~1; }
+// primitive pool record of a class (la, lb), ne = (la+1)(lb+1)(la+lb+1):
+//   [0] p  [1..3] P  [4] unused  [5 .. 5+ne) prefactor * E^x  [5+ne ..) E^y  [5+2ne ..) E^z      (ecoeffs.h layout)
+constexpr int COSX_PRIM_HDR = 5;
 
 struct CosxParams {
   const CosxPair *pairs;

@@ -356,10 +356,6 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
   const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
 }
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-  const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -394,8 +390,7 @@ __device__ __forceinline__ void take_F(double (&Ft)[cx_ncart(L)], const double *
 template <int LA, int LB>
 __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, int npairs, int chunk, int cls, int ntiles,
                                                      int nruns) {
-  constexpr int L = LA + LB, NE = (LA + 1) * (LB + 1) * (L + 1), NEP = cosx_ne_padded(NE), STRIDE = COSX_PRIM_HDR + 3 * NEP;
-  static_assert(STRIDE % 2 == 0 && COSX_PRIM_HDR % 2 == 0, "16-byte aligned records");
+  constexpr int L = LA + LB, NE = (LA + 1) * (LB + 1) * (L + 1), STRIDE = COSX_PRIM_HDR + 3 * NE;
   constexpr int NCA = cx_ncart(LA), NCB = cx_ncart(LB), NH = cx_nhermsum(L);
 #ifndef COSX_GROUPED
 #define COSX_GROUPED 1
@@ -407,7 +402,7 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
   constexpr int NBUF = GROUPED ? (L <= 1 ? 3 : 2) : (L <= 1 ? 4 : 2);
   constexpr int POOLCAP = L <= 1 ? 512 : 1024;
   constexpr int STAGE = (POOLCAP / STRIDE) > 0 ? (POOLCAP / STRIDE) : 1;
-  __shared__ __align__(16) double s_pool[NBUF][STAGE * STRIDE];
+  __shared__ double s_pool[NBUF][STAGE * STRIDE];
   __shared__ double s_F[NBUF][U][NCB][TILE_P];
   __shared__ CosxPair s_pairs[TILE_P];
   __shared__ int s_wcnt[TILE_P / 32];
@@ -473,7 +468,7 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
           const int ns = min(pr.nprim - i0_n, STAGE - used);
           const double *src = P.pool + pr.off + static_cast<size_t>(i0_n) * STRIDE;
           double *dst = &s_pool[buf][used * STRIDE];
-          for (int i = tid; i < ns * (STRIDE / 2); i += TILE_P) cp_async16(dst + 2 * i, src + 2 * i);
+          for (int i = tid; i < ns * STRIDE; i += TILE_P) cp_async8(dst + i, src + i);
           if (i0_n == 0) {
             const double *f = Fcol + static_cast<size_t>(pr.bfq) * TILE_P;
             for (int c = 0; c < nq_cols; ++c) cp_async8(&s_F[buf][j][c][tid], f + static_cast<size_t>(c) * TILE_P);
@@ -525,10 +520,9 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
           }
 #pragma unroll(L == 0 ? 4 : (L <= 2 ? 2 : 1))
           for (int sidx = 0; sidx < ns; ++sidx) {
-            const double *rec = static_cast<const double *>(__builtin_assume_aligned(s_pool[buf] + (used + sidx) * STRIDE, 16));
-            const double2 h0 = *reinterpret_cast<const double2 *>(rec), h1 = *reinterpret_cast<const double2 *>(rec + 2);
-            const double pe = h0.x;
-            const double PCx = h0.y - X, PCy = h1.x - Y, PCz = h1.y - Z; // rints_specialized.h:1457-1460: P - C
+            const double *rec = s_pool[buf] + (used + sidx) * STRIDE;
+            const double pe = rec[0];
+            const double PCx = rec[1] - X, PCy = rec[2] - Y, PCz = rec[3] - Z; // rints_specialized.h:1457-1460: P - C
             const double r2 = PCx * PCx + PCy * PCy + PCz * PCz;
             double S[L + 1];
 #pragma unroll
@@ -540,7 +534,7 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
             }
             double R[NH];
             hermite_R<L>(S, PCx, PCy, PCz, R);
-            contract<LA, LB>(rec + COSX_PRIM_HDR, rec + COSX_PRIM_HDR + NEP, rec + COSX_PRIM_HDR + 2 * NEP, R, Fp, Fq, Gp, Gq,
+            contract<LA, LB>(rec + COSX_PRIM_HDR, rec + COSX_PRIM_HDR + NE, rec + COSX_PRIM_HDR + 2 * NE, R, Fp, Fq, Gp, Gq,
                              offdiag);
           }
           used += ns;
@@ -561,7 +555,7 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
       const CosxPair &pr = s_pairs[li];
       const int ns = min(STAGE, pr.nprim - i0);
       const double *src = P.pool + pr.off + static_cast<size_t>(i0) * STRIDE;
-      for (int i = tid; i < ns * (STRIDE / 2); i += TILE_P) cp_async16(&s_pool[buf][2 * i], src + 2 * i);
+      for (int i = tid; i < ns * STRIDE; i += TILE_P) cp_async8(&s_pool[buf][i], src + i);
       if (i0 == 0) {
         const double *f = Fcol + static_cast<size_t>(pr.bfq) * TILE_P;
         for (int c = 0; c < nq_cols; ++c) cp_async8(&s_F[buf][0][c][tid], f + static_cast<size_t>(c) * TILE_P);
@@ -619,10 +613,9 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
       const int ns = min(STAGE, pr.nprim - i0);
 #pragma unroll(L == 0 ? 4 : (L <= 2 ? 2 : 1))
       for (int s = 0; s < ns; ++s) {
-        const double *rec = static_cast<const double *>(__builtin_assume_aligned(s_pool[buf] + s * STRIDE, 16));
-        const double2 h0 = *reinterpret_cast<const double2 *>(rec), h1 = *reinterpret_cast<const double2 *>(rec + 2);
-        const double pe = h0.x;
-        const double PCx = h0.y - X, PCy = h1.x - Y, PCz = h1.y - Z; // rints_specialized.h:1457-1460: P - C
+        const double *rec = s_pool[buf] + s * STRIDE;
+        const double pe = rec[0];
+        const double PCx = rec[1] - X, PCy = rec[2] - Y, PCz = rec[3] - Z; // rints_specialized.h:1457-1460: P - C
         const double r2 = PCx * PCx + PCy * PCy + PCz * PCz;
         double S[L + 1];
 #pragma unroll
@@ -633,12 +626,12 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
           add_seeds<L>(P.boys, pe * sc, r2, P.w_lr * sqrt(sc), S);
         }
         if constexpr (L >= 4) {
-          prim_sliced<LA, LB>(rec + COSX_PRIM_HDR, rec + COSX_PRIM_HDR + NEP, rec + COSX_PRIM_HDR + 2 * NEP, S, PCx, PCy, PCz,
+          prim_sliced<LA, LB>(rec + COSX_PRIM_HDR, rec + COSX_PRIM_HDR + NE, rec + COSX_PRIM_HDR + 2 * NE, S, PCx, PCy, PCz,
                               Fp, Fq, Gp, Gq, offdiag);
         } else {
           double R[NH];
           hermite_R<L>(S, PCx, PCy, PCz, R);
-          contract<LA, LB>(rec + COSX_PRIM_HDR, rec + COSX_PRIM_HDR + NEP, rec + COSX_PRIM_HDR + 2 * NEP, R, Fp, Fq, Gp,
+          contract<LA, LB>(rec + COSX_PRIM_HDR, rec + COSX_PRIM_HDR + NE, rec + COSX_PRIM_HDR + 2 * NE, R, Fp, Fq, Gp,
                            Gq, offdiag);
         }
       }
