@@ -507,7 +507,22 @@ int occ_cosx_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_
   CHECK(dev_upload(h, &h->d_shell_size, shell_size));
   CHECK(dev_upload(h, &h->d_pairs, pairs_all));
   CHECK(dev_upload(h, &h->d_pool, pool_all));
-  CHECK(dev_upload(h, &h->d_boys, boys_table()));
+  { // device copy in order-major layout [m][segment][8]: a class (la, lb) only ever reads the rows of order m = la + lb
+    // (lower orders come from the downward recursion), so its 253 x 64 B of table are one contiguous 16 KB region that
+    // stays L1-resident next to the kernels' shared memory instead of 64-byte pieces strided by 1 KiB
+    const std::vector<double> seg_major = boys_table();
+    constexpr int N = 8, MaxM = 16;
+    const size_t nseg = seg_major.size() / (N * MaxM);
+    std::vector<double> order_major(seg_major.size());
+    for (size_t sg = 0; sg < nseg; ++sg)
+      for (int m = 0; m < MaxM; ++m)
+        std::memcpy(&order_major[(m * nseg + sg) * N], &seg_major[(sg * MaxM + m) * N], N * sizeof(double));
+    if (nseg != static_cast<size_t>(COSX_BOYS_SEGMENTS)) {
+      occ_cosx_destroy(h);
+      return fail("occ_cosx_create: Boys table size mismatch");
+    }
+    CHECK(dev_upload(h, &h->d_boys, order_major));
+  }
   {
     std::vector<double> c2s(9 + 30 + 70, 0.0);
     const double p1[9] = {0, 1, 0, 0, 0, 1, 1, 0, 0}; // gto.cpp:296-305: (py, pz, px)

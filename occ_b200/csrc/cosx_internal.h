@@ -24,6 +24,7 @@ struct CosxPair {
 // primitive pool record of a class (la, lb), ne = (la+1)(lb+1)(la+lb+1):
 //   [0] p  [1..3] P  [4] unused  [5 .. 5+ne) prefactor * E^x  [5+ne ..) E^y  [5+2ne ..) E^z      (ecoeffs.h layout)
 constexpr int COSX_PRIM_HDR = 5;
+constexpr int COSX_BOYS_SEGMENTS = 253; // rows per order of the device Boys table (boys.h: 252 segments on [0, 36) + 1)
 
 struct CosxParams {
   const CosxPair *pairs;
@@ -35,7 +36,7 @@ struct CosxParams {
   const double *px, *py, *pz, *pw;  // padded SoA points / weights of all tiles
   const double *F;                  // chunk slabs
   double *G;
-  const double *boys;               // Chebyshev table (boys.h layout: [segment][m][8])
+  const double *boys;               // Chebyshev table of boys.h, order-major: [m][segment][8]
   const double *c2s;                // spherical tables: l = 1 at 0 (3x3), l = 2 at 9 (5x6), l = 3 at 39 (7x10)
   int tile0;                        // first tile of the chunk (slabs are chunk-relative)
   int nbp;

@@ -80,7 +80,7 @@ __device__ __forceinline__ void add_seeds(const double *__restrict__ tab, double
     const double xod = T * 7.0; // 1 / Delta, Delta = 36 / 252
     const int seg = static_cast<int>(xod);
     const double xd = xod - static_cast<double>(seg) - 0.5;
-    const double2 *c = reinterpret_cast<const double2 *>(tab + (static_cast<size_t>(seg) * 16 + L) * 8);
+    const double2 *c = reinterpret_cast<const double2 *>(tab + (static_cast<size_t>(L) * COSX_BOYS_SEGMENTS + seg) * 8);
     const double2 c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2), c3 = __ldg(c + 3);
     // Estrin evaluation of the degree-7 polynomial (dependency depth 4 instead of 8; boys.h:101-106 uses Horner)
     const double x2 = xd * xd, x4 = x2 * x2;
