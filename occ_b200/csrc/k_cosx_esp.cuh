@@ -382,6 +382,10 @@ __device__ __forceinline__ void take_F(double (&Ft)[cx_ncart(L)], const double *
   }
 }
 
+struct PairLite {
+  int p, q, bfp, bfq, nprim, off;
+};
+
 // One CTA = one grid batch x one run of `chunk` shell pairs of class (LA, LB).
 //   round:    128 candidate pairs are screened in parallel (density flag, geometric test) and the survivors compacted,
 //             in order, into shared memory — one global-load latency per 128 pairs instead of one per pair;
@@ -400,11 +404,13 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
   constexpr bool GROUPED = COSX_GROUPED && LB == 0;
   constexpr int U = GROUPED ? 4 : 1;
   constexpr int NBUF = GROUPED ? (L <= 1 ? 3 : 2) : (L <= 1 ? 4 : 2);
-  constexpr int POOLCAP = L <= 1 ? 512 : 1024;
+  // s-s runs 7 CTAs per SM: with 32 KB of shared memory each only ~30 KB of the unified L1 would be left for the Boys
+  // slice and the F / G columns, so its pool is halved (a pair with more than 32 primitives continues in the next step)
+  constexpr int POOLCAP = L == 0 ? 256 : (L == 1 ? 512 : 1024);
   constexpr int STAGE = (POOLCAP / STRIDE) > 0 ? (POOLCAP / STRIDE) : 1;
   __shared__ double s_pool[NBUF][STAGE * STRIDE];
   __shared__ double s_F[NBUF][U][NCB][TILE_P];
-  __shared__ CosxPair s_pairs[TILE_P];
+  __shared__ PairLite s_pairs[TILE_P]; // survivors of a screening round, without the screening-only fields
   __shared__ int s_wcnt[TILE_P / 32];
   // 1D grid, group-major: the CTAs of COSX_TILE_GROUP batches x all pair runs are adjacent, so that the F and G slabs of
   // a group (2 x 8 x 128 x nbp doubles) stay L2-resident while every pair run reads / accumulates into them
@@ -450,7 +456,7 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
       if (i < wid) base += s_wcnt[i];
       nsurv += s_wcnt[i];
     }
-    if (keep) s_pairs[base + __popc(bal & ((1u << lane) - 1u))] = cand;
+    if (keep) s_pairs[base + __popc(bal & ((1u << lane) - 1u))] = PairLite{cand.p, cand.q, cand.bfp, cand.bfq, cand.nprim, cand.off};
     __syncthreads();
     if (nsurv == 0) continue;
 
@@ -464,7 +470,7 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
         int used = 0;
 #pragma unroll 1
         for (int j = 0; j < U && li_n < nsurv && used < STAGE; ++j) {
-          const CosxPair &pr = s_pairs[li_n];
+          const PairLite &pr = s_pairs[li_n];
           const int ns = min(pr.nprim - i0_n, STAGE - used);
           const double *src = P.pool + pr.off + static_cast<size_t>(i0_n) * STRIDE;
           double *dst = &s_pool[buf][used * STRIDE];
@@ -496,7 +502,7 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
         int used = 0;
 #pragma unroll 1
         for (int j = 0; j < U && li < nsurv && used < STAGE; ++j) {
-          const CosxPair &pr = s_pairs[li];
+          const PairLite &pr = s_pairs[li];
           const bool offdiag = pr.p != pr.q;
           const int ns = min(pr.nprim - i0, STAGE - used);
           if (i0 == 0) {
@@ -552,7 +558,7 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
     }
     // ---- cp.async ring over (pair, primitive-chunk) units ----
     auto issue = [&](int li, int i0, int buf) {
-      const CosxPair &pr = s_pairs[li];
+      const PairLite &pr = s_pairs[li];
       const int ns = min(STAGE, pr.nprim - i0);
       const double *src = P.pool + pr.off + static_cast<size_t>(i0) * STRIDE;
       for (int i = tid; i < ns * STRIDE; i += TILE_P) cp_async8(&s_pool[buf][i], src + i);
@@ -589,7 +595,7 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
       cp_async_wait<NBUF - 1>();
       __syncthreads();
       const int buf = consumed % NBUF;
-      const CosxPair &pr = s_pairs[li];
+      const PairLite &pr = s_pairs[li];
       const bool offdiag = pr.p != pr.q;
       if (i0 == 0) {
         if (pr.p != cur_p) {
