@@ -80,13 +80,16 @@ __device__ __forceinline__ void add_seeds(const double *__restrict__ tab, double
     const double xod = T * 7.0; // 1 / Delta, Delta = 36 / 252
     const int seg = static_cast<int>(xod);
     const double xd = xod - static_cast<double>(seg) - 0.5;
-    const double2 *c = reinterpret_cast<const double2 *>(tab + (static_cast<size_t>(L) * COSX_BOYS_SEGMENTS + seg) * 8);
-    const double2 c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2), c3 = __ldg(c + 3);
     // Estrin evaluation of the degree-7 polynomial (dependency depth 4 instead of 8; boys.h:101-106 uses Horner)
     const double x2 = xd * xd, x4 = x2 * x2;
-    const double q0 = fma(c0.y, xd, c0.x), q1 = fma(c1.y, xd, c1.x), q2 = fma(c2.y, xd, c2.x), q3 = fma(c3.y, xd, c3.x);
-    F[L] = fma(fma(q3, x2, q2), x4, fma(q1, x2, q0));
-    if (L > 0) {
+    auto row = [&](int m) {
+      const double2 *c = reinterpret_cast<const double2 *>(tab + (static_cast<size_t>(m) * COSX_BOYS_SEGMENTS + seg) * 8);
+      const double2 c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2), c3 = __ldg(c + 3);
+      const double q0 = fma(c0.y, xd, c0.x), q1 = fma(c1.y, xd, c1.x), q2 = fma(c2.y, xd, c2.x), q3 = fma(c3.y, xd, c3.x);
+      return fma(fma(q3, x2, q2), x4, fma(q1, x2, q0));
+    };
+    F[L] = row(L);
+    if (L > 0) { // (a second table row for L = 1 instead of exp + recursion was measured: +48 ms on valinomycin, L1-bound)
       const double e = exp(-T), T2 = 2.0 * T;
 #pragma unroll
       for (int m = L - 1; m >= 0; --m) F[m] = (T2 * F[m + 1] + e) * (1.0 / (2 * m + 1));
@@ -403,7 +406,7 @@ __global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, in
   // barriers of a pipeline step weigh as much as the integrals: there a step carries up to U consecutive pairs
   constexpr bool GROUPED = COSX_GROUPED && LB == 0;
   constexpr int U = GROUPED ? 4 : 1;
-  constexpr int NBUF = GROUPED ? (L <= 1 ? 3 : 2) : (L <= 1 ? 4 : 2);
+  constexpr int NBUF = GROUPED ? (L == 1 ? 3 : 2) : (L <= 1 ? 4 : 2);
   // s-s runs 7 CTAs per SM: with 32 KB of shared memory each only ~30 KB of the unified L1 would be left for the Boys
   // slice and the F / G columns, so its pool is halved (a pair with more than 32 primitives continues in the next step)
   constexpr int POOLCAP = L == 0 ? 256 : (L == 1 ? 512 : 1024);
