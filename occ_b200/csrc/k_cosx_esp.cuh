@@ -385,6 +385,45 @@ __device__ __forceinline__ void take_F(double (&Ft)[cx_ncart(L)], const double *
   }
 }
 
+// minimum resident CTAs per SM asked of ptxas per class (a register cap; 0 = none). The low-l classes are latency-bound at
+// 120-250 registers; capping them (with at most 136 B of spill) bought 71 ms on valinomycin: (1,0) 124 -> 80 registers
+// (275 -> 240 ms), (1,1) / (2,0) -> 96, (2,1) 162 -> 128, (3,0) 166 -> 128, (3,1) 248 -> 168.
+#ifndef COSX_M00
+#define COSX_M00 0
+#endif
+#ifndef COSX_M10
+#define COSX_M10 6
+#endif
+#ifndef COSX_M11
+#define COSX_M11 5
+#endif
+#ifndef COSX_M20
+#define COSX_M20 5
+#endif
+#ifndef COSX_M21
+#define COSX_M21 4
+#endif
+#ifndef COSX_M22
+#define COSX_M22 0
+#endif
+#ifndef COSX_M30
+#define COSX_M30 4
+#endif
+#ifndef COSX_M31
+#define COSX_M31 3
+#endif
+#ifndef COSX_M32
+#define COSX_M32 0
+#endif
+#ifndef COSX_M33
+#define COSX_M33 0
+#endif
+__host__ __device__ constexpr int cosx_min_ctas(int la, int lb) {
+  constexpr int t[4][4] = {{COSX_M00, 0, 0, 0}, {COSX_M10, COSX_M11, 0, 0}, {COSX_M20, COSX_M21, COSX_M22, 0},
+                           {COSX_M30, COSX_M31, COSX_M32, COSX_M33}};
+  return t[la][lb];
+}
+
 struct PairLite {
   int p, q, bfp, bfq, nprim, off;
 };
@@ -395,7 +434,7 @@ struct PairLite {
 //   pipeline: the primitive records and the F columns of the surviving pairs stream through an NBUF-deep cp.async ring,
 //             so the loads of the next pairs are in flight while the current one is evaluated.
 template <int LA, int LB>
-__global__ void __launch_bounds__(TILE_P) k_cosx_esp(CosxParams P, int pair0, int npairs, int chunk, int cls, int ntiles,
+__global__ void __launch_bounds__(TILE_P, cosx_min_ctas(LA, LB)) k_cosx_esp(CosxParams P, int pair0, int npairs, int chunk, int cls, int ntiles,
                                                      int nruns) {
   constexpr int L = LA + LB, NE = (LA + 1) * (LB + 1) * (L + 1), STRIDE = COSX_PRIM_HDR + 3 * NE;
   constexpr int NCA = cx_ncart(LA), NCB = cx_ncart(LB), NH = cx_nhermsum(L);
