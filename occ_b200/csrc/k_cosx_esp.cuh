@@ -386,16 +386,17 @@ __device__ __forceinline__ void take_F(double (&Ft)[cx_ncart(L)], const double *
 }
 
 // minimum resident CTAs per SM asked of ptxas per class (a register cap; 0 = none). The low-l classes are latency-bound at
-// 120-250 registers; capping them (with at most 136 B of spill) bought 71 ms on valinomycin: (1,0) 124 -> 80 registers
-// (275 -> 240 ms), (1,1) / (2,0) -> 96, (2,1) 162 -> 128, (3,0) 166 -> 128, (3,1) 248 -> 168.
+// 64-250 registers; capping them (with at most 136 B of spill) bought about 90 ms on valinomycin: (0,0) 64 -> 56 registers
+// (161 -> 149 ms), (1,0) 124 -> 72 (275 -> 235 ms), (1,1) 120 -> 80, (2,0) 128 -> 96 (80 was slower again), (2,1) 162 -> 128,
+// (3,0) 166 -> 128, (3,1) 248 -> 168.
 #ifndef COSX_M00
-#define COSX_M00 0
+#define COSX_M00 9
 #endif
 #ifndef COSX_M10
-#define COSX_M10 6
+#define COSX_M10 7
 #endif
 #ifndef COSX_M11
-#define COSX_M11 5
+#define COSX_M11 6
 #endif
 #ifndef COSX_M20
 #define COSX_M20 5
