@@ -6,9 +6,10 @@
 //               (include/occ/ints/ecoeffs.h:150-198, kernels.h:293-340, src/ints/esp.cpp:85-100), the grid batches with
 //               their bounding spheres (:676-720) and the Boys table (boys.h:191-330) — built on the host, once.
 //   compute():  per SCF iteration, per chunk of batches: AO values (k_collocate) -> batch skip flags -> F = Phi D2q
-//               (library DGEMM) -> ESP + contraction kernels, one launch per (la, lb) class (k_cosx_esp) -> K' += Phi^T G
-//               (library DGEMM) -> K = c (K' + K'^T).
-// The two dense products are plain GEMMs and go to cuBLAS (loaded with dlopen so that the XC entry points do not depend
+//               (library DGEMM; factorised as (Phi (P C)) C^T when the caller passes the occupied orbitals) -> ESP +
+//               contraction kernels, one launch per (la, lb) class (k_cosx_esp) -> K' += Phi^T G (k_cosx_kgemm, DMMA)
+//               -> K = c (K' + K'^T).
+// F = Phi D2q is a plain batched GEMM and goes to cuBLAS (loaded with dlopen so that the XC entry points do not depend
 // on it); everything else is this library's own kernels. No CPU fallback.
 #include "../../include/occ_cosx_b200.h"
 #include "cosx_internal.h"
@@ -52,7 +53,7 @@ struct Blas {
   int open() {
     const char *names[] = {"libcublas.so.12", "/usr/local/cuda/lib64/libcublas.so.12", "libcublas.so", nullptr};
     for (int i = 0; names[i] && !lib; ++i) lib = dlopen(names[i], RTLD_NOW | RTLD_LOCAL);
-    if (!lib) return fail("occ_cosx_create: cannot load libcublas (needed for the two dense products of the COSX build)");
+    if (!lib) return fail("occ_cosx_create: cannot load libcublas (needed for the F = Phi.D2q product of the COSX build)");
     create = reinterpret_cast<decltype(create)>(dlsym(lib, "cublasCreate_v2"));
     destroy = reinterpret_cast<decltype(destroy)>(dlsym(lib, "cublasDestroy_v2"));
     set_stream = reinterpret_cast<decltype(set_stream)>(dlsym(lib, "cublasSetStream_v2"));
