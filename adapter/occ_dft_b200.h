@@ -9,6 +9,7 @@
 // (core/linear_algebra.h:23).  INTEGRATION.md shows the ~25-line body that replaces dft.h:216-382 with this class.
 #pragma once
 #include "../include/occ_xc_b200.h"
+#include <algorithm>
 #include <cstddef>
 #include <stdexcept>
 #include <string>
@@ -64,80 +65,79 @@ class XCBuild {
 public:
   // sorted_points (3 x npts, column-major), sorted_weights and leaves come from
   // m_grid.get_molecular_grid_points().get_hierarchy() (dft.h:295-298); func_ids from
-  // m_method.functionals[_polarized][i].id() (dft.h:207-209).
+  // m_method.functionals[_polarized][i].id() (dft.h:207-209).  nocc_alpha >= 0 enables compute_K_dft_mo (the handle
+  // then also holds the factorised-density work lists); nocc_beta = 0 is legal for unrestricted one-electron systems.
   XCBuild(const BasisArrays &basis, size_t npts, const double *sorted_points, const double *sorted_weights,
           const std::vector<occ_xc_leaf_t> &leaves, const std::vector<int> &func_ids, SpinorbitalKind kind,
           double density_threshold = 1e-10, double xc_screening_threshold = 1e-10, int device = -1, int rank = 0,
-          int world_size = 1, int nocc_alpha = 0, int nocc_beta = 0)
-      : m_nspin(static_cast<int>(kind)), m_nbf(basis.nbf()), m_nocc{nocc_alpha, nocc_beta} {
-    occ_xc_options_t opt{};
+          int world_size = 1, int nocc_alpha = -1, int nocc_beta = -1, bool deterministic = false)
+      : m_nspin(static_cast<int>(kind)), m_nbf(basis.nbf()) {
+    occ_xc_options_t opt;
+    occ_xc_options_init(&opt);
     opt.device = device;
     opt.rank = rank;
     opt.world_size = world_size;
-    opt.reserved[3] = nocc_alpha; // > 0: the handle can also run the factorised (MO-form) density, compute_K_dft_mo
-    opt.reserved[4] = nocc_beta;
-    if (m_nspin == 2 && nocc_beta == 0) m_nocc[1] = nocc_alpha;
+    opt.deterministic = deterministic ? 1 : 0;
+    // The reference hands over mo.D and mo.Cocc; D2 = 2 mo.D (dft.h:205) and C~ = sqrt(2) Cocc (restricted: mo.D =
+    // Cocc Cocc^T; unrestricted: mo.D_s = 1/2 C_s C_s^T, include/occ/qm/orb.h:64-82) are formed ON THE DEVICE
+    opt.density_scale = 2.0;
+    opt.orbital_scale = m_nspin == 1 ? 1.4142135623730951 : 1.0;
+    if (nocc_alpha >= 0) {
+      opt.mo_form = 1;
+      opt.nocc_alpha = nocc_alpha;
+      opt.nocc_beta = m_nspin == 2 ? (nocc_beta >= 0 ? nocc_beta : nocc_alpha) : 0;
+      m_nocc[0] = opt.nocc_alpha;
+      m_nocc[1] = opt.nocc_beta;
+    }
     const occ_xc_basis_t b = basis.view();
     check(occ_xc_create(&b, npts, sorted_points, sorted_weights, leaves.size(), leaves.data(), nullptr,
                         static_cast<int>(func_ids.size()), func_ids.data(), m_nspin, density_threshold,
                         xc_screening_threshold, &opt, &m_handle));
   }
   ~XCBuild() {
-    occ_xc_pinned_free(m_C);
+    for (void *p : m_registered) occ_xc_host_unregister(p);
     occ_xc_pinned_free(m_K);
-    occ_xc_pinned_free(m_D2);
     occ_xc_destroy(m_handle);
   }
   XCBuild(const XCBuild &) = delete;
   XCBuild &operator=(const XCBuild &) = delete;
 
-  // D = mo.D ((nspin*nbf) x nbf column-major). Writes K (same shape). Doubles D like dft.h:205.
+  // Page-lock caller storage that persists across SCF iterations (e.g. the Eigen storage of mo.D / mo.Cocc / K): the
+  // copies then run at PCIe speed instead of through the driver's bounce buffer.  Unregistered in the destructor.
+  void register_host_buffer(const void *p, size_t bytes) {
+    check(occ_xc_host_register(const_cast<void *>(p), bytes));
+    m_registered.push_back(const_cast<void *>(p));
+  }
+
+  // D = mo.D ((nspin*nbf) x nbf column-major), exactly as the reference stores it. Writes K (same shape).
+  // No host-side pass over D: the factor 2 of dft.h:205 is applied on the device (options.density_scale).
   void compute_K_dft(const double *D, double *K) {
-    const size_t n = static_cast<size_t>(m_nspin) * m_nbf * m_nbf;
-    if (!m_D2) { // the doubled copy lives in page-locked memory: its H2D then runs at PCIe speed
-      void *p = nullptr;
-      check(occ_xc_pinned_alloc(n * sizeof(double), &p));
-      m_D2 = static_cast<double *>(p);
-    }
-    for (size_t i = 0; i < n; ++i) m_D2[i] = 2 * D[i];
-    check(occ_xc_build(m_handle, m_D2, K, &m_exc_dft, &m_total_density_a, &m_total_density_b));
+    check(occ_xc_build(m_handle, D, K, &m_exc_dft, &m_total_density_a, &m_total_density_b));
   }
   // Same, but K stays in a page-locked buffer owned by this object (valid until the next call): the caller maps it
-  // (Eigen::Map<const Mat>(ptr, nspin * nbf, nbf)) — the reference negates / copies K anyway (dft.h:435) — so neither
-  // matrix crosses PCIe through pageable memory.
+  // (Eigen::Map<const Mat>(ptr, nspin * nbf, nbf)) — the reference negates / copies K anyway (dft.h:435).
   const double *compute_K_dft(const double *D) {
-    const size_t n = static_cast<size_t>(m_nspin) * m_nbf * m_nbf;
-    if (!m_K) {
-      void *p = nullptr;
-      check(occ_xc_pinned_alloc(n * sizeof(double), &p));
-      m_K = static_cast<double *>(p);
-    }
+    ensure_K();
     compute_K_dft(D, m_K);
     return m_K;
   }
-  // The same build with the occupied orbitals of `mo` as well (mo.Cocc; restricted: nbf x nocc, unrestricted: one
-  // nbf x nocc_s matrix per spin), column-major.  mo.D = Cocc Cocc^T (restricted) resp. 1/2 C_s C_s^T per spin block
-  // (include/occ/qm/orb.h:64-82), so D2_s = C~ C~^T with C~ = sqrt(2) Cocc resp. C_s: the scaling is applied here.
+  // The same build with the occupied orbitals of `mo` (mo.Cocc; restricted: nbf x nocc, unrestricted: one
+  // nbf x nocc_s matrix per spin, the beta block directly behind the alpha block as in mo.Cocc's column blocks),
+  // column-major.  D may be nullptr: the density matrix is then formed on the device from the orbitals and nothing
+  // but 8 nbf nocc bytes crosses PCIe on the way in.
+  void compute_K_dft_mo(const double *D, const double *Cocc, double *K) {
+    if (m_nocc[0] < 0) throw std::runtime_error("XCBuild was created without occupied-orbital counts");
+    check(occ_xc_build_mo(m_handle, D, Cocc, K, &m_exc_dft, &m_total_density_a, &m_total_density_b));
+  }
+  // two separate blocks (Cocc_alpha, Cocc_beta): packed into a buffer of this object
   void compute_K_dft_mo(const double *D, const double *Cocc_alpha, const double *Cocc_beta, double *K) {
-    const size_t n = static_cast<size_t>(m_nspin) * m_nbf * m_nbf;
-    const size_t nc = static_cast<size_t>(m_nbf) * (m_nocc[0] + (m_nspin == 2 ? m_nocc[1] : 0));
-    if (!m_D2) {
-      void *p = nullptr;
-      check(occ_xc_pinned_alloc(n * sizeof(double), &p));
-      m_D2 = static_cast<double *>(p);
-    }
-    if (!m_C) {
-      void *p = nullptr;
-      check(occ_xc_pinned_alloc(nc * sizeof(double), &p));
-      m_C = static_cast<double *>(p);
-    }
-    for (size_t i = 0; i < n; ++i) m_D2[i] = 2 * D[i];
-    const double f = m_nspin == 1 ? 1.4142135623730951 : 1.0;
-    const size_t na = static_cast<size_t>(m_nbf) * m_nocc[0];
-    for (size_t i = 0; i < na; ++i) m_C[i] = f * Cocc_alpha[i];
-    if (m_nspin == 2)
-      for (size_t i = 0; i < nc - na; ++i) m_C[na + i] = Cocc_beta[i];
-    check(occ_xc_build_mo(m_handle, m_D2, m_C, K, &m_exc_dft, &m_total_density_a, &m_total_density_b));
+    if (m_nocc[0] < 0) throw std::runtime_error("XCBuild was created without occupied-orbital counts");
+    const size_t na = static_cast<size_t>(m_nbf) * m_nocc[0], nb = m_nspin == 2 ? static_cast<size_t>(m_nbf) * m_nocc[1] : 0;
+    if (nb == 0 || Cocc_beta == Cocc_alpha + na) return compute_K_dft_mo(D, Cocc_alpha, K);
+    if (m_C.size() != na + nb) m_C.resize(na + nb);
+    std::copy(Cocc_alpha, Cocc_alpha + na, m_C.begin());
+    std::copy(Cocc_beta, Cocc_beta + nb, m_C.begin() + na);
+    compute_K_dft_mo(D, m_C.data(), K);
   }
   double exchange_correlation_energy() const { return m_exc_dft; }
   double total_density_alpha() const { return m_total_density_a; }
@@ -158,8 +158,16 @@ private:
   occ_xc_handle *m_handle = nullptr;
   int m_nspin, m_nbf;
   double m_exc_dft = 0.0, m_total_density_a = 0.0, m_total_density_b = 0.0;
-  int m_nocc[2];
-  double *m_D2 = nullptr, *m_K = nullptr, *m_C = nullptr;
+  int m_nocc[2] = {-1, -1};
+  double *m_K = nullptr;
+  std::vector<double> m_C;
+  std::vector<void *> m_registered;
+  void ensure_K() {
+    if (m_K) return;
+    void *p = nullptr;
+    check(occ_xc_pinned_alloc(static_cast<size_t>(m_nspin) * m_nbf * m_nbf * sizeof(double), &p));
+    m_K = static_cast<double *>(p);
+  }
 };
 
 } // namespace occ_b200

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define OCC_XC_B200_ABI_VERSION 1
+#define OCC_XC_B200_ABI_VERSION 2
 
 /* occ::gto::AOBasis as plain arrays (include/occ/gto/shell.h:18-191): one entry per Shell in
  * AOBasis::shells() order; coefficients AFTER Shell::incorporate_shell_norm (src/gto/shell.cpp:180-186);
@@ -66,20 +66,38 @@ enum {
   OCC_XC_HYB_GGA_XC_PBEH = 406,
   OCC_XC_HYB_GGA_XC_BHANDH = 435,
   OCC_XC_HYB_GGA_XC_BHANDHLYP = 436,
-  OCC_XC_HYB_GGA_XC_B3LYP5 = 475
+  OCC_XC_HYB_GGA_XC_B3LYP5 = 475,
+  OCC_XC_HYB_GGA_XC_WB97X = 464 /* range separated: occ_xc_range_separation gives omega / alpha / beta */
 };
 
+/* Options of a handle (ABI version 2: named fields; version 1 carried them in an anonymous int array).
+ * A zero-initialised struct means: current device, whole grid, default workspace, D-form entries only, atomics in
+ * arrival order, no NVTX.  occ_xc_options_init() writes exactly that, with device = -1. */
 typedef struct {
   int device;            /* CUDA device ordinal; -1 = current device */
   int rank, world_size;  /* grid-leaf shard of this handle: leaves are split by predicted cost over world_size
                             handles (one per GPU / process); every handle returns a PARTIAL K, Exc, N that the
                             caller sums (NCCL all-reduce).  world_size <= 1: whole grid. */
   size_t batch_bytes;    /* AO-value workspace per batch of leaves (0 = default 4 GiB) */
-  int reserved[8];       /* [0] developer timing switches, [1] 2 = second stream lane, [2] 1 = handle can also run
-                            occ_xc_gradient (needs basis->shell_atom, l <= 4; larger workspace), [3] / [4] number of
-                            occupied alpha / beta orbitals: enables occ_xc_build_mo (adds one 128 x nocc slab per
-                            spin to every tile's workspace); [4] = 0 with nspin = 2 means "same as alpha" */
+  int mo_form;           /* 1 = the handle can also run occ_xc_build_mo / occ_xc_gradient_mo (adds one 128 x nocc slab per
+                            spin to every tile's workspace); nocc_alpha / nocc_beta are then the occupied-orbital counts */
+  int nocc_alpha;        /* MolecularOrbitals::n_alpha (include/occ/qm/mo.h:34-51) */
+  int nocc_beta;         /* n_beta; ignored for nspin = 1; 0 is legal for nspin = 2 (one-electron systems: the beta
+                            spin then contributes nothing and its C block is empty) */
+  int gradient;          /* 1 = the handle can also run occ_xc_gradient (needs basis->shell_atom, l <= 4; larger workspace) */
+  int deterministic;     /* 1 = bit-repeatable results: every cross-CTA accumulation (density row sums, the K scatter) is
+                            done on two exactly-summable fixed-point bins instead of in arrival order, which makes the
+                            sum independent of the order (the reference reduces its thread-local copies serially,
+                            dft.h:375-380).  Costs one extra atomic per accumulated value. */
+  int nvtx;              /* 1 = NVTX ranges around the build and its phases (nsys / ncu --nvtx) */
+  int lanes;             /* 2 = batches alternate between two stream lanes (experimental; default 1) */
+  unsigned debug;        /* developer timing switches: 1 = no Vxc scatter, 2 = no density epilogue */
+  double density_scale;  /* the D handed to the HOST entry points is multiplied by this on the device before use;
+                            0 = 1.0.  2.0 lets the caller pass mo.D itself instead of D2 = 2 * mo.D (dft.h:205) */
+  double orbital_scale;  /* same for the C of occ_xc_build_mo; 0 = 1.0.  sqrt(2) lets a restricted caller pass mo.Cocc */
+  int reserved[6];       /* must be zero */
 } occ_xc_options_t;
+void occ_xc_options_init(occ_xc_options_t *options);
 
 typedef struct occ_xc_handle occ_xc_handle;
 
@@ -112,9 +130,10 @@ int occ_xc_build(occ_xc_handle *h, const double *D2, double *K, double *exc, dou
  * rounding of C C^T, but the density phase runs in the factorised form  psi = phi C, X = psi C^T  (4 n nb nocc flops
  * instead of 2 n nb^2; tau: 6 n nb nocc instead of 6 n nb^2) wherever that is cheaper for a leaf — about 40 % less
  * tensor work in the density phase of valinomycin/def2-TZVP, 4x less in the tau phase of a meta-GGA.
- *   D2  as in occ_xc_build (still used for leaves with few basis functions)
+ *   D2  as in occ_xc_build (still used for leaves with few basis functions); NULL = formed on the device as C C^T
+ *       (nothing but the 8 * nbf * nocc bytes of C then crosses PCIe on the way in)
  *   C   nspin blocks, block s is nbf x nocc_s column-major (ld = nbf); the beta block follows the alpha block
- * The handle must have been created with options.reserved[3] (and [4]) = the occupied counts. */
+ * The handle must have been created with options.mo_form = 1 and the occupied counts. */
 int occ_xc_build_mo(occ_xc_handle *h, const double *D2, const double *C, double *K, double *exc, double *n_alpha,
                     double *n_beta);
 int occ_xc_build_mo_device(occ_xc_handle *h, const double *D2_dev, const double *C_dev, double *K_dev,
@@ -137,7 +156,7 @@ int occ_xc_build_device(occ_xc_handle *h, const double *D2_dev, double *K_dev, d
 /* SURVEY 8(f) rank 1 — the XC nuclear gradient, Mat3N DFT::compute_xc_gradient(mo, Schwarz) without the VV10 term
  * (src/dft/dft_gradients.cpp:68-109 -> compute_xc_gradient_impl, include/occ/dft/dft.h:598-749,
  * src/dft/dft_gradient_kernels.cpp).  HOST buffers; D2 as in occ_xc_build; gradient is 3 x natoms column-major
- * (this rank's shard: partial sums add up over ranks).  The handle must have been created with options.reserved[2] = 1. */
+ * (this rank's shard: partial sums add up over ranks).  The handle must have been created with options.gradient = 1. */
 int occ_xc_gradient(occ_xc_handle *h, const double *D2, double *gradient);
 
 /* SURVEY 8(f) rank 4 (density-on-grid consumers: Hirshfeld, XDM, cube files) —
@@ -211,6 +230,9 @@ int occ_xc_partition_leaves(const occ_xc_basis_t *basis, size_t nleaves, const o
 
 int occ_xc_family(int func_id);          /* 0 LDA, 1 GGA, 2 meta-GGA, -1 unknown (DensityFunctional::family) */
 double occ_xc_exact_exchange(int func_id); /* DensityFunctional::exact_exchange_factor (functional.h:557-579) */
+/* DensityFunctional::range_separated_parameters (functional.h:581-603, xc_hyb_cam_coef): omega = 0 for functionals
+ * without range separation.  wB97X: omega 0.3, alpha 1.0, beta -0.842294. */
+int occ_xc_range_separation(int func_id, double *omega, double *alpha, double *beta);
 
 /* ---- once-per-geometry input producers (not on the per-iteration clock) --------------------------------
  * occ::numint::MolecularGrid + MolecularGridPoints + SpatialGridHierarchy

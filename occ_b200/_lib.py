@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("OCC_XC_B200_LIB", os.path.join(HERE, "libocc_xc_b200.
 SYMBOLS = ["occ_xc_create", "occ_xc_build", "occ_xc_build_device", "occ_xc_build_mo", "occ_xc_build_mo_device", "occ_xc_gradient", "occ_xc_gradient_mo", "occ_xc_vv10", "occ_xc_density_on_grid", "occ_xc_pinned_alloc",
            "occ_xc_pinned_free", "occ_xc_host_register", "occ_xc_host_unregister", "occ_xc_get_info", "occ_xc_set_profiling",
            "occ_xc_get_phase_ms", "occ_xc_decay_cutoff", "occ_xc_eval_functional", "occ_xc_leaf_collocation",
-           "occ_xc_family", "occ_xc_exact_exchange", "occ_xc_destroy", "occ_xc_last_error", "occ_xc_abi_version",
+           "occ_xc_family", "occ_xc_exact_exchange", "occ_xc_range_separation", "occ_xc_options_init", "occ_xc_destroy", "occ_xc_last_error", "occ_xc_abi_version",
            "occ_xc_partition_leaves", "occ_xc_register_lebedev", "occ_xc_grid_create", "occ_xc_grid_from_points", "occ_xc_grid_npts",
            "occ_xc_grid_nleaves", "occ_xc_grid_atom_info", "occ_xc_grid_copy", "occ_xc_grid_destroy"]
 # every symbol include/occ_cosx_b200.h declares
@@ -36,8 +36,11 @@ class LeafT(C.Structure):
 
 
 class OptionsT(C.Structure):
+    """occ_xc_options_t (ABI version 2)"""
     _fields_ = [("device", C.c_int), ("rank", C.c_int), ("world_size", C.c_int), ("batch_bytes", C.c_size_t),
-                ("reserved", C.c_int * 8)]
+                ("mo_form", C.c_int), ("nocc_alpha", C.c_int), ("nocc_beta", C.c_int), ("gradient", C.c_int),
+                ("deterministic", C.c_int), ("nvtx", C.c_int), ("lanes", C.c_int), ("debug", C.c_uint),
+                ("density_scale", C.c_double), ("orbital_scale", C.c_double), ("reserved", C.c_int * 6)]
 
 
 class InfoT(C.Structure):

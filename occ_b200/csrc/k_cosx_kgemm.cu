@@ -164,12 +164,9 @@ __global__ void __launch_bounds__(NTHREADS, 2)
 void launch_cosx_kgemm(const double *phi, const double *G, const int *tile_skip, int ntiles, int nbf, int nbp, double *K,
                        unsigned long long *stats, void *stream) {
   if (ntiles <= 0) return;
-  static bool configured = false;
   const int smem_bytes = R_SMEM_DOUBLES * sizeof(double);
-  if (!configured) {
-    cudaFuncSetAttribute(k_cosx_kgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    configured = true;
-  }
+  static SmemOptIn optin; // per device: cudaFuncSetAttribute applies to the current device only
+  optin.ensure(k_cosx_kgemm, smem_bytes);
   const int njb = (nbf + GN - 1) / GN;
   k_cosx_kgemm<<<ntiles * njb, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(phi, G, tile_skip, nbf, nbp, njb,
                                                                                           K, stats);

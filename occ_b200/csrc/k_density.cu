@@ -14,7 +14,7 @@ namespace xcb {
 // the companion slabs (H_s,d / phi_d / S_s,de), sums over the 128 points and scatters per atom:
 //   grad[A][d] += f * sum_p sum_{mu in A} companion_d[p, mu] * acc[p, mu]
 // which is  -2 sum_{mu in A, nu} D_{mu nu} V_d(mu, nu)  of dft_gradient_kernels.cpp:540-592 without ever forming V_d.
-template <int MODE> __device__ __forceinline__ void gemm_xd_body(const BuildParams &P, const DensItem it, double *smem) {
+template <int MODE> __device__ __forceinline__ void XC_SYM(gemm_xd_body)(const BuildParams &P, const DensItem it, double *smem) {
   const TileDesc t = P.tiles[it.tile];
   if (MODE == 1 && P.leaf_skip[t.leaf]) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -180,40 +180,38 @@ template <int MODE> __device__ __forceinline__ void gemm_xd_body(const BuildPara
       }
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (tig == 0) red_add_f64(accp + row * TILE_P + wm * 32 + mi * 8 + gid, s);
+      if (tig == 0) XC_ACC_ADD(P, accp + row * TILE_P + wm * 32 + mi * 8 + gid, s);
     }
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2) k_density(BuildParams P, const DensItem *__restrict__ items) {
+__global__ void __launch_bounds__(NTHREADS, 2) XC_SYM(k_density)(BuildParams P, const DensItem *__restrict__ items) {
   extern __shared__ __align__(16) double smem[];
-  gemm_xd_body<0>(P, items[blockIdx.x], smem);
+  XC_SYM(gemm_xd_body)<0>(P, items[blockIdx.x], smem);
 }
+#ifndef XC_DETERMINISTIC
 __global__ void __launch_bounds__(NTHREADS, 2) k_xc_gradient(BuildParams P, const DensItem *__restrict__ items) {
   extern __shared__ __align__(16) double smem[];
   gemm_xd_body<1>(P, items[blockIdx.x], smem);
 }
+#endif
 
-void launch_density(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
+void XC_SYM(launch_density)(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
   if (nitems <= 0) return;
-  static bool configured = false;
   const int smem_bytes = GSTAGES * D_STAGE * sizeof(double);
-  if (!configured) {
-    cudaFuncSetAttribute(k_density, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    configured = true;
-  }
-  k_density<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
+  static SmemOptIn optin; // per device: cudaFuncSetAttribute applies to the current device only
+  optin.ensure(XC_SYM(k_density), smem_bytes);
+  XC_SYM(k_density)<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
 }
 
+#ifndef XC_DETERMINISTIC
 void launch_grad_gemm(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
   if (nitems <= 0) return;
-  static bool configured = false;
   const int smem_bytes = GSTAGES * D_STAGE * sizeof(double);
-  if (!configured) {
-    cudaFuncSetAttribute(k_xc_gradient, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    configured = true;
-  }
+  static SmemOptIn optin; // per device: cudaFuncSetAttribute applies to the current device only
+  optin.ensure(k_xc_gradient, smem_bytes);
   k_xc_gradient<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
 }
+#endif
 
 } // namespace xcb

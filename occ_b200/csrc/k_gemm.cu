@@ -26,6 +26,7 @@ namespace xcb {
 // materialised in HBM only for the XC nuclear gradient (A operand of k_xc_gradient); the Vxc build forms its G block
 // in shared memory inside k_vxc_resident.
 // ------------------------------------------------------------------------------------------------
+#ifndef XC_DETERMINISTIC
 __global__ void __launch_bounds__(TILE_P) k_gbuild(BuildParams P, const DensItem *__restrict__ items) {
   const DensItem it = items[blockIdx.x];
   const TileDesc t = P.tiles[it.tile];
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(TILE_P) k_gbuild(BuildParams P, const DensItem
     }
   }
 }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // vxc, resident-B form (the one the build launches).  A CTA owns (tile, 64 output columns): its B operand — the
@@ -79,7 +81,7 @@ constexpr int R_WROWS = GM / 8;        // rows of a row block owned by one warp
 constexpr int R_ASZ = R_WROWS * R_LDA, R_BSZ = GN * R_LDB;
 constexpr int R_SMEM_DOUBLES = R_BSZ + 8 * RS * R_ASZ + GN / 2; // + 64 ints: global column of each output column
 
-__global__ void __launch_bounds__(NTHREADS, 2) k_vxc_resident(BuildParams P, const VxcItem *__restrict__ items) {
+__global__ void __launch_bounds__(NTHREADS, 2) XC_SYM(k_vxc_resident)(BuildParams P, const VxcItem *__restrict__ items) {
   extern __shared__ __align__(16) double smem[];
   const VxcItem it = items[blockIdx.x];
   const TileDesc t = P.tiles[it.tile];
@@ -237,8 +239,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_vxc_resident(BuildParams P, con
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi) {
           if (grow[mi] >= 0) {
-            if (gc.x >= 0) red_add_f64(Kt + static_cast<size_t>(gc.x) * P.ldD + grow[mi], acc[mi][ni][0]);
-            if (gc.y >= 0) red_add_f64(Kt + static_cast<size_t>(gc.y) * P.ldD + grow[mi], acc[mi][ni][1]);
+            if (gc.x >= 0) XC_K_ADD(P, Kt + static_cast<size_t>(gc.x) * P.ldD + grow[mi], acc[mi][ni][0]);
+            if (gc.y >= 0) XC_K_ADD(P, Kt + static_cast<size_t>(gc.y) * P.ldD + grow[mi], acc[mi][ni][1]);
           }
         }
       }
@@ -251,17 +253,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_vxc_resident(BuildParams P, con
   cp_async_wait<0>();
 }
 
-void launch_vxc_resident(const BuildParams &P, const VxcItem *items, int nitems, void *stream) {
+void XC_SYM(launch_vxc_resident)(const BuildParams &P, const VxcItem *items, int nitems, void *stream) {
   if (nitems <= 0) return;
-  static bool configured = false;
   const int smem_bytes = R_SMEM_DOUBLES * sizeof(double);
-  if (!configured) {
-    cudaFuncSetAttribute(k_vxc_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    configured = true;
-  }
-  k_vxc_resident<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
+  static SmemOptIn optin; // per device: cudaFuncSetAttribute applies to the current device only
+  optin.ensure(XC_SYM(k_vxc_resident), smem_bytes);
+  XC_SYM(k_vxc_resident)<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
 }
 
+#ifndef XC_DETERMINISTIC
 
 
 
@@ -289,5 +289,6 @@ void launch_gbuild(const BuildParams &P, const DensItem *items, int nitems, void
   if (nitems <= 0) return;
   k_gbuild<<<nitems, TILE_P, 0, static_cast<cudaStream_t>(stream)>>>(P, items);
 }
+#endif
 
 } // namespace xcb

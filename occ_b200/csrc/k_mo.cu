@@ -16,7 +16,7 @@ namespace xcb {
 // MODE 4 / 5: the same factorisation for the XC nuclear gradient (acc = A . D_s^T = (A C)(C^T) for the symmetric D2 = C C^T):
 //   MODE 4   psi_A = A . C_loc with A = G_s or phi_e (stored to the tile's psi slab; A = phi reuses the density's psi)
 //   MODE 5   X = psi_A . C_loc^T followed by the per-atom gradient epilogue of MODE 1
-template <int MODE> __device__ __forceinline__ void gemm_mo_body(const BuildParams &P, const DensItem it, double *smem) {
+template <int MODE> __device__ __forceinline__ void XC_SYM(gemm_mo_body)(const BuildParams &P, const DensItem it, double *smem) {
   const TileDesc t = P.tiles[it.tile];
   if ((MODE == 1 || MODE == 4 || MODE == 5) && P.leaf_skip[t.leaf]) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -162,7 +162,7 @@ template <int MODE> __device__ __forceinline__ void gemm_mo_body(const BuildPara
         for (int ni = 0; ni < 4; ++ni) sq += acc[mi][ni][0] * acc[mi][ni][0] + acc[mi][ni][1] * acc[mi][ni][1];
         sq += __shfl_xor_sync(0xffffffffu, sq, 1);
         sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-        if (tig == 0) red_add_f64(accp + wm * 32 + mi * 8 + gid, sq);
+        if (tig == 0) XC_ACC_ADD(P, accp + wm * 32 + mi * 8 + gid, sq);
       }
     }
     return;
@@ -221,19 +221,20 @@ template <int MODE> __device__ __forceinline__ void gemm_mo_body(const BuildPara
       }
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (tig == 0) red_add_f64(accp + row * TILE_P + wm * 32 + mi * 8 + gid, s);
+      if (tig == 0) XC_ACC_ADD(P, accp + row * TILE_P + wm * 32 + mi * 8 + gid, s);
     }
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2) k_mo_psi(BuildParams P, const DensItem *__restrict__ items) {
+__global__ void __launch_bounds__(NTHREADS, 2) XC_SYM(k_mo_psi)(BuildParams P, const DensItem *__restrict__ items) {
   extern __shared__ __align__(16) double smem[];
-  gemm_mo_body<2>(P, items[blockIdx.x], smem);
+  XC_SYM(gemm_mo_body)<2>(P, items[blockIdx.x], smem);
 }
-__global__ void __launch_bounds__(NTHREADS, 2) k_mo_density(BuildParams P, const DensItem *__restrict__ items) {
+__global__ void __launch_bounds__(NTHREADS, 2) XC_SYM(k_mo_density)(BuildParams P, const DensItem *__restrict__ items) {
   extern __shared__ __align__(16) double smem[];
-  gemm_mo_body<3>(P, items[blockIdx.x], smem);
+  XC_SYM(gemm_mo_body)<3>(P, items[blockIdx.x], smem);
 }
+#ifndef XC_DETERMINISTIC
 __global__ void __launch_bounds__(NTHREADS, 2) k_mo_grad_psi(BuildParams P, const DensItem *__restrict__ items) {
   extern __shared__ __align__(16) double smem[];
   gemm_mo_body<4>(P, items[blockIdx.x], smem);
@@ -242,52 +243,38 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_mo_xc_gradient(BuildParams P, c
   extern __shared__ __align__(16) double smem[];
   gemm_mo_body<5>(P, items[blockIdx.x], smem);
 }
+#endif
 
-
-
-
-
-void launch_mo_psi(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
+void XC_SYM(launch_mo_psi)(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
   if (nitems <= 0) return;
-  static bool configured = false;
   const int smem_bytes = GSTAGES * D_STAGE * sizeof(double);
-  if (!configured) {
-    cudaFuncSetAttribute(k_mo_psi, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    configured = true;
-  }
-  k_mo_psi<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
+  static SmemOptIn optin; // per device: cudaFuncSetAttribute applies to the current device only
+  optin.ensure(XC_SYM(k_mo_psi), smem_bytes);
+  XC_SYM(k_mo_psi)<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
 }
 
-void launch_mo_density(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
+void XC_SYM(launch_mo_density)(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
   if (nitems <= 0) return;
-  static bool configured = false;
   const int smem_bytes = GSTAGES * D_STAGE * sizeof(double);
-  if (!configured) {
-    cudaFuncSetAttribute(k_mo_density, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    configured = true;
-  }
-  k_mo_density<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
+  static SmemOptIn optin; // per device: cudaFuncSetAttribute applies to the current device only
+  optin.ensure(XC_SYM(k_mo_density), smem_bytes);
+  XC_SYM(k_mo_density)<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
 }
 
+#ifndef XC_DETERMINISTIC
 void launch_mo_grad_psi(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
   if (nitems <= 0) return;
-  static bool configured = false;
   const int smem_bytes = GSTAGES * D_STAGE * sizeof(double);
-  if (!configured) {
-    cudaFuncSetAttribute(k_mo_grad_psi, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    configured = true;
-  }
+  static SmemOptIn optin; // per device: cudaFuncSetAttribute applies to the current device only
+  optin.ensure(k_mo_grad_psi, smem_bytes);
   k_mo_grad_psi<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
 }
 
 void launch_mo_grad_gemm(const BuildParams &P, const DensItem *items, int nitems, void *stream) {
   if (nitems <= 0) return;
-  static bool configured = false;
   const int smem_bytes = GSTAGES * D_STAGE * sizeof(double);
-  if (!configured) {
-    cudaFuncSetAttribute(k_mo_xc_gradient, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    configured = true;
-  }
+  static SmemOptIn optin; // per device: cudaFuncSetAttribute applies to the current device only
+  optin.ensure(k_mo_xc_gradient, smem_bytes);
   k_mo_xc_gradient<<<nitems, NTHREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P, items);
 }
 
@@ -311,5 +298,6 @@ void launch_transpose_rect(const double *in, double *out, int nrow, int ncol, in
   dim3 grid((nrow + 31) / 32, (ncol + 31) / 32);
   k_transpose_rect<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(in, out, nrow, ncol, ld_in, ld_out);
 }
+#endif
 
 } // namespace xcb

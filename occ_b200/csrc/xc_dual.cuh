@@ -119,6 +119,9 @@ template <int N> XC_HD Dual<N> atan(const Dual<N> &a) { return lift(a, ::atan(a.
 template <int N> XC_HD Dual<N> asinh(const Dual<N> &a) {
   return lift(a, ::asinh(a.v), 1.0 / ::sqrt(1.0 + a.v * a.v));
 }
+template <int N> XC_HD Dual<N> erf(const Dual<N> &a) {
+  return lift(a, ::erf(a.v), 1.1283791670955126 * ::exp(-a.v * a.v)); // 2/sqrt(pi)
+}
 template <int N> XC_HD Dual<N> pow(const Dual<N> &a, double p) {
   const double f = ::pow(a.v, p);
   return lift(a, f, p * f / a.v);

@@ -5,7 +5,7 @@
 //   lda_x(1) lda_c_vwn(7) lda_c_vwn_rpa(8) lda_c_vwn_3(30) gga_x_pbe(101) gga_x_b88(106) gga_c_pbe(130)
 //   gga_c_lyp(131) hyb_gga_xc_b3lyp(402) mgga_x_r2scan(497) mgga_c_r2scan(498) mgga_x_tpss(202) mgga_c_tpss(231)
 //   hyb_gga_xc_b3lyp5(475) hyb_gga_xc_pbeh(406) hyb_gga_xc_bhandh(435) hyb_gga_xc_bhandhlyp(436) lda_c_pw(12)
-//   lda_c_pw_mod(13)
+//   lda_c_pw_mod(13) hyb_gga_xc_wb97x(464)
 // libxc conventions: exc = energy per particle; vrho = d(rho*exc)/d rho_s; vsigma = d(rho*exc)/d sigma with
 // sigma = grad rho . grad rho (polarized order aa, ab, bb); vtau = d(rho*exc)/d tau_s, tau = 1/2 sum |grad psi|^2.
 // Each functional is a single energy density in (rho_a, rho_b, sigma_aa, sigma_ab, sigma_bb, tau_a, tau_b);
@@ -20,7 +20,7 @@ enum : int {
   ID_GGA_X_B88 = 106, ID_GGA_C_PBE = 130, ID_GGA_C_LYP = 131, ID_HYB_GGA_XC_B3LYP = 402,
   ID_MGGA_X_R2SCAN = 497, ID_MGGA_C_R2SCAN = 498, ID_LDA_C_PW = 12, ID_LDA_C_PW_MOD = 13, ID_MGGA_X_TPSS = 202,
   ID_MGGA_C_TPSS = 231, ID_HYB_GGA_XC_PBEH = 406, ID_HYB_GGA_XC_BHANDH = 435, ID_HYB_GGA_XC_BHANDHLYP = 436,
-  ID_HYB_GGA_XC_B3LYP5 = 475
+  ID_HYB_GGA_XC_B3LYP5 = 475, ID_HYB_GGA_XC_WB97X = 464
 };
 
 XC_HD double xc_exx_of(int id) { // xc_hyb_exx_coef (include/occ/dft/functional.h:557-579)
@@ -28,7 +28,20 @@ XC_HD double xc_exx_of(int id) { // xc_hyb_exx_coef (include/occ/dft/functional.
   case ID_HYB_GGA_XC_B3LYP: case ID_HYB_GGA_XC_B3LYP5: return 0.20;
   case ID_HYB_GGA_XC_PBEH: return 0.25;
   case ID_HYB_GGA_XC_BHANDH: case ID_HYB_GGA_XC_BHANDHLYP: return 0.50;
+  case ID_HYB_GGA_XC_WB97X: return 1.0; // cam_alpha: libxc's xc_hyb_exx_coef returns the full-range fraction
   default: return 0.0;
+  }
+}
+
+// xc_hyb_cam_coef (include/occ/dft/functional.h:581-603): E_x^HF = alpha K + beta K^SR(omega); omega = 0: not range separated
+XC_HD void xc_cam_of(int id, double *omega, double *alpha, double *beta) {
+  *omega = 0.0;
+  *alpha = xc_exx_of(id);
+  *beta = 0.0;
+  if (id == ID_HYB_GGA_XC_WB97X) {
+    *omega = 0.3;
+    *alpha = 1.0;
+    *beta = -(1.0 - 0.157706);
   }
 }
 
@@ -37,7 +50,8 @@ XC_HD int xc_family_of(int id) {
   case ID_LDA_X: case ID_LDA_C_VWN: case ID_LDA_C_VWN_RPA: case ID_LDA_C_VWN_3: case ID_LDA_C_PW:
   case ID_LDA_C_PW_MOD: return 0;
   case ID_GGA_X_PBE: case ID_GGA_X_B88: case ID_GGA_C_PBE: case ID_GGA_C_LYP: case ID_HYB_GGA_XC_B3LYP:
-  case ID_HYB_GGA_XC_B3LYP5: case ID_HYB_GGA_XC_PBEH: case ID_HYB_GGA_XC_BHANDH: case ID_HYB_GGA_XC_BHANDHLYP: return 1;
+  case ID_HYB_GGA_XC_B3LYP5: case ID_HYB_GGA_XC_PBEH: case ID_HYB_GGA_XC_BHANDH: case ID_HYB_GGA_XC_BHANDHLYP:
+  case ID_HYB_GGA_XC_WB97X: return 1;
   case ID_MGGA_X_R2SCAN: case ID_MGGA_C_R2SCAN: case ID_MGGA_X_TPSS: case ID_MGGA_C_TPSS: return 2;
   default: return -1;
   }
@@ -415,6 +429,58 @@ template <class T> XC_HD T e_tpss_c(const XV<T> &v) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// wB97X (Chai & Head-Gordon, J. Chem. Phys. 128, 084106 (2008); libxc hyb_gga_xc_wb97x = 464): B97 power series in
+// u = gamma x^2 / (1 + gamma x^2), x_s = |grad rho_s| / rho_s^(4/3), on (i) the LSDA exchange attenuated by the
+// short-range operator erfc(omega r)/r, omega = 0.3, (ii) the same-spin and (iii) the opposite-spin parts of the
+// Stoll-partitioned PW92 correlation (1992 constants).  Golden: tests/isolated_xc_tests.cpp:296-319 of the reference.
+template <class T> XC_HD T wb97_attenuation(const T &a) { // eq. (8) of the paper; series for a >= 3
+  const T a2 = a * a;
+  if (val(a) >= 3.0) {
+    const T y = 1.0 / a2;
+    T r = y * (-1.0 / 2021444812800.0) + 1.0 / 44590694400.0;
+    r = r * y - 1.0 / 1073479680.0;
+    r = r * y + 1.0 / 28385280.0;
+    r = r * y - 1.0 / 829440.0;
+    r = r * y + 1.0 / 26880.0;
+    r = r * y - 1.0 / 960.0;
+    r = r * y + 1.0 / 36.0;
+    return r * y;
+  }
+  const T e = exp(-0.25 / a2);
+  return 1.0 - (8.0 / 3.0) * a *
+                   (1.7724538509055159 * erf(0.5 / a) - 3.0 * a + 4.0 * a * a2 + (2.0 * a - 4.0 * a * a2) * e);
+}
+template <class T> XC_HD T b97_poly(const T &x2, const double gam, const double c0, const double c1, const double c2,
+                                    const double c3, const double c4) {
+  const T gx = gam * x2;
+  const T u = gx / (1.0 + gx);
+  T r = c4 * u + c3;
+  r = r * u + c2;
+  r = r * u + c1;
+  return r * u + c0;
+}
+template <class T> XC_HD T pw92_ferro_1992(const T &n) { // eps_c of the fully polarized gas of density n
+  const PwP p1 = {0.015545, 0.20548, 14.1189, 6.1977, 3.3662, 0.62517};
+  const T rs = cbrt(XC_RS_C / n);
+  return pw_g(p1, rs, sqrt(rs));
+}
+template <class T> XC_HD T e_wb97x(const XV<T> &v) {
+  const double omega = 0.3;
+  const T ra43 = v.ra * cbrt(v.ra), rb43 = v.rb * cbrt(v.rb);
+  const T xa2 = v.saa / (ra43 * ra43), xb2 = v.sbb / (rb43 * rb43);
+  const T kfa = cbrt(2.0 * XC_3PI2 * v.ra), kfb = cbrt(2.0 * XC_3PI2 * v.rb);
+  const T ex = XC_LDAX_C * (ra43 * wb97_attenuation(0.5 * omega / kfa) *
+                                b97_poly(xa2, 0.004, 0.842294, 0.726479, 1.04760, -5.70635, 13.2794) +
+                            rb43 * wb97_attenuation(0.5 * omega / kfb) *
+                                b97_poly(xb2, 0.004, 0.842294, 0.726479, 1.04760, -5.70635, 13.2794));
+  const T eaa = v.ra * pw92_ferro_1992(v.ra), ebb = v.rb * pw92_ferro_1992(v.rb);
+  const T eab = e_pw92(v, false) - eaa - ebb;
+  return ex + eaa * b97_poly(xa2, 0.2, 1.0, -4.33879, 18.2308, -31.7430, 17.2901) +
+         ebb * b97_poly(xb2, 0.2, 1.0, -4.33879, 18.2308, -31.7430, 17.2901) +
+         eab * b97_poly(0.5 * (xa2 + xb2), 0.006, 1.0, 2.37031, -11.3995, 6.58405, -3.78132);
+}
+
+// ---------------------------------------------------------------------------------------------
 template <class T> XC_HD T e_b3lyp(const XV<T> &v) { // libxc hyb_gga_xc_b3lyp: a0 = 0.20, ax = 0.72, ac = 0.81
   return 0.08 * e_lda_x(v) + 0.72 * e_b88(v) + 0.19 * e_vwn<1>(v) + 0.81 * e_lyp(v);
 }
@@ -440,6 +506,7 @@ template <class T> XC_HD T xc_energy_density(int id, const XV<T> &v) {
   case ID_HYB_GGA_XC_PBEH: return 0.75 * e_pbe_x(v) + e_pbe_c(v);
   case ID_HYB_GGA_XC_BHANDH: return 0.5 * e_lda_x(v) + e_lyp(v);
   case ID_HYB_GGA_XC_BHANDHLYP: return 0.5 * e_b88(v) + e_lyp(v);
+  case ID_HYB_GGA_XC_WB97X: return e_wb97x(v);
   default: return T(0.0);
   }
 }

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <cuda_runtime.h>
 #include <numeric>
+#include <nvtx3/nvToolsExt.h>
 #include <string>
 #include <vector>
 
@@ -80,9 +81,8 @@ static void solid_harmonic_table(int l, double *M /* (2l+1) x ncart */) {
   }
 }
 static const C2STable &c2s_table() {
-  static C2STable t;
-  static bool built = false;
-  if (!built) {
+  static const C2STable table = [] { // magic static: built once, safe when several threads create handles
+    C2STable t;
     int off = 0;
     for (int l = 0; l <= MAX_L; ++l) {
       t.off[l] = off;
@@ -90,9 +90,9 @@ static const C2STable &c2s_table() {
       off += (2 * l + 1) * (l + 1) * (l + 2) / 2;
     }
     t.off[MAX_L + 1] = off;
-    built = true;
-  }
-  return t;
+    return t;
+  }();
+  return table;
 }
 
 namespace xcb {
@@ -218,9 +218,11 @@ struct occ_xc_handle {
   double *scratch2 = nullptr; // workspace of the second lane
   int lanes = 1;
   bool profiling = false;
+  bool deterministic = false, nvtx = false;
+  double density_scale = 1.0, orbital_scale = 1.0;
   double phase_ms[OCC_XC_NPHASES] = {0, 0, 0, 0, 0, 0, 0};
   size_t launches = 0;
-  // MO-form density (options.reserved[3..4] = occupied-orbital counts at create)
+  // MO-form density (options.mo_form with the occupied-orbital counts at create)
   bool mo = false;
   int nocc[2] = {0, 0}, noccp = 0;
   DensItem *d_densmo = nullptr, *d_psi = nullptr, *d_xpsi = nullptr;
@@ -269,6 +271,17 @@ extern "C" {
 const char *occ_xc_last_error(void) { return g_last_error.c_str(); }
 int occ_xc_abi_version(void) { return OCC_XC_B200_ABI_VERSION; }
 int occ_xc_family(int id) { return xc_family_of(id); }
+int occ_xc_range_separation(int id, double *omega, double *alpha, double *beta) {
+  if (!omega || !alpha || !beta) return fail("occ_xc_range_separation: null argument");
+  if (xc_family_of(id) < 0) return fail("functional with id = " + std::to_string(id) + " not found");
+  xc_cam_of(id, omega, alpha, beta);
+  return 0;
+}
+void occ_xc_options_init(occ_xc_options_t *o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->device = -1;
+}
 double occ_xc_exact_exchange(int id) { return xc_exx_of(id); }
 
 int occ_xc_decay_cutoff(const occ_xc_basis_t *basis, double threshold, double *extents) {
@@ -356,7 +369,13 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
   const int rank = world > 1 ? opt->rank : 0;
   if (rank < 0 || rank >= world) return fail("occ_xc_create: rank outside [0, world_size)");
   const size_t batch_bytes = (opt && opt->batch_bytes) ? opt->batch_bytes : (size_t(4096) << 20);
-  const bool want_grad = opt && opt->reserved[2] == 1; // handle can also run occ_xc_gradient
+  const bool want_grad = opt && opt->gradient == 1; // handle can also run occ_xc_gradient
+  if (opt)
+    for (int r : opt->reserved)
+      if (r != 0) return fail("occ_xc_create: options.reserved must be zero (was the struct built for ABI version 1?)");
+  const bool want_mo = opt && opt->mo_form == 1;
+  if (want_mo && (opt->nocc_alpha < 0 || opt->nocc_beta < 0 || (opt->nocc_alpha == 0 && (nspin == 1 || opt->nocc_beta == 0))))
+    return fail("occ_xc_create: mo_form needs nocc_alpha > 0 (restricted) or nocc_alpha + nocc_beta > 0 (unrestricted)");
   if (want_grad && !basis->shell_atom) return fail("occ_xc_create: the gradient option needs basis->shell_atom");
 
   const int nsh = basis->nsh, pure = basis->pure ? 1 : 0;
@@ -420,7 +439,7 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
   size_t l_lo = 0, l_hi = hl.size();
   if (world > 1) {
     std::vector<double> costs(hl.size());
-    const int mo_nocc = (opt && opt->reserved[3] > 0) ? opt->reserved[3] : 0;
+    const int mo_nocc = want_mo ? std::max(opt->nocc_alpha, nspin == 2 ? opt->nocc_beta : 0) : 0;
     for (size_t i = 0; i < hl.size(); ++i) {
       costs[i] = hl[i].cost;
       if (mo_nocc > 0 && hl[i].nb > 2 * mo_nocc) costs[i] *= 0.5 * (1.0 + 2.0 * mo_nocc / hl[i].nb);
@@ -448,10 +467,10 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
   const int nslab = h->ncomp + (want_grad ? nspin : 0) + (want_grad && deriv >= 1 ? 3 * nspin : 0) +
                     (want_grad && deriv >= 2 ? 6 * nspin : 0);
   std::vector<int> bf_atom;
-  if (opt && opt->reserved[3] > 0) {
+  if (want_mo) {
     h->mo = true;
-    h->nocc[0] = opt->reserved[3];
-    h->nocc[1] = nspin == 2 ? (opt->reserved[4] > 0 ? opt->reserved[4] : opt->reserved[3]) : 0;
+    h->nocc[0] = opt->nocc_alpha;
+    h->nocc[1] = nspin == 2 ? opt->nocc_beta : 0; // 0 is a legal beta count (hydrogen atom): that spin runs no item
     if (h->nocc[0] > nbf || h->nocc[1] > nbf) {
       delete h;
       return fail("occ_xc_create: more occupied orbitals than basis functions");
@@ -604,6 +623,7 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
           const int npsib = h->noccp / 64;
           for (int sp = 0; sp < nspin; ++sp) {
             const int no = h->nocc[sp];
+            if (no == 0) continue; // empty spin (e.g. the beta spin of a hydrogen atom): its accumulators stay zero
             auto push = [&](std::vector<DensItem> &list, int nblocks, int ac) {
               for (int jb = 0; jb < nblocks; ++jb) {
                 DensItem di;
@@ -646,11 +666,11 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
                 gi.spin = static_cast<signed char>(sp);
                 gi.acomp = static_cast<signed char>(wh);
                 gradit.push_back(gi);
-                if (h->mo && t.nb <= 2 * h->nocc[sp]) gradd.push_back(gi);
+                if (h->mo && h->nocc[sp] > 0 && t.nb <= 2 * h->nocc[sp]) gradd.push_back(gi);
               }
           if (h->mo)
             for (int sp = 0; sp < nspin; ++sp) {
-              if (t.nb <= 2 * h->nocc[sp]) continue;
+              if (h->nocc[sp] == 0 || t.nb <= 2 * h->nocc[sp]) continue; // an empty spin has D_s = 0: no gradient term
               for (int wh = w0; wh <= w1; ++wh) {
                 DensItem gi;
                 gi.tile = ti;
@@ -764,17 +784,24 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
     const size_t nt = std::max(h->ntiles, 1);
     const size_t ksz = static_cast<size_t>(nspin) * nbf * nbf;
     rc |= dev_alloc(h, &P.scratch, max_scratch);
-    // second lane is opt-in (options.reserved[1] == 2): measured on B200 it buys nothing, the block scheduler
+    // second lane is opt-in (options.lanes == 2): measured on B200 it buys nothing, the block scheduler
     // does not co-schedule the second lane's kernels while the first lane fills the SMs (profiles/r01_experiments.md)
-    h->lanes = (opt && opt->reserved[1] == 2 && h->batches.size() >= 2) ? 2 : 1;
+    h->lanes = (opt && opt->lanes == 2 && h->batches.size() >= 2) ? 2 : 1;
     if (h->lanes == 2) rc |= dev_alloc(h, &h->scratch2, max_scratch);
-    rc |= dev_alloc(h, &P.acc, nt * nspin * NACC * TILE_P);
+    h->deterministic = opt && opt->deterministic == 1;
+    h->nvtx = opt && opt->nvtx == 1;
+    h->density_scale = (opt && opt->density_scale != 0.0) ? opt->density_scale : 1.0;
+    h->orbital_scale = (opt && opt->orbital_scale != 0.0) ? opt->orbital_scale : 1.0;
+    const size_t det = h->deterministic ? 2 : 1; // low bins right behind the accumulators
+    P.det_acc_off = static_cast<long long>(nt * nspin * NACC * TILE_P);
+    P.det_K_off = static_cast<long long>(ksz);
+    rc |= dev_alloc(h, &P.acc, det * nt * nspin * NACC * TILE_P);
     rc |= dev_alloc(h, &P.coef, nt * nspin * NCOEF * TILE_P);
     rc |= dev_alloc(h, &P.leaf_skip, std::max(h->nleaves, 1));
     rc |= dev_alloc(h, &P.leaf_sums, 3 * static_cast<size_t>(std::max(h->nleaves, 1)));
     rc |= dev_alloc(h, &h->d_D, ksz);
     rc |= dev_alloc(h, &h->d_Dsym, nspin == 1 ? ksz : 1);
-    rc |= dev_alloc(h, &h->d_Ktmp, ksz);
+    rc |= dev_alloc(h, &h->d_Ktmp, det * ksz);
     rc |= dev_alloc(h, &h->d_K, ksz);
     rc |= dev_alloc(h, &h->d_scalars, 4);
     if (want_grad) {
@@ -800,7 +827,7 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
   P.slab_S = P.slab_H + 3 * nspin;
   P.grad = h->d_grad;
   P.grad_factor = deriv == 0 ? -4.0 : -2.0;
-  P.debug = opt ? opt->reserved[0] : 0;
+  P.debug = opt ? static_cast<int>(opt->debug) : 0;
   P.ldC = nbf;
   P.ldCT = h->noccp;
   P.mo_noccp = h->noccp;
@@ -841,7 +868,7 @@ int occ_xc_build_device(occ_xc_handle *h, const double *D2_dev, double *K_dev, d
 
 int occ_xc_build_mo_device(occ_xc_handle *h, const double *D2_dev, const double *C_dev, double *K_dev,
                            double *scalars_dev, void *cuda_stream) {
-  if (!h || !D2_dev || !C_dev || !K_dev || !scalars_dev) return fail("occ_xc_build_mo_device: null argument");
+  if (!h || !C_dev || !K_dev || !scalars_dev) return fail("occ_xc_build_mo_device: null argument");
   if (!h->mo) return fail("occ_xc_build_mo_device: the handle was created without occupied-orbital counts");
   return build_device_impl(h, D2_dev, C_dev, K_dev, scalars_dev, cuda_stream);
 }
@@ -854,25 +881,20 @@ static int build_device_impl(occ_xc_handle *h, const double *D2_dev, const doubl
   const size_t ksz = static_cast<size_t>(h->nspin) * h->nbf * h->nbf;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   const bool prof = h->profiling;
+  const bool det = h->deterministic, nvtx = h->nvtx;
   float ms = 0.f;
   if (prof) {
     CUDA_TRY(cudaEventCreate(&ev[0]));
     CUDA_TRY(cudaEventCreate(&ev[1]));
     for (double &x : h->phase_ms) x = 0.0;
   }
-#define PHASE_BEGIN() do { if (prof) cudaEventRecord(ev[0], st); } while (0)
+  // phase brackets: CUDA events when profiling is on, NVTX ranges when options.nvtx is set
+#define PHASE_BEGIN(name) do { if (nvtx) nvtxRangePushA(name); if (prof) cudaEventRecord(ev[0], st); } while (0)
 #define PHASE_END(k) do { if (prof) { cudaEventRecord(ev[1], st); cudaEventSynchronize(ev[1]); \
-    cudaEventElapsedTime(&ms, ev[0], ev[1]); h->phase_ms[k] += ms; } } while (0)
+    cudaEventElapsedTime(&ms, ev[0], ev[1]); h->phase_ms[k] += ms; } if (nvtx) nvtxRangePop(); } while (0)
 
-  PHASE_BEGIN();
-  if (h->nspin == 1) {
-    launch_prepare_density(D2_dev, h->d_Dsym, h->nbf, 1, st);
-    P.Drho[0] = h->d_Dsym;
-    P.Dtau[0] = D2_dev;
-  } else {
-    for (int s = 0; s < 2; ++s) P.Drho[s] = P.Dtau[s] = D2_dev + static_cast<size_t>(s) * h->nbf;
-  }
-  CUDA_TRY(cudaMemsetAsync(h->d_Ktmp, 0, ksz * sizeof(double), st));
+  if (nvtx) nvtxRangePushA("occ_xc_build");
+  PHASE_BEGIN("prepare_D");
   const bool mo = C_dev != nullptr;
   if (mo) { // C_s^T once per build: the X = psi C^T contraction gathers whole rows of it
     for (int sp = 0; sp < h->nspin; ++sp) {
@@ -882,6 +904,26 @@ static int build_device_impl(occ_xc_handle *h, const double *D2_dev, const doubl
                             h->noccp, st);
     }
   }
+  if (!D2_dev) { // D2_s = C_s C_s^T formed here (occ_xc_build_mo with D2 = NULL): only C crossed PCIe
+    if (!mo) return fail("occ_xc_build: no density matrix");
+    for (int sp = 0; sp < h->nspin; ++sp) {
+      double *Ds = h->d_D + static_cast<size_t>(sp) * h->nbf;
+      if (h->nocc[sp] == 0) {
+        CUDA_TRY(cudaMemset2DAsync(Ds, static_cast<size_t>(P.ldD) * sizeof(double), 0, h->nbf * sizeof(double), h->nbf, st));
+        continue;
+      }
+      launch_dgemm(true, h->nbf, h->nbf, h->nocc[sp], 1.0, P.moC[sp], h->nbf, 0, P.moC[sp], h->nbf, 0, Ds, P.ldD, 0, 1, st);
+    }
+    D2_dev = h->d_D;
+  }
+  if (h->nspin == 1) {
+    launch_prepare_density(D2_dev, h->d_Dsym, h->nbf, 1, st);
+    P.Drho[0] = h->d_Dsym;
+    P.Dtau[0] = D2_dev;
+  } else {
+    for (int s = 0; s < 2; ++s) P.Drho[s] = P.Dtau[s] = D2_dev + static_cast<size_t>(s) * h->nbf;
+  }
+  CUDA_TRY(cudaMemsetAsync(h->d_Ktmp, 0, (det ? 2 : 1) * ksz * sizeof(double), st));
   PHASE_END(0);
   // Two lanes: batches alternate between the caller's stream and an auxiliary stream, each lane with its own AO
   // workspace.  The HBM-bound phases of one lane (collocation, G slab) and the tails of its DMMA kernels then overlap
@@ -897,25 +939,28 @@ static int build_device_impl(occ_xc_handle *h, const double *D2_dev, const doubl
     const bool second = lanes == 2 && (bi & 1);
     st = second ? h->aux_stream : main_st;
     P.scratch = second ? h->scratch2 : h->P.scratch;
-    PHASE_BEGIN();
+    PHASE_BEGIN("collocation");
     launch_collocate(P, h->d_colloc + b.colloc_off, static_cast<int>(b.ncolloc), st);
     PHASE_END(1);
-    PHASE_BEGIN();
-    CUDA_TRY(cudaMemsetAsync(P.acc + static_cast<size_t>(b.tile0) * h->nspin * NACC * TILE_P, 0,
-                             static_cast<size_t>(b.ntiles) * h->nspin * NACC * TILE_P * sizeof(double), st));
+    PHASE_BEGIN("density");
+    double *acc_b = P.acc + static_cast<size_t>(b.tile0) * h->nspin * NACC * TILE_P;
+    const size_t acc_n = static_cast<size_t>(b.ntiles) * h->nspin * NACC * TILE_P;
+    CUDA_TRY(cudaMemsetAsync(acc_b, 0, acc_n * sizeof(double), st));
+    if (det) CUDA_TRY(cudaMemsetAsync(acc_b + P.det_acc_off, 0, acc_n * sizeof(double), st));
     if (mo) {
-      launch_mo_psi(P, h->d_psi + b.psi_off, static_cast<int>(b.npsi), st);
-      launch_density(P, h->d_densmo + b.densmo_off, static_cast<int>(b.ndensmo), st);
-      launch_mo_density(P, h->d_xpsi + b.xpsi_off, static_cast<int>(b.nxpsi), st);
+      (det ? launch_mo_psi_det : launch_mo_psi)(P, h->d_psi + b.psi_off, static_cast<int>(b.npsi), st);
+      (det ? launch_density_det : launch_density)(P, h->d_densmo + b.densmo_off, static_cast<int>(b.ndensmo), st);
+      (det ? launch_mo_density_det : launch_mo_density)(P, h->d_xpsi + b.xpsi_off, static_cast<int>(b.nxpsi), st);
     } else {
-      launch_density(P, h->d_dens + b.dens_off, static_cast<int>(b.ndens), st);
+      (det ? launch_density_det : launch_density)(P, h->d_dens + b.dens_off, static_cast<int>(b.ndens), st);
     }
+    if (det) launch_add_inplace(acc_b, acc_b + P.det_acc_off, acc_n, st); // fold the low bins: one fixed-order add
     PHASE_END(2);
-    PHASE_BEGIN();
+    PHASE_BEGIN("functional");
     launch_functional(P, b.leaf0, b.nleaves, st);
     PHASE_END(3);
-    PHASE_BEGIN();
-    launch_vxc_resident(P, h->d_vxc + b.vxc_off, static_cast<int>(b.nvxc), st);
+    PHASE_BEGIN("vxc");
+    (det ? launch_vxc_resident_det : launch_vxc_resident)(P, h->d_vxc + b.vxc_off, static_cast<int>(b.nvxc), st);
     PHASE_END(5);
   }
   st = main_st;
@@ -923,9 +968,11 @@ static int build_device_impl(occ_xc_handle *h, const double *D2_dev, const doubl
     CUDA_TRY(cudaEventRecord(h->ev_join, h->aux_stream));
     CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join, 0));
   }
-  PHASE_BEGIN();
+  PHASE_BEGIN("finalise");
+  if (det) launch_add_inplace(h->d_Ktmp, h->d_Ktmp + P.det_K_off, ksz, st);
   launch_finalize(P, h->nleaves, K_dev, scalars_dev, st);
   PHASE_END(6);
+  if (nvtx) nvtxRangePop();
 #undef PHASE_BEGIN
 #undef PHASE_END
   if (prof) {
@@ -936,12 +983,26 @@ static int build_device_impl(occ_xc_handle *h, const double *D2_dev, const doubl
   return 0;
 }
 
-int occ_xc_build(occ_xc_handle *h, const double *D2, double *K, double *exc, double *n_alpha, double *n_beta) {
-  if (!h || !D2 || !K) return fail("occ_xc_build: null argument");
-  CUDA_TRY(cudaSetDevice(h->device));
+// host D (and C) -> device copies of the handle, with options.density_scale / orbital_scale applied on the device
+static int upload_inputs(occ_xc_handle *h, const double *D2, const double *C, const double **D_dev, const double **C_dev) {
   const size_t ksz = static_cast<size_t>(h->nspin) * h->nbf * h->nbf;
-  CUDA_TRY(cudaMemcpyAsync(h->d_D, D2, ksz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  if (occ_xc_build_device(h, h->d_D, h->d_K, h->d_scalars, h->stream)) return 1;
+  *D_dev = nullptr;
+  *C_dev = nullptr;
+  if (D2) {
+    CUDA_TRY(cudaMemcpyAsync(h->d_D, D2, ksz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h->density_scale != 1.0) launch_scale(h->d_D, h->d_D, ksz, h->density_scale, h->stream);
+    *D_dev = h->d_D;
+  }
+  if (C) {
+    const size_t csz = static_cast<size_t>(h->nbf) * (h->nocc[0] + h->nocc[1]);
+    CUDA_TRY(cudaMemcpyAsync(h->d_C, C, csz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h->orbital_scale != 1.0) launch_scale(h->d_C, h->d_C, csz, h->orbital_scale, h->stream);
+    *C_dev = h->d_C;
+  }
+  return 0;
+}
+static int download_outputs(occ_xc_handle *h, double *K, double *exc, double *n_alpha, double *n_beta) {
+  const size_t ksz = static_cast<size_t>(h->nspin) * h->nbf * h->nbf;
   CUDA_TRY(cudaMemcpyAsync(K, h->d_K, ksz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   double sc[3];
   CUDA_TRY(cudaMemcpyAsync(sc, h->d_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -950,6 +1011,15 @@ int occ_xc_build(occ_xc_handle *h, const double *D2, double *K, double *exc, dou
   if (n_alpha) *n_alpha = sc[1];
   if (n_beta) *n_beta = sc[2];
   return 0;
+}
+
+int occ_xc_build(occ_xc_handle *h, const double *D2, double *K, double *exc, double *n_alpha, double *n_beta) {
+  if (!h || !D2 || !K) return fail("occ_xc_build: null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const double *Dd, *Cd;
+  if (upload_inputs(h, D2, nullptr, &Dd, &Cd)) return 1;
+  if (build_device_impl(h, Dd, nullptr, h->d_K, h->d_scalars, h->stream)) return 1;
+  return download_outputs(h, K, exc, n_alpha, n_beta);
 }
 
 int occ_xc_density_on_grid(occ_xc_handle *h, const double *D2, double *rho) {
@@ -1066,22 +1136,13 @@ int occ_xc_vv10(occ_xc_handle *h, const double *D2, const size_t *orig_index, do
 
 int occ_xc_build_mo(occ_xc_handle *h, const double *D2, const double *C, double *K, double *exc, double *n_alpha,
                     double *n_beta) {
-  if (!h || !D2 || !C || !K) return fail("occ_xc_build_mo: null argument");
+  if (!h || !C || !K) return fail("occ_xc_build_mo: null argument");
   if (!h->mo) return fail("occ_xc_build_mo: the handle was created without occupied-orbital counts");
   CUDA_TRY(cudaSetDevice(h->device));
-  const size_t ksz = static_cast<size_t>(h->nspin) * h->nbf * h->nbf;
-  const size_t csz = static_cast<size_t>(h->nbf) * (h->nocc[0] + h->nocc[1]);
-  CUDA_TRY(cudaMemcpyAsync(h->d_D, D2, ksz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(h->d_C, C, csz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  if (build_device_impl(h, h->d_D, h->d_C, h->d_K, h->d_scalars, h->stream)) return 1;
-  CUDA_TRY(cudaMemcpyAsync(K, h->d_K, ksz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  double sc[3];
-  CUDA_TRY(cudaMemcpyAsync(sc, h->d_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
-  if (exc) *exc = sc[0];
-  if (n_alpha) *n_alpha = sc[1];
-  if (n_beta) *n_beta = sc[2];
-  return 0;
+  const double *Dd, *Cd;
+  if (upload_inputs(h, D2, C, &Dd, &Cd)) return 1; // D2 == NULL: formed on the device as C C^T
+  if (build_device_impl(h, Dd, Cd, h->d_K, h->d_scalars, h->stream)) return 1;
+  return download_outputs(h, K, exc, n_alpha, n_beta);
 }
 
 int occ_xc_pinned_alloc(size_t bytes, void **out) {

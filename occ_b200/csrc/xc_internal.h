@@ -108,6 +108,9 @@ struct BuildParams {
   int mo_noccp;          // psi slab width: max nocc rounded up to 64
   const long long *tile_psi_off; // [ntiles] offset of the tile's psi slabs: psi_s at tile_psi_off[tile] + s * noccp * 128
                                  // (kept out of TileDesc: its layout feeds the register allocation of the tuned D-form kernel)
+  // ---- deterministic accumulation (options.deterministic): distance in doubles from an accumulator to its low bin
+  long long det_acc_off; // acc    -> acc_lo
+  long long det_K_off;   // Ktmp   -> Ktmp_lo
 };
 
 // ---- post-SCF VV10: per-point arrays in the REFERENCE's point order ----
@@ -133,6 +136,17 @@ void launch_collocate(const BuildParams &P, const CollocItem *items, int nitems,
 void launch_density(const BuildParams &P, const DensItem *items, int nitems, void *stream);
 void launch_functional(const BuildParams &P, int leaf0, int nleaves, void *stream);
 void launch_vxc_resident(const BuildParams &P, const VxcItem *items, int nitems, void *stream);
+// order-independent variants (k_*_det.cu)
+void launch_density_det(const BuildParams &P, const DensItem *items, int nitems, void *stream);
+void launch_vxc_resident_det(const BuildParams &P, const VxcItem *items, int nitems, void *stream);
+void launch_mo_psi_det(const BuildParams &P, const DensItem *items, int nitems, void *stream);
+void launch_mo_density_det(const BuildParams &P, const DensItem *items, int nitems, void *stream);
+// plain FP64 GEMM on the DMMA pipe and elementwise helpers (k_dgemm.cu)
+void launch_dgemm(bool b_transposed, int M, int N, int K, double alpha, const double *A, int lda, long long strideA,
+                  const double *B, int ldb, long long strideB, double *C, int ldc, long long strideC, int batches,
+                  void *stream);
+void launch_scale(const double *in, double *out, size_t n, double s, void *stream);
+void launch_add_inplace(double *a, const double *b, size_t n, void *stream);
 void launch_gbuild(const BuildParams &P, const DensItem *items, int nitems, void *stream);
 void launch_collocate_h(const BuildParams &P, const CollocItem *items, int nitems, void *stream);
 void launch_mo_psi(const BuildParams &P, const DensItem *items, int nitems, void *stream);

@@ -25,7 +25,7 @@ FUNCTIONAL_IDS = {"lda_x": 1, "lda_c_vwn": 7, "lda_c_vwn_rpa": 8, "lda_c_vwn_3":
                   "gga_x_b88": 106, "gga_c_pbe": 130, "gga_c_lyp": 131, "hyb_gga_xc_b3lyp": 402,
                   "mgga_x_r2scan": 497, "mgga_c_r2scan": 498, "lda_c_pw": 12, "lda_c_pw_mod": 13, "mgga_x_tpss": 202,
                   "mgga_c_tpss": 231, "hyb_gga_xc_pbeh": 406, "hyb_gga_xc_bhandh": 435, "hyb_gga_xc_bhandhlyp": 436,
-                  "hyb_gga_xc_b3lyp5": 475}
+                  "hyb_gga_xc_b3lyp5": 475, "hyb_gga_xc_wb97x": 464}
 
 # src/dft/dft_method.cpp:14-37 (builtin_definitions), restricted to components this library implements
 METHOD_DEFINITIONS = {
@@ -42,13 +42,14 @@ METHOD_DEFINITIONS = {
     "tpss": ["mgga_x_tpss", "mgga_c_tpss"],
     "b3lyp5": ["hyb_gga_xc_b3lyp5"],
     "pbeh": ["hyb_gga_xc_pbeh"],
+    "wb97x": ["hyb_gga_xc_wb97x"],
     # the 0.75 component factor of pbe0 / pbe1pbe is stored but never applied by the reference
     # (include/occ/dft/functional.h:506-508), so its XC build evaluates full PBE exchange; same here
     "pbe0": ["gga_x_pbe", "gga_c_pbe"],
     "pbe1pbe": ["gga_x_pbe", "gga_c_pbe"],
 }
 # builtin entries whose libxc components are NOT implemented here (get_dft_method raises for them):
-# b3pw91, b97, bp86 (gga_c_p86), m062x, wb97x, wb97m(-v)
+# b3pw91, b97, bp86 (gga_c_p86), m062x, wb97m(-v)
 
 RESTRICTED, UNRESTRICTED = "restricted", "unrestricted"
 
@@ -84,7 +85,8 @@ class DFT:
     def __init__(self, method: str, basis: AOBasis, grid: GridHierarchy, spinorbital_kind: str = RESTRICTED,
                  device: int = -1, rank: int = 0, world_size: int = 1, batch_bytes: int = 0,
                  density_threshold: float = 1e-10, xc_screening_threshold: float = 1e-10, shell_extents=None,
-                 debug: int = 0, lanes: int = 1, gradient: bool = False, nocc=None):
+                 debug: int = 0, lanes: int = 1, gradient: bool = False, nocc=None, deterministic: bool = False,
+                 nvtx: bool = False, density_scale: float = 0.0, orbital_scale: float = 0.0):
         self.basis = basis
         self.method = method
         self.func_ids = np.array(get_dft_method(method), dtype=np.int32)
@@ -95,15 +97,17 @@ class DFT:
         w = np.ascontiguousarray(grid.sorted_weights, dtype=np.float64)
         leaves = np.ascontiguousarray(grid.leaves, dtype=LEAF_DTYPE)
         ext = None if shell_extents is None else np.ascontiguousarray(shell_extents, dtype=np.float64)
-        opt = OptionsT(device, rank, world_size, batch_bytes)
-        opt.reserved[0] = debug
-        opt.reserved[1] = lanes
-        opt.reserved[2] = int(gradient)
+        opt = OptionsT()
+        lib().occ_xc_options_init(C.byref(opt))
+        opt.device, opt.rank, opt.world_size, opt.batch_bytes = device, rank, world_size, batch_bytes
+        opt.debug, opt.lanes, opt.gradient = debug, lanes, int(gradient)
+        opt.deterministic, opt.nvtx = int(deterministic), int(nvtx)
+        opt.density_scale, opt.orbital_scale = density_scale, orbital_scale
         self.nocc = None
-        if nocc is not None:        # enables build_mo: occupied-orbital counts (alpha[, beta])
+        if nocc is not None:        # enables build_mo: occupied-orbital counts (alpha[, beta]); beta may be 0
             na, nb_ = (nocc, nocc) if np.isscalar(nocc) else (nocc[0], nocc[-1])
-            opt.reserved[3], opt.reserved[4] = int(na), int(nb_)
-            self.nocc = (int(na), int(nb_))
+            opt.mo_form, opt.nocc_alpha, opt.nocc_beta = 1, int(na), int(nb_)
+            self.nocc = (int(na), int(nb_) if self.nspin == 2 else 0)
         self._h = C.c_void_p()
         check(lib().occ_xc_create(self._basis_arrays.ref, C.c_size_t(len(w)), ptr(pts), ptr(w), C.c_size_t(len(leaves)),
                                   ptr(leaves), ptr(ext) if ext is not None else None, C.c_int(len(self.func_ids)),
@@ -119,6 +123,16 @@ class DFT:
 
     def exact_exchange_factor(self) -> float:
         return float(sum(lib().occ_xc_exact_exchange(int(f)) for f in self.func_ids))
+
+    def range_separated_parameters(self) -> dict:
+        """DFT::range_separated_parameters (src/dft/dft.cpp:128-130): the component with omega != 0, if any"""
+        out = {"omega": 0.0, "alpha": 0.0, "beta": 0.0}
+        for f in self.func_ids:
+            o, a, b = C.c_double(), C.c_double(), C.c_double()
+            check(lib().occ_xc_range_separation(int(f), C.byref(o), C.byref(a), C.byref(b)))
+            if o.value != 0.0:
+                out = {"omega": o.value, "alpha": a.value, "beta": b.value}
+        return out
 
     def exchange_correlation_energy(self) -> float:
         return self.m_exc_dft
@@ -155,16 +169,18 @@ class DFT:
         if self.nocc is None:
             raise RuntimeError("DFT was created without nocc: build_mo is not available")
         n = self.nspin * self.nbf
-        D2 = np.asfortranarray(D2, dtype=np.float64)
-        if D2.shape != (n, self.nbf):
-            raise RuntimeError(f"density matrix has shape {D2.shape}, expected {(n, self.nbf)}")
+        if D2 is not None:            # None: D2 = C C^T is formed on the device
+            D2 = np.asfortranarray(D2, dtype=np.float64)
+            if D2.shape != (n, self.nbf):
+                raise RuntimeError(f"density matrix has shape {D2.shape}, expected {(n, self.nbf)}")
         Cs = [C] if isinstance(C, np.ndarray) else list(C)
         if len(Cs) != self.nspin or any(c.shape != (self.nbf, self.nocc[s]) for s, c in enumerate(Cs)):
             raise RuntimeError("orbital coefficients do not match (nbf, nocc) of the handle")
         packed = np.concatenate([np.asfortranarray(c, dtype=np.float64).ravel(order="F") for c in Cs])
         K = out if out is not None else np.zeros((n, self.nbf), order="F")
         exc, na, nb = C_.c_double(), C_.c_double(), C_.c_double()
-        check(lib().occ_xc_build_mo(self._h, ptr(D2), ptr(packed), ptr(K), C_.byref(exc), C_.byref(na), C_.byref(nb)))
+        check(lib().occ_xc_build_mo(self._h, ptr(D2) if D2 is not None else None, ptr(packed), ptr(K), C_.byref(exc),
+                                    C_.byref(na), C_.byref(nb)))
         self.m_exc_dft = exc.value
         self.total_density = (na.value, nb.value)
         return K

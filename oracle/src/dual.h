@@ -98,6 +98,9 @@ template <int N> inline Dual<N> atan(const Dual<N> &a) { return chain(a, std::at
 template <int N> inline Dual<N> asinh(const Dual<N> &a) {
   return chain(a, std::asinh(a.v), 1.0 / std::sqrt(1.0 + a.v * a.v));
 }
+template <int N> inline Dual<N> erf(const Dual<N> &a) {
+  return chain(a, std::erf(a.v), 1.1283791670955126 * std::exp(-a.v * a.v)); // 2/sqrt(pi)
+}
 template <int N> inline Dual<N> pow(const Dual<N> &a, double p) {
   const double f = std::pow(a.v, p);
   return chain(a, f, p * std::pow(a.v, p - 1.0));
@@ -111,6 +114,7 @@ inline double log1p(double x) { return std::log1p(x); }
 inline double expm1(double x) { return std::expm1(x); }
 inline double atan(double x) { return std::atan(x); }
 inline double asinh(double x) { return std::asinh(x); }
+inline double erf(double x) { return std::erf(x); }
 inline double pow(double x, double p) { return std::pow(x, p); }
 inline double value(double x) { return x; }
 template <int N> inline double value(const Dual<N> &x) { return x.v; }

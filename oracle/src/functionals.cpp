@@ -379,8 +379,69 @@ template <class T> T F_pbeh(const Vars<T> &v) { return 0.75 * F_pbe_x(v) + F_pbe
 template <class T> T F_bhandh(const Vars<T> &v) { return 0.5 * F_lda_x(v) + F_lyp(v); }
 template <class T> T F_bhandhlyp(const Vars<T> &v) { return 0.5 * F_b88(v) + F_lyp(v); }
 
+// ------------------------------------------------------------------------------------------------
+// B97-type power-series GGAs with a short-range (erf-attenuated) LSDA exchange: wB97X of Chai & Head-Gordon,
+// J. Chem. Phys. 128, 084106 (2008) [libxc hyb_gga_xc_wb97x, id 464; reference table src/dft/dft_method.cpp:35].
+//   E_xc = sum_s e_x^LSDA(rho_s) F(a_s) g_x(x_s^2) + sum_s e_c,ss g_ss(x_s^2) + e_c,ab g_ab((x_a^2 + x_b^2)/2)
+//   x_s = |grad rho_s| / rho_s^(4/3);  g(x^2) = sum_i c_i u^i,  u = gamma x^2 / (1 + gamma x^2),
+//   gamma_x = 0.004, gamma_ss = 0.2, gamma_ab = 0.006 (Becke, J. Chem. Phys. 107, 8554 (1997));
+//   e_c,ss / e_c,ab: Stoll partition of the PW92 correlation energy with the constants AS PRINTED in 1992 (libxc's
+//   lda_c_pw set; the more-digit "modified" set moves the water/3-21G golden by 4.5e-6 Eh, see tests/test_isolated_xc.py);
+//   F(a): attenuation of the LSDA exchange hole by erfc(omega r)/r, a_s = omega / (2 k_Fs), k_Fs = (6 pi^2 rho_s)^(1/3)
+//   (Gill, Adamson, Pople, Mol. Phys. 88, 1005 (1996); eq. 7-8 of the wB97X paper), omega = 0.3.
+// The exact-exchange part (100 % long range + 15.7706 % short range) is the Fock build's business
+// (DFT::compute_JK -> range-separated K); xc_hyb_cam_coef: omega 0.3, alpha 1.0, beta -0.842294.
+// Pinned by the reference's own isolated-XC golden -6.577307030585 (tests/isolated_xc_tests.cpp:296-319).
+template <class T> T sr_attenuation(const T &a) {
+  if (value(a) >= 3.0) { // asymptotic series (the closed form cancels to 1/(36 a^2) from O(1) terms)
+    const T i2 = 1.0 / sq(a);
+    return i2 * (1.0 / 36.0 + i2 * (-1.0 / 960.0 + i2 * (1.0 / 26880.0 + i2 * (-1.0 / 829440.0 + i2 * (1.0 / 28385280.0 +
+           i2 * (-1.0 / 1073479680.0 + i2 * (1.0 / 44590694400.0 + i2 * (-1.0 / 2021444812800.0))))))));
+  }
+  const T b = expm1(-0.25 / sq(a));
+  const T c = 2.0 * sq(a) * b + 0.5;
+  return 1.0 - (8.0 / 3.0) * a * (std::sqrt(kPi) * erf(0.5 / a) + 2.0 * a * (b - c));
+}
+template <class T> T b97_series(double gamma, const double *c, const T &x2) {
+  const T u = gamma * x2 / (1.0 + gamma * x2);
+  return c[0] + u * (c[1] + u * (c[2] + u * (c[3] + u * c[4])));
+}
+struct B97Set {
+  double cx[5], css[5], cab[5], omega;
+};
+const B97Set kWB97X = {{0.842294, 0.726479, 1.04760, -5.70635, 13.2794},
+                       {1.00000, -4.33879, 18.2308, -31.7430, 17.2901},
+                       {1.00000, 2.37031, -11.3995, 6.58405, -3.78132},
+                       0.3};
+template <class T> T F_b97_family(const B97Set &P, const Vars<T> &v) {
+  const double cx_lsda = -0.75 * std::cbrt(6.0 / kPi);
+  const T r43a = v.ra * cbrt(v.ra), r43b = v.rb * cbrt(v.rb);
+  const T x2a = v.saa / sq(r43a), x2b = v.sbb / sq(r43b);
+  // exchange
+  T ex = T(0.0);
+  const T *r43[2] = {&r43a, &r43b};
+  const T *x2[2] = {&x2a, &x2b};
+  const T *rs_[2] = {&v.ra, &v.rb};
+  for (int s = 0; s < 2; ++s) {
+    T att = T(1.0);
+    if (P.omega > 0.0) att = sr_attenuation(P.omega / (2.0 * cbrt(6.0 * kPi * kPi * *rs_[s])));
+    ex = ex + cx_lsda * *r43[s] * att * b97_series(0.004, P.cx, *x2[s]);
+  }
+  // correlation, Stoll partition of PW92
+  T rho, rs, z;
+  rs_zeta(v, rho, rs, z);
+  const T ec_tot = F_pw<T, 0>(v);
+  const T rsa = cbrt(3.0 / (4.0 * kPi * v.ra)), rsb = cbrt(3.0 / (4.0 * kPi * v.rb));
+  const T ec_aa = v.ra * pw_G(pw_orig[1], rsa), ec_bb = v.rb * pw_G(pw_orig[1], rsb);
+  const T ec_ab = ec_tot - ec_aa - ec_bb;
+  return ex + ec_aa * b97_series(0.2, P.css, x2a) + ec_bb * b97_series(0.2, P.css, x2b) +
+         ec_ab * b97_series(0.006, P.cab, 0.5 * (x2a + x2b));
+}
+template <class T> T F_wb97x(const Vars<T> &v) { return F_b97_family(kWB97X, v); }
+
 template <class T> bool F_dispatch(int id, const Vars<T> &v, T &out) {
   switch (id) {
+  case ORC_HYB_GGA_XC_WB97X: out = F_wb97x(v); return true;
   case ORC_LDA_C_PW: out = F_pw<T, 0>(v); return true;
   case ORC_LDA_C_PW_MOD: out = F_pw<T, 1>(v); return true;
   case ORC_MGGA_X_TPSS: out = F_tpss_x(v); return true;
@@ -495,6 +556,7 @@ int orc_xc_family(int id) {
   case ORC_HYB_GGA_XC_PBEH:
   case ORC_HYB_GGA_XC_BHANDH:
   case ORC_HYB_GGA_XC_BHANDHLYP:
+  case ORC_HYB_GGA_XC_WB97X:
     return 1;
   case ORC_MGGA_X_R2SCAN:
   case ORC_MGGA_C_R2SCAN:
@@ -516,6 +578,8 @@ double orc_xc_exx(int id) { // xc_hyb_exx_coef (include/occ/dft/functional.h:557
   case ORC_HYB_GGA_XC_BHANDH:
   case ORC_HYB_GGA_XC_BHANDHLYP:
     return 0.50;
+  case ORC_HYB_GGA_XC_WB97X:
+    return 1.0; // libxc: xc_hyb_exx_coef returns cam_alpha (the full-range fraction); beta = -0.842294 at omega = 0.3
   default:
     return 0.0;
   }

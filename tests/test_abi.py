@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
     assert sorted(_lib.SYMBOLS) == header_symbols()
     L.occ_xc_abi_version.restype = ctypes.c_int
-    assert L.occ_xc_abi_version() == 1
+    assert L.occ_xc_abi_version() == 2
 
 
 def test_pure_host_entry_points():
