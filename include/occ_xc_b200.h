@@ -202,6 +202,31 @@ typedef struct {
 } occ_xc_info_t;
 int occ_xc_get_info(const occ_xc_handle *h, occ_xc_info_t *info);
 
+/* ---- several GPUs of one box, driven from ONE host process ---------------------------------------------------
+ * The reference's SCF is a single process whose leaf loop is a tbb::parallel_for over thread-local K copies followed by
+ * a serial reduction (include/occ/dft/dft.h:221-232,303-371,375-380; caller include/occ/qm/scf_impl.h:539).  Here the
+ * "threads" are GPUs: occ_xc_multi_create builds one handle per device (leaf shard r of ndev, the split of
+ * occ_xc_partition_leaves), occ_xc_multi_build runs them concurrently and returns the SUMMED K / Exc / N:
+ *   inputs  each GPU pulls 1/ndev of D2 / C from the host over its own PCIe link and gathers the other slices from
+ *           its peers over NVLink, so the host matrix crosses PCIe once in total;
+ *   output  GPU r sums column panel r of K over all partial matrices through peer loads (NVSwitch), in rank order,
+ *           and writes the panel to the host matrix — a reduce-scatter without NCCL.
+ * Needs peer access between the devices.  `options`: device / rank / world_size are overwritten per handle;
+ * `devices` NULL = ordinals 0..ndev-1; an ordinal may repeat (several shards on one GPU).
+ * occ_xc_multi_build: D2, K, exc, n_alpha, n_beta as in occ_xc_build; C as in occ_xc_build_mo or NULL for the D form;
+ * D2 may be NULL when C is given. */
+typedef struct occ_xc_multi occ_xc_multi;
+int occ_xc_multi_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xyz, const double *weights,
+                        size_t nleaves, const occ_xc_leaf_t *leaves, const double *shell_extents, int nfunc,
+                        const int *func_ids, int nspin, double density_threshold, double screening_threshold,
+                        const occ_xc_options_t *options, int ndev, const int *devices, occ_xc_multi **out);
+int occ_xc_multi_build(occ_xc_multi *m, const double *D2, const double *C, double *K, double *exc, double *n_alpha,
+                       double *n_beta);
+int occ_xc_multi_ndev(const occ_xc_multi *m);
+int occ_xc_multi_get_info(const occ_xc_multi *m, int rank, occ_xc_info_t *info); /* the shard of handle `rank` */
+void occ_xc_multi_destroy(occ_xc_multi *m);
+
+
 /* Per-phase device times (ms, CUDA events on the build stream) of the LAST build when profiling is on.
  * phases: 0 prepare-D, 1 collocation, 2 density contraction, 3 functional, 4 (G slab: always 0 in the build since the
  * Vxc kernel forms its G block in shared memory; index kept stable), 5 Vxc contraction, 6 finalise */
@@ -261,6 +286,11 @@ int occ_xc_grid_atom_info(const occ_xc_grid *g, int atom, size_t *npts, int *nra
 int occ_xc_grid_copy(const occ_xc_grid *g, double *sorted_pts, double *sorted_w, occ_xc_leaf_t *leaves, size_t *perm,
                      double *pts, double *w);
 void occ_xc_grid_destroy(occ_xc_grid *g);
+
+/* Measurement aid: the sustained FP64 tensor-core (DMMA.8x8x4) rate of `device` (-1 = current) over about target_ms
+ * milliseconds of register-resident mma.sync.m8n8k4.f64 — the denominator bench.py quotes the contraction kernels
+ * against, measured in the same process and at the same clocks as the build (MEASURED_PEAKS.json has no FP64 entry). */
+int occ_xc_measure_fp64_tensor_peak(int device, double target_ms, double *tflops, double *measured_ms);
 
 void occ_xc_destroy(occ_xc_handle *h);
 const char *occ_xc_last_error(void);

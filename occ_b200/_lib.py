@@ -18,7 +18,8 @@ SYMBOLS = ["occ_xc_create", "occ_xc_build", "occ_xc_build_device", "occ_xc_build
            "occ_xc_get_phase_ms", "occ_xc_decay_cutoff", "occ_xc_eval_functional", "occ_xc_leaf_collocation",
            "occ_xc_family", "occ_xc_exact_exchange", "occ_xc_range_separation", "occ_xc_options_init", "occ_xc_destroy", "occ_xc_last_error", "occ_xc_abi_version",
            "occ_xc_partition_leaves", "occ_xc_register_lebedev", "occ_xc_grid_create", "occ_xc_grid_from_points", "occ_xc_grid_npts",
-           "occ_xc_grid_nleaves", "occ_xc_grid_atom_info", "occ_xc_grid_copy", "occ_xc_grid_destroy"]
+           "occ_xc_grid_nleaves", "occ_xc_grid_atom_info", "occ_xc_grid_copy", "occ_xc_grid_destroy",
+           "occ_xc_measure_fp64_tensor_peak", "occ_xc_multi_create", "occ_xc_multi_build", "occ_xc_multi_ndev", "occ_xc_multi_get_info", "occ_xc_multi_destroy"]
 # every symbol include/occ_cosx_b200.h declares
 COSX_SYMBOLS = ["occ_cosx_create", "occ_cosx_compute_K", "occ_cosx_compute_K_range_separated", "occ_cosx_compute_K_mo",
                 "occ_cosx_compute_K_range_separated_mo", "occ_cosx_K_for_density",
@@ -89,6 +90,11 @@ def lib():
         L.occ_xc_grid_destroy.argtypes = [C.c_void_p]
         L.occ_xc_grid_copy.argtypes = [C.c_void_p] + [C.c_void_p] * 6
         L.occ_xc_grid_atom_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.occ_xc_options_init.restype = None
+        L.occ_xc_multi_destroy.restype = None
+        L.occ_xc_multi_destroy.argtypes = [C.c_void_p]
+        L.occ_xc_multi_build.argtypes = [C.c_void_p] * 7
+        L.occ_xc_multi_get_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         tables = np.load(os.path.join(HERE, "data", "lebedev_tables.npz"))
         for k in tables.files:
             a = np.ascontiguousarray(tables[k], dtype=np.float64)

@@ -192,4 +192,57 @@ void launch_add_inplace(double *a, const double *b, size_t n, void *stream) {
   k_axpy1<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, n);
 }
 
+// ---- FP64 tensor-pipe ceiling, measured live (the roofline denominator of bench.py) ----------------------------
+// Register-resident mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4, the only f64 MMA shape sm_100a executes): 8 warps per CTA,
+// 2 CTAs per SM like the contraction kernels, 16 independent accumulator pairs per thread so the pipe never waits on
+// a dependency, no memory traffic inside the loop.  Flops per DMMA: 8 x 8 x 4 x 2 = 512 per warp.
+__global__ void __launch_bounds__(NTHREADS, 2) k_dmma_peak(double *out, int iters) {
+  double acc[16][2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i][0] = acc[i][1] = 0.0;
+  double a = 1e-3 * (threadIdx.x + 1), b = 1.0 + 1e-6 * threadIdx.x;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dmma884(acc[i][0], acc[i][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i][0] + acc[i][1];
+  out[static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x] = s;
+}
+
+// returns 0 on success; *tflops = sustained DMMA rate over ~`target_ms` of the current device
+int measure_dmma_peak(double target_ms, double *tflops, double *measured_ms) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1;
+  const int blocks = 2 * sms;
+  double *d_out = nullptr;
+  if (cudaMalloc(&d_out, static_cast<size_t>(blocks) * NTHREADS * sizeof(double)) != cudaSuccess) return 1;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  auto run = [&](int iters, float *ms) -> bool {
+    cudaEventRecord(e0);
+    k_dmma_peak<<<blocks, NTHREADS>>>(d_out, iters);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess || cudaGetLastError() != cudaSuccess) return false;
+    cudaEventElapsedTime(ms, e0, e1);
+    return true;
+  };
+  float ms = 0.f;
+  bool ok = run(2000, &ms) && run(20000, &ms); // warm-up, then calibrate
+  int iters = 20000;
+  if (ok && ms > 0.f) iters = static_cast<int>(std::min(4.0e7, std::max(2.0e4, 20000.0 * target_ms / ms)));
+  ok = ok && run(iters, &ms);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  if (!ok || !(ms > 0.f)) return 1;
+  const double flops = 512.0 * 16.0 * iters * (NTHREADS / 32.0) * blocks;
+  *tflops = flops / (ms * 1e-3) / 1e12;
+  if (measured_ms) *measured_ms = ms;
+  return 0;
+}
+
 } // namespace xcb

@@ -227,8 +227,17 @@ template <class T> XC_HD T deps_pw_drs(const T &rs, const T &z) {
   const T z4 = z2 * z2;
   return e0 - mac * fz * (1.0 - z4) / XC_FPP0 + (e1 - e0) * fz * z4;
 }
-template <class T> XC_HD T phi_zeta(const T &z) {
-  const T p = 1.0 + z, m = 1.0 - z;
+// 1 + zeta and 1 - zeta formed as 2 rho_s / rho rather than 1 +- (ra - rb) / rho: near full polarisation (a spin
+// density at its 1e-15 floor) the latter carries an O(1e-16) absolute rounding error in a quantity of size 1e-14, and
+// the functions below have derivatives like (1 - zeta)^(-1/3) there — two libm's then differ in the 3rd digit.
+template <class T> XC_HD void zeta_pm(const XV<T> &v, T &zp, T &zm) {
+  const T inv = 2.0 / (v.ra + v.rb);
+  zp = v.ra * inv;
+  zm = v.rb * inv;
+}
+template <class T> XC_HD T phi_zeta(const XV<T> &v) {
+  T p, m;
+  zeta_pm(v, p, m);
   return 0.5 * (cbrt(p * p) + cbrt(m * m));
 }
 template <class T> XC_HD T e_pbe_c(const XV<T> &v) {
@@ -236,7 +245,7 @@ template <class T> XC_HD T e_pbe_c(const XV<T> &v) {
   T rho, rs, z;
   rs_zeta(v, rho, rs, z);
   const T ec = eps_pw(rs, z);
-  const T phi = phi_zeta(z);
+  const T phi = phi_zeta(v);
   const T phi2 = phi * phi;
   const T phi3 = phi * phi2;
   const T stot = v.saa + 2.0 * v.sab + v.sbb;
@@ -306,10 +315,11 @@ template <class T> XC_HD T e_r2scan_c(const XV<T> &v) {
   const T stot = v.saa + 2.0 * v.sab + v.sbb;
   const T tau = v.ta + v.tb;
   const T p = red_grad2(rho, stot);
-  const T zp = 1.0 + z, zm = 1.0 - z;
+  T zp, zm;
+  zeta_pm(v, zp, zm);
   const T ds = 0.5 * (zp * cbrt(zp * zp) + zm * cbrt(zm * zm));
   const T dxz = 0.5 * (zp * cbrt(zp) + zm * cbrt(zm));
-  const T phi = phi_zeta(z);
+  const T phi = phi_zeta(v);
   const T phi2 = phi * phi;
   const T phi3 = phi * phi2;
   const T tauW = stot / (8.0 * rho);
@@ -415,7 +425,8 @@ template <class T> XC_HD T e_tpss_c(const XV<T> &v) {
   // xi^2 = |grad zeta|^2 / (4 (3 pi^2 n)^(2/3)), |grad zeta|^2 = 4 |nb grad na - na grad nb|^2 / n^4
   const T kF = cbrt(XC_3PI2 * rho);
   const T xi2 = (v.rb * v.rb * v.saa - 2.0 * (v.ra * v.rb) * v.sab + v.ra * v.ra * v.sbb) / (rho2 * rho2 * (kF * kF));
-  const T zp = 1.0 + zeta, zm = 1.0 - zeta;
+  T zp, zm;
+  zeta_pm(v, zp, zm);
   const T w = 1.0 + 0.5 * xi2 * (1.0 / (zp * cbrt(zp)) + 1.0 / (zm * cbrt(zm)));
   const T w2 = w * w;
   const T C = C0 / (w2 * w2);
@@ -433,11 +444,12 @@ template <class T> XC_HD T e_tpss_c(const XV<T> &v) {
 // u = gamma x^2 / (1 + gamma x^2), x_s = |grad rho_s| / rho_s^(4/3), on (i) the LSDA exchange attenuated by the
 // short-range operator erfc(omega r)/r, omega = 0.3, (ii) the same-spin and (iii) the opposite-spin parts of the
 // Stoll-partitioned PW92 correlation (1992 constants).  Golden: tests/isolated_xc_tests.cpp:296-319 of the reference.
-template <class T> XC_HD T wb97_attenuation(const T &a) { // eq. (8) of the paper; series for a >= 3
-  const T a2 = a * a;
-  if (val(a) >= 3.0) {
+template <class T> XC_HD T wb97_attenuation(const T &a) { // eq. (8) of the paper; its 1/a^2 series for a >= 1, where
+  const T a2 = a * a;                                      // the closed form cancels from O(a^4) terms to 1/(36 a^2)
+  if (val(a) >= 1.0) {
     const T y = 1.0 / a2;
-    T r = y * (-1.0 / 2021444812800.0) + 1.0 / 44590694400.0;
+    T r = y * (1.0 / 99407521382400.0) - 1.0 / 2021444812800.0;
+    r = r * y + 1.0 / 44590694400.0;
     r = r * y - 1.0 / 1073479680.0;
     r = r * y + 1.0 / 28385280.0;
     r = r * y - 1.0 / 829440.0;

@@ -1,0 +1,72 @@
+// xc_handle.h — the handle behind the C ABI (include/occ_xc_b200.h), shared by the host translation units
+// (xc_host.cu: create / build / gradient / VV10;  xc_multi.cu: several handles of one process, one per GPU).
+#pragma once
+#include "../../include/occ_xc_b200.h"
+#include "xc_internal.h"
+#include <cuda_runtime.h>
+#include <vector>
+
+struct Batch {
+  int tile0, ntiles, leaf0, nleaves;
+  size_t colloc_off, ncolloc, dens_off, ndens, g_off, ng, vxc_off, nvxc, grad_off, ngrad;
+  size_t densmo_off, ndensmo, psi_off, npsi, xpsi_off, nxpsi; // MO-form density work lists
+  // MO-form gradient: per A operand wh (0 phi, 1 G, 2..4 phi_e) the psi_A items and the X items; D-form remainder
+  size_t gpsi_off[5], ngpsi[5], gx_off[5], ngx[5], gradd_off, ngradd;
+};
+
+struct occ_xc_handle {
+  int device = 0;
+  int nbf = 0, nsh = 0, nspin = 1, deriv = 0, ncomp = 1, pure = 0;
+  size_t npts = 0;
+  int nleaves = 0, ntiles = 0;
+  double sum_n_nb2 = 0.0;
+  int nb_min = 0, nb_max = 0;
+  std::vector<Batch> batches;
+  std::vector<xcb::TileDesc> h_tiles;
+  std::vector<xcb::LeafDesc> h_leaves;
+  std::vector<size_t> leaf_global; // caller's leaf index of each local leaf
+  std::vector<int> h_bf_index;
+  xcb::BuildParams P;
+  std::vector<void *> allocs;
+  size_t alloc_bytes = 0;
+  xcb::CollocItem *d_colloc = nullptr;
+  xcb::DensItem *d_dens = nullptr, *d_g = nullptr, *d_gradit = nullptr;
+  bool gradient = false;
+  int natoms = 0;
+  double *d_DT = nullptr, *d_grad = nullptr;
+  xcb::VxcItem *d_vxc = nullptr;
+  double *d_D = nullptr, *d_Dsym = nullptr, *d_Ktmp = nullptr, *d_K = nullptr, *d_scalars = nullptr;
+  cudaStream_t stream = nullptr, aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  double *scratch2 = nullptr; // workspace of the second lane
+  int lanes = 1;
+  bool profiling = false;
+  bool deterministic = false, nvtx = false;
+  double density_scale = 1.0, orbital_scale = 1.0;
+  double phase_ms[OCC_XC_NPHASES] = {0, 0, 0, 0, 0, 0, 0};
+  size_t launches = 0;
+  // MO-form density (options.mo_form with the occupied-orbital counts at create)
+  bool mo = false;
+  int nocc[2] = {0, 0}, noccp = 0;
+  xcb::DensItem *d_densmo = nullptr, *d_psi = nullptr, *d_xpsi = nullptr;
+  xcb::DensItem *d_gpsi[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *d_gx[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  xcb::DensItem *d_gradd = nullptr;
+  double *d_C = nullptr, *d_CT = nullptr;
+  double mo_executed_flops = 0.0; // DMMA flops one MO-form build really issues (density side)
+  // post-SCF VV10 (allocated on first use)
+  std::vector<size_t> h_tile_src; // sorted index of the first point of each tile
+  std::vector<long long> h_tile_psi_off;
+  size_t npts_total = 0;          // points of the caller's whole grid (orig_index range)
+  int world = 1;
+  size_t *d_tile_src = nullptr;
+  xcb::VV10Params vv = {};
+  int2 *d_vv_items = nullptr;
+  int n_vv_items = 0;
+  size_t *d_vv_orig = nullptr;
+};
+
+
+// one build on device buffers (xc_host.cu); D2_dev may be NULL when C_dev is given (D2 = C C^T formed on the device)
+int xc_build_device_impl(occ_xc_handle *h, const double *D2_dev, const double *C_dev, double *K_dev, double *scalars_dev,
+                         void *cuda_stream);
+int occ_xc_set_error(const char *msg); // sets the calling thread's occ_xc_last_error() and returns 1

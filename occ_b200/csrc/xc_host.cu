@@ -8,6 +8,7 @@
 #include "../../include/occ_xc_b200.h"
 #include "xc_functionals.cuh"
 #include "xc_internal.h"
+#include "xc_handle.h"
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -182,66 +183,6 @@ static std::vector<size_t> partition_by_cost(const std::vector<double> &costs, i
   return cut;
 }
 
-// ------------------------------------------------------------------------------------------------
-struct Batch {
-  int tile0, ntiles, leaf0, nleaves;
-  size_t colloc_off, ncolloc, dens_off, ndens, g_off, ng, vxc_off, nvxc, grad_off, ngrad;
-  size_t densmo_off, ndensmo, psi_off, npsi, xpsi_off, nxpsi; // MO-form density work lists
-  // MO-form gradient: per A operand wh (0 phi, 1 G, 2..4 phi_e) the psi_A items and the X items; D-form remainder
-  size_t gpsi_off[5], ngpsi[5], gx_off[5], ngx[5], gradd_off, ngradd;
-};
-
-struct occ_xc_handle {
-  int device = 0;
-  int nbf = 0, nsh = 0, nspin = 1, deriv = 0, ncomp = 1, pure = 0;
-  size_t npts = 0;
-  int nleaves = 0, ntiles = 0;
-  double sum_n_nb2 = 0.0;
-  int nb_min = 0, nb_max = 0;
-  std::vector<Batch> batches;
-  std::vector<TileDesc> h_tiles;
-  std::vector<LeafDesc> h_leaves;
-  std::vector<size_t> leaf_global; // caller's leaf index of each local leaf
-  std::vector<int> h_bf_index;
-  BuildParams P;
-  std::vector<void *> allocs;
-  size_t alloc_bytes = 0;
-  CollocItem *d_colloc = nullptr;
-  DensItem *d_dens = nullptr, *d_g = nullptr, *d_gradit = nullptr;
-  bool gradient = false;
-  int natoms = 0;
-  double *d_DT = nullptr, *d_grad = nullptr;
-  VxcItem *d_vxc = nullptr;
-  double *d_D = nullptr, *d_Dsym = nullptr, *d_Ktmp = nullptr, *d_K = nullptr, *d_scalars = nullptr;
-  cudaStream_t stream = nullptr, aux_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  double *scratch2 = nullptr; // workspace of the second lane
-  int lanes = 1;
-  bool profiling = false;
-  bool deterministic = false, nvtx = false;
-  double density_scale = 1.0, orbital_scale = 1.0;
-  double phase_ms[OCC_XC_NPHASES] = {0, 0, 0, 0, 0, 0, 0};
-  size_t launches = 0;
-  // MO-form density (options.mo_form with the occupied-orbital counts at create)
-  bool mo = false;
-  int nocc[2] = {0, 0}, noccp = 0;
-  DensItem *d_densmo = nullptr, *d_psi = nullptr, *d_xpsi = nullptr;
-  DensItem *d_gpsi[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *d_gx[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  DensItem *d_gradd = nullptr;
-  double *d_C = nullptr, *d_CT = nullptr;
-  double mo_executed_flops = 0.0; // DMMA flops one MO-form build really issues (density side)
-  // post-SCF VV10 (allocated on first use)
-  std::vector<size_t> h_tile_src; // sorted index of the first point of each tile
-  std::vector<long long> h_tile_psi_off;
-  size_t npts_total = 0;          // points of the caller's whole grid (orig_index range)
-  int world = 1;
-  size_t *d_tile_src = nullptr;
-  VV10Params vv = {};
-  int2 *d_vv_items = nullptr;
-  int n_vv_items = 0;
-  size_t *d_vv_orig = nullptr;
-};
-
 template <class T> static int dev_alloc(occ_xc_handle *h, T **ptr, size_t count) {
   void *p = nullptr;
   const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
@@ -275,6 +216,13 @@ int occ_xc_range_separation(int id, double *omega, double *alpha, double *beta) 
   if (!omega || !alpha || !beta) return fail("occ_xc_range_separation: null argument");
   if (xc_family_of(id) < 0) return fail("functional with id = " + std::to_string(id) + " not found");
   xc_cam_of(id, omega, alpha, beta);
+  return 0;
+}
+int occ_xc_measure_fp64_tensor_peak(int device, double target_ms, double *tflops, double *measured_ms) {
+  if (!tflops) return fail("occ_xc_measure_fp64_tensor_peak: null argument");
+  if (device >= 0) CUDA_TRY(cudaSetDevice(device));
+  if (measure_dmma_peak(target_ms > 0.0 ? target_ms : 50.0, tflops, measured_ms))
+    return fail(std::string("occ_xc_measure_fp64_tensor_peak: ") + cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
 void occ_xc_options_init(occ_xc_options_t *o) {
@@ -857,24 +805,25 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
   return 0;
 }
 
-static int build_device_impl(occ_xc_handle *h, const double *D2_dev, const double *C_dev, double *K_dev,
-                             double *scalars_dev, void *cuda_stream);
+
 
 int occ_xc_build_device(occ_xc_handle *h, const double *D2_dev, double *K_dev, double *scalars_dev,
                         void *cuda_stream) {
   if (!h || !D2_dev || !K_dev || !scalars_dev) return fail("occ_xc_build_device: null argument");
-  return build_device_impl(h, D2_dev, nullptr, K_dev, scalars_dev, cuda_stream);
+  return xc_build_device_impl(h, D2_dev, nullptr, K_dev, scalars_dev, cuda_stream);
 }
 
 int occ_xc_build_mo_device(occ_xc_handle *h, const double *D2_dev, const double *C_dev, double *K_dev,
                            double *scalars_dev, void *cuda_stream) {
   if (!h || !C_dev || !K_dev || !scalars_dev) return fail("occ_xc_build_mo_device: null argument");
   if (!h->mo) return fail("occ_xc_build_mo_device: the handle was created without occupied-orbital counts");
-  return build_device_impl(h, D2_dev, C_dev, K_dev, scalars_dev, cuda_stream);
+  return xc_build_device_impl(h, D2_dev, C_dev, K_dev, scalars_dev, cuda_stream);
 }
 
-static int build_device_impl(occ_xc_handle *h, const double *D2_dev, const double *C_dev, double *K_dev,
-                             double *scalars_dev, void *cuda_stream) {
+} // extern "C"
+
+int xc_build_device_impl(occ_xc_handle *h, const double *D2_dev, const double *C_dev, double *K_dev, double *scalars_dev,
+                         void *cuda_stream) {
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->stream;
   BuildParams P = h->P;
@@ -983,6 +932,8 @@ static int build_device_impl(occ_xc_handle *h, const double *D2_dev, const doubl
   return 0;
 }
 
+extern "C" {
+
 // host D (and C) -> device copies of the handle, with options.density_scale / orbital_scale applied on the device
 static int upload_inputs(occ_xc_handle *h, const double *D2, const double *C, const double **D_dev, const double **C_dev) {
   const size_t ksz = static_cast<size_t>(h->nspin) * h->nbf * h->nbf;
@@ -1018,7 +969,7 @@ int occ_xc_build(occ_xc_handle *h, const double *D2, double *K, double *exc, dou
   CUDA_TRY(cudaSetDevice(h->device));
   const double *Dd, *Cd;
   if (upload_inputs(h, D2, nullptr, &Dd, &Cd)) return 1;
-  if (build_device_impl(h, Dd, nullptr, h->d_K, h->d_scalars, h->stream)) return 1;
+  if (xc_build_device_impl(h, Dd, nullptr, h->d_K, h->d_scalars, h->stream)) return 1;
   return download_outputs(h, K, exc, n_alpha, n_beta);
 }
 
@@ -1141,7 +1092,7 @@ int occ_xc_build_mo(occ_xc_handle *h, const double *D2, const double *C, double 
   CUDA_TRY(cudaSetDevice(h->device));
   const double *Dd, *Cd;
   if (upload_inputs(h, D2, C, &Dd, &Cd)) return 1; // D2 == NULL: formed on the device as C C^T
-  if (build_device_impl(h, Dd, Cd, h->d_K, h->d_scalars, h->stream)) return 1;
+  if (xc_build_device_impl(h, Dd, Cd, h->d_K, h->d_scalars, h->stream)) return 1;
   return download_outputs(h, K, exc, n_alpha, n_beta);
 }
 

@@ -147,6 +147,7 @@ void launch_dgemm(bool b_transposed, int M, int N, int K, double alpha, const do
                   void *stream);
 void launch_scale(const double *in, double *out, size_t n, double s, void *stream);
 void launch_add_inplace(double *a, const double *b, size_t n, void *stream);
+int measure_dmma_peak(double target_ms, double *tflops, double *measured_ms);
 void launch_gbuild(const BuildParams &P, const DensItem *items, int nitems, void *stream);
 void launch_collocate_h(const BuildParams &P, const CollocItem *items, int nitems, void *stream);
 void launch_mo_psi(const BuildParams &P, const DensItem *items, int nitems, void *stream);

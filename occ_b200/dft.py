@@ -186,8 +186,15 @@ class DFT:
         return K
 
     def build_mo_device(self, d2_dev_ptr: int, c_dev_ptr: int, k_dev_ptr: int, scalars_dev_ptr: int, stream: int = 0):
-        check(lib().occ_xc_build_mo_device(self._h, C_.c_void_p(d2_dev_ptr), C_.c_void_p(c_dev_ptr),
+        check(lib().occ_xc_build_mo_device(self._h, C_.c_void_p(d2_dev_ptr or None), C_.c_void_p(c_dev_ptr),
                                            C_.c_void_p(k_dev_ptr), C_.c_void_p(scalars_dev_ptr), C_.c_void_p(stream)))
+
+    def build_mo_raw(self, d2_ptr: int, c_ptr: int, k_ptr: int):
+        """occ_xc_build_mo on raw host pointers (d2_ptr = 0: D2 formed on the device); returns (exc, n_alpha, n_beta)"""
+        exc, na, nb = C_.c_double(), C_.c_double(), C_.c_double()
+        check(lib().occ_xc_build_mo(self._h, C_.c_void_p(d2_ptr or None), C_.c_void_p(c_ptr), C_.c_void_p(k_ptr),
+                                    C_.byref(exc), C_.byref(na), C_.byref(nb)))
+        return exc.value, na.value, nb.value
 
     def build_raw(self, d2_ptr: int, k_ptr: int):
         """occ_xc_build on raw host pointers (pinned buffers owned by the caller); returns (exc, n_alpha, n_beta)."""
@@ -247,6 +254,93 @@ class DFT:
         if getattr(self, "_h", None) is not None and self._h.value:
             lib().occ_xc_destroy(self._h)
             self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiGPUDFT:
+    """occ_xc_multi_*: the same build on several GPUs driven from THIS process (what the reference's single-process
+    SCF needs, include/occ/qm/scf_impl.h:539): one leaf shard per device, inputs sliced over the PCIe links and
+    gathered over NVLink, K reduce-scattered through peer memory.  Same constructor arguments as DFT plus `devices`
+    (list of CUDA ordinals; an ordinal may repeat)."""
+
+    def __init__(self, method: str, basis: AOBasis, grid: GridHierarchy, spinorbital_kind: str = RESTRICTED,
+                 devices=(0,), batch_bytes: int = 0, density_threshold: float = 1e-10,
+                 xc_screening_threshold: float = 1e-10, nocc=None, deterministic: bool = False,
+                 density_scale: float = 0.0, orbital_scale: float = 0.0):
+        self.basis, self.method = basis, method
+        self.func_ids = np.array(get_dft_method(method), dtype=np.int32)
+        self.nspin = 2 if spinorbital_kind == UNRESTRICTED else 1
+        self.nbf = basis.nbf
+        self._basis_arrays = BasisArrays(basis.as_arrays())
+        pts = np.ascontiguousarray(grid.sorted_points, dtype=np.float64).reshape(-1, 3)
+        w = np.ascontiguousarray(grid.sorted_weights, dtype=np.float64)
+        leaves = np.ascontiguousarray(grid.leaves, dtype=LEAF_DTYPE)
+        opt = OptionsT()
+        lib().occ_xc_options_init(C.byref(opt))
+        opt.batch_bytes, opt.deterministic = batch_bytes, int(deterministic)
+        opt.density_scale, opt.orbital_scale = density_scale, orbital_scale
+        self.nocc = None
+        if nocc is not None:
+            na, nb_ = (nocc, nocc) if np.isscalar(nocc) else (nocc[0], nocc[-1])
+            opt.mo_form, opt.nocc_alpha, opt.nocc_beta = 1, int(na), int(nb_)
+            self.nocc = (int(na), int(nb_) if self.nspin == 2 else 0)
+        dev = np.array(list(devices), dtype=np.int32)
+        self.devices = [int(x) for x in dev]
+        self._m = C.c_void_p()
+        check(lib().occ_xc_multi_create(self._basis_arrays.ref, C.c_size_t(len(w)), ptr(pts), ptr(w),
+                                        C.c_size_t(len(leaves)), ptr(leaves), None, C.c_int(len(self.func_ids)),
+                                        ptr(self.func_ids), C.c_int(self.nspin), C.c_double(density_threshold),
+                                        C.c_double(xc_screening_threshold), C.byref(opt), C.c_int(len(dev)), ptr(dev),
+                                        C.byref(self._m)))
+        self.m_exc_dft = 0.0
+        self.total_density = (0.0, 0.0)
+
+    def info(self, rank: int) -> dict:
+        i = InfoT()
+        check(lib().occ_xc_multi_get_info(self._m, C.c_int(rank), C.byref(i)))
+        return {f: getattr(i, f) for f, _ in InfoT._fields_}
+
+    def exchange_correlation_energy(self) -> float:
+        return self.m_exc_dft
+
+    def build(self, D2, Cs=None, out: np.ndarray | None = None) -> np.ndarray:
+        """occ_xc_multi_build: D2 (or None when Cs is given) and optionally the orbitals as in DFT.build_mo"""
+        n = self.nspin * self.nbf
+        if D2 is not None:
+            D2 = np.asfortranarray(D2, dtype=np.float64)
+            if D2.shape != (n, self.nbf):
+                raise RuntimeError(f"density matrix has shape {D2.shape}, expected {(n, self.nbf)}")
+        packed = None
+        if Cs is not None:
+            Cs = [Cs] if isinstance(Cs, np.ndarray) else list(Cs)
+            if self.nocc is None or any(c.shape != (self.nbf, self.nocc[s]) for s, c in enumerate(Cs)):
+                raise RuntimeError("orbital coefficients do not match (nbf, nocc) of the handles")
+            packed = np.concatenate([np.asfortranarray(c, dtype=np.float64).ravel(order="F") for c in Cs])
+        K = out if out is not None else np.zeros((n, self.nbf), order="F")
+        exc, na, nb = C.c_double(), C.c_double(), C.c_double()
+        check(lib().occ_xc_multi_build(self._m, ptr(D2) if D2 is not None else None,
+                                       ptr(packed) if packed is not None else None, ptr(K), C.byref(exc), C.byref(na),
+                                       C.byref(nb)))
+        self.m_exc_dft = exc.value
+        self.total_density = (na.value, nb.value)
+        return K
+
+    def build_raw(self, d2_ptr: int, c_ptr: int, k_ptr: int):
+        """occ_xc_multi_build on raw host pointers (pinned buffers owned by the caller; 0 = NULL)"""
+        exc, na, nb = C.c_double(), C.c_double(), C.c_double()
+        check(lib().occ_xc_multi_build(self._m, C.c_void_p(d2_ptr or None), C.c_void_p(c_ptr or None), C.c_void_p(k_ptr),
+                                       C.byref(exc), C.byref(na), C.byref(nb)))
+        return exc.value, na.value, nb.value
+
+    def close(self):
+        if getattr(self, "_m", None) is not None and self._m.value:
+            lib().occ_xc_multi_destroy(self._m)
+            self._m = C.c_void_p()
 
     def __del__(self):
         try:

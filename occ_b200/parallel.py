@@ -138,19 +138,19 @@ class DistributedDFT:
             self.d_red = torch.zeros(self._slice * self.world, dtype=torch.float64, device=dev)
             self.d_slice = torch.zeros(self._slice, dtype=torch.float64, device=dev)
 
-    def _launch(self, out: torch.Tensor, mo: bool):
+    def _launch(self, out: torch.Tensor, mo: bool, d2_resident: bool = True):
         n = self.nspin * self.nbf * self.nbf
-        if mo:
-            self.dft.build_mo_device(self.d_D.data_ptr(), self.d_C.data_ptr(), out.data_ptr(), out.data_ptr() + 8 * n,
-                                     self.stream.cuda_stream)
+        if mo:   # d2_resident False: the library forms D2 = C C^T itself (only the orbitals were uploaded)
+            self.dft.build_mo_device(self.d_D.data_ptr() if d2_resident else 0, self.d_C.data_ptr(), out.data_ptr(),
+                                     out.data_ptr() + 8 * n, self.stream.cuda_stream)
         else:
             self.dft.build_device(self.d_D.data_ptr(), out.data_ptr(), out.data_ptr() + 8 * n, self.stream.cuda_stream)
 
-    def build_device(self, mo: bool = False) -> torch.Tensor:
+    def build_device(self, mo: bool = False, d2_resident: bool = True) -> torch.Tensor:
         """D already in self.d_D (and, with mo=True, the orbitals in self.d_C), column-major. Enqueues build +
         all-reduce on self.stream; returns the packed device buffer [K | exc, n_alpha, n_beta] (valid once self.stream
         has been synchronised / waited on)."""
-        self._launch(self.d_out, mo)
+        self._launch(self.d_out, mo, d2_resident)
         if self.world > 1:
             with torch.cuda.stream(self.stream):
                 allreduce_partial(self.d_out, self.group)
@@ -159,20 +159,20 @@ class DistributedDFT:
     def build(self, D2_host: torch.Tensor | None, K_host: torch.Tensor | None, C_host: torch.Tensor | None = None,
               mo: bool = False):
         """Host-to-host build as the reference's single-process SCF driver would see it: rank 0 owns the host
-        matrices (pinned CPU tensors, column-major).  Rank 0 copies D to its GPU, D is broadcast to the other GPUs over
-        NVLink (NCCL), every rank builds its shard, the packed result is all-reduced and rank 0 copies K back.
+        matrices (pinned CPU tensors, column-major).  Rank 0 copies the inputs to its GPU — with mo=True ONLY the
+        occupied orbitals, D2 = C C^T is formed on each device — they are broadcast to the other GPUs over NVLink (NCCL),
+        every rank builds its shard, the packed result is all-reduced and rank 0 copies K back.
         Other ranks pass None (or buffers that are ignored). Returns (exc, n_alpha, n_beta) on every rank."""
         n = self.nspin * self.nbf * self.nbf
         with torch.cuda.stream(self.stream):
             if self.rank == 0:
-                self.d_D.copy_(D2_host.view(-1), non_blocking=True)
                 if mo:
                     self.d_C.copy_(C_host.view(-1), non_blocking=True)
+                else:
+                    self.d_D.copy_(D2_host.view(-1), non_blocking=True)
             if self.world > 1:
-                dist.broadcast(self.d_D, src=0, group=self.group)
-                if mo:
-                    dist.broadcast(self.d_C, src=0, group=self.group)
-            out = self.build_device(mo)
+                dist.broadcast(self.d_C if mo else self.d_D, src=0, group=self.group)
+            out = self.build_device(mo, d2_resident=False)
             if self.rank == 0 and K_host is not None:
                 K_host.view(-1)[:n].copy_(out[:n], non_blocking=True)
             self._sc_host.copy_(out[n:n + 3], non_blocking=True)
@@ -188,7 +188,7 @@ class DistributedDFT:
 
     def build_shared(self, mo: bool = False):
         """Host-to-host build for N > 1 with the host matrices in node-shared pinned memory (self.host_D / self.host_K,
-        column-major, owned by rank 0's caller — the SCF process).  Every rank: H2D of D over its own PCIe link ->
+        column-major, owned by rank 0's caller — the SCF process).  Every rank: H2D of D (mo: of C_occ only) over its own PCIe link ->
         sharded build -> NCCL reduce-scatter of the packed [K | exc, n_alpha, n_beta] -> D2H of its 1/N slice into
         host_K.  Rank 0 publishes "D is ready" and collects "slice written" through control words in the same shared
         segment (no collective on the host path).  Returns (exc, n_alpha, n_beta) on every rank."""
@@ -200,10 +200,11 @@ class DistributedDFT:
         else:
             self._spin_until(0, ep)
         with torch.cuda.stream(self.stream):
-            self.d_D.copy_(self.host_D.tensor, non_blocking=True)
-            if mo:
+            if mo:   # only the orbitals cross PCIe; D2 = C C^T is formed on the device
                 self.d_C.copy_(self.host_C.tensor, non_blocking=True)
-            self._launch(self.d_red, mo)
+            else:
+                self.d_D.copy_(self.host_D.tensor, non_blocking=True)
+            self._launch(self.d_red, mo, d2_resident=False)
             dist.reduce_scatter_tensor(self.d_slice, self.d_red, op=dist.ReduceOp.SUM, group=self.group)
             lo = self.rank * self._slice
             self.host_K.tensor[lo:lo + self._slice].copy_(self.d_slice, non_blocking=True)

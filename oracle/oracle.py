@@ -59,7 +59,8 @@ class LeafT(C.Structure):
 class StatsT(C.Structure):
     _fields_ = [("sum_n_nb2", C.c_double), ("sum_nb2", C.c_double), ("nleaves", C.c_size_t), ("nskipped", C.c_size_t),
                 ("nb_min", C.c_int), ("nb_max", C.c_int), ("t_colloc", C.c_double), ("t_density", C.c_double),
-                ("t_func", C.c_double), ("t_vxc", C.c_double), ("t_total", C.c_double)]
+                ("t_func", C.c_double), ("t_vxc", C.c_double), ("t_total", C.c_double), ("t_leaf_loop", C.c_double),
+                ("t_fixed", C.c_double)]
 
 
 LEAF_DTYPE = np.dtype([("offset", np.uint64), ("count", np.uint64), ("center", np.float64, 3), ("radius", np.float64)])

@@ -420,14 +420,22 @@ int orc_xc_build(const orc_basis_t *basis, size_t npts, const double *spts, cons
   for (int l = 0; l <= ORC_MAX_L && l <= 8; ++l)
     if (basis->pure) c2s_matrix(l); // build tables before the parallel region
   std::vector<Workspace> wss(nthreads);
+  // timing split for the CPU baseline: the leaf loop scales with the leaves handed in, the rest (extents, the
+  // per-thread full-size K copies of dft.h:221-232 and their serial reduction, dft.h:375-380) is a fixed cost per build
+  double t_loop0 = 0.0, t_loop1 = 0.0;
 #pragma omp parallel num_threads(nthreads)
   {
     Workspace &ws = wss[omp_get_thread_num()];
     ws.K.assign(ksz, 0.0);
+#pragma omp barrier
+#pragma omp master
+    t_loop0 = omp_get_wtime();
 #pragma omp for schedule(dynamic, 1)
     for (long li = 0; li < static_cast<long>(nleaves); ++li)
       process_leaf(B, extents.data(), spts, sw, leaves[li], nfunc, func_ids, nspin, deriv, density_threshold, screen,
                    D2, ws);
+#pragma omp master
+    t_loop1 = omp_get_wtime();
   }
   // dft.h:375-380 serial reduction over thread copies
   std::memset(K, 0, sizeof(double) * ksz);
@@ -452,6 +460,8 @@ int orc_xc_build(const orc_basis_t *basis, size_t npts, const double *spts, cons
   }
   st.nleaves = nleaves;
   st.t_total = omp_get_wtime() - tstart;
+  st.t_leaf_loop = t_loop1 - t_loop0;
+  st.t_fixed = st.t_total - st.t_leaf_loop;
   *exc = e;
   *n_alpha = na;
   *n_beta = nb;

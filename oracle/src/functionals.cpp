@@ -178,14 +178,25 @@ template <class T> T deps_pw_drs(const T &rs, const T &z) {
   const T fz = f_zeta(z), z4 = sq(sq(z));
   return e0 - mac * fz * (1.0 - z4) / kFpp0 + (e1 - e0) * fz * z4;
 }
-template <class T> T phi_zeta(const T &z) { return 0.5 * (cbrt(sq(1.0 + z)) + cbrt(sq(1.0 - z))); }
+// 1 +- zeta as 2 rho_s / rho (not 1 +- (ra - rb) / rho): keeps the relative accuracy of a spin density at its floor,
+// which matters where derivatives behave like (1 - zeta)^(-1/3)
+template <class T> void zeta_plus_minus(const Vars<T> &v, T &zp, T &zm) {
+  const T rho = v.ra + v.rb;
+  zp = 2.0 * v.ra / rho;
+  zm = 2.0 * v.rb / rho;
+}
+template <class T> T phi_zeta(const Vars<T> &v) {
+  T zp, zm;
+  zeta_plus_minus(v, zp, zm);
+  return 0.5 * (cbrt(sq(zp)) + cbrt(sq(zm)));
+}
 
 template <class T> T F_pbe_c(const Vars<T> &v) {
   const double beta = 0.06672455060314922, gamma = (1.0 - std::log(2.0)) / (kPi * kPi);
   T rho, rs, z;
   rs_zeta(v, rho, rs, z);
   const T ec = eps_pw(rs, z);
-  const T phi = phi_zeta(z);
+  const T phi = phi_zeta(v);
   const T phi3 = phi * sq(phi);
   const T stot = v.saa + 2.0 * v.sab + v.sbb;
   // t^2 = sigma / (4 phi^2 ks^2 rho^2), ks^2 = 4 kF / pi, kF = (3 pi^2 rho)^(1/3)
@@ -249,10 +260,11 @@ template <class T> T F_r2scan_c(const Vars<T> &v) {
   const T stot = v.saa + 2.0 * v.sab + v.sbb;
   const T tau = v.ta + v.tb;
   const T p = s2_of(rho, stot);
-  const T zp = 1.0 + z, zm = 1.0 - z;
+  T zp, zm;
+  zeta_plus_minus(v, zp, zm);
   const T ds = 0.5 * (zp * cbrt(sq(zp)) + zm * cbrt(sq(zm)));   // ((1+z)^(5/3) + (1-z)^(5/3))/2
   const T dxz = 0.5 * (zp * cbrt(zp) + zm * cbrt(zm));           // ((1+z)^(4/3) + (1-z)^(4/3))/2
-  const T phi = phi_zeta(z);
+  const T phi = phi_zeta(v);
   const T phi3 = phi * sq(phi);
   // iso-orbital indicator of the total density
   const T tauW = stot / (8.0 * rho);
@@ -353,7 +365,8 @@ template <class T> T F_tpss_c(const Vars<T> &v) {
   const T C0 = 0.53 + 0.87 * zeta2 + 0.50 * sq(zeta2) + 2.26 * zeta2 * sq(zeta2);
   const T gz2 = 4.0 * (sq(v.rb) * v.saa - 2.0 * v.ra * v.rb * v.sab + sq(v.ra) * v.sbb) / sq(sq(rho));
   const T xi2 = gz2 / (4.0 * cbrt(sq(3.0 * kPi * kPi * rho)));
-  const T zp = 1.0 + zeta, zm = 1.0 - zeta;
+  T zp, zm;
+  zeta_plus_minus(v, zp, zm);
   const T inv43 = 0.5 * (1.0 / (zp * cbrt(zp)) + 1.0 / (zm * cbrt(zm)));
   const T C = C0 / sq(sq(1.0 + xi2 * inv43));
   const T e_pbe = F_pbe_c(v) / rho;
@@ -393,10 +406,11 @@ template <class T> T F_bhandhlyp(const Vars<T> &v) { return 0.5 * F_b88(v) + F_l
 // (DFT::compute_JK -> range-separated K); xc_hyb_cam_coef: omega 0.3, alpha 1.0, beta -0.842294.
 // Pinned by the reference's own isolated-XC golden -6.577307030585 (tests/isolated_xc_tests.cpp:296-319).
 template <class T> T sr_attenuation(const T &a) {
-  if (value(a) >= 3.0) { // asymptotic series (the closed form cancels to 1/(36 a^2) from O(1) terms)
+  if (value(a) >= 1.0) { // asymptotic series (the closed form cancels to 1/(36 a^2) from O(a^4) terms)
     const T i2 = 1.0 / sq(a);
     return i2 * (1.0 / 36.0 + i2 * (-1.0 / 960.0 + i2 * (1.0 / 26880.0 + i2 * (-1.0 / 829440.0 + i2 * (1.0 / 28385280.0 +
-           i2 * (-1.0 / 1073479680.0 + i2 * (1.0 / 44590694400.0 + i2 * (-1.0 / 2021444812800.0))))))));
+           i2 * (-1.0 / 1073479680.0 + i2 * (1.0 / 44590694400.0 + i2 * (-1.0 / 2021444812800.0 +
+           i2 * (1.0 / 99407521382400.0)))))))));
   }
   const T b = expm1(-0.25 / sq(a));
   const T c = 2.0 * sq(a) * b + 0.5;

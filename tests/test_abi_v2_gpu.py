@@ -1,0 +1,169 @@
+"""ABI version 2 features of the XC build, on the GPU through the C ABI: the deterministic (order-independent)
+accumulation mode, D2 formed on the device from the orbitals, one-electron unrestricted systems (nocc_beta = 0), the
+on-device density / orbital scales the C++ adapter relies on, wB97X, NVTX switch.  Tolerances: the north-star 1e-9
+(Vxc max-abs) / 1e-8 (Exc) unless a tighter one is stated."""
+import numpy as np
+import pytest
+
+from occ_b200 import aobasis, dft, molecules
+
+pytestmark = pytest.mark.gpu
+
+
+def _names(method, O):
+    return [n for i in dft.get_dft_method(method) for n, v in O.FUNC_IDS.items() if v == i]
+
+
+def _hier(c):
+    return dft.GridHierarchy(c["spts"], c["sw"], c["leaves"])
+
+
+@pytest.mark.parametrize("mol,bas,method,nspin", [("water", "def2-svp", "b3lyp", 1), ("benzene", "def2-tzvp", "pbe", 2),
+                                                   ("water", "def2-svp", "r2scan", 2)])
+def test_deterministic_mode_is_bit_repeatable_and_matches_the_oracle(case, oracle, mol, bas, method, nspin):
+    c = case(mol, bas)
+    b = c["basis"]
+    kind = dft.UNRESTRICTED if nspin == 2 else dft.RESTRICTED
+    D2 = molecules.synthetic_density(b, nspin)
+    Cs = molecules.synthetic_orbitals(b, nspin)
+    ref = oracle.xc_build(c["obasis"], c["spts"], c["sw"], c["leaves"], _names(method, oracle), nspin, D2)
+    d = dft.DFT(method, b, _hier(c), kind, deterministic=True, nocc=[x.shape[1] for x in Cs])
+    runs = [(d.build(D2).copy(), d.exchange_correlation_energy(), d.total_density) for _ in range(3)]
+    runs_mo = [(d.build_mo(D2, Cs).copy(), d.exchange_correlation_energy(), d.total_density) for _ in range(3)]
+    d.close()
+    for rr in (runs, runs_mo):
+        for K, exc, n in rr[1:]:
+            assert np.array_equal(K, rr[0][0]) and exc == rr[0][1] and n == rr[0][2]      # bit for bit
+        assert np.abs(rr[0][0] - ref["K"]).max() < 1e-9 and abs(rr[0][1] - ref["exc"]) < 1e-8
+    # a second handle (different allocation, same work) gives the same bits as well
+    d2 = dft.DFT(method, b, _hier(c), kind, deterministic=True)
+    assert np.array_equal(d2.build(D2), runs[0][0])
+    d2.close()
+    # and the default (arrival-order) mode agrees to rounding
+    d3 = dft.DFT(method, b, _hier(c), kind)
+    assert np.abs(d3.build(D2) - runs[0][0]).max() < 1e-12
+    d3.close()
+
+
+@pytest.mark.parametrize("mol,bas,method,nspin", [("water", "def2-svp", "b3lyp", 1), ("benzene", "def2-tzvp", "r2scan", 2)])
+def test_density_matrix_formed_on_the_device_from_the_orbitals(case, oracle, mol, bas, method, nspin):
+    c = case(mol, bas)
+    b = c["basis"]
+    kind = dft.UNRESTRICTED if nspin == 2 else dft.RESTRICTED
+    Cs = molecules.synthetic_orbitals(b, nspin)
+    D2 = np.asfortranarray(np.vstack([x @ x.T for x in Cs]))
+    ref = oracle.xc_build(c["obasis"], c["spts"], c["sw"], c["leaves"], _names(method, oracle), nspin, D2)
+    d = dft.DFT(method, b, _hier(c), kind, nocc=[x.shape[1] for x in Cs])
+    K = d.build_mo(None, Cs)                        # occ_xc_build_mo(D2 = NULL)
+    assert np.abs(K - ref["K"]).max() < 1e-9 and abs(d.exchange_correlation_energy() - ref["exc"]) < 1e-8
+    K2 = d.build_mo(D2, Cs)
+    assert np.abs(K - K2).max() < 1e-12
+    d.close()
+
+
+@pytest.mark.parametrize("method", ["svwn", "pbe", "r2scan"])
+def test_unrestricted_one_electron_system_with_no_beta_electron(oracle, method):
+    """UKS hydrogen atom: nocc = (1, 0).  ABI version 1 read a zero beta count as "same as alpha" (ADVICE round 1)."""
+    Z, pos = np.array([1]), np.array([[0.0, 0.0, 0.0]])
+    b = aobasis.AOBasis.load(Z, pos, "def2-svp")
+    ob = oracle.Basis(b.as_arrays())
+    pts, w, _ = oracle.molecular_grid(Z, pos, ob)
+    spts, sw, perm, leaves = oracle.hierarchy(pts, w)
+    rng = np.random.default_rng(1)
+    ca = np.asfortranarray(rng.normal(size=(b.nbf, 1)) * 0.3)
+    ca[0, 0] = 1.0
+    D2 = np.asfortranarray(np.vstack([ca @ ca.T, np.zeros((b.nbf, b.nbf))]))
+    ref = oracle.xc_build(ob, spts, sw, leaves, _names(method, oracle), 2, D2)
+    d = dft.DFT(method, b, dft.GridHierarchy(spts, sw, leaves), dft.UNRESTRICTED, nocc=(1, 0))
+    assert d.nocc == (1, 0)
+    for K in (d.build(D2), d.build_mo(D2, [ca, np.zeros((b.nbf, 0))]), d.build_mo(None, [ca, np.zeros((b.nbf, 0))])):
+        assert np.abs(K - ref["K"]).max() < 1e-9
+        assert abs(d.exchange_correlation_energy() - ref["exc"]) < 1e-8
+        assert abs(d.total_density[0] - ref["n_alpha"]) < 1e-9 and abs(d.total_density[1]) < 1e-12
+    d.close()
+    with pytest.raises(RuntimeError):                                   # no electron at all is refused
+        dft.DFT(method, b, dft.GridHierarchy(spts, sw, leaves), dft.UNRESTRICTED, nocc=(0, 0))
+
+
+def test_device_side_scales_take_the_reference_conventions(case, oracle):
+    """density_scale = 2 / orbital_scale = sqrt(2): the caller passes mo.D and mo.Cocc as the reference stores them"""
+    c = case("water", "def2-svp")
+    b = c["basis"]
+    Cs = molecules.synthetic_orbitals(b, 1)
+    D2 = np.asfortranarray(Cs[0] @ Cs[0].T)
+    ref = oracle.xc_build(c["obasis"], c["spts"], c["sw"], c["leaves"], _names("b3lyp", oracle), 1, D2)
+    d = dft.DFT("b3lyp", b, _hier(c), nocc=Cs[0].shape[1], density_scale=2.0, orbital_scale=np.sqrt(2.0))
+    moD, Cocc = 0.5 * D2, Cs[0] / np.sqrt(2.0)
+    for K in (d.build(moD), d.build_mo(moD, [Cocc]), d.build_mo(None, [Cocc])):
+        assert np.abs(K - ref["K"]).max() < 1e-9 and abs(d.exchange_correlation_energy() - ref["exc"]) < 1e-8
+    d.close()
+
+
+@pytest.mark.parametrize("nspin", [1, 2])
+def test_wb97x_build_and_range_separation(case, oracle, nspin):
+    c = case("water", "def2-svp")
+    b = c["basis"]
+    D2 = molecules.synthetic_density(b, nspin)
+    ref = oracle.xc_build(c["obasis"], c["spts"], c["sw"], c["leaves"], ["hyb_gga_xc_wb97x"], nspin, D2)
+    d = dft.DFT("wb97x", b, _hier(c), dft.UNRESTRICTED if nspin == 2 else dft.RESTRICTED, nvtx=True)
+    K = d.build(D2)
+    assert np.abs(K - ref["K"]).max() < 1e-9 and abs(d.exchange_correlation_energy() - ref["exc"]) < 1e-8
+    rs = d.range_separated_parameters()          # xc_hyb_cam_coef of libxc's hyb_gga_xc_wb97x
+    assert rs == {"omega": 0.3, "alpha": 1.0, "beta": -(1.0 - 0.157706)}
+    assert d.exact_exchange_factor() == 1.0 and d.density_derivative() == 1
+    d.close()
+
+
+def test_options_struct_of_another_abi_version_is_refused(case):
+    import ctypes as C
+    from occ_b200 import _lib
+    c = case("water", "def2-svp")
+    b = c["basis"]
+    ba = _lib.BasisArrays(b.as_arrays())
+    opt = _lib.OptionsT()
+    _lib.lib().occ_xc_options_init(C.byref(opt))
+    opt.reserved[2] = 1                          # what a version-1 caller would have written for "gradient"
+    ids = np.array([1], dtype=np.int32)
+    leaves = np.ascontiguousarray(c["leaves"], dtype=_lib.LEAF_DTYPE)
+    h = C.c_void_p()
+    rc = _lib.lib().occ_xc_create(ba.ref, C.c_size_t(len(c["sw"])), _lib.ptr(c["spts"]), _lib.ptr(c["sw"]),
+                                  C.c_size_t(len(leaves)), _lib.ptr(leaves), None, C.c_int(1), _lib.ptr(ids), C.c_int(1),
+                                  C.c_double(1e-10), C.c_double(1e-10), C.byref(opt), C.byref(h))
+    assert rc != 0 and b"reserved" in _lib.lib().occ_xc_last_error()
+
+
+def _ndev():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("devices", [(0, 0), (0, 0, 0), (0, 1), (0, 1, 2, 3), (0, 1, 2, 3, 4, 5, 6, 7)])
+@pytest.mark.parametrize("mol,bas,method,nspin", [("benzene", "def2-tzvp", "b3lyp", 1), ("water", "def2-svp", "r2scan", 2)])
+def test_single_process_multi_gpu_build_sums_to_the_one_gpu_result(case, oracle, devices, mol, bas, method, nspin):
+    """occ_xc_multi_*: N leaf shards driven from one process; K matches the 1-GPU build to 1e-12 and the oracle to 1e-9.
+    (0, 0) / (0, 0, 0) run the whole multi-handle path — slicing, peer gather, panel reduction — on one GPU."""
+    if max(devices) >= _ndev():
+        pytest.skip(f"needs {max(devices) + 1} GPUs")
+    c = case(mol, bas)
+    b = c["basis"]
+    kind = dft.UNRESTRICTED if nspin == 2 else dft.RESTRICTED
+    Cs = molecules.synthetic_orbitals(b, nspin)
+    D2 = np.asfortranarray(np.vstack([x @ x.T for x in Cs]))
+    nocc = [x.shape[1] for x in Cs]
+    ref = oracle.xc_build(c["obasis"], c["spts"], c["sw"], c["leaves"], _names(method, oracle), nspin, D2)
+    one = dft.DFT(method, b, _hier(c), kind, nocc=nocc)
+    K1 = one.build(D2).copy()
+    e1 = one.exchange_correlation_energy()
+    one.close()
+    m = dft.MultiGPUDFT(method, b, _hier(c), kind, devices=devices, nocc=nocc)
+    assert sum(m.info(r)["npts"] for r in range(len(devices))) == len(c["sw"])     # every leaf on exactly one shard
+    for K in (m.build(D2), m.build(D2, Cs), m.build(None, Cs), m.build(D2)):
+        assert np.abs(K - K1).max() < 1e-12 and abs(m.exchange_correlation_energy() - e1) < 1e-11
+        assert np.abs(K - ref["K"]).max() < 1e-9 and abs(m.exchange_correlation_energy() - ref["exc"]) < 1e-8
+        assert abs(m.total_density[0] - ref["n_alpha"]) < 1e-9
+    m.close()
+    # deterministic mode: bit-repeatable across builds (fixed-order panel reduction over the ranks)
+    md = dft.MultiGPUDFT(method, b, _hier(c), kind, devices=devices, deterministic=True)
+    Ka = md.build(D2).copy()
+    assert np.array_equal(md.build(D2), Ka) and np.abs(Ka - K1).max() < 1e-12
+    md.close()
