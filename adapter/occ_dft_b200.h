@@ -70,7 +70,8 @@ public:
   XCBuild(const BasisArrays &basis, size_t npts, const double *sorted_points, const double *sorted_weights,
           const std::vector<occ_xc_leaf_t> &leaves, const std::vector<int> &func_ids, SpinorbitalKind kind,
           double density_threshold = 1e-10, double xc_screening_threshold = 1e-10, int device = -1, int rank = 0,
-          int world_size = 1, int nocc_alpha = -1, int nocc_beta = -1, bool deterministic = false)
+          int world_size = 1, int nocc_alpha = -1, int nocc_beta = -1, bool deterministic = false,
+          const std::vector<int> &devices = {})
       : m_nspin(static_cast<int>(kind)), m_nbf(basis.nbf()) {
     occ_xc_options_t opt;
     occ_xc_options_init(&opt);
@@ -90,14 +91,22 @@ public:
       m_nocc[1] = opt.nocc_beta;
     }
     const occ_xc_basis_t b = basis.view();
-    check(occ_xc_create(&b, npts, sorted_points, sorted_weights, leaves.size(), leaves.data(), nullptr,
-                        static_cast<int>(func_ids.size()), func_ids.data(), m_nspin, density_threshold,
-                        xc_screening_threshold, &opt, &m_handle));
+    // `devices` non-empty: one leaf shard per listed GPU, all driven from this process (occ_xc_multi_*) — the drop-in
+    // for the reference's tbb::parallel_for over leaves + serial reduction of thread copies (dft.h:303-371,375-380)
+    if (!devices.empty())
+      check(occ_xc_multi_create(&b, npts, sorted_points, sorted_weights, leaves.size(), leaves.data(), nullptr,
+                                static_cast<int>(func_ids.size()), func_ids.data(), m_nspin, density_threshold,
+                                xc_screening_threshold, &opt, static_cast<int>(devices.size()), devices.data(), &m_multi));
+    else
+      check(occ_xc_create(&b, npts, sorted_points, sorted_weights, leaves.size(), leaves.data(), nullptr,
+                          static_cast<int>(func_ids.size()), func_ids.data(), m_nspin, density_threshold,
+                          xc_screening_threshold, &opt, &m_handle));
   }
   ~XCBuild() {
     for (void *p : m_registered) occ_xc_host_unregister(p);
     occ_xc_pinned_free(m_K);
     occ_xc_destroy(m_handle);
+    occ_xc_multi_destroy(m_multi);
   }
   XCBuild(const XCBuild &) = delete;
   XCBuild &operator=(const XCBuild &) = delete;
@@ -112,7 +121,8 @@ public:
   // D = mo.D ((nspin*nbf) x nbf column-major), exactly as the reference stores it. Writes K (same shape).
   // No host-side pass over D: the factor 2 of dft.h:205 is applied on the device (options.density_scale).
   void compute_K_dft(const double *D, double *K) {
-    check(occ_xc_build(m_handle, D, K, &m_exc_dft, &m_total_density_a, &m_total_density_b));
+    if (m_multi) check(occ_xc_multi_build(m_multi, D, nullptr, K, &m_exc_dft, &m_total_density_a, &m_total_density_b));
+    else check(occ_xc_build(m_handle, D, K, &m_exc_dft, &m_total_density_a, &m_total_density_b));
   }
   // Same, but K stays in a page-locked buffer owned by this object (valid until the next call): the caller maps it
   // (Eigen::Map<const Mat>(ptr, nspin * nbf, nbf)) — the reference negates / copies K anyway (dft.h:435).
@@ -127,7 +137,8 @@ public:
   // but 8 nbf nocc bytes crosses PCIe on the way in.
   void compute_K_dft_mo(const double *D, const double *Cocc, double *K) {
     if (m_nocc[0] < 0) throw std::runtime_error("XCBuild was created without occupied-orbital counts");
-    check(occ_xc_build_mo(m_handle, D, Cocc, K, &m_exc_dft, &m_total_density_a, &m_total_density_b));
+    if (m_multi) check(occ_xc_multi_build(m_multi, D, Cocc, K, &m_exc_dft, &m_total_density_a, &m_total_density_b));
+    else check(occ_xc_build_mo(m_handle, D, Cocc, K, &m_exc_dft, &m_total_density_a, &m_total_density_b));
   }
   // two separate blocks (Cocc_alpha, Cocc_beta): packed into a buffer of this object
   void compute_K_dft_mo(const double *D, const double *Cocc_alpha, const double *Cocc_beta, double *K) {
@@ -142,20 +153,19 @@ public:
   double exchange_correlation_energy() const { return m_exc_dft; }
   double total_density_alpha() const { return m_total_density_a; }
   double total_density_beta() const { return m_total_density_b; }
-  int density_derivative() const { // DFT::density_derivative, src/dft/dft.cpp:11-17
-    occ_xc_info_t info;
-    check(occ_xc_get_info(m_handle, &info));
-    return info.deriv;
-  }
-  occ_xc_info_t info() const {
+  int density_derivative() const { return info().deriv; } // DFT::density_derivative, src/dft/dft.cpp:11-17
+  occ_xc_info_t info(int shard = 0) const {
     occ_xc_info_t i;
-    check(occ_xc_get_info(m_handle, &i));
+    if (m_multi) check(occ_xc_multi_get_info(m_multi, shard, &i));
+    else check(occ_xc_get_info(m_handle, &i));
     return i;
   }
+  int num_devices() const { return m_multi ? occ_xc_multi_ndev(m_multi) : 1; }
   occ_xc_handle *handle() { return m_handle; }
 
 private:
   occ_xc_handle *m_handle = nullptr;
+  occ_xc_multi *m_multi = nullptr;
   int m_nspin, m_nbf;
   double m_exc_dft = 0.0, m_total_density_a = 0.0, m_total_density_b = 0.0;
   int m_nocc[2] = {-1, -1};

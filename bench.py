@@ -146,8 +146,9 @@ def cpu_pick_threads(ob, spts, sw, leaves, names, nspin, D2):
     """thread count with the best leaf-loop throughput on a thin probe (more threads was slower on some boxes)"""
     from oracle import oracle as O
     cores = os.cpu_count() or 1
-    cands = sorted({cores, max(1, cores // 2), max(1, cores // 4)}, reverse=True)
-    probe = leaves[::max(1, len(leaves) // 96)]
+    cands = sorted({cores, max(1, cores // 2)}, reverse=True)
+    # >= 40 leaves per thread: with fewer, the imbalance of a dynamic schedule over unequal leaves decides the probe
+    probe = leaves[::max(1, len(leaves) // max(96, 40 * cores))]
     best, rows = None, []
     for nt in cands:
         O.xc_build(ob, spts, sw, probe[:8], names, nspin, D2, nthreads=nt)        # touch the per-thread buffers
@@ -389,7 +390,7 @@ def run_b200(args):
     ddft.dft.set_profiling(False)
 
     flops_total = info["flops_per_build"]
-    exec_total = 0.5 * info["flops_per_build"] + (info["mo_density_flops"] if mo else 0.5 * info["flops_per_build"])
+    exec_total = info["vxc_flops"] + (info["mo_density_flops"] if mo else 0.5 * info["flops_per_build"])
     nlaunch = float(info["launches_per_build_mo"] if mo else info["launches_per_build"])
     if world > 1:
         ft = torch.tensor([flops_total, nlaunch, exec_total], dtype=torch.float64, device=dev)
@@ -410,7 +411,7 @@ def run_b200(args):
                     cc = setup_case(wl, local, {}, args.batch_mb, mo)
                     mm = measure(cc, max(3, min(args.steps, 10)), 3, False)
                 ii = cc["info"]
-                ex = 0.5 * ii["flops_per_build"] + (ii["mo_density_flops"] if mo else 0.5 * ii["flops_per_build"])
+                ex = ii["vxc_flops"] + (ii["mo_density_flops"] if mo else 0.5 * ii["flops_per_build"])
                 npt = len(cc["h"].sorted_weights)
                 configs[wl] = {"config": common_config(wl, cc["basis"], cc["method"], cc["nspin"], npt, cc["h"].num_leaves),
                                "device_ms": mm["device_ms"], "e2e_ms": mm["e2e_ms"],
@@ -429,7 +430,7 @@ def run_b200(args):
     if rank == 0:
         kern = {}
         executed = {"density": info["mo_density_flops"] if mo else 0.5 * info["flops_per_build"],
-                    "vxc": 0.5 * info["flops_per_build"]}
+                    "vxc": info["vxc_flops"]}
         for name in ("density", "vxc"):
             fl = executed[name]      # tensor flops the phase really issues (the factorised density issues fewer)
             kern[name] = {"kernel": KERNEL_NAMES[name if (mo or name == "vxc") else "density_d"],

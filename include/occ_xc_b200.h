@@ -199,6 +199,8 @@ typedef struct {
   double mo_density_flops;   /* tensor flops the density phase of occ_xc_build_mo really issues (0 without MO mode);
                                 the D-form density phase issues flops_per_build / 2 */
   size_t launches_per_build_mo; /* kernel launches one occ_xc_build_mo issues (0 without MO mode) */
+  double vxc_flops;          /* tensor flops the Vxc phase really issues: flops_per_build / 2 for GGA builds, less where
+                                symmetric terms (LDA, the tau terms of a meta-GGA) are computed as upper triangles */
 } occ_xc_info_t;
 int occ_xc_get_info(const occ_xc_handle *h, occ_xc_info_t *info);
 

@@ -49,7 +49,7 @@ class InfoT(C.Structure):
                 ("nleaves", C.c_size_t), ("ntiles", C.c_size_t), ("nbatches", C.c_size_t), ("sum_n_nb2", C.c_double),
                 ("flops_per_build", C.c_double), ("nb_min", C.c_int), ("nb_max", C.c_int),
                 ("workspace_bytes", C.c_size_t), ("launches_per_build", C.c_size_t), ("mo_density_flops", C.c_double),
-                ("launches_per_build_mo", C.c_size_t)]
+                ("launches_per_build_mo", C.c_size_t), ("vxc_flops", C.c_double)]
 
 
 class GridSettingsT(C.Structure):

@@ -53,6 +53,7 @@ struct occ_xc_handle {
   xcb::DensItem *d_gradd = nullptr;
   double *d_C = nullptr, *d_CT = nullptr;
   double mo_executed_flops = 0.0; // DMMA flops one MO-form build really issues (density side)
+  double vxc_executed_flops = 0.0; // DMMA flops of the Vxc phase (upper triangles only for the symmetric terms)
   // post-SCF VV10 (allocated on first use)
   std::vector<size_t> h_tile_src; // sorted index of the first point of each tile
   std::vector<long long> h_tile_psi_off;

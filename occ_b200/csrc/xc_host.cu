@@ -565,6 +565,13 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
               vi.spin = static_cast<signed char>(sp);
               vi.acomp = static_cast<signed char>(ac);
               vxc.push_back(vi);
+              { // executed flops of this item: k_vxc_resident skips row blocks below the diagonal of symmetric terms
+                const bool symmetric = ac != 0 || deriv == 0;
+                const int n0 = jb * 64, nib_all = (t.nb + 127) / 128;
+                const int nib = symmetric ? std::min(nib_all, (n0 + 64 + 127) / 128) : nib_all;
+                const int rows = std::min(t.nb, nib * 128), cols = std::min(64, t.nb - n0);
+                if (cols > 0) h->vxc_executed_flops += 2.0 * t.count * rows * cols;
+              }
             }
         if (h->mo) {
           // per tile and spin: rho / grad rho in the factorised form when 4 n nb nocc < 2 n nb^2, tau when nocc < nb
@@ -1207,6 +1214,7 @@ int occ_xc_get_info(const occ_xc_handle *h, occ_xc_info_t *info) {
   info->workspace_bytes = h->alloc_bytes;
   info->launches_per_build = h->launches;
   info->mo_density_flops = h->mo_executed_flops;
+  info->vxc_flops = h->vxc_executed_flops;
   size_t lm = 0;
   if (h->mo) {
     for (const Batch &b : h->batches)

@@ -4,6 +4,7 @@
 #include "../../adapter/occ_dft_b200.h"
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -19,6 +20,15 @@ template <class T> static std::vector<T> read_vec(std::ifstream &f) {
 int main(int argc, char **argv) {
   if (argc < 3) return 2;
   const bool expect_error = argc > 3 && std::strcmp(argv[3], "--expect-error") == 0;
+  // --devices a,b,c : one leaf shard per listed GPU, driven from this process (occ_xc_multi_*)
+  std::vector<int> devices;
+  for (int a = 3; a + 1 < argc; ++a)
+    if (std::strcmp(argv[a], "--devices") == 0)
+      for (const char *p = argv[a + 1]; *p;) {
+        devices.push_back(std::atoi(p));
+        while (*p && *p != ',') ++p;
+        if (*p == ',') ++p;
+      }
   std::ifstream f(argv[1], std::ios::binary);
   auto meta = read_vec<int>(f); // pure, nspin, nfunc ids...
   occ_b200::BasisArrays basis;
@@ -41,12 +51,25 @@ int main(int argc, char **argv) {
     for (int d = 0; d < 3; ++d) leaves[i].center[d] = leaf_raw[6 * i + 2 + d];
     leaves[i].radius = leaf_raw[6 * i + 5];
   }
-  auto D = read_vec<double>(f);
+  auto D = read_vec<double>(f);     // mo.D exactly as the reference stores it (NOT doubled)
+  auto Cocc = read_vec<double>(f);  // mo.Cocc: nbf x nocc_alpha [, nbf x nocc_beta]; may be empty
+  auto nocc = read_vec<int>(f);     // {nocc_alpha, nocc_beta} or empty
   try {
     occ_b200::XCBuild xc(basis, w.size(), pts.data(), w.data(), leaves, func_ids,
-                         nspin == 2 ? occ_b200::SpinorbitalKind::Unrestricted : occ_b200::SpinorbitalKind::Restricted);
+                         nspin == 2 ? occ_b200::SpinorbitalKind::Unrestricted : occ_b200::SpinorbitalKind::Restricted,
+                         1e-10, 1e-10, -1, 0, 1, nocc.empty() ? -1 : nocc[0], nocc.empty() ? -1 : nocc[1], false, devices);
     std::vector<double> K(D.size());
     xc.compute_K_dft(D.data(), K.data());
+    if (!nocc.empty()) { // the factorised entry (with D and with the density formed on the device) must agree
+      std::vector<double> K2(D.size()), K3(D.size());
+      xc.compute_K_dft_mo(D.data(), Cocc.data(), K2.data());
+      xc.compute_K_dft_mo(nullptr, Cocc.data(), K3.data());
+      for (size_t i = 0; i < K.size(); ++i)
+        if (std::fabs(K2[i] - K[i]) > 1e-10 || std::fabs(K3[i] - K[i]) > 1e-10) {
+          std::printf("factorised K differs at %zu: %.15g %.15g %.15g\n", i, K[i], K2[i], K3[i]);
+          return 1;
+        }
+    }
     const double *Kp = xc.compute_K_dft(D.data());   // page-locked variant must give the same matrix
     for (size_t i = 0; i < K.size(); ++i)
       if (std::fabs(Kp[i] - K[i]) > 1e-12) {

@@ -21,7 +21,7 @@ def _compile():
     return EXE
 
 
-def _write_case(path, basis, nspin, func_ids, spts, sw, leaves, D):
+def _write_case(path, basis, nspin, func_ids, spts, sw, leaves, D, Cocc=None):
     a = basis.as_arrays()
 
     def vec(f, arr, fmt):
@@ -43,6 +43,13 @@ def _write_case(path, basis, nspin, func_ids, spts, sw, leaves, D):
                         leaves["center"][:, 1], leaves["center"][:, 2], leaves["radius"]], 1)
         vec(f, raw, np.float64)
         vec(f, np.asfortranarray(D).ravel(order="F"), np.float64)
+        # mo.Cocc blocks (column-major, alpha then beta) and the occupied counts; empty = D-only handle
+        if Cocc is None:
+            vec(f, [], np.float64)
+            vec(f, [], np.int32)
+        else:
+            vec(f, np.concatenate([np.asfortranarray(c).ravel(order="F") for c in Cocc]), np.float64)
+            vec(f, [Cocc[0].shape[1], Cocc[-1].shape[1]], np.int32)
 
 
 def test_adapter_compiles_and_reports_errors_as_exceptions(case, tmp_path):
@@ -65,16 +72,24 @@ def test_adapter_compiles_and_reports_errors_as_exceptions(case, tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("devices", [None, "0,0", "0,1", "0,1,2,3,4,5,6,7"])
 @pytest.mark.parametrize("method,nspin", [("b3lyp", 1), ("pbe", 2)])
-def test_adapter_build_matches_oracle(case, oracle, tmp_path, method, nspin):
+def test_adapter_build_matches_oracle(case, oracle, tmp_path, method, nspin, devices):
+    """XCBuild::compute_K_dft / compute_K_dft_mo with the reference's own conventions (mo.D undoubled, mo.Cocc
+    unscaled: the factors are applied on the device); `devices`: the single-process multi-GPU handle (ngpu = 2..8)."""
+    import torch
     from occ_b200 import dft, molecules
+    if devices is not None and max(int(x) for x in devices.split(",")) >= torch.cuda.device_count():
+        pytest.skip("not enough GPUs")
     exe = _compile()
     c = case("water", "def2-svp")
     b = c["basis"]
-    D2 = molecules.synthetic_density(b, nspin)
+    Cs = molecules.synthetic_orbitals(b, nspin)                 # D2_s = C_s C_s^T
+    D2 = np.asfortranarray(np.vstack([x @ x.T for x in Cs]))
+    Cocc = [x / np.sqrt(2.0) for x in Cs] if nspin == 1 else Cs  # restricted: mo.D = Cocc Cocc^T = D2 / 2
     p, o = str(tmp_path / "case.bin"), str(tmp_path / "out.bin")
-    _write_case(p, b, nspin, dft.get_dft_method(method), c["spts"], c["sw"], c["leaves"], 0.5 * D2)  # mo.D = D2 / 2
-    r = subprocess.run([exe, p, o], capture_output=True, text=True)
+    _write_case(p, b, nspin, dft.get_dft_method(method), c["spts"], c["sw"], c["leaves"], 0.5 * D2, Cocc)  # mo.D = D2 / 2
+    r = subprocess.run([exe, p, o] + (["--devices", devices] if devices else []), capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     raw = np.fromfile(o)
     K = raw[3:].reshape(b.nbf, nspin * b.nbf).T
