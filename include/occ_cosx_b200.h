@@ -31,7 +31,7 @@ typedef struct {
   int device;               /* CUDA ordinal, -1 = current */
   int collect_stats;        /* 1 = count evaluated (batch, pair) combinations (adds one atomic per combination) */
   int rank, world_size;     /* grid batches are dealt round-robin to ranks; each rank returns a partial K (sum = K) */
-  int reserved[4];          /* [0] & 1: K' += Phi^T G through one cuBLAS call per batch instead of k_cosx_kgemm (A/B timing) */
+  int reserved[4];          /* must be zero */
 } occ_cosx_options_t;
 
 typedef struct occ_cosx_handle occ_cosx_handle;
@@ -95,7 +95,8 @@ typedef struct {
   double gemm_flops;         /* F = phi D2q and K = phi^T G: 4 npt nbf^2 (factorised F: 2 npt nbf^2 + 4 npt nbf nocc) */
   double ms_collocate, ms_fgemm, ms_esp, ms_kgemm; /* device time of the last compute, by phase */
   size_t launches;           /* kernels of this library launched by the last compute (cuBLAS GEMMs not counted) */
-  size_t gemm_calls;         /* cuBLAS calls of the last compute */
+  size_t gemm_calls;         /* library (cuBLAS) GEMM calls of the last compute: always 0 since round 2, every product
+                                runs on this library's own DMMA kernels; the field is kept for the bench line */
   size_t kgemm_blocks;       /* (batch, 64-column block)s of G that were not identically zero, i.e. executed by k_cosx_kgemm */
 } occ_cosx_info_t;
 int occ_cosx_get_info(const occ_cosx_handle *h, occ_cosx_info_t *info);

@@ -78,7 +78,8 @@ class SemiNumericalExchange:
         self.weights = np.ascontiguousarray(w, dtype=np.float64)
         self._ba = BasisArrays(basis.as_arrays())
         opt = CosxOptionsT(margin, 0.0, 0.0, batch_bytes, device, int(collect_stats), rank, world_size)
-        opt.reserved[0] = 1 if kgemm_library else 0   # A/B timing switch: cuBLAS per batch instead of k_cosx_kgemm
+        if kgemm_library:
+            raise RuntimeError("the cuBLAS A/B path of K' += Phi^T G was removed in round 2 (no library GEMM is left)")
         self._h = C.c_void_p()
         L.occ_cosx_destroy.restype = None
         L.occ_cosx_destroy.argtypes = [C.c_void_p]

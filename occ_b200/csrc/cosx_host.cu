@@ -6,18 +6,17 @@
 //               (include/occ/ints/ecoeffs.h:150-198, kernels.h:293-340, src/ints/esp.cpp:85-100), the grid batches with
 //               their bounding spheres (:676-720) and the Boys table (boys.h:191-330) — built on the host, once.
 //   compute():  per SCF iteration, per chunk of batches: AO values (k_collocate) -> batch skip flags -> F = Phi D2q
-//               (library DGEMM; factorised as (Phi (P C)) C^T when the caller passes the occupied orbitals) -> ESP +
+//               (k_dgemm, DMMA; factorised as (Phi (P C)) C^T when the caller passes the occupied orbitals) -> ESP +
 //               contraction kernels, one launch per (la, lb) class (k_cosx_esp) -> K' += Phi^T G (k_cosx_kgemm, DMMA)
 //               -> K = c (K' + K'^T).
-// F = Phi D2q is a plain batched GEMM and goes to cuBLAS (loaded with dlopen so that the XC entry points do not depend
-// on it); everything else is this library's own kernels. No CPU fallback.
+// Every product, including the plain batched GEMMs F = Phi D2q / P C / P (2 D), runs on this library's own DMMA
+// kernels (k_dgemm.cu, k_cosx_kgemm.cu): no cuBLAS.  No CPU fallback.
 #include "../../include/occ_cosx_b200.h"
 #include "cosx_internal.h"
 #include <algorithm>
 #include <array>
 #include <cmath>
 #include <cstring>
-#include <cublas_v2.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <string>
@@ -37,37 +36,6 @@ static int fail(const std::string &m) { return occ_xc_set_error(m.c_str()); }
 namespace {
 
 constexpr double kPi = 3.14159265358979323846;
-
-// ---- cuBLAS through dlopen ----
-struct Blas {
-  void *lib = nullptr;
-  cublasHandle_t h = nullptr;
-  cublasStatus_t (*create)(cublasHandle_t *) = nullptr;
-  cublasStatus_t (*destroy)(cublasHandle_t) = nullptr;
-  cublasStatus_t (*set_stream)(cublasHandle_t, cudaStream_t) = nullptr;
-  cublasStatus_t (*dgemm)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int, const double *,
-                          const double *, int, const double *, int, const double *, double *, int) = nullptr;
-  cublasStatus_t (*dgemm_sb)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int, const double *,
-                             const double *, int, long long, const double *, int, long long, const double *, double *,
-                             int, long long, int) = nullptr;
-  int open() {
-    const char *names[] = {"libcublas.so.12", "/usr/local/cuda/lib64/libcublas.so.12", "libcublas.so", nullptr};
-    for (int i = 0; names[i] && !lib; ++i) lib = dlopen(names[i], RTLD_NOW | RTLD_LOCAL);
-    if (!lib) return fail("occ_cosx_create: cannot load libcublas (needed for the F = Phi.D2q product of the COSX build)");
-    create = reinterpret_cast<decltype(create)>(dlsym(lib, "cublasCreate_v2"));
-    destroy = reinterpret_cast<decltype(destroy)>(dlsym(lib, "cublasDestroy_v2"));
-    set_stream = reinterpret_cast<decltype(set_stream)>(dlsym(lib, "cublasSetStream_v2"));
-    dgemm = reinterpret_cast<decltype(dgemm)>(dlsym(lib, "cublasDgemm_v2"));
-    dgemm_sb = reinterpret_cast<decltype(dgemm_sb)>(dlsym(lib, "cublasDgemmStridedBatched"));
-    if (!create || !destroy || !set_stream || !dgemm || !dgemm_sb) return fail("occ_cosx_create: libcublas lacks a symbol");
-    if (create(&h) != CUBLAS_STATUS_SUCCESS) return fail("occ_cosx_create: cublasCreate failed");
-    return 0;
-  }
-  void close() {
-    if (h && destroy) destroy(h);
-    h = nullptr; // the library stays loaded for the life of the process
-  }
-};
 
 inline int ncart(int l) { return (l + 1) * (l + 2) / 2; }
 inline int nfun(int l, int pure) { return pure ? 2 * l + 1 : ncart(l); }
@@ -169,7 +137,6 @@ struct occ_cosx_handle {
   int ntiles = 0, tiles_per_chunk = 1, nruns = 1;
   double margin = 1.0, density_threshold = 1e-6;
   bool collect = false;
-  bool kgemm_library = false;
   std::vector<void *> allocs;
   size_t alloc_bytes = 0;
   BuildParams B = {};      // what k_collocate reads
@@ -193,7 +160,6 @@ struct occ_cosx_handle {
   std::vector<ClassRange> classes;
   std::vector<double> S_analytic;
   std::vector<int> h_counts;
-  Blas blas;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   occ_cosx_info_t info = {};
@@ -220,7 +186,6 @@ void occ_cosx_destroy(occ_cosx_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  h->blas.close();
   for (void *p : h->allocs) cudaFree(p);
   for (auto &e : h->ev)
     if (e) cudaEventDestroy(e);
@@ -262,7 +227,6 @@ int occ_cosx_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_
   h->margin = (opt && opt->margin > 0.0) ? opt->margin : 1.0;
   h->density_threshold = (opt && opt->density_threshold > 0.0) ? opt->density_threshold : 1e-6;
   h->collect = opt && opt->collect_stats;
-  h->kgemm_library = opt && (opt->reserved[0] & 1);
   const double pair_threshold = (opt && opt->pair_threshold > 0.0) ? opt->pair_threshold : 1e-12;
   const size_t batch_bytes = (opt && opt->batch_bytes) ? opt->batch_bytes : (size_t(4096) << 20);
   h->npts = atom_offsets[natoms] - atom_offsets[0];
@@ -460,8 +424,6 @@ int occ_cosx_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_
   // ---- device state ----
   CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess && fail("occ_cosx_create: stream"));
   for (auto &e : h->ev) CHECK(cudaEventCreate(&e) != cudaSuccess && fail("occ_cosx_create: event"));
-  CHECK(h->blas.open());
-  h->blas.set_stream(h->blas.h, h->stream);
   upload_default_c2s();
   {
     int *d_l = nullptr, *d_np = nullptr, *d_po = nullptr, *d_fb = nullptr, *d_list = nullptr;
@@ -615,7 +577,6 @@ static int sweep(occ_cosx_handle *h, const double *D2q, double precision, double
   P.w_lr = w_lr;
   P.omega = omega;
   P.stats = h->collect ? h->d_stats : nullptr;
-  const double one = 1.0, zero = 0.0;
   const long long slab = static_cast<long long>(nbp) * TILE_P;
   float ms[4] = {0, 0, 0, 0};
   for (int t0 = 0; t0 < h->ntiles; t0 += h->tiles_per_chunk) {
@@ -628,19 +589,15 @@ static int sweep(occ_cosx_handle *h, const double *D2q, double precision, double
     // F_t = Phi_t . D2q for every batch of the chunk (:733-734, the weight is applied when F is read)
     if (Cq && nocc > 0) {
       const long long pslab = static_cast<long long>(nocc) * TILE_P;
-      if (h->blas.dgemm_sb(h->blas.h, CUBLAS_OP_N, CUBLAS_OP_N, TILE_P, nocc, nbf, &one, h->d_phi, TILE_P, slab, Cq, nbf, 0,
-                           &zero, h->d_psi, TILE_P, pslab, nt) != CUBLAS_STATUS_SUCCESS ||
-          h->blas.dgemm_sb(h->blas.h, CUBLAS_OP_N, CUBLAS_OP_T, TILE_P, nbf, nocc, &one, h->d_psi, TILE_P, pslab, Cs, nbf, 0,
-                           &zero, h->d_F, TILE_P, slab, nt) != CUBLAS_STATUS_SUCCESS)
-        return fail("occ_cosx: cublasDgemmStridedBatched failed");
-      h->info.gemm_calls += 2;
+      // Psi_t = Phi_t (P C), F_t = Psi_t C^T: this library's DMMA GEMM (k_dgemm.cu), one batched launch each
+      launch_dgemm(false, TILE_P, nocc, nbf, 1.0, h->d_phi, TILE_P, slab, Cq, nbf, 0, h->d_psi, TILE_P, pslab, nt, st);
+      launch_dgemm(true, TILE_P, nbf, nocc, 1.0, h->d_psi, TILE_P, pslab, Cs, nbf, 0, h->d_F, TILE_P, slab, nt, st);
+      h->info.launches += 2;
     } else if (Cq) { // no occupied orbital of this spin: D2q = 0
       CUDA_TRY(cudaMemsetAsync(h->d_F, 0, static_cast<size_t>(nt) * slab * sizeof(double), st));
     } else {
-      if (h->blas.dgemm_sb(h->blas.h, CUBLAS_OP_N, CUBLAS_OP_N, TILE_P, nbf, nbf, &one, h->d_phi, TILE_P, slab, D2q, nbf, 0,
-                           &zero, h->d_F, TILE_P, slab, nt) != CUBLAS_STATUS_SUCCESS)
-        return fail("occ_cosx: cublasDgemmStridedBatched failed");
-      h->info.gemm_calls += 1;
+      launch_dgemm(false, TILE_P, nbf, nbf, 1.0, h->d_phi, TILE_P, slab, D2q, nbf, 0, h->d_F, TILE_P, slab, nt, st);
+      h->info.launches += 1;
     }
     CUDA_TRY(cudaMemsetAsync(h->d_G, 0, static_cast<size_t>(nt) * slab * sizeof(double), st));
     if (h->collect) cudaEventRecord(h->ev[2], st);
@@ -651,17 +608,8 @@ static int sweep(occ_cosx_handle *h, const double *D2q, double precision, double
     }
     if (h->collect) cudaEventRecord(h->ev[3], st);
     // K' += Phi_t^T . G_t (:797; G here is the reference's -Gg): k_cosx_kgemm, one launch per chunk
-    if (h->kgemm_library) { // A/B switch (options.reserved[0] & 1): one cuBLAS call per batch
-      for (int t = 0; t < nt; ++t) {
-        if (h->blas.dgemm(h->blas.h, CUBLAS_OP_T, CUBLAS_OP_N, nbf, nbf, TILE_P, &one, h->d_phi + t * slab, TILE_P,
-                          h->d_G + t * slab, TILE_P, &one, Kraw, nbf) != CUBLAS_STATUS_SUCCESS)
-          return fail("occ_cosx: cublasDgemm failed");
-      }
-      h->info.gemm_calls += nt;
-    } else {
-      launch_cosx_kgemm(h->d_phi, h->d_G, h->d_skip + t0, nt, nbf, nbp, Kraw, h->collect ? h->d_stats + 32 : nullptr, st);
-      h->info.launches += 1;
-    }
+    launch_cosx_kgemm(h->d_phi, h->d_G, h->d_skip + t0, nt, nbf, nbp, Kraw, h->collect ? h->d_stats + 32 : nullptr, st);
+    h->info.launches += 1;
     if (h->collect) {
       cudaEventRecord(h->ev[4], st);
       CUDA_TRY(cudaEventSynchronize(h->ev[4]));
@@ -753,7 +701,6 @@ static int compute_K_impl(occ_cosx_handle *h, int kind, const double *D, double 
   double *dD = kind == 2 ? h->d_Dg : h->d_D, *dK = kind == 2 ? h->d_Kg : h->d_K;
   CUDA_TRY(cudaMemcpyAsync(dD, D, static_cast<size_t>(rows) * cols * sizeof(double), cudaMemcpyHostToDevice, st));
   reset_info(h);
-  const double two = 2.0, zero = 0.0, one = 1.0;
   const int nocc_s[2] = {nocc_a, kind == 1 ? nocc_b : 0};
   if (C) { // orbitals on the device: [C_alpha | C_beta], nbf rows
     const int cap = std::max(1, std::max(nocc_s[0], nocc_s[1]));
@@ -769,18 +716,14 @@ static int compute_K_impl(occ_cosx_handle *h, int kind, const double *D, double 
   // Cq = P . C_s, so that Cq C_s^T = P (2 D_s)
   auto project_orbitals = [&](const double *Cs, int nocc) -> int {
     if (nocc == 0) return 0;
-    if (h->blas.dgemm(h->blas.h, CUBLAS_OP_N, CUBLAS_OP_N, nbf, nocc, nbf, &one, h->d_proj, nbf, Cs, nbf, &zero, h->d_Cq,
-                      nbf) != CUBLAS_STATUS_SUCCESS)
-      return fail("occ_cosx: cublasDgemm failed");
-    h->info.gemm_calls += 1;
+    launch_dgemm(false, nbf, nocc, nbf, 1.0, h->d_proj, nbf, 0, Cs, nbf, 0, h->d_Cq, nbf, 0, 1, st);
+    h->info.launches += 1;
     return 0;
   };
   // D2q = P . (2 D_block): the factor 2 is D2 = 2 D for restricted (:524) and the stored 1/2 otherwise (:632-633, 676-679)
   auto project = [&](const double *Dblk) -> int {
-    if (h->blas.dgemm(h->blas.h, CUBLAS_OP_N, CUBLAS_OP_N, nbf, nbf, nbf, &two, h->d_proj, nbf, Dblk, rows, &zero, h->d_D2q,
-                      nbf) != CUBLAS_STATUS_SUCCESS)
-      return fail("occ_cosx: cublasDgemm failed");
-    h->info.gemm_calls += 1;
+    launch_dgemm(false, nbf, nbf, nbf, 2.0, h->d_proj, nbf, 0, Dblk, rows, 0, h->d_D2q, nbf, 0, 1, st);
+    h->info.launches += 1;
     return 0;
   };
   if (kind < 2) {
