@@ -165,7 +165,7 @@ int occ_xc_gradient(occ_xc_handle *h, const double *D2, double *gradient);
  * selects max_derivative: LDA 0, GGA 1, meta-GGA 2) with world_size 1.
  *   D2   as in occ_xc_build
  *   rho  (nspin * npts) x {1, 4, 6} column-major, alpha rows [0, npts) then beta, in the handle's (sorted) point order;
- *        columns rho, rho_x, rho_y, rho_z, laplacian (NOT evaluated: 0), tau.  HOST buffers; synchronous.
+ *        columns rho, rho_x, rho_y, rho_z, laplacian, tau (src/gto/density.cpp:72-101).  HOST buffers; synchronous.
  * Points of leaves that keep no shell under the screening rule (dft.h:309-321) stay 0. */
 int occ_xc_density_on_grid(occ_xc_handle *h, const double *D2, double *rho);
 

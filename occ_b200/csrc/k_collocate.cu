@@ -159,6 +159,121 @@ __global__ void __launch_bounds__(TILE_P) k_collocate(BuildParams P, const Collo
   }
 }
 
+// ---- AO Laplacians (occ::density::evaluate_density<2>, src/gto/density.cpp:84-100: the laplacian column of the
+// density-on-grid consumers, include/occ/gto/density.h:67-107).  For phi = S(r^2) A(x, y, z), A a monomial of degree L:
+//   lap phi = A (S2 r^2 + (3 + 2 L) S1) + S0 lap A,   S1 = sum (-2a) c e^(-a r^2), S2 = sum (-2a)^2 c e^(-a r^2)
+// (grad S . grad A = S1 L A by Euler's theorem).  Writes lap phi to slab 0 and phi to slab 1, the layout the density
+// kernel needs to form rowsum(phi o (lap phi . D)) with its ordinary acomp = 0 items (accumulator row 1).
+template <int L, bool PURE>
+__device__ __forceinline__ void shell_laplacian(double x, double y, double z, double r2, double S0, double S1, double S2,
+                                                double fac, double *__restrict__ olap, double *__restrict__ ophi) {
+  constexpr int NC = (L + 1) * (L + 2) / 2;
+  double xp[L + 1], yp[L + 1], zp[L + 1];
+  xp[0] = yp[0] = zp[0] = 1.0;
+#pragma unroll
+  for (int i = 1; i <= L; ++i) {
+    xp[i] = xp[i - 1] * x;
+    yp[i] = yp[i - 1] * y;
+    zp[i] = zp[i - 1] * z;
+  }
+  const double radial = S2 * r2 + (3.0 + 2.0 * L) * S1;
+  double c0[NC], cl[NC];
+  int idx = 0;
+#pragma unroll
+  for (int lx = L; lx >= 0; --lx) {
+#pragma unroll
+    for (int ly = L - lx; ly >= 0; --ly) {
+      const int lz = L - lx - ly;
+      const double A = xp[lx] * yp[ly] * zp[lz];
+      double lapA = 0.0;
+      if (lx >= 2) lapA += lx * (lx - 1) * (xp[lx >= 2 ? lx - 2 : 0] * yp[ly] * zp[lz]);
+      if (ly >= 2) lapA += ly * (ly - 1) * (xp[lx] * yp[ly >= 2 ? ly - 2 : 0] * zp[lz]);
+      if (lz >= 2) lapA += lz * (lz - 1) * (xp[lx] * yp[ly] * zp[lz >= 2 ? lz - 2 : 0]);
+      c0[idx] = S0 * A;
+      cl[idx] = radial * A + S0 * lapA;
+      ++idx;
+    }
+  }
+  if (!PURE || L == 0) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      ophi[i * TILE_P] = c0[i] * fac;
+      olap[i * TILE_P] = cl[i] * fac;
+    }
+  } else {
+    constexpr int NS = 2 * L + 1;
+    const double *tab = c_c2s.coef + c_c2s.off[L];
+#pragma unroll
+    for (int m = 0; m < NS; ++m) {
+      double v = 0.0, vl = 0.0;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        const double t = tab[m * NC + i];
+        v += t * c0[i];
+        vl += t * cl[i];
+      }
+      ophi[m * TILE_P] = v * fac;
+      olap[m * TILE_P] = vl * fac;
+    }
+  }
+}
+
+template <bool PURE>
+__global__ void __launch_bounds__(TILE_P) k_collocate_laplacian(BuildParams P, const CollocItem *__restrict__ items) {
+  const CollocItem it = items[blockIdx.x];
+  const TileDesc t = P.tiles[it.tile];
+  const int p = threadIdx.x;
+  const bool valid = p < t.count;
+  const double px = P.px[t.pt0 + p], py = P.py[t.pt0 + p], pz = P.pz[t.pt0 + p];
+  const size_t slab = static_cast<size_t>(t.nbp) * TILE_P;
+  double *base = P.scratch + t.scr_off + p;
+  const DeviceBasis &B = P.basis;
+  for (int s = it.s0; s < it.s1; ++s) {
+    const int sh = __ldg(P.shell_list + t.sh_off + s);
+    const int col = __ldg(P.shell_col + t.sh_off + s);
+    const int L = __ldg(B.l + sh);
+    const int np = __ldg(B.nprim + sh);
+    const int po = __ldg(B.prim_off + sh);
+    const double x = px - __ldg(B.origin + 3 * sh), y = py - __ldg(B.origin + 3 * sh + 1),
+                 z = pz - __ldg(B.origin + 3 * sh + 2);
+    const double r2 = x * x + y * y + z * z;
+    double S0 = 0.0, S1 = 0.0, S2 = 0.0;
+    for (int k = 0; k < np; ++k) {
+      const double a = __ldg(B.exps + po + k);
+      const double T1 = __ldg(B.coefs + po + k) * exp(-a * r2);
+      S0 += T1;
+      S1 += (-2.0 * a) * T1;
+      S2 += (4.0 * a * a) * T1;
+    }
+    if (!valid) S0 = S1 = S2 = 0.0;
+    double *o = base + static_cast<size_t>(col) * TILE_P;
+    const double fac = common_fac_dev(L, PURE);
+    switch (L) {
+    case 0: shell_laplacian<0, PURE>(x, y, z, r2, S0, S1, S2, fac, o, o + slab); break;
+    case 1: shell_laplacian<1, PURE>(x, y, z, r2, S0, S1, S2, fac, o, o + slab); break;
+    case 2: shell_laplacian<2, PURE>(x, y, z, r2, S0, S1, S2, fac, o, o + slab); break;
+    case 3: shell_laplacian<3, PURE>(x, y, z, r2, S0, S1, S2, fac, o, o + slab); break;
+    case 4: shell_laplacian<4, PURE>(x, y, z, r2, S0, S1, S2, fac, o, o + slab); break;
+    case 5: shell_laplacian<5, PURE>(x, y, z, r2, S0, S1, S2, fac, o, o + slab); break;
+    case 6: shell_laplacian<6, PURE>(x, y, z, r2, S0, S1, S2, fac, o, o + slab); break;
+    default: break;
+    }
+  }
+  if (it.last)
+    for (int col = t.nb; col < t.nbp; ++col) {
+      double *o = base + static_cast<size_t>(col) * TILE_P;
+      o[0] = 0.0;
+      o[slab] = 0.0;
+    }
+}
+
+void launch_collocate_laplacian(const BuildParams &P, const CollocItem *items, int nitems, void *stream) {
+  if (nitems <= 0) return;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (P.basis.pure) k_collocate_laplacian<true><<<nitems, TILE_P, 0, st>>>(P, items);
+  else k_collocate_laplacian<false><<<nitems, TILE_P, 0, st>>>(P, items);
+}
+
 void launch_collocate(const BuildParams &P, const CollocItem *items, int nitems, void *stream) {
   if (nitems <= 0) return;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

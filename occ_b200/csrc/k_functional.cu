@@ -215,7 +215,7 @@ void launch_finalize(const BuildParams &P, int nleaves, double *K, double *scala
 
 // ---- density on the grid (occ::density::evaluate_density_on_grid, include/occ/gto/density.h:67-107): turn the
 // density-kernel accumulators into the reference's rho matrix, (nspin * npts) x {1, 4, 6} column-major with the
-// alpha rows first; columns rho, rho_x, rho_y, rho_z, laplacian (NOT evaluated: written as 0), tau ----
+// alpha rows first; columns rho, rho_x, rho_y, rho_z, laplacian, tau ----
 __global__ void __launch_bounds__(TILE_P) k_gather_rho(BuildParams P, const size_t *__restrict__ tile_src, size_t npts,
                                                        double *__restrict__ out) {
   const int tile = blockIdx.x, p = threadIdx.x;
@@ -232,10 +232,28 @@ __global__ void __launch_bounds__(TILE_P) k_gather_rho(BuildParams P, const size
       o[3 * ld] = 2.0 * a[3 * TILE_P];
     }
     if (P.deriv >= 2) {
-      o[4 * ld] = 0.0;
+      // laplacian = 2 rowsum(lap phi o D phi) + 2 sum_d rowsum(phi_d o (phi_d D)) (density.cpp:84-100): the second term
+      // here, the first one is added by k_gather_laplacian after the second density pass
+      o[4 * ld] = 2.0 * a[4 * TILE_P];
       o[5 * ld] = 0.5 * a[4 * TILE_P];
     }
   }
+}
+// second pass of a deriv-2 density-on-grid call: the AO slabs hold (lap phi, phi, ...), so accumulator row 1 of the
+// ordinary density items is rowsum(phi o (lap phi . D))
+__global__ void __launch_bounds__(TILE_P) k_gather_laplacian(BuildParams P, const size_t *__restrict__ tile_src,
+                                                             size_t npts, double *__restrict__ out) {
+  const int tile = blockIdx.x, p = threadIdx.x;
+  if (p >= P.tiles[tile].count) return;
+  const size_t si = tile_src[tile] + p;
+  const size_t ld = static_cast<size_t>(P.nspin) * npts;
+  for (int s = 0; s < P.nspin; ++s) {
+    const double *a = P.acc + (static_cast<size_t>(tile) * P.nspin + s) * NACC * TILE_P + p;
+    out[static_cast<size_t>(s) * npts + si + 4 * ld] += 2.0 * a[TILE_P];
+  }
+}
+void launch_gather_laplacian(const BuildParams &P, const size_t *tile_src, size_t npts, int ntiles, double *out, void *stream) {
+  if (ntiles > 0) k_gather_laplacian<<<ntiles, TILE_P, 0, static_cast<cudaStream_t>(stream)>>>(P, tile_src, npts, out);
 }
 void launch_gather_rho(const BuildParams &P, const size_t *tile_src, size_t npts, int ntiles, double *out, void *stream) {
   if (ntiles > 0) k_gather_rho<<<ntiles, TILE_P, 0, static_cast<cudaStream_t>(stream)>>>(P, tile_src, npts, out);

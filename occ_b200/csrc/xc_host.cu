@@ -992,8 +992,13 @@ int occ_xc_density_on_grid(occ_xc_handle *h, const double *D2, double *rho) {
   const size_t nout = static_cast<size_t>(h->nspin) * h->npts_total * ncol;
   double *d_out = nullptr;
   CUDA_TRY(cudaMalloc(&d_out, nout * sizeof(double)));
-  cudaMemsetAsync(d_out, 0, nout * sizeof(double), st);
-  cudaMemcpyAsync(h->d_D, D2, ksz * sizeof(double), cudaMemcpyHostToDevice, st);
+  struct Free { // released on every exit path
+    double *p;
+    ~Free() { cudaFree(p); }
+  } guard{d_out};
+  CUDA_TRY(cudaMemsetAsync(d_out, 0, nout * sizeof(double), st));
+  CUDA_TRY(cudaMemcpyAsync(h->d_D, D2, ksz * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (h->density_scale != 1.0) launch_scale(h->d_D, h->d_D, ksz, h->density_scale, st);
   if (h->nspin == 1) {
     launch_prepare_density(h->d_D, h->d_Dsym, h->nbf, 1, st);
     P.Drho[0] = h->d_Dsym;
@@ -1001,17 +1006,25 @@ int occ_xc_density_on_grid(occ_xc_handle *h, const double *D2, double *rho) {
   } else {
     for (int s = 0; s < 2; ++s) P.Drho[s] = P.Dtau[s] = h->d_D + static_cast<size_t>(s) * h->nbf;
   }
-  for (const Batch &b : h->batches) {
-    launch_collocate(P, h->d_colloc + b.colloc_off, static_cast<int>(b.ncolloc), st);
-    cudaMemsetAsync(P.acc + static_cast<size_t>(b.tile0) * h->nspin * NACC * TILE_P, 0,
-                    static_cast<size_t>(b.ntiles) * h->nspin * NACC * TILE_P * sizeof(double), st);
-    launch_density(P, h->d_dens + b.dens_off, static_cast<int>(b.ndens), st);
-  }
+  // the accumulators of all tiles persist across batches, so each pass can be gathered once at its end
+  auto density_pass = [&](bool laplacian) -> int {
+    for (const Batch &b : h->batches) {
+      if (laplacian) launch_collocate_laplacian(P, h->d_colloc + b.colloc_off, static_cast<int>(b.ncolloc), st);
+      else launch_collocate(P, h->d_colloc + b.colloc_off, static_cast<int>(b.ncolloc), st);
+      CUDA_TRY(cudaMemsetAsync(P.acc + static_cast<size_t>(b.tile0) * h->nspin * NACC * TILE_P, 0,
+                               static_cast<size_t>(b.ntiles) * h->nspin * NACC * TILE_P * sizeof(double), st));
+      launch_density(P, h->d_dens + b.dens_off, static_cast<int>(b.ndens), st);
+    }
+    return 0;
+  };
+  if (density_pass(false)) return 1;
   launch_gather_rho(P, h->d_tile_src, h->npts_total, h->ntiles, d_out, st);
-  cudaMemcpyAsync(rho, d_out, nout * sizeof(double), cudaMemcpyDeviceToHost, st);
-  cudaError_t e = cudaStreamSynchronize(st);
-  cudaFree(d_out);
-  if (e != cudaSuccess) return fail(std::string("occ_xc_density_on_grid: ") + cudaGetErrorString(e));
+  if (h->deriv >= 2) { // laplacian column (density.cpp:84-100): a second pass with A = lap phi, row-dotted with phi
+    if (density_pass(true)) return 1;
+    launch_gather_laplacian(P, h->d_tile_src, h->npts_total, h->ntiles, d_out, st);
+  }
+  CUDA_TRY(cudaMemcpyAsync(rho, d_out, nout * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

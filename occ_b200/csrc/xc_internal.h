@@ -150,6 +150,8 @@ void launch_add_inplace(double *a, const double *b, size_t n, void *stream);
 int measure_dmma_peak(double target_ms, double *tflops, double *measured_ms);
 void launch_gbuild(const BuildParams &P, const DensItem *items, int nitems, void *stream);
 void launch_collocate_h(const BuildParams &P, const CollocItem *items, int nitems, void *stream);
+void launch_collocate_laplacian(const BuildParams &P, const CollocItem *items, int nitems, void *stream);
+void launch_gather_laplacian(const BuildParams &P, const size_t *tile_src, size_t npts, int ntiles, double *out, void *stream);
 void launch_mo_psi(const BuildParams &P, const DensItem *items, int nitems, void *stream);
 void launch_mo_density(const BuildParams &P, const DensItem *items, int nitems, void *stream);
 void launch_mo_grad_psi(const BuildParams &P, const DensItem *items, int nitems, void *stream);

@@ -391,7 +391,7 @@ def evaluate_density_on_grid(basis: AOBasis, D: np.ndarray, grid_pts: np.ndarray
                              screening_threshold: float = 0.0) -> np.ndarray:
     """occ::density::evaluate_density_on_grid<max_derivative, kind>(basis, D, grid_pts) (include/occ/gto/density.h:67-107).
     D is the matrix evaluate_density receives (callers pass 2 * mo.D, density.h:84-87); grid_pts (npts, 3) in Bohr.
-    Returns (nspin * npts, {1, 4, 6}) in the CALLER's point order: rho, grad rho, laplacian (not evaluated: 0), tau.
+    Returns (nspin * npts, {1, 4, 6}) in the CALLER's point order: rho, grad rho, laplacian, tau.
     screening_threshold 0 = every shell at every point, like the reference's evaluate_basis."""
     from .grid import MolecularGrid          # local import: grid.py imports this module
     nspin = 2 if spinorbital_kind == UNRESTRICTED else 1

@@ -335,6 +335,18 @@ def test_density_on_grid_matches_dense_numpy_evaluation(oracle, nspin, deriv):
         if deriv >= 2:
             tau = 0.5 * sum((phi[1 + k] * (phi[1 + k] @ Ds)).sum(1) for k in range(3))
             assert np.abs(tau - got[s * n:(s + 1) * n, 5]).max() < 1e-10
+            # laplacian column (density.cpp:84-100): 2 rowsum((phi_xx + phi_yy + phi_zz) o D phi) + 4 tau, the AO second
+            # derivatives from the oracle's deriv-2 collocation (pinned against gau2grid, tests/test_xc_gradient.py)
+            lap_phi = np.zeros((len(pts), b.nbf))
+            col = 0
+            for sh in b.shells:
+                fac = oracle.lib().orc_common_fac(int(sh.l), int(b.pure))
+                v2 = oracle.collocate_shell_deriv2(sh.l, int(b.pure), pts, sh.coefficients, sh.exponents, sh.origin)
+                width = v2.shape[1]
+                lap_phi[:, col:col + width] = (v2[4] + v2[7] + v2[9]).T * fac
+                col += width
+            want = 2 * (lap_phi * X).sum(1) + 4 * tau
+            assert np.abs(want - got[s * n:(s + 1) * n, 4]).max() < 1e-9 * max(1.0, np.abs(want).max())
 
 
 def test_density_on_grid_far_points_and_screening():
@@ -445,3 +457,48 @@ def test_mo_form_at_full_size_on_a_leaf_sample(oracle):
     info = d.info()
     assert info["mo_density_flops"] < 0.35 * info["flops_per_build"]          # D form: 0.5
     d.close()
+
+
+@pytest.mark.parametrize("nspin", [1, 2])
+def test_hirshfeld_partition_and_cube_density_over_the_gpu_density(oracle, nspin):
+    """SURVEY 8(f) rank 4 consumers (src/dft/hirshfeld.cpp:247-476): charges / volumes from the GPU density against the
+    same sums over a dense numpy density built from the oracle's collocation; model pro-atoms exp(-2 zeta r)"""
+    from occ_b200 import hirshfeld
+    Z, pos = molecules.MOLECULES["water"]()
+    b = aobasis.AOBasis.load(Z, pos, "def2-svp")
+    ob = oracle.Basis(b.as_arrays())
+    pts, w, info = oracle.molecular_grid(Z, pos, ob)
+    off = np.concatenate([[0], np.cumsum(info["atom_npts"])]).astype(int) if isinstance(info, dict) else None
+    if off is None:
+        off = oracle.cosx_atom_grids(pts, info)
+    grids = [(pts[off[a]:off[a + 1]], w[off[a]:off[a + 1]]) for a in range(len(Z))]
+    zeta = {1: 1.0, 8: 2.2}
+    pro = lambda i, r: (zeta[int(Z[i])] ** 3 / np.pi) * np.exp(-2.0 * zeta[int(Z[i])] * r) * int(Z[i])   # noqa: E731
+    D = 0.5 * molecules.synthetic_density(b, nspin)                      # mo.D
+    kind = dft.UNRESTRICTED if nspin == 2 else dft.RESTRICTED
+    hp = hirshfeld.HirshfeldPartition(b, grids, pro)
+    q = hp.calculate(D, kind)
+    # dense numpy reference over the oracle's collocation
+    P, W = hp.pts, hp.w
+    phi = np.zeros((len(P), b.nbf))
+    col = 0
+    for sh in b.shells:
+        v = oracle.collocate_shell(sh.l, int(b.pure), P, sh.coefficients, sh.exponents, sh.origin, 0)[0].T
+        phi[:, col:col + v.shape[1]] = v * oracle.lib().orc_common_fac(int(sh.l), int(b.pure))
+        col += v.shape[1]
+    rho = np.zeros(len(P))
+    for s in range(nspin):
+        Ds = D[s * b.nbf:(s + 1) * b.nbf]
+        Dr = np.triu(Ds) + np.triu(Ds, 1).T if nspin == 1 else Ds
+        rho += (phi * (phi @ Dr)).sum(1)
+    r = np.linalg.norm(P[:, None, :] - np.asarray(pos).reshape(-1, 3)[None], axis=2)
+    rp = np.stack([pro(i, r[:, i]) for i in range(len(Z))], 1)
+    hw = rp / rp.sum(1)[:, None]
+    want_q = np.asarray(Z, float) - (hw * (2 * rho * W)[:, None]).sum(0)
+    want_v = (hw * r ** 3 * (2 * rho * W)[:, None]).sum(0)
+    assert np.abs(q - want_q).max() < 1e-9 and np.abs(hp.atom_volumes - want_v).max() < 1e-8
+    assert abs(hp.num_electrons - (2 * rho * W).sum()) < 1e-9
+    assert len(W) == len(w) - len(Z)                                     # the reference's dropped last point per atom grid
+    # cube grid: same numbers as the point-wise entry
+    cube = hirshfeld.cube_density(b, 2 * D, [-1.0, -1.0, -1.0], (5, 4, 3), spinorbital_kind=kind)
+    assert cube.shape == ((5, 4, 3) if nspin == 1 else (2, 5, 4, 3)) and np.all(cube >= -1e-12) and cube.max() > 1e-3
