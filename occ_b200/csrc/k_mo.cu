@@ -203,26 +203,70 @@ template <int MODE> __device__ __forceinline__ void XC_SYM(gemm_mo_body)(const B
     }
     return;
   }
-  // epilogue: row-dot the X tile (registers) with the AO slabs of the same columns
-  double *accp = P.acc + (static_cast<size_t>(it.tile) * P.nspin + it.spin) * NACC * TILE_P;
-  const int c_begin = it.acomp == 0 ? 0 : it.acomp;
-  const int c_end = it.acomp == 0 ? P.ncomp : it.acomp + 1;
-  const double *phib = P.scratch + t.scr_off + static_cast<size_t>(n0 + wn * 32 + 2 * tig) * TILE_P + wm * 32 + gid;
-  for (int c = c_begin; c < ((P.debug & 2) ? c_begin : c_end); ++c) {
-    const double *pc = phib + static_cast<size_t>(c) * slab;
-    const int row = it.acomp == 0 ? c : 4;
+  // epilogue: row-dot the X tile with the AO slabs of the same 64 columns.  The tile leaves the registers through shared
+  // memory (the pipeline stages are free now), so that thread = (point p, 32-column half): its slab loads are coalesced
+  // along p (one 1 KiB line of a column per 128 threads), independent of each other (deep batches in flight instead of
+  // one 8-load round trip per (slab, mi) with the accumulator fragment live) and need no shuffles; one red.add per
+  // (point, row) and CTA.  For small local bases (nb ~ 150) this epilogue moves as many bytes as the K loop.
+  constexpr int X_LD = GM + 2; // (col * X_LD + row): conflict-free for the fragment stores and for the row-wise reads
+  __syncthreads();             // every warp is done reading the last stages
+  {
+    double *Xs = smem;
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi) {
-      double s = 0.0;
+    for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) {
-        s += pc[(ni * 8) * TILE_P + mi * 8] * acc[mi][ni][0];
-        s += pc[(ni * 8 + 1) * TILE_P + mi * 8] * acc[mi][ni][1];
+      for (int mi = 0; mi < 4; ++mi) {
+        double *x = Xs + (wn * 32 + ni * 8 + 2 * tig) * X_LD + wm * 32 + mi * 8 + gid;
+        x[0] = acc[mi][ni][0];
+        x[X_LD] = acc[mi][ni][1];
       }
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (tig == 0) XC_ACC_ADD(P, accp + row * TILE_P + wm * 32 + mi * 8 + gid, s);
+  }
+  __syncthreads();
+  const int p = tid & (TILE_P - 1), half = tid >> 7;
+  const double *Xr = smem + (half * 32) * X_LD + p;
+  double *accp = P.acc + (static_cast<size_t>(it.tile) * P.nspin + it.spin) * NACC * TILE_P;
+  const double *phib = P.scratch + t.scr_off + static_cast<size_t>(n0 + half * 32) * TILE_P + p;
+  double *part = smem + GN * X_LD; // [4][128] partial sums of the upper half
+  if (P.debug & 2) return;
+  if (it.acomp == 0) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (P.ncomp > 1) {
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        const double x = Xr[j * X_LD];
+        const double *q = phib + j * TILE_P;
+        s0 = fma(q[0], x, s0);
+        s1 = fma(q[slab], x, s1);
+        s2 = fma(q[2 * slab], x, s2);
+        s3 = fma(q[3 * slab], x, s3);
+      }
+    } else {
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) s0 = fma(phib[j * TILE_P], Xr[j * X_LD], s0);
     }
+    if (half) {
+      part[p] = s0;
+      part[TILE_P + p] = s1;
+      part[2 * TILE_P + p] = s2;
+      part[3 * TILE_P + p] = s3;
+    }
+    __syncthreads();
+    if (!half) {
+      XC_ACC_ADD(P, accp + p, s0 + part[p]);
+      if (P.ncomp > 1) {
+        XC_ACC_ADD(P, accp + TILE_P + p, s1 + part[TILE_P + p]);
+        XC_ACC_ADD(P, accp + 2 * TILE_P + p, s2 + part[2 * TILE_P + p]);
+        XC_ACC_ADD(P, accp + 3 * TILE_P + p, s3 + part[3 * TILE_P + p]);
+      }
+    }
+  } else { // tau term: rowsum(phi_k o (phi_k D)) accumulates in row 4
+    const double *q = phib + static_cast<size_t>(it.acomp) * slab;
+    double s0 = 0.0;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) s0 = fma(q[j * TILE_P], Xr[j * X_LD], s0);
+    if (half) part[p] = s0;
+    __syncthreads();
+    if (!half) XC_ACC_ADD(P, accp + 4 * TILE_P + p, s0 + part[p]);
   }
 }
 
