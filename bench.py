@@ -441,7 +441,7 @@ def run_b200(args):
         achieved = kern[dom]["tflops"]
         traffic = None
         try:   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(args.workload)
             if tj and tj.get("batch_mb") == args.batch_mb and world == 1:
                 traffic = tj.get("k_vxc_resident" if dom == "vxc" else "k_density")
         except Exception:

@@ -14,7 +14,7 @@ def run(mol, bas, pure, angular, cpu_batches=0, reps=3, radial_precision=1e-5):
     D = molecules.synthetic_density(b, 1) * 0.5
     t0 = time.perf_counter()
     sgx = cosx.SemiNumericalExchange(b, cosx.sgx_grid_settings(angular, radial_precision), collect_stats=True,
-                                     kgemm_library=lib_k)
+                                     )
     t_setup = time.perf_counter() - t0
     K = sgx.compute_K(D)
     info = sgx.info()
@@ -24,7 +24,7 @@ def run(mol, bas, pure, angular, cpu_batches=0, reps=3, radial_precision=1e-5):
     sgx.close()
     # timed handle without the per-pair counters (one atomic per evaluated pair) and without per-chunk event syncs
     sgx = cosx.SemiNumericalExchange(b, atom_grids=(sgx.atom_offsets, sgx.points, sgx.weights),
-                                     projector=sgx.overlap_projector, kgemm_library=lib_k)
+                                     projector=sgx.overlap_projector, )
     sgx.compute_K(D)
     ts = []
     for _ in range(reps):
