@@ -67,39 +67,6 @@ __device__ __forceinline__ void add_seeds(const double *__restrict__ tab, double
                                           double (&S)[L + 1]) {
   const double T = p * r2;
   double F[L + 1];
-#ifndef COSX_BOYS_TABLE_ONLY
-  // L = 0 and L = 1 (the s-s and p-s classes: one or two Boys values per point and primitive, L1-bound on the 64-byte
-  // table rows, FP64 pipe 26 % / 39 % active): closed form instead of the table —
-  //   F_0(T) = sqrt(pi)/2 erf(sqrt T) / sqrt T,   F_1 = (F_0 - e^-T) / (2 T)   (upward step, benign for T >= 1/2)
-  // and the Taylor series sum_k (-T)^k / (k! (2m + 2k + 1)) for small T.  No memory traffic; same values to a few ulp.
-  if (L <= 1 && T < 36.0) {
-    if (L == 0) {
-      if (T < 1e-3) {
-        F[0] = 1.0 + T * (-1.0 / 3.0 + T * (0.1 + T * (-1.0 / 42.0)));
-      } else {
-        const double st = sqrt(T);
-        F[0] = 0.88622692545275801365 * erf(st) / st;
-      }
-    } else if (T < 0.5) {
-      // 15 terms: 0.5^15 / (15! * 33) = 7e-19
-      double f1 = 0.0, f0 = 0.0;
-      double c = 1.0; // (-T)^k / k!
-#pragma unroll
-      for (int k = 0; k < 15; ++k) {
-        f0 = fma(c, 1.0 / (2 * k + 1), f0);
-        f1 = fma(c, 1.0 / (2 * k + 3), f1);
-        c *= -T * (1.0 / (k + 1));
-      }
-      F[0] = f0;
-      F[L] = f1;
-    } else {
-      const double st = sqrt(T);
-      const double f0 = 0.88622692545275801365 * erf(st) / st;
-      F[0] = f0;
-      F[L] = (f0 - exp(-T)) / (2.0 * T);
-    }
-  } else
-#endif
   if (T >= 36.0) {
     const double inv = 1.0 / T;
     double Fm = 0.88622692545275801365 * sqrt(inv);
