@@ -56,6 +56,11 @@ int occ_cosx_compute_K(occ_cosx_handle *h, int kind, const double *D, double pre
  * grid sweep (restricted only, like the reference). */
 int occ_cosx_compute_K_range_separated(occ_cosx_handle *h, const double *D, double alpha, double beta, double omega,
                                        double precision, double *K);
+/* The same with the spinorbital kind of the reference's member (:862-893): kind 0 restricted as above; kind 1
+ * unrestricted — D and K are (2 nbf x nbf), one fused sweep per spin block, each block 0.5 (K' + K'^T); kind 2 (general)
+ * is refused like the reference ("not implemented for general spinorbitals"). */
+int occ_cosx_compute_K_range_separated_kind(occ_cosx_handle *h, int kind, const double *D, double alpha, double beta,
+                                            double omega, double precision, double *K);
 
 /* The same two builds for callers that also hand over the occupied orbitals — the reference's seam receives `mo`
  * (compute_K(const MolecularOrbitals &mo, ...), include/occ/qm/seminumerical_exchange.h:108), which holds mo.D and
@@ -68,6 +73,9 @@ int occ_cosx_compute_K_mo(occ_cosx_handle *h, int kind, const double *D, const d
                           double precision, double omega, double *K);
 int occ_cosx_compute_K_range_separated_mo(occ_cosx_handle *h, const double *D, const double *C, int nocc, double alpha,
                                           double beta, double omega, double precision, double *K);
+int occ_cosx_compute_K_range_separated_mo_kind(occ_cosx_handle *h, int kind, const double *D, const double *C,
+                                               int nocc_alpha, int nocc_beta, double alpha, double beta, double omega,
+                                               double precision, double *K);
 
 /* compute_K_for_density (:817-828): the raw, unsymmetrised K' of one projected density D2q (nbf x nbf); with
  * w_full / w_lr the fused two-operator form. Device-resident variant: pointers are device memory on h's device. */

@@ -22,7 +22,8 @@ SYMBOLS = ["occ_xc_create", "occ_xc_build", "occ_xc_build_device", "occ_xc_build
            "occ_xc_measure_fp64_tensor_peak", "occ_xc_multi_create", "occ_xc_multi_build", "occ_xc_multi_ndev", "occ_xc_multi_get_info", "occ_xc_multi_destroy"]
 # every symbol include/occ_cosx_b200.h declares
 COSX_SYMBOLS = ["occ_cosx_create", "occ_cosx_compute_K", "occ_cosx_compute_K_range_separated", "occ_cosx_compute_K_mo",
-                "occ_cosx_compute_K_range_separated_mo", "occ_cosx_K_for_density",
+                "occ_cosx_compute_K_range_separated_mo", "occ_cosx_compute_K_range_separated_kind",
+                "occ_cosx_compute_K_range_separated_mo_kind", "occ_cosx_K_for_density",
                 "occ_cosx_K_for_density_device", "occ_cosx_numerical_overlap", "occ_cosx_analytic_overlap",
                 "occ_cosx_set_projector", "occ_cosx_get_info", "occ_cosx_destroy"]
 

@@ -164,13 +164,20 @@ class SemiNumericalExchange:
         return K
 
     def compute_K_range_separated(self, D, alpha: float, beta: float, omega: float,
-                                  precision: float = np.finfo(np.float64).eps):
+                                  precision: float = np.finfo(np.float64).eps, unrestricted: bool = False):
+        """compute_K_range_separated (seminumerical_exchange.cpp:830-893): restricted, or unrestricted with the
+        stacked (2 nbf x nbf) D; general spinorbitals are refused like the reference"""
         nbf = self.basis.nbf
         D = np.asfortranarray(D, dtype=np.float64)
-        if D.shape != (nbf, nbf):
-            raise RuntimeError("compute_K_range_separated is restricted only")
-        K = np.zeros((nbf, nbf), order="F")
-        check(lib().occ_cosx_compute_K_range_separated(self._h, ptr(D), alpha, beta, omega, precision, ptr(K)))
+        rows = 2 * nbf if unrestricted else nbf
+        if D.shape != (rows, nbf):
+            raise RuntimeError(f"density matrix has shape {D.shape}, expected {(rows, nbf)}")
+        K = np.zeros((rows, nbf), order="F")
+        L = lib()
+        L.occ_cosx_compute_K_range_separated_kind.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double,
+                                                              C.c_double, C.c_double, C.c_void_p]
+        check(L.occ_cosx_compute_K_range_separated_kind(self._h, 1 if unrestricted else 0, ptr(D), alpha, beta, omega,
+                                                        precision, ptr(K)))
         return K
 
     def compute_K_for_density(self, D2q, precision: float = np.finfo(np.float64).eps):

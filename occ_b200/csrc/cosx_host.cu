@@ -174,6 +174,13 @@ template <class T> static int dev_alloc(occ_cosx_handle *h, T **ptr, size_t coun
   *ptr = static_cast<T *>(p);
   return 0;
 }
+template <class T> static void dev_free(occ_cosx_handle *h, T **ptr) { // a buffer that is being replaced by a larger one
+  if (!*ptr) return;
+  auto it = std::find(h->allocs.begin(), h->allocs.end(), static_cast<void *>(*ptr));
+  if (it != h->allocs.end()) h->allocs.erase(it);
+  cudaFree(*ptr);
+  *ptr = nullptr;
+}
 template <class T> static int dev_upload(occ_cosx_handle *h, T **ptr, const std::vector<T> &v) {
   if (dev_alloc(h, ptr, v.size())) return 1;
   if (!v.empty()) CUDA_TRY(cudaMemcpy(*ptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
@@ -705,6 +712,10 @@ static int compute_K_impl(occ_cosx_handle *h, int kind, const double *D, double 
   if (C) { // orbitals on the device: [C_alpha | C_beta], nbf rows
     const int cap = std::max(1, std::max(nocc_s[0], nocc_s[1]));
     if (cap > h->mo_cap) {
+      CUDA_TRY(cudaStreamSynchronize(st)); // nothing in flight may still read the buffers that are about to go
+      dev_free(h, &h->d_C);
+      dev_free(h, &h->d_Cq);
+      dev_free(h, &h->d_psi);
       if (dev_alloc(h, &h->d_C, 2 * static_cast<size_t>(nbf) * cap) || dev_alloc(h, &h->d_Cq, static_cast<size_t>(nbf) * cap) ||
           dev_alloc(h, &h->d_psi, static_cast<size_t>(h->tiles_per_chunk) * TILE_P * cap))
         return 1;
@@ -766,6 +777,23 @@ int occ_cosx_compute_K_range_separated(occ_cosx_handle *h, const double *D, doub
                                        double precision, double *K) {
   if (!(omega > 0.0)) return fail("occ_cosx_compute_K_range_separated: omega must be > 0");
   return compute_K_impl(h, 0, D, precision, alpha + beta, -beta, omega, K);
+}
+
+int occ_cosx_compute_K_range_separated_kind(occ_cosx_handle *h, int kind, const double *D, double alpha, double beta,
+                                            double omega, double precision, double *K) {
+  if (!(omega > 0.0)) return fail("occ_cosx_compute_K_range_separated: omega must be > 0");
+  if (kind != 0 && kind != 1) // seminumerical_exchange.cpp:862-893 handles Restricted and Unrestricted only
+    return fail("occ_cosx_compute_K_range_separated: not implemented for general spinorbitals");
+  return compute_K_impl(h, kind, D, precision, alpha + beta, -beta, omega, K);
+}
+
+int occ_cosx_compute_K_range_separated_mo_kind(occ_cosx_handle *h, int kind, const double *D, const double *C,
+                                               int nocc_alpha, int nocc_beta, double alpha, double beta, double omega,
+                                               double precision, double *K) {
+  if (!C) return fail("occ_cosx_compute_K_range_separated_mo: null argument");
+  if (!(omega > 0.0)) return fail("occ_cosx_compute_K_range_separated_mo: omega must be > 0");
+  if (kind != 0 && kind != 1) return fail("occ_cosx_compute_K_range_separated_mo: not implemented for general spinorbitals");
+  return compute_K_impl(h, kind, D, precision, alpha + beta, -beta, omega, K, C, nocc_alpha, kind == 1 ? nocc_beta : 0);
 }
 
 int occ_cosx_compute_K_mo(occ_cosx_handle *h, int kind, const double *D, const double *C, int nocc_alpha, int nocc_beta,

@@ -54,14 +54,39 @@ METHOD_DEFINITIONS = {
 RESTRICTED, UNRESTRICTED = "restricted", "unrestricted"
 
 
+def method_definitions() -> dict:
+    """get_method_definitions (src/dft/dft_method.cpp:96-132): `$OCC_DATA_PATH/methods/dft_methods.json`, else
+    `./dft_methods.json`, REPLACES the builtin table when it exists and holds a "methods" object; otherwise the
+    builtin definitions.  Each entry lists components {"id": libxc name, "factor", "hfx"}; like the reference's XC build
+    the component factor is carried but never applied (include/occ/dft/functional.h:506-508)."""
+    import json
+    import os
+    base = os.environ.get("OCC_DATA_PATH", ".")
+    for path in (os.path.join(base, "methods", "dft_methods.json"), "dft_methods.json"):
+        if os.path.exists(path):
+            try:
+                with open(path) as f:
+                    j = json.load(f)
+                if isinstance(j.get("methods"), dict):
+                    return {name: [c["id"] for c in d.get("components", [])] for name, d in j["methods"].items()}
+            except Exception:
+                pass
+            break
+    return METHOD_DEFINITIONS
+
+
 def get_dft_method(method_string: str) -> list[int]:
     """get_dft_method (src/dft/dft_method.cpp:161-227): space-separated tokens, each a method name or a libxc
     functional name; a leading 'u' marks the polarized variant (the spin kind is chosen by the caller here)."""
     ids = []
+    defs = method_definitions()
     for token in method_string.strip().lower().split():
-        m = token[1:] if token.startswith("u") and token[1:] in METHOD_DEFINITIONS else token
-        if m in METHOD_DEFINITIONS:
-            ids += [FUNCTIONAL_IDS[c] for c in METHOD_DEFINITIONS[m]]
+        m = token[1:] if token.startswith("u") and token[1:] in defs else token
+        if m in defs:
+            missing = [c for c in defs[m] if c not in FUNCTIONAL_IDS]
+            if missing:
+                raise RuntimeError(f"functional {missing[0]} not found")   # functional.cpp:32 analogue
+            ids += [FUNCTIONAL_IDS[c] for c in defs[m]]
         elif m in FUNCTIONAL_IDS:
             ids.append(FUNCTIONAL_IDS[m])
         else:

@@ -154,6 +154,15 @@ def test_cosx_long_range_and_fused_range_separated(oracle):
     assert np.abs(Klr).max() < np.abs(Kf).max()       # erf attenuates (tests/dft_tests.cpp:392-394)
     Kfused = sgx.compute_K_range_separated(D, alpha, beta, omega)
     assert np.abs(Kfused - ((alpha + beta) * Kf - beta * Klr)).max() < 1e-10   # tests/dft_tests.cpp:452-456
+    # unrestricted range-separated build (seminumerical_exchange.cpp:881-893): two fused sweeps, one per spin block
+    Du = np.asfortranarray(np.vstack([0.6 * D, 0.4 * D.T @ np.eye(b.nbf)]))
+    Ku_full = sgx.compute_K(Du, unrestricted=True)
+    sgx.set_range_separated_omega(omega)
+    Ku_lr = sgx.compute_K(Du, unrestricted=True)
+    sgx.set_range_separated_omega(0.0)
+    Ku_fused = sgx.compute_K_range_separated(Du, alpha, beta, omega, unrestricted=True)
+    assert Ku_fused.shape == (2 * b.nbf, b.nbf)
+    assert np.abs(Ku_fused - ((alpha + beta) * Ku_full - beta * Ku_lr)).max() < 1e-10
     sgx.close()
 
 

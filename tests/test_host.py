@@ -149,3 +149,27 @@ def test_device_functionals_on_host_lithium_atom():
         o = _device_functional_on_host(dft.FUNCTIONAL_IDS[func], True, fam, rho[keep], sigma[keep], tau[keep])
         got = float((o["exc"] * rho.sum(1)[keep] * vol[keep]).sum())
         assert abs(got - want) < 1.5e-4, (func, got, want)
+
+
+def test_dft_methods_json_overrides_the_builtin_table(tmp_path, monkeypatch):
+    """get_method_definitions (src/dft/dft_method.cpp:96-132): share/methods/dft_methods.json under OCC_DATA_PATH
+    replaces the builtin table; components this library does not implement fail with the reference's message"""
+    import json
+    from occ_b200 import dft
+    (tmp_path / "methods").mkdir()
+    (tmp_path / "methods" / "dft_methods.json").write_text(json.dumps({"methods": {
+        "mypbe": {"components": [{"id": "gga_x_b88"}, {"id": "gga_c_pbe", "factor": 0.5}]},
+        "bp86": {"components": [{"id": "gga_x_b88"}, {"id": "gga_c_p86"}]}}}))
+    assert dft.get_dft_method("pbe") == [101, 130]                      # builtin, no OCC_DATA_PATH file
+    monkeypatch.setenv("OCC_DATA_PATH", str(tmp_path))
+    assert dft.get_dft_method("mypbe") == [106, 130]
+    assert dft.get_dft_method("gga_x_pbe") == [101]                     # plain libxc names still resolve
+    with pytest.raises(RuntimeError):
+        dft.get_dft_method("pbe")                                       # the file REPLACES the builtin table
+    with pytest.raises(RuntimeError, match="gga_c_p86 not found"):
+        dft.get_dft_method("bp86")
+    # the reference's own share/methods file parses (when the reference tree is present in this container)
+    ref = "/root/reference/share"
+    if os.path.exists(os.path.join(ref, "methods", "dft_methods.json")):
+        monkeypatch.setenv("OCC_DATA_PATH", ref)
+        assert dft.get_dft_method("b3lyp") == [402] and dft.get_dft_method("wb97x") == [464]
