@@ -213,7 +213,12 @@ def run_reference(args):
     ob, spts, sw, leaves = oracle_grid(basis, quality)
     t_grid = time.perf_counter() - t0
     npts = len(sw)
-    # normalise the synthetic density to N_electrons like the GPU arm does (linear in D): estimated from a thin sample
+    # scale the synthetic density to N_electrons like the GPU arm does (the count is linear in D); here the integral is
+    # estimated from every 16th leaf, which fixes the magnitude of the input to a fraction of a percent
+    thin = leaves[::16]
+    r0 = O.xc_build(ob, spts, sw, thin, names, nspin, D2)
+    n_est = (r0["n_alpha"] + (r0["n_beta"] if nspin == 2 else 0.0)) * len(leaves) / max(1, len(thin))
+    D2 = np.asfortranarray(D2 * (float(basis.num_electrons()) / n_est))
     nsteps = args.steps + args.warmup
     budget = 170.0
     res = cpu_build_sample(ob, spts, sw, leaves, names, nspin, D2, target_seconds=max(1.0, min(20.0, budget / nsteps)),
