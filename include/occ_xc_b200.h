@@ -183,6 +183,19 @@ int occ_xc_density_on_grid(occ_xc_handle *h, const double *D2, double *rho);
 int occ_xc_vv10(occ_xc_handle *h, const double *D2, const size_t *orig_index, double vv10_b, double vv10_C, double *K,
                 double *energy);
 
+/* VV10 nuclear gradient, NonLocalCorrelationFunctional::vv10_gradient (src/dft/nonlocal_correlation.cpp:392-522; added to
+ * the XC gradient by DFT::compute_xc_gradient, src/dft/dft_gradients.cpp:103-104 -> include/occ/dft/dft.h:488-495).
+ * Post-SCF, restricted, no SCF response — as the reference.  Two terms:
+ *   potential  the restricted GGA gradient matrices V_x, V_y, V_z built from the VV10 vrho / vsigma (:462-496) and
+ *              distributed with Dval = 2 mo.D (:499-512; the |Dval| < 1e-12 skip is not applied);
+ *   grid       compute_vv10_grid_displacement_gradient (:193-328): every ordered pair of points of DIFFERENT atoms
+ *              within 15 Bohr with rho >= 1e-8 on both sides.
+ * The handle is created like for occ_xc_vv10 plus options.gradient = 1 and basis->shell_atom.
+ *   atom_offsets [natoms + 1]: point ranges of the reference's concatenated NLC atom grids (reference order, the
+ *              order orig_index maps to);  gradient 3 x natoms column-major (Mat3N), overwritten;  energy may be NULL. */
+int occ_xc_vv10_gradient(occ_xc_handle *h, const double *D2, const size_t *orig_index, const size_t *atom_offsets,
+                         double vv10_b, double vv10_C, double *gradient, double *energy);
+
 /* occ_xc_gradient with the occupied orbitals as well (D2_s = C_s C_s^T, C packed as in occ_xc_build_mo): the density and
  * the A . D^T products of the gradient run in the factorised form where cheaper.  Same gradient to rounding. */
 int occ_xc_gradient_mo(occ_xc_handle *h, const double *D2, const double *C, double *gradient);
@@ -227,6 +240,13 @@ int occ_xc_multi_build(occ_xc_multi *m, const double *D2, const double *C, doubl
 int occ_xc_multi_ndev(const occ_xc_multi *m);
 int occ_xc_multi_get_info(const occ_xc_multi *m, int rank, occ_xc_info_t *info); /* the shard of handle `rank` */
 void occ_xc_multi_destroy(occ_xc_multi *m);
+/* occ_xc_vv10 / occ_xc_vv10_gradient over the shards of a multi handle created on the NLC grid (same arguments and
+ * results): every GPU evaluates rho / grad rho on its leaves, gathers the other points' arrays from its peers, runs
+ * 1/ndev of the O(N^2) pair work, and the partial pair sums / K panels / gradients are summed in rank order. */
+int occ_xc_multi_vv10(occ_xc_multi *m, const double *D2, const size_t *orig_index, double vv10_b, double vv10_C, double *K,
+                      double *energy);
+int occ_xc_multi_vv10_gradient(occ_xc_multi *m, const double *D2, const size_t *orig_index, const size_t *atom_offsets,
+                               double vv10_b, double vv10_C, double *gradient, double *energy);
 
 
 /* Per-phase device times (ms, CUDA events on the build stream) of the LAST build when profiling is on.

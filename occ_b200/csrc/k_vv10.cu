@@ -16,14 +16,42 @@ namespace xcb {
 constexpr int VV_JCHUNK = 32; // j-blocks (of 128 points) per work item
 
 // every point starts inactive: points of leaves that keep no shell (dropped at create, dft.h:309-321) have no tile
-__global__ void k_vv10_init(VV10Params V) {
+// `unowned` is the kappa written for them: -1 (inactive) on a handle that holds the whole grid, 0 ("not this rank's point":
+// resolved by k_vv10_merge) on a shard of a multi-GPU call
+__global__ void k_vv10_init(VV10Params V, double unowned) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= V.n) return;
   V.X[i] = V.Y[i] = V.Z[i] = 0.0;
   V.rw2[i] = 0.0;
   V.om[i] = 1.0;
-  V.kap[i] = -1.0;
+  V.kap[i] = unowned;
   V.F[i] = V.U[i] = V.W[i] = 0.0;
+}
+
+// multi-GPU: every point is owned by at most one shard (the one whose kappa is non-zero); gather its six values
+__global__ void k_vv10_merge(VV10Peers src, VV10Params out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= out.n) return;
+  double x = 0.0, y = 0.0, z = 0.0, rw = 0.0, om = 1.0, kp = -1.0;
+  for (int r = 0; r < src.n; ++r) {
+    const double *b = src.base[r]; // X Y Z rw2 om kap, each of length n
+    const double k = b[5 * out.n + i];
+    if (k != 0.0) {
+      x = b[i];
+      y = b[out.n + i];
+      z = b[2 * out.n + i];
+      rw = b[3 * out.n + i];
+      om = b[4 * out.n + i];
+      kp = k;
+      break;
+    }
+  }
+  out.X[i] = x;
+  out.Y[i] = y;
+  out.Z[i] = z;
+  out.rw2[i] = rw;
+  out.om[i] = om;
+  out.kap[i] = kp;
 }
 
 __global__ void __launch_bounds__(TILE_P) k_vv10_prepare(BuildParams P, VV10Params V) {
@@ -187,8 +215,172 @@ __global__ void __launch_bounds__(TILE_P) k_vv10_coef(BuildParams P, VV10Params 
   }
 }
 
-void launch_vv10_prepare(const BuildParams &P, const VV10Params &V, int ntiles, void *stream) {
-  k_vv10_init<<<static_cast<unsigned>((V.n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(V);
+// ------------------------------------------------------------------------------------------------
+// VV10 nuclear gradient, grid-displacement term (compute_vv10_grid_displacement_gradient,
+// nonlocal_correlation.cpp:193-328).  The reference visits every ordered pair (i, j != i) within 15 Bohr and does
+//   grad[atom(i)] -= f_ij,  grad[atom(j)] += f_ij,   f_ij = 2 dPhi/dr^2 (r_i - r_j);
+// f_ji = -f_ij, so the total is  grad[a] = -2 sum_{i in a} sum_j f_ij  and pairs on the same atom cancel (skipped
+// here).  Thread = point i, the j side staged through shared memory, one reciprocal per pair:
+//   f_ij = 3 (rho_i w_i) * [ (2 rho_j w_j) dD / (g_i g_j (g_i + g_j))^2 ] (r_i - r_j),
+//   dD   = 2 om_i (g_j s + g_i g_j) + 2 om_j (g_i s + g_i g_j),  s = g_i + g_j.
+// "sqrt(r2) > 15" is `r2 > 225` exactly (only r2 == 225 rounds to 15).  The |denom| < 1e-20 guard of the reference
+// cannot fire (g >= kappa >= kappa(1e-8) > 0.1 for active points) and is not evaluated.  j-blocks whose bounding box is
+// farther than the cut-off from the i-block's are skipped as a whole.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_vv10_point_atoms(size_t n, int natoms, const size_t *__restrict__ atom_offsets, int *__restrict__ pt_atom) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int lo = 0, hi = natoms; // largest a with atom_offsets[a] <= i
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (atom_offsets[mid] <= i) lo = mid;
+    else hi = mid;
+  }
+  pt_atom[i] = lo;
+}
+
+// bounding box of the ACTIVE points of each block of 128 (empty box: lo = +inf)
+__global__ void __launch_bounds__(TILE_P) k_vv10_bbox(VV10Params V) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * TILE_P + threadIdx.x;
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  double lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+  if (i < V.n && V.kap[i] > 0.0) {
+    lo[0] = hi[0] = V.X[i];
+    lo[1] = hi[1] = V.Y[i];
+    lo[2] = hi[2] = V.Z[i];
+  }
+  __shared__ double red[6][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[d] = fmin(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+      hi[d] = fmax(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+    }
+    if (lane == 0) {
+      red[d][warp] = lo[d];
+      red[3 + d][warp] = hi[d];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int d = threadIdx.x;
+    V.bbox[6 * static_cast<size_t>(blockIdx.x) + d] = fmin(fmin(red[d][0], red[d][1]), fmin(red[d][2], red[d][3]));
+    V.bbox[6 * static_cast<size_t>(blockIdx.x) + 3 + d] =
+        fmax(fmax(red[3 + d][0], red[3 + d][1]), fmax(red[3 + d][2], red[3 + d][3]));
+  }
+}
+
+// work item = (i-block bi, j-chunk): j-blocks [jc*VV_JCHUNK, min((jc+1)*VV_JCHUNK, nblk)) — the full square
+__global__ void __launch_bounds__(TILE_P) k_vv10_grid_pairs(VV10Params V, const int2 *__restrict__ items, int nblk) {
+  __shared__ double sx[TILE_P], sy[TILE_P], sz[TILE_P], srw[TILE_P], som[TILE_P], skp[TILE_P];
+  __shared__ int sat[TILE_P];
+  const int2 it = items[blockIdx.x];
+  const int bi = it.x, tid = threadIdx.x;
+  const size_t i = static_cast<size_t>(bi) * TILE_P + tid;
+  const bool ivalid = i < V.n;
+  double xi = 0, yi = 0, zi = 0, omi = 1, kpi = -1;
+  int ati = -1;
+  if (ivalid) {
+    xi = V.X[i];
+    yi = V.Y[i];
+    zi = V.Z[i];
+    omi = V.om[i];
+    kpi = V.kap[i];
+    ati = V.pt_atom[i];
+  }
+  const bool active = kpi > 0.0;
+  if (!active) kpi = 1.0;
+  double bl[3], bh[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    bl[d] = V.bbox[6 * static_cast<size_t>(bi) + d];
+    bh[d] = V.bbox[6 * static_cast<size_t>(bi) + 3 + d];
+  }
+  if (!(bl[0] <= bh[0])) return; // no active point in this block
+  double fx = 0.0, fy = 0.0, fz = 0.0;
+  const int jb0 = it.y * VV_JCHUNK, jb1 = min(jb0 + VV_JCHUNK, nblk);
+  for (int jb = jb0; jb < jb1; ++jb) {
+    double d2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double jl = V.bbox[6 * static_cast<size_t>(jb) + d], jh = V.bbox[6 * static_cast<size_t>(jb) + 3 + d];
+      const double gap = fmax(0.0, fmax(bl[d] - jh, jl - bh[d]));
+      d2 += gap * gap; // +inf for an empty j box
+    }
+    if (!(d2 <= 225.0)) continue; // every pair of the two blocks is beyond the cut-off (uniform over the CTA)
+    const size_t j = static_cast<size_t>(jb) * TILE_P + tid;
+    __syncthreads();
+    if (j < V.n) {
+      sx[tid] = V.X[j];
+      sy[tid] = V.Y[j];
+      sz[tid] = V.Z[j];
+      srw[tid] = V.rw2[j];
+      som[tid] = V.om[j];
+      skp[tid] = fabs(V.kap[j]);
+      sat[tid] = V.pt_atom[j];
+    } else {
+      sx[tid] = sy[tid] = sz[tid] = 0.0;
+      srw[tid] = 0.0;
+      som[tid] = skp[tid] = 1.0;
+      sat[tid] = -2;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int jj = 0; jj < TILE_P; ++jj) {
+      const double dx = xi - sx[jj], dy = yi - sy[jj], dz = zi - sz[jj];
+      const double r2 = dx * dx + dy * dy + dz * dz;
+      const double gi = fma(r2, omi, kpi), gj = fma(r2, som[jj], skp[jj]);
+      const double s = gi + gj, gg = gi * gj;
+      const double inv = 1.0 / (gg * s);
+      const double dD = 2.0 * omi * fma(gj, s, gg) + 2.0 * som[jj] * fma(gi, s, gg);
+      double t = srw[jj] * dD * (inv * inv);
+      if (r2 > 225.0 || sat[jj] == ati) t = 0.0; // beyond the cut-off / same atom (cancels, also covers j == i)
+      fx = fma(t, dx, fx);
+      fy = fma(t, dy, fy);
+      fz = fma(t, dz, fz);
+    }
+  }
+  if (ivalid && active) {
+    const double c = 1.5 * V.rw2[i]; // 3 rho_i w_i
+    atomicAdd(V.GX + i, c * fx);
+    atomicAdd(V.GY + i, c * fy);
+    atomicAdd(V.GZ + i, c * fz);
+  }
+}
+
+// grad[atom(i)] -= 2 f_i
+__global__ void k_vv10_grid_reduce(VV10Params V, double *__restrict__ grad) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= V.n) return;
+  const double gx = V.GX[i], gy = V.GY[i], gz = V.GZ[i];
+  if (gx == 0.0 && gy == 0.0 && gz == 0.0) return;
+  const int a = V.pt_atom[i];
+  atomicAdd(grad + 3 * a, -2.0 * gx);
+  atomicAdd(grad + 3 * a + 1, -2.0 * gy);
+  atomicAdd(grad + 3 * a + 2, -2.0 * gz);
+}
+
+void launch_vv10_point_atoms(const VV10Params &V, int natoms, const size_t *atom_offsets_dev, void *stream) {
+  k_vv10_point_atoms<<<static_cast<unsigned>((V.n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      V.n, natoms, atom_offsets_dev, V.pt_atom);
+}
+void launch_vv10_grid_pairs(const VV10Params &V, const int2 *items, int nitems, void *stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nblk = static_cast<int>((V.n + TILE_P - 1) / TILE_P);
+  k_vv10_bbox<<<nblk, TILE_P, 0, st>>>(V);
+  if (nitems > 0) k_vv10_grid_pairs<<<nitems, TILE_P, 0, st>>>(V, items, nblk);
+}
+void launch_vv10_grid_reduce(const VV10Params &V, double *grad, void *stream) {
+  k_vv10_grid_reduce<<<static_cast<unsigned>((V.n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(V, grad);
+}
+void launch_vv10_merge(const VV10Peers &src, const VV10Params &out, void *stream) {
+  k_vv10_merge<<<static_cast<unsigned>((out.n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, out);
+}
+
+void launch_vv10_prepare(const BuildParams &P, const VV10Params &V, int ntiles, double unowned, void *stream) {
+  k_vv10_init<<<static_cast<unsigned>((V.n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(V, unowned);
   if (ntiles > 0) k_vv10_prepare<<<ntiles, TILE_P, 0, static_cast<cudaStream_t>(stream)>>>(P, V);
 }
 void launch_vv10_pairs(const VV10Params &V, const int2 *items, int nitems, void *stream) {

@@ -64,7 +64,21 @@ struct occ_xc_handle {
   int2 *d_vv_items = nullptr;
   int n_vv_items = 0;
   size_t *d_vv_orig = nullptr;
+  xcb::BuildParams vvP;           // build parameters of the running VV10 call (D pointers set by the density stage)
+  int2 *d_vv_grid_items = nullptr; // full-square work list of the gradient's grid-displacement term
+  int n_vv_grid_items = 0;
+  size_t *d_vv_atom_off = nullptr;
 };
+
+// post-SCF VV10 in stages (xc_host.cu); every stage only enqueues on h->stream
+int vv10_check_handle(occ_xc_handle *h, const char *who, bool gradient);
+int vv10_setup(occ_xc_handle *h, int part, int nparts);
+int vv10_setup_gradient(occ_xc_handle *h, int part, int nparts, const size_t *atom_offsets);
+int vv10_stage_density(occ_xc_handle *h, const double *D2, const size_t *orig_index, double vv10_b, double vv10_C,
+                       double unowned, bool with_transpose);
+int vv10_stage_pairs(occ_xc_handle *h, const xcb::VV10Params &in);
+int vv10_stage_vxc(occ_xc_handle *h, const xcb::VV10Params &sums);
+int vv10_stage_gradient(occ_xc_handle *h, const xcb::VV10Params &merged, const xcb::VV10Params &sums);
 
 
 // one build on device buffers (xc_host.cu); D2_dev may be NULL when C_dev is given (D2 = C C^T formed on the device)

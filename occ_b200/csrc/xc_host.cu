@@ -1029,42 +1029,77 @@ int occ_xc_density_on_grid(occ_xc_handle *h, const double *D2, double *rho) {
   return 0;
 }
 
-int occ_xc_vv10(occ_xc_handle *h, const double *D2, const size_t *orig_index, double vv10_b, double vv10_C, double *K,
-                double *energy) {
-  if (!h || !D2 || !K || !energy) return fail("occ_xc_vv10: null argument");
-  if (h->nspin != 1)
-    return fail("Only restricted NLC functional implemented right now"); // nonlocal_correlation.cpp:370-372
-  if (h->deriv != 1) return fail("occ_xc_vv10: the handle must be created with a GGA functional list (rho and grad rho)");
-  if (h->world != 1) return fail("occ_xc_vv10: the handle must hold the whole NLC grid (world_size 1)");
-  CUDA_TRY(cudaSetDevice(h->device));
+} // extern "C"
+
+// ---- post-SCF VV10 in stages (shared by the single-handle entries below and occ_xc_multi_vv10* in xc_multi.cu) ----
+// first use: per-point arrays in the reference's order + this shard's slice of the triangular work list
+int vv10_setup(occ_xc_handle *h, int part, int nparts) {
+  if (ensure_tile_src(h)) return 1;
+  if (h->vv.X) return 0;
+  const size_t n = h->npts_total;
+  double *buf = nullptr;
+  if (dev_alloc(h, &buf, 9 * n) || dev_alloc(h, &h->d_vv_orig, n)) return 1;
+  h->vv.n = n;
+  h->vv.tile_src = h->d_tile_src;
+  h->vv.X = buf;
+  h->vv.Y = buf + n;
+  h->vv.Z = buf + 2 * n;
+  h->vv.rw2 = buf + 3 * n;
+  h->vv.om = buf + 4 * n;
+  h->vv.kap = buf + 5 * n;
+  h->vv.F = buf + 6 * n;
+  h->vv.U = buf + 7 * n;
+  h->vv.W = buf + 8 * n;
+  std::vector<int2> items;
+  const int nblk = static_cast<int>((n + TILE_P - 1) / TILE_P), jc = vv10_jchunk();
+  size_t k = 0;
+  for (int bi = nblk - 1; bi >= 0; --bi) // longest rows first; dealt round-robin to the shards of a multi-GPU call
+    for (int c = 0; c * jc <= bi; ++c, ++k)
+      if (static_cast<int>(k % nparts) == part) items.push_back(make_int2(bi, c));
+  h->n_vv_items = static_cast<int>(items.size());
+  if (dev_alloc(h, &h->d_vv_items, items.size())) return 1;
+  CUDA_TRY(cudaMemcpy(h->d_vv_items, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// gradient extras: per-point force accumulators, point -> atom map, block boxes, the full-square work list
+int vv10_setup_gradient(occ_xc_handle *h, int part, int nparts, const size_t *atom_offsets) {
+  const size_t n = h->npts_total;
+  const int nblk = static_cast<int>((n + TILE_P - 1) / TILE_P), jc = vv10_jchunk();
+  if (!h->vv.GX) {
+    double *buf = nullptr;
+    if (dev_alloc(h, &buf, 3 * n) || dev_alloc(h, &h->vv.pt_atom, n) || dev_alloc(h, &h->vv.bbox, 6 * static_cast<size_t>(nblk)) ||
+        dev_alloc(h, &h->d_vv_atom_off, static_cast<size_t>(h->natoms) + 1))
+      return 1;
+    h->vv.GX = buf;
+    h->vv.GY = buf + n;
+    h->vv.GZ = buf + 2 * n;
+    std::vector<int2> items;
+    size_t k = 0;
+    for (int bi = 0; bi < nblk; ++bi)
+      for (int c = 0; c * jc < nblk; ++c, ++k)
+        if (static_cast<int>(k % nparts) == part) items.push_back(make_int2(bi, c));
+    h->n_vv_grid_items = static_cast<int>(items.size());
+    if (dev_alloc(h, &h->d_vv_grid_items, items.size())) return 1;
+    CUDA_TRY(cudaMemcpy(h->d_vv_grid_items, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  }
+  if (atom_offsets[0] != 0 || atom_offsets[h->natoms] != n)
+    return fail("occ_xc_vv10_gradient: atom_offsets must run from 0 to the number of NLC grid points");
+  CUDA_TRY(cudaMemcpyAsync(h->d_vv_atom_off, atom_offsets, (static_cast<size_t>(h->natoms) + 1) * sizeof(size_t),
+                           cudaMemcpyHostToDevice, h->stream));
+  launch_vv10_point_atoms(h->vv, h->natoms, h->d_vv_atom_off, h->stream);
+  return 0;
+}
+
+// D2 (host) -> device, rho / grad rho on this handle's tiles, per-point arrays of ITS points into h->vv (reference order)
+int vv10_stage_density(occ_xc_handle *h, const double *D2, const size_t *orig_index, double vv10_b, double vv10_C,
+                       double unowned, bool with_transpose) {
   cudaStream_t st = h->stream;
-  BuildParams P = h->P;
+  BuildParams &P = h->vvP;
+  P = h->P;
   const size_t n = h->npts_total;
   const size_t ksz = static_cast<size_t>(h->nbf) * h->nbf;
-  if (ensure_tile_src(h)) return 1;
-  if (!h->vv.X) { // first use: per-point arrays in the reference's order + the triangular work list
-    double *buf = nullptr;
-    if (dev_alloc(h, &buf, 9 * n) || dev_alloc(h, &h->d_vv_orig, n)) return 1;
-    h->vv.n = n;
-    h->vv.tile_src = h->d_tile_src;
-    h->vv.X = buf;
-    h->vv.Y = buf + n;
-    h->vv.Z = buf + 2 * n;
-    h->vv.rw2 = buf + 3 * n;
-    h->vv.om = buf + 4 * n;
-    h->vv.kap = buf + 5 * n;
-    h->vv.F = buf + 6 * n;
-    h->vv.U = buf + 7 * n;
-    h->vv.W = buf + 8 * n;
-    std::vector<int2> items;
-    const int nblk = static_cast<int>((n + TILE_P - 1) / TILE_P), jc = vv10_jchunk();
-    for (int bi = nblk - 1; bi >= 0; --bi) // longest rows first
-      for (int c = 0; c * jc <= bi; ++c) items.push_back(make_int2(bi, c));
-    h->n_vv_items = static_cast<int>(items.size());
-    if (dev_alloc(h, &h->d_vv_items, items.size())) return 1;
-    CUDA_TRY(cudaMemcpy(h->d_vv_items, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice));
-  }
-  VV10Params V = h->vv;
+  VV10Params &V = h->vv;
   if (orig_index) {
     CUDA_TRY(cudaMemcpyAsync(h->d_vv_orig, orig_index, n * sizeof(size_t), cudaMemcpyHostToDevice, st));
     V.orig = h->d_vv_orig;
@@ -1079,7 +1114,10 @@ int occ_xc_vv10(occ_xc_handle *h, const double *D2, const size_t *orig_index, do
   launch_prepare_density(h->d_D, h->d_Dsym, h->nbf, 1, st);
   P.Drho[0] = h->d_Dsym;
   P.Dtau[0] = h->d_D;
-  CUDA_TRY(cudaMemsetAsync(h->d_Ktmp, 0, ksz * sizeof(double), st));
+  if (with_transpose) {
+    launch_transpose(h->d_D, h->d_DT, h->nbf, P.ldD, st);
+    P.DT[0] = h->d_DT;
+  }
   // pass 1: rho, grad rho on every tile (the accumulators persist across batches)
   for (const Batch &b : h->batches) {
     launch_collocate(P, h->d_colloc + b.colloc_off, static_cast<int>(b.ncolloc), st);
@@ -1087,8 +1125,30 @@ int occ_xc_vv10(occ_xc_handle *h, const double *D2, const size_t *orig_index, do
                              static_cast<size_t>(b.ntiles) * NACC * TILE_P * sizeof(double), st));
     launch_density(P, h->d_dens + b.dens_off, static_cast<int>(b.ndens), st);
   }
-  launch_vv10_prepare(P, V, h->ntiles, st);
-  launch_vv10_pairs(V, h->d_vv_items, h->n_vv_items, st);
+  launch_vv10_prepare(P, V, h->ntiles, unowned, st);
+  return 0;
+}
+
+// pair sums of this handle's work items: reads X..kap of `in`, accumulates into F, U, W of h->vv
+int vv10_stage_pairs(occ_xc_handle *h, const xcb::VV10Params &in) {
+  VV10Params V = in;
+  V.F = h->vv.F;
+  V.U = h->vv.U;
+  V.W = h->vv.W;
+  launch_vv10_pairs(V, h->d_vv_items, h->n_vv_items, h->stream);
+  return 0;
+}
+
+// coefficients from the (summed) F, U, W of `sums`, then the Vxc contraction into h->d_K / h->d_scalars
+int vv10_stage_vxc(occ_xc_handle *h, const xcb::VV10Params &sums) {
+  cudaStream_t st = h->stream;
+  const BuildParams &P = h->vvP;
+  const size_t ksz = static_cast<size_t>(h->nbf) * h->nbf;
+  VV10Params V = h->vv;
+  V.F = sums.F;
+  V.U = sums.U;
+  V.W = sums.W;
+  CUDA_TRY(cudaMemsetAsync(h->d_Ktmp, 0, ksz * sizeof(double), st));
   launch_vv10_coef(P, V, h->nleaves, st);
   // pass 2: Vxc contraction with the VV10 coefficients (AO values are recomputed: one batch of workspace)
   for (const Batch &b : h->batches) {
@@ -1096,12 +1156,96 @@ int occ_xc_vv10(occ_xc_handle *h, const double *D2, const size_t *orig_index, do
     launch_vxc_resident(P, h->d_vxc + b.vxc_off, static_cast<int>(b.nvxc), st);
   }
   launch_finalize(P, h->nleaves, h->d_K, h->d_scalars, st);
+  return 0;
+}
+
+// coefficients, then the potential term of the gradient (the restricted GGA gradient matrices of
+// nonlocal_correlation.cpp:462-512 with Dval = 2 mo.D = D2, i.e. HALF the weight of the XC gradient's distribution loop)
+// and this handle's share of the grid-displacement term, into h->d_grad; energy into h->d_scalars[0]
+int vv10_stage_gradient(occ_xc_handle *h, const xcb::VV10Params &merged, const xcb::VV10Params &sums) {
+  cudaStream_t st = h->stream;
+  BuildParams P = h->vvP;
+  P.grad_factor = -1.0;
+  VV10Params V = h->vv;
+  V.F = sums.F;
+  V.U = sums.U;
+  V.W = sums.W;
+  CUDA_TRY(cudaMemsetAsync(h->d_grad, 0, 3 * static_cast<size_t>(h->natoms) * sizeof(double), st));
+  CUDA_TRY(cudaMemsetAsync(h->vv.GX, 0, 3 * h->vv.n * sizeof(double), st));
+  launch_vv10_coef(P, V, h->nleaves, st);
+  for (const Batch &b : h->batches) {
+    if (h->batches.size() > 1) launch_collocate(P, h->d_colloc + b.colloc_off, static_cast<int>(b.ncolloc), st);
+    launch_gbuild(P, h->d_g + b.g_off, static_cast<int>(b.ng), st);
+    launch_collocate_h(P, h->d_colloc + b.colloc_off, static_cast<int>(b.ncolloc), st);
+    launch_grad_gemm(P, h->d_gradit + b.grad_off, static_cast<int>(b.ngrad), st);
+  }
+  launch_finalize(P, h->nleaves, h->d_K, h->d_scalars, st); // leaf energy sums -> d_scalars[0] (K is not used)
+  VV10Params G = merged; // X..kap of the whole grid; force accumulators / boxes / atoms of this handle
+  G.GX = h->vv.GX;
+  G.GY = h->vv.GY;
+  G.GZ = h->vv.GZ;
+  G.pt_atom = h->vv.pt_atom;
+  G.bbox = h->vv.bbox;
+  launch_vv10_grid_pairs(G, h->d_vv_grid_items, h->n_vv_grid_items, st);
+  launch_vv10_grid_reduce(G, h->d_grad, st);
+  return 0;
+}
+
+static int vv10_check(occ_xc_handle *h, const char *who, bool gradient) {
+  if (h->nspin != 1)
+    return fail("Only restricted NLC functional implemented right now"); // nonlocal_correlation.cpp:370-372
+  if (h->deriv != 1)
+    return fail((std::string(who) + ": the handle must be created with a GGA functional list (rho and grad rho)").c_str());
+  if (gradient && !h->gradient)
+    return fail((std::string(who) + ": handle was created without the gradient option").c_str());
+  return 0;
+}
+int vv10_check_handle(occ_xc_handle *h, const char *who, bool gradient) { return vv10_check(h, who, gradient); }
+
+extern "C" {
+
+int occ_xc_vv10(occ_xc_handle *h, const double *D2, const size_t *orig_index, double vv10_b, double vv10_C, double *K,
+                double *energy) {
+  if (!h || !D2 || !K || !energy) return fail("occ_xc_vv10: null argument");
+  if (vv10_check(h, "occ_xc_vv10", false)) return 1;
+  if (h->world != 1)
+    return fail("occ_xc_vv10: the handle must hold the whole NLC grid (world_size 1; several GPUs: occ_xc_multi_vv10)");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const size_t ksz = static_cast<size_t>(h->nbf) * h->nbf;
+  if (vv10_setup(h, 0, 1)) return 1;
+  if (vv10_stage_density(h, D2, orig_index, vv10_b, vv10_C, -1.0, false)) return 1;
+  if (vv10_stage_pairs(h, h->vv)) return 1;
+  if (vv10_stage_vxc(h, h->vv)) return 1;
   CUDA_TRY(cudaMemcpyAsync(K, h->d_K, ksz * sizeof(double), cudaMemcpyDeviceToHost, st));
   double sc[3];
   CUDA_TRY(cudaMemcpyAsync(sc, h->d_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   CUDA_TRY(cudaGetLastError());
   *energy = sc[0];
+  return 0;
+}
+
+int occ_xc_vv10_gradient(occ_xc_handle *h, const double *D2, const size_t *orig_index, const size_t *atom_offsets,
+                         double vv10_b, double vv10_C, double *gradient, double *energy) {
+  if (!h || !D2 || !atom_offsets || !gradient) return fail("occ_xc_vv10_gradient: null argument");
+  if (vv10_check(h, "occ_xc_vv10_gradient", true)) return 1;
+  if (h->world != 1)
+    return fail("occ_xc_vv10_gradient: the handle must hold the whole NLC grid (world_size 1; several GPUs: "
+                "occ_xc_multi_vv10_gradient)");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  if (vv10_setup(h, 0, 1) || vv10_setup_gradient(h, 0, 1, atom_offsets)) return 1;
+  if (vv10_stage_density(h, D2, orig_index, vv10_b, vv10_C, -1.0, true)) return 1;
+  if (vv10_stage_pairs(h, h->vv)) return 1;
+  if (vv10_stage_gradient(h, h->vv, h->vv)) return 1;
+  CUDA_TRY(cudaMemcpyAsync(gradient, h->d_grad, 3 * static_cast<size_t>(h->natoms) * sizeof(double),
+                           cudaMemcpyDeviceToHost, st));
+  double sc[3];
+  CUDA_TRY(cudaMemcpyAsync(sc, h->d_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  if (energy) *energy = sc[0];
   return 0;
 }
 

@@ -123,6 +123,15 @@ struct VV10Params {
   double *om, *kap;       // omega_0, kappa (kappa < 0 marks an inactive point)
   double *F, *U, *W;      // pair sums
   double kappa_factor, beta, C;
+  // nuclear gradient, grid-displacement term (allocated on the first occ_xc_vv10_gradient call)
+  double *GX, *GY, *GZ;   // per-point sum_j f_ij
+  int *pt_atom;           // [n] atom whose grid the point belongs to (reference order)
+  double *bbox;           // [nblk][6] bounding boxes of the active points of each block of 128
+};
+// multi-GPU: base pointers of the shards' (X Y Z rw2 om kap) blocks, each 6 n doubles
+struct VV10Peers {
+  const double *base[16];
+  int n;
 };
 
 // spherical transform tables (real solid harmonics, CCA order m = -l..l) in constant memory
@@ -162,7 +171,11 @@ void launch_transpose(const double *D, double *DT, int nbf, int ld, void *stream
 void launch_prepare_density(const double *D2, double *Dsym, int nbf, int nspin, void *stream);
 void launch_finalize(const BuildParams &P, int nleaves, double *K, double *scalars, void *stream);
 void launch_gather_rho(const BuildParams &P, const size_t *tile_src, size_t npts, int ntiles, double *out, void *stream);
-void launch_vv10_prepare(const BuildParams &P, const VV10Params &V, int ntiles, void *stream);
+void launch_vv10_prepare(const BuildParams &P, const VV10Params &V, int ntiles, double unowned, void *stream);
+void launch_vv10_point_atoms(const VV10Params &V, int natoms, const size_t *atom_offsets_dev, void *stream);
+void launch_vv10_grid_pairs(const VV10Params &V, const int2 *items, int nitems, void *stream);
+void launch_vv10_grid_reduce(const VV10Params &V, double *grad, void *stream);
+void launch_vv10_merge(const VV10Peers &src, const VV10Params &out, void *stream);
 void launch_vv10_pairs(const VV10Params &V, const int2 *items, int nitems, void *stream);
 void launch_vv10_coef(const BuildParams &P, const VV10Params &V, int nleaves, void *stream);
 int vv10_jchunk();

@@ -110,6 +110,10 @@ struct occ_xc_multi {
   double *h_scalars = nullptr;   // pinned, 3 per rank
   size_t ksz = 0, csz = 0;
   double last_ms[MAX_DEV];
+  // post-SCF VV10 over the shards (allocated on first use)
+  cudaEvent_t ev_vv[MAX_DEV];    // this rank's coefficient / contraction stage is complete
+  double *d_vv2[MAX_DEV];        // merged per-point arrays (X Y Z rw2 om kap) and summed F U W: 9 n doubles
+  double *h_grad = nullptr;      // pinned, 3 natoms per rank
 };
 
 #define MULTI_TRY(expr)                                                                                        \
@@ -143,10 +147,13 @@ void occ_xc_multi_destroy(occ_xc_multi *m) {
       if (m->ev_in[r]) cudaEventDestroy(m->ev_in[r]);
       if (m->ev_built[r]) cudaEventDestroy(m->ev_built[r]);
       if (m->d_red[r]) cudaFree(m->d_red[r]);
+      if (m->ev_vv[r]) cudaEventDestroy(m->ev_vv[r]);
+      if (m->d_vv2[r]) cudaFree(m->d_vv2[r]);
       occ_xc_destroy(m->h[r]);
     }
   }
   if (m->h_scalars) cudaFreeHost(m->h_scalars);
+  if (m->h_grad) cudaFreeHost(m->h_grad);
   delete m;
 }
 
@@ -166,6 +173,8 @@ int occ_xc_multi_create(const occ_xc_basis_t *basis, size_t npts, const double *
     m->worker[r] = nullptr;
     m->ev_in[r] = m->ev_built[r] = nullptr;
     m->d_red[r] = nullptr;
+    m->ev_vv[r] = nullptr;
+    m->d_vv2[r] = nullptr;
     m->last_ms[r] = 0.0;
   }
   for (int r = 0; r < ndev; ++r) {
@@ -338,6 +347,143 @@ int occ_xc_multi_build(occ_xc_multi *m, const double *D2, const double *C, doubl
   if (n_alpha) *n_alpha = s[1];
   if (n_beta) *n_beta = s[2];
   return 0;
+}
+
+// ---- post-SCF VV10 over the shards (NonLocalCorrelationFunctional::vv10 / vv10_gradient,
+// src/dft/nonlocal_correlation.cpp:367-420, 392-522).  Every rank evaluates rho / grad rho on ITS leaves and publishes
+// the per-point arrays of its points (reference order); each rank then gathers the whole grid's arrays from its peers,
+// runs its round-robin share of the O(N^2) pair work, the partial F / U / W are summed through peer loads in rank order,
+// and the Vxc contraction (or the gradient's potential term) runs on the rank's own leaves again.
+static int multi_vv10(occ_xc_multi *m, const double *D2, const size_t *orig_index, const size_t *atom_offsets, double vv10_b,
+                      double vv10_C, double *K, double *gradient, double *energy) {
+  const int n = m->n;
+  const bool grad = gradient != nullptr;
+  const char *who = grad ? "occ_xc_multi_vv10_gradient" : "occ_xc_multi_vv10";
+  for (int r = 0; r < n; ++r)
+    if (vv10_check_handle(m->h[r], who, grad)) return 1;
+  const size_t npts = m->h[0]->npts_total;
+  const int natoms = m->h[0]->natoms;
+  if (grad && !m->h_grad &&
+      cudaHostAlloc(&m->h_grad, 3 * static_cast<size_t>(natoms) * MAX_DEV * sizeof(double), cudaHostAllocPortable) != cudaSuccess)
+    return occ_xc_set_error("occ_xc_multi_vv10_gradient: cudaHostAlloc failed");
+  std::string err;
+  int rc = 0;
+  // stage 1: density on the rank's own leaves, its points' arrays published in h->vv (0 = "not mine")
+  for (int r = 0; r < n; ++r) {
+    m->worker[r]->submit([=]() -> int {
+      occ_xc_handle *h = m->h[r];
+      MULTI_TRY(cudaSetDevice(h->device));
+      if (!m->ev_vv[r]) MULTI_TRY(cudaEventCreateWithFlags(&m->ev_vv[r], cudaEventDisableTiming));
+      if (!m->d_vv2[r]) MULTI_TRY(cudaMalloc(&m->d_vv2[r], 9 * npts * sizeof(double)));
+      if (vv10_setup(h, r, n)) return 1;
+      if (grad && vv10_setup_gradient(h, r, n, atom_offsets)) return 1;
+      if (vv10_stage_density(h, D2, orig_index, vv10_b, vv10_C, 0.0, grad)) return 1;
+      MULTI_TRY(cudaEventRecord(m->ev_in[r], h->stream));
+      return 0;
+    });
+  }
+  for (int r = 0; r < n; ++r) rc |= m->worker[r]->wait(&err);
+  if (rc) return occ_xc_set_error(err.c_str());
+  auto second_set = [=](int r) {
+    xcb::VV10Params V = m->h[r]->vv;
+    double *b = m->d_vv2[r];
+    V.X = b, V.Y = b + npts, V.Z = b + 2 * npts, V.rw2 = b + 3 * npts, V.om = b + 4 * npts, V.kap = b + 5 * npts;
+    V.F = b + 6 * npts, V.U = b + 7 * npts, V.W = b + 8 * npts;
+    return V;
+  };
+  // stage 2: gather the whole grid's arrays, this rank's share of the pair work
+  for (int r = 0; r < n; ++r) {
+    m->worker[r]->submit([=]() -> int {
+      occ_xc_handle *h = m->h[r];
+      MULTI_TRY(cudaSetDevice(h->device));
+      for (int p = 0; p < n; ++p)
+        if (p != r) MULTI_TRY(cudaStreamWaitEvent(h->stream, m->ev_in[p], 0));
+      xcb::VV10Peers src;
+      src.n = n;
+      for (int p = 0; p < n; ++p) src.base[p] = m->h[p]->vv.X;
+      const xcb::VV10Params merged = second_set(r);
+      xcb::launch_vv10_merge(src, merged, h->stream);
+      if (vv10_stage_pairs(h, merged)) return 1;
+      MULTI_TRY(cudaEventRecord(m->ev_built[r], h->stream));
+      return 0;
+    });
+  }
+  for (int r = 0; r < n; ++r) rc |= m->worker[r]->wait(&err);
+  if (rc) return occ_xc_set_error(err.c_str());
+  // stage 3: sum F / U / W over the ranks (rank order), then the contraction on the rank's own leaves
+  for (int r = 0; r < n; ++r) {
+    m->worker[r]->submit([=]() -> int {
+      occ_xc_handle *h = m->h[r];
+      MULTI_TRY(cudaSetDevice(h->device));
+      for (int p = 0; p < n; ++p)
+        if (p != r) MULTI_TRY(cudaStreamWaitEvent(h->stream, m->ev_built[p], 0));
+      PeerPtrs parts;
+      parts.n = n;
+      for (int p = 0; p < n; ++p) parts.p[p] = m->h[p]->vv.F; // F, U, W are contiguous
+      const xcb::VV10Params merged = second_set(r);
+      const unsigned g = static_cast<unsigned>(std::min<size_t>((3 * npts + 255) / 256, 148 * 8));
+      k_reduce_panel<<<g, 256, 0, h->stream>>>(parts, merged.F, 0, 3 * npts);
+      if (grad) {
+        if (vv10_stage_gradient(h, merged, merged)) return 1;
+        MULTI_TRY(cudaMemcpyAsync(m->h_grad + 3 * static_cast<size_t>(natoms) * r, h->d_grad,
+                                  3 * static_cast<size_t>(natoms) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      } else {
+        if (vv10_stage_vxc(h, merged)) return 1;
+      }
+      MULTI_TRY(cudaMemcpyAsync(m->h_scalars + 3 * r, h->d_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      MULTI_TRY(cudaEventRecord(m->ev_vv[r], h->stream));
+      return 0;
+    });
+  }
+  for (int r = 0; r < n; ++r) rc |= m->worker[r]->wait(&err);
+  if (rc) return occ_xc_set_error(err.c_str());
+  // stage 4: column panels of K summed over the ranks and written to the host (as occ_xc_multi_build); sync
+  const size_t ld = m->h[0]->nbf, ncols = m->h[0]->nbf;
+  for (int r = 0; r < n; ++r) {
+    m->worker[r]->submit([=]() -> int {
+      occ_xc_handle *h = m->h[r];
+      MULTI_TRY(cudaSetDevice(h->device));
+      for (int p = 0; p < n; ++p)
+        if (p != r) MULTI_TRY(cudaStreamWaitEvent(h->stream, m->ev_vv[p], 0));
+      size_t lo, hi;
+      panel(ld, ncols, n, r, &lo, &hi);
+      if (!grad && hi > lo) {
+        PeerPtrs parts;
+        parts.n = n;
+        for (int p = 0; p < n; ++p) parts.p[p] = m->h[p]->d_K;
+        const unsigned g = static_cast<unsigned>(std::min<size_t>((hi - lo + 255) / 256, 148 * 8));
+        k_reduce_panel<<<g, 256, 0, h->stream>>>(parts, m->d_red[r], lo, hi);
+        MULTI_TRY(cudaMemcpyAsync(K + lo, m->d_red[r] + lo, (hi - lo) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      }
+      MULTI_TRY(cudaStreamSynchronize(h->stream));
+      MULTI_TRY(cudaGetLastError());
+      return 0;
+    });
+  }
+  for (int r = 0; r < n; ++r) rc |= m->worker[r]->wait(&err);
+  if (rc) return occ_xc_set_error(err.c_str());
+  double e = 0.0;
+  for (int r = 0; r < n; ++r) e += m->h_scalars[3 * r];
+  if (energy) *energy = e;
+  if (grad)
+    for (int k = 0; k < 3 * natoms; ++k) {
+      double g = 0.0;
+      for (int r = 0; r < n; ++r) g += m->h_grad[3 * static_cast<size_t>(natoms) * r + k];
+      gradient[k] = g;
+    }
+  return 0;
+}
+
+int occ_xc_multi_vv10(occ_xc_multi *m, const double *D2, const size_t *orig_index, double vv10_b, double vv10_C, double *K,
+                      double *energy) {
+  if (!m || !D2 || !K || !energy) return occ_xc_set_error("occ_xc_multi_vv10: null argument");
+  return multi_vv10(m, D2, orig_index, nullptr, vv10_b, vv10_C, K, nullptr, energy);
+}
+
+int occ_xc_multi_vv10_gradient(occ_xc_multi *m, const double *D2, const size_t *orig_index, const size_t *atom_offsets,
+                               double vv10_b, double vv10_C, double *gradient, double *energy) {
+  if (!m || !D2 || !atom_offsets || !gradient) return occ_xc_set_error("occ_xc_multi_vv10_gradient: null argument");
+  return multi_vv10(m, D2, orig_index, atom_offsets, vv10_b, vv10_C, nullptr, gradient, energy);
 }
 
 } // extern "C"

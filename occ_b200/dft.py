@@ -296,7 +296,7 @@ class MultiGPUDFT:
     def __init__(self, method: str, basis: AOBasis, grid: GridHierarchy, spinorbital_kind: str = RESTRICTED,
                  devices=(0,), batch_bytes: int = 0, density_threshold: float = 1e-10,
                  xc_screening_threshold: float = 1e-10, nocc=None, deterministic: bool = False,
-                 density_scale: float = 0.0, orbital_scale: float = 0.0):
+                 density_scale: float = 0.0, orbital_scale: float = 0.0, gradient: bool = False):
         self.basis, self.method = basis, method
         self.func_ids = np.array(get_dft_method(method), dtype=np.int32)
         self.nspin = 2 if spinorbital_kind == UNRESTRICTED else 1
@@ -309,6 +309,7 @@ class MultiGPUDFT:
         lib().occ_xc_options_init(C.byref(opt))
         opt.batch_bytes, opt.deterministic = batch_bytes, int(deterministic)
         opt.density_scale, opt.orbital_scale = density_scale, orbital_scale
+        opt.gradient = int(gradient)
         self.nocc = None
         if nocc is not None:
             na, nb_ = (nocc, nocc) if np.isscalar(nocc) else (nocc[0], nocc[-1])

@@ -349,6 +349,29 @@ def vv10(basis: Basis, pts, w, D2, b=6.0, Cpar=0.01, nthreads=None):
     return {"energy": e.value, "K": K, "rho": rho4, "F": fuw[0], "U": fuw[1], "W": fuw[2]}
 
 
+def vv10_gradient(basis: Basis, pts, w, atom_offsets, D2, b=6.0, Cpar=0.01, nthreads=None):
+    """NonLocalCorrelationFunctional::vv10_gradient restatement (src/dft/nonlocal_correlation.cpp:108-328, 392-522).
+    atom_offsets (natoms + 1): point ranges of the concatenated NLC atom grids.  Returns the gradient (natoms, 3), its
+    potential and grid-displacement parts, and the energy."""
+    nbf = basis.nbf
+    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    off = np.ascontiguousarray(atom_offsets, dtype=np.uint64)
+    natoms = len(off) - 1
+    D2 = np.asfortranarray(D2, dtype=np.float64)
+    assert D2.shape == (nbf, nbf) and int(off[-1]) == len(w)
+    g = np.zeros((natoms, 3))
+    parts = np.zeros((2, natoms, 3))
+    e = C.c_double(0)
+    lib().orc_vv10_gradient.restype = C.c_int
+    rc = lib().orc_vv10_gradient(basis.ref, C.c_size_t(len(w)), _p(pts), _p(w), C.c_int(natoms), _p(off), _p(D2),
+                                 C.c_double(b), C.c_double(Cpar), _p(g), C.byref(e), _p(parts),
+                                 C.c_int(nthreads or os.cpu_count() or 1))
+    if rc:
+        raise RuntimeError("orc_vv10_gradient failed")
+    return {"gradient": g, "potential": parts[0], "grid": parts[1], "energy": e.value}
+
+
 # ---------------------------------------------------------------------------------------------------------
 # COSX seminumerical exchange (oracle/src/cosx.cpp): SURVEY 8(f) rank 2
 # ---------------------------------------------------------------------------------------------------------

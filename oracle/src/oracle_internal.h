@@ -16,6 +16,10 @@ void collocate_shell(int l, int pure, size_t npts, const double *xyz, int nprim,
                      const double *exps, const double *center, int deriv, double *phi, double *phi_x,
                      double *phi_y, double *phi_z);
 
+// value, gradient and xx, xy, xz, yy, yz, zz of one shell, component-major, no common_fac (oracle/src/gradient.cpp)
+void collocate_shell_deriv2(int l, int pure, size_t npts, const double *xyz, int nprim, const double *coefs,
+                            const double *exps, const double *center, double *out[10]);
+
 struct Basis {
   explicit Basis(const orc_basis_t *b);
   orc_basis_t raw;

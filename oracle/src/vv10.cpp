@@ -175,3 +175,142 @@ int orc_vv10(const orc_basis_t *basis, size_t npts, const double *pts, const dou
   return 0;
 }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// VV10 nuclear gradient (post-SCF, restricted): nonlocal_correlation.cpp:108-190, 193-328, 392-522
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int orc_vv10_gradient(const orc_basis_t *basis, size_t npts, const double *pts, const double *w, int natoms,
+                                 const size_t *atom_offsets, const double *D2, double b, double C, double *grad,
+                                 double *energy, double *parts, int nthreads) {
+  using namespace orc;
+  const Basis B(basis);
+  const orc_basis_t &raw = B.raw;
+  const int nbf = B.nbf;
+  if (!raw.shell_atom) return 1;
+  // vv10_kernel_gradient is the same arithmetic as vv10_kernel (:113-190 vs :38-106): take rho, grad rho, F, U, W from it
+  std::vector<double> Kdummy(static_cast<size_t>(nbf) * nbf), rho4(4 * npts), fuw(3 * npts);
+  if (orc_vv10(basis, npts, pts, w, D2, b, C, Kdummy.data(), energy, rho4.data(), fuw.data(), nthreads)) return 1;
+  const double kappa_factor = b * 1.5 * kPi * std::pow(9.0 * kPi, -1.0 / 6.0);
+  const double beta = std::pow(3.0 / (b * b), 0.75) / 32.0;
+  const double pi43 = 4.0 * kPi / 3.0;
+  std::vector<double> c0(npts), cx(npts), cy(npts), cz(npts), om(npts), kap(npts);
+  for (size_t i = 0; i < npts; ++i) {
+    const double rho = rho4[4 * i], gx = rho4[4 * i + 1], gy = rho4[4 * i + 2], gz = rho4[4 * i + 3];
+    const double g = gx * gx + gy * gy + gz * gz;
+    double t = g / (rho * rho);
+    t = C * t * t;
+    om[i] = std::sqrt(t + pi43 * rho);
+    kap[i] = kappa_factor * std::pow(rho, 1.0 / 6.0);
+    const double F = fuw[i], U = fuw[npts + i], W = fuw[2 * npts + i];
+    double vrho = beta * w[i], vsig = 0.0;
+    if (rho >= 1e-8) {
+      vrho = (beta + F + 1.5 * (U * (kap[i] / 6.0) + W * ((0.5 * pi43 * rho - 2.0 * t) / om[i]))) * w[i];
+      vsig = W == 0.0 ? 0.0 : 1.5 * W * (t * rho / (g * om[i])) * w[i];
+    }
+    c0[i] = 0.5 * vrho; // :446 "vrho = vxc.col(0) * 0.5"
+    cx[i] = 2.0 * vsig * gx;
+    cy[i] = 2.0 * vsig * gy;
+    cz[i] = 2.0 * vsig * gz;
+  }
+  // ---- potential term: V_d = phi_d^T aow + (phi^T aow_d)^T (:462-496), then the distribution loop (:499-512) ----
+  const size_t n2 = static_cast<size_t>(nbf) * nbf;
+  std::vector<double> V[3];
+  for (int d = 0; d < 3; ++d) V[d].assign(n2, 0.0);
+  constexpr size_t BLK = 128;
+  const size_t nblk = (npts + BLK - 1) / BLK;
+  static const int hess_slot[3][3] = {{4, 5, 6}, {5, 7, 8}, {6, 8, 9}}; // xx xy xz yy yz zz
+#pragma omp parallel
+  {
+    std::vector<double> phi[10], tmp[10], aow, Vl[3];
+    for (int d = 0; d < 3; ++d) Vl[d].assign(n2, 0.0);
+#pragma omp for schedule(dynamic)
+    for (size_t blk = 0; blk < nblk; ++blk) {
+      const size_t p0 = blk * BLK;
+      const int n = static_cast<int>(std::min(BLK, npts - p0));
+      for (int c = 0; c < 10; ++c) phi[c].assign(static_cast<size_t>(n) * nbf, 0.0);
+      for (int s = 0; s < raw.nsh; ++s) {
+        const int l = raw.l[s], sz = orc_nbf_shell(l, raw.pure);
+        double *out[10];
+        for (int c = 0; c < 10; ++c) {
+          tmp[c].assign(static_cast<size_t>(sz) * n, 0.0);
+          out[c] = tmp[c].data();
+        }
+        collocate_shell_deriv2(l, raw.pure, n, pts + 3 * p0, raw.nprim[s], raw.coefs + raw.prim_off[s],
+                               raw.exps + raw.prim_off[s], raw.origin + 3 * s, out);
+        const double fac = orc_common_fac(l, raw.pure);
+        for (int c = 0; c < 10; ++c)
+          for (int f = 0; f < sz; ++f)
+            for (int p = 0; p < n; ++p)
+              phi[c][static_cast<size_t>(B.first_bf[s] + f) * n + p] = fac * tmp[c][static_cast<size_t>(f) * n + p];
+      }
+      aow.assign(static_cast<size_t>(n) * nbf, 0.0);
+      auto fill = [&](int a, int bx, int by, int bz) { // aow = c0 phi[a] + cx phi[bx] + cy phi[by] + cz phi[bz]
+        for (int f = 0; f < nbf; ++f)
+          for (int p = 0; p < n; ++p) {
+            const size_t o = static_cast<size_t>(f) * n + p, i = p0 + p;
+            aow[o] = phi[a][o] * c0[i] + phi[bx][o] * cx[i] + phi[by][o] * cy[i] + phi[bz][o] * cz[i];
+          }
+      };
+      fill(0, 1, 2, 3);
+      for (int d = 0; d < 3; ++d)
+        dgemm('T', 'N', nbf, nbf, n, 1.0, phi[1 + d].data(), n, aow.data(), n, 1.0, Vl[d].data(), nbf);
+      for (int d = 0; d < 3; ++d) {
+        fill(1 + d, hess_slot[d][0], hess_slot[d][1], hess_slot[d][2]);
+        dgemm('T', 'N', nbf, nbf, n, 1.0, aow.data(), n, phi[0].data(), n, 1.0, Vl[d].data(), nbf); // (phi^T aow_d)^T
+      }
+    }
+#pragma omp critical
+    for (int d = 0; d < 3; ++d)
+      for (size_t k = 0; k < n2; ++k) V[d][k] += Vl[d][k];
+  }
+  std::vector<int> bf_atom(nbf);
+  for (int s = 0; s < raw.nsh; ++s)
+    for (int f = 0; f < orc_nbf_shell(raw.l[s], raw.pure); ++f) bf_atom[B.first_bf[s] + f] = raw.shell_atom[s];
+  std::vector<double> gpot(3 * static_cast<size_t>(natoms), 0.0), ggrid(3 * static_cast<size_t>(natoms), 0.0);
+  for (int mu = 0; mu < nbf; ++mu)
+    for (int nu = 0; nu < nbf; ++nu) {
+      const double Dval = D2[static_cast<size_t>(nu) * nbf + mu]; // 2.0 * mo.D(mu, nu)
+      if (std::fabs(Dval) < 1e-12) continue;
+      for (int d = 0; d < 3; ++d) gpot[3 * bf_atom[mu] + d] -= V[d][static_cast<size_t>(nu) * nbf + mu] * Dval;
+    }
+  // ---- grid-displacement term (:196-328) ----
+  std::vector<int> pt_atom(npts, 0);
+  for (int a = 0; a < natoms; ++a)
+    for (size_t i = atom_offsets[a]; i < atom_offsets[a + 1]; ++i) pt_atom[i] = a;
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel
+  {
+    std::vector<double> gl(3 * static_cast<size_t>(natoms), 0.0);
+#pragma omp for schedule(dynamic, 64)
+    for (size_t i = 0; i < npts; ++i) {
+      const double rho_i = rho4[4 * i];
+      if (rho_i < 1e-8) continue;
+      for (size_t j = 0; j < npts; ++j) {
+        const double rho_j = rho4[4 * j];
+        if (i == j || rho_j < 1e-8) continue;
+        const double dx = pts[3 * i] - pts[3 * j], dy = pts[3 * i + 1] - pts[3 * j + 1], dz = pts[3 * i + 2] - pts[3 * j + 2];
+        const double r2 = dx * dx + dy * dy + dz * dz;
+        if (std::sqrt(r2) > 15.0) continue;
+        const double gi = r2 * om[i] + kap[i], gj = r2 * om[j] + kap[j];
+        const double Theta = 2.0 * rho_i * w[i] * rho_j * w[j];
+        const double denom = gi * gj * (gi + gj);
+        if (std::fabs(denom) < 1e-20) continue;
+        const double dD = 2.0 * om[i] * (gj * (gi + gj) + gi * gj) + 2.0 * om[j] * (gi * (gi + gj) + gi * gj);
+        const double dPhi = 1.5 * Theta * dD / (denom * denom);
+        const double f[3] = {2.0 * dPhi * dx, 2.0 * dPhi * dy, 2.0 * dPhi * dz};
+        for (int d = 0; d < 3; ++d) {
+          gl[3 * pt_atom[i] + d] -= f[d];
+          gl[3 * pt_atom[j] + d] += f[d];
+        }
+      }
+    }
+#pragma omp critical
+    for (size_t k = 0; k < gl.size(); ++k) ggrid[k] += gl[k];
+  }
+  for (size_t k = 0; k < gpot.size(); ++k) grad[k] = gpot[k] + ggrid[k];
+  if (parts) {
+    std::copy(gpot.begin(), gpot.end(), parts);
+    std::copy(ggrid.begin(), ggrid.end(), parts + gpot.size());
+  }
+  return 0;
+}

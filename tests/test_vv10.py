@@ -160,3 +160,124 @@ def test_cuda_vv10_identity_order_and_low_density_points(oracle):
     r = oracle.vv10(ob, h.sorted_points, h.sorted_weights, D2)      # same (sorted) order on both sides
     assert (r["rho"][:, 0] < 1e-8).sum() >= 256
     assert abs(e.value - r["energy"]) < 1e-8 and np.abs(K - r["K"]).max() < 1e-9
+
+
+# ---------------------------------------------------------------------------------------------------------
+# VV10 nuclear gradient: NonLocalCorrelationFunctional::vv10_gradient (nonlocal_correlation.cpp:108-328, 392-522)
+# ---------------------------------------------------------------------------------------------------------
+def _nlc_atom_grid(oracle, basis, ob):
+    pts, w, info = oracle.molecular_grid(basis.atomic_numbers, basis.positions, ob,
+                                         oracle.default_grid_settings(**NLC_GRID))
+    return pts, w, oracle.cosx_atom_grids(pts, info)
+
+
+def test_oracle_vv10_gradient_matches_numpy_transcription(oracle):
+    """both terms of vv10_gradient transcribed independently in numpy on a thinned water grid"""
+    Z, pos = molecules.water()
+    b = aobasis.AOBasis.load(Z, pos, "def2-svp")
+    ob = oracle.Basis(b.as_arrays())
+    pts, w, off = _nlc_atom_grid(oracle, b, ob)
+    keep = np.arange(0, len(w), 5)
+    atom_of = np.searchsorted(off, keep, side="right") - 1
+    pts, w = pts[keep], w[keep] * 5.0
+    off = np.concatenate([[0], np.cumsum(np.bincount(atom_of, minlength=len(Z)))]).astype(np.uint64)
+    D2 = molecules.synthetic_density(b, 1)
+    r = oracle.vv10_gradient(ob, pts, w, off, D2)
+    e = oracle.vv10(ob, pts, w, D2)
+    assert abs(r["energy"] - e["energy"]) < 1e-14
+    rho, grad = e["rho"][:, 0], e["rho"][:, 1:]
+    g = (grad ** 2).sum(1)
+    _, vrho, vsig, _ = _numpy_vv10_kernel(rho, g, pts, w)
+    # ---- potential term (:446-512) ----
+    nbf = b.nbf
+    phi = [np.zeros((len(w), nbf)) for _ in range(10)]
+    bf_atom = np.zeros(nbf, dtype=int)
+    col = 0
+    for sh, at in zip(b.shells, b.as_arrays()["shell_atom"]):
+        fac = oracle.lib().orc_common_fac(int(sh.l), int(b.pure))
+        vals = oracle.collocate_shell_deriv2(sh.l, int(b.pure), pts, sh.coefficients, sh.exponents, sh.origin)
+        width = vals[0].shape[0]
+        for k in range(10):
+            phi[k][:, col:col + width] = vals[k].T * fac
+        bf_atom[col:col + width] = at
+        col += width
+    p, (px, py, pz), (pxx, pxy, pxz, pyy, pyz, pzz) = phi[0], phi[1:4], phi[4:10]
+    vr = 0.5 * vrho
+    dx, dy, dz = grad[:, 0], grad[:, 1], grad[:, 2]
+
+    def aow(a, bx, by, bz):
+        return a * vr[:, None] + bx * (2 * vsig * dx)[:, None] + by * (2 * vsig * dy)[:, None] + bz * (2 * vsig * dz)[:, None]
+
+    first = aow(p, px, py, pz)
+    V = [px.T @ first + (p.T @ aow(px, pxx, pxy, pxz)).T,
+         py.T @ first + (p.T @ aow(py, pxy, pyy, pyz)).T,
+         pz.T @ first + (p.T @ aow(pz, pxz, pyz, pzz)).T]
+    Dm = np.where(np.abs(D2) < 1e-12, 0.0, D2)
+    gpot = np.zeros((len(Z), 3))
+    for d in range(3):
+        np.subtract.at(gpot[:, d], bf_atom, (V[d] * Dm).sum(1))
+    assert np.abs(gpot - r["potential"]).max() < 1e-12
+    # ---- grid-displacement term (:196-328), every ordered pair ----
+    pi43 = 4 * np.pi / 3
+    kf = 6.0 * 1.5 * np.pi * (9 * np.pi) ** (-1 / 6)
+    om = np.sqrt(0.01 * (g / rho ** 2) ** 2 + pi43 * rho)
+    kap = kf * rho ** (1 / 6)
+    atom = np.searchsorted(off, np.arange(len(w)), side="right") - 1
+    ggrid = np.zeros((len(Z), 3))
+    act = rho >= 1e-8
+    for i in np.nonzero(act)[0]:
+        rij = pts[i] - pts
+        r2 = (rij ** 2).sum(1)
+        ok = act & (np.sqrt(r2) <= 15.0)
+        ok[i] = False
+        gi, gj = r2 * om[i] + kap[i], r2 * om + kap
+        theta = 2.0 * rho[i] * w[i] * rho * w
+        den = gi * gj * (gi + gj)
+        dD = 2 * om[i] * (gj * (gi + gj) + gi * gj) + 2 * om * (gi * (gi + gj) + gi * gj)
+        force = (2.0 * 1.5 * theta * dD / den ** 2)[:, None] * rij
+        force[~ok] = 0.0
+        ggrid[atom[i]] -= force.sum(0)
+        np.add.at(ggrid, atom, force)
+    assert np.abs(ggrid - r["grid"]).max() < 1e-13
+    assert np.abs(r["gradient"] - (r["potential"] + r["grid"])).max() == 0.0
+    assert np.abs(r["grid"]).max() > 1e-4 and np.abs(r["potential"]).max() > 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mol,bas,devices", [("water", "def2-svp", None), ("benzene", "def2-svp", None),
+                                             ("water", "def2-svp", [0, 0]), ("benzene", "def2-svp", [0, 0, 0])])
+def test_cuda_vv10_gradient_matches_oracle(oracle, mol, bas, devices):
+    """occ_xc_vv10_gradient / occ_xc_multi_vv10_gradient (shards on one device when the box has one GPU) vs the oracle:
+    1e-9 Eh/Bohr per component; the multi-handle VV10 energy / Vxc against the oracle as well"""
+    from occ_b200 import nlc
+    Z, pos = molecules.MOLECULES[mol]()
+    b = aobasis.AOBasis.load(Z, pos, bas)
+    ob = oracle.Basis(b.as_arrays())
+    D2 = molecules.synthetic_density(b, 1)
+    f = nlc.NonLocalCorrelationFunctional()
+    f.set_integration_grid(b, gradient=True, devices=devices)
+    e, g = f.vv10_gradient(D2)
+    pts, w, off = _nlc_atom_grid(oracle, b, ob)
+    assert len(w) == f.num_grid_points and np.array_equal(off, f._atom_offsets)
+    r = oracle.vv10_gradient(ob, pts, w, off, D2)
+    assert abs(e - r["energy"]) < 1e-8
+    assert np.abs(g - r["gradient"]).max() < 1e-9
+    assert np.abs(r["gradient"]).max() > 1e-4
+    gm = f.compute_gradient(0.5 * D2)               # the reference-named entry takes mo.D
+    assert np.abs(gm - g).max() < 1e-12
+    e2, K = f.vv10(D2)                              # the same handle(s) still serve the energy / Vxc call
+    rk = oracle.vv10(ob, pts, w, D2)
+    assert abs(e2 - rk["energy"]) < 1e-8 and np.abs(K - rk["K"]).max() < 1e-9
+    f.close()
+
+
+@pytest.mark.gpu
+def test_cuda_vv10_gradient_needs_the_gradient_option():
+    from occ_b200 import nlc
+    Z, pos = molecules.water()
+    b = aobasis.AOBasis.load(Z, pos, "def2-svp")
+    f = nlc.NonLocalCorrelationFunctional()
+    f.set_integration_grid(b)
+    with pytest.raises(RuntimeError, match="gradient option"):
+        f.vv10_gradient(molecules.synthetic_density(b, 1))
+    f.close()
