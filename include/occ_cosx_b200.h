@@ -41,7 +41,7 @@ typedef struct occ_cosx_handle occ_cosx_handle;
  *                             batches are blocks of 128 consecutive points of one atom grid (:676-699)
  *   overlap_projector         m_overlap_projector = Sn.ldlt().solve(S), nbf x nbf column-major; NULL = identity
  * Shell pairs (precompute_significant_shell_pairs, :293-331), their E coefficients, centres and extents
- * (src/ints/esp.cpp:85-100, include/occ/ints/kernels.h:256-340) are built here, on the host, once. Shells up to l = 3. */
+ * (src/ints/esp.cpp:85-100, include/occ/ints/kernels.h:256-340) are built here, on the host, once. Shells up to l = 4 (g). */
 int occ_cosx_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_offsets, const double *pts_xyz,
                     const double *weights, const double *overlap_projector, const occ_cosx_options_t *opt,
                     occ_cosx_handle **out);

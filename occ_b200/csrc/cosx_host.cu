@@ -219,7 +219,7 @@ int occ_cosx_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_
   int nbf = 0;
   for (int s = 0; s < nsh; ++s) {
     if (basis->l[s] < 0 || basis->l[s] > COSX_MAX_L)
-      return fail("occ_cosx_create: shells up to l = 3 are supported by the COSX build");
+      return fail("occ_cosx_create: shells up to l = 4 (g) are supported by the COSX build");
     first_bf[s] = nbf;
     shell_size[s] = nfun(basis->l[s], pure);
     nbf += shell_size[s];
@@ -248,8 +248,9 @@ int occ_cosx_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_
   // ---- shell pairs, grouped by (la >= lb) class, sorted by the resident shell inside a class ----
   std::vector<double> Tfull[COSX_MAX_L + 1];
   for (int l = 0; l <= COSX_MAX_L; ++l) Tfull[l] = c2s_full(l);
-  std::vector<HostPair> hp[16];
-  std::vector<double> pool[16];
+  constexpr int NCLS = (COSX_MAX_L + 1) * (COSX_MAX_L + 1);
+  std::vector<HostPair> hp[NCLS];
+  std::vector<double> pool[NCLS];
   h->S_analytic.assign(static_cast<size_t>(nbf) * nbf, 0.0);
   std::vector<double> Ex, Ey, Ez, Sc, Ss, tmp;
   for (int p0 = 0; p0 < nsh; ++p0)
@@ -260,7 +261,7 @@ int occ_cosx_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_
       const int p = swap_roles ? q0 : p0, q = swap_roles ? p0 : q0;
       const int la = basis->l[p], lb = basis->l[q], L1 = la + lb + 1, ne = (la + 1) * (lb + 1) * L1;
       const double *A = basis->origin + 3 * p, *Bc = basis->origin + 3 * q;
-      const int cls = la * 4 + lb, stride = COSX_PRIM_HDR + 3 * ne;
+      const int cls = la * (COSX_MAX_L + 1) + lb, stride = COSX_PRIM_HDR + 3 * ne;
       const int nca = ncart(la), ncb = ncart(lb);
       const double sph_fac = (la == 0 ? 0.282094791773878143 : (la == 1 ? 0.488602511902919921 : 1.0)) *
                              (lb == 0 ? 0.282094791773878143 : (lb == 1 ? 0.488602511902919921 : 1.0)); // kernels.h:11-18
@@ -355,9 +356,9 @@ int occ_cosx_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_
     }
   std::vector<CosxPair> pairs_all;
   std::vector<double> pool_all;
-  for (int cls = 0; cls < 16; ++cls) {
+  for (int cls = 0; cls < NCLS; ++cls) {
     if (hp[cls].empty()) continue;
-    occ_cosx_handle::ClassRange cr = {cls / 4, cls % 4, static_cast<int>(pairs_all.size()), static_cast<int>(hp[cls].size())};
+    occ_cosx_handle::ClassRange cr = {cls / (COSX_MAX_L + 1), cls % (COSX_MAX_L + 1), static_cast<int>(pairs_all.size()), static_cast<int>(hp[cls].size())};
     const size_t base = pool_all.size();
     if (base + pool[cls].size() > 0x7fffffffULL) {
       occ_cosx_destroy(h);
@@ -494,15 +495,16 @@ int occ_cosx_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_
     CHECK(dev_upload(h, &h->d_boys, order_major));
   }
   {
-    std::vector<double> c2s(9 + 30 + 70, 0.0);
+    std::vector<double> c2s(9 + 30 + 70 + 135, 0.0);
     const double p1[9] = {0, 1, 0, 0, 0, 1, 1, 0, 0}; // gto.cpp:296-305: (py, pz, px)
     std::copy(p1, p1 + 9, c2s.begin());
     std::copy(Tfull[2].begin(), Tfull[2].end(), c2s.begin() + 9);
     std::copy(Tfull[3].begin(), Tfull[3].end(), c2s.begin() + 39);
+    std::copy(Tfull[4].begin(), Tfull[4].end(), c2s.begin() + 109);
     CHECK(dev_upload(h, &h->d_c2s, c2s));
   }
   CHECK(dev_alloc(h, &h->d_active, h->npairs));
-  CHECK(dev_alloc(h, &h->d_stats, 40));
+  CHECK(dev_alloc(h, &h->d_stats, 64)); // 2 per (la, lb) class (25 classes), [56] = k_cosx_kgemm blocks
   const size_t slab_d = static_cast<size_t>(h->nbp) * TILE_P * h->tiles_per_chunk;
   CHECK(dev_alloc(h, &h->d_phi, slab_d));
   CHECK(dev_alloc(h, &h->d_F, slab_d));
@@ -558,7 +560,7 @@ static int sweep(occ_cosx_handle *h, const double *D2q, double precision, double
   launch_cosx_pair_flags(h->d_pairs, h->d_shell_size, static_cast<int>(h->npairs), D2q, nbf, h->density_threshold,
                          h->d_active, st);
   h->info.launches += 1;
-  if (h->collect) CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, 40 * sizeof(unsigned long long), st));
+  if (h->collect) CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, 64 * sizeof(unsigned long long), st));
   CosxParams P = {};
   P.pairs = h->d_pairs;
   P.pool = h->d_pool;
@@ -615,7 +617,7 @@ static int sweep(occ_cosx_handle *h, const double *D2q, double precision, double
     }
     if (h->collect) cudaEventRecord(h->ev[3], st);
     // K' += Phi_t^T . G_t (:797; G here is the reference's -Gg): k_cosx_kgemm, one launch per chunk
-    launch_cosx_kgemm(h->d_phi, h->d_G, h->d_skip + t0, nt, nbf, nbp, Kraw, h->collect ? h->d_stats + 32 : nullptr, st);
+    launch_cosx_kgemm(h->d_phi, h->d_G, h->d_skip + t0, nt, nbf, nbp, Kraw, h->collect ? h->d_stats + 56 : nullptr, st);
     h->info.launches += 1;
     if (h->collect) {
       cudaEventRecord(h->ev[4], st);
@@ -629,7 +631,7 @@ static int sweep(occ_cosx_handle *h, const double *D2q, double precision, double
   }
   CUDA_TRY(cudaGetLastError());
   if (h->collect) {
-    unsigned long long st_h[40];
+    unsigned long long st_h[64];
     CUDA_TRY(cudaMemcpyAsync(st_h, h->d_stats, sizeof(st_h), cudaMemcpyDeviceToHost, st));
     int skip_n = 0;
     std::vector<int> sk(h->ntiles);
@@ -637,13 +639,13 @@ static int sweep(occ_cosx_handle *h, const double *D2q, double precision, double
     CUDA_TRY(cudaStreamSynchronize(st));
     for (int v : sk) skip_n += v;
     h->info.skipped_batches += skip_n;
-    for (int cls = 0; cls < 16; ++cls) {
-      const int la = cls / 4, lb = cls % 4, L = la + lb;
+    for (int cls = 0; cls < (COSX_MAX_L + 1) * (COSX_MAX_L + 1); ++cls) {
+      const int la = cls / (COSX_MAX_L + 1), lb = cls % (COSX_MAX_L + 1), L = la + lb;
       const double nherm = (L + 1) * (L + 2) * (L + 3) / 6.0, nab = static_cast<double>(nfun(la, h->pure)) * nfun(lb, h->pure);
       h->info.pair_evals += st_h[2 * cls];
       h->info.dense_flops += 2.0 * nherm * nab * static_cast<double>(st_h[2 * cls + 1]);
     }
-    h->info.kgemm_blocks += st_h[32];
+    h->info.kgemm_blocks += st_h[56];
     h->info.ms_collocate += ms[0];
     h->info.ms_fgemm += ms[1];
     h->info.ms_esp += ms[2];

@@ -10,7 +10,7 @@
 
 namespace xcb {
 
-constexpr int COSX_MAX_L = 3;
+constexpr int COSX_MAX_L = 4;
 constexpr int COSX_TILE_GROUP = 8; // batches whose F / G slabs share the L2 while all their pair runs execute
 
 struct CosxPair {
@@ -37,7 +37,7 @@ struct CosxParams {
   const double *F;                  // chunk slabs
   double *G;
   const double *boys;               // Chebyshev table of boys.h, order-major: [m][segment][8]
-  const double *c2s;                // spherical tables: l = 1 at 0 (3x3), l = 2 at 9 (5x6), l = 3 at 39 (7x10)
+  const double *c2s;                // spherical tables: l = 1 at 0 (3x3), l = 2 at 9 (5x6), l = 3 at 39 (7x10), l = 4 at 109 (9x15)
   int tile0;                        // first tile of the chunk (slabs are chunk-relative)
   int nbp;
   int pure;

@@ -31,19 +31,25 @@ extern template void launch_class<3, 0>(const CosxParams &, int, int, int, cudaS
 extern template void launch_class<3, 1>(const CosxParams &, int, int, int, cudaStream_t);
 extern template void launch_class<3, 2>(const CosxParams &, int, int, int, cudaStream_t);
 extern template void launch_class<3, 3>(const CosxParams &, int, int, int, cudaStream_t);
+extern template void launch_class<4, 0>(const CosxParams &, int, int, int, cudaStream_t);
+extern template void launch_class<4, 1>(const CosxParams &, int, int, int, cudaStream_t);
+extern template void launch_class<4, 2>(const CosxParams &, int, int, int, cudaStream_t);
+extern template void launch_class<4, 3>(const CosxParams &, int, int, int, cudaStream_t);
+extern template void launch_class<4, 4>(const CosxParams &, int, int, int, cudaStream_t);
 
 void launch_cosx_esp(const CosxParams &P, int la, int lb, int pair0, int npairs, int ntiles, void *stream) {
   if (npairs <= 0 || ntiles <= 0) return;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define COSX_CASE(A, B)                                                                                      \
-  case (A) * 4 + (B):                                                                                        \
+  case (A) * 8 + (B):                                                                                        \
     launch_class<A, B>(P, pair0, npairs, ntiles, st);                                                        \
     break;
-  switch (la * 4 + lb) {
+  switch (la * 8 + lb) {
     COSX_CASE(0, 0)   
     COSX_CASE(1, 0) COSX_CASE(1, 1)  
     COSX_CASE(2, 0) COSX_CASE(2, 1) COSX_CASE(2, 2) 
     COSX_CASE(3, 0) COSX_CASE(3, 1) COSX_CASE(3, 2) COSX_CASE(3, 3)
+    COSX_CASE(4, 0) COSX_CASE(4, 1) COSX_CASE(4, 2) COSX_CASE(4, 3) COSX_CASE(4, 4)
   default: break;
   }
 #undef COSX_CASE

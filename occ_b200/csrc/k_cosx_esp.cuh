@@ -14,9 +14,9 @@ __host__ __device__ constexpr int cx_hidx(int t, int u, int v) {
 }
 
 // fully normalised cartesian -> spherical tables of gto.cpp:289-400 in global memory: l = 1 (the (y, z, x)
-// permutation) at 0, l = 2 at 9, l = 3 at 39
+// permutation) at 0, l = 2 at 9, l = 3 at 39, l = 4 at 109
 template <int L> __device__ __forceinline__ const double *c2s_of(const double *tab) {
-  return tab + (L == 1 ? 0 : (L == 2 ? 9 : 39));
+  return tab + (L == 1 ? 0 : (L == 2 ? 9 : (L == 3 ? 39 : 109)));
 }
 
 // F~[c] = w * sum_m T[m][c] F[m]  (spherical) or w * F[c] (Cartesian): the transposed c2s applied to the row of F
@@ -420,8 +420,11 @@ __device__ __forceinline__ void take_F(double (&Ft)[cx_ncart(L)], const double *
 #define COSX_M33 0
 #endif
 __host__ __device__ constexpr int cosx_min_ctas(int la, int lb) {
-  constexpr int t[4][4] = {{COSX_M00, 0, 0, 0}, {COSX_M10, COSX_M11, 0, 0}, {COSX_M20, COSX_M21, COSX_M22, 0},
-                           {COSX_M30, COSX_M31, COSX_M32, COSX_M33}};
+  constexpr int t[5][5] = {{COSX_M00, 0, 0, 0, 0},
+                           {COSX_M10, COSX_M11, 0, 0, 0},
+                           {COSX_M20, COSX_M21, COSX_M22, 0, 0},
+                           {COSX_M30, COSX_M31, COSX_M32, COSX_M33, 0},
+                           {0, 0, 0, 0, 0}}; // g shells: no cap
   return t[la][lb];
 }
 

@@ -1,0 +1,7 @@
+// k_cosx_la4.cu — instantiations of the COSX ESP kernel for shell pairs with a g shell (see k_cosx_esp.cuh)
+#include "k_cosx_esp.cuh"
+namespace xcb {
+template void launch_class<4, 0>(const CosxParams &, int, int, int, cudaStream_t);
+template void launch_class<4, 1>(const CosxParams &, int, int, int, cudaStream_t);
+template void launch_class<4, 2>(const CosxParams &, int, int, int, cudaStream_t);
+} // namespace xcb

@@ -198,12 +198,32 @@ def test_cosx_sharded_partials_sum_to_K(oracle):
     assert np.abs(sum(parts) - K).max() < 1e-12
 
 
-def test_cosx_rejects_g_shells_loudly():
+@pytest.mark.parametrize("mol,pure", [("water", True), ("water", False), ("benzene", True)])
+def test_cosx_g_shells(oracle, mol, pure):
+    """def2-QZVP: g functions on the heavy atoms, i.e. the (4, lb) classes up to (4, 4) (L = 8); benzene adds two-centre
+    g-g pairs"""
+    O, b, ob, off, pts, w, P, S, Sn, D, sgx = _setup(oracle, mol, "def2-qzvp", pure, angular=14, radial_precision=1e-3)
+    assert max(sh.l for sh in b.shells) == 4
+    K = sgx.compute_K(D)
+    Kref, stats = O.cosx_compute_K(ob, off, pts, w, P, D)
+    assert np.abs(Kref).max() > 1e-3
+    assert np.abs(K - Kref).max() < TOL, np.abs(K - Kref).max()
+    info = sgx.info()
+    assert info["pair_evals"] == stats[0]["pair_evals"]
+    assert info["dense_flops"] == pytest.approx(stats[0]["dense_flops"], rel=1e-12)
+    assert np.abs(sgx.analytic_overlap() - S).max() < 1e-12
+    sgx.close()
+
+
+def test_cosx_rejects_h_shells_loudly():
     from occ_b200 import cosx
     Z, pos = molecules.MOLECULES["water"]()
-    b = aobasis.AOBasis.load(Z, pos, "def2-qzvp")          # g functions on oxygen
+    b = aobasis.AOBasis.load(Z, pos, "def2-svp")
+    sh = b.shells[0]
+    exps = np.array([1.3])
+    b.shells.append(aobasis.Shell(5, sh.origin.copy(), exps, aobasis.incorporate_shell_norm(5, exps, np.array([1.0])), 0))
     offs = np.array([0, 1, 2, 3], dtype=np.uint64)
-    with pytest.raises(RuntimeError, match="l = 3"):
+    with pytest.raises(RuntimeError, match="l = 4"):
         cosx.SemiNumericalExchange(b, atom_grids=(offs, np.zeros((3, 3)), np.ones(3)), projector=None)
 
 

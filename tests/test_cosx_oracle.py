@@ -88,13 +88,13 @@ def test_esp_s_gaussian_closed_forms(oracle):
         assert np.abs(Vlr - exact).max() < 5e-14
 
 
-def _two_centre_basis(pure):
+def _two_centre_basis(pure, ls=range(4)):
     Z = np.array([6, 8], dtype=np.int32)
     pos = np.array([[0.0, 0.0, 0.0], [1.1, -0.7, 0.9]])
     b = aobasis.AOBasis(Z, pos, [], pure, "test")
     rng = np.random.default_rng(5)
     for a in range(2):
-        for l in range(4):
+        for l in ls:
             exps = np.array([1.9 - 0.3 * l + 0.2 * a, 0.6 + 0.1 * l])
             coefs = rng.uniform(0.3, 1.0, 2)
             b.shells.append(aobasis.Shell(l, pos[a].copy(), exps, aobasis.incorporate_shell_norm(l, exps, coefs), a))
@@ -128,6 +128,31 @@ def test_esp_matches_quadrature_of_collocated_aos(oracle, pure):
                                     sq.origin, pure, C[None, :])[0]
                 blk = Vq[fb[p]:fb[p] + V.shape[0], fb[q]:fb[q] + V.shape[1]]
                 assert np.abs(V - blk).max() < 2e-8, (p, q, np.abs(V - blk).max())
+
+
+@pytest.mark.parametrize("pure", [False, True])
+def test_esp_g_shells_match_quadrature(oracle, pure):
+    """the same check for g shells (COSX handles def2-QZVP): (4, lb) and (la, 4) blocks, one- and two-centre, up to L = 8"""
+    O = oracle
+    Z, pos, b = _two_centre_basis(pure, ls=(0, 2, 4))
+    ob = O.Basis(b.as_arrays())
+    pts, w, _ = O.molecular_grid(Z, pos, ob, O.default_grid_settings(max_angular_points=590, min_angular_points=590,
+                                                                    reduced_first_row_element_grid=0))
+    phi = np.zeros((len(w), ob.nbf))
+    fb = b.first_bf
+    for s, sh in enumerate(b.shells):
+        v = O.collocate_shell(sh.l, int(pure), pts, sh.coefficients, sh.exponents, sh.origin, 0)[0]
+        phi[:, fb[s]:fb[s] + v.shape[0]] = v.T * O.lib().orc_common_fac(sh.l, int(pure))
+    C = np.array([7.0, 5.0, -6.0])
+    Vq = phi.T @ (phi * (w / np.linalg.norm(pts - C, axis=1))[:, None])
+    for p, sp in enumerate(b.shells):
+        for q, sq in enumerate(b.shells):
+            if 4 not in (sp.l, sq.l):
+                continue
+            V = O.cosx_esp_pair(sp.l, sq.l, sp.exponents, sq.exponents, sp.coefficients, sq.coefficients, sp.origin,
+                                sq.origin, pure, C[None, :])[0]
+            blk = Vq[fb[p]:fb[p] + V.shape[0], fb[q]:fb[q] + V.shape[1]]
+            assert np.abs(V - blk).max() < 5e-8, (p, q, np.abs(V - blk).max())
 
 
 @pytest.mark.parametrize("pure", [False, True])
