@@ -292,6 +292,12 @@ typedef struct {
   double radial_precision; /* 1e-12 */
   int reduced_first_row_element_grid; /* 1 */
   int treutler_alrichs_adjustment;    /* 1 */
+  int pruning_scheme;      /* 0 = NWChem (default); 1 = None: max_angular_points on every radial shell, the rule of
+                              GridSettings::for_sgx (src/numint/grid_settings.cpp:59-69) */
+  double int_acc;          /* > 0: ORCA IntAcc radial point count nr = 15 IntAcc - 40 + 5 row (grid_settings.cpp:176-181) */
+  int angular_regions[5];  /* [0] > 0: the COSX grids of GridSettings::for_cosx (grid_settings.cpp:71-103): Treutler-
+                              Ahlrichs M4 radial grid scaled by the Bragg radius and ORCA 5-region angular pruning
+                              (src/numint/grid_utils.cpp:296-335,559-572,598-611,693-705) */
 } occ_xc_grid_settings_t;
 typedef struct occ_xc_grid occ_xc_grid;
 /* Lebedev-Laikov tables are data (src/numint/lebedev.cpp): rows of x, y, z, w; register each order once */

@@ -56,7 +56,8 @@ class InfoT(C.Structure):
 
 class GridSettingsT(C.Structure):
     _fields_ = [("max_angular_points", C.c_int), ("min_angular_points", C.c_int), ("radial_precision", C.c_double),
-                ("reduced_first_row_element_grid", C.c_int), ("treutler_alrichs_adjustment", C.c_int)]
+                ("reduced_first_row_element_grid", C.c_int), ("treutler_alrichs_adjustment", C.c_int),
+                ("pruning_scheme", C.c_int), ("int_acc", C.c_double), ("angular_regions", C.c_int * 5)]
 
 
 LEAF_DTYPE = np.dtype([("offset", np.uint64), ("count", np.uint64), ("center", np.float64, 3), ("radius", np.float64)])

@@ -42,6 +42,11 @@ def sgx_grid_settings(angular_points: int = 50, radial_precision: float = 1e-5) 
     return GridSettings(angular_points, angular_points, radial_precision, False, True)
 
 
+def cosx_grid_settings(level: int = 1) -> GridSettings:
+    """GridSettings::for_cosx(level) — the grid HartreeFock::set_cosx_exchange builds the engine on (src/qm/hf.cpp:62-68)"""
+    return GridSettings.for_cosx(level)
+
+
 def batch_shard(atom_offsets, rank: int, world_size: int):
     """(start, count) of the grid batches rank `rank` owns: blocks of 128 consecutive points of each atom grid
     (seminumerical_exchange.cpp:676-699), numbered over the whole molecule and dealt round-robin — the rule

@@ -116,6 +116,26 @@ Radial lmg_radial(int Z, double eps, double alpha_max, int l_max, const std::vec
   return g;
 }
 
+// generate_treutler_alrichs_radial_grid (grid_utils.cpp:559-572) with the scaling of generate_atom_grid's COSX branch
+// (:600-611): nodes and weights times the Bragg radius rm, then r^2 folded into the weights
+Radial treutler_ahlrichs_radial(int n, double rm) {
+  Radial g;
+  g.r.resize(n);
+  g.w.resize(n);
+  const double step = M_PI / (n + 1), ln2 = 1 / std::log(2.0);
+  for (int i = 1; i <= n; ++i) {
+    const double x = std::cos(i * step);
+    const double t1 = ln2 * std::pow(1 + x, 0.6), t2 = std::log((1 - x) / 2);
+    const double r = (-t1 * t2) * rm;
+    double w = step * std::sin(i * step) * t1 * (-0.6 / (1 + x) * t2 + 1 / (1 - x));
+    w *= rm;
+    w *= r * r;
+    g.r[n - i] = r;
+    g.w[n - i] = w;
+  }
+  return g;
+}
+
 // prune_nwchem_scheme, grid_utils.cpp:234-274: Lebedev order per radial shell
 int pruned_order(int Z, int max_angular, double r) {
   if (max_angular < 50) return max_angular;
@@ -297,7 +317,8 @@ int occ_xc_grid_create(int natoms, const int *Z, const double *pos, const occ_xc
     return occ_xc_set_error("occ_xc_grid_create: null argument (shell_atom is required)");
   occ_xc_grid_settings_t s = *settings;
   // MolecularGrid::ensure_settings, molecular_grid.cpp:133-181
-  if (s.max_angular_points < s.min_angular_points) s.max_angular_points = s.min_angular_points + 1;
+  const bool orca = s.angular_regions[0] > 0; // has_angular_regions(): the COSX grids of GridSettings::for_cosx
+  if (!orca && s.max_angular_points < s.min_angular_points) s.max_angular_points = s.min_angular_points + 1;
   s.max_angular_points = lebedev_at_or_above(s.max_angular_points);
   s.min_angular_points = lebedev_at_or_above(s.min_angular_points);
   if (s.max_angular_points < 0 || s.min_angular_points < 0)
@@ -324,7 +345,20 @@ int occ_xc_grid_create(int natoms, const int *Z, const double *pos, const occ_xc
   for (int a = 0; a < natoms; ++a) {
     if (egrids.count(Z[a])) continue;
     Radial rad;
-    if (!has_shells[a] || amax[a] <= 0.0 || lmax <= 0) // generate_atom_grid defaults, grid_utils.cpp:617-626
+    int regions[5] = {0, 0, 0, 0, 0};
+    if (orca) { // grid_utils.cpp:588-611: IntAcc radial count, Treutler-Ahlrichs nodes scaled by the Bragg radius
+      int nr = 50;
+      if (s.int_acc > 0) {
+        const int z = Z[a];
+        const int row = z <= 2 ? 1 : (z <= 10 ? 2 : (z <= 18 ? 3 : (z <= 36 ? 4 : (z <= 54 ? 5 : (z <= 86 ? 6 : 7)))));
+        nr = static_cast<int>(std::max(1.0, std::round((15.0 * s.int_acc - 40.0) + 5.0 * row))); // grid_settings.cpp:176-181
+      }
+      rad = treutler_ahlrichs_radial(nr, bragg_bohr(Z[a]));
+      for (int k = 0; k < 5; ++k) { // grid_utils.cpp:693-701
+        regions[k] = (s.reduced_first_row_element_grid && Z[a] < 3) ? lebedev_below(s.angular_regions[k]) : s.angular_regions[k];
+        if (lebedev_at_or_above(regions[k]) < 0) return occ_xc_set_error("Requested number of angular points exceeds 5810");
+      }
+    } else if (!has_shells[a] || amax[a] <= 0.0 || lmax <= 0) // generate_atom_grid defaults, grid_utils.cpp:617-626
       rad = lmg_radial(Z[a], s.radial_precision, 20.0, 3, std::vector<double>(4, 0.1));
     else
       rad = lmg_radial(Z[a], s.radial_precision, amax[a], lmax, amin[a]);
@@ -333,7 +367,16 @@ int occ_xc_grid_create(int natoms, const int *Z, const double *pos, const occ_xc
     ElementGrid eg;
     eg.nradial = static_cast<int>(rad.r.size());
     for (size_t i = 0; i < rad.r.size(); ++i) {
-      const int order = lebedev_at_or_above(pruned_order(Z[a], max_ang, rad.r[i]));
+      int order;
+      if (orca) { // prune_orca_scheme, grid_utils.cpp:296-335
+        const double R = bragg_bohr(Z[a]), r = rad.r[i];
+        const int region = r < 0.25 * R ? 0 : (r < 0.50 * R ? 1 : (r < 1.00 * R ? 2 : (r < 2.50 * R ? 3 : 4)));
+        order = lebedev_at_or_above(regions[region]);
+      } else if (s.pruning_scheme == 1) { // PruningScheme::None, grid_utils.cpp:719-722
+        order = max_ang;
+      } else {
+        order = lebedev_at_or_above(pruned_order(Z[a], max_ang, rad.r[i]));
+      }
       auto it = lebedev_tables().find(order);
       if (it == lebedev_tables().end())
         return occ_xc_set_error(("Lebedev table of order " + std::to_string(order) + " not registered").c_str());

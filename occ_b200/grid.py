@@ -24,6 +24,23 @@ class GridSettings:
     radial_precision: float = 1e-12
     reduced_first_row_element_grid: bool = True
     treutler_alrichs_adjustment: bool = True
+    pruning_scheme: int = 0            # 0 NWChem, 1 None (uniform angular order: GridSettings::for_sgx)
+    int_acc: float = 0.0               # ORCA IntAcc (GridSettings::for_cosx)
+    angular_regions: tuple = (0, 0, 0, 0, 0)   # ORCA 5-region angular orders; [0] > 0 selects the COSX grid producer
+
+    @staticmethod
+    def for_sgx(angular_points: int = 50) -> "GridSettings":
+        """GridSettings::for_sgx (src/numint/grid_settings.cpp:59-69)"""
+        return GridSettings(angular_points, angular_points, 1e-5, False, True, 1)
+
+    @staticmethod
+    def for_cosx(level: int = 1) -> "GridSettings":
+        """GridSettings::for_cosx(COSXGridLevel) (src/numint/grid_settings.cpp:10-18,71-103): ORCA GRIDX 1 / 2 / 3 —
+        IntAcc radial count, Treutler-Ahlrichs radial nodes, 5-region angular pruning, H / He one Lebedev level lower"""
+        table = {1: (3.816, (14, 26, 50, 50, 26), 50, 14), 2: (4.020, (14, 26, 50, 110, 50), 110, 14),
+                 3: (4.338, (26, 50, 110, 194, 110), 194, 26)}
+        ia, regions, mx, mn = table[int(level)]
+        return GridSettings(mx, mn, 1e-12, True, True, 0, ia, regions)
 
     @staticmethod
     def from_grid_quality(quality: str) -> "GridSettings":
@@ -39,7 +56,8 @@ class MolecularGrid:
         self.settings = settings or GridSettings()
         s = self.settings
         st = GridSettingsT(s.max_angular_points, s.min_angular_points, s.radial_precision,
-                           int(s.reduced_first_row_element_grid), int(s.treutler_alrichs_adjustment))
+                           int(s.reduced_first_row_element_grid), int(s.treutler_alrichs_adjustment),
+                           int(s.pruning_scheme), float(s.int_acc), (C.c_int * 5)(*[int(x) for x in s.angular_regions]))
         ba = BasisArrays(basis.as_arrays())
         Z = np.ascontiguousarray(basis.atomic_numbers, dtype=np.int32)
         pos = np.ascontiguousarray(basis.positions, dtype=np.float64)

@@ -49,7 +49,8 @@ class BasisT(C.Structure):
 
 class GridSettingsT(C.Structure):
     _fields_ = [("max_angular_points", C.c_int), ("min_angular_points", C.c_int), ("radial_precision", C.c_double),
-                ("reduced_first_row_element_grid", C.c_int), ("treutler_alrichs_adjustment", C.c_int)]
+                ("reduced_first_row_element_grid", C.c_int), ("treutler_alrichs_adjustment", C.c_int),
+                ("pruning_scheme", C.c_int), ("int_acc", C.c_double), ("angular_regions", C.c_int * 5)]
 
 
 class LeafT(C.Structure):
@@ -159,8 +160,21 @@ def decay_cutoff(basis: Basis, threshold=1e-10):
 def default_grid_settings(**kw):
     s = GridSettingsT(302, 110, 1e-12, 1, 1)
     for k, v in kw.items():
+        if k == "angular_regions":
+            v = (C.c_int * 5)(*[int(x) for x in v])
         setattr(s, k, v)
     return s
+
+
+# GridSettings::for_cosx (src/numint/grid_settings.cpp:10-18,71-103): IntAcc, 5 angular regions, max / min angular points
+COSX_GRIDS = {1: (3.816, (14, 26, 50, 50, 26), 50, 14), 2: (4.020, (14, 26, 50, 110, 50), 110, 14),
+              3: (4.338, (26, 50, 110, 194, 110), 194, 26)}
+
+
+def cosx_grid_settings(level: int = 1):
+    ia, regions, mx, mn = COSX_GRIDS[int(level)]
+    return default_grid_settings(max_angular_points=mx, min_angular_points=mn, int_acc=ia, angular_regions=regions,
+                                 reduced_first_row_element_grid=1, treutler_alrichs_adjustment=1)
 
 
 def molecular_grid(atomic_numbers, positions, basis: Basis, settings=None, nthreads=None):

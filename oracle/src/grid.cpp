@@ -133,6 +133,41 @@ static Radial lmg_radial(int Z, double precision, double alpha_max, int l_max, c
   return g;
 }
 
+// generate_treutler_alrichs_radial_grid, grid_utils.cpp:559-572 (points ascending)
+static Radial treutler_ahlrichs_radial(size_t n) {
+  Radial g;
+  g.r.resize(n);
+  g.w.resize(n);
+  const double step = M_PI / (n + 1), ln2 = 1 / std::log(2.0);
+  for (size_t i = 1; i <= n; ++i) {
+    const double x = std::cos(i * step);
+    const double tmp1 = ln2 * std::pow(1 + x, 0.6);
+    const double tmp2 = std::log((1 - x) / 2);
+    g.r[n - i] = -tmp1 * tmp2;
+    g.w[n - i] = step * std::sin(i * step) * tmp1 * (-0.6 / (1 + x) * tmp2 + 1 / (1 - x));
+  }
+  return g;
+}
+
+// calculate_radial_points_orca, grid_settings.cpp:176-181 with get_periodic_row (:21-30)
+static size_t radial_points_orca(double int_acc, int Z) {
+  const int row = Z <= 2 ? 1 : (Z <= 10 ? 2 : (Z <= 18 ? 3 : (Z <= 36 ? 4 : (Z <= 54 ? 5 : (Z <= 86 ? 6 : 7)))));
+  const double nr = (15.0 * int_acc - 40.0) + 5.0 * row;
+  return static_cast<size_t>(std::max(1.0, std::round(nr)));
+}
+
+// prune_orca_scheme, grid_utils.cpp:296-335
+static std::vector<int> prune_orca(int Z, const int regions[5], const std::vector<double> &radii) {
+  const double R = atomic_radius(Z);
+  std::vector<int> out(radii.size());
+  for (size_t i = 0; i < radii.size(); ++i) {
+    const double r = radii[i];
+    const int region = r < 0.25 * R ? 0 : (r < 0.50 * R ? 1 : (r < 1.00 * R ? 2 : (r < 2.50 * R ? 3 : 4)));
+    out[i] = level_at_or_above(regions[region]);
+  }
+  return out;
+}
+
 // grid_utils.cpp:234-274
 static std::vector<int> prune_nwchem(int Z, int max_angular, const std::vector<double> &radii) {
   std::vector<int> out(radii.size());
@@ -182,7 +217,17 @@ const std::vector<double> *lebedev_table(int n) {
 static AtomGrid generate_atom_grid(int Z, const orc_grid_settings_t &s, double alpha_max, int l_max,
                                    const std::vector<double> &alpha_min) {
   Radial radial;
-  if (alpha_max <= 0.0 || l_max <= 0 || alpha_min.empty()) { // grid_utils.cpp:617-626 defaults
+  const bool orca = s.angular_regions[0] > 0; // has_angular_regions(), :598
+  if (orca) { // :600-611: Treutler-Ahlrichs radial grid scaled by the Bragg radius, r^2 folded into the weights
+    const size_t n_radial = s.int_acc > 0 ? radial_points_orca(s.int_acc, Z) : 50; // :588-596
+    radial = treutler_ahlrichs_radial(n_radial);
+    const double rm = atomic_radius(Z);
+    for (size_t i = 0; i < n_radial; ++i) {
+      radial.r[i] *= rm;
+      radial.w[i] *= rm;
+      radial.w[i] *= radial.r[i] * radial.r[i];
+    }
+  } else if (alpha_max <= 0.0 || l_max <= 0 || alpha_min.empty()) { // grid_utils.cpp:617-626 defaults
     std::vector<double> def(4, 0.1);
     radial = lmg_radial(Z, s.radial_precision, 20.0, 3, def.data());
   } else {
@@ -191,7 +236,17 @@ static AtomGrid generate_atom_grid(int Z, const orc_grid_settings_t &s, double a
   for (auto &w : radial.w) w *= 4 * M_PI; // :679
   int max_angular = s.max_angular_points;
   if (s.reduced_first_row_element_grid && Z < 3) max_angular = level_below(max_angular); // :682-687
-  std::vector<int> n_angular = prune_nwchem(Z, max_angular, radial.r);
+  std::vector<int> n_angular;
+  if (orca) { // :693-705
+    int regions[5];
+    for (int k = 0; k < 5; ++k)
+      regions[k] = (s.reduced_first_row_element_grid && Z < 3) ? level_below(s.angular_regions[k]) : s.angular_regions[k];
+    n_angular = prune_orca(Z, regions, radial.r);
+  } else if (s.pruning_scheme == 1) { // PruningScheme::None, :719-722
+    n_angular.assign(radial.r.size(), max_angular);
+  } else {
+    n_angular = prune_nwchem(Z, max_angular, radial.r);
+  }
   size_t total = 0;
   for (int na : n_angular) total += level_at_or_above(na);
   AtomGrid g;
@@ -291,7 +346,8 @@ void *orc_molecular_grid_create(int natoms, const int *Z, const double *pos, con
   using namespace orc;
   orc_grid_settings_t s = *settings;
   // molecular_grid.cpp:133-181 ensure_settings
-  if (s.max_angular_points < s.min_angular_points) s.max_angular_points = s.min_angular_points + 1;
+  if (s.angular_regions[0] <= 0 && s.max_angular_points < s.min_angular_points)
+    s.max_angular_points = s.min_angular_points + 1;
   s.max_angular_points = level_at_or_above(s.max_angular_points);
   s.min_angular_points = level_at_or_above(s.min_angular_points);
 

@@ -248,3 +248,23 @@ def test_cosx_ragged_atom_grids(oracle):
     Kref, _ = O.cosx_compute_K(ob, off, pts, w, np.eye(b.nbf), D)
     assert np.abs(K - Kref).max() < TOL
     sgx.close()
+
+
+def test_cosx_on_the_for_cosx_grid(oracle):
+    """the engine as HartreeFock::set_cosx_exchange builds it (src/qm/hf.cpp:62-68): GridSettings::for_cosx(Grid1) from the
+    product's own grid producer, projector solved by the mirror, K against the oracle on the oracle's copy of that grid"""
+    from occ_b200 import cosx
+    O = oracle
+    Z, pos = molecules.MOLECULES["water"]()
+    b = aobasis.AOBasis.load(Z, pos, "def2-svp", pure=True)
+    ob = O.Basis(b.as_arrays())
+    sgx = cosx.SemiNumericalExchange(b, settings=cosx.cosx_grid_settings(1))
+    pts, w, info = O.molecular_grid(Z, pos, ob, O.cosx_grid_settings(1))
+    off = O.cosx_atom_grids(pts, info)
+    assert sgx.num_grid_points() == len(w) and np.array_equal(sgx.atom_offsets, off)
+    P, S, Sn = O.cosx_overlap_projector(ob, off, pts, w)
+    D = molecules.synthetic_density(b, 1, seed=7) * 0.5
+    K = sgx.compute_K(D)
+    Kref, _ = O.cosx_compute_K(ob, off, pts, w, P, D)
+    assert np.abs(K - Kref).max() < 1e-8 * max(1.0, np.abs(Kref).max())   # the projector is solved on either side
+    sgx.close()

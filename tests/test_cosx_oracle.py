@@ -15,7 +15,7 @@ import math
 import numpy as np
 import pytest
 
-from occ_b200 import aobasis
+from occ_b200 import aobasis, molecules
 
 
 def _ref_or_skip(O):
@@ -249,3 +249,65 @@ def test_significant_pairs_and_screening_inputs(oracle, case):
     p, q = pq[k]
     pmin = min(b.shells[p].exponents) + min(b.shells[q].exponents)
     assert ext[k] == pytest.approx(math.sqrt(27.631021115928547 / pmin), rel=1e-14)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the COSX grid producer: GridSettings::for_cosx (src/numint/grid_settings.cpp:10-18,71-103,176-181) and the ORCA branch
+# of generate_atom_grid (src/numint/grid_utils.cpp:296-335,559-572,588-611,693-705)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("level,nr_h,nr_o", [(1, 22, 27), (2, 25, 30), (3, 30, 35)])
+def test_cosx_grid_levels_follow_the_orca_rules(oracle, level, nr_h, nr_o):
+    """radial counts nr = round(15 IntAcc - 40 + 5 row); the 5-region angular orders (H / He one Lebedev level lower);
+    Treutler-Ahlrichs nodes scaled by the Bragg radius; the partitioned grid integrates a density"""
+    O = oracle
+    Z, pos = molecules.MOLECULES["water"]()
+    b = aobasis.AOBasis.load(Z, pos, "def2-svp")
+    ob = O.Basis(b.as_arrays())
+    pts, w, info = O.molecular_grid(Z, pos, ob, O.cosx_grid_settings(level))
+    assert info["atom_nradial"] == [nr_o, nr_h, nr_h]
+    off = O.cosx_atom_grids(pts, info)
+    regions = np.array(O.COSX_GRIDS[level][1])
+    below = {14: 6, 26: 14, 50: 38, 110: 86, 194: 170}
+    bragg = {1: 0.35, 8: 0.60}                                 # Angstrom (grid_utils.cpp bragg_radii: H 0.35, O 0.60)
+    for a in range(3):
+        P = pts[off[a]:off[a + 1]] - pos[a]
+        r = np.linalg.norm(P, axis=1)
+        shells, counts = np.unique(np.round(r, 10), return_counts=True)
+        assert len(shells) == info["atom_nradial"][a]
+        R = bragg[int(Z[a])] / 0.52917721092
+        reg = np.searchsorted([0.25 * R, 0.5 * R, 1.0 * R, 2.5 * R], shells, side="right")
+        want = regions[reg] if Z[a] > 2 else np.array([below[int(x)] for x in regions[reg]])
+        assert np.array_equal(counts, want), (a, counts, want)
+        # Treutler-Ahlrichs nodes (grid_utils.cpp:559-572) times the Bragg radius
+        n = len(shells)
+        i = np.arange(1, n + 1)
+        x = np.cos(i * np.pi / (n + 1))
+        nodes = np.sort(-(1 / np.log(2)) * (1 + x) ** 0.6 * np.log((1 - x) / 2)) * R
+        assert np.abs(shells - nodes).max() < 1e-9 * nodes.max()
+    # the Becke-partitioned COSX grid integrates the synthetic density's electron count to grid accuracy
+    D2 = molecules.synthetic_density(b, 1)
+    phi = np.zeros((len(w), b.nbf))
+    col = 0
+    for sh in b.shells:
+        v = O.collocate_shell(sh.l, int(b.pure), pts, sh.coefficients, sh.exponents, sh.origin, 0)[0].T
+        phi[:, col:col + v.shape[1]] = v * O.lib().orc_common_fac(int(sh.l), int(b.pure))
+        col += v.shape[1]
+    S = O.cosx_overlap(ob)
+    n_exact = float((D2 * S).sum())
+    n_grid = float(((phi @ D2) * phi).sum(1) @ w)
+    assert abs(n_grid - n_exact) < {1: 3e-2, 2: 2e-2, 3: 5e-3}[level] * abs(n_exact)
+
+
+def test_for_sgx_uniform_angular_grid(oracle):
+    """GridSettings::for_sgx: PruningScheme::None keeps max_angular_points on every radial shell, also at >= 50 points
+    where the NWChem scheme switches to its own level table (grid_utils.cpp:240-250,719-722)"""
+    O = oracle
+    Z, pos = molecules.MOLECULES["water"]()
+    b = aobasis.AOBasis.load(Z, pos, "def2-svp")
+    ob = O.Basis(b.as_arrays())
+    kw = dict(max_angular_points=50, min_angular_points=50, radial_precision=1e-5, reduced_first_row_element_grid=0)
+    p0, w0, i0 = O.molecular_grid(Z, pos, ob, O.default_grid_settings(**kw))
+    p1, w1, i1 = O.molecular_grid(Z, pos, ob, O.default_grid_settings(pruning_scheme=1, **kw))
+    assert i1["atom_nradial"] == i0["atom_nradial"]
+    assert i1["atom_npts"] == [50 * n for n in i1["atom_nradial"]]
+    assert i0["atom_npts"] != i1["atom_npts"]

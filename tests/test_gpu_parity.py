@@ -502,3 +502,28 @@ def test_hirshfeld_partition_and_cube_density_over_the_gpu_density(oracle, nspin
     # cube grid: same numbers as the point-wise entry
     cube = hirshfeld.cube_density(b, 2 * D, [-1.0, -1.0, -1.0], (5, 4, 3), spinorbital_kind=kind)
     assert cube.shape == ((5, 4, 3) if nspin == 1 else (2, 5, 4, 3)) and np.all(cube >= -1e-12) and cube.max() > 1e-3
+
+
+@pytest.mark.parametrize("which", ["cosx1", "cosx3", "sgx50"])
+def test_product_cosx_grid_producers_match_oracle(oracle, which):
+    """GridSettings::for_cosx (ORCA IntAcc radial count, Treutler-Ahlrichs nodes, 5-region pruning) and for_sgx
+    (PruningScheme::None) through occ_xc_grid_create vs the oracle: same points bit for bit, weights to 1e-13"""
+    from occ_b200 import grid
+    Z, pos = molecules.MOLECULES["benzene"]()
+    b = aobasis.AOBasis.load(Z, pos, "def2-svp")
+    ob = oracle.Basis(b.as_arrays())
+    if which == "sgx50":
+        gs, os_ = grid.GridSettings.for_sgx(50), oracle.default_grid_settings(
+            max_angular_points=50, min_angular_points=50, radial_precision=1e-5, reduced_first_row_element_grid=0,
+            pruning_scheme=1)
+    else:
+        level = int(which[-1])
+        gs, os_ = grid.GridSettings.for_cosx(level), oracle.cosx_grid_settings(level)
+    mg = grid.MolecularGrid(b, gs)
+    pts, w = mg.points()
+    counts = [mg.atom_info(a) for a in range(mg.natoms)]
+    mg.close()
+    opts, ow, info = oracle.molecular_grid(Z, pos, ob, os_)
+    assert [c[0] for c in counts] == info["atom_npts"] and [c[1] for c in counts] == info["atom_nradial"]
+    assert np.array_equal(pts, opts)
+    assert np.abs(w - ow).max() < 1e-13 * np.abs(ow).max()
