@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -484,7 +485,10 @@ int occ_cosx_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_
     const std::vector<double> seg_major = boys_table();
     constexpr int N = 8, MaxM = 16;
     const size_t nseg = seg_major.size() / (N * MaxM);
-    std::vector<double> order_major(seg_major.size());
+    static_assert(MaxM == COSX_BOYS_ORDERS, "device table layout");
+    std::vector<double> order_major(seg_major.size() + COSX_BOYS_SEGMENTS);
+    for (int sg = 0; sg < COSX_BOYS_SEGMENTS; ++sg) // e^-T at the segment midpoints (k_cosx_esp.cuh add_seeds)
+      order_major[seg_major.size() + sg] = std::exp(-(sg + 0.5) / 7.0);
     for (size_t sg = 0; sg < nseg; ++sg)
       for (int m = 0; m < MaxM; ++m)
         std::memcpy(&order_major[(m * nseg + sg) * N], &seg_major[(sg * MaxM + m) * N], N * sizeof(double));
@@ -585,6 +589,10 @@ static int sweep(occ_cosx_handle *h, const double *D2q, double precision, double
   P.w_full = w_full;
   P.w_lr = w_lr;
   P.omega = omega;
+  {
+    const char *dbg = std::getenv("OCC_COSX_DEBUG");
+    P.debug = dbg ? std::atoi(dbg) : 0;
+  }
   P.stats = h->collect ? h->d_stats : nullptr;
   const long long slab = static_cast<long long>(nbp) * TILE_P;
   float ms[4] = {0, 0, 0, 0};

@@ -24,6 +24,8 @@ struct CosxPair {
 // primitive pool record of a class (la, lb), ne = (la+1)(lb+1)(la+lb+1):
 //   [0] p  [1..3] P  [4] unused  [5 .. 5+ne) prefactor * E^x  [5+ne ..) E^y  [5+2ne ..) E^z      (ecoeffs.h layout)
 constexpr int COSX_PRIM_HDR = 5;
+constexpr int COSX_BOYS_ORDERS = 16;
+constexpr int COSX_BOYS_EXP_OFFSET = COSX_BOYS_ORDERS * 253 * 8; // behind the Boys rows: exp(-(segment + 1/2) / 7), 253 values
 constexpr int COSX_BOYS_SEGMENTS = 253; // rows per order of the device Boys table (boys.h: 252 segments on [0, 36) + 1)
 
 struct CosxParams {
@@ -43,6 +45,7 @@ struct CosxParams {
   int pure;
   double margin;
   double w_full, w_lr, omega;
+  int debug;                        // timing experiments (env OCC_COSX_DEBUG): 1 = no G atomics, 2 = no primitive loop
   unsigned long long *stats;        // [0] pair evaluations, [1] sum npt*nprim*nherm*nab of them; may be NULL
 };
 

@@ -4,6 +4,10 @@
 #include "cosx_internal.h"
 #include <cuda_runtime.h>
 
+#ifndef COSX_EXP_TABLE
+#define COSX_EXP_TABLE 1
+#endif
+
 namespace xcb {
 
 __host__ __device__ constexpr int cx_ncart(int l) { return (l + 1) * (l + 2) / 2; }
@@ -68,8 +72,11 @@ __device__ __forceinline__ void add_seeds(const double *__restrict__ tab, double
   const double T = p * r2;
   double F[L + 1];
   if (T >= 36.0) {
-    const double inv = 1.0 / T;
-    double Fm = 0.88622692545275801365 * sqrt(inv);
+    // F_m = (2m-1)!! / 2^(m+1) sqrt(pi / T^(2m+1)) (boys.h:17-64).  One reciprocal square root (MUFU.RSQ64H + Newton,
+    // 2 ulp) instead of the division and the square root of the reference's form: those two cost more than the
+    // table path they stand in for, and most s-s / p-s evaluations of a large molecule take this branch
+    const double rs = rsqrt(T), inv = rs * rs;
+    double Fm = 0.88622692545275801365 * rs;
     F[0] = Fm;
 #pragma unroll
     for (int i = 1; i <= L; ++i) {
@@ -90,7 +97,23 @@ __device__ __forceinline__ void add_seeds(const double *__restrict__ tab, double
     };
     F[L] = row(L);
     if (L > 0) { // (a second table row for L = 1 instead of exp + recursion was measured: +48 ms on valinomycin, L1-bound)
+#if COSX_EXP_TABLE
+      // e^-T = e^-(seg + 1/2)/7 . e^(-xd/7): the segment's midpoint value from a 2 KB table behind the Boys rows, the
+      // rest (|xd / 7| <= 1/14) by a degree-9 Taylor polynomial (remainder 1e-18) — about half the instructions of exp()
+      const double y = xd * (-1.0 / 7.0);
+      double ey = fma(y, 1.0 / 362880.0, 1.0 / 40320.0);
+      ey = fma(ey, y, 1.0 / 5040.0);
+      ey = fma(ey, y, 1.0 / 720.0);
+      ey = fma(ey, y, 1.0 / 120.0);
+      ey = fma(ey, y, 1.0 / 24.0);
+      ey = fma(ey, y, 1.0 / 6.0);
+      ey = fma(ey, y, 0.5);
+      ey = fma(ey, y, 1.0);
+      ey = fma(ey, y, 1.0);
+      const double e = __ldg(tab + COSX_BOYS_EXP_OFFSET + seg) * ey, T2 = 2.0 * T;
+#else
       const double e = exp(-T), T2 = 2.0 * T;
+#endif
 #pragma unroll
       for (int m = L - 1; m >= 0; --m) F[m] = (T2 * F[m + 1] + e) * (1.0 / (2 * m + 1));
     }
@@ -428,6 +451,14 @@ __host__ __device__ constexpr int cosx_min_ctas(int la, int lb) {
   return t[la][lb];
 }
 
+// which classes run the warp-private kernel (k_cosx_esp_w): those with la + lb <= COSX_WARP_MAXL.  Measured on valinomycin
+// (whole compute_K_mo call, profiles/r02_experiments.md): s-s 1406 -> 1394 ms; every class with L >= 1 is SLOWER there
+// (L = 1 +22 ms, L = 2 +52 ms, all classes 1534 ms) because its primitive records then come from global memory in the
+// inner loop, so only s-s uses it.  OCC_COSX_DEBUG bit 8 forces the staged kernel everywhere (A/B timing).
+#ifndef COSX_WARP_MAXL
+#define COSX_WARP_MAXL 0
+#endif
+
 struct PairLite {
   int p, q, bfp, bfq, nprim, off;
 };
@@ -553,7 +584,7 @@ __global__ void __launch_bounds__(TILE_P, cosx_min_ctas(LA, LB)) k_cosx_esp(Cosx
           const int ns = min(pr.nprim - i0, STAGE - used);
           if (i0 == 0) {
             if (pr.p != cur_p) {
-              if (gp_dirty) flush_G<LA>(Gp, Gcol, cur_bfp, pure, P.c2s);
+              if (gp_dirty) if (!(P.debug & 1)) flush_G<LA>(Gp, Gcol, cur_bfp, pure, P.c2s);
               cur_p = pr.p;
               cur_bfp = pr.bfp;
               gp_dirty = false;
@@ -571,7 +602,7 @@ __global__ void __launch_bounds__(TILE_P, cosx_min_ctas(LA, LB)) k_cosx_esp(Cosx
             }
           }
 #pragma unroll(L == 0 ? 4 : (L <= 2 ? 2 : 1))
-          for (int sidx = 0; sidx < ns; ++sidx) {
+          for (int sidx = 0; sidx < ((P.debug & 2) ? 0 : ns); ++sidx) {
             const double *rec = s_pool[buf] + (used + sidx) * STRIDE;
             const double pe = rec[0];
             const double PCx = rec[1] - X, PCy = rec[2] - Y, PCz = rec[3] - Z; // rints_specialized.h:1457-1460: P - C
@@ -592,7 +623,7 @@ __global__ void __launch_bounds__(TILE_P, cosx_min_ctas(LA, LB)) k_cosx_esp(Cosx
           used += ns;
           i0 += ns;
           if (i0 < pr.nprim) break;
-          flush_G<LB>(Gq, Gcol, pr.bfq, pure, P.c2s);
+          if (!(P.debug & 1)) flush_G<LB>(Gq, Gcol, pr.bfq, pure, P.c2s);
           i0 = 0;
           ++li;
         }
@@ -645,7 +676,7 @@ __global__ void __launch_bounds__(TILE_P, cosx_min_ctas(LA, LB)) k_cosx_esp(Cosx
       const bool offdiag = pr.p != pr.q;
       if (i0 == 0) {
         if (pr.p != cur_p) {
-          if (gp_dirty) flush_G<LA>(Gp, Gcol, cur_bfp, pure, P.c2s);
+          if (gp_dirty) if (!(P.debug & 1)) flush_G<LA>(Gp, Gcol, cur_bfp, pure, P.c2s);
           cur_p = pr.p;
           cur_bfp = pr.bfp;
           gp_dirty = false;
@@ -664,7 +695,7 @@ __global__ void __launch_bounds__(TILE_P, cosx_min_ctas(LA, LB)) k_cosx_esp(Cosx
       }
       const int ns = min(STAGE, pr.nprim - i0);
 #pragma unroll(L == 0 ? 4 : (L <= 2 ? 2 : 1))
-      for (int s = 0; s < ns; ++s) {
+      for (int s = 0; s < ((P.debug & 2) ? 0 : ns); ++s) {
         const double *rec = s_pool[buf] + s * STRIDE;
         const double pe = rec[0];
         const double PCx = rec[1] - X, PCy = rec[2] - Y, PCz = rec[3] - Z; // rints_specialized.h:1457-1460: P - C
@@ -689,7 +720,7 @@ __global__ void __launch_bounds__(TILE_P, cosx_min_ctas(LA, LB)) k_cosx_esp(Cosx
       }
       i0 += STAGE;
       if (i0 >= pr.nprim) {
-        flush_G<LB>(Gq, Gcol, pr.bfq, pure, P.c2s);
+        if (!(P.debug & 1)) flush_G<LB>(Gq, Gcol, pr.bfq, pure, P.c2s);
         i0 = 0;
         ++li;
       }
@@ -698,7 +729,145 @@ __global__ void __launch_bounds__(TILE_P, cosx_min_ctas(LA, LB)) k_cosx_esp(Cosx
     }
     cp_async_wait<0>();
   }
-  if (gp_dirty) flush_G<LA>(Gp, Gcol, cur_bfp, pure, P.c2s);
+  if (gp_dirty) if (!(P.debug & 1)) flush_G<LA>(Gp, Gcol, cur_bfp, pure, P.c2s);
+}
+
+// Warp-private variant (COSX_WARP classes): after the CTA-wide screening round each WARP walks the survivor list on its
+// own — 32 grid points, no CTA barrier and no shared-memory staging inside the pair loop.  The primitive records are read
+// straight from global memory with warp-uniform (broadcast) loads, the F column values of the NEXT pair are fetched into
+// registers while the current pair is evaluated.  Measured motive (valinomycin, OCC_COSX_DEBUG=2): with the primitive
+// loop removed the staged pipeline still takes 734 of 1146 ms — two CTA barriers, the cp.async address arithmetic and the
+// shared-memory round trip per step cost more than the integrals of the low-l classes.
+template <int LA, int LB>
+__global__ void __launch_bounds__(TILE_P, cosx_min_ctas(LA, LB)) k_cosx_esp_w(CosxParams P, int pair0, int npairs, int chunk, int cls,
+                                                                               int ntiles, int nruns) {
+  constexpr int L = LA + LB, NE = (LA + 1) * (LB + 1) * (L + 1), STRIDE = COSX_PRIM_HDR + 3 * NE;
+  constexpr int NCA = cx_ncart(LA), NCB = cx_ncart(LB), NH = cx_nhermsum(L);
+  __shared__ PairLite s_pairs[TILE_P];
+  __shared__ int s_wcnt[TILE_P / 32];
+  const int tl = blockIdx.x % COSX_TILE_GROUP;
+  const int yrun = (blockIdx.x / COSX_TILE_GROUP) % nruns;
+  const int ltile = (blockIdx.x / (COSX_TILE_GROUP * nruns)) * COSX_TILE_GROUP + tl;
+  if (ltile >= ntiles) return;
+  const int tile = P.tile0 + ltile;
+  if (P.tile_skip[tile]) return;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int k0 = pair0 + yrun * chunk;
+  const int k1 = min(k0 + chunk, pair0 + npairs);
+  const double tcx = P.tcx[tile], tcy = P.tcy[tile], tcz = P.tcz[tile], lim = P.trad[tile] + P.margin;
+  const size_t pt = static_cast<size_t>(tile) * TILE_P + tid;
+  const double X = P.px[pt], Y = P.py[pt], Z = P.pz[pt], w = P.pw[pt];
+  const size_t slab = static_cast<size_t>(ltile) * P.nbp * TILE_P + tid;
+  const double *__restrict__ Fcol = P.F + slab;
+  double *Gcol = P.G + slab;
+  const double *__restrict__ pool = P.pool;
+  const bool pure = P.pure != 0;
+  const int nq_cols = (pure && LB > 0) ? 2 * LB + 1 : NCB;
+  const double w2 = P.omega * P.omega;
+
+  double Fp[NCA], Gp[NCA];
+  int cur_p = -1, cur_bfp = 0;
+  bool gp_dirty = false;
+  for (int kr = k0; kr < k1; kr += TILE_P) {
+    const int k = kr + tid;
+    bool keep = false;
+    CosxPair cand;
+    if (k < k1 && P.pair_active[k]) {
+      cand = P.pairs[k];
+      const double dx = cand.cx - tcx, dy = cand.cy - tcy, dz = cand.cz - tcz;
+      keep = !(sqrt(dx * dx + dy * dy + dz * dz) - cand.extent >= lim);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    __syncthreads(); // every warp is done with the previous round's survivor list
+    if (lane == 0) s_wcnt[wid] = __popc(bal);
+    __syncthreads();
+    int base = 0, nsurv = 0;
+#pragma unroll
+    for (int i = 0; i < TILE_P / 32; ++i) {
+      if (i < wid) base += s_wcnt[i];
+      nsurv += s_wcnt[i];
+    }
+    if (keep) s_pairs[base + __popc(bal & ((1u << lane) - 1u))] = PairLite{cand.p, cand.q, cand.bfp, cand.bfq, cand.nprim, cand.off};
+    __syncthreads();
+    if (nsurv == 0) continue;
+
+    // ---- warp-private walk over the survivors ----
+    double Fn[NCB]; // raw F columns of the next pair's q shell
+    {
+      const double *f = Fcol + static_cast<size_t>(s_pairs[0].bfq) * TILE_P;
+#pragma unroll
+      for (int c = 0; c < NCB; ++c) Fn[c] = c < nq_cols ? __ldg(f + static_cast<size_t>(c) * TILE_P) : 0.0;
+    }
+#pragma unroll 1
+    for (int li = 0; li < nsurv; ++li) {
+      const PairLite pr = s_pairs[li];
+      const bool offdiag = pr.p != pr.q;
+      double Fq[NCB], Gq[NCB];
+      if (!pure || LB == 0) {
+#pragma unroll
+        for (int c = 0; c < NCB; ++c) Fq[c] = w * Fn[c];
+      } else {
+        const double *T = c2s_of<LB>(P.c2s);
+#pragma unroll
+        for (int c = 0; c < NCB; ++c) Fq[c] = 0.0;
+#pragma unroll
+        for (int m = 0; m < 2 * LB + 1; ++m) {
+          const double f = w * Fn[m];
+#pragma unroll
+          for (int c = 0; c < NCB; ++c) Fq[c] += __ldg(T + m * NCB + c) * f;
+        }
+      }
+      if (li + 1 < nsurv) { // the next pair's F values travel while this pair is evaluated
+        const double *f = Fcol + static_cast<size_t>(s_pairs[li + 1].bfq) * TILE_P;
+#pragma unroll
+        for (int c = 0; c < NCB; ++c) Fn[c] = c < nq_cols ? __ldg(f + static_cast<size_t>(c) * TILE_P) : 0.0;
+      }
+      if (pr.p != cur_p) {
+        if (gp_dirty && !(P.debug & 1)) flush_G<LA>(Gp, Gcol, cur_bfp, pure, P.c2s);
+        cur_p = pr.p;
+        cur_bfp = pr.bfp;
+        gp_dirty = false;
+        load_F<LA>(Fp, Fcol, pr.bfp, w, pure, P.c2s);
+#pragma unroll
+        for (int i = 0; i < NCA; ++i) Gp[i] = 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < NCB; ++j) Gq[j] = 0.0;
+      gp_dirty = gp_dirty || offdiag;
+      if (P.stats && tid == 0) {
+        atomicAdd(P.stats + 2 * cls, 1ULL);
+        atomicAdd(P.stats + 2 * cls + 1, static_cast<unsigned long long>(pr.nprim) * P.counts[tile]);
+      }
+      const double *__restrict__ rec0 = pool + pr.off;
+      const int np = (P.debug & 2) ? 0 : pr.nprim;
+#pragma unroll(L == 0 ? 4 : (L <= 2 ? 2 : 1))
+      for (int i = 0; i < np; ++i) {
+        const double *__restrict__ rec = rec0 + static_cast<size_t>(i) * STRIDE;
+        const double pe = __ldg(rec);
+        const double PCx = __ldg(rec + 1) - X, PCy = __ldg(rec + 2) - Y, PCz = __ldg(rec + 3) - Z;
+        const double r2 = PCx * PCx + PCy * PCy + PCz * PCz;
+        double S[L + 1];
+#pragma unroll
+        for (int m = 0; m <= L; ++m) S[m] = 0.0;
+        if (P.w_full != 0.0) add_seeds<L>(P.boys, pe, r2, P.w_full, S);
+        if (P.w_lr != 0.0) {
+          const double sc = w2 / (pe + w2);
+          add_seeds<L>(P.boys, pe * sc, r2, P.w_lr * sqrt(sc), S);
+        }
+        if constexpr (L >= 4) {
+          prim_sliced<LA, LB>(rec + COSX_PRIM_HDR, rec + COSX_PRIM_HDR + NE, rec + COSX_PRIM_HDR + 2 * NE, S, PCx, PCy, PCz,
+                              Fp, Fq, Gp, Gq, offdiag);
+        } else {
+          double R[NH];
+          hermite_R<L>(S, PCx, PCy, PCz, R);
+          contract<LA, LB>(rec + COSX_PRIM_HDR, rec + COSX_PRIM_HDR + NE, rec + COSX_PRIM_HDR + 2 * NE, R, Fp, Fq, Gp, Gq,
+                           offdiag);
+        }
+      }
+      if (!(P.debug & 1)) flush_G<LB>(Gq, Gcol, pr.bfq, pure, P.c2s);
+    }
+  }
+  if (gp_dirty && !(P.debug & 1)) flush_G<LA>(Gp, Gcol, cur_bfp, pure, P.c2s);
 }
 
 template <int LA, int LB>
@@ -708,8 +877,15 @@ void launch_class(const CosxParams &P, int pair0, int npairs, int ntiles, cudaSt
   const int ngroups = (ntiles + COSX_TILE_GROUP - 1) / COSX_TILE_GROUP;
   while (static_cast<long long>(ngroups) * COSX_TILE_GROUP * ((npairs + chunk - 1) / chunk) > 0x7fffffffLL) chunk *= 2;
   const int nruns = (npairs + chunk - 1) / chunk;
+  if constexpr (LA + LB <= COSX_WARP_MAXL) {
+    if (!(P.debug & 256)) {
+      k_cosx_esp_w<LA, LB><<<ngroups * COSX_TILE_GROUP * nruns, TILE_P, 0, st>>>(P, pair0, npairs, chunk,
+                                                                                  LA * (COSX_MAX_L + 1) + LB, ntiles, nruns);
+      return;
+    }
+  }
   k_cosx_esp<LA, LB><<<ngroups * COSX_TILE_GROUP * nruns, TILE_P, 0, st>>>(P, pair0, npairs, chunk,
-                                                                            LA * (COSX_MAX_L + 1) + LB, ntiles, nruns);
+                                                                              LA * (COSX_MAX_L + 1) + LB, ntiles, nruns);
 }
 
 } // namespace xcb
