@@ -209,6 +209,55 @@ __global__ void k_becke(int natoms, const double *__restrict__ pos, const double
   if (valid) w[p] *= mine / total;
 }
 
+// The same partition with every unordered atom pair visited ONCE: v_{hi,lo} feeds cell[hi] (factor (1 - v)/2) and
+// cell[lo] (factor (1 + v)/2).  Walking hi ascending and lo < hi ascending hands cell[k] its factors in the order
+// j = 0 .. natoms-1 of k_becke, so the products are the same; the division by the interatomic distance becomes a
+// multiplication with its precomputed reciprocal (1 ulp in v, 1e-16 in the weights).  Shared memory: distances and
+// cell products, 2 x natoms x THREADS doubles; THREADS is 64 or 32, larger molecules use k_becke.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_becke_pairs(int natoms, const double *__restrict__ pos,
+                                                         const double *__restrict__ rdist, const double *__restrict__ aij,
+                                                         const size_t *__restrict__ atom_off,
+                                                         const double *__restrict__ xyz_all, double *__restrict__ w_all) {
+  extern __shared__ double sm[]; // gd[natoms][THREADS], cell[natoms][THREADS]
+  double *gd = sm, *cell = sm + static_cast<size_t>(natoms) * THREADS;
+  const int owner = blockIdx.y;
+  const int npts = static_cast<int>(atom_off[owner + 1] - atom_off[owner]);
+  if (static_cast<int>(blockIdx.x) * THREADS >= npts) return;
+  const double *xyz = xyz_all + 3 * atom_off[owner];
+  double *w = w_all + atom_off[owner];
+  const int t = threadIdx.x;
+  const int p = blockIdx.x * THREADS + t;
+  const bool valid = p < npts;
+  const double x = valid ? xyz[3 * p] : 0.0, y = valid ? xyz[3 * p + 1] : 0.0, z = valid ? xyz[3 * p + 2] : 0.0;
+  for (int a = 0; a < natoms; ++a) {
+    const double dx = x - pos[3 * a], dy = y - pos[3 * a + 1], dz = z - pos[3 * a + 2];
+    gd[a * THREADS + t] = sqrt(dx * dx + dy * dy + dz * dz);
+    cell[a * THREADS + t] = 1.0;
+  }
+  for (int hi = 1; hi < natoms; ++hi) {
+    const double ghi = gd[hi * THREADS + t];
+    double chi = cell[hi * THREADS + t];
+    const double *rd = rdist + static_cast<size_t>(hi) * natoms, *ar = aij + static_cast<size_t>(hi) * natoms;
+#pragma unroll 4
+    for (int lo = 0; lo < hi; ++lo) {
+      double v = (ghi - gd[lo * THREADS + t]) * __ldg(rd + lo);
+      const double a = __ldg(ar + lo);
+      v = fma(a, 1.0 - v * v, v); // a = 0 for equal Bragg radii: v unchanged
+      v = (3 - v * v) * v * 0.5;
+      v = (3 - v * v) * v * 0.5;
+      v = (3 - v * v) * v * 0.5;
+      const bool saturated = fabs(1.0 - v) < 1e-14;
+      chi = saturated ? 0.0 : chi * (0.5 * (1.0 - v));
+      if (!saturated) cell[lo * THREADS + t] *= 0.5 * (1.0 + v);
+    }
+    cell[hi * THREADS + t] = chi;
+  }
+  double total = 0.0;
+  for (int k = 0; k < natoms; ++k) total += cell[k * THREADS + t];
+  if (valid) w[p] *= cell[owner * THREADS + t] / total;
+}
+
 // 21 bits of each coordinate interleaved x -> bit 0, y -> bit 1, z -> bit 2 (spatial_grid_hierarchy.cpp:11-24)
 inline uint64_t morton63(uint64_t qx, uint64_t qy, uint64_t qz) {
   uint64_t code = 0;
@@ -444,10 +493,16 @@ int occ_xc_grid_create(int natoms, const int *Z, const double *pos, const occ_xc
       chk(cudaMemcpy(d_xyz, g->pts.data(), 3 * total * sizeof(double), cudaMemcpyHostToDevice));
       chk(cudaMemcpy(d_w, g->w.data(), total * sizeof(double), cudaMemcpyHostToDevice));
     }
+    // pair-once kernel when distances and cell products of 64 or 32 points fit shared memory (up to ~430 atoms)
+    const size_t smem_pairs64 = 2 * static_cast<size_t>(natoms) * 64 * sizeof(double), smem_pairs32 = smem_pairs64 / 2;
+    const int pair_threads = smem_pairs64 <= 200 * 1024 ? 64 : (smem_pairs32 <= 200 * 1024 ? 32 : 0);
+    std::vector<double> rdist(dist.size(), 0.0);
+    for (size_t i = 0; i < dist.size(); ++i) rdist[i] = dist[i] != 0.0 ? 1.0 / dist[i] : 0.0;
+    if (e == cudaSuccess && pair_threads) chk(cudaMemcpy(d_dist, rdist.data(), rdist.size() * sizeof(double), cudaMemcpyHostToDevice));
     const size_t smem = static_cast<size_t>(natoms) * BECKE_THREADS * sizeof(double);
-    if (e == cudaSuccess && smem > 48 * 1024)
+    if (e == cudaSuccess && !pair_threads && smem > 48 * 1024)
       chk(cudaFuncSetAttribute(k_becke, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    if (e == cudaSuccess && smem > 220 * 1024) {
+    if (e == cudaSuccess && !pair_threads && smem > 220 * 1024) {
       e = cudaErrorInvalidValue;
     }
     std::vector<size_t> atom_off(natoms + 1, 0);
@@ -461,8 +516,20 @@ int occ_xc_grid_create(int natoms, const int *Z, const double *pos, const occ_xc
     if (e == cudaSuccess)
       chk(cudaMemcpy(d_off, atom_off.data(), atom_off.size() * sizeof(size_t), cudaMemcpyHostToDevice));
     if (e == cudaSuccess && max_n > 0) {
-      const dim3 grid_dim(static_cast<unsigned>((max_n + BECKE_THREADS - 1) / BECKE_THREADS), natoms);
-      k_becke<<<grid_dim, BECKE_THREADS, smem>>>(natoms, d_pos, d_dist, d_aij, d_off, d_xyz, d_w);
+      if (pair_threads == 64) {
+        if (smem_pairs64 > 48 * 1024)
+          chk(cudaFuncSetAttribute(k_becke_pairs<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_pairs64)));
+        const dim3 grid_dim(static_cast<unsigned>((max_n + 63) / 64), natoms);
+        if (e == cudaSuccess) k_becke_pairs<64><<<grid_dim, 64, smem_pairs64>>>(natoms, d_pos, d_dist, d_aij, d_off, d_xyz, d_w);
+      } else if (pair_threads == 32) {
+        if (smem_pairs32 > 48 * 1024)
+          chk(cudaFuncSetAttribute(k_becke_pairs<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_pairs32)));
+        const dim3 grid_dim(static_cast<unsigned>((max_n + 31) / 32), natoms);
+        if (e == cudaSuccess) k_becke_pairs<32><<<grid_dim, 32, smem_pairs32>>>(natoms, d_pos, d_dist, d_aij, d_off, d_xyz, d_w);
+      } else {
+        const dim3 grid_dim(static_cast<unsigned>((max_n + BECKE_THREADS - 1) / BECKE_THREADS), natoms);
+        k_becke<<<grid_dim, BECKE_THREADS, smem>>>(natoms, d_pos, d_dist, d_aij, d_off, d_xyz, d_w);
+      }
     }
     if (e == cudaSuccess) chk(cudaGetLastError());
     if (e == cudaSuccess) chk(cudaMemcpy(g->w.data(), d_w, total * sizeof(double), cudaMemcpyDeviceToHost));
