@@ -17,9 +17,28 @@ for method, nspin in (("b3lyp", 1), ("tpss", 2), ("svwn", 1)):
     g = d.gradient(D2)
     print(method, nspin, float(np.abs(K).max()), float(np.abs(g).max()))
     d.close()
-f = nlc.NonLocalCorrelationFunctional()
-f.set_integration_grid(b, grid.GridSettings(50, 26, 1e-5, False, True))
-print("vv10", f.vv10(molecules.synthetic_density(b, 1))[0])
-f.close()
+for devices in (None, [0, 0]):                      # single handle, then two shards of one process (peer-memory paths)
+    f = nlc.NonLocalCorrelationFunctional()
+    f.set_integration_grid(b, grid.GridSettings(50, 26, 1e-5, False, True), gradient=True, devices=devices)
+    print("vv10", devices, f.vv10(molecules.synthetic_density(b, 1))[0])
+    print("vv10 gradient", float(np.abs(f.vv10_gradient(molecules.synthetic_density(b, 1))[1]).max()))
+    f.close()
+# multi-handle build (MO and D form), deterministic variant
+Cs = molecules.synthetic_orbitals(b, 1)
+m = dft.MultiGPUDFT("b3lyp", b, hs, devices=[0, 0], nocc=Cs[0].shape[1])
+print("multi", float(np.abs(m.build(molecules.synthetic_density(b, 1), Cs)).max()))
+m.close()
+m = dft.MultiGPUDFT("b3lyp", b, hs, devices=[0, 0], deterministic=True)
+print("multi det", float(np.abs(m.build(molecules.synthetic_density(b, 1))).max()))
+m.close()
+# COSX: s / p / d (def2-SVP) and up to g shells (def2-QZVP), ORCA GRIDX 1 grid, D and MO forms
+from occ_b200 import cosx
+for bas in ("def2-svp", "def2-qzvp"):
+    bs = aobasis.AOBasis.load(Z, pos, bas, pure=True)
+    sgx = cosx.SemiNumericalExchange(bs, settings=cosx.cosx_grid_settings(1))
+    D = 0.5 * molecules.synthetic_density(bs, 1)
+    print("cosx", bas, float(np.abs(sgx.compute_K(D)).max()),
+          float(np.abs(sgx.compute_K_mo(D, molecules.synthetic_orbitals(bs, 1)[0])).max()))
+    sgx.close()
 rho = dft.evaluate_density_on_grid(b, molecules.synthetic_density(b, 1), np.random.default_rng(1).uniform(-3, 3, (300, 3)), 2)
 print("rho", float(rho[:, 0].max()))
