@@ -71,7 +71,7 @@ public:
           const std::vector<occ_xc_leaf_t> &leaves, const std::vector<int> &func_ids, SpinorbitalKind kind,
           double density_threshold = 1e-10, double xc_screening_threshold = 1e-10, int device = -1, int rank = 0,
           int world_size = 1, int nocc_alpha = -1, int nocc_beta = -1, bool deterministic = false,
-          const std::vector<int> &devices = {})
+          const std::vector<int> &devices = {}, bool gradient = false)
       : m_nspin(static_cast<int>(kind)), m_nbf(basis.nbf()) {
     occ_xc_options_t opt;
     occ_xc_options_init(&opt);
@@ -79,6 +79,7 @@ public:
     opt.rank = rank;
     opt.world_size = world_size;
     opt.deterministic = deterministic ? 1 : 0;
+    opt.gradient = gradient ? 1 : 0; // the handle then also serves compute_xc_gradient (needs basis.shell_atom)
     // The reference hands over mo.D and mo.Cocc; D2 = 2 mo.D (dft.h:205) and C~ = sqrt(2) Cocc (restricted: mo.D =
     // Cocc Cocc^T; unrestricted: mo.D_s = 1/2 C_s C_s^T, include/occ/qm/orb.h:64-82) are formed ON THE DEVICE
     opt.density_scale = 2.0;
@@ -150,6 +151,16 @@ public:
     std::copy(Cocc_beta, Cocc_beta + nb, m_C.begin() + na);
     compute_K_dft_mo(D, m_C.data(), K);
   }
+  // DFT::compute_xc_gradient_impl (dft.h:598-749) without the VV10 term: D = mo.D, gradient 3 x natoms column-major
+  // (Mat3N).  Needs `gradient = true` at construction and a single-device handle.
+  void compute_xc_gradient(const double *D, double *gradient) {
+    if (m_multi) throw std::runtime_error("compute_xc_gradient: single-device handle required");
+    check(occ_xc_gradient(m_handle, D, gradient));
+  }
+  void compute_xc_gradient_mo(const double *D, const double *Cocc, double *gradient) {
+    if (m_multi) throw std::runtime_error("compute_xc_gradient_mo: single-device handle required");
+    check(occ_xc_gradient_mo(m_handle, D, Cocc, gradient));
+  }
   double exchange_correlation_energy() const { return m_exc_dft; }
   double total_density_alpha() const { return m_total_density_a; }
   double total_density_beta() const { return m_total_density_b; }
@@ -178,6 +189,70 @@ private:
     check(occ_xc_pinned_alloc(static_cast<size_t>(m_nspin) * m_nbf * m_nbf * sizeof(double), &p));
     m_K = static_cast<double *>(p);
   }
+};
+
+// occ::dft::NonLocalCorrelationFunctional (include/occ/dft/nonlocal_correlation.h): the post-SCF VV10 correction and its
+// nuclear gradient.  Created over the NLC grid — hierarchy of the concatenated m_nlc_atom_grids
+// (set_integration_grid, nonlocal_correlation.cpp:17-31): sorted points / weights / leaves, the sort permutation
+// (sorted index -> atom-grid order) and the prefix sums of the atom-grid sizes.
+class NonLocalCorrelation {
+public:
+  struct Parameters {
+    double vv10_b{6.0};
+    double vv10_C{0.01};
+  }; // nonlocal_correlation.h:14-18
+  NonLocalCorrelation(const BasisArrays &basis, size_t npts, const double *sorted_points, const double *sorted_weights,
+                      const std::vector<occ_xc_leaf_t> &leaves, const std::vector<size_t> &sort_permutation,
+                      const std::vector<size_t> &atom_offsets, bool gradient = false, int device = -1,
+                      const std::vector<int> &devices = {})
+      : m_nbf(basis.nbf()), m_perm(sort_permutation), m_atom_offsets(atom_offsets) {
+    occ_xc_options_t opt;
+    occ_xc_options_init(&opt);
+    opt.device = device;
+    opt.gradient = gradient ? 1 : 0;
+    opt.density_scale = 2.0; // the caller passes mo.D; D2 = 2 mo.D (nonlocal_correlation.cpp:376) is formed on the device
+    const occ_xc_basis_t b = basis.view();
+    const int b88 = 106; // any GGA id: only rho and grad rho of the handle are used
+    if (!devices.empty())
+      check(occ_xc_multi_create(&b, npts, sorted_points, sorted_weights, leaves.size(), leaves.data(), nullptr, 1, &b88, 1,
+                                1e-10, 0.0, &opt, static_cast<int>(devices.size()), devices.data(), &m_multi));
+    else
+      check(occ_xc_create(&b, npts, sorted_points, sorted_weights, leaves.size(), leaves.data(), nullptr, 1, &b88, 1, 1e-10,
+                          0.0, &opt, &m_handle));
+  }
+  ~NonLocalCorrelation() {
+    occ_xc_destroy(m_handle);
+    occ_xc_multi_destroy(m_multi);
+  }
+  NonLocalCorrelation(const NonLocalCorrelation &) = delete;
+  NonLocalCorrelation &operator=(const NonLocalCorrelation &) = delete;
+  void set_parameters(const Parameters &p) { m_params = p; }
+
+  // Result operator()(basis, mo) (nonlocal_correlation.cpp:524-527): D = mo.D (restricted); Vxc nbf x nbf; returns the energy
+  double vv10(const double *D, double *Vxc) {
+    double e = 0.0;
+    if (m_multi) check(occ_xc_multi_vv10(m_multi, D, m_perm.data(), m_params.vv10_b, m_params.vv10_C, Vxc, &e));
+    else check(occ_xc_vv10(m_handle, D, m_perm.data(), m_params.vv10_b, m_params.vv10_C, Vxc, &e));
+    return e;
+  }
+  // GradientResult compute_gradient(basis, mo) (nonlocal_correlation.cpp:530-534): gradient 3 x natoms (Mat3N); returns the energy
+  double compute_gradient(const double *D, double *gradient) {
+    double e = 0.0;
+    if (m_multi)
+      check(occ_xc_multi_vv10_gradient(m_multi, D, m_perm.data(), m_atom_offsets.data(), m_params.vv10_b, m_params.vv10_C,
+                                       gradient, &e));
+    else
+      check(occ_xc_vv10_gradient(m_handle, D, m_perm.data(), m_atom_offsets.data(), m_params.vv10_b, m_params.vv10_C,
+                                 gradient, &e));
+    return e;
+  }
+
+private:
+  occ_xc_handle *m_handle = nullptr;
+  occ_xc_multi *m_multi = nullptr;
+  int m_nbf;
+  Parameters m_params;
+  std::vector<size_t> m_perm, m_atom_offsets;
 };
 
 } // namespace occ_b200

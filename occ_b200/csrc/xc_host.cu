@@ -1111,6 +1111,7 @@ int vv10_stage_density(occ_xc_handle *h, const double *D2, const size_t *orig_in
   V.beta = std::pow(3.0 / (vv10_b * vv10_b), 0.75) / 32.0;
   V.C = vv10_C;
   CUDA_TRY(cudaMemcpyAsync(h->d_D, D2, ksz * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (h->density_scale != 1.0) launch_scale(h->d_D, h->d_D, ksz, h->density_scale, st); // as every host entry point
   launch_prepare_density(h->d_D, h->d_Dsym, h->nbf, 1, st);
   P.Drho[0] = h->d_Dsym;
   P.Dtau[0] = h->d_D;
@@ -1301,9 +1302,11 @@ static int gradient_impl(occ_xc_handle *h, const double *D2, const double *C, do
   const size_t ksz = static_cast<size_t>(h->nspin) * h->nbf * h->nbf;
   const bool mo = C != nullptr;
   CUDA_TRY(cudaMemcpyAsync(h->d_D, D2, ksz * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (h->density_scale != 1.0) launch_scale(h->d_D, h->d_D, ksz, h->density_scale, st); // as every host entry point
   if (mo) {
     const size_t csz = static_cast<size_t>(h->nbf) * (h->nocc[0] + h->nocc[1]);
     CUDA_TRY(cudaMemcpyAsync(h->d_C, C, csz * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (h->orbital_scale != 1.0) launch_scale(h->d_C, h->d_C, csz, h->orbital_scale, st);
     for (int sp = 0; sp < h->nspin; ++sp) {
       const double *Cs = h->d_C + static_cast<size_t>(sp) * h->nbf * h->nocc[0];
       P.moC[sp] = Cs;
