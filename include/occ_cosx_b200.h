@@ -111,6 +111,35 @@ int occ_cosx_get_info(const occ_cosx_handle *h, occ_cosx_info_t *info);
 
 void occ_cosx_destroy(occ_cosx_handle *h);
 
+/* ---- several GPUs of one box, driven from ONE host process (the layout of occ_xc_multi_*, include/occ_xc_b200.h) ----
+ * SemiNumericalExchange::compute_K is called from the reference's single-process SCF (HartreeFock::compute_K,
+ * src/qm/hf.cpp:179-258); its tbb loops over batches (:660-815) become: one handle per device with the grid batches dealt
+ * round-robin, one host thread per device for the call, every GPU uploads D (and C) over its own PCIe link, and GPU r
+ * sums slice r of the symmetrised partial K matrices through peer loads in rank order and writes it to the host matrix.
+ * Needs peer access between the devices; an ordinal may repeat (several shards on one GPU).
+ *   occ_cosx_multi_create     as occ_cosx_create (options.device / rank / world_size are overwritten per handle);
+ *                             devices NULL = ordinals 0..ndev-1.  With batches sharded the projector has to be built from
+ *                             the SUMMED numerical overlap: pass it here, or NULL and set it later from
+ *                             occ_cosx_multi_numerical_overlap / _analytic_overlap (Sn.ldlt().solve(S)).
+ *   occ_cosx_multi_compute_K  compute_K / compute_K_mo: kind 0 restricted, 1 unrestricted, 2 general (D form only);
+ *                             C NULL = D form, else the occupied orbitals as in occ_cosx_compute_K_mo; omega > 0 = long range
+ *   ..._range_separated       (alpha + beta) K(1/r) - beta K(erf(omega r)/r) in one sweep, kinds 0 and 1 */
+typedef struct occ_cosx_multi occ_cosx_multi;
+int occ_cosx_multi_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_offsets, const double *pts_xyz,
+                          const double *weights, const double *overlap_projector, const occ_cosx_options_t *options,
+                          int ndev, const int *devices, occ_cosx_multi **out);
+int occ_cosx_multi_compute_K(occ_cosx_multi *m, int kind, const double *D, const double *C, int nocc_alpha, int nocc_beta,
+                             double precision, double omega, double *K);
+int occ_cosx_multi_compute_K_range_separated(occ_cosx_multi *m, int kind, const double *D, const double *C, int nocc_alpha,
+                                             int nocc_beta, double alpha, double beta, double omega, double precision,
+                                             double *K);
+int occ_cosx_multi_numerical_overlap(occ_cosx_multi *m, double *S_numeric);
+int occ_cosx_multi_analytic_overlap(occ_cosx_multi *m, double *S_analytic);
+int occ_cosx_multi_set_projector(occ_cosx_multi *m, const double *overlap_projector);
+int occ_cosx_multi_ndev(const occ_cosx_multi *m);
+int occ_cosx_multi_get_info(const occ_cosx_multi *m, int rank, occ_cosx_info_t *info);
+void occ_cosx_multi_destroy(occ_cosx_multi *m);
+
 #ifdef __cplusplus
 }
 #endif

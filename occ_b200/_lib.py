@@ -26,7 +26,10 @@ COSX_SYMBOLS = ["occ_cosx_create", "occ_cosx_compute_K", "occ_cosx_compute_K_ran
                 "occ_cosx_compute_K_range_separated_mo", "occ_cosx_compute_K_range_separated_kind",
                 "occ_cosx_compute_K_range_separated_mo_kind", "occ_cosx_K_for_density",
                 "occ_cosx_K_for_density_device", "occ_cosx_numerical_overlap", "occ_cosx_analytic_overlap",
-                "occ_cosx_set_projector", "occ_cosx_get_info", "occ_cosx_destroy"]
+                "occ_cosx_set_projector", "occ_cosx_get_info", "occ_cosx_destroy",
+                "occ_cosx_multi_create", "occ_cosx_multi_compute_K", "occ_cosx_multi_compute_K_range_separated",
+                "occ_cosx_multi_numerical_overlap", "occ_cosx_multi_analytic_overlap", "occ_cosx_multi_set_projector",
+                "occ_cosx_multi_ndev", "occ_cosx_multi_get_info", "occ_cosx_multi_destroy"]
 
 
 class BasisT(C.Structure):

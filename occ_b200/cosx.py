@@ -243,3 +243,121 @@ class SemiNumericalExchange:
             self.close()
         except Exception:
             pass
+
+
+class MultiGPUSemiNumericalExchange:
+    """occ_cosx_multi_*: the same engine on several GPUs driven from THIS process (one shard of grid batches per device,
+    inputs over every GPU's own PCIe link, the partial K matrices summed through peer memory).  Same constructor arguments
+    as SemiNumericalExchange plus `devices` (list of CUDA ordinals; an ordinal may repeat)."""
+
+    def __init__(self, basis: AOBasis, settings: GridSettings | None = None, atom_grids=None, devices=(0,),
+                 margin: float = 1.0, batch_bytes: int = 0, projector: np.ndarray | None | str = "auto"):
+        L = lib()
+        self.basis = basis
+        self.omega = 0.0
+        if atom_grids is None:
+            mg = MolecularGrid(basis, settings or sgx_grid_settings())
+            pts, w = mg.points()
+            counts = [mg.atom_info(a)[0] for a in range(mg.natoms)]
+            mg.close()
+            offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint64)
+        else:
+            offs, pts, w = atom_grids
+        self.atom_offsets = np.ascontiguousarray(offs, dtype=np.uint64)
+        self.points = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+        self.weights = np.ascontiguousarray(w, dtype=np.float64)
+        self._ba = BasisArrays(basis.as_arrays())
+        opt = CosxOptionsT(margin, 0.0, 0.0, batch_bytes, -1, 0, 0, 1)
+        dev = np.array(list(devices), dtype=np.int32)
+        self.devices = [int(x) for x in dev]
+        P0 = None if isinstance(projector, str) or projector is None else np.asfortranarray(projector, dtype=np.float64)
+        self._m = C.c_void_p()
+        L.occ_cosx_multi_destroy.restype = None
+        L.occ_cosx_multi_destroy.argtypes = [C.c_void_p]
+        L.occ_cosx_multi_compute_K.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double,
+                                               C.c_double, C.c_void_p]
+        L.occ_cosx_multi_compute_K_range_separated.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                                               C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                                               C.c_void_p]
+        L.occ_cosx_multi_numerical_overlap.argtypes = [C.c_void_p, C.c_void_p]
+        L.occ_cosx_multi_analytic_overlap.argtypes = [C.c_void_p, C.c_void_p]
+        L.occ_cosx_multi_set_projector.argtypes = [C.c_void_p, C.c_void_p]
+        L.occ_cosx_multi_get_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        check(L.occ_cosx_multi_create(self._ba.ref, C.c_int(len(self.atom_offsets) - 1), ptr(self.atom_offsets),
+                                      ptr(self.points), ptr(self.weights), ptr(P0) if P0 is not None else None,
+                                      C.byref(opt), C.c_int(len(dev)), ptr(dev), C.byref(self._m)))
+        self.overlap_projector = P0
+        if isinstance(projector, str):      # Sn.ldlt().solve(S) over the SUMMED numerical overlap of the shards
+            S, Sn = self.analytic_overlap(), self.compute_overlap_matrix()
+            self.set_projector(np.linalg.solve(Sn, S))
+
+    def set_range_separated_omega(self, omega: float):
+        self.omega = float(omega)
+
+    @staticmethod
+    def _pack(nbf, Cocc, unrestricted):
+        if Cocc is None:
+            return None, 0, 0
+        blocks = [np.asarray(c, dtype=np.float64).reshape(nbf, -1) for c in (Cocc if unrestricted else (Cocc,))]
+        nocc = [b.shape[1] for b in blocks] + [0]
+        Cp = np.asfortranarray(np.concatenate(blocks, axis=1)) if sum(nocc) else np.zeros((nbf, 1), order="F")
+        return Cp, nocc[0], nocc[1]
+
+    def compute_K(self, D, Cocc=None, precision: float = np.finfo(np.float64).eps, unrestricted: bool = False,
+                  general: bool = False):
+        """compute_K(mo) / compute_K_mo over all devices; Cocc as in SemiNumericalExchange.compute_K_mo or None"""
+        nbf = self.basis.nbf
+        kind = 2 if general else (1 if unrestricted else 0)
+        shape = ((nbf, nbf), (2 * nbf, nbf), (2 * nbf, 2 * nbf))[kind]
+        D = np.asfortranarray(D, dtype=np.float64)
+        if D.shape != shape:
+            raise RuntimeError(f"compute_K: density matrix of shape {D.shape}, expected {shape}")
+        Cp, na, nb = self._pack(nbf, Cocc, unrestricted)
+        K = np.zeros(shape, order="F")
+        check(lib().occ_cosx_multi_compute_K(self._m, kind, ptr(D), ptr(Cp) if Cp is not None else None, na, nb,
+                                             precision, self.omega, ptr(K)))
+        return K
+
+    def compute_K_range_separated(self, D, alpha: float, beta: float, omega: float, Cocc=None,
+                                  precision: float = np.finfo(np.float64).eps, unrestricted: bool = False):
+        nbf = self.basis.nbf
+        rows = 2 * nbf if unrestricted else nbf
+        D = np.asfortranarray(D, dtype=np.float64)
+        if D.shape != (rows, nbf):
+            raise RuntimeError(f"density matrix has shape {D.shape}, expected {(rows, nbf)}")
+        Cp, na, nb = self._pack(nbf, Cocc, unrestricted)
+        K = np.zeros((rows, nbf), order="F")
+        check(lib().occ_cosx_multi_compute_K_range_separated(self._m, 1 if unrestricted else 0, ptr(D),
+                                                             ptr(Cp) if Cp is not None else None, na, nb, alpha, beta,
+                                                             omega, precision, ptr(K)))
+        return K
+
+    def compute_overlap_matrix(self):
+        S = np.zeros((self.basis.nbf, self.basis.nbf), order="F")
+        check(lib().occ_cosx_multi_numerical_overlap(self._m, ptr(S)))
+        return S
+
+    def analytic_overlap(self):
+        S = np.zeros((self.basis.nbf, self.basis.nbf), order="F")
+        check(lib().occ_cosx_multi_analytic_overlap(self._m, ptr(S)))
+        return S
+
+    def set_projector(self, P):
+        self.overlap_projector = None if P is None else np.asfortranarray(P, dtype=np.float64)
+        check(lib().occ_cosx_multi_set_projector(self._m, ptr(self.overlap_projector) if P is not None else None))
+
+    def info(self, rank: int) -> dict:
+        t = CosxInfoT()
+        check(lib().occ_cosx_multi_get_info(self._m, C.c_int(rank), C.byref(t)))
+        return {f: getattr(t, f) for f, _ in CosxInfoT._fields_}
+
+    def close(self):
+        if getattr(self, "_m", None) is not None and self._m.value:
+            lib().occ_cosx_multi_destroy(self._m)
+            self._m = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace xcb;
@@ -699,9 +700,10 @@ int occ_cosx_K_for_density(occ_cosx_handle *h, const double *D2q, double precisi
 }
 
 // compute_K_restricted / _unrestricted / _general (:517-545, 617-660, 662-712) and compute_K_range_separated (:830-860)
-static int compute_K_impl(occ_cosx_handle *h, int kind, const double *D, double precision, double w_full, double w_lr,
-                          double omega, double *K, const double *C = nullptr, int nocc_a = 0, int nocc_b = 0) {
-  if (!h || !D || !K) return fail("occ_cosx_compute_K: null argument");
+// the build up to the symmetrised K on the device (*dK_out); nothing is synchronised
+static int compute_K_device(occ_cosx_handle *h, int kind, const double *D, double precision, double w_full, double w_lr,
+                            double omega, double **dK_out, const double *C = nullptr, int nocc_a = 0, int nocc_b = 0) {
+  if (!h || !D) return fail("occ_cosx_compute_K: null argument");
   if (C && kind == 2) return fail("occ_cosx_compute_K_mo: restricted (0) or unrestricted (1) only");
   if (C && (nocc_a < 0 || nocc_b < 0 || nocc_a > h->nbf || nocc_b > h->nbf))
     return fail("occ_cosx_compute_K_mo: occupied counts outside [0, nbf]");
@@ -772,8 +774,19 @@ static int compute_K_impl(occ_cosx_handle *h, int kind, const double *D, double 
     launch_cosx_symmetrize(Kbb, Kbb, nbf, 0.5, dK + off[3], rows, st);
     h->info.launches += 4;
   }
-  CUDA_TRY(cudaMemcpyAsync(K, dK, static_cast<size_t>(rows) * cols * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  *dK_out = dK;
+  return 0;
+}
+
+static int compute_K_impl(occ_cosx_handle *h, int kind, const double *D, double precision, double w_full, double w_lr,
+                          double omega, double *K, const double *C = nullptr, int nocc_a = 0, int nocc_b = 0) {
+  if (!K) return fail("occ_cosx_compute_K: null argument");
+  double *dK = nullptr;
+  if (compute_K_device(h, kind, D, precision, w_full, w_lr, omega, &dK, C, nocc_a, nocc_b)) return 1;
+  const int nbf = h->nbf;
+  const size_t count = static_cast<size_t>(kind == 0 ? nbf : 2 * nbf) * (kind == 2 ? 2 * nbf : nbf);
+  CUDA_TRY(cudaMemcpyAsync(K, dK, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -852,6 +865,214 @@ int occ_cosx_get_info(const occ_cosx_handle *h, occ_cosx_info_t *info) {
   if (!h || !info) return fail("occ_cosx_get_info: null argument");
   *info = h->info;
   return 0;
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Several GPUs of one box driven from ONE host process (the layout of occ_xc_multi_*, csrc/xc_multi.cu): one handle per
+// device with the grid batches dealt round-robin (options.rank / world_size), a host thread per device for the call,
+// every GPU uploads D (and C) over its own PCIe link, and GPU r sums its contiguous slice of the symmetrised partial K
+// matrices through peer loads in rank order and writes the slice to the host matrix.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int COSX_MAX_DEV = 16;
+struct CosxPeers {
+  const double *p[COSX_MAX_DEV];
+  int n;
+};
+__global__ void k_cosx_reduce_slice(CosxPeers parts, double *__restrict__ out, size_t begin, size_t end) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = begin + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < end; i += stride) {
+    double s = parts.p[0][i];
+    for (int r = 1; r < parts.n; ++r) s += parts.p[r][i];
+    out[i] = s;
+  }
+}
+// run job(r) for every rank on its own thread; first error message wins
+template <class F> int for_each_rank(int n, F job) {
+  std::vector<int> rc(n, 0);
+  std::vector<std::string> err(n);
+  std::vector<std::thread> th;
+  for (int r = 0; r < n; ++r)
+    th.emplace_back([&, r] {
+      rc[r] = job(r);
+      if (rc[r]) err[r] = occ_xc_last_error();
+    });
+  for (auto &t : th) t.join();
+  for (int r = 0; r < n; ++r)
+    if (rc[r]) return occ_xc_set_error(err[r].c_str());
+  return 0;
+}
+} // namespace
+
+struct occ_cosx_multi {
+  int n = 0;
+  int device[COSX_MAX_DEV];
+  occ_cosx_handle *h[COSX_MAX_DEV];
+  double *d_red[COSX_MAX_DEV]; // reduced slice (full-size buffer; only the rank's slice is written)
+  size_t red_count = 0;
+};
+
+extern "C" {
+
+void occ_cosx_multi_destroy(occ_cosx_multi *m) {
+  if (!m) return;
+  for (int r = 0; r < m->n; ++r) {
+    if (m->d_red[r]) {
+      cudaSetDevice(m->device[r]);
+      cudaFree(m->d_red[r]);
+    }
+    occ_cosx_destroy(m->h[r]);
+  }
+  delete m;
+}
+
+int occ_cosx_multi_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_offsets, const double *pts_xyz,
+                          const double *weights, const double *overlap_projector, const occ_cosx_options_t *options,
+                          int ndev, const int *devices, occ_cosx_multi **out) {
+  if (!out) return fail("occ_cosx_multi_create: null argument");
+  if (ndev < 1 || ndev > COSX_MAX_DEV) return fail("occ_cosx_multi_create: between 1 and 16 devices");
+  int avail = 0;
+  if (cudaGetDeviceCount(&avail) != cudaSuccess || avail == 0)
+    return fail("occ_cosx_multi_create: no CUDA device available (this library has no CPU fallback)");
+  occ_cosx_multi *m = new occ_cosx_multi();
+  m->n = ndev;
+  for (int r = 0; r < COSX_MAX_DEV; ++r) {
+    m->h[r] = nullptr;
+    m->d_red[r] = nullptr;
+    m->device[r] = 0;
+  }
+  for (int r = 0; r < ndev; ++r) {
+    m->device[r] = devices ? devices[r] : r;
+    if (m->device[r] < 0 || m->device[r] >= avail) {
+      occ_cosx_multi_destroy(m);
+      return fail("occ_cosx_multi_create: device ordinal out of range");
+    }
+  }
+  for (int a = 0; a < ndev; ++a)
+    for (int b = 0; b < ndev; ++b) {
+      if (m->device[a] == m->device[b]) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, m->device[a], m->device[b]);
+      if (!can) {
+        occ_cosx_multi_destroy(m);
+        return fail("occ_cosx_multi_create: the devices cannot access each other's memory; use one handle per process "
+                    "with options.rank / world_size and sum the partial matrices instead");
+      }
+      cudaSetDevice(m->device[a]);
+      const cudaError_t e = cudaDeviceEnablePeerAccess(m->device[b], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        occ_cosx_multi_destroy(m);
+        return fail(std::string("occ_cosx_multi_create: cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+      }
+      cudaGetLastError();
+    }
+  const int rc = for_each_rank(ndev, [&](int r) -> int {
+    occ_cosx_options_t opt;
+    if (options) opt = *options;
+    else std::memset(&opt, 0, sizeof(opt));
+    opt.device = m->device[r];
+    opt.rank = r;
+    opt.world_size = ndev;
+    return occ_cosx_create(basis, natoms, atom_offsets, pts_xyz, weights, overlap_projector, &opt, &m->h[r]);
+  });
+  if (rc) {
+    occ_cosx_multi_destroy(m);
+    return 1;
+  }
+  *out = m;
+  return 0;
+}
+
+int occ_cosx_multi_ndev(const occ_cosx_multi *m) { return m ? m->n : 0; }
+
+int occ_cosx_multi_get_info(const occ_cosx_multi *m, int rank, occ_cosx_info_t *info) {
+  if (!m || rank < 0 || rank >= m->n) return fail("occ_cosx_multi_get_info: bad argument");
+  return occ_cosx_get_info(m->h[rank], info);
+}
+
+int occ_cosx_multi_set_projector(occ_cosx_multi *m, const double *overlap_projector) {
+  if (!m) return fail("occ_cosx_multi_set_projector: null argument");
+  for (int r = 0; r < m->n; ++r)
+    if (occ_cosx_set_projector(m->h[r], overlap_projector)) return 1;
+  return 0;
+}
+
+int occ_cosx_multi_analytic_overlap(occ_cosx_multi *m, double *S) {
+  if (!m) return fail("occ_cosx_multi_analytic_overlap: null argument");
+  return occ_cosx_analytic_overlap(m->h[0], S);
+}
+
+// the shards' partial numerical overlaps summed on the host in rank order (a once-per-geometry nbf x nbf matrix)
+int occ_cosx_multi_numerical_overlap(occ_cosx_multi *m, double *Sn) {
+  if (!m || !Sn) return fail("occ_cosx_multi_numerical_overlap: null argument");
+  const size_t n2 = static_cast<size_t>(m->h[0]->nbf) * m->h[0]->nbf;
+  std::vector<std::vector<double>> part(m->n, std::vector<double>(n2));
+  if (for_each_rank(m->n, [&](int r) -> int { return occ_cosx_numerical_overlap(m->h[r], part[r].data()); })) return 1;
+  std::copy(part[0].begin(), part[0].end(), Sn);
+  for (int r = 1; r < m->n; ++r)
+    for (size_t i = 0; i < n2; ++i) Sn[i] += part[r][i];
+  return 0;
+}
+
+// K = w_full K(1/r) + w_lr K(erf(omega r)/r) over all devices; C may be NULL (D form)
+static int multi_compute(occ_cosx_multi *m, int kind, const double *D, const double *C, int nocc_a, int nocc_b,
+                         double precision, double w_full, double w_lr, double omega, double *K) {
+  if (!m || !D || !K) return fail("occ_cosx_multi_compute_K: null argument");
+  const int n = m->n, nbf = m->h[0]->nbf;
+  const size_t count = static_cast<size_t>(kind == 0 ? nbf : 2 * nbf) * (kind == 2 ? 2 * nbf : nbf);
+  std::vector<double *> dK(n, nullptr);
+  // stage 1: every rank builds its symmetrised partial K on its device
+  if (for_each_rank(n, [&](int r) -> int {
+        occ_cosx_handle *h = m->h[r];
+        if (compute_K_device(h, kind, D, precision, w_full, w_lr, omega, &dK[r], C, nocc_a, nocc_b)) return 1;
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+      }))
+    return 1;
+  if (m->red_count < count) {
+    for (int r = 0; r < n; ++r) {
+      CUDA_TRY(cudaSetDevice(m->device[r]));
+      if (m->d_red[r]) cudaFree(m->d_red[r]);
+      m->d_red[r] = nullptr;
+      CUDA_TRY(cudaMalloc(&m->d_red[r], count * sizeof(double)));
+    }
+    m->red_count = count;
+  }
+  // stage 2: rank r sums slice r over all partial matrices (peer loads, rank order) and writes it to the host matrix
+  return for_each_rank(n, [&](int r) -> int {
+    occ_cosx_handle *h = m->h[r];
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t per = ((count + n - 1) / n + 1) & ~size_t(1);
+    const size_t lo = std::min(count, per * r), hi = std::min(count, per * (r + 1));
+    if (hi > lo) {
+      CosxPeers parts;
+      parts.n = n;
+      for (int p = 0; p < n; ++p) parts.p[p] = dK[p];
+      const unsigned grid = static_cast<unsigned>(std::min<size_t>((hi - lo + 255) / 256, 148 * 8));
+      k_cosx_reduce_slice<<<grid, 256, 0, h->stream>>>(parts, m->d_red[r], lo, hi);
+      CUDA_TRY(cudaMemcpyAsync(K + lo, m->d_red[r] + lo, (hi - lo) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  });
+}
+
+int occ_cosx_multi_compute_K(occ_cosx_multi *m, int kind, const double *D, const double *C, int nocc_alpha, int nocc_beta,
+                             double precision, double omega, double *K) {
+  if (omega < 0.0) return fail("occ_cosx_multi_compute_K: omega must be >= 0");
+  return multi_compute(m, kind, D, C, nocc_alpha, nocc_beta, precision, omega > 0.0 ? 0.0 : 1.0, omega > 0.0 ? 1.0 : 0.0, omega, K);
+}
+
+int occ_cosx_multi_compute_K_range_separated(occ_cosx_multi *m, int kind, const double *D, const double *C, int nocc_alpha,
+                                             int nocc_beta, double alpha, double beta, double omega, double precision,
+                                             double *K) {
+  if (kind == 2) return fail("occ_cosx_multi_compute_K_range_separated: restricted (0) or unrestricted (1) only");
+  if (omega <= 0.0) return fail("occ_cosx_multi_compute_K_range_separated: omega must be > 0");
+  return multi_compute(m, kind, D, C, nocc_alpha, nocc_beta, precision, alpha + beta, -beta, omega, K);
 }
 
 } // extern "C"

@@ -268,3 +268,31 @@ def test_cosx_on_the_for_cosx_grid(oracle):
     Kref, _ = O.cosx_compute_K(ob, off, pts, w, P, D)
     assert np.abs(K - Kref).max() < 1e-8 * max(1.0, np.abs(Kref).max())   # the projector is solved on either side
     sgx.close()
+
+
+@pytest.mark.parametrize("devices", [(0, 0), (0, 0, 0), (0, 1), (0, 1, 2, 3)])
+def test_cosx_single_process_multi_gpu(oracle, devices):
+    """occ_cosx_multi_*: shards of grid batches driven from one process; K (D form, factorised form, unrestricted,
+    fused range-separated) equals the one-handle build to 1e-12 and the oracle to 1e-9; the projector is solved from the
+    summed numerical overlap of the shards"""
+    import torch
+    from occ_b200 import cosx
+    if max(devices) >= torch.cuda.device_count():
+        pytest.skip(f"needs {max(devices) + 1} GPUs")
+    O, b, ob, off, pts, w, P, S, Sn, D, sgx = _setup(oracle, "water", "def2-tzvp", True)
+    K1 = sgx.compute_K(D)
+    m = cosx.MultiGPUSemiNumericalExchange(b, atom_grids=(off, pts, w), devices=devices)
+    assert sum(m.info(r)["nbatches"] for r in range(len(devices))) == sgx.info()["nbatches"]
+    assert np.abs(m.compute_overlap_matrix() - Sn).max() < 1e-12
+    assert np.abs(m.overlap_projector - P).max() < 1e-8
+    m.set_projector(P)
+    Kref, _ = O.cosx_compute_K(ob, off, pts, w, P, D)
+    Cocc = molecules.synthetic_orbitals(b, 1, seed=7)[0]
+    for K in (m.compute_K(D), m.compute_K(D, Cocc)):
+        assert np.abs(K - K1).max() < 1e-12 and np.abs(K - Kref).max() < TOL
+    Du = np.asfortranarray(np.vstack([0.6 * D, 0.4 * D]))
+    assert np.abs(m.compute_K(Du, unrestricted=True) - sgx.compute_K(Du, unrestricted=True)).max() < 1e-12
+    Kf = m.compute_K_range_separated(D, 1.0, -0.842294, 0.3)
+    assert np.abs(Kf - sgx.compute_K_range_separated(D, 1.0, -0.842294, 0.3)).max() < 1e-12
+    m.close()
+    sgx.close()
