@@ -187,21 +187,29 @@ template <int MODE> __device__ __forceinline__ void XC_SYM(gemm_xd_body)(const B
   const double *phib = P.scratch + t.scr_off + static_cast<size_t>(n0 + half * 32) * TILE_P + p;
   double *part = smem + GN * X_LD; // [4][128] partial sums of the upper half
   if (P.debug & 2) return;
+  // columns of this half that exist (in groups of 8; the slabs are zero-padded to nbp, the X columns beyond nb are zero):
+  // for local bases of 100-250 functions the last 64-column block is mostly padding, and its slab loads are skipped
+  const int jv = min(32, max(0, nb - (n0 + half * 32)));
   if (it.acomp == 0) {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     if (P.ncomp > 1) {
-#pragma unroll 8
-      for (int j = 0; j < 32; ++j) {
-        const double x = Xr[j * X_LD];
-        const double *q = phib + j * TILE_P;
-        s0 = fma(q[0], x, s0);
-        s1 = fma(q[slab], x, s1);
-        s2 = fma(q[2 * slab], x, s2);
-        s3 = fma(q[3 * slab], x, s3);
+      for (int j0 = 0; j0 < jv; j0 += 8) {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int j = j0 + jj;
+          const double x = Xr[j * X_LD];
+          const double *q = phib + j * TILE_P;
+          s0 = fma(q[0], x, s0);
+          s1 = fma(q[slab], x, s1);
+          s2 = fma(q[2 * slab], x, s2);
+          s3 = fma(q[3 * slab], x, s3);
+        }
       }
     } else {
-#pragma unroll 8
-      for (int j = 0; j < 32; ++j) s0 = fma(phib[j * TILE_P], Xr[j * X_LD], s0);
+      for (int j0 = 0; j0 < jv; j0 += 8) {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) s0 = fma(phib[(j0 + jj) * TILE_P], Xr[(j0 + jj) * X_LD], s0);
+      }
     }
     if (half) {
       part[p] = s0;
@@ -221,8 +229,10 @@ template <int MODE> __device__ __forceinline__ void XC_SYM(gemm_xd_body)(const B
   } else { // tau term: rowsum(phi_k o (phi_k D)) accumulates in row 4
     const double *q = phib + static_cast<size_t>(it.acomp) * slab;
     double s0 = 0.0;
-#pragma unroll 8
-    for (int j = 0; j < 32; ++j) s0 = fma(q[j * TILE_P], Xr[j * X_LD], s0);
+    for (int j0 = 0; j0 < jv; j0 += 8) {
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) s0 = fma(q[(j0 + jj) * TILE_P], Xr[(j0 + jj) * X_LD], s0);
+    }
     if (half) part[p] = s0;
     __syncthreads();
     if (!half) XC_ACC_ADD(P, accp + 4 * TILE_P + p, s0 + part[p]);

@@ -135,24 +135,37 @@ __global__ void __launch_bounds__(NTHREADS, 2) XC_SYM(k_vxc_resident)(BuildParam
     double *dst = Bres + (half * 32) * R_LDB;
     if (P.debug & 16) { // timing experiment: B block without the slab loads
       for (int j = 0; j < 32; ++j) dst[j * R_LDB + (p ^ R_SW(j))] = 1e-3 * j;
-    } else if (it.acomp == 0) {
-      const double c0 = cf[0];
-      if (P.deriv >= 1) {
-        const double cx = cf[TILE_P], cy = cf[2 * TILE_P], cz = cf[3 * TILE_P];
-#pragma unroll 8
-        for (int j = 0; j < 32; ++j) {
-          const double *q = q0 + j * TILE_P;
-          dst[j * R_LDB + (p ^ R_SW(j))] = c0 * q[0] + cx * q[slab] + cy * q[2 * slab] + cz * q[3 * slab];
+    } else {
+      // only the columns that exist are read (groups of 8; the rest of the block is zero): for local bases of 100-250
+      // functions the last 64-column block is mostly padding
+      const int jv = min(32, max(0, nb - (n0 + half * 32)));
+      if (it.acomp == 0) {
+        const double c0 = cf[0];
+        if (P.deriv >= 1) {
+          const double cx = cf[TILE_P], cy = cf[2 * TILE_P], cz = cf[3 * TILE_P];
+          for (int j0 = 0; j0 < jv; j0 += 8) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const int j = j0 + jj;
+              const double *q = q0 + j * TILE_P;
+              dst[j * R_LDB + (p ^ R_SW(j))] = c0 * q[0] + cx * q[slab] + cy * q[2 * slab] + cz * q[3 * slab];
+            }
+          }
+        } else {
+          for (int j0 = 0; j0 < jv; j0 += 8) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) dst[(j0 + jj) * R_LDB + (p ^ R_SW(j0 + jj))] = c0 * q0[(j0 + jj) * TILE_P];
+          }
         }
       } else {
-#pragma unroll 8
-        for (int j = 0; j < 32; ++j) dst[j * R_LDB + (p ^ R_SW(j))] = c0 * q0[j * TILE_P];
+        const double ct = cf[4 * TILE_P];
+        const double *qk = q0 + static_cast<size_t>(it.acomp) * slab;
+        for (int j0 = 0; j0 < jv; j0 += 8) {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) dst[(j0 + jj) * R_LDB + (p ^ R_SW(j0 + jj))] = ct * qk[(j0 + jj) * TILE_P];
+        }
       }
-    } else {
-      const double ct = cf[4 * TILE_P];
-      const double *qk = q0 + static_cast<size_t>(it.acomp) * slab;
-#pragma unroll 8
-      for (int j = 0; j < 32; ++j) dst[j * R_LDB + (p ^ R_SW(j))] = ct * qk[j * TILE_P];
+      for (int j = (jv + 7) & ~7; j < 32; ++j) dst[j * R_LDB + (p ^ R_SW(j))] = 0.0;
     }
     if (tid < GN) scol[tid] = n0 + tid < nb ? __ldg(gidx + n0 + tid) : -1;
   }
