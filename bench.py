@@ -580,7 +580,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--batch-mb", type=int, default=4096)
+    ap.add_argument("--batch-mb", type=int, default=16384)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cosx", action="store_true", help="skip the COSX next-row measurement at N = 1")

@@ -78,7 +78,7 @@ typedef struct {
   int rank, world_size;  /* grid-leaf shard of this handle: leaves are split by predicted cost over world_size
                             handles (one per GPU / process); every handle returns a PARTIAL K, Exc, N that the
                             caller sums (NCCL all-reduce).  world_size <= 1: whole grid. */
-  size_t batch_bytes;    /* AO-value workspace per batch of leaves (0 = default 4 GiB) */
+  size_t batch_bytes;    /* AO-value workspace per batch of leaves (0 = default 16 GiB; only what the grid needs is allocated) */
   int mo_form;           /* 1 = the handle can also run occ_xc_build_mo / occ_xc_gradient_mo (adds one 128 x nocc slab per
                             spin to every tile's workspace); nocc_alpha / nocc_beta are then the occupied-orbital counts */
   int nocc_alpha;        /* MolecularOrbitals::n_alpha (include/occ/qm/mo.h:34-51) */

@@ -14,7 +14,8 @@ for wl in sys.argv[1:] or ["water_b3lyp_svp", "benzene_pbe_tzvp", "h2o32_b3lyp_s
     h = grid.MolecularGrid(basis).hierarchy()
     Cs = molecules.synthetic_orbitals(basis, nspin)
     kind = dft.UNRESTRICTED if nspin == 2 else dft.RESTRICTED
-    d = dft.DFT(method, basis, h, kind, nocc=[c.shape[1] for c in Cs])
+    d = dft.DFT(method, basis, h, kind, nocc=[c.shape[1] for c in Cs],
+                batch_bytes=int(os.environ.get("OCC_XC_BATCH_MB", "0")) << 20)
     info = d.info()
     for form in ("D", "mo"):
         call = (lambda: d.build(D2)) if form == "D" else (lambda: d.build_mo(D2, Cs))
