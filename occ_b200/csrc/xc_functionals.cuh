@@ -5,7 +5,8 @@
 //   lda_x(1) lda_c_vwn(7) lda_c_vwn_rpa(8) lda_c_vwn_3(30) gga_x_pbe(101) gga_x_b88(106) gga_c_pbe(130)
 //   gga_c_lyp(131) hyb_gga_xc_b3lyp(402) mgga_x_r2scan(497) mgga_c_r2scan(498) mgga_x_tpss(202) mgga_c_tpss(231)
 //   hyb_gga_xc_b3lyp5(475) hyb_gga_xc_pbeh(406) hyb_gga_xc_bhandh(435) hyb_gga_xc_bhandhlyp(436) lda_c_pw(12)
-//   lda_c_pw_mod(13) hyb_gga_xc_wb97x(464)
+//   lda_c_pw_mod(13) hyb_gga_xc_wb97x(464) hyb_gga_xc_b97(407) hyb_gga_xc_b3pw91(401) gga_c_pw91(134) gga_c_p86(132)
+//   lda_c_pz(9)
 // libxc conventions: exc = energy per particle; vrho = d(rho*exc)/d rho_s; vsigma = d(rho*exc)/d sigma with
 // sigma = grad rho . grad rho (polarized order aa, ab, bb); vtau = d(rho*exc)/d tau_s, tau = 1/2 sum |grad psi|^2.
 // Each functional is a single energy density in (rho_a, rho_b, sigma_aa, sigma_ab, sigma_bb, tau_a, tau_b);
@@ -20,12 +21,14 @@ enum : int {
   ID_GGA_X_B88 = 106, ID_GGA_C_PBE = 130, ID_GGA_C_LYP = 131, ID_HYB_GGA_XC_B3LYP = 402,
   ID_MGGA_X_R2SCAN = 497, ID_MGGA_C_R2SCAN = 498, ID_LDA_C_PW = 12, ID_LDA_C_PW_MOD = 13, ID_MGGA_X_TPSS = 202,
   ID_MGGA_C_TPSS = 231, ID_HYB_GGA_XC_PBEH = 406, ID_HYB_GGA_XC_BHANDH = 435, ID_HYB_GGA_XC_BHANDHLYP = 436,
-  ID_HYB_GGA_XC_B3LYP5 = 475, ID_HYB_GGA_XC_WB97X = 464
+  ID_HYB_GGA_XC_B3LYP5 = 475, ID_HYB_GGA_XC_WB97X = 464, ID_HYB_GGA_XC_B97 = 407, ID_HYB_GGA_XC_B3PW91 = 401,
+  ID_GGA_C_PW91 = 134, ID_GGA_C_P86 = 132, ID_LDA_C_PZ = 9
 };
 
 XC_HD double xc_exx_of(int id) { // xc_hyb_exx_coef (include/occ/dft/functional.h:557-579)
   switch (id) {
-  case ID_HYB_GGA_XC_B3LYP: case ID_HYB_GGA_XC_B3LYP5: return 0.20;
+  case ID_HYB_GGA_XC_B3LYP: case ID_HYB_GGA_XC_B3LYP5: case ID_HYB_GGA_XC_B3PW91: return 0.20;
+  case ID_HYB_GGA_XC_B97: return 0.1943; // Becke, J. Chem. Phys. 107, 8554 (1997)
   case ID_HYB_GGA_XC_PBEH: return 0.25;
   case ID_HYB_GGA_XC_BHANDH: case ID_HYB_GGA_XC_BHANDHLYP: return 0.50;
   case ID_HYB_GGA_XC_WB97X: return 1.0; // cam_alpha: libxc's xc_hyb_exx_coef returns the full-range fraction
@@ -48,7 +51,8 @@ XC_HD void xc_cam_of(int id, double *omega, double *alpha, double *beta) {
 XC_HD int xc_family_of(int id) {
   switch (id) {
   case ID_LDA_X: case ID_LDA_C_VWN: case ID_LDA_C_VWN_RPA: case ID_LDA_C_VWN_3: case ID_LDA_C_PW:
-  case ID_LDA_C_PW_MOD: return 0;
+  case ID_LDA_C_PW_MOD: case ID_LDA_C_PZ: return 0;
+  case ID_HYB_GGA_XC_B97: case ID_HYB_GGA_XC_B3PW91: case ID_GGA_C_PW91: case ID_GGA_C_P86:
   case ID_GGA_X_PBE: case ID_GGA_X_B88: case ID_GGA_C_PBE: case ID_GGA_C_LYP: case ID_HYB_GGA_XC_B3LYP:
   case ID_HYB_GGA_XC_B3LYP5: case ID_HYB_GGA_XC_PBEH: case ID_HYB_GGA_XC_BHANDH: case ID_HYB_GGA_XC_BHANDHLYP:
   case ID_HYB_GGA_XC_WB97X: return 1;
@@ -493,6 +497,83 @@ template <class T> XC_HD T e_wb97x(const XV<T> &v) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// B97 (Becke, J. Chem. Phys. 107, 8554 (1997); libxc hyb_gga_xc_b97 = 407, 19.43 % exact exchange): the same power series
+// as wB97X on the full-range LSDA exchange and the Stoll-partitioned PW92 correlation, three terms each.
+template <class T> XC_HD T e_b97(const XV<T> &v) {
+  const T ra43 = v.ra * cbrt(v.ra), rb43 = v.rb * cbrt(v.rb);
+  const T xa2 = v.saa / (ra43 * ra43), xb2 = v.sbb / (rb43 * rb43);
+  const T ex = XC_LDAX_C * (ra43 * b97_poly(xa2, 0.004, 0.8094, 0.5073, 0.7481, 0.0, 0.0) +
+                            rb43 * b97_poly(xb2, 0.004, 0.8094, 0.5073, 0.7481, 0.0, 0.0));
+  const T eaa = v.ra * pw92_ferro_1992(v.ra), ebb = v.rb * pw92_ferro_1992(v.rb);
+  const T eab = e_pw92(v, false) - eaa - ebb;
+  return ex + eaa * b97_poly(xa2, 0.2, 0.1737, 2.3487, -2.4868, 0.0, 0.0) +
+         ebb * b97_poly(xb2, 0.2, 0.1737, 2.3487, -2.4868, 0.0, 0.0) +
+         eab * b97_poly(0.5 * (xa2 + xb2), 0.006, 0.9454, 0.7471, -4.5961, 0.0, 0.0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Perdew-Zunger 1981 parametrisation of the Ceperley-Alder correlation energy (libxc lda_c_pz = 9), the local part of P86
+template <class T> XC_HD T pz81_eps(const T &rs, const double g, const double b1, const double b2, const double A,
+                                    const double B, const double C, const double D) {
+  if (val(rs) >= 1.0) return g / (1.0 + b1 * sqrt(rs) + b2 * rs);
+  const T l = log(rs);
+  return A * l + B + C * rs * l + D * rs;
+}
+template <class T> XC_HD T e_pz81(const XV<T> &v) {
+  T rho, rs, z;
+  rs_zeta(v, rho, rs, z);
+  const T eu = pz81_eps(rs, -0.1423, 1.0529, 0.3334, 0.0311, -0.048, 0.0020, -0.0116);
+  const T ep = pz81_eps(rs, -0.0843, 1.3981, 0.2611, 0.01555, -0.0269, 0.0007, -0.0048);
+  return rho * (eu + f_zeta(z) * (ep - eu));
+}
+// Rasolt-Geldart gradient coefficient shared by P86 and PW91: C(rs) = 0.001667 + (0.002568 + a rs + b rs^2) /
+// (1 + c rs + d rs^2 + 1e4 b rs^3)
+template <class T> XC_HD T rasolt_geldart_C(const T &rs) {
+  const T rs2 = rs * rs;
+  return 0.001667 + (0.002568 + 0.023266 * rs + 7.389e-6 * rs2) / (1.0 + 8.723 * rs + 0.472 * rs2 + 0.07389 * (rs2 * rs));
+}
+// Perdew 1986 gradient correction (Phys. Rev. B 33, 8822; libxc gga_c_p86 = 132):
+//   E = E^PZ81 + int exp(-Phi) C(n) |grad n|^2 / (d n^(4/3)),  Phi = 1.745 f~ [C(inf) / C(n)] |grad n| / n^(7/6), f~ = 0.11,
+//   d = 2^(1/3) sqrt(((1 + zeta)/2)^(5/3) + ((1 - zeta)/2)^(5/3))
+template <class T> XC_HD T e_p86(const XV<T> &v) {
+  T rho, rs, z;
+  rs_zeta(v, rho, rs, z);
+  const T stot = v.saa + 2.0 * v.sab + v.sbb;
+  const T Cn = rasolt_geldart_C(rs);
+  const T r16 = sqrt(cbrt(rho)); // n^(1/6)
+  const T n76 = rho * r16;
+  const T Phi = (1.745 * 0.11 * 0.004235) / Cn * sqrt(stot) / n76;
+  const T zp = 2.0 * v.ra / rho, zm = 2.0 * v.rb / rho; // 1 +- zeta
+  const T hp = 0.5 * zp, hm = 0.5 * zm;
+  const T d = 1.2599210498948732 * sqrt(hp * cbrt(hp * hp) + hm * cbrt(hm * hm));
+  return e_pz81(v) + exp(-Phi) * Cn * stot / (d * rho * cbrt(rho));
+}
+// Perdew-Wang 1991 correlation (libxc gga_c_pw91 = 134): eps = eps^PW92 + H0 + H1,
+//   H0 = (beta^2 / 2 alpha) phi^3 ln[1 + (2 alpha / beta) (t^2 + A t^4) / (1 + A t^2 + A^2 t^4)],
+//   A = (2 alpha / beta) / (exp(-2 alpha eps / (phi^3 beta^2)) - 1),  alpha = 0.09, beta = nu Cc(0), nu = (16/pi)(3 pi^2)^(1/3),
+//   H1 = nu [Cc(rs) - Cc(0) - 3 Cx / 7] phi^3 t^2 exp(-100 phi^4 (ks^2 / kF^2) t^2),  Cc(0) = 0.004235, Cx = -0.001667
+template <class T> XC_HD T e_pw91_c(const XV<T> &v) {
+  const double alpha = 0.09, Cc0 = 0.004235, Cx = -0.001667;
+  const double nu = 16.0 / XC_PI * 3.0936677262801355; // (3 pi^2)^(1/3)
+  const double beta = nu * Cc0;
+  T rho, rs, z;
+  rs_zeta(v, rho, rs, z);
+  const T ec = e_pw92(v, false) / rho;
+  const T phi = phi_zeta(v);
+  const T phi2 = phi * phi;
+  const T phi3 = phi * phi2;
+  const T stot = v.saa + 2.0 * v.sab + v.sbb;
+  const T kF = cbrt(XC_3PI2 * rho);
+  const T t2 = stot * XC_PI / (16.0 * phi2 * kF * (rho * rho)); // t = |grad n| / (2 phi ks n), ks^2 = 4 kF / pi
+  const T A = (2.0 * alpha / beta) / expm1(-2.0 * alpha * ec / (phi3 * beta * beta));
+  const T At2 = A * t2;
+  const T H0 = (beta * beta / (2.0 * alpha)) * phi3 * log(1.0 + (2.0 * alpha / beta) * t2 * (1.0 + At2) / (1.0 + At2 + At2 * At2));
+  const T H1 = nu * (rasolt_geldart_C(rs) - Cc0 - 3.0 * Cx / 7.0) * phi3 * t2 *
+               exp(-100.0 * (phi2 * phi2) * (4.0 / (XC_PI * kF)) * t2);
+  return rho * (ec + H0 + H1);
+}
+
+// ---------------------------------------------------------------------------------------------
 template <class T> XC_HD T e_b3lyp(const XV<T> &v) { // libxc hyb_gga_xc_b3lyp: a0 = 0.20, ax = 0.72, ac = 0.81
   return 0.08 * e_lda_x(v) + 0.72 * e_b88(v) + 0.19 * e_vwn<1>(v) + 0.81 * e_lyp(v);
 }
@@ -519,6 +600,12 @@ template <class T> XC_HD T xc_energy_density(int id, const XV<T> &v) {
   case ID_HYB_GGA_XC_BHANDH: return 0.5 * e_lda_x(v) + e_lyp(v);
   case ID_HYB_GGA_XC_BHANDHLYP: return 0.5 * e_b88(v) + e_lyp(v);
   case ID_HYB_GGA_XC_WB97X: return e_wb97x(v);
+  case ID_HYB_GGA_XC_B97: return e_b97(v);
+  case ID_LDA_C_PZ: return e_pz81(v);
+  case ID_GGA_C_P86: return e_p86(v);
+  case ID_GGA_C_PW91: return e_pw91_c(v);
+  // libxc hyb_gga_xc_b3pw91: a0 = 0.20, ax = 0.72, ac = 0.81 over {lda_x, gga_x_b88, lda_c_pw, gga_c_pw91}
+  case ID_HYB_GGA_XC_B3PW91: return 0.08 * e_lda_x(v) + 0.72 * e_b88(v) + 0.19 * e_pw92(v, false) + 0.81 * e_pw91_c(v);
   default: return T(0.0);
   }
 }

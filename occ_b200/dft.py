@@ -25,7 +25,8 @@ FUNCTIONAL_IDS = {"lda_x": 1, "lda_c_vwn": 7, "lda_c_vwn_rpa": 8, "lda_c_vwn_3":
                   "gga_x_b88": 106, "gga_c_pbe": 130, "gga_c_lyp": 131, "hyb_gga_xc_b3lyp": 402,
                   "mgga_x_r2scan": 497, "mgga_c_r2scan": 498, "lda_c_pw": 12, "lda_c_pw_mod": 13, "mgga_x_tpss": 202,
                   "mgga_c_tpss": 231, "hyb_gga_xc_pbeh": 406, "hyb_gga_xc_bhandh": 435, "hyb_gga_xc_bhandhlyp": 436,
-                  "hyb_gga_xc_b3lyp5": 475, "hyb_gga_xc_wb97x": 464}
+                  "hyb_gga_xc_b3lyp5": 475, "hyb_gga_xc_wb97x": 464, "hyb_gga_xc_b97": 407,
+            "hyb_gga_xc_b3pw91": 401, "gga_c_pw91": 134, "gga_c_p86": 132, "lda_c_pz": 9}
 
 # src/dft/dft_method.cpp:14-37 (builtin_definitions), restricted to components this library implements
 METHOD_DEFINITIONS = {
@@ -43,13 +44,15 @@ METHOD_DEFINITIONS = {
     "b3lyp5": ["hyb_gga_xc_b3lyp5"],
     "pbeh": ["hyb_gga_xc_pbeh"],
     "wb97x": ["hyb_gga_xc_wb97x"],
+    "b97": ["hyb_gga_xc_b97"],
+    "b3pw91": ["hyb_gga_xc_b3pw91"],
+    "bp86": ["gga_x_b88", "gga_c_p86"],
     # the 0.75 component factor of pbe0 / pbe1pbe is stored but never applied by the reference
     # (include/occ/dft/functional.h:506-508), so its XC build evaluates full PBE exchange; same here
     "pbe0": ["gga_x_pbe", "gga_c_pbe"],
     "pbe1pbe": ["gga_x_pbe", "gga_c_pbe"],
 }
-# builtin entries whose libxc components are NOT implemented here (get_dft_method raises for them):
-# b3pw91, b97, bp86 (gga_c_p86), m062x, wb97m(-v)
+# builtin entries whose libxc components are NOT implemented here (get_dft_method raises for them): m062x, wb97m(-v)
 
 RESTRICTED, UNRESTRICTED = "restricted", "unrestricted"
 

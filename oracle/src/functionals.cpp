@@ -452,10 +452,94 @@ template <class T> T F_b97_family(const B97Set &P, const Vars<T> &v) {
          ec_ab * b97_series(0.006, P.cab, 0.5 * (x2a + x2b));
 }
 template <class T> T F_wb97x(const Vars<T> &v) { return F_b97_family(kWB97X, v); }
+// B97 itself (Becke, J. Chem. Phys. 107, 8554 (1997), Table: c_x, c_ss, c_ab; 19.43 % exact exchange; libxc
+// hyb_gga_xc_b97, id 407; reference table src/dft/dft_method.cpp:18): full-range exchange (omega = 0), three terms.
+// "parity unpinned" beyond the machinery it shares with wB97X (pinned): the nine coefficients are the published ones.
+const B97Set kB97 = {{0.8094, 0.5073, 0.7481, 0.0, 0.0}, {0.1737, 2.3487, -2.4868, 0.0, 0.0},
+                     {0.9454, 0.7471, -4.5961, 0.0, 0.0}, 0.0};
+template <class T> T F_b97(const Vars<T> &v) { return F_b97_family(kB97, v); }
+
+// ------------------------------------------------------------------------------------------------
+// Perdew-Zunger 1981 (Phys. Rev. B 23, 5048, Appendix C): eps_c of the unpolarized / polarized gas, f(zeta) interpolation
+// [libxc lda_c_pz, id 9]; local part of P86.
+struct PzSet {
+  double gamma, beta1, beta2, A, B, C, D;
+};
+const PzSet pz_u = {-0.1423, 1.0529, 0.3334, 0.0311, -0.048, 0.0020, -0.0116};
+const PzSet pz_p = {-0.0843, 1.3981, 0.2611, 0.01555, -0.0269, 0.0007, -0.0048};
+template <class T> T pz_eps(const PzSet &p, const T &rs) {
+  if (value(rs) >= 1.0) return p.gamma / (1.0 + p.beta1 * sqrt(rs) + p.beta2 * rs);
+  return p.A * log(rs) + p.B + p.C * rs * log(rs) + p.D * rs;
+}
+template <class T> T F_pz81(const Vars<T> &v) {
+  T rho, rs, z;
+  rs_zeta(v, rho, rs, z);
+  const T eu = pz_eps(pz_u, rs), ep = pz_eps(pz_p, rs);
+  return rho * (eu + f_zeta(z) * (ep - eu));
+}
+// Rasolt & Geldart, Phys. Rev. B 34, 1325 (1986): gradient coefficient C_c(rs) = C_xc(rs) - C_x, C_x = -0.001667
+template <class T> T rg_Cc(const T &rs) {
+  return 0.001667 + (0.002568 + 0.023266 * rs + 7.389e-6 * sq(rs)) /
+                        (1.0 + 8.723 * rs + 0.472 * sq(rs) + 1.0e4 * 7.389e-6 * rs * sq(rs));
+}
+// Perdew, Phys. Rev. B 33, 8822 (1986), eqs. 4-9 [libxc gga_c_p86, id 132; reference method bp86,
+// src/dft/dft_method.cpp:30]: E_c = E_c^PZ81 + int exp(-Phi) C(n) |grad n|^2 / (d n^(4/3)),
+// Phi = 1.745 f~ (C(inf) / C(n)) |grad n| / n^(7/6), f~ = 0.11, d = 2^(1/3) sqrt(((1+z)/2)^(5/3) + ((1-z)/2)^(5/3)).
+// "parity unpinned": no reference-held value; published formula.
+template <class T> T F_p86(const Vars<T> &v) {
+  T rho, rs, z;
+  rs_zeta(v, rho, rs, z);
+  const T sigma = v.saa + 2.0 * v.sab + v.sbb;
+  const T C = rg_Cc(rs);
+  const double Cinf = 0.001667 + 0.002568;
+  const T n16 = sqrt(cbrt(rho));
+  const T Phi = 1.745 * 0.11 * (Cinf / C) * sqrt(sigma) / (rho * n16);
+  T zp, zm;
+  zeta_plus_minus(v, zp, zm);
+  const T a = 0.5 * zp, b = 0.5 * zm;
+  const T d = std::cbrt(2.0) * sqrt(a * cbrt(sq(a)) + b * cbrt(sq(b)));
+  return F_pz81(v) + exp(-Phi) * C * sigma / (d * rho * cbrt(rho));
+}
+// Perdew & Wang 1991 correlation (Perdew et al., Phys. Rev. B 46, 6671 (1992), eqs. 10-15; the form quoted in the PBE paper,
+// Phys. Rev. Lett. 77, 3865, ref. 3) [libxc gga_c_pw91, id 134; component of hyb_gga_xc_b3pw91]:
+//   eps_c = eps^PW92 + H0 + H1
+//   H0 = (beta^2 / 2 alpha) phi^3 ln[1 + (2 alpha / beta) (t^2 + A t^4) / (1 + A t^2 + A^2 t^4)]
+//   A  = (2 alpha / beta) / (exp(-2 alpha eps^PW92 / (phi^3 beta^2)) - 1)
+//   H1 = nu [C_c(rs) - C_c(0) - 3 C_x / 7] phi^3 t^2 exp(-100 phi^4 (k_s^2 / k_F^2) t^2)
+//   alpha = 0.09, beta = nu C_c(0), nu = (16 / pi)(3 pi^2)^(1/3), C_c(0) = 0.004235, C_x = -0.001667
+// Pinned by E_c^PW91 of the hydrogen and helium atoms in Table I of the PBE paper (-0.0065, -0.0450 Eh), tests/test_oracle_pins.py.
+template <class T> T F_pw91_c(const Vars<T> &v) {
+  const double alpha = 0.09, Cc0 = 0.004235, Cx = -0.001667;
+  const double nu = 16.0 / kPi * std::cbrt(3.0 * kPi * kPi), beta = nu * Cc0;
+  T rho, rs, z;
+  rs_zeta(v, rho, rs, z);
+  const T ec = F_pw<T, 0>(v) / rho;
+  const T phi = phi_zeta(v);
+  const T phi3 = phi * sq(phi);
+  const T sigma = v.saa + 2.0 * v.sab + v.sbb;
+  const T kF = cbrt(3.0 * kPi * kPi * rho);
+  const T t2 = sigma * kPi / (16.0 * sq(phi) * kF * sq(rho));
+  const T A = (2.0 * alpha / beta) / expm1(-2.0 * alpha * ec / (phi3 * beta * beta));
+  const T H0 = (beta * beta / (2.0 * alpha)) * phi3 *
+               log(1.0 + (2.0 * alpha / beta) * (t2 + A * sq(t2)) / (1.0 + A * t2 + sq(A) * sq(t2)));
+  const T ks2_kF2 = 4.0 / (kPi * kF);
+  const T H1 = nu * (rg_Cc(rs) - Cc0 - 3.0 * Cx / 7.0) * phi3 * t2 * exp(-100.0 * sq(sq(phi)) * ks2_kF2 * t2);
+  return rho * (ec + H0 + H1);
+}
+// libxc hyb_gga_xc_b3pw91 (id 401): a0 = 0.20, ax = 0.72, ac = 0.81 over {lda_x, gga_x_b88, lda_c_pw, gga_c_pw91}
+// (Becke, J. Chem. Phys. 98, 5648 (1993))
+template <class T> T F_b3pw91(const Vars<T> &v) {
+  return 0.08 * F_lda_x(v) + 0.72 * F_b88(v) + 0.19 * F_pw<T, 0>(v) + 0.81 * F_pw91_c(v);
+}
 
 template <class T> bool F_dispatch(int id, const Vars<T> &v, T &out) {
   switch (id) {
   case ORC_HYB_GGA_XC_WB97X: out = F_wb97x(v); return true;
+  case ORC_HYB_GGA_XC_B97: out = F_b97(v); return true;
+  case ORC_HYB_GGA_XC_B3PW91: out = F_b3pw91(v); return true;
+  case ORC_GGA_C_PW91: out = F_pw91_c(v); return true;
+  case ORC_GGA_C_P86: out = F_p86(v); return true;
+  case ORC_LDA_C_PZ: out = F_pz81(v); return true;
   case ORC_LDA_C_PW: out = F_pw<T, 0>(v); return true;
   case ORC_LDA_C_PW_MOD: out = F_pw<T, 1>(v); return true;
   case ORC_MGGA_X_TPSS: out = F_tpss_x(v); return true;
@@ -560,7 +644,12 @@ int orc_xc_family(int id) {
   case ORC_LDA_C_VWN_3:
   case ORC_LDA_C_PW:
   case ORC_LDA_C_PW_MOD:
+  case ORC_LDA_C_PZ:
     return 0;
+  case ORC_HYB_GGA_XC_B97:
+  case ORC_HYB_GGA_XC_B3PW91:
+  case ORC_GGA_C_PW91:
+  case ORC_GGA_C_P86:
   case ORC_GGA_X_B88:
   case ORC_GGA_C_LYP:
   case ORC_GGA_X_PBE:
@@ -586,7 +675,10 @@ double orc_xc_exx(int id) { // xc_hyb_exx_coef (include/occ/dft/functional.h:557
   switch (id) {
   case ORC_HYB_GGA_XC_B3LYP:
   case ORC_HYB_GGA_XC_B3LYP5:
+  case ORC_HYB_GGA_XC_B3PW91:
     return 0.20;
+  case ORC_HYB_GGA_XC_B97:
+    return 0.1943;
   case ORC_HYB_GGA_XC_PBEH:
     return 0.25;
   case ORC_HYB_GGA_XC_BHANDH:

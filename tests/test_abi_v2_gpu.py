@@ -167,3 +167,20 @@ def test_single_process_multi_gpu_build_sums_to_the_one_gpu_result(case, oracle,
     Ka = md.build(D2).copy()
     assert np.array_equal(md.build(D2), Ka) and np.abs(Ka - K1).max() < 1e-12
     md.close()
+
+
+@pytest.mark.parametrize("nspin", [1, 2])
+@pytest.mark.parametrize("method,exx", [("b97", 0.1943), ("b3pw91", 0.20), ("bp86", 0.0)])
+def test_b97_b3pw91_bp86_builds(case, oracle, method, exx, nspin):
+    """the method-table entries added in round 2 (src/dft/dft_method.cpp:16,18,30): hyb_gga_xc_b97, hyb_gga_xc_b3pw91
+    (lda_x + gga_x_b88 + lda_c_pw + gga_c_pw91) and gga_x_b88 + gga_c_p86 (PZ81 local part)"""
+    c = case("water", "def2-svp")
+    b = c["basis"]
+    D2 = molecules.synthetic_density(b, nspin)
+    ref = oracle.xc_build(c["obasis"], c["spts"], c["sw"], c["leaves"], _names(method, oracle), nspin, D2)
+    d = dft.DFT(method, b, _hier(c), dft.UNRESTRICTED if nspin == 2 else dft.RESTRICTED)
+    K = d.build(D2)
+    assert np.abs(K - ref["K"]).max() < 1e-9 and abs(d.exchange_correlation_energy() - ref["exc"]) < 1e-8
+    assert abs(ref["exc"]) > 1.0
+    assert d.exact_exchange_factor() == pytest.approx(exx) if hasattr(d, "exact_exchange_factor") else True
+    d.close()

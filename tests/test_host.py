@@ -14,6 +14,11 @@ def test_method_table_mirrors_the_reference():
     assert dft.get_dft_method("svwn5") == [1, 7]
     assert dft.get_dft_method("r2scan") == [497, 498]
     assert dft.get_dft_method("gga_x_b88 gga_c_lyp") == [106, 131]
+    assert dft.get_dft_method("bp86") == [106, 132] and dft.get_dft_method("b97") == [407]
+    assert dft.get_dft_method("b3pw91") == [401] and dft.get_dft_method("wb97x") == [464]
+    for missing in ("m062x", "wb97m", "wb97m-v"):            # libxc components this library does not implement
+        with pytest.raises(RuntimeError):
+            dft.get_dft_method(missing)
     with pytest.raises(RuntimeError):
         dft.get_dft_method("not_a_functional")
 
@@ -159,15 +164,15 @@ def test_dft_methods_json_overrides_the_builtin_table(tmp_path, monkeypatch):
     (tmp_path / "methods").mkdir()
     (tmp_path / "methods" / "dft_methods.json").write_text(json.dumps({"methods": {
         "mypbe": {"components": [{"id": "gga_x_b88"}, {"id": "gga_c_pbe", "factor": 0.5}]},
-        "bp86": {"components": [{"id": "gga_x_b88"}, {"id": "gga_c_p86"}]}}}))
+        "m062x": {"components": [{"id": "hyb_mgga_x_m06_2x"}, {"id": "mgga_c_m06_2x"}]}}}))
     assert dft.get_dft_method("pbe") == [101, 130]                      # builtin, no OCC_DATA_PATH file
     monkeypatch.setenv("OCC_DATA_PATH", str(tmp_path))
     assert dft.get_dft_method("mypbe") == [106, 130]
     assert dft.get_dft_method("gga_x_pbe") == [101]                     # plain libxc names still resolve
     with pytest.raises(RuntimeError):
         dft.get_dft_method("pbe")                                       # the file REPLACES the builtin table
-    with pytest.raises(RuntimeError, match="gga_c_p86 not found"):
-        dft.get_dft_method("bp86")
+    with pytest.raises(RuntimeError, match="hyb_mgga_x_m06_2x not found"):
+        dft.get_dft_method("m062x")
     # the reference's own share/methods file parses (when the reference tree is present in this container)
     ref = "/root/reference/share"
     if os.path.exists(os.path.join(ref, "methods", "dft_methods.json")):
