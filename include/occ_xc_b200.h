@@ -243,6 +243,8 @@ void occ_xc_multi_destroy(occ_xc_multi *m);
 /* occ_xc_vv10 / occ_xc_vv10_gradient over the shards of a multi handle created on the NLC grid (same arguments and
  * results): every GPU evaluates rho / grad rho on its leaves, gathers the other points' arrays from its peers, runs
  * 1/ndev of the O(N^2) pair work, and the partial pair sums / K panels / gradients are summed in rank order. */
+/* occ_xc_gradient / occ_xc_gradient_mo (C NULL = D form) over the shards: partial gradients summed in rank order */
+int occ_xc_multi_gradient(occ_xc_multi *m, const double *D2, const double *C, double *gradient);
 int occ_xc_multi_vv10(occ_xc_multi *m, const double *D2, const size_t *orig_index, double vv10_b, double vv10_C, double *K,
                       double *energy);
 int occ_xc_multi_vv10_gradient(occ_xc_multi *m, const double *D2, const size_t *orig_index, const size_t *atom_offsets,

@@ -20,7 +20,7 @@ SYMBOLS = ["occ_xc_create", "occ_xc_build", "occ_xc_build_device", "occ_xc_build
            "occ_xc_partition_leaves", "occ_xc_register_lebedev", "occ_xc_grid_create", "occ_xc_grid_from_points", "occ_xc_grid_npts",
            "occ_xc_grid_nleaves", "occ_xc_grid_atom_info", "occ_xc_grid_copy", "occ_xc_grid_destroy",
            "occ_xc_measure_fp64_tensor_peak", "occ_xc_multi_create", "occ_xc_multi_build", "occ_xc_multi_ndev", "occ_xc_multi_get_info", "occ_xc_multi_destroy",
-           "occ_xc_vv10_gradient", "occ_xc_multi_vv10", "occ_xc_multi_vv10_gradient"]
+           "occ_xc_vv10_gradient", "occ_xc_multi_vv10", "occ_xc_multi_vv10_gradient", "occ_xc_multi_gradient"]
 # every symbol include/occ_cosx_b200.h declares
 COSX_SYMBOLS = ["occ_cosx_create", "occ_cosx_compute_K", "occ_cosx_compute_K_range_separated", "occ_cosx_compute_K_mo",
                 "occ_cosx_compute_K_range_separated_mo", "occ_cosx_compute_K_range_separated_kind",

@@ -84,4 +84,5 @@ int vv10_stage_gradient(occ_xc_handle *h, const xcb::VV10Params &merged, const x
 // one build on device buffers (xc_host.cu); D2_dev may be NULL when C_dev is given (D2 = C C^T formed on the device)
 int xc_build_device_impl(occ_xc_handle *h, const double *D2_dev, const double *C_dev, double *K_dev, double *scalars_dev,
                          void *cuda_stream);
+int xc_gradient_impl(occ_xc_handle *h, const double *D2, const double *C, double *gradient); // host D2 (, C) -> host gradient
 int occ_xc_set_error(const char *msg); // sets the calling thread's occ_xc_last_error() and returns 1

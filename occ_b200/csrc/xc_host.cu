@@ -1281,22 +1281,22 @@ int occ_xc_host_unregister(void *p) {
   return 0;
 }
 
-static int gradient_impl(occ_xc_handle *h, const double *D2, const double *C, double *gradient);
 
 int occ_xc_gradient(occ_xc_handle *h, const double *D2, double *gradient) {
   if (!h || !D2 || !gradient) return fail("occ_xc_gradient: null argument");
   if (!h->gradient) return fail("occ_xc_gradient: handle was created without the gradient option");
-  return gradient_impl(h, D2, nullptr, gradient);
+  return xc_gradient_impl(h, D2, nullptr, gradient);
 }
 
 int occ_xc_gradient_mo(occ_xc_handle *h, const double *D2, const double *C, double *gradient) {
   if (!h || !D2 || !C || !gradient) return fail("occ_xc_gradient_mo: null argument");
   if (!h->gradient) return fail("occ_xc_gradient_mo: handle was created without the gradient option");
   if (!h->mo) return fail("occ_xc_gradient_mo: the handle was created without occupied-orbital counts");
-  return gradient_impl(h, D2, C, gradient);
+  return xc_gradient_impl(h, D2, C, gradient);
 }
 
-static int gradient_impl(occ_xc_handle *h, const double *D2, const double *C, double *gradient) {
+} // extern "C"
+int xc_gradient_impl(occ_xc_handle *h, const double *D2, const double *C, double *gradient) {
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   BuildParams P = h->P;
@@ -1357,6 +1357,8 @@ static int gradient_impl(occ_xc_handle *h, const double *D2, const double *C, do
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
+
+extern "C" {
 
 int occ_xc_get_info(const occ_xc_handle *h, occ_xc_info_t *info) {
   if (!h || !info) return fail("occ_xc_get_info: null argument");

@@ -486,4 +486,33 @@ int occ_xc_multi_vv10_gradient(occ_xc_multi *m, const double *D2, const size_t *
   return multi_vv10(m, D2, orig_index, atom_offsets, vv10_b, vv10_C, nullptr, gradient, energy);
 }
 
+// XC nuclear gradient over the shards (DFT::compute_xc_gradient_impl, dft.h:598-749: its tbb loop over leaves with
+// thread-local gradients summed at the end, :741-746): every rank evaluates the contribution of its leaves — uploading D2
+// (and C) over its own PCIe link — and the 3 x natoms partial gradients are summed on the host in rank order.
+int occ_xc_multi_gradient(occ_xc_multi *m, const double *D2, const double *C, double *gradient) {
+  if (!m || !D2 || !gradient) return occ_xc_set_error("occ_xc_multi_gradient: null argument");
+  const int n = m->n, natoms = m->h[0]->natoms;
+  for (int r = 0; r < n; ++r) {
+    if (!m->h[r]->gradient) return occ_xc_set_error("occ_xc_multi_gradient: handles were created without the gradient option");
+    if (C && !m->h[r]->mo) return occ_xc_set_error("occ_xc_multi_gradient: the handles were created without occupied-orbital counts");
+  }
+  if (!m->h_grad &&
+      cudaHostAlloc(&m->h_grad, 3 * static_cast<size_t>(natoms) * MAX_DEV * sizeof(double), cudaHostAllocPortable) != cudaSuccess)
+    return occ_xc_set_error("occ_xc_multi_gradient: cudaHostAlloc failed");
+  for (int r = 0; r < n; ++r)
+    m->worker[r]->submit([=]() -> int {
+      return xc_gradient_impl(m->h[r], D2, C, m->h_grad + 3 * static_cast<size_t>(natoms) * r);
+    });
+  std::string err;
+  int rc = 0;
+  for (int r = 0; r < n; ++r) rc |= m->worker[r]->wait(&err);
+  if (rc) return occ_xc_set_error(err.c_str());
+  for (int k = 0; k < 3 * natoms; ++k) {
+    double g = 0.0;
+    for (int r = 0; r < n; ++r) g += m->h_grad[3 * static_cast<size_t>(natoms) * r + k];
+    gradient[k] = g;
+  }
+  return 0;
+}
+
 } // extern "C"

@@ -359,6 +359,20 @@ class MultiGPUDFT:
         self.total_density = (na.value, nb.value)
         return K
 
+    def gradient(self, D2: np.ndarray, Cs=None) -> np.ndarray:
+        """occ_xc_multi_gradient: the XC nuclear gradient (natoms, 3) summed over the shards; needs gradient=True"""
+        n = self.nspin * self.nbf
+        D2 = np.asfortranarray(D2, dtype=np.float64)
+        if D2.shape != (n, self.nbf):
+            raise RuntimeError(f"density matrix has shape {D2.shape}, expected {(n, self.nbf)}")
+        packed = None
+        if Cs is not None:
+            Cs = [Cs] if isinstance(Cs, np.ndarray) else list(Cs)
+            packed = np.concatenate([np.asfortranarray(c, dtype=np.float64).ravel(order="F") for c in Cs])
+        g = np.zeros((len(self.basis.atomic_numbers), 3))
+        check(lib().occ_xc_multi_gradient(self._m, ptr(D2), ptr(packed) if packed is not None else None, ptr(g)))
+        return g
+
     def build_raw(self, d2_ptr: int, c_ptr: int, k_ptr: int):
         """occ_xc_multi_build on raw host pointers (pinned buffers owned by the caller; 0 = NULL)"""
         exc, na, nb = C.c_double(), C.c_double(), C.c_double()

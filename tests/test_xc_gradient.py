@@ -140,3 +140,35 @@ def test_cuda_gradient_mo_form_matches_oracle_and_d_form(case, oracle, mol, bas,
     assert np.abs(gm - gd).max() < 1e-9
     assert np.abs(gm - ref).max() < 1e-8
     assert np.abs(ref).max() > 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("devices", [(0, 0), (0, 0, 0), (0, 1), (0, 1, 2, 3)])
+def test_cuda_gradient_on_shards_of_one_process(case, oracle, devices):
+    """occ_xc_multi_gradient: the leaf shards' partial gradients sum to the one-handle gradient (1e-11) and to the oracle's
+    (1e-8); D form and factorised form"""
+    import torch
+    from occ_b200 import dft
+    if max(devices) >= torch.cuda.device_count():
+        pytest.skip(f"needs {max(devices) + 1} GPUs")
+    c = case("benzene", "def2-tzvp")
+    b = c["basis"]
+    Cs = molecules.synthetic_orbitals(b, 1, nocc=100)
+    D2 = molecules.synthetic_density(b, 1, nocc=100)
+    names = [n for i in dft.get_dft_method("b3lyp") for n, v in oracle.FUNC_IDS.items() if v == i]
+    ref = oracle.xc_gradient(c["obasis"], c["spts"], c["sw"], c["leaves"], names, 1, D2, len(c["Z"]))
+    h = dft.GridHierarchy(c["spts"], c["sw"], c["leaves"])
+    one = dft.DFT("b3lyp", b, h, gradient=True)
+    g1 = one.gradient(D2)
+    one.close()
+    m = dft.MultiGPUDFT("b3lyp", b, h, devices=devices, gradient=True, nocc=100)
+    for g in (m.gradient(D2), m.gradient(D2, Cs)):
+        assert np.abs(g - g1).max() < 1e-9 and np.abs(g - ref).max() < 1e-8
+    K = m.build(D2)                                  # the same handles still serve the build
+    refK = oracle.xc_build(c["obasis"], c["spts"], c["sw"], c["leaves"], names, 1, D2)
+    assert np.abs(K - refK["K"]).max() < 1e-9
+    m.close()
+    plain = dft.MultiGPUDFT("b3lyp", b, h, devices=devices)
+    with pytest.raises(RuntimeError, match="gradient option"):
+        plain.gradient(D2)
+    plain.close()
