@@ -473,6 +473,12 @@ def run_b200(args):
                 cosx_row = cosx_next_row(basis, WORKLOADS[args.workload][0], WORKLOADS[args.workload][1], peak)
             except Exception as e:  # noqa: BLE001
                 cosx_row = {"error": str(e)[:200]}
+        grad_row = vv10_row = None
+        if world == 1 and not args.no_cosx and nspin == 1:
+            try:     # SURVEY 8(f) ranks 1 and 4 on the same molecule (host D -> host result, one call each)
+                grad_row, vv10_row = gradient_and_vv10_next_rows(basis, c["method"], args.workload)
+            except Exception as e:  # noqa: BLE001
+                grad_row = {"error": str(e)[:200]}
         nC = int(c["hC"].numel())
         h2d = 8 * (nC if mo else n)
         line = {
@@ -522,7 +528,7 @@ def run_b200(args):
                              "into the host K")},
             "gpu_launches": int(launches_total * args.steps),
             "clocks": clocks, "setup_seconds": c["setup_s"],
-            "next_rows": {"cosx": cosx_row},
+            "next_rows": {"cosx": cosx_row, "xc_gradient": grad_row, "vv10": vv10_row},
         }
         print(json.dumps(line), flush=True)
     ddft.close()
@@ -564,6 +570,43 @@ def cosx_next_row(basis, mol, bas, peak, reps=2):
             "h2d_bytes": 8 * basis.nbf ** 2 + 8 * basis.nbf * int(Cocc.shape[1]), "d2h_bytes": 8 * basis.nbf ** 2,
             "K_absmax": head["K_absmax"], "d_form": dict(out["occ_cosx_compute_K"], entry="occ_cosx_compute_K"),
             "setup_seconds": t_setup}
+
+
+def gradient_and_vv10_next_rows(basis, method, workload, reps=2):
+    """occ_xc_gradient_mo on the workload's own grid and occ_xc_vv10 / occ_xc_vv10_gradient on the reference's default
+    NLC grid (host D2 -> host result; restricted)."""
+    from occ_b200 import dft, grid, molecules, nlc
+    quality = WORKLOADS[workload][4]
+    h = grid.MolecularGrid(basis, grid.GridSettings.from_grid_quality(quality) if quality else None).hierarchy()
+    D2 = molecules.synthetic_density(basis, 1)
+    Cs = molecules.synthetic_orbitals(basis, 1)
+
+    def best(call):
+        call()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            r = call()
+            ts.append(time.perf_counter() - t0)
+        return 1e3 * min(ts), r
+
+    d = dft.DFT(method, basis, h, gradient=True, nocc=Cs[0].shape[1])
+    ms_g, g = best(lambda: d.gradient_mo(D2, Cs))
+    ms_gd, _ = best(lambda: d.gradient(D2))
+    d.close()
+    grad_row = {"entry": "occ_xc_gradient_mo", "workload": workload, "grid_points": len(h.sorted_weights),
+                "ms_per_call": ms_g, "d_form_ms_per_call": ms_gd, "gradient_absmax": float(np.abs(g).max())}
+    f = nlc.NonLocalCorrelationFunctional()
+    f.set_integration_grid(basis, screening_threshold=1e-10, gradient=True)
+    ms_e, (e, _) = best(lambda: f.vv10(D2))
+    ms_vg, (_, gv) = best(lambda: f.vv10_gradient(D2))
+    n = f.num_grid_points
+    f.close()
+    vv10_row = {"entry": "occ_xc_vv10 / occ_xc_vv10_gradient", "workload": f"{workload} density, default NLC grid (110/50, 1e-7)",
+                "nlc_grid_points": n, "pairs": n * (n - 1) // 2, "energy_vxc_ms_per_call": ms_e,
+                "gradient_ms_per_call": ms_vg, "pairs_per_s": n * (n - 1) / 2 / (1e-3 * ms_e), "energy": e,
+                "gradient_absmax": float(np.abs(gv).max())}
+    return grad_row, vv10_row
 
 
 def _workspace_gb(info, nspin):
