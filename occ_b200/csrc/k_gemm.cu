@@ -93,17 +93,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) XC_SYM(k_vxc_resident)(BuildParam
   const double *base = P.scratch + t.scr_off;
   const double *Ag = base + static_cast<size_t>(it.acomp) * slab; // phi_a[i*128 + p]
   const int *gidx = P.bf_index + t.bf_off;
-  double *Kt = P.Ktmp[it.spin];
-  const int n0 = it.jb * GN;
+  // it.spin == 2 (unrestricted builds): the CTA owns 32 basis-function columns for BOTH spins — B columns 0..31 are the
+  // alpha block, 32..63 the beta block of the same functions — so that the four AO slabs of those columns are read once
+  // for the two spins (the B-block build is a quarter of the kernel's warp time at nb ~ 200)
+  const bool both = it.spin == 2;
+  const int ncol = both ? GN / 2 : GN;
+  const int n0 = it.jb * ncol;
   // Symmetric terms — phi_k^T diag(c_tau) phi_k of a meta-GGA (acomp != 0) and phi^T diag(c0) phi of an LDA build —
   // need only their upper triangle, because the build returns K = Ktmp + Ktmp^T: row blocks strictly below the CTA's
   // 64 columns are skipped, blocks strictly above count twice, blocks that straddle the diagonal are computed whole.
   const bool symmetric = it.acomp != 0 || P.deriv == 0;
   const int nib_all = (nb + GM - 1) / GM;
-  const int nib = symmetric ? min(nib_all, (n0 + GN + GM - 1) / GM) : nib_all;
+  const int nib = symmetric ? min(nib_all, (n0 + ncol + GM - 1) / GM) : nib_all;
   constexpr int NKC = TILE_P / RK;
   const int nq = nib * NKC; // flattened (ib, kc) chunks
-  const int ni_valid = min(8, max(0, (nb - n0 + 7) >> 3));
+  const int ni_valid = min(ncol / 8, max(0, (nb - n0 + 7) >> 3)); // valid 8-column groups (per spin when `both`)
   double *Bres = smem;                                   // [64][R_LDB]
   double *Aw = smem + R_BSZ + warp * (RS * R_ASZ);       // this warp's ring: RS x [16][R_LDA]
   int *scol = reinterpret_cast<int *>(smem + R_BSZ + 8 * RS * R_ASZ);
@@ -130,15 +134,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) XC_SYM(k_vxc_resident)(BuildParam
 
   { // resident B block: thread = (point, 32-column half)
     const int p = tid & (TILE_P - 1), half = tid >> 7;
-    const double *cf = P.coef + (static_cast<size_t>(it.tile) * P.nspin + it.spin) * NCOEF * TILE_P + p;
-    const double *q0 = base + static_cast<size_t>(n0 + half * 32) * TILE_P + p;
+    const int sp = both ? half : it.spin, cbase = both ? n0 : n0 + half * 32;
+    const double *cf = P.coef + (static_cast<size_t>(it.tile) * P.nspin + sp) * NCOEF * TILE_P + p;
+    const double *q0 = base + static_cast<size_t>(cbase) * TILE_P + p;
     double *dst = Bres + (half * 32) * R_LDB;
     if (P.debug & 16) { // timing experiment: B block without the slab loads
       for (int j = 0; j < 32; ++j) dst[j * R_LDB + (p ^ R_SW(j))] = 1e-3 * j;
     } else {
       // only the columns that exist are read (groups of 8; the rest of the block is zero): for local bases of 100-250
       // functions the last 64-column block is mostly padding
-      const int jv = min(32, max(0, nb - (n0 + half * 32)));
+      const int jv = min(32, max(0, nb - cbase));
       if (it.acomp == 0) {
         const double c0 = cf[0];
         if (P.deriv >= 1) {
@@ -167,7 +172,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) XC_SYM(k_vxc_resident)(BuildParam
       }
       for (int j = (jv + 7) & ~7; j < 32; ++j) dst[j * R_LDB + (p ^ R_SW(j))] = 0.0;
     }
-    if (tid < GN) scol[tid] = n0 + tid < nb ? __ldg(gidx + n0 + tid) : -1;
+    if (tid < GN) {
+      const int c = both ? n0 + (tid & 31) : n0 + tid;
+      scol[tid] = c < nb ? __ldg(gidx + c) : -1;
+    }
   }
   __syncthreads(); // the only CTA-wide barrier: B block and column map complete
 
@@ -181,7 +189,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) XC_SYM(k_vxc_resident)(BuildParam
   for (int q = 0; q < nq; ++q) {
     if (kc == 0) {
       mi_valid = min(2, max(0, (nb - (ib * GM + warp * R_WROWS) + 7) >> 3));
-      full = mi_valid == 2 && ni_valid == 8;
+      full = mi_valid == 2 && ni_valid == ncol / 8;
 #pragma unroll
       for (int mi = 0; mi < 2; ++mi) {
         const int i = ib * GM + warp * R_WROWS + mi * 8 + gid;
@@ -218,6 +226,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) XC_SYM(k_vxc_resident)(BuildParam
       if (q + RS - 1 < nq) load_stage(q + RS - 1, (q + RS - 1) % RS);
       cp_async_commit();
       if (mi_valid > 0 && ni_valid > 0) {
+        const int nmask = both ? 3 : 7; // position of an 8-column group inside its spin block
 #pragma unroll
         for (int k4 = 0; k4 < RK / 4; ++k4) {
           double a[2];
@@ -226,7 +235,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) XC_SYM(k_vxc_resident)(BuildParam
           for (int mi = 0; mi < 2; ++mi) a[mi] = As[mi * 8 * R_LDA + ko];
 #pragma unroll
           for (int ni = 0; ni < 8; ++ni)
-            if (ni < ni_valid) {
+            if ((ni & nmask) < ni_valid) {
               const double b = Bs[ni * 8 * R_LDB + ko];
 #pragma unroll
               for (int mi = 0; mi < 2; ++mi)
@@ -248,6 +257,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) XC_SYM(k_vxc_resident)(BuildParam
       }
 #pragma unroll
       for (int ni = 0; ni < 8; ++ni) {
+        double *Kt = P.Ktmp[both ? (ni >> 2) : it.spin];
         const int2 gc = *reinterpret_cast<const int2 *>(scol + ni * 8 + 2 * tig);
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi) {

@@ -560,6 +560,7 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
               di.spin = static_cast<signed char>(sp);
               di.acomp = static_cast<signed char>(ac);
               dens.push_back(di);
+              if (nspin == 2) continue; // unrestricted: spin-fused Vxc items below
               VxcItem vi;
               vi.tile = ti;
               vi.jb = static_cast<short>(jb);
@@ -573,6 +574,21 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
                 const int rows = std::min(t.nb, nib * 128), cols = std::min(64, t.nb - n0);
                 if (cols > 0) h->vxc_executed_flops += 2.0 * t.count * rows * cols;
               }
+            }
+        if (nspin == 2) // one item = 32 basis-function columns x both spins (k_vxc_resident, it.spin == 2)
+          for (int ac = 0; ac < nac; ++ac)
+            for (int jb = 0; jb * 32 < t.nb; ++jb) {
+              VxcItem vi;
+              vi.tile = ti;
+              vi.jb = static_cast<short>(jb);
+              vi.spin = 2;
+              vi.acomp = static_cast<signed char>(ac);
+              vxc.push_back(vi);
+              const bool symmetric = ac != 0 || deriv == 0;
+              const int n0 = jb * 32, nib_all = (t.nb + 127) / 128;
+              const int nib = symmetric ? std::min(nib_all, (n0 + 32 + 127) / 128) : nib_all;
+              const int rows = std::min(t.nb, nib * 128), cols = std::min(32, t.nb - n0);
+              h->vxc_executed_flops += 2.0 * 2.0 * t.count * rows * cols;
             }
         if (h->mo) {
           // per tile and spin: rho / grad rho in the factorised form when 4 n nb nocc < 2 n nb^2, tau when nocc < nb
