@@ -25,9 +25,16 @@ template <int MODE> __device__ __forceinline__ void XC_SYM(gemm_xd_body)(const B
   const size_t slab = static_cast<size_t>(t.nbp) * TILE_P;
   const int a_slab = MODE == 0 ? it.acomp : (it.acomp == 0 ? 0 : (it.acomp == 1 ? P.slab_G + it.spin : it.acomp - 1));
   const double *Ag = P.scratch + t.scr_off + static_cast<size_t>(a_slab) * slab;
-  const double *Dm = MODE == 0 ? (it.acomp == 0 ? P.Drho : P.Dtau)[it.spin] : P.DT[it.spin];
+  // it.spin == 2 (MODE 0, unrestricted builds): the CTA owns 32 basis-function columns for BOTH spins — X columns 0..31 are
+  // phi_a D_alpha, 32..63 phi_a D_beta of the same functions — so that the AO slabs of the row-dot epilogue (for local bases
+  // of 100-250 functions as many bytes as the K loop) are read once for the two spins
+  const bool both = MODE == 0 && it.spin == 2;
+  const int s0 = both ? 0 : it.spin;
+  const double *Dsp[2];
+  Dsp[0] = MODE == 0 ? (it.acomp == 0 ? P.Drho : P.Dtau)[s0] : P.DT[s0];
+  Dsp[1] = both ? (it.acomp == 0 ? P.Drho : P.Dtau)[1] : Dsp[0];
   const int *gidx = P.bf_index + t.bf_off;
-  const int n0 = it.jb * GN;
+  const int n0 = it.jb * (both ? GN / 2 : GN);
 
   // B loader assignment: this thread stages k = kk of every chunk for NBR columns
   constexpr int NROWT = NTHREADS / GK;   // columns covered per pass
@@ -37,12 +44,13 @@ template <int MODE> __device__ __forceinline__ void XC_SYM(gemm_xd_body)(const B
   bool nvalid[NBR];
 #pragma unroll
   for (int r = 0; r < NBR; ++r) {
-    const int n = n0 + nn + NROWT * r;
+    const int c = nn + NROWT * r;                 // column of the 64-wide block
+    const int n = n0 + (both ? (c & 31) : c);     // basis function
     nvalid[r] = n < nb;
     coloff[r] = nvalid[r] ? static_cast<size_t>(__ldg(gidx + n)) * P.ldD : 0;
   }
   // 8-column groups of this warp's 32 columns that hold real basis functions (the rest is padding: no DMMA)
-  const int ni_valid = min(4, max(0, (nb - (n0 + wn * 32) + 7) >> 3));
+  const int ni_valid = min(4, max(0, (nb - (n0 + (both ? 0 : wn * 32)) + 7) >> 3));
 
   int grow_next = 0;
   auto load_stage = [&](int kc, int stage) {
@@ -59,7 +67,7 @@ template <int MODE> __device__ __forceinline__ void XC_SYM(gemm_xd_body)(const B
     const int grow = grow_next;
 #pragma unroll
     for (int r = 0; r < NBR; ++r)
-      cp_async8(Bs + (nn + NROWT * r) * D_LDB + kk, Dm + coloff[r] + grow, kvalid && nvalid[r]);
+      cp_async8(Bs + (nn + NROWT * r) * D_LDB + kk, Dsp[(NROWT * r) >> 5] + coloff[r] + grow, kvalid && nvalid[r]);
   };
   auto fetch_row = [&](int kc) { grow_next = (kc * GK + kk < nb) ? __ldg(gidx + kc * GK + kk) : 0; };
 
@@ -183,13 +191,14 @@ template <int MODE> __device__ __forceinline__ void XC_SYM(gemm_xd_body)(const B
   __syncthreads();
   const int p = tid & (TILE_P - 1), half = tid >> 7;
   const double *Xr = smem + (half * 32) * X_LD + p;
-  double *accp = P.acc + (static_cast<size_t>(it.tile) * P.nspin + it.spin) * NACC * TILE_P;
-  const double *phib = P.scratch + t.scr_off + static_cast<size_t>(n0 + half * 32) * TILE_P + p;
+  const int cb = both ? n0 : n0 + half * 32; // first basis function of this half's 32 X columns
+  double *accp = P.acc + (static_cast<size_t>(it.tile) * P.nspin + (both ? half : it.spin)) * NACC * TILE_P;
+  const double *phib = P.scratch + t.scr_off + static_cast<size_t>(cb) * TILE_P + p;
   double *part = smem + GN * X_LD; // [4][128] partial sums of the upper half
   if (P.debug & 2) return;
   // columns of this half that exist (in groups of 8; the slabs are zero-padded to nbp, the X columns beyond nb are zero):
   // for local bases of 100-250 functions the last 64-column block is mostly padding, and its slab loads are skipped
-  const int jv = min(32, max(0, nb - (n0 + half * 32)));
+  const int jv = min(32, max(0, nb - cb));
   if (it.acomp == 0) {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     if (P.ncomp > 1) {
@@ -210,6 +219,15 @@ template <int MODE> __device__ __forceinline__ void XC_SYM(gemm_xd_body)(const B
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) s0 = fma(phib[(j0 + jj) * TILE_P], Xr[(j0 + jj) * X_LD], s0);
       }
+    }
+    if (both) { // each half holds one spin's sums: no exchange between the halves
+      XC_ACC_ADD(P, accp + p, s0);
+      if (P.ncomp > 1) {
+        XC_ACC_ADD(P, accp + TILE_P + p, s1);
+        XC_ACC_ADD(P, accp + 2 * TILE_P + p, s2);
+        XC_ACC_ADD(P, accp + 3 * TILE_P + p, s3);
+      }
+      return;
     }
     if (half) {
       part[p] = s0;
@@ -232,6 +250,10 @@ template <int MODE> __device__ __forceinline__ void XC_SYM(gemm_xd_body)(const B
     for (int j0 = 0; j0 < jv; j0 += 8) {
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) s0 = fma(q[(j0 + jj) * TILE_P], Xr[(j0 + jj) * X_LD], s0);
+    }
+    if (both) {
+      XC_ACC_ADD(P, accp + 4 * TILE_P + p, s0);
+      return;
     }
     if (half) part[p] = s0;
     __syncthreads();

@@ -554,13 +554,13 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
         for (int sp = 0; sp < nspin; ++sp)
           for (int ac = 0; ac < nac; ++ac)
             for (int jb = 0; jb < njb; ++jb) {
+              if (nspin == 2) continue; // unrestricted: spin-fused density / Vxc items below
               DensItem di;
               di.tile = ti;
               di.jb = static_cast<short>(jb);
               di.spin = static_cast<signed char>(sp);
               di.acomp = static_cast<signed char>(ac);
               dens.push_back(di);
-              if (nspin == 2) continue; // unrestricted: spin-fused Vxc items below
               VxcItem vi;
               vi.tile = ti;
               vi.jb = static_cast<short>(jb);
@@ -575,9 +575,15 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
                 if (cols > 0) h->vxc_executed_flops += 2.0 * t.count * rows * cols;
               }
             }
-        if (nspin == 2) // one item = 32 basis-function columns x both spins (k_vxc_resident, it.spin == 2)
+        if (nspin == 2) // one item = 32 basis-function columns x both spins (k_density / k_vxc_resident, it.spin == 2)
           for (int ac = 0; ac < nac; ++ac)
             for (int jb = 0; jb * 32 < t.nb; ++jb) {
+              DensItem di;
+              di.tile = ti;
+              di.jb = static_cast<short>(jb);
+              di.spin = 2;
+              di.acomp = static_cast<signed char>(ac);
+              dens.push_back(di);
               VxcItem vi;
               vi.tile = ti;
               vi.jb = static_cast<short>(jb);
@@ -593,6 +599,24 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
         if (h->mo) {
           // per tile and spin: rho / grad rho in the factorised form when 4 n nb nocc < 2 n nb^2, tau when nocc < nb
           const int npsib = h->noccp / 64;
+          // unrestricted: where BOTH spins take the D form for a term, one spin-fused item per 32 columns serves them
+          bool fused_d[4] = {false, false, false, false};
+          if (nspin == 2 && h->nocc[0] > 0 && h->nocc[1] > 0)
+            for (int ac = 0; ac < nac; ++ac) {
+              const bool d0 = ac == 0 ? t.nb <= 2 * h->nocc[0] : t.nb <= h->nocc[0];
+              const bool d1 = ac == 0 ? t.nb <= 2 * h->nocc[1] : t.nb <= h->nocc[1];
+              fused_d[ac] = d0 && d1;
+              if (!fused_d[ac]) continue;
+              for (int jb = 0; jb * 32 < t.nb; ++jb) {
+                DensItem di;
+                di.tile = ti;
+                di.jb = static_cast<short>(jb);
+                di.spin = 2;
+                di.acomp = static_cast<signed char>(ac);
+                densmo.push_back(di);
+              }
+              h->mo_executed_flops += 2.0 * 2.0 * t.count * t.nb * t.nb;
+            }
           for (int sp = 0; sp < nspin; ++sp) {
             const int no = h->nocc[sp];
             if (no == 0) continue; // empty spin (e.g. the beta spin of a hydrogen atom): its accumulators stay zero
@@ -611,7 +635,7 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
               push(psi, npsib, 0);
               push(xpsi, njb, 0);
               h->mo_executed_flops += 4.0 * n_pts * t.nb * no;
-            } else {
+            } else if (!fused_d[0]) {
               push(densmo, njb, 0);
               h->mo_executed_flops += 2.0 * n_pts * t.nb * t.nb;
             }
@@ -619,7 +643,7 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
               if (t.nb > no) {
                 push(psi, npsib, ac);
                 h->mo_executed_flops += 2.0 * n_pts * t.nb * no;
-              } else {
+              } else if (!fused_d[ac]) {
                 push(densmo, njb, ac);
                 h->mo_executed_flops += 2.0 * n_pts * t.nb * t.nb;
               }
