@@ -578,6 +578,18 @@ template <class T> XC_HD T e_b3lyp(const XV<T> &v) { // libxc hyb_gga_xc_b3lyp: 
   return 0.08 * e_lda_x(v) + 0.72 * e_b88(v) + 0.19 * e_vwn<1>(v) + 0.81 * e_lyp(v);
 }
 
+// The functionals added in round 2 are reached through real calls: inlining them as well into every (family, spin) kernel
+// took the build of this unit from under a minute to five (cicc + ptxas on one giant function per dual-number width).
+#define XC_HD_CALL __host__ __device__ __noinline__
+template <class T> XC_HD_CALL T call_b97(const XV<T> &v) { return e_b97(v); }
+template <class T> XC_HD_CALL T call_pz81(const XV<T> &v) { return e_pz81(v); }
+template <class T> XC_HD_CALL T call_p86(const XV<T> &v) { return e_p86(v); }
+template <class T> XC_HD_CALL T call_pw91_c(const XV<T> &v) { return e_pw91_c(v); }
+// libxc hyb_gga_xc_b3pw91: a0 = 0.20, ax = 0.72, ac = 0.81 over {lda_x, gga_x_b88, lda_c_pw, gga_c_pw91}
+template <class T> XC_HD_CALL T call_b3pw91(const XV<T> &v) {
+  return 0.08 * e_lda_x(v) + 0.72 * e_b88(v) + 0.19 * e_pw92(v, false) + 0.81 * e_pw91_c(v);
+}
+
 template <class T> XC_HD T xc_energy_density(int id, const XV<T> &v) {
   switch (id) {
   case ID_LDA_X: return e_lda_x(v);
@@ -600,12 +612,11 @@ template <class T> XC_HD T xc_energy_density(int id, const XV<T> &v) {
   case ID_HYB_GGA_XC_BHANDH: return 0.5 * e_lda_x(v) + e_lyp(v);
   case ID_HYB_GGA_XC_BHANDHLYP: return 0.5 * e_b88(v) + e_lyp(v);
   case ID_HYB_GGA_XC_WB97X: return e_wb97x(v);
-  case ID_HYB_GGA_XC_B97: return e_b97(v);
-  case ID_LDA_C_PZ: return e_pz81(v);
-  case ID_GGA_C_P86: return e_p86(v);
-  case ID_GGA_C_PW91: return e_pw91_c(v);
-  // libxc hyb_gga_xc_b3pw91: a0 = 0.20, ax = 0.72, ac = 0.81 over {lda_x, gga_x_b88, lda_c_pw, gga_c_pw91}
-  case ID_HYB_GGA_XC_B3PW91: return 0.08 * e_lda_x(v) + 0.72 * e_b88(v) + 0.19 * e_pw92(v, false) + 0.81 * e_pw91_c(v);
+  case ID_HYB_GGA_XC_B97: return call_b97(v);
+  case ID_LDA_C_PZ: return call_pz81(v);
+  case ID_GGA_C_P86: return call_p86(v);
+  case ID_GGA_C_PW91: return call_pw91_c(v);
+  case ID_HYB_GGA_XC_B3PW91: return call_b3pw91(v);
   default: return T(0.0);
   }
 }
