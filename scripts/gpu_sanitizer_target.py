@@ -10,7 +10,7 @@ b = aobasis.AOBasis.load(Z, pos, "def2-svp")
 h = grid.MolecularGrid(b).hierarchy()
 leaves = h.leaves[::8]                      # a thin sample keeps the sanitizer run short
 hs = dft.GridHierarchy(h.sorted_points, h.sorted_weights, leaves)
-for method, nspin in (("b3lyp", 1), ("tpss", 2), ("svwn", 1)):
+for method, nspin in (("b3lyp", 1), ("tpss", 2), ("svwn", 1), ("b97", 2), ("b3pw91", 1), ("bp86", 2)):
     D2 = molecules.synthetic_density(b, nspin)
     d = dft.DFT(method, b, hs, dft.UNRESTRICTED if nspin == 2 else dft.RESTRICTED, gradient=True)
     K = d.build(D2)
@@ -28,6 +28,9 @@ Cs = molecules.synthetic_orbitals(b, 1)
 m = dft.MultiGPUDFT("b3lyp", b, hs, devices=[0, 0], nocc=Cs[0].shape[1])
 print("multi", float(np.abs(m.build(molecules.synthetic_density(b, 1), Cs)).max()))
 m.close()
+m = dft.MultiGPUDFT("pbe", b, hs, dft.UNRESTRICTED, devices=[0, 0], gradient=True)
+print("multi gradient", float(np.abs(m.gradient(molecules.synthetic_density(b, 2))).max()))
+m.close()
 m = dft.MultiGPUDFT("b3lyp", b, hs, devices=[0, 0], deterministic=True)
 print("multi det", float(np.abs(m.build(molecules.synthetic_density(b, 1))).max()))
 m.close()
@@ -40,5 +43,9 @@ for bas in ("def2-svp", "def2-qzvp"):
     print("cosx", bas, float(np.abs(sgx.compute_K(D)).max()),
           float(np.abs(sgx.compute_K_mo(D, molecules.synthetic_orbitals(bs, 1)[0])).max()))
     sgx.close()
+    if bas == "def2-svp":
+        mg = cosx.MultiGPUSemiNumericalExchange(bs, settings=cosx.cosx_grid_settings(1), devices=[0, 0])
+        print("cosx multi", float(np.abs(mg.compute_K(D, molecules.synthetic_orbitals(bs, 1)[0])).max()))
+        mg.close()
 rho = dft.evaluate_density_on_grid(b, molecules.synthetic_density(b, 1), np.random.default_rng(1).uniform(-3, 3, (300, 3)), 2)
 print("rho", float(rho[:, 0].max()))
