@@ -110,7 +110,8 @@ typedef struct occ_xc_handle occ_xc_handle;
  *   func_ids      DensityFunctional::id() of m_method.functionals (nspin == 1) / functionals_polarized (nspin == 2)
  *   nspin         1 Restricted, 2 Unrestricted
  *   density_threshold / screening_threshold   DFT::m_density_threshold / m_xc_screening_threshold (1e-10 both);
- *                 screening_threshold <= 0 keeps every shell in every leaf (OCC_XC_NO_SCREEN analogue)
+ *                 screening_threshold <= 0 — or the reference's environment variable OCC_XC_NO_SCREEN being set (dft.h:274-275) —
+ *                 keeps every shell in every leaf
  * Everything is copied; no pointer is retained. */
 int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xyz, const double *weights,
                   size_t nleaves, const occ_xc_leaf_t *leaves, const double *shell_extents, int nfunc,

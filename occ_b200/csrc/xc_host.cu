@@ -243,7 +243,8 @@ int occ_xc_partition_leaves(const occ_xc_basis_t *basis, size_t nleaves, const o
   if (!basis || !leaves || !leaf_rank) return fail("occ_xc_partition_leaves: null argument");
   if (world_size < 1) return fail("occ_xc_partition_leaves: world_size must be positive");
   const int nsh = basis->nsh, pure = basis->pure ? 1 : 0;
-  const bool screen = screening_threshold > 0.0;
+  // the reference's environment switch for its dense path (dft.h:274-275) is honoured here too
+  const bool screen = screening_threshold > 0.0 && std::getenv("OCC_XC_NO_SCREEN") == nullptr;
   std::vector<double> extents(nsh, 0.0);
   if (screen) {
     if (shell_extents) std::copy(shell_extents, shell_extents + nsh, extents.begin());
@@ -340,7 +341,8 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
     if (leaves_in[l].offset + leaves_in[l].count > npts) return fail("occ_xc_create: leaf exceeds the point array");
 
   // ---- shell extents (dft.h:293-294) ----
-  const bool screen = screening_threshold > 0.0;
+  // the reference's environment switch for its dense path (dft.h:274-275) is honoured here too
+  const bool screen = screening_threshold > 0.0 && std::getenv("OCC_XC_NO_SCREEN") == nullptr;
   std::vector<double> extents(nsh, 0.0);
   if (screen) {
     if (shell_extents) std::copy(shell_extents, shell_extents + nsh, extents.begin());

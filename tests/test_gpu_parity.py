@@ -178,6 +178,12 @@ def test_edge_cases(case, oracle):
     res, ref = _build_both(c, "pbe", 1, oracle, xc_screening_threshold=0.0)
     _assert_parity(res, ref)
     assert res["info"]["nb_min"] == b.nbf
+    os.environ["OCC_XC_NO_SCREEN"] = "1"       # the reference's environment switch (dft.h:274-275) forces the same path
+    try:
+        res_env, _ = _build_both(c, "pbe", 1, oracle)
+    finally:
+        del os.environ["OCC_XC_NO_SCREEN"]
+    assert res_env["info"]["nb_min"] == b.nbf and np.abs(res_env["K"] - res["K"]).max() < 1e-12
     # (2) screened == dense to 1e-8 (the reference's own check, tests/dft_tests.cpp:904-931)
     res_s, _ = _build_both(c, "pbe", 1, oracle)
     assert np.abs(res_s["K"] - res["K"]).max() < 1e-8
