@@ -495,6 +495,11 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
   h->h_tile_psi_off.assign(std::max(h->ntiles, 1), 0);
   // ---- batches of consecutive leaves under the workspace budget; per-phase work lists ----
   std::vector<CollocItem> colloc;
+  // factorised density where nb > xo * nocc (rho / grad rho; flop break-even 2.0) and nb > xo/2 * nocc (tau; break-even 1.0)
+  const char *xo_env = std::getenv("OCC_XC_MO_CROSSOVER"); // experiment switch
+  const double mo_xo = xo_env ? std::atof(xo_env) : 2.0;
+  auto mo_rho = [&](int nb, int no) { return static_cast<double>(nb) > mo_xo * no; };
+  auto mo_tau = [&](int nb, int no) { return static_cast<double>(nb) > 0.5 * mo_xo * no; };
   std::vector<DensItem> dens, gitems, gradit, densmo, psi, xpsi, gpsi_w[5], gx_w[5], gradd;
   std::vector<VxcItem> vxc;
   size_t max_scratch = 0;
@@ -605,8 +610,8 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
           bool fused_d[4] = {false, false, false, false};
           if (nspin == 2 && h->nocc[0] > 0 && h->nocc[1] > 0)
             for (int ac = 0; ac < nac; ++ac) {
-              const bool d0 = ac == 0 ? t.nb <= 2 * h->nocc[0] : t.nb <= h->nocc[0];
-              const bool d1 = ac == 0 ? t.nb <= 2 * h->nocc[1] : t.nb <= h->nocc[1];
+              const bool d0 = ac == 0 ? !mo_rho(t.nb, h->nocc[0]) : !mo_tau(t.nb, h->nocc[0]);
+              const bool d1 = ac == 0 ? !mo_rho(t.nb, h->nocc[1]) : !mo_tau(t.nb, h->nocc[1]);
               fused_d[ac] = d0 && d1;
               if (!fused_d[ac]) continue;
               for (int jb = 0; jb * 32 < t.nb; ++jb) {
@@ -633,7 +638,7 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
               }
             };
             const double n_pts = t.count;
-            if (t.nb > 2 * no) {
+            if (mo_rho(t.nb, no)) {
               push(psi, npsib, 0);
               push(xpsi, njb, 0);
               h->mo_executed_flops += 4.0 * n_pts * t.nb * no;
@@ -642,7 +647,7 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
               h->mo_executed_flops += 2.0 * n_pts * t.nb * t.nb;
             }
             for (int ac = 1; ac < nac; ++ac) {
-              if (t.nb > no) {
+              if (mo_tau(t.nb, no)) {
                 push(psi, npsib, ac);
                 h->mo_executed_flops += 2.0 * n_pts * t.nb * no;
               } else if (!fused_d[ac]) {
@@ -664,11 +669,11 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
                 gi.spin = static_cast<signed char>(sp);
                 gi.acomp = static_cast<signed char>(wh);
                 gradit.push_back(gi);
-                if (h->mo && h->nocc[sp] > 0 && t.nb <= 2 * h->nocc[sp]) gradd.push_back(gi);
+                if (h->mo && h->nocc[sp] > 0 && !mo_rho(t.nb, h->nocc[sp])) gradd.push_back(gi);
               }
           if (h->mo)
             for (int sp = 0; sp < nspin; ++sp) {
-              if (h->nocc[sp] == 0 || t.nb <= 2 * h->nocc[sp]) continue; // an empty spin has D_s = 0: no gradient term
+              if (h->nocc[sp] == 0 || !mo_rho(t.nb, h->nocc[sp])) continue; // an empty spin has D_s = 0: no gradient term
               for (int wh = w0; wh <= w1; ++wh) {
                 DensItem gi;
                 gi.tile = ti;
