@@ -263,7 +263,7 @@ int occ_cosx_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_
       const int p = swap_roles ? q0 : p0, q = swap_roles ? p0 : q0;
       const int la = basis->l[p], lb = basis->l[q], L1 = la + lb + 1, ne = (la + 1) * (lb + 1) * L1;
       const double *A = basis->origin + 3 * p, *Bc = basis->origin + 3 * q;
-      const int cls = la * (COSX_MAX_L + 1) + lb, stride = COSX_PRIM_HDR + 3 * ne;
+      const int cls = la * (COSX_MAX_L + 1) + lb, stride = cosx_stride(la, lb);
       const int nca = ncart(la), ncb = ncart(lb);
       const double sph_fac = (la == 0 ? 0.282094791773878143 : (la == 1 ? 0.488602511902919921 : 1.0)) *
                              (lb == 0 ? 0.282094791773878143 : (lb == 1 ? 0.488602511902919921 : 1.0)); // kernels.h:11-18
@@ -308,10 +308,23 @@ int occ_cosx_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_
           rec_all[o + 2] = P[1];
           rec_all[o + 3] = P[2];
           rec_all[o + 4] = pref;
-          for (int i = 0; i < ne; ++i) {
-            rec_all[o + COSX_PRIM_HDR + i] = pref * Ex[i];
-            rec_all[o + COSX_PRIM_HDR + ne + i] = Ey[i];
-            rec_all[o + COSX_PRIM_HDR + 2 * ne + i] = Ez[i];
+          if (la == 0 && lb == 0) { // pre-combined: V = [4] R_000
+            rec_all[o + 4] = pref * Ex[0] * Ey[0] * Ez[0];
+          } else if (la == 1 && lb == 0) { // pre-combined: V_a = cA_a R_000 + cB_a R_(1 in a); E^d[(i * 1 + 0) * 2 + t], i = 0, 1
+            const double *E[3] = {Ex.data(), Ey.data(), Ez.data()};
+            for (int a = 0; a < 3; ++a) {
+              double other = 1.0;
+              for (int d = 0; d < 3; ++d)
+                if (d != a) other *= E[d][0];
+              rec_all[o + COSX_PRIM_HDR + a] = pref * E[a][2] * other;     // t = 0 of (i = 1, j = 0)
+              rec_all[o + COSX_PRIM_HDR + 3 + a] = pref * E[a][3] * other; // t = 1
+            }
+          } else {
+            for (int i = 0; i < ne; ++i) {
+              rec_all[o + COSX_PRIM_HDR + i] = pref * Ex[i];
+              rec_all[o + COSX_PRIM_HDR + ne + i] = Ey[i];
+              rec_all[o + COSX_PRIM_HDR + 2 * ne + i] = Ez[i];
+            }
           }
         }
       // block in the basis' own (Cartesian or spherical) functions

@@ -24,6 +24,15 @@ struct CosxPair {
 // primitive pool record of a class (la, lb), ne = (la+1)(lb+1)(la+lb+1):
 //   [0] p  [1..3] P  [4] unused  [5 .. 5+ne) prefactor * E^x  [5+ne ..) E^y  [5+2ne ..) E^z      (ecoeffs.h layout)
 constexpr int COSX_PRIM_HDR = 5;
+// doubles per primitive record of class (la >= lb).  The s-s and p-s classes carry PRE-COMBINED coefficients instead of the
+// three 1D tables (the products E^x E^y E^z are the same for all 128 points of a batch):
+//   (0,0): [4] = prefactor E^x_000 E^y_000 E^z_000                                   -> V = [4] R_000
+//   (1,0): [5..7] = cA_a, [8..10] = cB_a (a = x, y, z of the p shell)                 -> V_a = cA_a R_000 + cB_a R_(1 in a)
+//          cA_a = prefactor E^a_{1,0;0} prod_{d != a} E^d_{0,0;0},  cB_a = the same with E^a_{1,0;1}
+__host__ __device__ constexpr int cosx_stride(int la, int lb) {
+  return (la == 0 && lb == 0) ? COSX_PRIM_HDR : ((la == 1 && lb == 0) ? COSX_PRIM_HDR + 6
+                                                                     : COSX_PRIM_HDR + 3 * (la + 1) * (lb + 1) * (la + lb + 1));
+}
 constexpr int COSX_BOYS_ORDERS = 16;
 constexpr int COSX_BOYS_EXP_OFFSET = COSX_BOYS_ORDERS * 253 * 8; // behind the Boys rows: exp(-(segment + 1/2) / 7), 253 values
 constexpr int COSX_BOYS_SEGMENTS = 253; // rows per order of the device Boys table (boys.h: 252 segments on [0, 36) + 1)

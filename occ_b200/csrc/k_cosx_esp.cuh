@@ -378,6 +378,37 @@ __device__ __forceinline__ void prim_sliced(const double *__restrict__ Ex, const
   }
 }
 
+// one primitive pair of class (LA, LB): Hermite integrals from the seeds S, contraction with the E coefficients of the
+// record, F . V into the two G rows.  s-s and p-s use the pre-combined coefficients of the record (cosx_stride).
+template <int LA, int LB>
+__device__ __forceinline__ void prim_eval(const double *__restrict__ rec, const double (&S)[LA + LB + 1], double x, double y,
+                                          double z, const double (&Fp)[cx_ncart(LA)], const double (&Fq)[cx_ncart(LB)],
+                                          double (&Gp)[cx_ncart(LA)], double (&Gq)[cx_ncart(LB)], bool offdiag) {
+  constexpr int L = LA + LB, NE = (LA + 1) * (LB + 1) * (L + 1);
+  if constexpr (L == 0) {
+    const double V = rec[4] * S[0];
+    Gq[0] += Fp[0] * V;
+    if (offdiag) Gp[0] += Fq[0] * V;
+  } else if constexpr (LA == 1 && LB == 0) {
+    const double r[3] = {x * S[1], y * S[1], z * S[1]}; // R_100, R_010, R_001 (rints.h:183-219 with L = 1)
+    double gq = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double V = fma(rec[COSX_PRIM_HDR + 3 + a], r[a], rec[COSX_PRIM_HDR + a] * S[0]);
+      gq = fma(Fp[a], V, gq);
+      if (offdiag) Gp[a] = fma(Fq[0], V, Gp[a]);
+    }
+    Gq[0] += gq;
+  } else if constexpr (L >= 4) {
+    prim_sliced<LA, LB>(rec + COSX_PRIM_HDR, rec + COSX_PRIM_HDR + NE, rec + COSX_PRIM_HDR + 2 * NE, S, x, y, z, Fp, Fq, Gp, Gq,
+                        offdiag);
+  } else {
+    double R[cx_nhermsum(L)];
+    hermite_R<L>(S, x, y, z, R);
+    contract<LA, LB>(rec + COSX_PRIM_HDR, rec + COSX_PRIM_HDR + NE, rec + COSX_PRIM_HDR + 2 * NE, R, Fp, Fq, Gp, Gq, offdiag);
+  }
+}
+
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
   const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
@@ -471,7 +502,7 @@ struct PairLite {
 template <int LA, int LB>
 __global__ void __launch_bounds__(TILE_P, cosx_min_ctas(LA, LB)) k_cosx_esp(CosxParams P, int pair0, int npairs, int chunk, int cls, int ntiles,
                                                      int nruns) {
-  constexpr int L = LA + LB, NE = (LA + 1) * (LB + 1) * (L + 1), STRIDE = COSX_PRIM_HDR + 3 * NE;
+  constexpr int L = LA + LB, NE = (LA + 1) * (LB + 1) * (L + 1), STRIDE = cosx_stride(LA, LB);
   constexpr int NCA = cx_ncart(LA), NCB = cx_ncart(LB), NH = cx_nhermsum(L);
 #ifndef COSX_GROUPED
 #define COSX_GROUPED 1
@@ -615,10 +646,7 @@ __global__ void __launch_bounds__(TILE_P, cosx_min_ctas(LA, LB)) k_cosx_esp(Cosx
               const double sc = w2 / (pe + w2);
               add_seeds<L>(P.boys, pe * sc, r2, P.w_lr * sqrt(sc), S);
             }
-            double R[NH];
-            hermite_R<L>(S, PCx, PCy, PCz, R);
-            contract<LA, LB>(rec + COSX_PRIM_HDR, rec + COSX_PRIM_HDR + NE, rec + COSX_PRIM_HDR + 2 * NE, R, Fp, Fq, Gp, Gq,
-                             offdiag);
+            prim_eval<LA, LB>(rec, S, PCx, PCy, PCz, Fp, Fq, Gp, Gq, offdiag);
           }
           used += ns;
           i0 += ns;
@@ -708,15 +736,7 @@ __global__ void __launch_bounds__(TILE_P, cosx_min_ctas(LA, LB)) k_cosx_esp(Cosx
           const double sc = w2 / (pe + w2);
           add_seeds<L>(P.boys, pe * sc, r2, P.w_lr * sqrt(sc), S);
         }
-        if constexpr (L >= 4) {
-          prim_sliced<LA, LB>(rec + COSX_PRIM_HDR, rec + COSX_PRIM_HDR + NE, rec + COSX_PRIM_HDR + 2 * NE, S, PCx, PCy, PCz,
-                              Fp, Fq, Gp, Gq, offdiag);
-        } else {
-          double R[NH];
-          hermite_R<L>(S, PCx, PCy, PCz, R);
-          contract<LA, LB>(rec + COSX_PRIM_HDR, rec + COSX_PRIM_HDR + NE, rec + COSX_PRIM_HDR + 2 * NE, R, Fp, Fq, Gp,
-                           Gq, offdiag);
-        }
+        prim_eval<LA, LB>(rec, S, PCx, PCy, PCz, Fp, Fq, Gp, Gq, offdiag);
       }
       i0 += STAGE;
       if (i0 >= pr.nprim) {
@@ -741,7 +761,7 @@ __global__ void __launch_bounds__(TILE_P, cosx_min_ctas(LA, LB)) k_cosx_esp(Cosx
 template <int LA, int LB>
 __global__ void __launch_bounds__(TILE_P, cosx_min_ctas(LA, LB)) k_cosx_esp_w(CosxParams P, int pair0, int npairs, int chunk, int cls,
                                                                                int ntiles, int nruns) {
-  constexpr int L = LA + LB, NE = (LA + 1) * (LB + 1) * (L + 1), STRIDE = COSX_PRIM_HDR + 3 * NE;
+  constexpr int L = LA + LB, NE = (LA + 1) * (LB + 1) * (L + 1), STRIDE = cosx_stride(LA, LB);
   constexpr int NCA = cx_ncart(LA), NCB = cx_ncart(LB), NH = cx_nhermsum(L);
   __shared__ PairLite s_pairs[TILE_P];
   __shared__ int s_wcnt[TILE_P / 32];
@@ -854,15 +874,7 @@ __global__ void __launch_bounds__(TILE_P, cosx_min_ctas(LA, LB)) k_cosx_esp_w(Co
           const double sc = w2 / (pe + w2);
           add_seeds<L>(P.boys, pe * sc, r2, P.w_lr * sqrt(sc), S);
         }
-        if constexpr (L >= 4) {
-          prim_sliced<LA, LB>(rec + COSX_PRIM_HDR, rec + COSX_PRIM_HDR + NE, rec + COSX_PRIM_HDR + 2 * NE, S, PCx, PCy, PCz,
-                              Fp, Fq, Gp, Gq, offdiag);
-        } else {
-          double R[NH];
-          hermite_R<L>(S, PCx, PCy, PCz, R);
-          contract<LA, LB>(rec + COSX_PRIM_HDR, rec + COSX_PRIM_HDR + NE, rec + COSX_PRIM_HDR + 2 * NE, R, Fp, Fq, Gp, Gq,
-                           offdiag);
-        }
+        prim_eval<LA, LB>(rec, S, PCx, PCy, PCz, Fp, Fq, Gp, Gq, offdiag);
       }
       if (!(P.debug & 1)) flush_G<LB>(Gq, Gcol, pr.bfq, pure, P.c2s);
     }
