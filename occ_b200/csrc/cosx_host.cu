@@ -319,6 +319,21 @@ int occ_cosx_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_
               rec_all[o + COSX_PRIM_HDR + a] = pref * E[a][2] * other;     // t = 0 of (i = 1, j = 0)
               rec_all[o + COSX_PRIM_HDR + 3 + a] = pref * E[a][3] * other; // t = 1
             }
+          } else if (la + lb == 2) { // dense pre-combined products, loop order of prim_eval / cosx_dense_count
+            size_t k = o + COSX_PRIM_HDR;
+            for (int ax = la; ax >= 0; --ax)
+              for (int ay = la - ax; ay >= 0; --ay) {
+                const int az = la - ax - ay;
+                for (int bx = lb; bx >= 0; --bx)
+                  for (int by = lb - bx; by >= 0; --by) {
+                    const int bz = lb - bx - by;
+                    for (int t = 0; t <= ax + bx; ++t)
+                      for (int u = 0; u <= ay + by; ++u)
+                        for (int v = 0; v <= az + bz; ++v)
+                          rec_all[k++] = pref * Ex[(ax * (lb + 1) + bx) * L1 + t] * Ey[(ay * (lb + 1) + by) * L1 + u] *
+                                         Ez[(az * (lb + 1) + bz) * L1 + v];
+                  }
+              }
           } else {
             for (int i = 0; i < ne; ++i) {
               rec_all[o + COSX_PRIM_HDR + i] = pref * Ex[i];

@@ -399,6 +399,43 @@ __device__ __forceinline__ void prim_eval(const double *__restrict__ rec, const 
       if (offdiag) Gp[a] = fma(Fq[0], V, Gp[a]);
     }
     Gq[0] += gq;
+  } else if constexpr (L == 2) { // (1,1), (2,0): dense pre-combined coefficients, every index a compile-time constant
+    double R[cx_nhermsum(2)];
+    hermite_R<2>(S, x, y, z, R);
+    const double *c = rec + COSX_PRIM_HDR;
+    int k = 0;
+#pragma unroll
+    for (int ax = LA; ax >= 0; --ax) {
+#pragma unroll
+      for (int ay = LA; ay >= 0; --ay) {
+        if (ay <= LA - ax) {
+          const int az = LA - ax - ay;
+          const int ia = (LA - ax) * (LA - ax + 1) / 2 + (LA - ax - ay);
+          double gp = 0.0;
+#pragma unroll
+          for (int bx = LB; bx >= 0; --bx) {
+#pragma unroll
+            for (int by = LB; by >= 0; --by) {
+              if (by <= LB - bx) {
+                const int bz = LB - bx - by;
+                const int jb = (LB - bx) * (LB - bx + 1) / 2 + (LB - bx - by);
+                double V = 0.0;
+#pragma unroll
+                for (int t = 0; t <= 2; ++t)
+#pragma unroll
+                  for (int u = 0; u <= 2; ++u)
+#pragma unroll
+                    for (int v = 0; v <= 2; ++v)
+                      if (t <= ax + bx && u <= ay + by && v <= az + bz) V = fma(c[k++], R[cx_hidx(t, u, v)], V);
+                Gq[jb] = fma(Fp[ia], V, Gq[jb]);
+                gp = fma(Fq[jb], V, gp);
+              }
+            }
+          }
+          if (offdiag) Gp[ia] += gp;
+        }
+      }
+    }
   } else if constexpr (L >= 4) {
     prim_sliced<LA, LB>(rec + COSX_PRIM_HDR, rec + COSX_PRIM_HDR + NE, rec + COSX_PRIM_HDR + 2 * NE, S, x, y, z, Fp, Fq, Gp, Gq,
                         offdiag);
