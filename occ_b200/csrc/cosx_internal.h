@@ -29,6 +29,9 @@ constexpr int COSX_PRIM_HDR = 5;
 //   (0,0): [4] = prefactor E^x_000 E^y_000 E^z_000                                   -> V = [4] R_000
 //   (1,0): [5..7] = cA_a, [8..10] = cB_a (a = x, y, z of the p shell)                 -> V_a = cA_a R_000 + cB_a R_(1 in a)
 //          cA_a = prefactor E^a_{1,0;0} prod_{d != a} E^d_{0,0;0},  cB_a = the same with E^a_{1,0;1}
+#ifndef COSX_DENSE_MAXL
+#define COSX_DENSE_MAXL 2
+#endif
 // number of (a, b, t, u, v) products of a class in the dense pre-combined form: sum over Cartesian components of
 // (ax + bx + 1)(ay + by + 1)(az + bz + 1); component order lx descending, then ly (kernels.h:256-290)
 __host__ __device__ constexpr int cosx_dense_count(int la, int lb) {
@@ -40,12 +43,12 @@ __host__ __device__ constexpr int cosx_dense_count(int la, int lb) {
           n += (ax + bx + 1) * (ay + by + 1) * ((la - ax - ay) + (lb - bx - by) + 1);
   return n;
 }
-//   L = 2, i.e. (1,1) and (2,0): [5 ..) = prefactor E^x_t E^y_u E^z_v for every (a, b) and every (t, u, v) it reaches, in the
+//   2 <= L <= COSX_DENSE_MAXL, i.e. (1,1), (2,0) (and (2,1), (3,0)): [5 ..) = prefactor E^x_t E^y_u E^z_v for every (a, b) and every (t, u, v) it reaches, in the
 //          loop order of cosx_dense_count / prim_eval                                  -> V_ab = sum c_k R_tuv
 __host__ __device__ constexpr int cosx_stride(int la, int lb) {
   return (la == 0 && lb == 0) ? COSX_PRIM_HDR
          : (la == 1 && lb == 0) ? COSX_PRIM_HDR + 6
-         : (la + lb == 2)       ? COSX_PRIM_HDR + cosx_dense_count(la, lb)
+         : (la + lb >= 2 && la + lb <= COSX_DENSE_MAXL) ? COSX_PRIM_HDR + cosx_dense_count(la, lb)
                                 : COSX_PRIM_HDR + 3 * (la + 1) * (lb + 1) * (la + lb + 1);
 }
 constexpr int COSX_BOYS_ORDERS = 16;

@@ -399,9 +399,9 @@ __device__ __forceinline__ void prim_eval(const double *__restrict__ rec, const 
       if (offdiag) Gp[a] = fma(Fq[0], V, Gp[a]);
     }
     Gq[0] += gq;
-  } else if constexpr (L == 2) { // (1,1), (2,0): dense pre-combined coefficients, every index a compile-time constant
-    double R[cx_nhermsum(2)];
-    hermite_R<2>(S, x, y, z, R);
+  } else if constexpr (L >= 2 && L <= COSX_DENSE_MAXL) { // dense pre-combined coefficients, every index a compile-time constant
+    double R[cx_nhermsum(L)];
+    hermite_R<L>(S, x, y, z, R);
     const double *c = rec + COSX_PRIM_HDR;
     int k = 0;
 #pragma unroll
@@ -421,11 +421,11 @@ __device__ __forceinline__ void prim_eval(const double *__restrict__ rec, const 
                 const int jb = (LB - bx) * (LB - bx + 1) / 2 + (LB - bx - by);
                 double V = 0.0;
 #pragma unroll
-                for (int t = 0; t <= 2; ++t)
+                for (int t = 0; t <= L; ++t)
 #pragma unroll
-                  for (int u = 0; u <= 2; ++u)
+                  for (int u = 0; u <= L; ++u)
 #pragma unroll
-                    for (int v = 0; v <= 2; ++v)
+                    for (int v = 0; v <= L; ++v)
                       if (t <= ax + bx && u <= ay + by && v <= az + bz) V = fma(c[k++], R[cx_hidx(t, u, v)], V);
                 Gq[jb] = fma(Fp[ia], V, Gq[jb]);
                 gp = fma(Fq[jb], V, gp);
