@@ -67,7 +67,15 @@ enum {
   OCC_XC_HYB_GGA_XC_BHANDH = 435,
   OCC_XC_HYB_GGA_XC_BHANDHLYP = 436,
   OCC_XC_HYB_GGA_XC_B3LYP5 = 475,
-  OCC_XC_HYB_GGA_XC_WB97X = 464 /* range separated: occ_xc_range_separation gives omega / alpha / beta */
+  OCC_XC_HYB_GGA_XC_WB97X = 464, /* range separated: occ_xc_range_separation gives omega / alpha / beta */
+  OCC_XC_HYB_GGA_XC_WB97X_V = 466, /* range separated; its VV10 part (b 6.0, C 0.01) is occ_xc_vv10 / occ_xc_vv10_gradient */
+  OCC_XC_HYB_GGA_XC_B97 = 407,
+  OCC_XC_HYB_GGA_XC_B3PW91 = 401,
+  OCC_XC_HYB_GGA_XC_B3P86 = 403,
+  OCC_XC_GGA_X_B86_MGC = 105,
+  OCC_XC_GGA_C_PW91 = 134,
+  OCC_XC_GGA_C_P86 = 132,
+  OCC_XC_LDA_C_PZ = 9
 };
 
 /* Options of a handle (ABI version 2: named fields; version 1 carried them in an anonymous int array).

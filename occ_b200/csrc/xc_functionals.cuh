@@ -5,6 +5,7 @@
 //   lda_x(1) lda_c_vwn(7) lda_c_vwn_rpa(8) lda_c_vwn_3(30) gga_x_pbe(101) gga_x_b88(106) gga_c_pbe(130)
 //   gga_c_lyp(131) hyb_gga_xc_b3lyp(402) mgga_x_r2scan(497) mgga_c_r2scan(498) mgga_x_tpss(202) mgga_c_tpss(231)
 //   hyb_gga_xc_b3lyp5(475) hyb_gga_xc_pbeh(406) hyb_gga_xc_bhandh(435) hyb_gga_xc_bhandhlyp(436) lda_c_pw(12)
+//   hyb_gga_xc_wb97x_v(466) hyb_gga_xc_b3p86(403) gga_x_b86_mgc(105)
 //   lda_c_pw_mod(13) hyb_gga_xc_wb97x(464) hyb_gga_xc_b97(407) hyb_gga_xc_b3pw91(401) gga_c_pw91(134) gga_c_p86(132)
 //   lda_c_pz(9)
 // libxc conventions: exc = energy per particle; vrho = d(rho*exc)/d rho_s; vsigma = d(rho*exc)/d sigma with
@@ -22,15 +23,18 @@ enum : int {
   ID_MGGA_X_R2SCAN = 497, ID_MGGA_C_R2SCAN = 498, ID_LDA_C_PW = 12, ID_LDA_C_PW_MOD = 13, ID_MGGA_X_TPSS = 202,
   ID_MGGA_C_TPSS = 231, ID_HYB_GGA_XC_PBEH = 406, ID_HYB_GGA_XC_BHANDH = 435, ID_HYB_GGA_XC_BHANDHLYP = 436,
   ID_HYB_GGA_XC_B3LYP5 = 475, ID_HYB_GGA_XC_WB97X = 464, ID_HYB_GGA_XC_B97 = 407, ID_HYB_GGA_XC_B3PW91 = 401,
-  ID_GGA_C_PW91 = 134, ID_GGA_C_P86 = 132, ID_LDA_C_PZ = 9
+  ID_GGA_C_PW91 = 134, ID_GGA_C_P86 = 132, ID_LDA_C_PZ = 9, ID_HYB_GGA_XC_WB97X_V = 466, ID_HYB_GGA_XC_B3P86 = 403,
+  ID_GGA_X_B86_MGC = 105
 };
 
 XC_HD double xc_exx_of(int id) { // xc_hyb_exx_coef (include/occ/dft/functional.h:557-579)
   switch (id) {
-  case ID_HYB_GGA_XC_B3LYP: case ID_HYB_GGA_XC_B3LYP5: case ID_HYB_GGA_XC_B3PW91: return 0.20;
+  case ID_HYB_GGA_XC_B3LYP: case ID_HYB_GGA_XC_B3LYP5: case ID_HYB_GGA_XC_B3PW91: case ID_HYB_GGA_XC_B3P86:
+    return 0.20;
   case ID_HYB_GGA_XC_B97: return 0.1943; // Becke, J. Chem. Phys. 107, 8554 (1997)
   case ID_HYB_GGA_XC_PBEH: return 0.25;
   case ID_HYB_GGA_XC_BHANDH: case ID_HYB_GGA_XC_BHANDHLYP: return 0.50;
+  case ID_HYB_GGA_XC_WB97X_V:
   case ID_HYB_GGA_XC_WB97X: return 1.0; // cam_alpha: libxc's xc_hyb_exx_coef returns the full-range fraction
   default: return 0.0;
   }
@@ -46,6 +50,11 @@ XC_HD void xc_cam_of(int id, double *omega, double *alpha, double *beta) {
     *alpha = 1.0;
     *beta = -(1.0 - 0.157706);
   }
+  if (id == ID_HYB_GGA_XC_WB97X_V) {
+    *omega = 0.3;
+    *alpha = 1.0;
+    *beta = -(1.0 - 0.167);
+  }
 }
 
 XC_HD int xc_family_of(int id) {
@@ -55,7 +64,7 @@ XC_HD int xc_family_of(int id) {
   case ID_HYB_GGA_XC_B97: case ID_HYB_GGA_XC_B3PW91: case ID_GGA_C_PW91: case ID_GGA_C_P86:
   case ID_GGA_X_PBE: case ID_GGA_X_B88: case ID_GGA_C_PBE: case ID_GGA_C_LYP: case ID_HYB_GGA_XC_B3LYP:
   case ID_HYB_GGA_XC_B3LYP5: case ID_HYB_GGA_XC_PBEH: case ID_HYB_GGA_XC_BHANDH: case ID_HYB_GGA_XC_BHANDHLYP:
-  case ID_HYB_GGA_XC_WB97X: return 1;
+  case ID_HYB_GGA_XC_WB97X: case ID_HYB_GGA_XC_WB97X_V: case ID_HYB_GGA_XC_B3P86: case ID_GGA_X_B86_MGC: return 1;
   case ID_MGGA_X_R2SCAN: case ID_MGGA_C_R2SCAN: case ID_MGGA_X_TPSS: case ID_MGGA_C_TPSS: return 2;
   default: return -1;
   }
@@ -157,6 +166,13 @@ template <class T> XC_HD T b88_spin(const T &r, const T &s) {
   return -(r43 * (XC_B88_CX + beta * (x * x) / (1.0 + gam * beta * x * asinh(x))));
 }
 template <class T> XC_HD T e_b88(const XV<T> &v) { return b88_spin(v.ra, v.saa) + b88_spin(v.rb, v.sbb); }
+// Becke 1986 "B86b" exchange (J. Chem. Phys. 85, 7184; libxc gga_x_b86_mgc = 105): beta = 0.00375, gamma = 0.007, power 4/5
+template <class T> XC_HD T b86b_spin(const T &r, const T &s) {
+  const T r43 = r * cbrt(r);
+  const T x2 = s / (r43 * r43);
+  return -(r43 * (XC_B88_CX + 0.00375 * x2 / pow(1.0 + 0.007 * x2, 0.8)));
+}
+template <class T> XC_HD T e_b86b(const XV<T> &v) { return b86b_spin(v.ra, v.saa) + b86b_spin(v.rb, v.sbb); }
 
 // ---------------------------------------------------------------------------------------------
 // Lee-Yang-Parr correlation in the Miehlich-Savin-Stoll-Preuss gradient form
@@ -496,6 +512,21 @@ template <class T> XC_HD T e_wb97x(const XV<T> &v) {
          eab * b97_poly(0.5 * (xa2 + xb2), 0.006, 1.0, 2.37031, -11.3995, 6.58405, -3.78132);
 }
 
+// wB97X-V (Mardirossian & Head-Gordon, PCCP 16, 9904 (2014); libxc hyb_gga_xc_wb97x_v = 466): the wB97X form with seven
+// linear coefficients, omega = 0.3; the VV10 part (b = 6.0, C = 0.01) is occ_xc_vv10.  Golden: isolated_xc_tests.cpp:340-364.
+template <class T> XC_HD T e_wb97x_v(const XV<T> &v) {
+  const double omega = 0.3;
+  const T ra43 = v.ra * cbrt(v.ra), rb43 = v.rb * cbrt(v.rb);
+  const T xa2 = v.saa / (ra43 * ra43), xb2 = v.sbb / (rb43 * rb43);
+  const T kfa = cbrt(2.0 * XC_3PI2 * v.ra), kfb = cbrt(2.0 * XC_3PI2 * v.rb);
+  const T ex = XC_LDAX_C * (ra43 * wb97_attenuation(0.5 * omega / kfa) * b97_poly(xa2, 0.004, 0.833, 0.603, 1.194, 0.0, 0.0) +
+                            rb43 * wb97_attenuation(0.5 * omega / kfb) * b97_poly(xb2, 0.004, 0.833, 0.603, 1.194, 0.0, 0.0));
+  const T eaa = v.ra * pw92_ferro_1992(v.ra), ebb = v.rb * pw92_ferro_1992(v.rb);
+  const T eab = e_pw92(v, false) - eaa - ebb;
+  return ex + eaa * b97_poly(xa2, 0.2, 0.556, -0.257, 0.0, 0.0, 0.0) + ebb * b97_poly(xb2, 0.2, 0.556, -0.257, 0.0, 0.0, 0.0) +
+         eab * b97_poly(0.5 * (xa2 + xb2), 0.006, 1.219, -1.850, 0.0, 0.0, 0.0);
+}
+
 // ---------------------------------------------------------------------------------------------
 // B97 (Becke, J. Chem. Phys. 107, 8554 (1997); libxc hyb_gga_xc_b97 = 407, 19.43 % exact exchange): the same power series
 // as wB97X on the full-range LSDA exchange and the Stoll-partitioned PW92 correlation, three terms each.
@@ -590,8 +621,18 @@ template <class T> XC_HD_CALL T call_b3pw91(const XV<T> &v) {
   return 0.08 * e_lda_x(v) + 0.72 * e_b88(v) + 0.19 * e_pw92(v, false) + 0.81 * e_pw91_c(v);
 }
 
+template <class T> XC_HD_CALL T call_wb97x_v(const XV<T> &v) { return e_wb97x_v(v); }
+template <class T> XC_HD_CALL T call_b86b(const XV<T> &v) { return e_b86b(v); }
+// libxc hyb_gga_xc_b3p86: a0 = 0.20, ax = 0.72, ac = 0.81 over {lda_x, gga_x_b88, lda_c_vwn_rpa, gga_c_p86}
+template <class T> XC_HD_CALL T call_b3p86(const XV<T> &v) {
+  return 0.08 * e_lda_x(v) + 0.72 * e_b88(v) + 0.19 * e_vwn<1>(v) + 0.81 * e_p86(v);
+}
+
 template <class T> XC_HD T xc_energy_density(int id, const XV<T> &v) {
   switch (id) {
+  case ID_HYB_GGA_XC_WB97X_V: return call_wb97x_v(v);
+  case ID_HYB_GGA_XC_B3P86: return call_b3p86(v);
+  case ID_GGA_X_B86_MGC: return call_b86b(v);
   case ID_LDA_X: return e_lda_x(v);
   case ID_LDA_C_VWN: return e_vwn<0>(v);
   case ID_LDA_C_VWN_RPA: return e_vwn<1>(v);

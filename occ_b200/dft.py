@@ -26,7 +26,10 @@ FUNCTIONAL_IDS = {"lda_x": 1, "lda_c_vwn": 7, "lda_c_vwn_rpa": 8, "lda_c_vwn_3":
                   "mgga_x_r2scan": 497, "mgga_c_r2scan": 498, "lda_c_pw": 12, "lda_c_pw_mod": 13, "mgga_x_tpss": 202,
                   "mgga_c_tpss": 231, "hyb_gga_xc_pbeh": 406, "hyb_gga_xc_bhandh": 435, "hyb_gga_xc_bhandhlyp": 436,
                   "hyb_gga_xc_b3lyp5": 475, "hyb_gga_xc_wb97x": 464, "hyb_gga_xc_b97": 407,
-            "hyb_gga_xc_b3pw91": 401, "gga_c_pw91": 134, "gga_c_p86": 132, "lda_c_pz": 9}
+                  "hyb_gga_xc_b3pw91": 401, "gga_c_pw91": 134, "gga_c_p86": 132, "lda_c_pz": 9,
+                  "hyb_gga_xc_wb97x_v": 466, "hyb_gga_xc_b3p86": 403, "gga_x_b86_mgc": 105}
+# DensityFunctional::needs_nlc_correction (src/dft/functional.cpp:66-74): hyb_mgga_xc_wb97m_v (not implemented), hyb_gga_xc_wb97x_v
+NLC_FUNCTIONAL_IDS = (466,)
 
 # src/dft/dft_method.cpp:14-37 (builtin_definitions), restricted to components this library implements
 METHOD_DEFINITIONS = {
@@ -47,6 +50,11 @@ METHOD_DEFINITIONS = {
     "b97": ["hyb_gga_xc_b97"],
     "b3pw91": ["hyb_gga_xc_b3pw91"],
     "bp86": ["gga_x_b88", "gga_c_p86"],
+    # share/methods/dft_methods.json entries beyond the compiled-in table
+    "wb97x-v": ["hyb_gga_xc_wb97x_v"],        # "dispersion": "vv10" -> DFT.post_scf_nlc_correction
+    "b3p86": ["hyb_gga_xc_b3p86"],
+    "b86bpbe": ["gga_x_b86_mgc", "gga_c_pbe"],
+    "b86bpbeh": ["gga_x_b86_mgc", "gga_c_pbe"],   # factor 0.75 / hfx 0.25 carried, never applied (as pbe0 below)
     # the 0.75 component factor of pbe0 / pbe1pbe is stored but never applied by the reference
     # (include/occ/dft/functional.h:506-508), so its XC build evaluates full PBE exchange; same here
     "pbe0": ["gga_x_pbe", "gga_c_pbe"],
@@ -117,6 +125,7 @@ class DFT:
                  nvtx: bool = False, density_scale: float = 0.0, orbital_scale: float = 0.0):
         self.basis = basis
         self.method = method
+        self._device, self._nlc, self.nlc_energy = device, None, 0.0
         self.func_ids = np.array(get_dft_method(method), dtype=np.int32)
         self.nspin = 2 if spinorbital_kind == UNRESTRICTED else 1
         self.nbf = basis.nbf
@@ -237,9 +246,42 @@ class DFT:
                                         C.c_void_p(scalars_dev_ptr), C.c_void_p(stream)))
 
     def compute_xc_gradient(self, D: np.ndarray) -> np.ndarray:
-        """DFT::compute_xc_gradient(mo) without the VV10 term (src/dft/dft_gradients.cpp:68-109); D = mo.D.
+        """DFT::compute_xc_gradient(mo) (src/dft/dft_gradients.cpp:68-109); D = mo.D.  For a functional with a VV10 part
+        (wB97X-V) the NLC gradient is added like the reference does (:104).
         Returns (natoms, 3) — the bytes of the reference's 3 x natoms column-major Mat3N."""
-        return self.gradient(np.asfortranarray(2.0 * np.asarray(D, dtype=np.float64)))
+        g = self.gradient(np.asfortranarray(2.0 * np.asarray(D, dtype=np.float64)))
+        if self.have_nonlocal_correlation():
+            g = g + self.compute_nlc_gradient(D)
+        return g
+
+    # --- VV10 (include/occ/dft/dft.h:44,467-495): post-SCF energy and gradient of the NLC part of wB97X-V ----------------
+    def have_nonlocal_correlation(self) -> bool:
+        return any(int(i) in NLC_FUNCTIONAL_IDS for i in self.func_ids)
+
+    def set_nlc_grid(self, settings=None, gradient: bool = True, devices=None):
+        """DFT::set_nlc_grid (src/dft/dft.cpp:119-121); default {110, 50, 50, 1e-7, no first-row reduction}"""
+        from .nlc import NonLocalCorrelationFunctional
+        if self.nspin != 1:
+            raise RuntimeError("Only restricted NLC functional implemented right now")   # nonlocal_correlation.cpp:370
+        if getattr(self, "_nlc", None) is not None:
+            self._nlc.close()
+        self._nlc = NonLocalCorrelationFunctional()
+        self._nlc.set_integration_grid(self.basis, settings, device=self._device, gradient=gradient, devices=devices)
+        return self._nlc
+
+    def post_scf_nlc_correction(self, D: np.ndarray) -> float:
+        """DFT::post_scf_nlc_correction(mo): the VV10 energy of D = mo.D, 0 for a functional without an NLC part"""
+        if self.have_nonlocal_correlation():
+            nlc = getattr(self, "_nlc", None) or self.set_nlc_grid()
+            self.nlc_energy = nlc(D)[0]
+        return self.nlc_energy
+
+    def compute_nlc_gradient(self, D: np.ndarray) -> np.ndarray:
+        """DFT::compute_nlc_gradient(mo): zeros without an NLC part, else NonLocalCorrelationFunctional::compute_gradient"""
+        if not self.have_nonlocal_correlation():
+            return np.zeros((len(self.basis.atomic_numbers), 3))
+        nlc = getattr(self, "_nlc", None) or self.set_nlc_grid()
+        return nlc.compute_gradient(D)
 
     def gradient(self, D2: np.ndarray) -> np.ndarray:
         n = self.nspin * self.nbf
@@ -279,6 +321,9 @@ class DFT:
         return [o[:count * nb.value].reshape(nb.value, count).T for o in outs]
 
     def close(self):
+        if getattr(self, "_nlc", None) is not None:
+            self._nlc.close()
+            self._nlc = None
         if getattr(self, "_h", None) is not None and self._h.value:
             lib().occ_xc_destroy(self._h)
             self._h = C.c_void_p()

@@ -20,7 +20,8 @@ FUNC_IDS = {"lda_x": 1, "lda_c_vwn": 7, "lda_c_vwn_rpa": 8, "lda_c_vwn_3": 30, "
             "gga_c_pbe": 130, "gga_c_lyp": 131, "hyb_gga_xc_b3lyp": 402, "mgga_x_r2scan": 497, "mgga_c_r2scan": 498,
             "lda_c_pw": 12, "lda_c_pw_mod": 13, "mgga_x_tpss": 202, "mgga_c_tpss": 231, "hyb_gga_xc_pbeh": 406,
             "hyb_gga_xc_bhandh": 435, "hyb_gga_xc_bhandhlyp": 436, "hyb_gga_xc_b3lyp5": 475, "hyb_gga_xc_wb97x": 464, "hyb_gga_xc_b97": 407,
-            "hyb_gga_xc_b3pw91": 401, "gga_c_pw91": 134, "gga_c_p86": 132, "lda_c_pz": 9}
+            "hyb_gga_xc_b3pw91": 401, "gga_c_pw91": 134, "gga_c_p86": 132, "lda_c_pz": 9,
+            "hyb_gga_xc_wb97x_v": 466, "hyb_gga_xc_b3p86": 403, "gga_x_b86_mgc": 105}
 
 # src/dft/dft_method.cpp:14-37 (same entries in share/methods/dft_methods.json)
 METHODS = {
@@ -37,6 +38,9 @@ METHODS = {
     "b97": ["hyb_gga_xc_b97"],
     "b3pw91": ["hyb_gga_xc_b3pw91"],
     "bp86": ["gga_x_b88", "gga_c_p86"],
+    "wb97x-v": ["hyb_gga_xc_wb97x_v"],
+    "b3p86": ["hyb_gga_xc_b3p86"],
+    "b86bpbe": ["gga_x_b86_mgc", "gga_c_pbe"],
     "pbeh": ["hyb_gga_xc_pbeh"],
     "bpbe": ["gga_x_b88", "gga_c_pbe"],
     # pbe0 / pbe1pbe carry a 0.75 component factor that the reference stores but never applies

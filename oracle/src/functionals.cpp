@@ -110,6 +110,16 @@ template <class T> T b88_spin(const T &r, const T &s) {
   return -r43 * (Cx + beta * sq(x) / (1.0 + gamma * beta * x * asinh(x)));
 }
 template <class T> T F_b88(const Vars<T> &v) { return b88_spin(v.ra, v.saa) + b88_spin(v.rb, v.sbb); }
+// Becke, J. Chem. Phys. 85, 7184 (1986) ("B86b", libxc gga_x_b86_mgc, id 105; reference methods b86bpbe / b86bpbeh):
+// E_x = E_x^LSDA - beta sum_s rho_s^(4/3) x_s^2 / (1 + gamma x_s^2)^(4/5), beta = 0.00375, gamma = 0.007.
+// "parity unpinned": the reference holds no number for it; the two constants are the published ones.
+template <class T> T b86b_spin(const T &r, const T &s) {
+  const double Cx = 0.375 * std::cbrt(3.0 / kPi) * std::pow(4.0, 2.0 / 3.0);
+  const T r43 = r * cbrt(r);
+  const T x2 = s / sq(r43);
+  return -r43 * (Cx + 0.00375 * x2 / pow(1.0 + 0.007 * x2, 0.8));
+}
+template <class T> T F_b86b(const Vars<T> &v) { return b86b_spin(v.ra, v.saa) + b86b_spin(v.rb, v.sbb); }
 
 // ------------------------------------------------------------------------------------------------
 // Lee, Yang, Parr, Phys. Rev. B 37, 785 (1988) in the gradient-only form of Miehlich, Savin, Stoll,
@@ -452,6 +462,13 @@ template <class T> T F_b97_family(const B97Set &P, const Vars<T> &v) {
          ec_ab * b97_series(0.006, P.cab, 0.5 * (x2a + x2b));
 }
 template <class T> T F_wb97x(const Vars<T> &v) { return F_b97_family(kWB97X, v); }
+// wB97X-V (Mardirossian & Head-Gordon, Phys. Chem. Chem. Phys. 16, 9904 (2014), Table 3; libxc hyb_gga_xc_wb97x_v, id 466;
+// reference table share/methods/dft_methods.json "wb97x-v", dispersion "vv10" with b = 6.0, C = 0.01): seven linear
+// coefficients on the same three series, omega = 0.3, 16.7 % short-range + 100 % long-range exact exchange
+// (xc_hyb_cam_coef: alpha 1.0, beta -0.833).  Pinned by the reference's golden -6.539400300836
+// (tests/isolated_xc_tests.cpp:340-364: the local part only, the VV10 energy is post-SCF).
+const B97Set kWB97XV = {{0.833, 0.603, 1.194, 0.0, 0.0}, {0.556, -0.257, 0.0, 0.0, 0.0}, {1.219, -1.850, 0.0, 0.0, 0.0}, 0.3};
+template <class T> T F_wb97x_v(const Vars<T> &v) { return F_b97_family(kWB97XV, v); }
 // B97 itself (Becke, J. Chem. Phys. 107, 8554 (1997), Table: c_x, c_ss, c_ab; 19.43 % exact exchange; libxc
 // hyb_gga_xc_b97, id 407; reference table src/dft/dft_method.cpp:18): full-range exchange (omega = 0), three terms.
 // "parity unpinned" beyond the machinery it shares with wB97X (pinned): the nine coefficients are the published ones.
@@ -532,8 +549,16 @@ template <class T> T F_b3pw91(const Vars<T> &v) {
   return 0.08 * F_lda_x(v) + 0.72 * F_b88(v) + 0.19 * F_pw<T, 0>(v) + 0.81 * F_pw91_c(v);
 }
 
+// libxc hyb_gga_xc_b3p86 (id 403): a0 = 0.20, ax = 0.72, ac = 0.81 over {lda_x, gga_x_b88, lda_c_vwn_rpa, gga_c_p86}
+template <class T> T F_b3p86(const Vars<T> &v) {
+  return 0.08 * F_lda_x(v) + 0.72 * F_b88(v) + 0.19 * F_vwn<T, 1>(v) + 0.81 * F_p86(v);
+}
+
 template <class T> bool F_dispatch(int id, const Vars<T> &v, T &out) {
   switch (id) {
+  case ORC_HYB_GGA_XC_WB97X_V: out = F_wb97x_v(v); return true;
+  case ORC_HYB_GGA_XC_B3P86: out = F_b3p86(v); return true;
+  case ORC_GGA_X_B86_MGC: out = F_b86b(v); return true;
   case ORC_HYB_GGA_XC_WB97X: out = F_wb97x(v); return true;
   case ORC_HYB_GGA_XC_B97: out = F_b97(v); return true;
   case ORC_HYB_GGA_XC_B3PW91: out = F_b3pw91(v); return true;
@@ -660,6 +685,9 @@ int orc_xc_family(int id) {
   case ORC_HYB_GGA_XC_BHANDH:
   case ORC_HYB_GGA_XC_BHANDHLYP:
   case ORC_HYB_GGA_XC_WB97X:
+  case ORC_HYB_GGA_XC_WB97X_V:
+  case ORC_HYB_GGA_XC_B3P86:
+  case ORC_GGA_X_B86_MGC:
     return 1;
   case ORC_MGGA_X_R2SCAN:
   case ORC_MGGA_C_R2SCAN:
@@ -676,6 +704,7 @@ double orc_xc_exx(int id) { // xc_hyb_exx_coef (include/occ/dft/functional.h:557
   case ORC_HYB_GGA_XC_B3LYP:
   case ORC_HYB_GGA_XC_B3LYP5:
   case ORC_HYB_GGA_XC_B3PW91:
+  case ORC_HYB_GGA_XC_B3P86:
     return 0.20;
   case ORC_HYB_GGA_XC_B97:
     return 0.1943;
@@ -684,6 +713,7 @@ double orc_xc_exx(int id) { // xc_hyb_exx_coef (include/occ/dft/functional.h:557
   case ORC_HYB_GGA_XC_BHANDH:
   case ORC_HYB_GGA_XC_BHANDHLYP:
     return 0.50;
+  case ORC_HYB_GGA_XC_WB97X_V: // beta = -0.833 at omega = 0.3
   case ORC_HYB_GGA_XC_WB97X:
     return 1.0; // libxc: xc_hyb_exx_coef returns cam_alpha (the full-range fraction); beta = -0.842294 at omega = 0.3
   default:

@@ -170,7 +170,8 @@ def test_single_process_multi_gpu_build_sums_to_the_one_gpu_result(case, oracle,
 
 
 @pytest.mark.parametrize("nspin", [1, 2])
-@pytest.mark.parametrize("method,exx", [("b97", 0.1943), ("b3pw91", 0.20), ("bp86", 0.0)])
+@pytest.mark.parametrize("method,exx", [("b97", 0.1943), ("b3pw91", 0.20), ("bp86", 0.0), ("b3p86", 0.20), ("b86bpbe", 0.0),
+                                        ("wb97x-v", 1.0)])
 def test_b97_b3pw91_bp86_builds(case, oracle, method, exx, nspin):
     """the method-table entries added in round 2 (src/dft/dft_method.cpp:16,18,30): hyb_gga_xc_b97, hyb_gga_xc_b3pw91
     (lda_x + gga_x_b88 + lda_c_pw + gga_c_pw91) and gga_x_b88 + gga_c_p86 (PZ81 local part)"""

@@ -35,9 +35,9 @@ import pytest
 from occ_b200 import aobasis, molecules
 
 GOLD = {"lda": -8.786388687644, "pbe": -9.262866622721, "blyp": -9.325386381715, "r2scan": -9.313583890330,
-        "wb97x": -6.577307030585}
-# margins of the reference's assertions (isolated_xc_tests.cpp:94,138,182,228,274,319)
-REF_MARGIN_DEFAULT = {"lda": 1e-8, "pbe": 1e-8, "blyp": 1e-8, "r2scan": 1e-6, "wb97x": 1e-8}
+        "wb97x": -6.577307030585, "wb97x-v": -6.539400300836}
+# margins of the reference's assertions (isolated_xc_tests.cpp:94,138,182,228,274,319,364)
+REF_MARGIN_DEFAULT = {"lda": 1e-8, "pbe": 1e-8, "blyp": 1e-8, "r2scan": 1e-6, "wb97x": 1e-8, "wb97x-v": 1e-8}
 HERE = os.path.dirname(os.path.abspath(__file__))
 BOHR_PYSCF = 0.52917721092
 BRAGG = {1: 0.35 / BOHR_PYSCF, 8: 0.60 / BOHR_PYSCF}

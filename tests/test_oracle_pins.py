@@ -89,7 +89,8 @@ def test_tpss_known_answers_energies_and_potentials(oracle):
 FUNCS = ["lda_x", "lda_c_vwn", "lda_c_vwn_rpa", "lda_c_vwn_3", "gga_x_pbe", "gga_x_b88", "gga_c_pbe", "gga_c_lyp",
          "hyb_gga_xc_b3lyp", "mgga_x_r2scan", "mgga_c_r2scan", "lda_c_pw", "lda_c_pw_mod", "mgga_x_tpss",
          "mgga_c_tpss", "hyb_gga_xc_b3lyp5", "hyb_gga_xc_pbeh", "hyb_gga_xc_bhandh", "hyb_gga_xc_bhandhlyp",
-         "hyb_gga_xc_b97", "hyb_gga_xc_b3pw91", "gga_c_pw91", "gga_c_p86", "lda_c_pz"]
+         "hyb_gga_xc_b97", "hyb_gga_xc_b3pw91", "gga_c_pw91", "gga_c_p86", "lda_c_pz", "hyb_gga_xc_wb97x",
+         "hyb_gga_xc_wb97x_v", "hyb_gga_xc_b3p86", "gga_x_b86_mgc"]
 
 
 def _sample(n, seed, polarized):
@@ -382,6 +383,28 @@ def test_b97_and_b3pw91_are_their_published_mixtures(oracle):
     for k in ("exc", "vrho", "vsigma"):
         assert np.allclose(mix[k], sum(c * q[k] for c, q in zip((0.08, 0.72, 0.19, 0.81), parts)), rtol=1e-12, atol=1e-14)
     assert oracle.lib().orc_xc_exx(407) == pytest.approx(0.1943) and oracle.lib().orc_xc_exx(401) == pytest.approx(0.20)
+    # libxc hyb_gga_xc_b3p86: the same weights over {lda_x, gga_x_b88, lda_c_vwn_rpa, gga_c_p86}
+    mix = oracle.xc_eval("hyb_gga_xc_b3p86", True, rho, sigma, tau)
+    parts = [oracle.xc_eval(n, True, rho, sigma, tau) for n in ("lda_x", "gga_x_b88", "lda_c_vwn_rpa", "gga_c_p86")]
+    for k in ("exc", "vrho", "vsigma"):
+        assert np.allclose(mix[k], sum(c * q[k] for c, q in zip((0.08, 0.72, 0.19, 0.81), parts)), rtol=1e-12, atol=1e-14)
+    assert oracle.lib().orc_xc_exx(403) == pytest.approx(0.20) and oracle.lib().orc_xc_exx(466) == pytest.approx(1.0)
+
+
+def test_b86b_exchange_limits_and_enhancement_factor(oracle):
+    """gga_x_b86_mgc (Becke 1986b): F(x) = 1 + (beta / C_x) x^2 / (1 + gamma x^2)^(4/5); LSDA exchange at zero gradient,
+    the closed form at finite gradient, and the small-gradient coefficient against B88's (0.0042) ratio"""
+    rho, sigma, tau = _sample(30, 11, True)
+    lda = oracle.xc_eval("lda_x", True, rho, 0 * sigma, tau)["exc"]
+    assert np.allclose(oracle.xc_eval("gga_x_b86_mgc", True, rho, 0 * sigma, tau)["exc"], lda, rtol=1e-14)
+    got = oracle.xc_eval("gga_x_b86_mgc", True, rho, sigma, tau)["exc"] * rho.sum(1)
+    cx = 0.75 * (6.0 / np.pi) ** (1.0 / 3.0)
+    want = 0.0
+    for k, sk in ((0, 0), (1, 2)):
+        r43 = rho[:, k] ** (4.0 / 3.0)
+        x2 = sigma[:, sk] / r43 ** 2
+        want = want - r43 * (cx + 0.00375 * x2 / (1.0 + 0.007 * x2) ** 0.8)
+    assert np.allclose(got, want, rtol=1e-13)
 
 
 @pytest.mark.parametrize("atom", sorted(ATOMS))

@@ -15,7 +15,28 @@ PYSCF = {  # O z, H1 y, H1 z
     "pbe": (-0.3409121608, -0.2022757063, 0.1704560022),
     "blyp": (-0.3356949358, -0.1988199134, 0.1678460822),
     "r2scan": (-0.3636272278, -0.2156250191, 0.1817690714),
+    "wb97x": (-0.2460843462, -0.1496303514, 0.1230730362),     # isolated_xc_tests.cpp:321-335
 }
+# the reference's own margins on the default grid (O z, H1 y, H1 z): isolated_xc_tests.cpp:104-106,148-150,192-194,288-290,333-335
+MARGINS = {"r2scan": (2e-3, 2e-4, 2e-4), "wb97x": (5e-4, 1e-4, 1e-4)}
+# wB97X-V (isolated_xc_tests.cpp:340-385): compute_xc_gradient = local part + VV10 gradient on the NLC grid; the PySCF numbers
+# exclude VV10, the reference asserts 7e-3 / 5e-3 / 4e-3 and symmetry to 1e-5 ("relaxed tolerances for NLC grid")
+WB97XV = ((-0.2414466543, -0.1465413018, 0.1207241947), (7e-3, 5e-3, 4e-3))
+NLC_GRID = dict(max_angular_points=110, min_angular_points=50, radial_precision=1e-7, reduced_first_row_element_grid=False)
+
+
+def _check(m, g):
+    oz, hy, hz = PYSCF[m]
+    t = MARGINS.get(m, (1e-4, 1e-4, 1e-4))
+    assert abs(g[0, 2] - oz) < t[0] and abs(g[1, 1] - hy) < t[1] and abs(g[1, 2] - hz) < t[2], (m, g)
+
+
+def _check_wb97xv(g):
+    (oz, hy, hz), t = WB97XV
+    assert abs(g[0, 2] - oz) < t[0] and abs(g[1, 1] - hy) < t[1] and abs(g[1, 2] - hz) < t[2], g
+    assert np.abs(g[:, 0]).max() < 1e-5 and abs(g[1, 1] + g[2, 1]) < 1e-5
+    # the deviations the reference's margins were cut to ("~0.006 Ha/Bohr for VV10") are reproduced, not just bounded
+    assert 5.5e-3 < g[0, 2] - oz < 6.5e-3 and 4.0e-3 < g[1, 1] - hy < 5.0e-3 and -3.5e-3 < g[1, 2] - hz < -2.6e-3
 
 
 @pytest.mark.parametrize("pure", [0, 1])
@@ -42,13 +63,27 @@ def test_oracle_gradient_against_pyscf_values_quoted_by_the_reference(oracle):
     ob = oracle.Basis(b.as_arrays())
     pts, w, _ = oracle.molecular_grid(Z, pos, ob)
     spts, sw, perm, leaves = oracle.hierarchy(pts, w)
-    for m, (oz, hy, hz) in PYSCF.items():
+    for m in PYSCF:
         g = oracle.xc_gradient(ob, spts, sw, leaves, oracle.METHODS[m], 1, P, 3)
-        tol = 2e-3 if m == "r2scan" else 1e-4          # the reference's own margins (default grid)
-        assert abs(g[0, 2] - oz) < tol and abs(g[1, 1] - hy) < tol and abs(g[1, 2] - hz) < tol, (m, g)
+        _check(m, g)                                      # the reference's own margins (default grid)
         assert np.abs(g[:, 0]).max() < 1e-10 and abs(g[1, 1] + g[2, 1]) < 1e-10       # symmetry checks of the reference
         gu = oracle.xc_gradient(ob, spts, sw, leaves, oracle.METHODS[m], 2, np.asfortranarray(np.vstack([0.5 * P, 0.5 * P])), 3)
         assert np.abs(gu - g).max() < 1e-10               # unrestricted(zeta = 0) == restricted
+
+
+def test_oracle_wb97xv_gradient_meets_the_reference_assertions(oracle):
+    """the one reference-held number for the VV10 gradient (and for occ_xc_vv10_gradient's oracle): wB97X-V on the
+    RHF/3-21G water density, local gradient on the default grid + NLC gradient on the {110, 50, 1e-7} grid"""
+    Z, pos, b, P = _water_rhf()
+    ob = oracle.Basis(b.as_arrays())
+    pts, w, _ = oracle.molecular_grid(Z, pos, ob)
+    spts, sw, perm, leaves = oracle.hierarchy(pts, w)
+    g = oracle.xc_gradient(ob, spts, sw, leaves, oracle.METHODS["wb97x-v"], 1, P, 3)
+    (oz, hy, hz), _ = WB97XV
+    assert abs(g[0, 2] - oz) < 2e-5 and abs(g[1, 1] - hy) < 2e-5 and abs(g[1, 2] - hz) < 2e-5   # local part = PySCF's
+    p2, w2, info = oracle.molecular_grid(Z, pos, ob, oracle.default_grid_settings(**NLC_GRID))
+    r = oracle.vv10_gradient(ob, p2, w2, oracle.cosx_atom_grids(p2, info), P)
+    _check_wb97xv(g + r["gradient"])
 
 
 def test_oracle_gradient_is_the_derivative_of_exc_for_a_frozen_density_matrix(oracle):
@@ -105,15 +140,39 @@ def test_cuda_gradient_against_pyscf_values_quoted_by_the_reference():
     from occ_b200 import dft, grid
     Z, pos, b, P = _water_rhf()
     h = grid.MolecularGrid(b).hierarchy()
-    for m, (oz, hy, hz) in PYSCF.items():
+    for m in PYSCF:
         d = dft.DFT(m, b, h, gradient=True)
         g = d.compute_xc_gradient(0.5 * P)
-        tol = 2e-3 if m == "r2scan" else 1e-4
-        assert abs(g[0, 2] - oz) < tol and abs(g[1, 1] - hy) < tol and abs(g[1, 2] - hz) < tol, (m, g)
+        _check(m, g)
+        assert not d.have_nonlocal_correlation() and d.post_scf_nlc_correction(0.5 * P) == 0.0
+        assert np.array_equal(d.compute_nlc_gradient(0.5 * P), np.zeros((3, 3)))
         d.close()
     with pytest.raises(RuntimeError):
         d = dft.DFT("pbe", b, h)            # no gradient option
         d.gradient(P)
+
+
+@pytest.mark.gpu
+def test_cuda_wb97xv_gradient_and_nlc_energy_meet_the_reference_assertions(oracle):
+    """DFT("wb97x-v"): compute_xc_gradient adds the VV10 gradient (dft_gradients.cpp:104), post_scf_nlc_correction gives
+    the VV10 energy (dft.h:477-483); reference margins of isolated_xc_tests.cpp:340-385 and 1e-8 against the oracle"""
+    from occ_b200 import dft, grid
+    Z, pos, b, P = _water_rhf()
+    d = dft.DFT("wb97x-v", b, grid.MolecularGrid(b).hierarchy(), gradient=True)
+    assert d.have_nonlocal_correlation()
+    rs = d.range_separated_parameters()
+    assert abs(rs["omega"] - 0.3) < 1e-15 and abs(rs["alpha"] - 1.0) < 1e-15 and abs(rs["beta"] + 0.833) < 1e-15
+    g = d.compute_xc_gradient(0.5 * P)
+    _check_wb97xv(g)
+    e = d.post_scf_nlc_correction(0.5 * P)
+    ob = oracle.Basis(b.as_arrays())
+    pts, w, _ = oracle.molecular_grid(Z, pos, ob)
+    spts, sw, perm, leaves = oracle.hierarchy(pts, w)
+    p2, w2, info = oracle.molecular_grid(Z, pos, ob, oracle.default_grid_settings(**NLC_GRID))
+    r = oracle.vv10_gradient(ob, p2, w2, oracle.cosx_atom_grids(p2, info), P)
+    go = oracle.xc_gradient(ob, spts, sw, leaves, oracle.METHODS["wb97x-v"], 1, P, 3) + r["gradient"]
+    assert np.abs(g - go).max() < 1e-8 and abs(e - r["energy"]) < 1e-10
+    d.close()
 
 
 @pytest.mark.gpu
