@@ -127,6 +127,8 @@ class DFT:
         self.method = method
         self._device, self._nlc, self.nlc_energy = device, None, 0.0
         self.func_ids = np.array(get_dft_method(method), dtype=np.int32)
+        if spinorbital_kind not in (RESTRICTED, UNRESTRICTED):
+            raise RuntimeError("Not implemented: DFT for General spinorbitals")      # dft.h:426-428
         self.nspin = 2 if spinorbital_kind == UNRESTRICTED else 1
         self.nbf = basis.nbf
         self._basis_arrays = BasisArrays(basis.as_arrays())

@@ -5,6 +5,15 @@ import pytest
 from occ_b200 import aobasis, dft, molecules
 
 
+def test_general_spinorbitals_are_rejected_like_the_reference():
+    """compute_vxc: "Not implemented: DFT for General spinorbitals" (include/occ/dft/dft.h:426-428) — raised before any
+    device call"""
+    Z, pos = molecules.water()
+    b = aobasis.AOBasis.load(Z, pos, "def2-svp")
+    with pytest.raises(RuntimeError, match="General spinorbitals"):
+        dft.DFT("pbe", b, dft.GridHierarchy(np.zeros((0, 3)), np.zeros(0), np.zeros(0, dtype=dft.LEAF_DTYPE)), "general")
+
+
 def test_method_table_mirrors_the_reference():
     """src/dft/dft_method.cpp:14-37"""
     assert dft.get_dft_method("b3lyp") == [402]
