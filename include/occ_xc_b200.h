@@ -99,7 +99,8 @@ typedef struct {
                             dft.h:375-380).  Costs one extra atomic per accumulated value. */
   int nvtx;              /* 1 = NVTX ranges around the build and its phases (nsys / ncu --nvtx) */
   int lanes;             /* 2 = batches alternate between two stream lanes (experimental; default 1) */
-  unsigned debug;        /* developer timing switches: 1 = no Vxc scatter, 2 = no density epilogue */
+  unsigned debug;        /* developer timing switches: 1 = no Vxc scatter, 2 = no density epilogue, 8 = no A refills, 16 = B block
+                          * without slab loads, 32 = no L2 prefetch of a later item's B-block columns; bits 8.. = prefetch distance */
   double density_scale;  /* the D handed to the HOST entry points is multiplied by this on the device before use;
                             0 = 1.0.  2.0 lets the caller pass mo.D itself instead of D2 = 2 * mo.D (dft.h:205) */
   double orbital_scale;  /* same for the C of occ_xc_build_mo; 0 = 1.0.  sqrt(2) lets a restricted caller pass mo.Cocc */

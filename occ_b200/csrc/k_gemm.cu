@@ -69,6 +69,9 @@ __global__ void __launch_bounds__(TILE_P) k_gbuild(BuildParams P, const DensItem
 #define XC_RS 2
 #endif
 constexpr int RK = XC_RK, RS = XC_RS;
+#ifndef XC_BPF_AHEAD
+#define XC_BPF_AHEAD 64
+#endif
 #ifndef XC_SWZ
 #define XC_SWZ 0
 #endif
@@ -178,6 +181,29 @@ __global__ void __launch_bounds__(NTHREADS, 2) XC_SYM(k_vxc_resident)(BuildParam
     }
   }
   __syncthreads(); // the only CTA-wide barrier: B block and column map complete
+
+#ifndef XC_NO_BPREFETCH
+  // The B-block build is the one phase of this kernel that waits on HBM with the tensor pipe idle.  While this CTA
+  // multiplies, pull the slab columns of the item that starts XC_BPF_AHEAD launches later into L2, so that CTA's build
+  // pays L2 latency: 4 slabs x 64 (32) columns x 8 lines of 128 bytes.
+  const int ahead = (P.debug >> 8) ? static_cast<int>(P.debug >> 8) : XC_BPF_AHEAD;
+  if (blockIdx.x + ahead < gridDim.x && !(P.debug & 32)) {
+    const VxcItem nx = items[blockIdx.x + ahead];
+    const TileDesc tn = P.tiles[nx.tile];
+    const int ncn = nx.spin == 2 ? GN / 2 : GN;
+    const int c0n = nx.jb * ncn;
+    const int cols = min(ncn, max(0, tn.nb - c0n));
+    const size_t slabn = static_cast<size_t>(tn.nbp) * TILE_P;
+    const double *bn = P.scratch + tn.scr_off + static_cast<size_t>(c0n) * TILE_P;
+    const int nslab = nx.acomp == 0 ? (P.deriv >= 1 ? 4 : 1) : 1;
+    const double *b0 = nx.acomp == 0 ? bn : bn + static_cast<size_t>(nx.acomp) * slabn;
+    const int nlines = nslab * cols * 8;
+    for (int L = tid; L < nlines; L += NTHREADS) {
+      const int sl = L / (cols * 8), r = L - sl * (cols * 8);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(b0 + sl * slabn + static_cast<size_t>(r) * 16));
+    }
+  }
+#endif
 
   double acc[2][8][2];
   int ib = 0, kc = 0;
