@@ -10,12 +10,16 @@ b = aobasis.AOBasis.load(Z, pos, "def2-svp")
 h = grid.MolecularGrid(b).hierarchy()
 leaves = h.leaves[::8]                      # a thin sample keeps the sanitizer run short
 hs = dft.GridHierarchy(h.sorted_points, h.sorted_weights, leaves)
-for method, nspin in (("b3lyp", 1), ("tpss", 2), ("svwn", 1), ("b97", 2), ("b3pw91", 1), ("bp86", 2)):
+for method, nspin in (("b3lyp", 1), ("tpss", 2), ("svwn", 1), ("b97", 2), ("b3pw91", 1), ("bp86", 2),
+                      ("wb97x-v", 1), ("b3p86", 2), ("b86bpbe", 1)):
     D2 = molecules.synthetic_density(b, nspin)
     d = dft.DFT(method, b, hs, dft.UNRESTRICTED if nspin == 2 else dft.RESTRICTED, gradient=True)
     K = d.build(D2)
     g = d.gradient(D2)
     print(method, nspin, float(np.abs(K).max()), float(np.abs(g).max()))
+    if d.have_nonlocal_correlation():             # wB97X-V: VV10 energy and gradient through the DFT mirror
+        d.set_nlc_grid(grid.GridSettings(50, 26, 1e-5, False, True))
+        print("nlc", d.post_scf_nlc_correction(0.5 * D2), float(np.abs(d.compute_xc_gradient(0.5 * D2)).max()))
     d.close()
 for devices in (None, [0, 0]):                      # single handle, then two shards of one process (peer-memory paths)
     f = nlc.NonLocalCorrelationFunctional()
