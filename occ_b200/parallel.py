@@ -156,6 +156,21 @@ class DistributedDFT:
                 allreduce_partial(self.d_out, self.group)
         return self.d_out
 
+    def capture_device_build(self, mo: bool = False, d2_resident: bool = True) -> "torch.cuda.CUDAGraph":
+        """CUDA graph of one device-resident build (one GPU).  occ_xc_build(_mo)_device is a fixed sequence of kernel
+        launches and memsets on the caller's stream, with no host synchronisation and every buffer owned by the handle or
+        by this object, so it can be captured once and replayed: for small systems (water: 9 launches of a few
+        microseconds each) the replay removes the launch gaps.  `with torch.cuda.stream(self.stream): g.replay()`
+        leaves the packed result in self.d_out, computed from whatever self.d_D / self.d_C hold at replay time."""
+        if self.world > 1:
+            raise RuntimeError("capture_device_build: one GPU only (the all-reduce is not captured)")
+        self._launch(self.d_out, mo, d2_resident)        # warm-up outside the capture (shared-memory opt-ins, lazy module loads)
+        self.stream.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self.stream, capture_error_mode="thread_local"):
+            self._launch(self.d_out, mo, d2_resident)
+        return g
+
     def build(self, D2_host: torch.Tensor | None, K_host: torch.Tensor | None, C_host: torch.Tensor | None = None,
               mo: bool = False):
         """Host-to-host build as the reference's single-process SCF driver would see it: rank 0 owns the host

@@ -185,3 +185,39 @@ def test_b97_b3pw91_bp86_builds(case, oracle, method, exx, nspin):
     assert abs(ref["exc"]) > 1.0
     assert d.exact_exchange_factor() == pytest.approx(exx) if hasattr(d, "exact_exchange_factor") else True
     d.close()
+
+
+def test_device_entry_is_cuda_graph_capturable(case):
+    """occ_xc_build_device / _build_mo_device enqueue a fixed launch sequence on the caller's stream without host
+    synchronisation: a CUDA graph captured once replays the build, and follows new contents of the same D / C buffers"""
+    import torch
+    from occ_b200 import parallel
+    c = case("water", "def2-svp")
+    b = c["basis"]
+    Cs = molecules.synthetic_orbitals(b, 1)
+    nocc = Cs[0].shape[1]
+    ddft = parallel.DistributedDFT("b3lyp", b, _hier(c), dft.RESTRICTED, device=0, nocc=[nocc])
+    n = b.nbf * b.nbf
+    for mo in (False, True):
+        D2 = molecules.synthetic_density(b, 1)
+        ddft.d_D.copy_(torch.from_numpy(np.ascontiguousarray(D2.ravel(order="F"))))
+        ddft.d_C.copy_(torch.from_numpy(np.ascontiguousarray(Cs[0].ravel(order="F"))))
+        torch.cuda.synchronize()
+        g = ddft.capture_device_build(mo)
+        direct = ddft.build_device(mo).clone()
+        ddft.stream.synchronize()
+        ddft.d_out.zero_()
+        with torch.cuda.stream(ddft.stream):
+            g.replay()
+        ddft.stream.synchronize()
+        assert float((ddft.d_out[:n] - direct[:n]).abs().max()) < 1e-12 and float(direct[:n].abs().max()) > 0.1
+        assert float((ddft.d_out[n:n + 3] - direct[n:n + 3]).abs().max()) < 1e-12
+        if not mo:                      # same graph, new density in the same buffer: K and N_el scale with it
+            ddft.d_D.mul_(0.5)
+            with torch.cuda.stream(ddft.stream):
+                g.replay()
+            ddft.stream.synchronize()
+            assert abs(float(ddft.d_out[n + 1]) - 0.5 * float(direct[n + 1])) < 1e-10
+            ddft.d_D.mul_(2.0)
+        del g
+    ddft.close()
