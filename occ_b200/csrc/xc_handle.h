@@ -42,6 +42,7 @@ struct occ_xc_handle {
   int lanes = 1;
   bool profiling = false;
   bool deterministic = false, nvtx = false;
+  bool vxc_ws = false; // Vxc contraction through the warp-specialised persistent kernel (k_vxc_ws.cu)
   double density_scale = 1.0, orbital_scale = 1.0;
   double phase_ms[OCC_XC_NPHASES] = {0, 0, 0, 0, 0, 0, 0};
   size_t launches = 0;

@@ -792,6 +792,8 @@ int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xy
     h->lanes = (opt && opt->lanes == 2 && h->batches.size() >= 2) ? 2 : 1;
     if (h->lanes == 2) rc |= dev_alloc(h, &h->scratch2, max_scratch);
     h->deterministic = opt && opt->deterministic == 1;
+    // experiment switch: restricted GGA builds (every Vxc item is a plain (tile, 64 columns) item) through k_vxc_ws
+    h->vxc_ws = std::getenv("OCC_XC_VXC_WS") != nullptr && nspin == 1 && deriv == 1 && !h->deterministic;
     h->nvtx = opt && opt->nvtx == 1;
     h->density_scale = (opt && opt->density_scale != 0.0) ? opt->density_scale : 1.0;
     h->orbital_scale = (opt && opt->orbital_scale != 0.0) ? opt->orbital_scale : 1.0;
@@ -964,7 +966,8 @@ int xc_build_device_impl(occ_xc_handle *h, const double *D2_dev, const double *C
     launch_functional(P, b.leaf0, b.nleaves, st);
     PHASE_END(3);
     PHASE_BEGIN("vxc");
-    (det ? launch_vxc_resident_det : launch_vxc_resident)(P, h->d_vxc + b.vxc_off, static_cast<int>(b.nvxc), st);
+    if (h->vxc_ws) launch_vxc_ws(P, h->d_vxc + b.vxc_off, static_cast<int>(b.nvxc), st);
+    else (det ? launch_vxc_resident_det : launch_vxc_resident)(P, h->d_vxc + b.vxc_off, static_cast<int>(b.nvxc), st);
     PHASE_END(5);
   }
   st = main_st;

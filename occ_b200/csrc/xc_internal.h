@@ -145,6 +145,7 @@ void launch_collocate(const BuildParams &P, const CollocItem *items, int nitems,
 void launch_density(const BuildParams &P, const DensItem *items, int nitems, void *stream);
 void launch_functional(const BuildParams &P, int leaf0, int nleaves, void *stream);
 void launch_vxc_resident(const BuildParams &P, const VxcItem *items, int nitems, void *stream);
+void launch_vxc_ws(const BuildParams &P, const VxcItem *items, int nitems, void *stream); // k_vxc_ws.cu: restricted GGA items only
 // order-independent variants (k_*_det.cu)
 void launch_density_det(const BuildParams &P, const DensItem *items, int nitems, void *stream);
 void launch_vxc_resident_det(const BuildParams &P, const VxcItem *items, int nitems, void *stream);

@@ -533,3 +533,26 @@ def test_product_cosx_grid_producers_match_oracle(oracle, which):
     assert [c[0] for c in counts] == info["atom_npts"] and [c[1] for c in counts] == info["atom_nradial"]
     assert np.array_equal(pts, opts)
     assert np.abs(w - ow).max() < 1e-13 * np.abs(ow).max()
+
+
+def test_warp_specialised_vxc_kernel_matches_the_default_kernel(case, monkeypatch):
+    """OCC_XC_VXC_WS=1 routes restricted GGA builds through k_vxc_ws (persistent CTA, mbarrier-fed consumer warps, B block
+    of the next item built by dedicated warps; csrc/k_vxc_ws.cu).  Experimental (slower than k_vxc_resident, see
+    profiles/r02_experiments.md) but kept bit-for-bit honest: same K up to the order of the atomics"""
+    c = case("benzene", "def2-tzvp", True)
+    b = c["basis"]
+    D2 = molecules.synthetic_density(b, 1)
+    h = dft.GridHierarchy(c["spts"], c["sw"], c["leaves"])
+    monkeypatch.delenv("OCC_XC_VXC_WS", raising=False)
+    d = dft.DFT("pbe", b, h)
+    K0 = d.build(D2)
+    e0 = d.exchange_correlation_energy()
+    d.close()
+    monkeypatch.setenv("OCC_XC_VXC_WS", "1")
+    d = dft.DFT("pbe", b, h)
+    K1 = d.build(D2)
+    assert abs(d.exchange_correlation_energy() - e0) < 1e-12 and np.abs(K1 - K0).max() < 1e-12 and np.abs(K0).max() > 0.1
+    d.close()
+    d = dft.DFT("b3lyp", b, h, dft.UNRESTRICTED)          # not a restricted GGA build: the switch is ignored
+    d.build(molecules.synthetic_density(b, 2))
+    d.close()
