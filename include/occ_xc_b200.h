@@ -121,7 +121,10 @@ typedef struct occ_xc_handle occ_xc_handle;
  *   density_threshold / screening_threshold   DFT::m_density_threshold / m_xc_screening_threshold (1e-10 both);
  *                 screening_threshold <= 0 — or the reference's environment variable OCC_XC_NO_SCREEN being set (dft.h:274-275) —
  *                 keeps every shell in every leaf
- * Everything is copied; no pointer is retained. */
+ * Everything is copied; no pointer is retained.
+ * Developer switches read here from the environment (experiments, not part of the contract): OCC_XC_MO_CROSSOVER (crossover
+ * between the D form and the factorised form of the density, default 2.0), OCC_XC_VXC_WS (restricted GGA builds through the
+ * warp-specialised persistent Vxc kernel csrc/k_vxc_ws.cu instead of k_vxc_resident; same results, measured slower). */
 int occ_xc_create(const occ_xc_basis_t *basis, size_t npts, const double *pts_xyz, const double *weights,
                   size_t nleaves, const occ_xc_leaf_t *leaves, const double *shell_extents, int nfunc,
                   const int *func_ids, int nspin, double density_threshold, double screening_threshold,
