@@ -117,7 +117,49 @@ class GridHierarchy:
         return len(self.leaves)
 
 
-class DFT:
+class _NonLocalCorrelationMixin:
+    """VV10 hooks of occ::dft::DFT (include/occ/dft/dft.h:44,467-495): post-SCF energy and gradient of the NLC part of
+    wB97X-V.  The host class provides func_ids, nspin, basis and _nlc_devices() (None: one handle on its own device)."""
+    _nlc = None
+    nlc_energy = 0.0
+
+    def have_nonlocal_correlation(self) -> bool:
+        return any(int(i) in NLC_FUNCTIONAL_IDS for i in self.func_ids)
+
+    def set_nlc_grid(self, settings=None, gradient: bool = True, devices=None):
+        """DFT::set_nlc_grid (src/dft/dft.cpp:119-121); default {110, 50, 50, 1e-7, no first-row reduction}"""
+        from .nlc import NonLocalCorrelationFunctional
+        if self.nspin != 1:
+            raise RuntimeError("Only restricted NLC functional implemented right now")   # nonlocal_correlation.cpp:370
+        if self._nlc is not None:
+            self._nlc.close()
+        self._nlc = NonLocalCorrelationFunctional()
+        devices = devices if devices is not None else self._nlc_devices()
+        self._nlc.set_integration_grid(self.basis, settings, device=getattr(self, "_device", -1), gradient=gradient,
+                                       devices=devices)
+        return self._nlc
+
+    def post_scf_nlc_correction(self, D: np.ndarray) -> float:
+        """DFT::post_scf_nlc_correction(mo): the VV10 energy of D = mo.D, 0 for a functional without an NLC part"""
+        if self.have_nonlocal_correlation():
+            nlc = self._nlc or self.set_nlc_grid()
+            self.nlc_energy = nlc(D)[0]
+        return self.nlc_energy
+
+    def compute_nlc_gradient(self, D: np.ndarray) -> np.ndarray:
+        """DFT::compute_nlc_gradient(mo): zeros without an NLC part, else NonLocalCorrelationFunctional::compute_gradient"""
+        if not self.have_nonlocal_correlation():
+            return np.zeros((len(self.basis.atomic_numbers), 3))
+        nlc = self._nlc or self.set_nlc_grid()
+        return nlc.compute_gradient(D)
+
+    def _close_nlc(self):
+        if self._nlc is not None:
+            self._nlc.close()
+            self._nlc = None
+
+
+class DFT(_NonLocalCorrelationMixin):
     def __init__(self, method: str, basis: AOBasis, grid: GridHierarchy, spinorbital_kind: str = RESTRICTED,
                  device: int = -1, rank: int = 0, world_size: int = 1, batch_bytes: int = 0,
                  density_threshold: float = 1e-10, xc_screening_threshold: float = 1e-10, shell_extents=None,
@@ -125,7 +167,7 @@ class DFT:
                  nvtx: bool = False, density_scale: float = 0.0, orbital_scale: float = 0.0):
         self.basis = basis
         self.method = method
-        self._device, self._nlc, self.nlc_energy = device, None, 0.0
+        self._device = device
         self.func_ids = np.array(get_dft_method(method), dtype=np.int32)
         if spinorbital_kind not in (RESTRICTED, UNRESTRICTED):
             raise RuntimeError("Not implemented: DFT for General spinorbitals")      # dft.h:426-428
@@ -256,34 +298,8 @@ class DFT:
             g = g + self.compute_nlc_gradient(D)
         return g
 
-    # --- VV10 (include/occ/dft/dft.h:44,467-495): post-SCF energy and gradient of the NLC part of wB97X-V ----------------
-    def have_nonlocal_correlation(self) -> bool:
-        return any(int(i) in NLC_FUNCTIONAL_IDS for i in self.func_ids)
-
-    def set_nlc_grid(self, settings=None, gradient: bool = True, devices=None):
-        """DFT::set_nlc_grid (src/dft/dft.cpp:119-121); default {110, 50, 50, 1e-7, no first-row reduction}"""
-        from .nlc import NonLocalCorrelationFunctional
-        if self.nspin != 1:
-            raise RuntimeError("Only restricted NLC functional implemented right now")   # nonlocal_correlation.cpp:370
-        if getattr(self, "_nlc", None) is not None:
-            self._nlc.close()
-        self._nlc = NonLocalCorrelationFunctional()
-        self._nlc.set_integration_grid(self.basis, settings, device=self._device, gradient=gradient, devices=devices)
-        return self._nlc
-
-    def post_scf_nlc_correction(self, D: np.ndarray) -> float:
-        """DFT::post_scf_nlc_correction(mo): the VV10 energy of D = mo.D, 0 for a functional without an NLC part"""
-        if self.have_nonlocal_correlation():
-            nlc = getattr(self, "_nlc", None) or self.set_nlc_grid()
-            self.nlc_energy = nlc(D)[0]
-        return self.nlc_energy
-
-    def compute_nlc_gradient(self, D: np.ndarray) -> np.ndarray:
-        """DFT::compute_nlc_gradient(mo): zeros without an NLC part, else NonLocalCorrelationFunctional::compute_gradient"""
-        if not self.have_nonlocal_correlation():
-            return np.zeros((len(self.basis.atomic_numbers), 3))
-        nlc = getattr(self, "_nlc", None) or self.set_nlc_grid()
-        return nlc.compute_gradient(D)
+    def _nlc_devices(self):
+        return None
 
     def gradient(self, D2: np.ndarray) -> np.ndarray:
         n = self.nspin * self.nbf
@@ -323,9 +339,7 @@ class DFT:
         return [o[:count * nb.value].reshape(nb.value, count).T for o in outs]
 
     def close(self):
-        if getattr(self, "_nlc", None) is not None:
-            self._nlc.close()
-            self._nlc = None
+        self._close_nlc()
         if getattr(self, "_h", None) is not None and self._h.value:
             lib().occ_xc_destroy(self._h)
             self._h = C.c_void_p()
@@ -337,7 +351,7 @@ class DFT:
             pass
 
 
-class MultiGPUDFT:
+class MultiGPUDFT(_NonLocalCorrelationMixin):
     """occ_xc_multi_*: the same build on several GPUs driven from THIS process (what the reference's single-process
     SCF needs, include/occ/qm/scf_impl.h:539): one leaf shard per device, inputs sliced over the PCIe links and
     gathered over NVLink, K reduce-scattered through peer memory.  Same constructor arguments as DFT plus `devices`
@@ -420,6 +434,17 @@ class MultiGPUDFT:
         check(lib().occ_xc_multi_gradient(self._m, ptr(D2), ptr(packed) if packed is not None else None, ptr(g)))
         return g
 
+    def compute_xc_gradient(self, D: np.ndarray) -> np.ndarray:
+        """DFT::compute_xc_gradient(mo) on the shards (src/dft/dft_gradients.cpp:68-109), D = mo.D; the VV10 gradient of a
+        functional with an NLC part is added (:104), computed on the same devices"""
+        g = self.gradient(np.asfortranarray(2.0 * np.asarray(D, dtype=np.float64)))
+        if self.have_nonlocal_correlation():
+            g = g + self.compute_nlc_gradient(D)
+        return g
+
+    def _nlc_devices(self):
+        return self.devices
+
     def build_raw(self, d2_ptr: int, c_ptr: int, k_ptr: int):
         """occ_xc_multi_build on raw host pointers (pinned buffers owned by the caller; 0 = NULL)"""
         exc, na, nb = C.c_double(), C.c_double(), C.c_double()
@@ -428,6 +453,7 @@ class MultiGPUDFT:
         return exc.value, na.value, nb.value
 
     def close(self):
+        self._close_nlc()
         if getattr(self, "_m", None) is not None and self._m.value:
             lib().occ_xc_multi_destroy(self._m)
             self._m = C.c_void_p()

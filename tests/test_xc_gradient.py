@@ -173,6 +173,11 @@ def test_cuda_wb97xv_gradient_and_nlc_energy_meet_the_reference_assertions(oracl
     go = oracle.xc_gradient(ob, spts, sw, leaves, oracle.METHODS["wb97x-v"], 1, P, 3) + r["gradient"]
     assert np.abs(g - go).max() < 1e-8 and abs(e - r["energy"]) < 1e-10
     d.close()
+    # the same through two shards of one process (occ_xc_multi_gradient + occ_xc_multi_vv10_gradient)
+    m = dft.MultiGPUDFT("wb97x-v", b, grid.MolecularGrid(b).hierarchy(), devices=[0, 0], gradient=True)
+    gm = m.compute_xc_gradient(0.5 * P)
+    assert np.abs(gm - go).max() < 1e-8 and abs(m.post_scf_nlc_correction(0.5 * P) - r["energy"]) < 1e-10
+    m.close()
 
 
 @pytest.mark.gpu
