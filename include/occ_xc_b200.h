@@ -185,7 +185,8 @@ int occ_xc_density_on_grid(occ_xc_handle *h, const double *D2, double *rho);
 /* SURVEY 8(f) rank 4 — post-SCF VV10 non-local correlation, NonLocalCorrelationFunctional::vv10(basis, mo)
  * (src/dft/nonlocal_correlation.cpp:38-118 vv10_kernel, :367-420 vv10; called from DFT::post_scf_nlc_correction,
  * include/occ/dft/dft.h:477-483).  The handle is created over the NLC grid (the reference's default NLC GridSettings
- * are {110, 50, 50, 1e-7, no first-row reduction}, nonlocal_correlation.h:38-41) with nspin = 1, a GGA functional list
+ * are written {110, 50, 50, 1e-7, false}, nonlocal_correlation.h:37-40 — max / min angular 110 / 50, LMG precision 1e-7;
+ * the fifth initialiser lands on int_acc, so H / He keep the first-row reduction) with nspin = 1, a GGA functional list
  * (only rho / grad rho are used), world_size 1, and screening_threshold <= 0 to reproduce the reference's dense
  * evaluate_basis (a positive threshold screens shells per leaf like the XC build: a ~1e-10 change).
  *   D2          nbf x nbf column-major, doubled (2 * mo.D)

@@ -127,7 +127,7 @@ class _NonLocalCorrelationMixin:
         return any(int(i) in NLC_FUNCTIONAL_IDS for i in self.func_ids)
 
     def set_nlc_grid(self, settings=None, gradient: bool = True, devices=None):
-        """DFT::set_nlc_grid (src/dft/dft.cpp:119-121); default {110, 50, 50, 1e-7, no first-row reduction}"""
+        """DFT::set_nlc_grid (src/dft/dft.cpp:119-121); default as NonLocalCorrelationFunctional.set_integration_grid (110 / 50 angular, 1e-7, H / He reduced)"""
         from .nlc import NonLocalCorrelationFunctional
         if self.nspin != 1:
             raise RuntimeError("Only restricted NLC functional implemented right now")   # nonlocal_correlation.cpp:370

@@ -3,7 +3,7 @@ src/dft/nonlocal_correlation.cpp): the post-SCF VV10 correction, SURVEY.md 8(f) 
 
     nlc = NonLocalCorrelationFunctional()
     nlc.set_parameters(vv10_b=6.0, vv10_C=0.01)
-    nlc.set_integration_grid(basis)              # default NLC grid {110, 50, 50, 1e-7, no first-row reduction}
+    nlc.set_integration_grid(basis)              # default NLC grid: 110 / 50 angular, LMG 1e-7, H / He one Lebedev level lower
     energy, Vxc = nlc(D)                         # D = mo.D (restricted); operator()(basis, mo) of the reference
 
     g = nlc.compute_gradient(D)                  # GradientResult::gradient (natoms, 3): vv10_gradient of the reference
@@ -38,7 +38,10 @@ class NonLocalCorrelationFunctional:
         """set_integration_grid (nonlocal_correlation.cpp:17-31).  screening_threshold 0 keeps every shell at every
         point like the reference's dense evaluate_basis; 1e-10 screens per Morton leaf like the XC build."""
         self.close()
-        s = settings or GridSettings(110, 50, 1e-7, False, True)
+        # nonlocal_correlation.h:37-40 passes {110, 50, 50, 1e-7, false}; the struct's fifth member is int_acc
+        # (grid_settings.h:81-90), so reduced_first_row_element_grid keeps its default TRUE in the reference — H and He get 86
+        # angular points.  Pinned by the reference's H2 golden (tests/dft_tests.cpp:608-683), met to 2e-11 only this way.
+        s = settings or GridSettings(110, 50, 1e-7, True, True)
         mg = MolecularGrid(basis, s)
         h, perm = mg.hierarchy(with_permutation=True)
         counts = [mg.atom_info(a)[0] for a in range(mg.natoms)]

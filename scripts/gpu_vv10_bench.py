@@ -30,7 +30,7 @@ def run(mol, bas, thr, cpu=False, devices=None):
            "gradient_energy_minus_energy": eg - e}
     if cpu:
         from oracle import oracle as O
-        mg = grid.MolecularGrid(b, grid.GridSettings(110, 50, 1e-7, False, True))
+        mg = grid.MolecularGrid(b, grid.GridSettings(110, 50, 1e-7, True, True))
         pts, w = mg.points()
         t0 = time.perf_counter(); r = O.vv10(O.Basis(b.as_arrays()), pts, w, D2); tc = time.perf_counter() - t0
         out["cpu_oracle_s"] = tc

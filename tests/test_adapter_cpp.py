@@ -137,7 +137,7 @@ def test_adapter_nonlocal_correlation_matches_oracle(oracle, tmp_path, devices):
     Z, pos = molecules.water()
     b = aobasis.AOBasis.load(Z, pos, "def2-svp")
     ob = oracle.Basis(b.as_arrays())
-    mg = grid.MolecularGrid(b, grid.GridSettings(110, 50, 1e-7, False, True))
+    mg = grid.MolecularGrid(b, grid.GridSettings(110, 50, 1e-7, True, True))
     h, perm = mg.hierarchy(with_permutation=True)
     pts, w = mg.points()
     off = np.concatenate([[0], np.cumsum([mg.atom_info(a)[0] for a in range(mg.natoms)])])

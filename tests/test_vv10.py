@@ -1,14 +1,66 @@
 """Post-SCF VV10 non-local correlation: NonLocalCorrelationFunctional::vv10
-(src/dft/nonlocal_correlation.cpp:38-118, 367-420).  The reference pins it only through a 1e-3-level wB97X-V gradient
-(tests/dft_gradient_tests.cpp:449-520), so the oracle is checked against an independent numpy transcription of the
-same lines, and the CUDA path against the oracle (Exc-like energy 1e-8 Eh, Vxc 1e-9 max-abs)."""
+(src/dft/nonlocal_correlation.cpp:38-118, 367-420).  Reference-held numbers: the VV10 ENERGY of H2 / STO-3G from an ORCA
+wavefunction (tests/dft_tests.cpp:608-683: 0.008940471, Catch::Approx default = 1.07e-7 absolute) — met to 2e-11 by the
+oracle and by the CUDA path on the default NLC grid — and the wB97X-V gradient assertions (tests/test_xc_gradient.py).
+Beyond those the oracle is checked against an independent numpy transcription of the same lines, and the CUDA path
+against the oracle (Exc-like energy 1e-8 Eh, Vxc 1e-9 max-abs)."""
 import numpy as np
 import pytest
 
 from occ_b200 import aobasis, molecules
 
 NLC_GRID = dict(max_angular_points=110, min_angular_points=50, radial_precision=1e-7,
-                reduced_first_row_element_grid=False)   # nonlocal_correlation.h:38-41 default {110, 50, 50, 1e-7, false}
+                reduced_first_row_element_grid=True)   # nonlocal_correlation.h:37-40 passes {110, 50, 50, 1e-7, false}: the fifth
+# initialiser lands on int_acc (grid_settings.h:81-90), reduced_first_row_element_grid keeps its default true
+
+
+H2_VV10_ORCA = 0.008940471          # tests/dft_tests.cpp:681
+H2_CATCH_TOL = 100.0 * float(np.finfo(np.float32).eps) * H2_VV10_ORCA   # Catch::Approx(expected): epsilon * |expected|
+
+
+def h2_orca_case():
+    """the wavefunction of tests/dft_tests.cpp:610-648 (molden written by orca_2mkl): H2 at 1.3983973391 Bohr, one
+    3-primitive s shell per atom whose coefficients multiply UNNORMALISED primitives (MoldenReader rescales them by
+    (4 alpha)^-(l/2 + 3/4) and Shell::incorporate_shell_norm normalises the contraction, moldenreader.cpp:201-224), one
+    doubly occupied MO"""
+    Z = np.array([1, 1], dtype=np.int32)
+    pos = np.array([[0.0, 0.0, 0.0], [0.0, 0.0, 1.3983973391]])
+    exps = np.array([3.42525091, 0.62391373, 0.1688554])
+    c = np.array([0.2769343610, 0.2678388518, 0.0834736696]) / (4.0 * exps) ** 0.75
+    b = aobasis.AOBasis(Z, pos, [], False, "h2-orca-molden")
+    for a in range(2):
+        b.shells.append(aobasis.Shell(0, pos[a].copy(), exps.copy(), aobasis.incorporate_shell_norm(0, exps, c), a))
+    Cocc = np.array([-0.548842275549, -0.548842275421])
+    return Z, pos, b, np.outer(Cocc, Cocc)          # mo.D = Cocc Cocc^T
+
+
+def test_oracle_meets_the_reference_h2_vv10_energy(oracle):
+    """REQUIRE(result.energy == Catch::Approx(0.008940471)) of the reference, on the NLC grid the reference really builds:
+    its default {110, 50, 50, 1e-7, false} leaves reduced_first_row_element_grid TRUE (the fifth member is int_acc), so
+    both H atoms get 86 instead of 110 angular points — with the unreduced grid the energy is 1.4e-7 off and the
+    reference's own assertion would fail"""
+    Z, pos, b, D = h2_orca_case()
+    ob = oracle.Basis(b.as_arrays())
+    pts, w, info = oracle.molecular_grid(Z, pos, ob, oracle.default_grid_settings(**NLC_GRID))
+    e = oracle.vv10(ob, pts, w, np.asfortranarray(2.0 * D))["energy"]
+    assert abs(e - H2_VV10_ORCA) < H2_CATCH_TOL and abs(e - H2_VV10_ORCA) < 1e-9, e - H2_VV10_ORCA
+    unreduced = dict(NLC_GRID, reduced_first_row_element_grid=False)
+    pts, w, info = oracle.molecular_grid(Z, pos, ob, oracle.default_grid_settings(**unreduced))
+    e2 = oracle.vv10(ob, pts, w, np.asfortranarray(2.0 * D))["energy"]
+    assert abs(e2 - H2_VV10_ORCA) > H2_CATCH_TOL
+
+
+@pytest.mark.gpu
+def test_cuda_meets_the_reference_h2_vv10_energy():
+    from occ_b200 import nlc
+    Z, pos, b, D = h2_orca_case()
+    f = nlc.NonLocalCorrelationFunctional()
+    f.set_parameters(6.0, 0.01)
+    f.set_integration_grid(b)                       # the default NLC grid
+    e, V = f(D)
+    assert abs(e - H2_VV10_ORCA) < H2_CATCH_TOL and abs(e - H2_VV10_ORCA) < 1e-9, e - H2_VV10_ORCA
+    assert V.shape == (2, 2) and abs(V[0, 1] - V[1, 0]) < 1e-14
+    f.close()
 
 
 def _numpy_vv10_kernel(rho, g, pts, w, b=6.0, C=0.01):
