@@ -255,6 +255,37 @@ def test_significant_pairs_and_screening_inputs(oracle, case):
 # the COSX grid producer: GridSettings::for_cosx (src/numint/grid_settings.cpp:10-18,71-103,176-181) and the ORCA branch
 # of generate_atom_grid (src/numint/grid_utils.cpp:296-335,559-572,588-611,693-705)
 # ---------------------------------------------------------------------------------------------------------
+def _treutler_ahlrichs(n):
+    """generate_treutler_alrichs_radial_grid (src/numint/grid_utils.cpp:559-572), points ascending"""
+    i = np.arange(1, n + 1)
+    step = np.pi / (n + 1)
+    x = np.cos(i * step)
+    t1 = (1 + x) ** 0.6 / np.log(2.0)
+    t2 = np.log((1 - x) / 2)
+    return (-t1 * t2)[::-1], (step * np.sin(i * step) * t1 * (-0.6 / (1 + x) * t2 + 1 / (1 - x)))[::-1]
+
+
+def test_treutler_ahlrichs_radial_grid_golden_and_single_atom_shell_weights(oracle):
+    """the reference's own known answer for the radial rule of the COSX grids (tests/dft_tests.cpp:279-289, 1e-5), and the
+    oracle's single-atom COSX grid: shell k carries 4 pi (w_k r_m) (x_k r_m)^2 in total (grid_utils.cpp:603-609,680)"""
+    r, w = _treutler_ahlrichs(3)
+    assert np.abs(r - [0.10934791, 1.0, 3.82014324]).max() < 1e-5
+    assert np.abs(w - [0.34905607, 1.60432893, 4.51614622]).max() < 1e-5
+    Z, pos = np.array([8], dtype=np.int32), np.zeros((1, 3))
+    b = aobasis.AOBasis.load(Z, pos, "def2-svp")
+    pts, wts, info = oracle.molecular_grid(Z, pos, oracle.Basis(b.as_arrays()), oracle.cosx_grid_settings(1))
+    n = info["atom_nradial"][0]
+    assert n == 27
+    rm = 0.60 / 0.52917721092
+    x, wr = _treutler_ahlrichs(n)
+    rad = np.linalg.norm(pts, axis=1)
+    for k in range(n):
+        sel = np.abs(rad - x[k] * rm) < 1e-9 * max(1.0, x[k] * rm)
+        assert sel.any()
+        want = 4 * np.pi * wr[k] * rm * (x[k] * rm) ** 2
+        assert abs(wts[sel].sum() - want) < 1e-8 * want, k       # the Lebedev weights sum to 1 to ~1e-9
+
+
 @pytest.mark.parametrize("level,nr_h,nr_o", [(1, 22, 27), (2, 25, 30), (3, 30, 35)])
 def test_cosx_grid_levels_follow_the_orca_rules(oracle, level, nr_h, nr_o):
     """radial counts nr = round(15 IntAcc - 40 + 5 row); the 5-region angular orders (H / He one Lebedev level lower);
