@@ -65,13 +65,15 @@ class SemiNumericalExchange:
     def __init__(self, basis: AOBasis, settings: GridSettings | None = None, atom_grids=None, device: int = -1,
                  margin: float = 1.0, collect_stats: bool = False, batch_bytes: int = 0, rank: int = 0,
                  world_size: int = 1, projector: np.ndarray | None | str = "auto", kgemm_library: bool = False):
-        """SemiNumericalExchange(basis, grid settings) (seminumerical_exchange.cpp:245-275). atom_grids, when given, is
-        (offsets[natoms+1], points (N,3), weights (N,)) — the reference's m_atom_grids."""
+        """SemiNumericalExchange(basis, grid settings = {}) (seminumerical_exchange.cpp:232-275): like the reference's
+        constructor, no settings means the default-constructed GridSettings (the 302 / 110 DFT grid); the SCF front end
+        passes GridSettings::for_cosx(level) (src/qm/hf.cpp:63-64) = cosx_grid_settings(level) here.  atom_grids, when
+        given, is (offsets[natoms+1], points (N,3), weights (N,)) — the reference's m_atom_grids."""
         L = lib()
         self.basis = basis
         self.omega = 0.0
         if atom_grids is None:
-            mg = MolecularGrid(basis, settings or sgx_grid_settings())
+            mg = MolecularGrid(basis, settings or GridSettings())
             pts, w = mg.points()
             counts = [mg.atom_info(a)[0] for a in range(mg.natoms)]
             mg.close()
@@ -256,7 +258,7 @@ class MultiGPUSemiNumericalExchange:
         self.basis = basis
         self.omega = 0.0
         if atom_grids is None:
-            mg = MolecularGrid(basis, settings or sgx_grid_settings())
+            mg = MolecularGrid(basis, settings or GridSettings())
             pts, w = mg.points()
             counts = [mg.atom_info(a)[0] for a in range(mg.natoms)]
             mg.close()
