@@ -92,7 +92,7 @@ def get_dft_method(method_string: str) -> list[int]:
     ids = []
     defs = method_definitions()
     for token in method_string.strip().lower().split():
-        m = token[1:] if token.startswith("u") and token[1:] in defs else token
+        m = token[1:] if token.startswith("u") else token      # dft_method.cpp:175-178 strips a leading 'u' unconditionally
         if m in defs:
             missing = [c for c in defs[m] if c not in FUNCTIONAL_IDS]
             if missing:
@@ -203,7 +203,14 @@ class DFT(_NonLocalCorrelationMixin):
         return max(lib().occ_xc_family(int(f)) for f in self.func_ids)
 
     def exact_exchange_factor(self) -> float:
-        return float(sum(lib().occ_xc_exact_exchange(int(f)) for f in self.func_ids))
+        """DFTMethod::exchange_factor (src/dft/dft_method.cpp:39-47): the first component with a positive factor.  The "hfx"
+        of a method definition (pbe0: 0.25) is set on the POLARIZED functional objects only (:150-152) while this walk
+        uses the unpolarized list, so it never shows up here either — pbe0 reports 0 like in the reference."""
+        for f in self.func_ids:
+            x = float(lib().occ_xc_exact_exchange(int(f)))
+            if x > 0.0:
+                return x
+        return 0.0
 
     def range_separated_parameters(self) -> dict:
         """DFT::range_separated_parameters (src/dft/dft.cpp:128-130): the component with omega != 0, if any"""

@@ -25,6 +25,7 @@ def test_method_table_mirrors_the_reference():
     assert dft.get_dft_method("gga_x_b88 gga_c_lyp") == [106, 131]
     assert dft.get_dft_method("bp86") == [106, 132] and dft.get_dft_method("b97") == [407]
     assert dft.get_dft_method("b3pw91") == [401] and dft.get_dft_method("wb97x") == [464]
+    assert dft.get_dft_method("ub3lyp") == [402] and dft.get_dft_method("upbe") == [101, 130]   # leading 'u' stripped (:175-178)
     # entries of share/methods/dft_methods.json beyond the compiled-in table
     assert dft.get_dft_method("wb97x-v") == [466] and dft.get_dft_method("b3p86") == [403]
     assert dft.get_dft_method("b86bpbe") == [105, 130] and dft.get_dft_method("b86bpbeh") == [105, 130]
