@@ -319,7 +319,7 @@ int occ_cosx_create(const occ_xc_basis_t *basis, int natoms, const size_t *atom_
               rec_all[o + COSX_PRIM_HDR + a] = pref * E[a][2] * other;     // t = 0 of (i = 1, j = 0)
               rec_all[o + COSX_PRIM_HDR + 3 + a] = pref * E[a][3] * other; // t = 1
             }
-          } else if (la + lb >= 2 && la + lb <= COSX_DENSE_MAXL) { // dense pre-combined products, loop order of prim_eval / cosx_dense_count
+          } else if (cosx_dense(la, lb)) { // dense pre-combined products, loop order of prim_eval / cosx_dense_count
             size_t k = o + COSX_PRIM_HDR;
             for (int ax = la; ax >= 0; --ax)
               for (int ay = la - ax; ay >= 0; --ay) {

@@ -32,6 +32,12 @@ constexpr int COSX_PRIM_HDR = 5;
 #ifndef COSX_DENSE_MAXL
 #define COSX_DENSE_MAXL 2
 #endif
+#ifndef COSX_DENSE_30
+#define COSX_DENSE_30 0 // the dense record also for the (3,0) class (56 products against 48 table entries): measured equal
+#endif
+__host__ __device__ constexpr bool cosx_dense(int la, int lb) {
+  return (la + lb >= 2 && la + lb <= COSX_DENSE_MAXL) || (COSX_DENSE_30 && la == 3 && lb == 0);
+}
 // number of (a, b, t, u, v) products of a class in the dense pre-combined form: sum over Cartesian components of
 // (ax + bx + 1)(ay + by + 1)(az + bz + 1); component order lx descending, then ly (kernels.h:256-290)
 __host__ __device__ constexpr int cosx_dense_count(int la, int lb) {
@@ -48,7 +54,7 @@ __host__ __device__ constexpr int cosx_dense_count(int la, int lb) {
 __host__ __device__ constexpr int cosx_stride(int la, int lb) {
   return (la == 0 && lb == 0) ? COSX_PRIM_HDR
          : (la == 1 && lb == 0) ? COSX_PRIM_HDR + 6
-         : (la + lb >= 2 && la + lb <= COSX_DENSE_MAXL) ? COSX_PRIM_HDR + cosx_dense_count(la, lb)
+         : cosx_dense(la, lb) ? COSX_PRIM_HDR + cosx_dense_count(la, lb)
                                 : COSX_PRIM_HDR + 3 * (la + 1) * (lb + 1) * (la + lb + 1);
 }
 constexpr int COSX_BOYS_ORDERS = 16;

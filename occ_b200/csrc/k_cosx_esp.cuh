@@ -399,7 +399,7 @@ __device__ __forceinline__ void prim_eval(const double *__restrict__ rec, const 
       if (offdiag) Gp[a] = fma(Fq[0], V, Gp[a]);
     }
     Gq[0] += gq;
-  } else if constexpr (L >= 2 && L <= COSX_DENSE_MAXL) { // dense pre-combined coefficients, every index a compile-time constant
+  } else if constexpr (cosx_dense(LA, LB)) { // dense pre-combined coefficients, every index a compile-time constant
     double R[cx_nhermsum(L)];
     hermite_R<L>(S, x, y, z, R);
     const double *c = rec + COSX_PRIM_HDR;
