@@ -182,6 +182,33 @@ def test_polarized_potentials_by_finite_differences(oracle, func):
             assert np.allclose(d, r0["vtau"][:, k], rtol=5e-5, atol=1e-8)
 
 
+@pytest.mark.parametrize("method,nspin", [("svwn", 1), ("pbe", 1), ("pbe", 2), ("tpss", 1), ("tpss", 2), ("b3lyp", 1),
+                                          ("b3lyp", 2), ("wb97x", 1), ("wb97x", 2), ("r2scan", 1)])
+def test_vxc_matrix_is_the_derivative_of_exc_with_respect_to_the_density_matrix(oracle, case, method, nspin):
+    """dExc = sum_ij K_ij dD2_ij for a symmetric perturbation of the (doubled) density matrix, restricted and unrestricted:
+    the ASSEMBLY of the Vxc matrix (quadrature weights, the 1/2 and 2 of the gradient terms, K = Ktmp + Ktmp^T, the tau
+    term, the shell screening) is pinned against the energies, which the reference's goldens pin.  An error common to
+    the oracle and the CUDA path in that assembly would break this identity."""
+    c = case("water", "def2-svp")
+    b = c["basis"]
+    n = b.nbf
+    D2 = molecules.synthetic_density(b, nspin)
+    rng = np.random.default_rng(3)
+    dD = rng.normal(size=(nspin * n, n))
+    for s in range(nspin):
+        dD[s * n:(s + 1) * n] = 0.5 * (dD[s * n:(s + 1) * n] + dD[s * n:(s + 1) * n].T)
+    dD *= 1e-3 * np.abs(D2).max()
+    names = oracle.METHODS[method]
+
+    def build(D):
+        return oracle.xc_build(c["obasis"], c["spts"], c["sw"], c["leaves"], names, nspin, np.asfortranarray(D))
+
+    eps = 1e-3
+    fd = (build(D2 + eps * dD)["exc"] - build(D2 - eps * dD)["exc"]) / (2 * eps)
+    an = float((build(D2)["K"] * dD).sum())
+    assert abs(fd - an) < 2e-8 * abs(an), (fd, an)
+
+
 def test_b3lyp_is_its_libxc_mixture(oracle):
     rho, sigma, tau = _sample(25, 5, False)
     mix = {"lda_x": 0.08, "gga_x_b88": 0.72, "lda_c_vwn_rpa": 0.19, "gga_c_lyp": 0.81}
